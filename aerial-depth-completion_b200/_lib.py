@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI declared in include/adc_b200.h (libadc_b200.so, built by csrc/Makefile).
+
+The library is the only compute path: if it is missing this module raises at import, loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadc_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "aerial_depth_completion_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C aerial-depth-completion_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+ADC_PYR_CALLS = 11
+ADC_PYR_MODULES = 7
+ADC_WSLOTS = 4
+
+c_float_p = ctypes.c_void_p   # device pointers travel as integers
+c_ll = ctypes.c_longlong
+c_int = ctypes.c_int
+
+
+class Src(ctypes.Structure):
+    """adc_src_t"""
+    _fields_ = [("x", ctypes.c_void_p), ("c", ctypes.c_void_p), ("batch_stride", c_ll),
+                ("channels", c_int), ("H", c_int), ("W", c_int)]
+
+
+class PyramidFwd(ctypes.Structure):
+    """adc_pyramid_fwd_t"""
+    _fields_ = [("N", c_int), ("H", c_int), ("W", c_int), ("training", c_int), ("slot", c_int),
+                ("x0", ctypes.c_void_p), ("c0", ctypes.c_void_p), ("x0_batch_stride", c_ll), ("c0_batch_stride", c_ll),
+                ("weight", ctypes.c_void_p * ADC_PYR_MODULES), ("bias", ctypes.c_void_p * ADC_PYR_MODULES),
+                ("weight_out", ctypes.c_void_p), ("saved", ctypes.c_void_p), ("idx", ctypes.c_void_p),
+                ("xout", ctypes.c_void_p), ("cout", ctypes.c_void_p)]
+
+
+class PyramidBwd(ctypes.Structure):
+    """adc_pyramid_bwd_t"""
+    _fields_ = [("N", c_int), ("H", c_int), ("W", c_int), ("slot", c_int), ("need_input_grad", c_int),
+                ("need_weight_grad", c_int),
+                ("x0", ctypes.c_void_p), ("c0", ctypes.c_void_p), ("x0_batch_stride", c_ll), ("c0_batch_stride", c_ll),
+                ("weight_bwd", ctypes.c_void_p * ADC_PYR_MODULES), ("bias", ctypes.c_void_p * ADC_PYR_MODULES),
+                ("saved", ctypes.c_void_p), ("idx", ctypes.c_void_p), ("xout", ctypes.c_void_p), ("cout", ctypes.c_void_p),
+                ("g_xout", ctypes.c_void_p), ("g_cout", ctypes.c_void_p), ("scratch", ctypes.c_void_p),
+                ("gx0", ctypes.c_void_p), ("gc0", ctypes.c_void_p), ("gweight", ctypes.c_void_p), ("gbias", ctypes.c_void_p)]
+
+
+# every symbol include/adc_b200.h declares: name -> (restype, argtypes)
+_vp, _sp = ctypes.c_void_p, ctypes.POINTER(Src)
+SIGNATURES = {
+    "adc_abi_version": (c_int, []),
+    "adc_last_error": (ctypes.c_char_p, []),
+    "adc_nconv2d_fwd": (c_int, [_sp, _sp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_nconv2d_bwd_scratch_floats": (ctypes.c_size_t, [c_int] * 6),
+    "adc_nconv2d_bwd": (c_int, [_sp, _sp] + [_vp] * 14 + [c_int] * 6 + [_vp]),
+    "adc_conf_pool_fwd": (c_int, [_vp] * 5 + [c_int] * 4 + [_vp]),
+    "adc_conf_pool_bwd": (c_int, [_vp] * 7 + [c_int] * 4 + [_vp]),
+    "adc_softplus_pow": (c_int, [_vp, _vp, c_int, c_int, _vp]),
+    "adc_pyramid_weight_floats": (ctypes.c_size_t, []),
+    "adc_pyramid_saved_floats": (ctypes.c_size_t, [c_int] * 3),
+    "adc_pyramid_idx_count": (ctypes.c_size_t, [c_int] * 3),
+    "adc_pyramid_idx_layout": (c_int, [c_int] * 3 + [ctypes.POINTER(c_ll), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "adc_pyramid_fwd": (c_int, [ctypes.POINTER(PyramidFwd), _vp]),
+    "adc_pyramid_bwd_scratch_floats": (ctypes.c_size_t, [c_int] * 3),
+    "adc_pyramid_bwd": (c_int, [ctypes.POINTER(PyramidBwd), _vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)      # AttributeError here = the library does not export what the header declares
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc, what):
+    """Convert a non-zero C-ABI status into the RuntimeError the reference's callers expect."""
+    if rc != 0:
+        msg = lib.adc_last_error()
+        raise RuntimeError("%s failed (status %d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,139 @@
+/*
+ * adc_b200.h -- C ABI of the B200-native (sm_100a) hot path of aerial-depth-completion.
+ *
+ * Plain pointers and sizes only; no torch types.  All tensor pointers are DEVICE pointers to fp32
+ * NCHW data (channel planes contiguous: element (n,ch,h,w) lives at n*batch_stride + ch*H*W + h*W + w;
+ * batch_stride is C*H*W unless stated), indices are int64.  Every call only ENQUEUES work on `stream`
+ * (a cudaStream_t) and never synchronises, so calls are CUDA-graph capturable.
+ *
+ * Return value: 0 on success; a positive cudaError_t value if the CUDA runtime failed; a negative
+ * ADC_E_* for argument errors.  adc_last_error() returns a thread-local message for the last failure.
+ * There is no CPU fallback: without a CUDA device the calls fail with the CUDA error.
+ *
+ * Each entry point cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef ADC_B200_H
+#define ADC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* adc_stream_t; /* cudaStream_t */
+
+#define ADC_E_BADARG   (-1) /* null pointer / non-positive size                                   */
+#define ADC_E_UNSUPP   (-2) /* (Ci,Co,k) or layer shape outside the instantiated set              */
+#define ADC_E_ALIGN    (-3) /* pointer not 4-byte aligned                                         */
+
+#define ADC_PYR_CALLS   11  /* NConv2d calls in one CNN.forward (model_zoo/nconv_sd.py:38-97)     */
+#define ADC_PYR_MODULES 7   /* nconv1..nconv7 (model_zoo/nconv_sd.py:21-32)                       */
+#define ADC_WSLOTS      4   /* independent constant-memory weight slots (one per CNN instance)    */
+
+int adc_abi_version(void);
+const char* adc_last_error(void);
+
+/* ---- a source of input channels for one NConv2d call ------------------------------------------
+ * `channels` planes of data `x` and confidence `c` of size H x W.  If (H,W) differs from the layer's
+ * output size the source is read through ATen's nearest-neighbour index map, i.e. it stands for
+ * F.interpolate(src, out_size, mode='nearest') followed by torch.cat -- neither tensor is ever
+ * materialised (model_zoo/nconv_sd.py:81-94). */
+typedef struct {
+    const float* x;
+    const float* c;
+    long long batch_stride; /* in floats */
+    int channels, H, W;
+} adc_src_t;
+
+/* NConv2d.forward (model_zoo/nconv.py:37-67): y = conv(x*c,w)/(conv(c,w)+1e-20)+b, cout = conv(c,w)/sum(w).
+ * stride 1, dilation 1, groups 1, padding k/2 -- the only configuration the nets use
+ * (model_zoo/nconv_sd.py:21-32).  w is [Co,Ci,k,k], b is [Co], Ci = src0.channels (+ src1.channels).
+ * src1 may be NULL.  Channel order of the virtual concatenation is src0 then src1.
+ * slot selects the constant-memory weight slot (0..ADC_WSLOTS-1); calls that may run concurrently on
+ * different streams must use different slots. */
+int adc_nconv2d_fwd(const adc_src_t* src0, const adc_src_t* src1, const float* w, const float* b,
+                    float* y, float* cout, int N, int Co, int H, int W, int k, int slot, adc_stream_t stream);
+
+/* Backward of the above as the reference's autograd graph computes it:
+ * w_fwd = the weight the forward call used (fixes s = sum(w)); w_bwd = the Parameter's contents at
+ * backward time (used by the conv data-gradients; model_zoo/nconv.py:114-117 swaps weight.data).
+ * gx0/gc0 (and gx1/gc1 for src1) receive the input gradients -- for an upsampled source they are the
+ * gradients w.r.t. the LOW-resolution tensors.  Any of them may be NULL (no input gradient needed).
+ * gw [Co,Ci,k,k] and gb [Co] are ACCUMULATED into (+=) unless NULL.  `scratch` must hold
+ * adc_nconv2d_bwd_scratch_floats() floats. */
+size_t adc_nconv2d_bwd_scratch_floats(int N, int Ci, int Co, int H, int W, int k);
+int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y, const float* cout,
+                    const float* gy, const float* gcout, const float* w_fwd, const float* w_bwd, const float* b,
+                    float* gx0, float* gc0, float* gx1, float* gc1, float* gw, float* gb, float* scratch,
+                    int N, int Co, int H, int W, int k, int slot, adc_stream_t stream);
+
+/* Confidence-argmax pooling (model_zoo/nconv_sd.py:43-49): c_ds,idx = max_pool2d(c,2,2,return_indices);
+ * x_ds = x.view(-1)[idx]; c_ds /= 4.  idx is int64 ih*W+iw per (n,ch) plane, bit-exact with ATen (ties ->
+ * first in row-major window order, NaN propagates, odd H/W floor).  Outputs are [N,C,H/2,W/2]. */
+int adc_conf_pool_fwd(const float* x, const float* c, float* x_ds, float* c_ds, long long* idx,
+                      int N, int C, int H, int W, adc_stream_t stream);
+/* Backward: gx = scatter(g_xds) (+ add_x), gc = scatter(g_cds/4) (+ add_c).  add_* may be NULL; they are the
+ * gradients arriving over the skip connection (same [N,C,H,W] shape) so the sum needs no extra pass. */
+int adc_conf_pool_bwd(const float* g_xds, const float* g_cds, const long long* idx, const float* add_x,
+                      const float* add_c, float* gx, float* gc, int N, int C, int H, int W, adc_stream_t stream);
+
+/* softplus^n(w, beta=10, threshold=20) element-wise (EnforcePos, model_zoo/nconv.py:114-131). */
+int adc_softplus_pow(const float* w, float* out, int numel, int times, adc_stream_t stream);
+
+/* ---- the whole unguided pyramid (CNN.forward, model_zoo/nconv_sd.py:35-101) in one call ---------- */
+typedef struct {
+    int N, H, W;                 /* level-0 size; levels are floor-halved three times                */
+    int training;                /* 1: every call first applies softplus to its module's weight      */
+    int slot;                    /* constant-memory weight slot                                      */
+    const float* x0;             /* [N,1,H,W] sparse depth                                           */
+    const float* c0;             /* [N,1,H,W] input confidence                                       */
+    long long x0_batch_stride, c0_batch_stride;
+    const float* weight[ADC_PYR_MODULES]; /* nconv1..7 .weight as stored in the Parameters           */
+    const float* bias[ADC_PYR_MODULES];
+    float* weight_out;           /* training: adc_pyramid_weight_floats() floats, the weights the      *
+                                  * Parameters hold after the forward (softplus^calls), module-major  */
+    float* saved;                /* adc_pyramid_saved_floats(N,H,W) floats: activations kept for bwd  */
+    long long* idx;              /* adc_pyramid_idx_count(N,H,W) int64: the three pooling index maps  */
+    float* xout;                 /* [N,1,H,W]                                                        */
+    float* cout;                 /* [N,1,H,W]                                                        */
+} adc_pyramid_fwd_t;
+
+size_t adc_pyramid_weight_floats(void);
+size_t adc_pyramid_saved_floats(int N, int H, int W);
+size_t adc_pyramid_idx_count(int N, int H, int W);
+/* offsets (in elements) of the three index maps inside `idx`, and their [N,2,h,w] sizes */
+int adc_pyramid_idx_layout(int N, int H, int W, long long offsets[3], int hs[3], int ws[3]);
+int adc_pyramid_fwd(const adc_pyramid_fwd_t* a, adc_stream_t stream);
+
+typedef struct {
+    int N, H, W;
+    int slot;
+    int need_input_grad;         /* 0: x0/c0 need no gradient (first layer dgrad skipped)            */
+    int need_weight_grad;        /* 0: frozen net, only data gradients                               */
+    const float* x0;
+    const float* c0;
+    long long x0_batch_stride, c0_batch_stride;
+    const float* weight_bwd[ADC_PYR_MODULES]; /* Parameter contents at backward time                 */
+    const float* bias[ADC_PYR_MODULES];
+    const float* saved;          /* from the forward                                                 */
+    const long long* idx;
+    const float* xout;           /* forward outputs                                                  */
+    const float* cout;
+    const float* g_xout;         /* [N,1,H,W] incoming gradients                                     */
+    const float* g_cout;
+    float* scratch;              /* adc_pyramid_bwd_scratch_floats(N,H,W) floats                      */
+    float* gx0;                  /* [N,1,H,W] or NULL                                                */
+    float* gc0;
+    float* gweight;              /* adc_pyramid_weight_floats() floats, module-major, OVERWRITTEN     */
+    float* gbias;                /* 13 floats (2,2,2,2,2,2,1), OVERWRITTEN                            */
+} adc_pyramid_bwd_t;
+
+size_t adc_pyramid_bwd_scratch_floats(int N, int H, int W);
+int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADC_B200_H */

@@ -1,0 +1,89 @@
+"""CPU suite: the C-ABI library loads and exports what include/adc_b200.h declares, host-side size/layout logic,
+drop-in surface (state_dict keys, seeded init) and loud failure without CUDA.  No kernel is launched here."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import reference_shim
+from golden_util import gold
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not reference_shim.have_reference(), reason="/root/reference not present")
+
+
+def test_library_exports_every_declared_symbol():
+    from aerial_depth_completion_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "adc_b200.h")).read()
+    declared = set(re.findall(r"\b(adc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), "libadc_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree: %s" % (declared ^ set(_lib.SIGNATURES))
+    assert _lib.lib.adc_abi_version() == 1
+
+
+def test_host_side_layout_functions():
+    from aerial_depth_completion_b200._lib import lib
+    n, h, w = 2, 228, 304
+    off = (ctypes.c_longlong * 3)()
+    hs = (ctypes.c_int * 3)()
+    ws = (ctypes.c_int * 3)()
+    assert lib.adc_pyramid_idx_layout(n, h, w, off, hs, ws) == 0
+    assert list(hs) == [114, 57, 28] and list(ws) == [152, 76, 38]            # floor pooling
+    assert list(off) == [0, 2 * n * 114 * 152, 2 * n * (114 * 152 + 57 * 76)]
+    assert lib.adc_pyramid_idx_count(n, h, w) == 2 * n * (114 * 152 + 57 * 76 + 28 * 38)
+    assert lib.adc_pyramid_weight_floats() == 468                              # 481 params = 468 weights + 13 biases
+    px = [n * 228 * 304, n * 114 * 152, n * 57 * 76, n * 28 * 38]
+    assert lib.adc_pyramid_saved_floats(n, h, w) == 11 * 128 + 4 * (4 * px[0] + 4 * px[1] + 3 * px[2] + 2 * px[3])
+    assert lib.adc_pyramid_bwd_scratch_floats(n, h, w) > 0
+    # argument errors come back as negative status + message, not a crash
+    assert lib.adc_pyramid_idx_layout(0, h, w, off, hs, ws) == -1
+    assert b"bad argument" in lib.adc_last_error()
+
+
+def test_weight_count_matches_reference_pyramid():
+    from aerial_depth_completion_b200.model_zoo.nconv_sd import CNN
+    m = CNN()
+    assert sum(p.numel() for p in m.parameters()) == 481
+    assert sum(p.numel() for n_, p in m.named_parameters() if n_.endswith("weight")) == 468
+    keys = list(m.state_dict().keys())
+    assert keys == ["nconv%d.%s" % (i, s) for i in range(1, 8) for s in ("weight", "bias")]
+
+
+def test_cpu_tensors_raise_no_fallback():
+    from aerial_depth_completion_b200.model_zoo.nconv import NConv2d
+    from aerial_depth_completion_b200.model_zoo.nconv_sd import CNN
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CNN()(torch.rand(1, 1, 32, 32), torch.rand(1, 1, 32, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        NConv2d(2, 2, (5, 5), padding=2).eval()(torch.rand(1, 2, 16, 16), torch.rand(1, 2, 16, 16))
+    with pytest.raises(NotImplementedError):
+        NConv2d(2, 2, (5, 5), padding=0).eval()(torch.rand(1, 2, 16, 16), torch.rand(1, 2, 16, 16))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "aerial-depth-completion_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+@needs_ref
+def test_seeded_construction_equals_reference():
+    R = reference_shim.load()
+    from aerial_depth_completion_b200.model_zoo.nconv_sd import CNN
+    torch.manual_seed(0)
+    mine = CNN()
+    torch.manual_seed(0)
+    ref = R.nconv_sd.CNN()
+    a, b = mine.state_dict(), ref.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
