@@ -55,8 +55,9 @@ _vp, _sp = ctypes.c_void_p, ctypes.POINTER(Src)
 SIGNATURES = {
     "adc_abi_version": (c_int, []),
     "adc_last_error": (ctypes.c_char_p, []),
-    "adc_nconv2d_fwd": (c_int, [_sp, _sp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
-    "adc_nconv2d_bwd_scratch_floats": (ctypes.c_size_t, [c_int] * 6),
+    "adc_nconv2d_fwd_scratch_floats": (ctypes.c_size_t, [_sp, _sp] + [c_int] * 4),
+    "adc_nconv2d_fwd": (c_int, [_sp, _sp, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_nconv2d_bwd_scratch_floats": (ctypes.c_size_t, [_sp, _sp] + [c_int] * 4),
     "adc_nconv2d_bwd": (c_int, [_sp, _sp] + [_vp] * 14 + [c_int] * 6 + [_vp]),
     "adc_conf_pool_fwd": (c_int, [_vp] * 5 + [c_int] * 4 + [_vp]),
     "adc_conf_pool_bwd": (c_int, [_vp] * 7 + [c_int] * 4 + [_vp]),

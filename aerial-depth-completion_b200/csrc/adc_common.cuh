@@ -1,4 +1,10 @@
 // Shared device/host helpers for the sm_100a kernels of the NConv depth-completion hot path.
+//
+// Internal data layout ("pair tensors"): inside the pyramid every activation is stored as float2 {x, c}
+// (data, confidence) per pixel, [N, C, H, W] of float2, and every gradient as float2 {GN, GD} (or raw {gx, gc}).
+// A pair is exactly one operand of the packed sm_100 FFMA2 (fma.rn.f32x2): {Nm, D} += {x*c, c} * w, so the two
+// convolutions of a normalized convolution (and the two correlations of its backward) ride in the two lanes of
+// one instruction, one TMA box brings both planes, and loads/stores are 8/16-byte vectors by construction.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,6 +22,8 @@ constexpr int kWMax = 100;           // max Co*Ci*k*k (2*2*25)
 
 // Constant-memory weight images: [slot][fwd/bwd][call][kWStride].  Written with stream-ordered D2D copies,
 // read through the uniform datapath (LDCU -> FFMA2 UR operands), so weights cost no vector registers.
+// forward image : w[(co*Ci+ci)*K*K + u*K + v]            (= the Parameter's own layout)
+// backward image: w[(ci*Co+co)*K*K + u'*K + v'] = W*[co][ci][K-1-u'][K-1-v']   (transposed + flipped)
 __constant__ float c_wimg[ADC_WSLOTS][2][ADC_PYR_CALLS][kWStride];  // single-TU build (adc_nconv.cu)
 
 void set_error(const char* fmt, ...);
@@ -56,29 +64,15 @@ struct NearestMap {
     }
 };
 
-// One source of input channels as the kernels see it.
-struct Src {
-    const float* x;
-    const float* c;
-    long long bs;      // batch stride (floats)
+// One source of input channels as the kernels see it: a pair tensor [N, ch, H, W] of float2 {x, c}.
+struct SrcP {
+    const float2* p;
+    long long bs;      // batch stride in float2 units
     int ch, H, W;
     NearestMap mh, mw; // dst(row/col of the layer) -> src index
-    int up;            // 1 if (H,W) differs from the layer size
+    int up;            // 1 if (H,W) differs from the layer size (nearest-upsampled on the fly)
+    int tma;           // 1 if the tile is fetched with a TMA box copy (map passed separately)
 };
-
-__host__ inline Src make_src(const adc_src_t* s, int H, int W) {
-    Src r;
-    r.x = s->x;
-    r.c = s->c;
-    r.bs = s->batch_stride;
-    r.ch = s->channels;
-    r.H = s->H;
-    r.W = s->W;
-    r.mh = NearestMap::make(s->H, H);
-    r.mw = NearestMap::make(s->W, W);
-    r.up = (s->H != H || s->W != W) ? 1 : 0;
-    return r;
-}
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 bcast(float a) { return make_float2(a, a); }
@@ -92,12 +86,41 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
+// Raw gradient (gy, gc) of a layer output whose forward values were (y, cout)  ->  {GN, GD} of that layer:
+//   GN = gy/(D+eps),  GD = -gy*(y-b)/(D+eps) + gc/s,  D = cout*s   (SURVEY.md appendix A),
+// and the per-pixel terms of the bias gradient (gb += gy) and of gs = -sum gc*cout/s.
+__device__ __forceinline__ float2 grad_xform(float gy, float gc, float y, float cout, float b, float s, float inv_s, float& gb,
+                                             float& gs) {
+    const float inv = rcp_approx(fmaf(cout, s, kEps));
+    const float gcs = gc * inv_s;
+    gb += gy;
+    gs = fmaf(-gcs, cout, gs);
+    return make_float2(gy * inv, fmaf(-gy * (y - b), inv, gcs));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
+// Sum four per-thread values over the CTA and write them as one row {a0,a1,a2,a3} (deterministic two-pass reductions).
+template <int NT>
+__device__ __forceinline__ void block_sum4_store(float a0, float a1, float a2, float a3, float* row) {
+    __shared__ float red[4][NT / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = a2; red[3][warp] = a3; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) t += red[threadIdx.x][w];
+        row[threadIdx.x] = t;
+    }
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 }  // namespace adc

@@ -1,6 +1,7 @@
 // C-ABI entry points of the NConv path (include/adc_b200.h) + the pyramid orchestration.
 // Single translation unit for every kernel that reads the constant-memory weight images.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "adc_common.cuh"
@@ -8,6 +9,7 @@
 #include "nconv_fwd.cuh"
 #include "pool.cuh"
 #include "prep.cuh"
+#include "tma.cuh"
 
 namespace adc {
 
@@ -27,8 +29,13 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 static float* g_stage = nullptr;  // [ADC_WSLOTS][2][ADC_PYR_CALLS][kWStride] device staging for the single-layer API
+static int g_use_tma = -1;
 
 static int ensure_init() {
+    if (g_use_tma < 0) {
+        const char* e = getenv("ADC_NO_TMA");   // testing aid: force the gather loaders everywhere
+        g_use_tma = (e && e[0] == '1') ? 0 : 1;
+    }
     if (g_stage) return 0;
     ADC_CUDA(cudaMalloc(&g_stage, sizeof(float) * ADC_WSLOTS * 2 * ADC_PYR_CALLS * kWStride));
     return 0;
@@ -44,108 +51,143 @@ static int upload_images(const float* img, int slot, int fb, int first_call, int
                       "cudaMemcpyToSymbolAsync(c_wimg)");
 }
 
-static int dispatch_fwd(int Ci, int K, const Src& s0, const Src& s1, float* y, float* cout, int N, int H, int W, int wimg,
-                        cudaStream_t st) {
-    if (Ci == 1 && K == 5) return launch_nconv_fwd<1, 5>(s0, s1, y, cout, N, H, W, wimg, st);
-    if (Ci == 2 && K == 5) return launch_nconv_fwd<2, 5>(s0, s1, y, cout, N, H, W, wimg, st);
-    if (Ci == 4 && K == 3) return launch_nconv_fwd<4, 3>(s0, s1, y, cout, N, H, W, wimg, st);
-    if (Ci == 1 && K == 3) return launch_nconv_fwd<1, 3>(s0, s1, y, cout, N, H, W, wimg, st);
-    if (Ci == 2 && K == 3) return launch_nconv_fwd<2, 3>(s0, s1, y, cout, N, H, W, wimg, st);
-    set_error("NConv2d forward: (Ci=%d, Co=2, k=%d) is not instantiated", Ci, K);
-    return ADC_E_UNSUPP;
+// ---- pair-tensor sources ------------------------------------------------------------------------------------------
+static SrcP make_srcp(const float2* p, long long bs, int ch, int Hs, int Ws, int H, int W) {
+    SrcP r;
+    r.p = p;
+    r.bs = bs;
+    r.ch = ch;
+    r.H = Hs;
+    r.W = Ws;
+    r.mh = NearestMap::make(Hs, H);
+    r.mw = NearestMap::make(Ws, W);
+    r.up = (Hs != H || Ws != W) ? 1 : 0;
+    // TMA needs a 16-byte aligned base and 16-byte multiples for every stride: even width, even batch stride
+    r.tma = (g_use_tma == 1 && !r.up && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (Ws % 2 == 0) && (bs % 2 == 0)) ? 1 : 0;
+    return r;
 }
 
-static int dispatch_bwd_data(int Ci, int K, const Src& s0, const Src& s1, const GradIn& g, float* gx0, float* gc0, float* gx1,
-                             float* gc1, int N, int H, int W, int wimg, cudaStream_t st) {
-    if (Ci == 1 && K == 5) return launch_nconv_bwd_data<1, 5>(s0, s1, g, gx0, gc0, gx1, gc1, N, H, W, wimg, st);
-    if (Ci == 2 && K == 5) return launch_nconv_bwd_data<2, 5>(s0, s1, g, gx0, gc0, gx1, gc1, N, H, W, wimg, st);
-    if (Ci == 4 && K == 3) return launch_nconv_bwd_data<4, 3>(s0, s1, g, gx0, gc0, gx1, gc1, N, H, W, wimg, st);
-    if (Ci == 1 && K == 3) return launch_nconv_bwd_data<1, 3>(s0, s1, g, gx0, gc0, gx1, gc1, N, H, W, wimg, st);
-    if (Ci == 2 && K == 3) return launch_nconv_bwd_data<2, 3>(s0, s1, g, gx0, gc0, gx1, gc1, N, H, W, wimg, st);
-    set_error("NConv2d backward(data): (Ci=%d, Co=2, k=%d) is not instantiated", Ci, K);
-    return ADC_E_UNSUPP;
-}
-
-static int dispatch_bwd_weight(int Ci, int K, const Src& s0, const Src& s1, const GradIn& g, float* partial, int N, int H, int W,
-                               int wimg, cudaStream_t st) {
-    if (Ci == 1 && K == 5) return launch_nconv_bwd_weight<1, 5>(s0, s1, g, partial, N, H, W, wimg, st);
-    if (Ci == 2 && K == 5) return launch_nconv_bwd_weight<2, 5>(s0, s1, g, partial, N, H, W, wimg, st);
-    if (Ci == 4 && K == 3) return launch_nconv_bwd_weight<4, 3>(s0, s1, g, partial, N, H, W, wimg, st);
-    if (Ci == 1 && K == 3) return launch_nconv_bwd_weight<1, 3>(s0, s1, g, partial, N, H, W, wimg, st);
-    if (Ci == 2 && K == 3) return launch_nconv_bwd_weight<2, 3>(s0, s1, g, partial, N, H, W, wimg, st);
-    set_error("NConv2d backward(weight): (Ci=%d, Co=2, k=%d) is not instantiated", Ci, K);
-    return ADC_E_UNSUPP;
-}
-
-static inline int tiles(int H, int W) { return ceil_div(W, 64) * ceil_div(H, 32); }
-static inline int blocks_1x1(long long plane) { return (int)((plane + 1023) / 1024); }
-
-// number of per-CTA partial rows the weight-gradient kernel of a layer writes
-static inline int wg_blocks(int N, int Co, int H, int W) {
-    return Co == 1 ? N * blocks_1x1((long long)H * W) : N * tiles(H, W);
-}
-
-static int run_layer_fwd(const Src& s0, const Src* s1, int Ci, int Co, int K, float* y, float* cout, int N, int H, int W,
-                         int wimg, cudaStream_t st) {
-    Src dummy = s0;
-    if (Co == 2) return dispatch_fwd(Ci, K, s0, s1 ? *s1 : dummy, y, cout, N, H, W, wimg, st);
-    if (Co == 1 && Ci == 2 && K == 1 && !s1 && !s0.up) {
-        const long long plane = (long long)H * W;
-        dim3 grid(blocks_1x1(plane), N);
-        nconv_1x1_c2_fwd_kernel<<<grid, 256, 0, st>>>(s0.x, s0.c, s0.bs, y, cout, plane, wimg);
-        return check_cuda(cudaGetLastError(), "nconv_1x1_c2_fwd_kernel launch");
+// 4-D map over a pair tensor seen as floats: (2W, H, C, N), box (2*box_w_pairs, box_h, 1, 1)
+static int make_pair_map(CUtensorMap* m, const SrcP& s, int N, int box_w_pairs, int box_h) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return ADC_E_UNSUPP;
     }
-    set_error("NConv2d forward: (Ci=%d, Co=%d, k=%d) is not instantiated", Ci, Co, K);
-    return ADC_E_UNSUPP;
-}
-
-// gx/gc for an upsampled source are produced at layer resolution into `up_scratch` and then reduced.
-static int run_layer_bwd(const Src& s0, const Src* s1, int Ci, int Co, int K, const GradIn& g, float* gx0, float* gc0, float* gx1,
-                         float* gc1, float* partial, float* up_scratch, int N, int H, int W, int wimg_f, int wimg_b,
-                         bool need_data, bool need_weight, cudaStream_t st) {
-    Src dummy = s0;
-    const long long plane = (long long)H * W;
-    if (Co == 1) {
-        if (!(Ci == 2 && K == 1 && !s1 && !s0.up)) {
-            set_error("NConv2d backward: (Ci=%d, Co=1, k=%d) is not instantiated", Ci, K);
-            return ADC_E_UNSUPP;
-        }
-        dim3 grid(blocks_1x1(plane), N);
-        nconv_1x1_c2_bwd_kernel<<<grid, 256, 0, st>>>(s0.x, s0.c, s0.bs, g, need_data ? gx0 : nullptr, gc0, partial, plane,
-                                                     wimg_f, wimg_b);
-        return check_cuda(cudaGetLastError(), "nconv_1x1_c2_bwd_kernel launch");
-    }
-    if (need_weight) {
-        int rc = dispatch_bwd_weight(Ci, K, s0, s1 ? *s1 : dummy, g, partial, N, H, W, wimg_f, st);
-        if (rc) return rc;
-    }
-    if (need_data) {
-        // destinations at layer resolution
-        float* d0x = gx0; float* d0c = gc0; float* d1x = gx1; float* d1c = gc1;
-        float* sc = up_scratch;
-        if (s0.up) { d0x = sc; d0c = sc + (long long)N * s0.ch * plane; sc += 2LL * N * s0.ch * plane; }
-        if (s1 && s1->up) { d1x = sc; d1c = sc + (long long)N * s1->ch * plane; }
-        // the data kernel reads b and s from the image it is given: the backward image carries both
-        int rc = dispatch_bwd_data(Ci, K, s0, s1 ? *s1 : dummy, g, d0x, d0c, d1x, d1c, N, H, W, wimg_b, st);
-        if (rc) return rc;
-        const Src* ss[2] = {&s0, s1};
-        float* dx[2] = {d0x, d1x}; float* dc[2] = {d0c, d1c};
-        float* ox[2] = {gx0, gx1}; float* oc[2] = {gc0, gc1};
-        for (int k = 0; k < 2; ++k) {
-            if (!ss[k] || !ss[k]->up) continue;
-            const long long planes = (long long)N * ss[k]->ch;
-            const long long total = planes * ss[k]->H * ss[k]->W;
-            const int nb = (int)((total + 255) / 256);
-            upsample_bwd_kernel<<<nb, 256, 0, st>>>(dx[k], ox[k], H, W, ss[k]->H, ss[k]->W, ss[k]->mh, ss[k]->mw, planes);
-            upsample_bwd_kernel<<<nb, 256, 0, st>>>(dc[k], oc[k], H, W, ss[k]->H, ss[k]->W, ss[k]->mh, ss[k]->mw, planes);
-            int rc2 = check_cuda(cudaGetLastError(), "upsample_bwd_kernel launch");
-            if (rc2) return rc2;
-        }
+    cuuint64_t dims[4] = {(cuuint64_t)2 * s.W, (cuuint64_t)s.H, (cuuint64_t)s.ch, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)s.W * 8, (cuuint64_t)s.H * s.W * 8, (cuuint64_t)s.bs * 8};
+    cuuint32_t box[4] = {(cuuint32_t)(2 * box_w_pairs), (cuuint32_t)box_h, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float2*>(s.p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d C=%d N=%d box %dx%d)", (int)r, s.W, s.H, s.ch, N,
+                  box_w_pairs, box_h);
+        return ADC_E_UNSUPP;
     }
     return 0;
 }
 
-// ---- pyramid geometry -------------------------------------------------------------------------
+template <int K>
+static int fill_maps(Maps2* maps, const SrcP& s0, const SrcP* s1, int N) {
+    memset(maps, 0, sizeof(*maps));
+    using C = TileCfg<K>;
+    int rc = 0;
+    if (s0.tma && (rc = make_pair_map(&maps->m0, s0, N, C::SWP, C::SH))) return rc;
+    if (s1 && s1->tma && (rc = make_pair_map(&maps->m1, *s1, N, C::SWP, C::SH))) return rc;
+    return 0;
+}
+
+template <typename Kern>
+static int set_smem(Kern kern, int bytes) {
+    return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute(smem)");
+}
+
+static inline dim3 tile_grid(int N, int H, int W) { return dim3(ceil_div(W, 64), ceil_div(H, 32), N); }
+static inline int tiles(int N, int H, int W) { return N * ceil_div(W, 64) * ceil_div(H, 32); }
+static inline int blocks_1x1(long long plane) { return (int)ceil_div_ll(plane, 512); }
+
+template <int CI, int K>
+static int launch_fwd(const SrcP& s0, const SrcP* s1, float2* out, int N, int H, int W, int wimg, cudaStream_t st) {
+    using C = TileCfg<K>;
+    static bool done = false;
+    const int smem = C::smem_bytes(CI);
+    if (!done) { int rc = set_smem(nconv_fwd_kernel<CI, K>, smem); if (rc) return rc; done = true; }
+    Maps2 maps;
+    int rc = fill_maps<K>(&maps, s0, s1, N);
+    if (rc) return rc;
+    nconv_fwd_kernel<CI, K><<<tile_grid(N, H, W), 128, smem, st>>>(maps, s0, s1 ? *s1 : s0, s1 ? 1 : 0, out, H, W, wimg);
+    return check_cuda(cudaGetLastError(), "nconv_fwd_kernel launch");
+}
+
+template <int CI, int K>
+static int launch_bwd_data(const SrcP& g, const SrcP& s0, const SrcP* s1, float2* out0, float2* out1, float* bpart, int N, int H,
+                           int W, int wimg, int ximg, cudaStream_t st) {
+    using C = TileCfg<K>;
+    static bool done = false;
+    const int smem = C::smem_bytes(2);
+    if (!done) { int rc = set_smem(nconv_bwd_data_kernel<CI, K>, smem); if (rc) return rc; done = true; }
+    Maps2 maps;
+    int rc = fill_maps<K>(&maps, g, nullptr, N);
+    if (rc) return rc;
+    nconv_bwd_data_kernel<CI, K><<<tile_grid(N, H, W), 128, smem, st>>>(maps, g, s0, s1 ? *s1 : s0, s1 ? 1 : 0, out0, out1, bpart,
+                                                                         H, W, wimg, ximg);
+    return check_cuda(cudaGetLastError(), "nconv_bwd_data_kernel launch");
+}
+
+template <int CI, int K>
+static int launch_bwd_weight(const SrcP& g, const SrcP& s0, const SrcP* s1, float* wpart, int N, int H, int W, cudaStream_t st) {
+    using C = WgCfg<CI, K>;
+    static bool done = false;
+    const int smem = C::smem_bytes();
+    if (!done) { int rc = set_smem(nconv_bwd_weight_kernel<CI, K>, smem); if (rc) return rc; done = true; }
+    Maps2 maps;
+    int rc = fill_maps<K>(&maps, s0, s1, N);
+    if (rc) return rc;
+    CUtensorMap gmap;
+    memset(&gmap, 0, sizeof(gmap));
+    if (g.tma && (rc = make_pair_map(&gmap, g, N, C::TW, C::TH))) return rc;
+    nconv_bwd_weight_kernel<CI, K><<<tile_grid(N, H, W), C::NT, smem, st>>>(maps, gmap, g, s0, s1 ? *s1 : s0, s1 ? 1 : 0, wpart, H, W);
+    return check_cuda(cudaGetLastError(), "nconv_bwd_weight_kernel launch");
+}
+
+#define ADC_DISPATCH(FN, ...)                                         \
+    do {                                                              \
+        if (Ci == 1 && K == 5) return FN<1, 5>(__VA_ARGS__);          \
+        if (Ci == 2 && K == 5) return FN<2, 5>(__VA_ARGS__);          \
+        if (Ci == 4 && K == 3) return FN<4, 3>(__VA_ARGS__);          \
+        if (Ci == 1 && K == 3) return FN<1, 3>(__VA_ARGS__);          \
+        if (Ci == 2 && K == 3) return FN<2, 3>(__VA_ARGS__);          \
+    } while (0)
+
+static int dispatch_fwd(int Ci, int K, const SrcP& s0, const SrcP* s1, float2* out, int N, int H, int W, int wimg, cudaStream_t st) {
+    ADC_DISPATCH(launch_fwd, s0, s1, out, N, H, W, wimg, st);
+    set_error("NConv2d forward: (Ci=%d, Co=2, k=%d) is not instantiated", Ci, K);
+    return ADC_E_UNSUPP;
+}
+static int dispatch_bwd_data(int Ci, int K, const SrcP& g, const SrcP& s0, const SrcP* s1, float2* out0, float2* out1, float* bpart,
+                             int N, int H, int W, int wimg, int ximg, cudaStream_t st) {
+    ADC_DISPATCH(launch_bwd_data, g, s0, s1, out0, out1, bpart, N, H, W, wimg, ximg, st);
+    set_error("NConv2d backward(data): (Ci=%d, Co=2, k=%d) is not instantiated", Ci, K);
+    return ADC_E_UNSUPP;
+}
+static int dispatch_bwd_weight(int Ci, int K, const SrcP& g, const SrcP& s0, const SrcP* s1, float* wpart, int N, int H, int W,
+                               cudaStream_t st) {
+    ADC_DISPATCH(launch_bwd_weight, g, s0, s1, wpart, N, H, W, st);
+    set_error("NConv2d backward(weight): (Ci=%d, Co=2, k=%d) is not instantiated", Ci, K);
+    return ADC_E_UNSUPP;
+}
+
+static int run_upsample_bwd(const float2* g_full, const SrcP& s, float2* G, float* bpart, int N, int H, int W, int ximg,
+                            cudaStream_t st) {
+    const long long planes = (long long)N * s.ch, total = planes * s.H * s.W;
+    pair_upsample_bwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(g_full, s.p, G, bpart, s.ch, H, W, s.H, s.W, s.mh, s.mw,
+                                                                          planes, ximg);
+    return check_cuda(cudaGetLastError(), "pair_upsample_bwd_kernel launch");
+}
+
+// ---- pyramid geometry -------------------------------------------------------------------------------------------
 struct Geo {
     int N, h[4], w[4];
     long long px[4];  // N*h*w
@@ -156,9 +198,10 @@ struct Geo {
     }
 };
 
-// saved activations: each entry is an (x, c) pair of [N,2,h,w] tensors: x at off, c at off + 2*px
-enum Act { A0, A1, A2, P1, A3, A4, P2, A5, P3, A6, A7, A8, A9, ACT_COUNT };
-static const int kActLevel[ACT_COUNT] = {0, 0, 0, 1, 1, 1, 2, 2, 3, 3, 2, 1, 0};
+// saved activations: pair tensors [N,2,h,w] (AIN: [N,1,H,W])
+enum Act { A0, A1, A2, P1, A3, A4, P2, A5, P3, A6, A7, A8, A9, AIN, ACT_COUNT };
+static const int kActLevel[ACT_COUNT] = {0, 0, 0, 1, 1, 1, 2, 2, 3, 3, 2, 1, 0, 0};
+static const int kActCh[ACT_COUNT] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1};
 static const long long kImgFloats = (long long)ADC_PYR_CALLS * kWStride;
 
 struct SavedLayout {
@@ -168,7 +211,7 @@ struct SavedLayout {
         long long o = kImgFloats;  // forward weight images first
         for (int a = 0; a < ACT_COUNT; ++a) {
             off[a] = o;
-            o += 4 * g.px[kActLevel[a]];
+            o += 2LL * kActCh[a] * g.px[kActLevel[a]];
         }
         total = o;
     }
@@ -187,25 +230,13 @@ static long long mod_offset(int m) {
     return o;
 }
 
-static adc_src_t mk_src(const float* base, long long px, int N, int ch, int h, int w) {
-    adc_src_t s;
-    s.x = base;
-    s.c = base + 2 * px;  // (x, c) pair layout of the saved activations (2 channels each)
-    s.batch_stride = (long long)ch * h * w;
-    s.channels = ch;
-    s.H = h;
-    s.W = w;
-    (void)N;
-    return s;
-}
-
 }  // namespace adc
 
 using namespace adc;
 
 extern "C" {
 
-int adc_abi_version(void) { return 1; }
+int adc_abi_version(void) { return 2; }
 const char* adc_last_error(void) { return g_err; }
 
 int adc_softplus_pow(const float* w, float* out, int numel, int times, adc_stream_t stream) {
@@ -220,7 +251,7 @@ int adc_conf_pool_fwd(const float* x, const float* c, float* x_ds, float* c_ds, 
                   "adc_conf_pool_fwd: bad argument");
     const int Ho = H / 2, Wo = W / 2;
     const long long planes = (long long)N * C, total = planes * Ho * Wo;
-    conf_pool_fwd_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, c, x_ds, c_ds, idx, H, W, Ho, Wo, planes);
+    conf_pool_fwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(x, c, x_ds, c_ds, idx, H, W, Ho, Wo, planes);
     return check_cuda(cudaGetLastError(), "conf_pool_fwd_kernel launch");
 }
 
@@ -230,8 +261,8 @@ int adc_conf_pool_bwd(const float* g_xds, const float* g_cds, const long long* i
                   "adc_conf_pool_bwd: bad argument");
     const int Ho = H / 2, Wo = W / 2;
     const long long planes = (long long)N * C, total = planes * ((H + 1) / 2) * ((W + 1) / 2);
-    conf_pool_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g_xds, g_cds, idx, add_x, add_c, gx, gc, H,
-                                                                                       W, Ho, Wo, planes);
+    conf_pool_bwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(g_xds, g_cds, idx, add_x, add_c, gx, gc, H,
+                                                                                         W, Ho, Wo, planes);
     return check_cuda(cudaGetLastError(), "conf_pool_bwd_kernel launch");
 }
 
@@ -242,14 +273,31 @@ static int check_layer_args(const char* fn, const adc_src_t* s0, const adc_src_t
     ADC_CHECK_ARG(slot >= 0 && slot < ADC_WSLOTS, ADC_E_BADARG, "%s: slot out of range", fn);
     const int Ci = s0->channels + (s1 ? s1->channels : 0);
     ADC_CHECK_ARG(Co * Ci * k * k <= kWMax, ADC_E_UNSUPP, "%s: Co*Ci*k*k = %d exceeds %d", fn, Co * Ci * k * k, kWMax);
+    ADC_CHECK_ARG(Co == 2 || (Ci == 2 && k == 1 && !s1 && s0->H == H && s0->W == W), ADC_E_UNSUPP,
+                  "%s: Co=1 is instantiated for the 2->1 1x1 head only", fn);
     return 0;
 }
 
-int adc_nconv2d_fwd(const adc_src_t* src0, const adc_src_t* src1, const float* w, const float* b, float* y, float* cout, int N,
-                    int Co, int H, int W, int k, int slot, adc_stream_t stream) {
+static long long src_pairs(const adc_src_t* s, int N) { return s ? (long long)N * s->channels * s->H * s->W : 0; }
+
+// planar source -> pair tensor in scratch
+static int pack_source(const adc_src_t* s, int N, float2* dst, cudaStream_t st) {
+    const long long per_image = (long long)s->channels * s->H * s->W;
+    dim3 grid((unsigned)ceil_div_ll(per_image, 256), N);
+    pack_pairs_kernel<<<grid, 256, 0, st>>>(s->x, s->c, s->batch_stride, s->batch_stride, dst, per_image);
+    return check_cuda(cudaGetLastError(), "pack_pairs_kernel launch");
+}
+
+size_t adc_nconv2d_fwd_scratch_floats(const adc_src_t* src0, const adc_src_t* src1, int N, int Co, int H, int W) {
+    if (!src0) return 0;
+    return (size_t)(2 * (src_pairs(src0, N) + src_pairs(src1, N) + (long long)N * Co * H * W));
+}
+
+int adc_nconv2d_fwd(const adc_src_t* src0, const adc_src_t* src1, const float* w, const float* b, float* y, float* cout,
+                    float* scratch, int N, int Co, int H, int W, int k, int slot, adc_stream_t stream) {
     int rc = check_layer_args("adc_nconv2d_fwd", src0, src1, N, Co, H, W, k, slot);
     if (rc) return rc;
-    ADC_CHECK_ARG(w && b && y && cout, ADC_E_BADARG, "adc_nconv2d_fwd: null pointer");
+    ADC_CHECK_ARG(w && b && y && cout && scratch, ADC_E_BADARG, "adc_nconv2d_fwd: null pointer");
     if ((rc = ensure_init())) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int Ci = src0->channels + (src1 ? src1->channels : 0);
@@ -260,15 +308,53 @@ int adc_nconv2d_fwd(const adc_src_t* src0, const adc_src_t* src1, const float* w
     prep_weights_kernel<<<1, 128, 0, st>>>(pa);
     ADC_CUDA(cudaGetLastError());
     if ((rc = upload_images(pa.img, slot, 0, 0, 1, st))) return rc;
-    Src s0 = make_src(src0, H, W), s1;
-    if (src1) s1 = make_src(src1, H, W);
-    return run_layer_fwd(s0, src1 ? &s1 : nullptr, Ci, Co, k, y, cout, N, H, W, wimg_index(slot, 0, 0), st);
+    float2* p0 = reinterpret_cast<float2*>(scratch);
+    float2* p1 = p0 + src_pairs(src0, N);
+    float2* po = p1 + src_pairs(src1, N);
+    if ((rc = pack_source(src0, N, p0, st))) return rc;
+    if (src1 && (rc = pack_source(src1, N, p1, st))) return rc;
+    SrcP s0 = make_srcp(p0, (long long)src0->channels * src0->H * src0->W, src0->channels, src0->H, src0->W, H, W), s1;
+    if (src1) s1 = make_srcp(p1, (long long)src1->channels * src1->H * src1->W, src1->channels, src1->H, src1->W, H, W);
+    const int wimg = wimg_index(slot, 0, 0);
+    const long long plane = (long long)H * W;
+    if (Co == 1) {
+        dim3 grid(blocks_1x1(plane), N);
+        nconv_1x1_fwd_kernel<<<grid, 256, 0, st>>>(p0, y, cout, plane, wimg);
+        return check_cuda(cudaGetLastError(), "nconv_1x1_fwd_kernel launch");
+    }
+    if ((rc = dispatch_fwd(Ci, k, s0, src1 ? &s1 : nullptr, po, N, H, W, wimg, st))) return rc;
+    const long long total = (long long)N * Co * plane;
+    unpack_pairs_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(po, y, cout, total);
+    return check_cuda(cudaGetLastError(), "unpack_pairs_kernel launch");
 }
 
-size_t adc_nconv2d_bwd_scratch_floats(int N, int Ci, int Co, int H, int W, int k) {
-    (void)k;
-    // per-CTA weight-gradient partials + layer-resolution gradients of (possibly) upsampled sources
-    return (size_t)wg_blocks(N, Co, H, W) * kWStride + (size_t)2 * N * Ci * H * W;
+// scratch of the single-layer backward: [packed sources][G pairs][raw grads at layer res][raw low-res grads][wpart][bpart]
+namespace adc {
+struct LayerBwdLayout {
+    long long p0, p1, G, r0, r1, l0, l1, wpart, bpart, total;
+    int wblocks, bblocks;
+    LayerBwdLayout(const adc_src_t* s0, const adc_src_t* s1, int N, int Co, int H, int W) {
+        const long long plane = (long long)H * W;
+        long long o = 0;
+        p0 = o; o += 2 * src_pairs(s0, N);
+        p1 = o; o += 2 * src_pairs(s1, N);
+        G = o; o += 2LL * N * Co * plane;
+        r0 = o; o += 2LL * N * s0->channels * plane;
+        r1 = o; o += s1 ? 2LL * N * s1->channels * plane : 0;
+        l0 = o; o += 2 * src_pairs(s0, N);
+        l1 = o; o += 2 * src_pairs(s1, N);
+        wblocks = Co == 1 ? N * blocks_1x1(plane) : tiles(N, H, W);
+        bblocks = Co == 1 ? wblocks : N * (int)ceil_div_ll(plane, 256);
+        wpart = o; o += (long long)wblocks * kWStride;
+        bpart = o; o += (long long)bblocks * 4;
+        total = o;
+    }
+};
+}  // namespace adc
+
+size_t adc_nconv2d_bwd_scratch_floats(const adc_src_t* src0, const adc_src_t* src1, int N, int Co, int H, int W) {
+    if (!src0) return 0;
+    return (size_t)LayerBwdLayout(src0, src1, N, Co, H, W).total;
 }
 
 int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y, const float* cout, const float* gy,
@@ -282,10 +368,13 @@ int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y
                   "adc_nconv2d_bwd: gx/gc must be given in pairs");
     ADC_CHECK_ARG(!src1 || ((gx0 == nullptr) == (gx1 == nullptr)), ADC_E_BADARG,
                   "adc_nconv2d_bwd: input gradients are all-or-none across sources");
+    ADC_CHECK_ARG((gw == nullptr) == (gb == nullptr), ADC_E_BADARG, "adc_nconv2d_bwd: gw/gb must be given together");
     if ((rc = ensure_init())) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int Ci = src0->channels + (src1 ? src1->channels : 0);
     const bool need_data = gx0 != nullptr, need_weight = gw != nullptr;
+    const long long plane = (long long)H * W;
+    LayerBwdLayout L(src0, src1, N, Co, H, W);
     PrepArgs pa;
     memset(&pa, 0, sizeof(pa));
     float* img_f = g_stage + (size_t)wimg_index(slot, 0, 0) * kWStride;
@@ -293,25 +382,61 @@ int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y
     pa.call[0] = PrepCall{w_fwd, b, nullptr, Co, Ci, k, 0, 0, nullptr};
     pa.img = img_f;
     prep_weights_kernel<<<1, 128, 0, st>>>(pa);
-    pa.call[0] = PrepCall{w_bwd, b, nullptr, Co, Ci, k, 0, Co == 2 ? 1 : 0, img_f};
+    pa.call[0] = PrepCall{w_bwd, b, nullptr, Co, Ci, k, 0, 1, img_f};
     pa.img = img_b;
     prep_weights_kernel<<<1, 128, 0, st>>>(pa);
     ADC_CUDA(cudaGetLastError());
     if ((rc = upload_images(img_f, slot, 0, 0, 1, st))) return rc;
     if ((rc = upload_images(img_b, slot, 1, 0, 1, st))) return rc;
-    Src s0 = make_src(src0, H, W), s1;
-    if (src1) s1 = make_src(src1, H, W);
-    GradIn g{y, cout, gy, gcout};
-    float* partial = scratch;
-    const int nblk = wg_blocks(N, Co, H, W);
-    float* up_scratch = scratch + (size_t)nblk * kWStride;
-    rc = run_layer_bwd(s0, src1 ? &s1 : nullptr, Ci, Co, k, g, gx0, gc0, gx1, gc1, partial, up_scratch, N, H, W,
-                       wimg_index(slot, 0, 0), wimg_index(slot, 1, 0), need_data, need_weight || Co == 1, st);
-    if (rc) return rc;
+    const int wf = wimg_index(slot, 0, 0), wb = wimg_index(slot, 1, 0);
+    float2* p0 = reinterpret_cast<float2*>(scratch + L.p0);
+    float2* p1 = reinterpret_cast<float2*>(scratch + L.p1);
+    float2* G = reinterpret_cast<float2*>(scratch + L.G);
+    float2* r0 = reinterpret_cast<float2*>(scratch + L.r0);
+    float2* r1 = reinterpret_cast<float2*>(scratch + L.r1);
+    float* wpart = scratch + L.wpart;
+    float* bpart = scratch + L.bpart;
+    if ((rc = pack_source(src0, N, p0, st))) return rc;
+    if (src1 && (rc = pack_source(src1, N, p1, st))) return rc;
+    SrcP s0 = make_srcp(p0, (long long)src0->channels * src0->H * src0->W, src0->channels, src0->H, src0->W, H, W), s1;
+    if (src1) s1 = make_srcp(p1, (long long)src1->channels * src1->H * src1->W, src1->channels, src1->H, src1->W, H, W);
+
+    if (Co == 1) {
+        dim3 grid(blocks_1x1(plane), N);
+        nconv_1x1_bwd_kernel<<<grid, 256, 0, st>>>(p0, y, cout, gy, gcout, need_data ? r0 : nullptr, wpart, bpart, nullptr, plane, wf,
+                                                  wb, -1);
+        ADC_CUDA(cudaGetLastError());
+    } else {
+        dim3 grid((unsigned)ceil_div_ll(plane, 256), N);
+        grad_transform_kernel<2><<<grid, 256, 0, st>>>(gy, gcout, y, cout, G, bpart, plane, wf);
+        ADC_CUDA(cudaGetLastError());
+        SrcP g = make_srcp(G, 2 * plane, 2, H, W, H, W);
+        if (need_weight && (rc = dispatch_bwd_weight(Ci, k, g, s0, src1 ? &s1 : nullptr, wpart, N, H, W, st))) return rc;
+        if (need_data && (rc = dispatch_bwd_data(Ci, k, g, s0, src1 ? &s1 : nullptr, r0, r1, nullptr, N, H, W, wb, -1, st))) return rc;
+    }
+    if (need_data) {
+        const adc_src_t* ss[2] = {src0, src1};
+        const SrcP* sp[2] = {&s0, src1 ? &s1 : nullptr};
+        float2* raw[2] = {r0, r1};
+        float2* low[2] = {reinterpret_cast<float2*>(scratch + L.l0), reinterpret_cast<float2*>(scratch + L.l1)};
+        float* ox[2] = {gx0, gx1};
+        float* oc[2] = {gc0, gc1};
+        for (int q = 0; q < 2; ++q) {
+            if (!ss[q]) continue;
+            const float2* fin = raw[q];
+            if (sp[q]->up) {
+                if ((rc = run_upsample_bwd(raw[q], *sp[q], low[q], nullptr, N, H, W, -1, st))) return rc;
+                fin = low[q];
+            }
+            const long long total = src_pairs(ss[q], N);
+            unpack_pairs_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(fin, ox[q], oc[q], total);
+            ADC_CUDA(cudaGetLastError());
+        }
+    }
     if (need_weight) {
         WgReduceArgs ra;
         memset(&ra, 0, sizeof(ra));
-        ra.call[0] = WgReduceCall{partial, nblk, 0, Co, Co * Ci * k * k};
+        ra.call[0] = WgReduceCall{wpart, bpart, L.wblocks, L.bblocks, 0, Co, Co * Ci * k * k};
         ra.ncalls = 1;
         ra.gw[0] = gw;
         ra.gb[0] = gb;
@@ -354,12 +479,14 @@ int adc_pyramid_fwd(const adc_pyramid_fwd_t* a, adc_stream_t stream) {
     ADC_CHECK_ARG(!a->training || a->weight_out, ADC_E_BADARG, "adc_pyramid_fwd: training needs weight_out");
     for (int m = 0; m < ADC_PYR_MODULES; ++m)
         ADC_CHECK_ARG(a->weight[m] && a->bias[m], ADC_E_BADARG, "adc_pyramid_fwd: missing parameter %d", m);
+    int rc = ensure_init();
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     Geo g(a->N, a->H, a->W);
     SavedLayout L(g);
     float* S = a->saved;
 
-    // 1. weights: softplus^k per call, sums, kernel layout -> constant memory
+    // 1. weights: softplus^k per call, sums -> constant memory
     PrepArgs pa;
     memset(&pa, 0, sizeof(pa));
     int seen[ADC_PYR_MODULES] = {0};
@@ -374,70 +501,84 @@ int adc_pyramid_fwd(const adc_pyramid_fwd_t* a, adc_stream_t stream) {
     pa.img = S;
     prep_weights_kernel<<<ADC_PYR_CALLS, 128, 0, st>>>(pa);
     ADC_CUDA(cudaGetLastError());
-    int rc = upload_images(S, a->slot, 0, 0, ADC_PYR_CALLS, st);
-    if (rc) return rc;
+    if ((rc = upload_images(S, a->slot, 0, 0, ADC_PYR_CALLS, st))) return rc;
 
-    auto act = [&](int id) { return S + L.off[id]; };
-    auto src_of = [&](int id) {
-        const int l = kActLevel[id];
-        adc_src_t s = mk_src(act(id), g.px[l], g.N, 2, g.h[l], g.w[l]);
-        return s;
+    auto act = [&](int id) { return reinterpret_cast<float2*>(S + L.off[id]); };
+    auto src_of = [&](int id, int lvl) {   // activation `id` as a source of a layer at level `lvl`
+        const int l = kActLevel[id], ch = kActCh[id];
+        return make_srcp(act(id), (long long)ch * g.h[l] * g.w[l], ch, g.h[l], g.w[l], g.h[lvl], g.w[lvl]);
     };
-    auto layer = [&](int call, const adc_src_t& a0, const adc_src_t* a1, float* y, float* cout) -> int {
+    auto layer = [&](int call, int in0, int in1, int out) -> int {
         const int m = kCallModule[call], l = kCallLevel[call];
-        Src s0 = make_src(&a0, g.h[l], g.w[l]), s1;
-        if (a1) s1 = make_src(a1, g.h[l], g.w[l]);
-        return run_layer_fwd(s0, a1 ? &s1 : nullptr, kModCi[m], kModCo[m], kModK[m], y, cout, g.N, g.h[l], g.w[l],
-                             wimg_index(a->slot, 0, call), st);
+        SrcP s0 = src_of(in0, l), s1;
+        if (in1 >= 0) s1 = src_of(in1, l);
+        return dispatch_fwd(kModCi[m], kModK[m], s0, in1 >= 0 ? &s1 : nullptr, act(out), g.N, g.h[l], g.w[l],
+                            wimg_index(a->slot, 0, call), st);
     };
-    auto out_of = [&](int id, float*& y, float*& c) { y = act(id); c = act(id) + 2 * g.px[kActLevel[id]]; };
+    long long ioff[3]; int ihs[3], iws[3];
+    adc_pyramid_idx_layout(g.N, a->H, a->W, ioff, ihs, iws);
     auto pool = [&](int in_id, int out_id, int lvl) -> int {  // lvl = level of the input
-        float *xi, *ci, *xo, *co;
-        out_of(in_id, xi, ci);
-        out_of(out_id, xo, co);
-        long long off[3]; int hs[3], ws[3];
-        adc_pyramid_idx_layout(g.N, a->H, a->W, off, hs, ws);
-        return adc_conf_pool_fwd(xi, ci, xo, co, a->idx + off[lvl], g.N, 2, g.h[lvl], g.w[lvl], stream);
+        const int Ho = g.h[lvl + 1], Wo = g.w[lvl + 1];
+        const long long planes = (long long)g.N * 2, total = planes * Ho * Wo;
+        pair_pool_fwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(act(in_id), act(out_id), a->idx + ioff[lvl], g.h[lvl],
+                                                                            g.w[lvl], Ho, Wo, planes);
+        return check_cuda(cudaGetLastError(), "pair_pool_fwd_kernel launch");
     };
 #define RUN(expr) do { rc = (expr); if (rc) return rc; } while (0)
-    adc_src_t in0;
-    in0.x = a->x0; in0.c = a->c0; in0.batch_stride = a->x0_batch_stride; in0.channels = 1; in0.H = a->H; in0.W = a->W;
-    ADC_CHECK_ARG(a->x0_batch_stride == a->c0_batch_stride, ADC_E_BADARG, "adc_pyramid_fwd: x0/c0 batch strides must match");
-    float *y, *c;
-    out_of(A0, y, c); RUN(layer(0, in0, nullptr, y, c));
-    { adc_src_t s = src_of(A0); out_of(A1, y, c); RUN(layer(1, s, nullptr, y, c)); }
-    { adc_src_t s = src_of(A1); out_of(A2, y, c); RUN(layer(2, s, nullptr, y, c)); }
+    {
+        const long long per_image = (long long)a->H * a->W;
+        dim3 grid((unsigned)ceil_div_ll(per_image, 256), g.N);
+        pack_pairs_kernel<<<grid, 256, 0, st>>>(a->x0, a->c0, a->x0_batch_stride, a->c0_batch_stride, act(AIN), per_image);
+        ADC_CUDA(cudaGetLastError());
+    }
+    RUN(layer(0, AIN, -1, A0));
+    RUN(layer(1, A0, -1, A1));
+    RUN(layer(2, A1, -1, A2));
     RUN(pool(A2, P1, 0));
-    { adc_src_t s = src_of(P1); out_of(A3, y, c); RUN(layer(3, s, nullptr, y, c)); }
-    { adc_src_t s = src_of(A3); out_of(A4, y, c); RUN(layer(4, s, nullptr, y, c)); }
+    RUN(layer(3, P1, -1, A3));
+    RUN(layer(4, A3, -1, A4));
     RUN(pool(A4, P2, 1));
-    { adc_src_t s = src_of(P2); out_of(A5, y, c); RUN(layer(5, s, nullptr, y, c)); }
+    RUN(layer(5, P2, -1, A5));
     RUN(pool(A5, P3, 2));
-    { adc_src_t s = src_of(P3); out_of(A6, y, c); RUN(layer(6, s, nullptr, y, c)); }
-    { adc_src_t s = src_of(A5), u = src_of(A6); out_of(A7, y, c); RUN(layer(7, s, &u, y, c)); }   // nconv4: cat(x3_ds, up(x4_ds))
-    { adc_src_t s = src_of(A4), u = src_of(A7); out_of(A8, y, c); RUN(layer(8, s, &u, y, c)); }   // nconv5: cat(x2_ds, up(x34_ds))
-    { adc_src_t u = src_of(A8), s = src_of(A2); out_of(A9, y, c); RUN(layer(9, u, &s, y, c)); }   // nconv6: cat(up(x23_ds), x1)
-    { adc_src_t s = src_of(A9); RUN(layer(10, s, nullptr, a->xout, a->cout)); }
+    RUN(layer(6, P3, -1, A6));
+    RUN(layer(7, A5, A6, A7));   // nconv4: cat(x3_ds, up(x4_ds))
+    RUN(layer(8, A4, A7, A8));   // nconv5: cat(x2_ds, up(x34_ds))
+    RUN(layer(9, A8, A2, A9));   // nconv6: cat(up(x23_ds), x1)  -- upsampled FIRST (model_zoo/nconv_sd.py:94)
+    {
+        const long long plane = (long long)a->H * a->W;
+        dim3 grid(blocks_1x1(plane), g.N);
+        nconv_1x1_fwd_kernel<<<grid, 256, 0, st>>>(act(A9), a->xout, a->cout, plane, wimg_index(a->slot, 0, 10));
+        ADC_CUDA(cudaGetLastError());
+    }
 #undef RUN
     return 0;
 }
 
-// backward scratch: [bwd images][partials per call][gradient buffers per level][upsample scratch]
+// backward scratch: [bwd images][wpart per call][bpart per call][G buffers per level][layer-res raw grads of upsampled sources]
 namespace adc {
 struct BwdLayout {
-    long long img, partial[ADC_PYR_CALLS], gbuf[4][4], up[3], total;
-    int nblk[ADC_PYR_CALLS];
+    long long img, wpart[ADC_PYR_CALLS], bpart[ADC_PYR_CALLS], gbuf[4][4], up[3], total;
+    int wblk[ADC_PYR_CALLS], bblk[ADC_PYR_CALLS];
     explicit BwdLayout(const Geo& g) {
         long long o = 0;
         img = o; o += kImgFloats;
+        auto pool_blocks = [&](int l) { return (int)ceil_div_ll(2LL * g.N * ((g.h[l] + 1) / 2) * ((g.w[l] + 1) / 2), 256); };
+        auto red_blocks = [&](int l) { return (int)ceil_div_ll(2 * g.px[l], 256); };
+        const int b1 = g.N * blocks_1x1((long long)g.h[0] * g.w[0]);
+        // who finalises the raw gradient of each call's output (see adc_pyramid_bwd)
+        bblk[10] = b1; bblk[9] = b1;
+        bblk[8] = red_blocks(1); bblk[7] = red_blocks(2); bblk[6] = red_blocks(3);
+        bblk[5] = pool_blocks(2); bblk[4] = pool_blocks(1); bblk[2] = pool_blocks(0);
+        bblk[3] = tiles(g.N, g.h[1], g.w[1]); bblk[1] = tiles(g.N, g.h[0], g.w[0]); bblk[0] = tiles(g.N, g.h[0], g.w[0]);
         for (int k = 0; k < ADC_PYR_CALLS; ++k) {
-            const int m = kCallModule[k], l = kCallLevel[k];
-            nblk[k] = wg_blocks(g.N, kModCo[m], g.h[l], g.w[l]);
-            partial[k] = o; o += (long long)nblk[k] * kWStride;
+            const int l = kCallLevel[k];
+            wblk[k] = k == 10 ? b1 : tiles(g.N, g.h[l], g.w[l]);
+            wpart[k] = o; o += (long long)wblk[k] * kWStride;
+            bpart[k] = o; o += (long long)bblk[k] * 4;
         }
         for (int l = 0; l < 4; ++l)
-            for (int b = 0; b < 4; ++b) { gbuf[l][b] = o; o += 4 * g.px[l]; }   // (gx, gc) pair of [N,2,h,w]
-        for (int l = 0; l < 3; ++l) { up[l] = o; o += 4 * g.px[l]; }             // layer-resolution grads of an upsampled source
+            for (int b = 0; b < 4; ++b) { gbuf[l][b] = o; o += 4 * g.px[l]; }   // pair tensor [N,2,h,w]
+        for (int l = 0; l < 3; ++l) { up[l] = o; o += 4 * g.px[l]; }
         total = o;
     }
 };
@@ -449,117 +590,116 @@ size_t adc_pyramid_bwd_scratch_floats(int N, int H, int W) {
 }
 
 int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
-    ADC_CHECK_ARG(a && a->x0 && a->c0 && a->saved && a->idx && a->xout && a->cout && a->g_xout && a->g_cout && a->scratch,
-                  ADC_E_BADARG, "adc_pyramid_bwd: null pointer");
+    ADC_CHECK_ARG(a && a->saved && a->idx && a->xout && a->cout && a->g_xout && a->g_cout && a->scratch, ADC_E_BADARG,
+                  "adc_pyramid_bwd: null pointer");
     ADC_CHECK_ARG(a->N > 0 && a->H >= 8 && a->W >= 8, ADC_E_BADARG, "adc_pyramid_bwd: bad sizes");
     ADC_CHECK_ARG(a->slot >= 0 && a->slot < ADC_WSLOTS, ADC_E_BADARG, "adc_pyramid_bwd: slot out of range");
     ADC_CHECK_ARG(!a->need_input_grad || (a->gx0 && a->gc0), ADC_E_BADARG, "adc_pyramid_bwd: gx0/gc0 missing");
     ADC_CHECK_ARG(!a->need_weight_grad || (a->gweight && a->gbias), ADC_E_BADARG, "adc_pyramid_bwd: gweight/gbias missing");
-    ADC_CHECK_ARG(a->x0_batch_stride == a->c0_batch_stride, ADC_E_BADARG, "adc_pyramid_bwd: x0/c0 batch strides must match");
     for (int m = 0; m < ADC_PYR_MODULES; ++m)
         ADC_CHECK_ARG(a->weight_bwd[m] && a->bias[m], ADC_E_BADARG, "adc_pyramid_bwd: missing parameter %d", m);
+    int rc = ensure_init();
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     Geo g(a->N, a->H, a->W);
     SavedLayout L(g);
     BwdLayout B(g);
     const float* S = a->saved;
     float* X = a->scratch;
-    int rc;
+    const bool need_w = a->need_weight_grad != 0;
 
-    // forward images (b, s of each call) back into constant memory; backward-time weights, flipped, next to them
+    // forward images (b, s, 1/s of each call) back into constant memory; backward-time weights, flipped, next to them
     if ((rc = upload_images(S, a->slot, 0, 0, ADC_PYR_CALLS, st))) return rc;
     PrepArgs pa;
     memset(&pa, 0, sizeof(pa));
     for (int k = 0; k < ADC_PYR_CALLS; ++k) {
         const int m = kCallModule[k];
-        pa.call[k] = PrepCall{a->weight_bwd[m], a->bias[m], nullptr, kModCo[m], kModCi[m], kModK[m], 0, kModCo[m] == 2 ? 1 : 0,
-                              S + (size_t)k * kWStride};
+        pa.call[k] = PrepCall{a->weight_bwd[m], a->bias[m], nullptr, kModCo[m], kModCi[m], kModK[m], 0, 1, S + (size_t)k * kWStride};
     }
     pa.img = X + B.img;
     prep_weights_kernel<<<ADC_PYR_CALLS, 128, 0, st>>>(pa);
     ADC_CUDA(cudaGetLastError());
     if ((rc = upload_images(X + B.img, a->slot, 1, 0, ADC_PYR_CALLS, st))) return rc;
 
-    auto actp = [&](int id) { return S + L.off[id]; };
-    auto src_of = [&](int id) {
-        const int l = kActLevel[id];
-        return mk_src(actp(id), g.px[l], g.N, 2, g.h[l], g.w[l]);
+    auto act = [&](int id) { return reinterpret_cast<const float2*>(S + L.off[id]); };
+    auto src_of = [&](int id, int lvl) {
+        const int l = kActLevel[id], ch = kActCh[id];
+        return make_srcp(act(id), (long long)ch * g.h[l] * g.w[l], ch, g.h[l], g.w[l], g.h[lvl], g.w[lvl]);
     };
-    auto gb = [&](int l, int b) { return X + B.gbuf[l][b]; };
-    const bool need_w = a->need_weight_grad != 0;
-
-    // one layer backward.  gin: (gy, gcout) buffer of the layer output; outputs go to (gx0,gc0)/(gx1,gc1)
-    auto layer_bwd = [&](int call, const adc_src_t& a0, const adc_src_t* a1, const float* yv, const float* cv, const float* gyv,
-                         const float* gcv, float* gx0, float* gc0, float* gx1, float* gc1, bool need_data) -> int {
+    auto gb = [&](int l, int b) { return reinterpret_cast<float2*>(X + B.gbuf[l][b]); };
+    auto upb = [&](int l) { return reinterpret_cast<float2*>(X + B.up[l]); };
+    auto fimg = [&](int call) { return wimg_index(a->slot, 0, call); };
+    auto bimg = [&](int call) { return wimg_index(a->slot, 1, call); };
+    // one layer: G (transformed gradient of the call's output) -> weight partials + gradients of its sources
+    auto layer_bwd = [&](int call, const float2* G, int in0, int in1, float2* out0, float2* out1, int xcall, bool need_data) -> int {
         const int m = kCallModule[call], l = kCallLevel[call];
-        Src s0 = make_src(&a0, g.h[l], g.w[l]), s1;
-        if (a1) s1 = make_src(a1, g.h[l], g.w[l]);
-        GradIn gi{yv, cv, gyv, gcv};
-        return run_layer_bwd(s0, a1 ? &s1 : nullptr, kModCi[m], kModCo[m], kModK[m], gi, gx0, gc0, gx1, gc1, X + B.partial[call],
-                             l < 3 ? X + B.up[l] : nullptr, g.N, g.h[l], g.w[l], wimg_index(a->slot, 0, call),
-                             wimg_index(a->slot, 1, call), need_data, need_w || kModCo[m] == 1, st);
+        SrcP gsrc = make_srcp(G, 2LL * g.h[l] * g.w[l], 2, g.h[l], g.w[l], g.h[l], g.w[l]);
+        SrcP s0 = src_of(in0, l), s1;
+        if (in1 >= 0) s1 = src_of(in1, l);
+        int r = 0;
+        if (need_w && (r = dispatch_bwd_weight(kModCi[m], kModK[m], gsrc, s0, in1 >= 0 ? &s1 : nullptr, X + B.wpart[call], g.N, g.h[l],
+                                               g.w[l], st)))
+            return r;
+        if (need_data)
+            r = dispatch_bwd_data(kModCi[m], kModK[m], gsrc, s0, in1 >= 0 ? &s1 : nullptr, out0, out1,
+                                  xcall >= 0 ? X + B.bpart[xcall] : nullptr, g.N, g.h[l], g.w[l], bimg(call),
+                                  xcall >= 0 ? fimg(xcall) : -1, st);
+        return r;
     };
-    auto yc = [&](int id, const float*& y, const float*& c) { y = actp(id); c = actp(id) + 2 * g.px[kActLevel[id]]; };
-    auto gpair = [&](int l, int b, float*& gx, float*& gc) { gx = gb(l, b); gc = gb(l, b) + 2 * g.px[l]; };
+    auto reduce_up = [&](int lvl, int act_id, int xcall, float2* G) -> int {   // raw grads in up[lvl] -> G of call `xcall`
+        SrcP s = src_of(act_id, lvl);
+        return run_upsample_bwd(upb(lvl), s, G, X + B.bpart[xcall], g.N, g.h[lvl], g.w[lvl], fimg(xcall), st);
+    };
     long long ioff[3]; int ihs[3], iws[3];
     adc_pyramid_idx_layout(g.N, a->H, a->W, ioff, ihs, iws);
+    auto pool_bwd = [&](int lvl, const float2* g_ds, const float2* skip, int act_id, int xcall, float2* G) -> int {
+        const int H = g.h[lvl], W = g.w[lvl];
+        const long long planes = 2LL * g.N, total = planes * ((H + 1) / 2) * ((W + 1) / 2);
+        pair_pool_bwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(g_ds, a->idx + ioff[lvl], skip, act(act_id), G,
+                                                                            X + B.bpart[xcall], 2, H, W, g.h[lvl + 1], g.w[lvl + 1],
+                                                                            planes, fimg(xcall));
+        return check_cuda(cudaGetLastError(), "pair_pool_bwd_kernel launch");
+    };
 #define RUN(expr) do { rc = (expr); if (rc) return rc; } while (0)
-    const float *y, *c;
-    float *gx, *gc, *hx, *hc, *kx, *kc;
-
-    // call 10: nconv7 on A9 -> grads of A9 in gbuf[0][0]
-    gpair(0, 0, gx, gc);
-    { adc_src_t s = src_of(A9); RUN(layer_bwd(10, s, nullptr, a->xout, a->cout, a->g_xout, a->g_cout, gx, gc, nullptr, nullptr, true)); }
-    // call 9: nconv6 on cat(up(A8), A2): grads of A8 (L1) -> gbuf[1][0], skip grads of A2 -> gbuf[0][2]
-    yc(A9, y, c);
-    gpair(1, 0, hx, hc); gpair(0, 2, kx, kc);
-    { adc_src_t u = src_of(A8), s = src_of(A2); RUN(layer_bwd(9, u, &s, y, c, gx, gc, hx, hc, kx, kc, true)); }
-    // call 8: nconv5 on cat(A4, up(A7)): skip grads of A4 -> gbuf[1][2], grads of A7 (L2) -> gbuf[2][0]
-    yc(A8, y, c);
-    gpair(1, 2, gx, gc); gpair(2, 0, kx, kc);
-    { adc_src_t s = src_of(A4), u = src_of(A7); RUN(layer_bwd(8, s, &u, y, c, hx, hc, gx, gc, kx, kc, true)); }
-    // call 7: nconv4 on cat(A5, up(A6)): skip grads of A5 -> gbuf[2][2], grads of A6 (L3) -> gbuf[3][0]
-    yc(A7, y, c);
-    gpair(2, 2, gx, gc); gpair(3, 0, hx, hc);
-    { adc_src_t s = src_of(A5), u = src_of(A6); RUN(layer_bwd(7, s, &u, y, c, kx, kc, gx, gc, hx, hc, true)); }
-    // call 6: nconv2 @L3 on P3 -> grads of P3 in gbuf[3][1]
-    yc(A6, y, c);
-    gpair(3, 1, gx, gc);
-    { adc_src_t s = src_of(P3); RUN(layer_bwd(6, s, nullptr, y, c, hx, hc, gx, gc, nullptr, nullptr, true)); }
-    // pool3 backward (+ skip grads of A5) -> grads of A5 in gbuf[2][1]
-    gpair(2, 2, kx, kc); gpair(2, 1, hx, hc);
-    RUN(adc_conf_pool_bwd(gx, gc, a->idx + ioff[2], kx, kc, hx, hc, g.N, 2, g.h[2], g.w[2], stream));
-    // call 5: nconv2 @L2 on P2 -> grads of P2 in gbuf[2][3]
-    yc(A5, y, c);
-    gpair(2, 3, gx, gc);
-    { adc_src_t s = src_of(P2); RUN(layer_bwd(5, s, nullptr, y, c, hx, hc, gx, gc, nullptr, nullptr, true)); }
-    // pool2 backward (+ skip grads of A4 in gbuf[1][2]) -> grads of A4 in gbuf[1][1]
-    gpair(1, 2, kx, kc); gpair(1, 1, hx, hc);
-    RUN(adc_conf_pool_bwd(gx, gc, a->idx + ioff[1], kx, kc, hx, hc, g.N, 2, g.h[1], g.w[1], stream));
-    // call 4: nconv3 @L1 on A3 -> gbuf[1][3];  call 3: nconv2 @L1 on P1 -> gbuf[1][0]
-    yc(A4, y, c);
-    gpair(1, 3, gx, gc);
-    { adc_src_t s = src_of(A3); RUN(layer_bwd(4, s, nullptr, y, c, hx, hc, gx, gc, nullptr, nullptr, true)); }
-    yc(A3, y, c);
-    gpair(1, 0, hx, hc);
-    { adc_src_t s = src_of(P1); RUN(layer_bwd(3, s, nullptr, y, c, gx, gc, hx, hc, nullptr, nullptr, true)); }
-    // pool1 backward (+ skip grads of A2 in gbuf[0][2]) -> grads of A2 in gbuf[0][1]
-    gpair(0, 2, kx, kc); gpair(0, 1, gx, gc);
-    RUN(adc_conf_pool_bwd(hx, hc, a->idx + ioff[0], kx, kc, gx, gc, g.N, 2, g.h[0], g.w[0], stream));
-    // call 2: nconv3 @L0 on A1 -> gbuf[0][0];  call 1: nconv2 @L0 on A0 -> gbuf[0][3];  call 0: nconv1 on (x0, c0)
-    yc(A2, y, c);
-    gpair(0, 0, hx, hc);
-    { adc_src_t s = src_of(A1); RUN(layer_bwd(2, s, nullptr, y, c, gx, gc, hx, hc, nullptr, nullptr, true)); }
-    yc(A1, y, c);
-    gpair(0, 3, gx, gc);
-    { adc_src_t s = src_of(A0); RUN(layer_bwd(1, s, nullptr, y, c, hx, hc, gx, gc, nullptr, nullptr, true)); }
-    yc(A0, y, c);
+    // call 10 (nconv7 1x1 head): raw autograd gradients -> G of call 9 in gbuf[0][0]
     {
-        adc_src_t in0;
-        in0.x = a->x0; in0.c = a->c0; in0.batch_stride = a->x0_batch_stride; in0.channels = 1; in0.H = a->H; in0.W = a->W;
+        const long long plane = (long long)a->H * a->W;
+        dim3 grid(blocks_1x1(plane), g.N);
+        nconv_1x1_bwd_kernel<<<grid, 256, 0, st>>>(act(A9), a->xout, a->cout, a->g_xout, a->g_cout, gb(0, 0), X + B.wpart[10],
+                                                  X + B.bpart[10], X + B.bpart[9], plane, fimg(10), bimg(10), fimg(9));
+        ADC_CUDA(cudaGetLastError());
+    }
+    // call 9 (nconv6 on cat(up(A8), A2)): raw grads of up(A8) -> up[0] -> reduce -> G8 in gbuf[1][0]; skip grads of A2 -> gbuf[0][2]
+    RUN(layer_bwd(9, gb(0, 0), A8, A2, upb(0), gb(0, 2), -1, true));
+    RUN(reduce_up(0, A8, 8, gb(1, 0)));
+    // call 8 (nconv5 on cat(A4, up(A7))): skip grads of A4 -> gbuf[1][2]; up(A7) -> up[1] -> G7 in gbuf[2][0]
+    RUN(layer_bwd(8, gb(1, 0), A4, A7, gb(1, 2), upb(1), -1, true));
+    RUN(reduce_up(1, A7, 7, gb(2, 0)));
+    // call 7 (nconv4 on cat(A5, up(A6))): skip grads of A5 -> gbuf[2][2]; up(A6) -> up[2] -> G6 in gbuf[3][0]
+    RUN(layer_bwd(7, gb(2, 0), A5, A6, gb(2, 2), upb(2), -1, true));
+    RUN(reduce_up(2, A6, 6, gb(3, 0)));
+    // call 6 (nconv2 @L3 on P3): raw grads of P3 -> gbuf[3][1]; pool3 backward (+ skip of A5) -> G5 in gbuf[2][1]
+    RUN(layer_bwd(6, gb(3, 0), P3, -1, gb(3, 1), nullptr, -1, true));
+    RUN(pool_bwd(2, gb(3, 1), gb(2, 2), A5, 5, gb(2, 1)));
+    // call 5 (nconv2 @L2 on P2): raw grads of P2 -> gbuf[2][3]; pool2 backward (+ skip of A4) -> G4 in gbuf[1][1]
+    RUN(layer_bwd(5, gb(2, 1), P2, -1, gb(2, 3), nullptr, -1, true));
+    RUN(pool_bwd(1, gb(2, 3), gb(1, 2), A4, 4, gb(1, 1)));
+    // call 4 (nconv3 @L1 on A3): G3 in gbuf[1][3];  call 3 (nconv2 @L1 on P1): raw grads of P1 -> gbuf[1][0]
+    RUN(layer_bwd(4, gb(1, 1), A3, -1, gb(1, 3), nullptr, 3, true));
+    RUN(layer_bwd(3, gb(1, 3), P1, -1, gb(1, 0), nullptr, -1, true));
+    // pool1 backward (+ skip of A2) -> G2 in gbuf[0][1]
+    RUN(pool_bwd(0, gb(1, 0), gb(0, 2), A2, 2, gb(0, 1)));
+    // call 2 (nconv3 @L0 on A1): G1 in gbuf[0][0];  call 1 (nconv2 @L0 on A0): G0 in gbuf[0][3];  call 0 (nconv1 on the input)
+    RUN(layer_bwd(2, gb(0, 1), A1, -1, gb(0, 0), nullptr, 1, true));
+    RUN(layer_bwd(1, gb(0, 0), A0, -1, gb(0, 3), nullptr, 0, true));
+    {
         const bool nd = a->need_input_grad != 0;
-        if (nd || need_w)
-            RUN(layer_bwd(0, in0, nullptr, y, c, gx, gc, nd ? a->gx0 : nullptr, nd ? a->gc0 : nullptr, nullptr, nullptr, nd));
+        if (nd || need_w) RUN(layer_bwd(0, gb(0, 3), AIN, -1, gb(0, 1), nullptr, -1, nd));
+        if (nd) {
+            const long long total = g.px[0];
+            unpack_pairs_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(gb(0, 1), a->gx0, a->gc0, total);
+            ADC_CUDA(cudaGetLastError());
+        }
     }
 #undef RUN
     if (need_w) {
@@ -567,7 +707,7 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
         memset(&ra, 0, sizeof(ra));
         for (int k = 0; k < ADC_PYR_CALLS; ++k) {
             const int m = kCallModule[k];
-            ra.call[k] = WgReduceCall{X + B.partial[k], B.nblk[k], m, kModCo[m], mod_numel(m)};
+            ra.call[k] = WgReduceCall{X + B.wpart[k], X + B.bpart[k], B.wblk[k], B.bblk[k], m, kModCo[m], mod_numel(m)};
         }
         ra.ncalls = ADC_PYR_CALLS;
         long long bo = 0;

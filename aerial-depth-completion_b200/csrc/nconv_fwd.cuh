@@ -1,284 +1,247 @@
-// K1: fused NConv2d forward (model_zoo/nconv.py:37-67) for sm_100a.
+// K1: fused NConv2d forward (model_zoo/nconv.py:37-67) for sm_100a, on pair tensors (see adc_common.cuh).
 //
-// One CTA = one 64x32 output tile of one image, all channels.  The c and x*c tiles (+halo) of every
-// input channel are staged in shared memory as separate planes; each thread owns a 4x4 output patch and
-// keeps, for both output channels, the confidence sum D and the numerator Nm in registers as float2
-// {co0,co1} pairs, so one packed FFMA2 (sm_100 fma.rn.f32x2) does two FMAs: the input scalar is the
-// broadcast operand, the weight pair {w[co0],w[co1]} comes from constant memory through a uniform register.
-// Epilogue: y = Nm*rcp(D+eps)+b (SFU reciprocal, <=1 ulp; D+eps >= 1e-20 is never denormal) and cout = D*(1/s)
-// with 1/s computed once per call by IEEE division -- monotone in D, so the pooled argmax downstream sees the
-// same ordering as D/s; coalesced float4 stores.
-// A source whose (H,W) differs from the layer size is read through ATen's nearest-neighbour map, which
-// folds F.interpolate + torch.cat (model_zoo/nconv_sd.py:81-94) into the tile loader.
+// One CTA = one 64x32 output tile of one image, all channels.  The {x,c} tile (+halo) of every input channel is
+// brought into shared memory by ONE TMA box copy per channel (cp.async.bulk.tensor, hardware zero fill outside the
+// image = the convolution's zero padding; mbarrier completion), or -- for a source that is read through ATen's
+// nearest-neighbour map, which folds F.interpolate + torch.cat (model_zoo/nconv_sd.py:81-94) into the loader, or whose
+// row pitch TMA cannot describe -- by batched 8-byte gathers.  Each thread owns a 2-wide x 8-tall output patch:
+// a warp then reads 512 contiguous bytes per LDS.128 (no bank conflicts) and keeps {Nm, D} of both output channels
+// in 32 float2 accumulators; one packed FFMA2 per (tap, pixel, channel) with the weight as the uniform-register
+// broadcast operand.  Epilogue: y = Nm*rcp(D+eps)+b (SFU reciprocal, <=1 ulp; D+eps >= 1e-20 is never denormal)
+// and cout = D*(1/s), 1/s computed once per call by IEEE division -- monotone in D, so the pooled argmax downstream
+// sees the ordering D/s would give; one coalesced STG.128 {y0,c0,y1,c1} per (channel,row) and thread.
 #pragma once
 #include "adc_common.cuh"
+#include "tma.cuh"
 
 namespace adc {
 
-template <int CI, int K>
-struct FwdCfg {
+template <int K>
+struct TileCfg {
     static constexpr int P = K / 2;
     static constexpr int TW = 64, TH = 32, NT = 128;
-    static constexpr int SW = TW + 2 * P;
-    static constexpr int PITCH = (SW + 3) & ~3;
+    // A TMA box must start on a 16-byte boundary of the innermost dimension (measured: an odd pair offset raises
+    // 'illegal instruction'), so for odd halos the tile keeps XOFF spare pair(s) on the left.
+    static constexpr int XOFF = P & 1;
+    static constexpr int SWP = (TW + 2 * P + 2 * XOFF + 3) & ~3;            // pairs per tile row (= TMA box width)
     static constexpr int SH = TH + 2 * P;
-    static constexpr int PLANE = PITCH * SH;
-    static constexpr int SMEM_BYTES = CI * 2 * PLANE * 4;
+    static constexpr int PLANE_BYTES = ((SH * SWP * 8 + 127) / 128) * 128;  // TMA destinations are 128-B aligned
+    static constexpr int PLANE = PLANE_BYTES / 8;                           // in pairs
+    static constexpr int smem_bytes(int planes) { return planes * PLANE_BYTES + 128 + 16; }
 };
 
-template <int P>
-__device__ __forceinline__ void sts4(float* dst, float4 v) {
-    if constexpr (P % 4 == 0) {
-        *reinterpret_cast<float4*>(dst) = v;
-    } else if constexpr (P % 2 == 0) {
-        *reinterpret_cast<float2*>(dst) = make_float2(v.x, v.y);
-        *reinterpret_cast<float2*>(dst + 2) = make_float2(v.z, v.w);
-    } else {
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-    }
+struct Maps2 {
+    CUtensorMap m0, m1;
+};
+
+__device__ __forceinline__ float2* align128(void* p) {
+    return reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
 }
 
-// Stage planes {c, x*c} of one source channel into shared memory (zero outside the image = conv zero padding).
-template <int K, int CI>
-__device__ __forceinline__ void load_channel_tile(const Src& s, int sc, int n, int h0, int w0, int H, int W,
-                                                  float* smc, float* smx, int tid) {
-    using C = FwdCfg<CI, K>;
-    constexpr int P = C::P;
-    const float* xp = s.x + (long long)n * s.bs + (long long)sc * s.H * s.W;
-    const float* cp = s.c + (long long)n * s.bs + (long long)sc * s.H * s.W;
-    const bool vec = !s.up && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(xp) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
-    if (vec) {
-        constexpr int Q = C::TW / 4;
-        for (int i = tid; i < C::SH * Q; i += C::NT) {
-            const int r = i / Q, q = i % Q;
-            const int gh = h0 - P + r, gw = w0 + q * 4;
-            float4 cv = make_float4(0.f, 0.f, 0.f, 0.f), xv = cv;
-            if (gh >= 0 && gh < H && gw < W) {
-                cv = __ldg(reinterpret_cast<const float4*>(cp + (long long)gh * W + gw));
-                xv = __ldg(reinterpret_cast<const float4*>(xp + (long long)gh * W + gw));
-            }
-            sts4<P>(smc + r * C::PITCH + P + q * 4, cv);
-            sts4<P>(smx + r * C::PITCH + P + q * 4, make_float4(xv.x * cv.x, xv.y * cv.y, xv.z * cv.z, xv.w * cv.w));
+// Batched gather of one channel tile (generic path: upsampled / unaligned sources).  Four independent 8-byte loads are
+// issued per thread before any is consumed, so the loop is not serialised on DRAM latency.
+template <int K, int NT>
+__device__ __forceinline__ void gather_pair_tile(const SrcP& s, int sc, int n, int h0, int w0, int H, int W, float2* dst,
+                                                 int tid) {
+    using C = TileCfg<K>;
+    constexpr int P = C::P, TOTAL = C::SH * C::SWP, U = 4;
+    const float2* base = s.p + (long long)n * s.bs + (long long)sc * s.H * s.W;
+    for (int i0 = tid; i0 < TOTAL; i0 += NT * U) {
+        float2 v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int i = i0 + j * NT;
+            const int r = i / C::SWP, col = i - r * C::SWP;
+            const int gh = h0 - P + r, gw = w0 - P - C::XOFF + col;
+            const bool ok = i < TOTAL && gh >= 0 && gh < H && gw >= 0 && gw < W;
+            const long long off = ok ? (long long)s.mh(gh) * s.W + s.mw(gw) : 0;
+            const float2 t = __ldg(base + off);
+            v[j] = ok ? t : make_float2(0.f, 0.f);
         }
-        if constexpr (P > 0) {
-            for (int i = tid; i < C::SH * 2 * P; i += C::NT) {
-                const int r = i / (2 * P), j = i % (2 * P);
-                const int col = j < P ? j : C::TW + j;
-                const int gh = h0 - P + r, gw = w0 - P + col;
-                float cv = 0.f, xv = 0.f;
-                if (gh >= 0 && gh < H && gw >= 0 && gw < W) {
-                    cv = __ldg(cp + (long long)gh * W + gw);
-                    xv = __ldg(xp + (long long)gh * W + gw);
-                }
-                smc[r * C::PITCH + col] = cv;
-                smx[r * C::PITCH + col] = xv * cv;
-            }
-        }
-    } else {
-        for (int i = tid; i < C::SH * C::SW; i += C::NT) {
-            const int r = i / C::SW, col = i % C::SW;
-            const int gh = h0 - P + r, gw = w0 - P + col;
-            float cv = 0.f, xv = 0.f;
-            if (gh >= 0 && gh < H && gw >= 0 && gw < W) {
-                const long long off = (long long)s.mh(gh) * s.W + s.mw(gw);
-                cv = __ldg(cp + off);
-                xv = __ldg(xp + off);
-            }
-            smc[r * C::PITCH + col] = cv;
-            smx[r * C::PITCH + col] = xv * cv;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int i = i0 + j * NT;
+            if (i < TOTAL) dst[i] = v[j];
         }
     }
 }
 
-// The shared compute core: for a thread's 4x4 patch, accumulate two correlations at once --
-// accA += sum_{n,u,v} planeA[n] * w2[n,u,v] and accB += sum planeB[n] * w2[n,u,v] -- where each accumulator
-// and each weight is a float2 over a PAIR of output channels (packed FFMA2) and the plane values are the
-// broadcast scalar operand.  Forward: planes {c, x*c}, pairs {co0,co1}.  Data-gradient: planes {gD, gNm},
-// flipped weights, pairs {ci0,ci1}.  Plane n lives at smem + (2n)*PLANE (A) and (2n+1)*PLANE (B).
-template <int NIN, int K>
-__device__ __forceinline__ void conv_patch(const float* smem, const float2* __restrict__ wp, int tx, int ty,
-                                           float2 (&accA)[4][4], float2 (&accB)[4][4]) {
-    using C = FwdCfg<NIN, K>;
+// Stage all input-channel tiles of up to two sources.  Returns true if a TMA transaction is pending on `bar`.
+template <int K, int NT>
+__device__ __forceinline__ bool stage_sources(const Maps2& maps, const SrcP& s0, const SrcP& s1, bool has1, int n, int h0, int w0,
+                                              int H, int W, float2* planes, uint64_t* bar, int tid) {
+    using C = TileCfg<K>;
+    const bool any_tma = s0.tma || (has1 && s1.tma);
+    if (any_tma) {
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const int nplanes = (s0.tma ? s0.ch : 0) + ((has1 && s1.tma) ? s1.ch : 0);
+            mbar_expect_tx(bar, (uint32_t)(nplanes * C::SH * C::SWP * 8));
+            if (s0.tma)
+                for (int c = 0; c < s0.ch; ++c)
+                    tma_load_plane(planes + c * C::PLANE, &maps.m0, bar, 2 * (w0 - C::P - C::XOFF), h0 - C::P, c, n);
+            if (has1 && s1.tma)
+                for (int c = 0; c < s1.ch; ++c)
+                    tma_load_plane(planes + (s0.ch + c) * C::PLANE, &maps.m1, bar, 2 * (w0 - C::P - C::XOFF), h0 - C::P, c, n);
+        }
+    }
+    if (!s0.tma)
+        for (int c = 0; c < s0.ch; ++c) gather_pair_tile<K, NT>(s0, c, n, h0, w0, H, W, planes + c * C::PLANE, tid);
+    if (has1 && !s1.tma)
+        for (int c = 0; c < s1.ch; ++c) gather_pair_tile<K, NT>(s1, c, n, h0, w0, H, W, planes + (s0.ch + c) * C::PLANE, tid);
+    return any_tma;
+}
+
+// The shared compute core.  For a thread's 2x8 patch and NOUT output maps:
+//   acc[no][row][px] += sum_{ni,u,v} in[ni](row+u, px+v) * w[(no*NIN+ni)*K*K + u*K + v]
+// where `in` and `acc` are float2 pairs (two correlations per packed FFMA2) and w is a broadcast scalar from constant
+// memory.  MULX turns a stored {x, c} pair into {x*c, c} on the fly (forward); the backward feeds {GN, GD} as is.
+template <int NIN, int NOUT, int K, bool MULX>
+__device__ __forceinline__ void conv_patch(const float2* planes, const float* __restrict__ w, int tx, int ty,
+                                           float2 (&acc)[NOUT][8][2]) {
+    using C = TileCfg<K>;
+    constexpr int XO = C::XOFF;
+    constexpr int NP = (2 + K - 1 + XO + 1) & ~1;   // pairs loaded per window row, from an even (16-byte aligned) offset
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int no = 0; no < NOUT; ++no)
 #pragma unroll
-        for (int p = 0; p < 4; ++p) accA[r][p] = accB[r][p] = make_float2(0.f, 0.f);
+        for (int r = 0; r < 8; ++r) acc[no][r][0] = acc[no][r][1] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int ci = 0; ci < NIN; ++ci) {
-        const float* sa = smem + (ci * 2) * C::PLANE + (ty * 4) * C::PITCH + tx * 4;
-        const float* sb = sa + C::PLANE;
+    for (int ni = 0; ni < NIN; ++ni) {
+        const float2* row0 = planes + ni * C::PLANE + (ty * 8) * C::SWP + tx * 2;
 #pragma unroll
-        for (int ir = 0; ir < 4 + K - 1; ++ir) {
-            float aw[8], bw[8];
-            {
-                const float4 a = *reinterpret_cast<const float4*>(sa + ir * C::PITCH);
-                const float4 b = *reinterpret_cast<const float4*>(sb + ir * C::PITCH);
-                aw[0] = a.x; aw[1] = a.y; aw[2] = a.z; aw[3] = a.w;
-                bw[0] = b.x; bw[1] = b.y; bw[2] = b.z; bw[3] = b.w;
-                if constexpr (K == 5) {
-                    const float4 a2 = *reinterpret_cast<const float4*>(sa + ir * C::PITCH + 4);
-                    const float4 b2 = *reinterpret_cast<const float4*>(sb + ir * C::PITCH + 4);
-                    aw[4] = a2.x; aw[5] = a2.y; aw[6] = a2.z; aw[7] = a2.w;
-                    bw[4] = b2.x; bw[5] = b2.y; bw[6] = b2.z; bw[7] = b2.w;
-                } else if constexpr (K == 3) {
-                    const float2 a2 = *reinterpret_cast<const float2*>(sa + ir * C::PITCH + 4);
-                    const float2 b2 = *reinterpret_cast<const float2*>(sb + ir * C::PITCH + 4);
-                    aw[4] = a2.x; aw[5] = a2.y;
-                    bw[4] = b2.x; bw[5] = b2.y;
-                }
+        for (int ir = 0; ir < 8 + K - 1; ++ir) {
+            float2 in[NP];
+#pragma unroll
+            for (int t = 0; t < NP / 2; ++t) {
+                const float4 a = *reinterpret_cast<const float4*>(row0 + ir * C::SWP + 2 * t);
+                in[2 * t] = make_float2(a.x, a.y);
+                in[2 * t + 1] = make_float2(a.z, a.w);
+            }
+            if constexpr (MULX) {
+#pragma unroll
+                for (int t = 0; t < NP; ++t) in[t].x *= in[t].y;
             }
 #pragma unroll
-            for (int orow = 0; orow < 4; ++orow) {
+            for (int orow = 0; orow < 8; ++orow) {
                 const int u = ir - orow;
                 if (u >= 0 && u < K) {
 #pragma unroll
-                    for (int v = 0; v < K; ++v) {
-                        const float2 w2 = wp[(ci * K + u) * K + v];
+                    for (int v = 0; v < K; ++v)
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            accA[orow][p] = ffma2(bcast(aw[p + v]), w2, accA[orow][p]);
-                            accB[orow][p] = ffma2(bcast(bw[p + v]), w2, accB[orow][p]);
+                        for (int no = 0; no < NOUT; ++no) {
+                            const float wv = w[(no * NIN + ni) * K * K + u * K + v];
+                            acc[no][orow][0] = ffma2(in[XO + v], bcast(wv), acc[no][orow][0]);
+                            acc[no][orow][1] = ffma2(in[XO + v + 1], bcast(wv), acc[no][orow][1]);
                         }
-                    }
                 }
             }
         }
     }
 }
 
-// CO is fixed to 2 here (float2 output-channel pairs); the 1x1 2->1 head has its own kernel below.
+// Co = 2 (the float4 store packs two pixels of one channel); the 1x1 2->1 head has its own kernel below.
 template <int CI, int K>
-__global__ void __launch_bounds__(128) nconv_fwd_kernel(Src s0, Src s1, float* __restrict__ y, float* __restrict__ cout,
-                                                        int H, int W, int wimg) {
-    using C = FwdCfg<CI, K>;
-    constexpr int P = C::P;
-    extern __shared__ __align__(16) float smem[];
+__global__ void __launch_bounds__(128) nconv_fwd_kernel(const __grid_constant__ Maps2 maps, SrcP s0, SrcP s1, int has1,
+                                                        float2* __restrict__ out, int H, int W, int wimg) {
+    using C = TileCfg<K>;
+    extern __shared__ uint8_t smem_raw[];
+    float2* planes = align128(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(planes + CI * C::PLANE);
     const int tid = threadIdx.x;
     const int n = blockIdx.z, h0 = blockIdx.y * C::TH, w0 = blockIdx.x * C::TW;
     const float* wc = &c_wimg[0][0][0][0] + (size_t)wimg * kWStride;
 
-#pragma unroll
-    for (int ci = 0; ci < CI; ++ci) {
-        const bool first = ci < s0.ch;
-        load_channel_tile<K, CI>(first ? s0 : s1, first ? ci : ci - s0.ch, n, h0, w0, H, W,
-                                 smem + (ci * 2) * C::PLANE, smem + (ci * 2 + 1) * C::PLANE, tid);
-    }
+    const bool pending = stage_sources<K, 128>(maps, s0, s1, has1 != 0, n, h0, w0, H, W, planes, bar, tid);
     __syncthreads();
+    if (pending) mbar_wait(bar, 0);
 
-    const int tx = tid & 15, ty = tid >> 4;
-    const int oh = h0 + ty * 4, ow = w0 + tx * 4;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int oh = h0 + ty * 8, ow = w0 + tx * 2;
     if (oh >= H || ow >= W) return;
 
-    float2 accD[4][4], accN[4][4];
-    conv_patch<CI, K>(smem, reinterpret_cast<const float2*>(wc), tx, ty, accD, accN);
+    float2 acc[2][8][2];
+    conv_patch<CI, 2, K, true>(planes, wc, tx, ty, acc);
 
-    const float b0 = wc[kWBias], b1 = wc[kWBias + 1];
-    const float is0 = wc[kWInvSum], is1 = wc[kWInvSum + 1];
     const long long plane = (long long)H * W;
-    float* y0 = y + ((long long)n * 2) * plane;
-    float* c0 = cout + ((long long)n * 2) * plane;
-    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(cout) & 15) == 0);
+    const bool vec = (W & 1) == 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int h = oh + r;
-        if (h >= H) break;
-        float yv0[4], yv1[4], cv0[4], cv1[4];
+    for (int co = 0; co < 2; ++co) {
+        const float b = wc[kWBias + co], is = wc[kWInvSum + co];
+        float2* o = out + ((long long)n * 2 + co) * plane + ow;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            yv0[p] = fmaf(accN[r][p].x, rcp_approx(accD[r][p].x + kEps), b0);
-            yv1[p] = fmaf(accN[r][p].y, rcp_approx(accD[r][p].y + kEps), b1);
-            cv0[p] = accD[r][p].x * is0;
-            cv1[p] = accD[r][p].y * is1;
-        }
-        const long long o = (long long)h * W + ow;
-        if (vec) {  // W%4==0 and ow%4==0 => the whole float4 is inside the row
-            *reinterpret_cast<float4*>(y0 + o) = make_float4(yv0[0], yv0[1], yv0[2], yv0[3]);
-            *reinterpret_cast<float4*>(y0 + plane + o) = make_float4(yv1[0], yv1[1], yv1[2], yv1[3]);
-            *reinterpret_cast<float4*>(c0 + o) = make_float4(cv0[0], cv0[1], cv0[2], cv0[3]);
-            *reinterpret_cast<float4*>(c0 + plane + o) = make_float4(cv1[0], cv1[1], cv1[2], cv1[3]);
-        } else {
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                if (ow + p < W) {
-                    y0[o + p] = yv0[p];
-                    y0[plane + o + p] = yv1[p];
-                    c0[o + p] = cv0[p];
-                    c0[plane + o + p] = cv1[p];
-                }
+        for (int r = 0; r < 8; ++r) {
+            const int h = oh + r;
+            if (h >= H) break;
+            const float2 a0 = acc[co][r][0], a1 = acc[co][r][1];
+            const float2 r0 = make_float2(fmaf(a0.x, rcp_approx(a0.y + kEps), b), a0.y * is);
+            const float2 r1 = make_float2(fmaf(a1.x, rcp_approx(a1.y + kEps), b), a1.y * is);
+            if (vec) {
+                *reinterpret_cast<float4*>(o + (long long)h * W) = make_float4(r0.x, r0.y, r1.x, r1.y);
+            } else {
+                o[(long long)h * W] = r0;
+                if (ow + 1 < W) o[(long long)h * W + 1] = r1;
             }
         }
     }
 }
 
-// nconv7: 2 -> 1, 1x1 (model_zoo/nconv_sd.py:32).  Purely HBM-bound (AI 0.3): one float4 per thread per plane.
-__global__ void __launch_bounds__(256) nconv_1x1_c2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ c,
-                                                               long long bs, float* __restrict__ y,
-                                                               float* __restrict__ cout, long long plane, int wimg) {
+// nconv7: 2 -> 1, 1x1 (model_zoo/nconv_sd.py:32).  Reads the {x,c} pairs of both channels, writes the planar
+// xout / cout tensors the caller sees.  Purely HBM-bound (AI 0.3): two pixels per thread, 16-byte loads.
+__global__ void __launch_bounds__(256) nconv_1x1_fwd_kernel(const float2* __restrict__ in, float* __restrict__ y,
+                                                            float* __restrict__ cout, long long plane, int wimg) {
     const float* wc = &c_wimg[0][0][0][0] + (size_t)wimg * kWStride;
     const float w0 = wc[0], w1 = wc[1], b = wc[kWBias], is = wc[kWInvSum];
     const int n = blockIdx.y;
-    const float* x0 = x + (long long)n * bs;
-    const float* c0 = c + (long long)n * bs;
-    float* yo = y + (long long)n * plane;
-    float* co = cout + (long long)n * plane;
-    const bool vec = (plane % 4 == 0) && (bs % 4 == 0) &&
-                     (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(y) |
-                        reinterpret_cast<uintptr_t>(cout)) & 15) == 0);
-    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i4 >= plane) return;
-    float xa[4], xb[4], ca[4], cb[4], yv[4], cv[4];
-    if (vec) {
-        const float4 t0 = __ldg(reinterpret_cast<const float4*>(x0 + i4));
-        const float4 t1 = __ldg(reinterpret_cast<const float4*>(x0 + plane + i4));
-        const float4 t2 = __ldg(reinterpret_cast<const float4*>(c0 + i4));
-        const float4 t3 = __ldg(reinterpret_cast<const float4*>(c0 + plane + i4));
-        xa[0] = t0.x; xa[1] = t0.y; xa[2] = t0.z; xa[3] = t0.w;
-        xb[0] = t1.x; xb[1] = t1.y; xb[2] = t1.z; xb[3] = t1.w;
-        ca[0] = t2.x; ca[1] = t2.y; ca[2] = t2.z; ca[3] = t2.w;
-        cb[0] = t3.x; cb[1] = t3.y; cb[2] = t3.z; cb[3] = t3.w;
+    const float2* p0 = in + (long long)n * 2 * plane;
+    const float2* p1 = p0 + plane;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= plane) return;
+    const bool two = i + 1 < plane;
+    const bool even = (plane & 1) == 0;
+    float2 a0, a1, b0, b1;
+    if (two && even) {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p0 + i));
+        const float4 t1 = __ldg(reinterpret_cast<const float4*>(p1 + i));
+        a0 = make_float2(t0.x, t0.y); a1 = make_float2(t0.z, t0.w);
+        b0 = make_float2(t1.x, t1.y); b1 = make_float2(t1.z, t1.w);
     } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool ok = i4 + j < plane;
-            xa[j] = ok ? __ldg(x0 + i4 + j) : 0.f;
-            xb[j] = ok ? __ldg(x0 + plane + i4 + j) : 0.f;
-            ca[j] = ok ? __ldg(c0 + i4 + j) : 0.f;
-            cb[j] = ok ? __ldg(c0 + plane + i4 + j) : 0.f;
-        }
+        a0 = __ldg(p0 + i); b0 = __ldg(p1 + i);
+        a1 = two ? __ldg(p0 + i + 1) : make_float2(0.f, 0.f);
+        b1 = two ? __ldg(p1 + i + 1) : make_float2(0.f, 0.f);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float D = fmaf(w1, cb[j], w0 * ca[j]);
-        const float Nm = fmaf(w1, xb[j] * cb[j], w0 * (xa[j] * ca[j]));
-        yv[j] = fmaf(Nm, rcp_approx(D + kEps), b);
-        cv[j] = D * is;
-    }
-    if (vec) {
-        *reinterpret_cast<float4*>(yo + i4) = make_float4(yv[0], yv[1], yv[2], yv[3]);
-        *reinterpret_cast<float4*>(co + i4) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+    const float D0 = fmaf(w1, b0.y, w0 * a0.y), N0 = fmaf(w1, b0.x * b0.y, w0 * (a0.x * a0.y));
+    const float D1 = fmaf(w1, b1.y, w0 * a1.y), N1 = fmaf(w1, b1.x * b1.y, w0 * (a1.x * a1.y));
+    float* yo = y + (long long)n * plane + i;
+    float* co = cout + (long long)n * plane + i;
+    const float y0 = fmaf(N0, rcp_approx(D0 + kEps), b), y1 = fmaf(N1, rcp_approx(D1 + kEps), b);
+    if (two && even && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(cout)) & 7) == 0) {
+        *reinterpret_cast<float2*>(yo) = make_float2(y0, y1);
+        *reinterpret_cast<float2*>(co) = make_float2(D0 * is, D1 * is);
     } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (i4 + j < plane) {
-                yo[i4 + j] = yv[j];
-                co[i4 + j] = cv[j];
-            }
+        yo[0] = y0; co[0] = D0 * is;
+        if (two) { yo[1] = y1; co[1] = D1 * is; }
     }
 }
 
-template <int CI, int K>
-int launch_nconv_fwd(const Src& s0, const Src& s1, float* y, float* cout, int N, int H, int W, int wimg, cudaStream_t st) {
-    using C = FwdCfg<CI, K>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        ADC_CUDA(cudaFuncSetAttribute(nconv_fwd_kernel<CI, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_done = true;
-    }
-    dim3 grid(ceil_div(W, C::TW), ceil_div(H, C::TH), N);
-    nconv_fwd_kernel<CI, K><<<grid, C::NT, C::SMEM_BYTES, st>>>(s0, s1, y, cout, H, W, wimg);
-    return check_cuda(cudaGetLastError(), "nconv_fwd_kernel launch");
+// planar (x, c) [N,C,H,W] with batch strides  <->  pair tensor.  Used at the pyramid's entry (x0, c0 come from the caller
+// as separate tensors) and by the single-layer API.
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const float* __restrict__ x, const float* __restrict__ c, long long bsx,
+                                                         long long bsc, float2* __restrict__ out, long long per_image) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_image) return;
+    const int n = blockIdx.y;
+    out[(long long)n * per_image + i] = make_float2(__ldg(x + (long long)n * bsx + i), __ldg(c + (long long)n * bsc + i));
+}
+
+__global__ void __launch_bounds__(256) unpack_pairs_kernel(const float2* __restrict__ in, float* __restrict__ x,
+                                                           float* __restrict__ c, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float2 v = __ldg(in + i);
+    x[i] = v.x;
+    c[i] = v.y;
 }
 
 }  // namespace adc

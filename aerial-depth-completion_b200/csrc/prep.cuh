@@ -1,5 +1,5 @@
-// Weight preparation: EnforcePos softplus iteration (model_zoo/nconv.py:114-131), sum(w) (nconv.py:58-61) and
-// re-layout of the <=100 weights of each NConv2d call into the constant-memory image the kernels read.
+// Weight preparation: EnforcePos softplus iteration (model_zoo/nconv.py:114-131), sum(w) (nconv.py:58-61) and the
+// constant-memory images the kernels read (layouts in adc_common.cuh).
 #pragma once
 #include "adc_common.cuh"
 
@@ -17,8 +17,8 @@ struct PrepCall {
     float* w_out;       // standard layout copy of the weight this call used (may be null)
     int Co, Ci, K;
     int times;          // softplus applications before use
-    int flip;           // 0: forward image, 1: data-gradient image (flipped taps, ci-pair major)
-    const float* s_in;  // flip=1: s of the forward call (image of the forward), else null
+    int flip;           // 0: forward image, 1: data-gradient image (transposed + flipped taps)
+    const float* s_in;  // flip=1: image of the forward call (source of s, 1/s), else null
 };
 
 struct PrepArgs {
@@ -26,9 +26,6 @@ struct PrepArgs {
     float* img;         // [ncalls][kWStride] global staging copy of the constant image
 };
 
-// Forward image (Co == 2): float2 index (ci*K+u)*K+v = {w[0,ci,u,v], w[1,ci,u,v]}; (Co == 1): float index (ci*K+u)*K+v.
-// Data-gradient image: for ci-pair q, float2 index ((q*Co+o)*K+u')*K+v' = {w[o,2q,K-1-u',K-1-v'], w[o,2q+1,...]}
-// (an odd Ci is padded with a zero channel).  [kWBias..] = bias, [kWSum..] = s = sum_{ci,u,v} w (forward weight).
 __global__ void __launch_bounds__(128) prep_weights_kernel(PrepArgs a) {
     const PrepCall& c = a.call[blockIdx.x];
     float* img = a.img + (size_t)blockIdx.x * kWStride;
@@ -44,12 +41,10 @@ __global__ void __launch_bounds__(128) prep_weights_kernel(PrepArgs a) {
         if (c.w_out) c.w_out[t] = w;
         const int co = t / per_co, rem = t % per_co, ci = rem / KK, u = (rem % KK) / c.K, v = rem % c.K;
         part[co] = w;
-        if (!c.flip) {
-            img[((ci * c.K + u) * c.K + v) * c.Co + co] = w;
-        } else {
-            const int q = ci >> 1, j = ci & 1;
-            img[((((q * c.Co + co) * c.K) + (c.K - 1 - u)) * c.K + (c.K - 1 - v)) * 2 + j] = w;
-        }
+        if (!c.flip)
+            img[t] = w;
+        else
+            img[(ci * c.Co + co) * KK + (c.K - 1 - u) * c.K + (c.K - 1 - v)] = w;
     }
     const float s0 = warp_sum(part[0]), s1 = warp_sum(part[1]);
     if ((t & 31) == 0) {

@@ -81,8 +81,10 @@ class NConv2dFunction(torch.autograd.Function):
         y = torch.empty((n, co, h, w), device=x.device, dtype=torch.float32)
         cout = torch.empty_like(y)
         s0 = _src(x, c, bsx)
+        scratch = torch.empty(lib.adc_nconv2d_fwd_scratch_floats(ctypes.byref(s0), None, n, co, h, w), device=x.device,
+                              dtype=torch.float32)
         check(lib.adc_nconv2d_fwd(ctypes.byref(s0), None, wv.data_ptr(), bv.data_ptr(), y.data_ptr(), cout.data_ptr(),
-                                  n, co, h, w, k, LAYER_SLOT, _stream()), "adc_nconv2d_fwd")
+                                  scratch.data_ptr(), n, co, h, w, k, LAYER_SLOT, _stream()), "adc_nconv2d_fwd")
         ctx.save_for_backward(x, c, y, cout, wv, bv)
         ctx.bs = bsx
         ctx.module = module
@@ -102,8 +104,9 @@ class NConv2dFunction(torch.autograd.Function):
         gc = torch.empty_like(gx) if need_in else None
         gw = torch.zeros_like(w_fwd) if need_w else None
         gb = torch.zeros_like(b) if need_w else None
-        scratch = torch.empty(lib.adc_nconv2d_bwd_scratch_floats(n, ci, co, h, w, k), device=x.device, dtype=torch.float32)
         s0 = _src(x, c, ctx.bs)
+        scratch = torch.empty(lib.adc_nconv2d_bwd_scratch_floats(ctypes.byref(s0), None, n, co, h, w), device=x.device,
+                              dtype=torch.float32)
         ptr = lambda t: t.data_ptr() if t is not None else None
         check(lib.adc_nconv2d_bwd(ctypes.byref(s0), None, y.data_ptr(), cout.data_ptr(), gy.data_ptr(), gcout.data_ptr(),
                                   w_fwd.data_ptr(), w_bwd.data_ptr(), b.data_ptr(), ptr(gx), ptr(gc), None, None, ptr(gw), ptr(gb),

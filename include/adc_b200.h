@@ -51,19 +51,23 @@ typedef struct {
  * stride 1, dilation 1, groups 1, padding k/2 -- the only configuration the nets use
  * (model_zoo/nconv_sd.py:21-32).  w is [Co,Ci,k,k], b is [Co], Ci = src0.channels (+ src1.channels).
  * src1 may be NULL.  Channel order of the virtual concatenation is src0 then src1.
+ * `scratch` must hold adc_nconv2d_fwd_scratch_floats() floats (the kernels work on interleaved {x,c} pair tensors;
+ * this single-layer entry packs/unpacks the planar tensors, the pyramid entry below stays packed throughout).
  * slot selects the constant-memory weight slot (0..ADC_WSLOTS-1); calls that may run concurrently on
  * different streams must use different slots. */
+size_t adc_nconv2d_fwd_scratch_floats(const adc_src_t* src0, const adc_src_t* src1, int N, int Co, int H, int W);
 int adc_nconv2d_fwd(const adc_src_t* src0, const adc_src_t* src1, const float* w, const float* b,
-                    float* y, float* cout, int N, int Co, int H, int W, int k, int slot, adc_stream_t stream);
+                    float* y, float* cout, float* scratch, int N, int Co, int H, int W, int k, int slot,
+                    adc_stream_t stream);
 
 /* Backward of the above as the reference's autograd graph computes it:
  * w_fwd = the weight the forward call used (fixes s = sum(w)); w_bwd = the Parameter's contents at
  * backward time (used by the conv data-gradients; model_zoo/nconv.py:114-117 swaps weight.data).
  * gx0/gc0 (and gx1/gc1 for src1) receive the input gradients -- for an upsampled source they are the
- * gradients w.r.t. the LOW-resolution tensors.  Any of them may be NULL (no input gradient needed).
- * gw [Co,Ci,k,k] and gb [Co] are ACCUMULATED into (+=) unless NULL.  `scratch` must hold
+ * gradients w.r.t. the LOW-resolution tensors.  They may be NULL (no input gradient needed; all or none).
+ * gw [Co,Ci,k,k] and gb [Co] are ACCUMULATED into (+=) unless NULL (both or none).  `scratch` must hold
  * adc_nconv2d_bwd_scratch_floats() floats. */
-size_t adc_nconv2d_bwd_scratch_floats(int N, int Ci, int Co, int H, int W, int k);
+size_t adc_nconv2d_bwd_scratch_floats(const adc_src_t* src0, const adc_src_t* src1, int N, int Co, int H, int W);
 int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y, const float* cout,
                     const float* gy, const float* gcout, const float* w_fwd, const float* w_bwd, const float* b,
                     float* gx0, float* gc0, float* gx1, float* gc1, float* gw, float* gb, float* scratch,

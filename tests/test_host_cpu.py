@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(_lib.lib, name), "libadc_b200.so does not export %s" % name
     assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree: %s" % (declared ^ set(_lib.SIGNATURES))
-    assert _lib.lib.adc_abi_version() == 1
+    assert _lib.lib.adc_abi_version() == 2
 
 
 def test_host_side_layout_functions():
@@ -38,7 +38,8 @@ def test_host_side_layout_functions():
     assert lib.adc_pyramid_idx_count(n, h, w) == 2 * n * (114 * 152 + 57 * 76 + 28 * 38)
     assert lib.adc_pyramid_weight_floats() == 468                              # 481 params = 468 weights + 13 biases
     px = [n * 228 * 304, n * 114 * 152, n * 57 * 76, n * 28 * 38]
-    assert lib.adc_pyramid_saved_floats(n, h, w) == 11 * 128 + 4 * (4 * px[0] + 4 * px[1] + 3 * px[2] + 2 * px[3])
+    # 13 saved pair tensors [N,2,h,w] + the packed input [N,1,H,W], after the 11 weight images
+    assert lib.adc_pyramid_saved_floats(n, h, w) == 11 * 128 + 4 * (4 * px[0] + 4 * px[1] + 3 * px[2] + 2 * px[3]) + 2 * px[0]
     assert lib.adc_pyramid_bwd_scratch_floats(n, h, w) > 0
     # argument errors come back as negative status + message, not a crash
     assert lib.adc_pyramid_idx_layout(0, h, w, off, hs, ws) == -1
