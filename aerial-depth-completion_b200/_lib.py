@@ -55,6 +55,10 @@ _vp, _sp = ctypes.c_void_p, ctypes.POINTER(Src)
 SIGNATURES = {
     "adc_abi_version": (c_int, []),
     "adc_last_error": (ctypes.c_char_p, []),
+    "adc_launch_count": (c_ll, []),
+    "adc_profile_enable": (c_int, [c_int]),
+    "adc_profile_read": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                 ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
     "adc_nconv2d_fwd_scratch_floats": (ctypes.c_size_t, [_sp, _sp] + [c_int] * 4),
     "adc_nconv2d_fwd": (c_int, [_sp, _sp, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_nconv2d_bwd_scratch_floats": (ctypes.c_size_t, [_sp, _sp] + [c_int] * 4),

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 #include "../../include/adc_b200.h"
 
 namespace adc {
@@ -73,6 +74,18 @@ struct SrcP {
     int up;            // 1 if (H,W) differs from the layer size (nearest-upsampled on the fly)
     int tma;           // 1 if the tile is fetched with a TMA box copy (map passed separately)
 };
+
+// Compile-time loop: f(std::integral_constant<int, 0>{}) ... f(<N-1>).  The row loops of the convolution cores MUST be
+// fully unrolled (accumulator indices are registers, weights are uniform-register operands); `#pragma unroll` alone was
+// observed to unroll the 12-iteration row loop only 4x, leaving run-time tap indices, branches and 500 dependent LDCUs.
+template <typename F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 bcast(float a) { return make_float2(a, a); }

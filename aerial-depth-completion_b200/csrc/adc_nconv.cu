@@ -28,6 +28,32 @@ int check_cuda(cudaError_t e, const char* what) {
     return (int)e;
 }
 
+// ---- instrumentation: launch counter (always on) and optional per-kernel CUDA-event timing -----------------------
+static long long g_launches = 0;
+struct ProfRec { cudaEvent_t a, b; int kind, call; double bytes; };
+static const int kProfMax = 512;
+static ProfRec g_prof[kProfMax];
+static int g_prof_n = 0, g_prof_on = 0, g_prof_events = 0;
+
+struct ProfScope {   // records an event pair around the launches made while it is alive
+    cudaStream_t st; int idx;
+    ProfScope(cudaStream_t s, int kind, int call, double bytes) : st(s), idx(-1) {
+        g_launches++;
+        if (!g_prof_on || g_prof_n >= kProfMax) return;
+        if (g_prof_n >= g_prof_events) {
+            if (cudaEventCreate(&g_prof[g_prof_n].a) != cudaSuccess || cudaEventCreate(&g_prof[g_prof_n].b) != cudaSuccess) return;
+            g_prof_events = g_prof_n + 1;
+        }
+        idx = g_prof_n++;
+        g_prof[idx].kind = kind; g_prof[idx].call = call; g_prof[idx].bytes = bytes;
+        cudaEventRecord(g_prof[idx].a, st);
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].b, st); }
+};
+enum { KIND_FWD = 0, KIND_BWD_DATA = 1, KIND_BWD_WEIGHT = 2, KIND_POOL_FWD = 3, KIND_POOL_BWD = 4, KIND_UP_BWD = 5, KIND_HEAD_FWD = 6,
+       KIND_HEAD_BWD = 7, KIND_PACK = 8, KIND_REDUCE = 9, KIND_PREP = 10 };
+static int g_cur_call = -1;   // pyramid call index of the launches being issued (for the profile records)
+
 static float* g_stage = nullptr;  // [ADC_WSLOTS][2][ADC_PYR_CALLS][kWStride] device staging for the single-layer API
 static int g_use_tma = -1;
 
@@ -117,7 +143,8 @@ static int launch_fwd(const SrcP& s0, const SrcP* s1, float2* out, int N, int H,
     Maps2 maps;
     int rc = fill_maps<K>(&maps, s0, s1, N);
     if (rc) return rc;
-    nconv_fwd_kernel<CI, K><<<tile_grid(N, H, W), 128, smem, st>>>(maps, s0, s1 ? *s1 : s0, s1 ? 1 : 0, out, H, W, wimg);
+    { ProfScope _p(st, KIND_FWD, g_cur_call, 8.0 * (CI + 2) * N * H * W);
+    nconv_fwd_kernel<CI, K><<<tile_grid(N, H, W), 128, smem, st>>>(maps, s0, s1 ? *s1 : s0, s1 ? 1 : 0, out, H, W, wimg); }
     return check_cuda(cudaGetLastError(), "nconv_fwd_kernel launch");
 }
 
@@ -131,8 +158,9 @@ static int launch_bwd_data(const SrcP& g, const SrcP& s0, const SrcP* s1, float2
     Maps2 maps;
     int rc = fill_maps<K>(&maps, g, nullptr, N);
     if (rc) return rc;
+    { ProfScope _p(st, KIND_BWD_DATA, g_cur_call, 8.0 * (2 + 2 * CI) * N * H * W);
     nconv_bwd_data_kernel<CI, K><<<tile_grid(N, H, W), 128, smem, st>>>(maps, g, s0, s1 ? *s1 : s0, s1 ? 1 : 0, out0, out1, bpart,
-                                                                         H, W, wimg, ximg);
+                                                                         H, W, wimg, ximg); }
     return check_cuda(cudaGetLastError(), "nconv_bwd_data_kernel launch");
 }
 
@@ -148,7 +176,8 @@ static int launch_bwd_weight(const SrcP& g, const SrcP& s0, const SrcP* s1, floa
     CUtensorMap gmap;
     memset(&gmap, 0, sizeof(gmap));
     if (g.tma && (rc = make_pair_map(&gmap, g, N, C::TW, C::TH))) return rc;
-    nconv_bwd_weight_kernel<CI, K><<<tile_grid(N, H, W), C::NT, smem, st>>>(maps, gmap, g, s0, s1 ? *s1 : s0, s1 ? 1 : 0, wpart, H, W);
+    { ProfScope _p(st, KIND_BWD_WEIGHT, g_cur_call, 8.0 * (2 + CI) * N * H * W);
+    nconv_bwd_weight_kernel<CI, K><<<tile_grid(N, H, W), C::NT, smem, st>>>(maps, gmap, g, s0, s1 ? *s1 : s0, s1 ? 1 : 0, wpart, H, W); }
     return check_cuda(cudaGetLastError(), "nconv_bwd_weight_kernel launch");
 }
 
@@ -182,8 +211,9 @@ static int dispatch_bwd_weight(int Ci, int K, const SrcP& g, const SrcP& s0, con
 static int run_upsample_bwd(const float2* g_full, const SrcP& s, float2* G, float* bpart, int N, int H, int W, int ximg,
                             cudaStream_t st) {
     const long long planes = (long long)N * s.ch, total = planes * s.H * s.W;
+    { ProfScope _p(st, KIND_UP_BWD, g_cur_call, 8.0 * s.ch * N * ((double)H * W + 2.0 * s.H * s.W));
     pair_upsample_bwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(g_full, s.p, G, bpart, s.ch, H, W, s.H, s.W, s.mh, s.mw,
-                                                                          planes, ximg);
+                                                                          planes, ximg); }
     return check_cuda(cudaGetLastError(), "pair_upsample_bwd_kernel launch");
 }
 
@@ -237,11 +267,35 @@ using namespace adc;
 extern "C" {
 
 int adc_abi_version(void) { return 2; }
+
+long long adc_launch_count(void) { return g_launches; }
+
+int adc_profile_enable(int on) {
+    g_prof_on = on ? 1 : 0;
+    g_prof_n = 0;
+    return 0;
+}
+
+int adc_profile_read(int max_records, int* n_out, int* kinds, int* calls, float* ms, double* bytes) {
+    ADC_CHECK_ARG(n_out && kinds && calls && ms && bytes && max_records >= 0, ADC_E_BADARG, "adc_profile_read: bad argument");
+    const int n = g_prof_n < max_records ? g_prof_n : max_records;
+    for (int i = 0; i < n; ++i) {
+        ADC_CUDA(cudaEventSynchronize(g_prof[i].b));
+        float t = 0.f;
+        ADC_CUDA(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
+        kinds[i] = g_prof[i].kind; calls[i] = g_prof[i].call; ms[i] = t; bytes[i] = g_prof[i].bytes;
+    }
+    g_prof_n = 0;
+    *n_out = n;
+    return 0;
+}
 const char* adc_last_error(void) { return g_err; }
 
 int adc_softplus_pow(const float* w, float* out, int numel, int times, adc_stream_t stream) {
     ADC_CHECK_ARG(w && out && numel > 0 && times >= 0, ADC_E_BADARG, "adc_softplus_pow: bad argument");
+    { ProfScope _p((cudaStream_t)stream, KIND_PACK, g_cur_call, 0.0);
     softplus_pow_kernel<<<ceil_div(numel, 256), 256, 0, (cudaStream_t)stream>>>(w, out, numel, times);
+    }
     return check_cuda(cudaGetLastError(), "softplus_pow_kernel launch");
 }
 
@@ -251,7 +305,9 @@ int adc_conf_pool_fwd(const float* x, const float* c, float* x_ds, float* c_ds, 
                   "adc_conf_pool_fwd: bad argument");
     const int Ho = H / 2, Wo = W / 2;
     const long long planes = (long long)N * C, total = planes * Ho * Wo;
+    { ProfScope _p((cudaStream_t)stream, KIND_PACK, g_cur_call, 0.0);
     conf_pool_fwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(x, c, x_ds, c_ds, idx, H, W, Ho, Wo, planes);
+    }
     return check_cuda(cudaGetLastError(), "conf_pool_fwd_kernel launch");
 }
 
@@ -261,8 +317,10 @@ int adc_conf_pool_bwd(const float* g_xds, const float* g_cds, const long long* i
                   "adc_conf_pool_bwd: bad argument");
     const int Ho = H / 2, Wo = W / 2;
     const long long planes = (long long)N * C, total = planes * ((H + 1) / 2) * ((W + 1) / 2);
+    { ProfScope _p((cudaStream_t)stream, KIND_PACK, g_cur_call, 0.0);
     conf_pool_bwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(g_xds, g_cds, idx, add_x, add_c, gx, gc, H,
                                                                                          W, Ho, Wo, planes);
+    }
     return check_cuda(cudaGetLastError(), "conf_pool_bwd_kernel launch");
 }
 
@@ -284,7 +342,9 @@ static long long src_pairs(const adc_src_t* s, int N) { return s ? (long long)N 
 static int pack_source(const adc_src_t* s, int N, float2* dst, cudaStream_t st) {
     const long long per_image = (long long)s->channels * s->H * s->W;
     dim3 grid((unsigned)ceil_div_ll(per_image, 256), N);
+    { ProfScope _p(st, KIND_PACK, g_cur_call, 0.0);
     pack_pairs_kernel<<<grid, 256, 0, st>>>(s->x, s->c, s->batch_stride, s->batch_stride, dst, per_image);
+    }
     return check_cuda(cudaGetLastError(), "pack_pairs_kernel launch");
 }
 
@@ -305,7 +365,9 @@ int adc_nconv2d_fwd(const adc_src_t* src0, const adc_src_t* src1, const float* w
     memset(&pa, 0, sizeof(pa));
     pa.call[0] = PrepCall{w, b, nullptr, Co, Ci, k, 0, 0, nullptr};
     pa.img = g_stage + (size_t)wimg_index(slot, 0, 0) * kWStride;
+    { ProfScope _p(st, KIND_PREP, g_cur_call, 0.0);
     prep_weights_kernel<<<1, 128, 0, st>>>(pa);
+    }
     ADC_CUDA(cudaGetLastError());
     if ((rc = upload_images(pa.img, slot, 0, 0, 1, st))) return rc;
     float2* p0 = reinterpret_cast<float2*>(scratch);
@@ -319,19 +381,23 @@ int adc_nconv2d_fwd(const adc_src_t* src0, const adc_src_t* src1, const float* w
     const long long plane = (long long)H * W;
     if (Co == 1) {
         dim3 grid(blocks_1x1(plane), N);
+        { ProfScope _p(st, KIND_HEAD_FWD, g_cur_call, 24.0 * grid.y * plane);
         nconv_1x1_fwd_kernel<<<grid, 256, 0, st>>>(p0, y, cout, plane, wimg);
+        }
         return check_cuda(cudaGetLastError(), "nconv_1x1_fwd_kernel launch");
     }
     if ((rc = dispatch_fwd(Ci, k, s0, src1 ? &s1 : nullptr, po, N, H, W, wimg, st))) return rc;
     const long long total = (long long)N * Co * plane;
+    { ProfScope _p(st, KIND_PACK, g_cur_call, 0.0);
     unpack_pairs_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(po, y, cout, total);
+    }
     return check_cuda(cudaGetLastError(), "unpack_pairs_kernel launch");
 }
 
 // scratch of the single-layer backward: [packed sources][G pairs][raw grads at layer res][raw low-res grads][wpart][bpart]
 namespace adc {
 struct LayerBwdLayout {
-    long long p0, p1, G, r0, r1, l0, l1, wpart, bpart, total;
+    long long p0, p1, G, r0, r1, l0, l1, wpart, bpart, stage, total;
     int wblocks, bblocks;
     LayerBwdLayout(const adc_src_t* s0, const adc_src_t* s1, int N, int Co, int H, int W) {
         const long long plane = (long long)H * W;
@@ -347,6 +413,7 @@ struct LayerBwdLayout {
         bblocks = Co == 1 ? wblocks : N * (int)ceil_div_ll(plane, 256);
         wpart = o; o += (long long)wblocks * kWStride;
         bpart = o; o += (long long)bblocks * 4;
+        stage = o; o += (long long)kRedChunks * kWStride;
         total = o;
     }
 };
@@ -381,10 +448,14 @@ int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y
     float* img_b = g_stage + (size_t)wimg_index(slot, 1, 0) * kWStride;
     pa.call[0] = PrepCall{w_fwd, b, nullptr, Co, Ci, k, 0, 0, nullptr};
     pa.img = img_f;
+    { ProfScope _p(st, KIND_PREP, g_cur_call, 0.0);
     prep_weights_kernel<<<1, 128, 0, st>>>(pa);
+    }
     pa.call[0] = PrepCall{w_bwd, b, nullptr, Co, Ci, k, 0, 1, img_f};
     pa.img = img_b;
+    { ProfScope _p(st, KIND_PREP, g_cur_call, 0.0);
     prep_weights_kernel<<<1, 128, 0, st>>>(pa);
+    }
     ADC_CUDA(cudaGetLastError());
     if ((rc = upload_images(img_f, slot, 0, 0, 1, st))) return rc;
     if ((rc = upload_images(img_b, slot, 1, 0, 1, st))) return rc;
@@ -403,12 +474,16 @@ int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y
 
     if (Co == 1) {
         dim3 grid(blocks_1x1(plane), N);
+        { ProfScope _p(st, KIND_HEAD_BWD, g_cur_call, 48.0 * grid.y * plane);
         nconv_1x1_bwd_kernel<<<grid, 256, 0, st>>>(p0, y, cout, gy, gcout, need_data ? r0 : nullptr, wpart, bpart, nullptr, plane, wf,
                                                   wb, -1);
+        }
         ADC_CUDA(cudaGetLastError());
     } else {
         dim3 grid((unsigned)ceil_div_ll(plane, 256), N);
+        { ProfScope _p(st, KIND_PACK, g_cur_call, 0.0);
         grad_transform_kernel<2><<<grid, 256, 0, st>>>(gy, gcout, y, cout, G, bpart, plane, wf);
+        }
         ADC_CUDA(cudaGetLastError());
         SrcP g = make_srcp(G, 2 * plane, 2, H, W, H, W);
         if (need_weight && (rc = dispatch_bwd_weight(Ci, k, g, s0, src1 ? &s1 : nullptr, wpart, N, H, W, st))) return rc;
@@ -429,7 +504,9 @@ int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y
                 fin = low[q];
             }
             const long long total = src_pairs(ss[q], N);
+            { ProfScope _p(st, KIND_PACK, g_cur_call, 0.0);
             unpack_pairs_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(fin, ox[q], oc[q], total);
+            }
             ADC_CUDA(cudaGetLastError());
         }
     }
@@ -441,7 +518,12 @@ int adc_nconv2d_bwd(const adc_src_t* src0, const adc_src_t* src1, const float* y
         ra.gw[0] = gw;
         ra.gb[0] = gb;
         ra.accumulate = 1;
-        wgrad_reduce_kernel<<<1, 1024, 0, st>>>(ra);
+        { ProfScope _p(st, KIND_REDUCE, g_cur_call, 0.0);
+        wgrad_reduce1_kernel<<<dim3(1, kRedChunks), 1024, 0, st>>>(ra, scratch + L.stage);
+        }
+        { ProfScope _p(st, KIND_REDUCE, g_cur_call, 0.0);
+        wgrad_reduce2_kernel<<<1, 128, 0, st>>>(ra, scratch + L.stage);
+        }
         ADC_CUDA(cudaGetLastError());
     }
     return 0;
@@ -499,7 +581,9 @@ int adc_pyramid_fwd(const adc_pyramid_fwd_t* a, adc_stream_t stream) {
         pa.call[k] = PrepCall{a->weight[m], a->bias[m], wout, kModCo[m], kModCi[m], kModK[m], a->training ? seen[m] : 0, 0, nullptr};
     }
     pa.img = S;
+    { ProfScope _p(st, KIND_PREP, g_cur_call, 0.0);
     prep_weights_kernel<<<ADC_PYR_CALLS, 128, 0, st>>>(pa);
+    }
     ADC_CUDA(cudaGetLastError());
     if ((rc = upload_images(S, a->slot, 0, 0, ADC_PYR_CALLS, st))) return rc;
 
@@ -509,6 +593,7 @@ int adc_pyramid_fwd(const adc_pyramid_fwd_t* a, adc_stream_t stream) {
         return make_srcp(act(id), (long long)ch * g.h[l] * g.w[l], ch, g.h[l], g.w[l], g.h[lvl], g.w[lvl]);
     };
     auto layer = [&](int call, int in0, int in1, int out) -> int {
+        g_cur_call = call;
         const int m = kCallModule[call], l = kCallLevel[call];
         SrcP s0 = src_of(in0, l), s1;
         if (in1 >= 0) s1 = src_of(in1, l);
@@ -520,15 +605,19 @@ int adc_pyramid_fwd(const adc_pyramid_fwd_t* a, adc_stream_t stream) {
     auto pool = [&](int in_id, int out_id, int lvl) -> int {  // lvl = level of the input
         const int Ho = g.h[lvl + 1], Wo = g.w[lvl + 1];
         const long long planes = (long long)g.N * 2, total = planes * Ho * Wo;
+        { ProfScope _p(st, KIND_POOL_FWD, g_cur_call, 24.0 * planes * g.h[lvl] * g.w[lvl] / 2);
         pair_pool_fwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(act(in_id), act(out_id), a->idx + ioff[lvl], g.h[lvl],
                                                                             g.w[lvl], Ho, Wo, planes);
+        }
         return check_cuda(cudaGetLastError(), "pair_pool_fwd_kernel launch");
     };
 #define RUN(expr) do { rc = (expr); if (rc) return rc; } while (0)
     {
         const long long per_image = (long long)a->H * a->W;
         dim3 grid((unsigned)ceil_div_ll(per_image, 256), g.N);
+        { ProfScope _p(st, KIND_PACK, g_cur_call, 0.0);
         pack_pairs_kernel<<<grid, 256, 0, st>>>(a->x0, a->c0, a->x0_batch_stride, a->c0_batch_stride, act(AIN), per_image);
+        }
         ADC_CUDA(cudaGetLastError());
     }
     RUN(layer(0, AIN, -1, A0));
@@ -547,7 +636,9 @@ int adc_pyramid_fwd(const adc_pyramid_fwd_t* a, adc_stream_t stream) {
     {
         const long long plane = (long long)a->H * a->W;
         dim3 grid(blocks_1x1(plane), g.N);
+        { ProfScope _p(st, KIND_HEAD_FWD, g_cur_call, 24.0 * grid.y * plane);
         nconv_1x1_fwd_kernel<<<grid, 256, 0, st>>>(act(A9), a->xout, a->cout, plane, wimg_index(a->slot, 0, 10));
+        }
         ADC_CUDA(cudaGetLastError());
     }
 #undef RUN
@@ -557,7 +648,7 @@ int adc_pyramid_fwd(const adc_pyramid_fwd_t* a, adc_stream_t stream) {
 // backward scratch: [bwd images][wpart per call][bpart per call][G buffers per level][layer-res raw grads of upsampled sources]
 namespace adc {
 struct BwdLayout {
-    long long img, wpart[ADC_PYR_CALLS], bpart[ADC_PYR_CALLS], gbuf[4][4], up[3], total;
+    long long img, wpart[ADC_PYR_CALLS], bpart[ADC_PYR_CALLS], gbuf[4][4], up[3], stage, total;
     int wblk[ADC_PYR_CALLS], bblk[ADC_PYR_CALLS];
     explicit BwdLayout(const Geo& g) {
         long long o = 0;
@@ -579,6 +670,7 @@ struct BwdLayout {
         for (int l = 0; l < 4; ++l)
             for (int b = 0; b < 4; ++b) { gbuf[l][b] = o; o += 4 * g.px[l]; }   // pair tensor [N,2,h,w]
         for (int l = 0; l < 3; ++l) { up[l] = o; o += 4 * g.px[l]; }
+        stage = o; o += (long long)ADC_PYR_CALLS * kRedChunks * kWStride;
         total = o;
     }
 };
@@ -617,7 +709,9 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
         pa.call[k] = PrepCall{a->weight_bwd[m], a->bias[m], nullptr, kModCo[m], kModCi[m], kModK[m], 0, 1, S + (size_t)k * kWStride};
     }
     pa.img = X + B.img;
+    { ProfScope _p(st, KIND_PREP, g_cur_call, 0.0);
     prep_weights_kernel<<<ADC_PYR_CALLS, 128, 0, st>>>(pa);
+    }
     ADC_CUDA(cudaGetLastError());
     if ((rc = upload_images(X + B.img, a->slot, 1, 0, ADC_PYR_CALLS, st))) return rc;
 
@@ -632,6 +726,7 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
     auto bimg = [&](int call) { return wimg_index(a->slot, 1, call); };
     // one layer: G (transformed gradient of the call's output) -> weight partials + gradients of its sources
     auto layer_bwd = [&](int call, const float2* G, int in0, int in1, float2* out0, float2* out1, int xcall, bool need_data) -> int {
+        g_cur_call = call;
         const int m = kCallModule[call], l = kCallLevel[call];
         SrcP gsrc = make_srcp(G, 2LL * g.h[l] * g.w[l], 2, g.h[l], g.w[l], g.h[l], g.w[l]);
         SrcP s0 = src_of(in0, l), s1;
@@ -655,9 +750,11 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
     auto pool_bwd = [&](int lvl, const float2* g_ds, const float2* skip, int act_id, int xcall, float2* G) -> int {
         const int H = g.h[lvl], W = g.w[lvl];
         const long long planes = 2LL * g.N, total = planes * ((H + 1) / 2) * ((W + 1) / 2);
+        { ProfScope _p(st, KIND_POOL_BWD, g_cur_call, 28.0 * planes * H * W);
         pair_pool_bwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(g_ds, a->idx + ioff[lvl], skip, act(act_id), G,
                                                                             X + B.bpart[xcall], 2, H, W, g.h[lvl + 1], g.w[lvl + 1],
                                                                             planes, fimg(xcall));
+        }
         return check_cuda(cudaGetLastError(), "pair_pool_bwd_kernel launch");
     };
 #define RUN(expr) do { rc = (expr); if (rc) return rc; } while (0)
@@ -665,8 +762,10 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
     {
         const long long plane = (long long)a->H * a->W;
         dim3 grid(blocks_1x1(plane), g.N);
+        { ProfScope _p(st, KIND_HEAD_BWD, g_cur_call, 48.0 * grid.y * plane);
         nconv_1x1_bwd_kernel<<<grid, 256, 0, st>>>(act(A9), a->xout, a->cout, a->g_xout, a->g_cout, gb(0, 0), X + B.wpart[10],
                                                   X + B.bpart[10], X + B.bpart[9], plane, fimg(10), bimg(10), fimg(9));
+        }
         ADC_CUDA(cudaGetLastError());
     }
     // call 9 (nconv6 on cat(up(A8), A2)): raw grads of up(A8) -> up[0] -> reduce -> G8 in gbuf[1][0]; skip grads of A2 -> gbuf[0][2]
@@ -697,7 +796,9 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
         if (nd || need_w) RUN(layer_bwd(0, gb(0, 3), AIN, -1, gb(0, 1), nullptr, -1, nd));
         if (nd) {
             const long long total = g.px[0];
+            { ProfScope _p(st, KIND_PACK, g_cur_call, 0.0);
             unpack_pairs_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(gb(0, 1), a->gx0, a->gc0, total);
+            }
             ADC_CUDA(cudaGetLastError());
         }
     }
@@ -717,7 +818,12 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
             bo += kModCo[m];
         }
         ra.accumulate = 0;
-        wgrad_reduce_kernel<<<ADC_PYR_MODULES, 1024, 0, st>>>(ra);
+        { ProfScope _p(st, KIND_REDUCE, g_cur_call, 0.0);
+        wgrad_reduce1_kernel<<<dim3(ADC_PYR_CALLS, kRedChunks), 1024, 0, st>>>(ra, X + B.stage);
+        }
+        { ProfScope _p(st, KIND_REDUCE, g_cur_call, 0.0);
+        wgrad_reduce2_kernel<<<ADC_PYR_MODULES, 128, 0, st>>>(ra, X + B.stage);
+        }
         ADC_CUDA(cudaGetLastError());
     }
     return 0;

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) nconv_bwd_data_kernel(const __grid_consta
                                                              float2* __restrict__ out0, float2* __restrict__ out1,
                                                              float* __restrict__ bpart, int H, int W, int wimg, int ximg) {
     using C = TileCfg<K>;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     float2* planes = align128(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(planes + 2 * C::PLANE);
     const int tid = threadIdx.x;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) nconv_bwd_data_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             float2 acc[NO][8][2];
-            conv_patch<2, NO, K, false>(planes, wc + q * (2 * 2 * K * K), tx, ty, acc);
+            conv_patch<2, NO, K>(planes, wc + q * (2 * 2 * K * K), tx, ty, acc);
 #pragma unroll
             for (int j = 0; j < NO; ++j) {
                 const int ci = 2 * q + j;
@@ -61,24 +61,30 @@ __global__ void __launch_bounds__(128) nconv_bwd_data_kernel(const __grid_consta
                     xb = xc[kWBias + ci]; xs = xc[kWSum + ci]; xis = xc[kWInvSum + ci];
                 }
                 const bool vec = !s.up && (W & 1) == 0;
+                // all eight rows of {x, c} are requested before the first one is consumed (the loop was latency-bound:
+                // long_scoreboard 7-13 stall cycles per issue with load -> use -> store per row)
+                float2 a0[8], a1[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int h = oh + r < H ? oh + r : H - 1;
+                    if (vec) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(xp + (long long)h * W + ow));
+                        a0[r] = make_float2(t.x, t.y); a1[r] = make_float2(t.z, t.w);
+                    } else {
+                        const long long ro = (long long)s.mh(h) * s.W;
+                        a0[r] = __ldg(xp + ro + s.mw(ow));
+                        a1[r] = __ldg(xp + ro + s.mw(ow + 1 < W ? ow + 1 : ow));
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int h = oh + r;
                     if (h >= H) break;
-                    float2 a0, a1;
-                    if (vec) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(xp + (long long)h * W + ow));
-                        a0 = make_float2(t.x, t.y); a1 = make_float2(t.z, t.w);
-                    } else {
-                        const long long ro = (long long)s.mh(h) * s.W;
-                        a0 = __ldg(xp + ro + s.mw(ow));
-                        a1 = ow + 1 < W ? __ldg(xp + ro + s.mw(ow + 1)) : make_float2(0.f, 0.f);
-                    }
-                    float2 r0 = make_float2(acc[j][r][0].x * a0.y, fmaf(acc[j][r][0].x, a0.x, acc[j][r][0].y));
-                    float2 r1 = make_float2(acc[j][r][1].x * a1.y, fmaf(acc[j][r][1].x, a1.x, acc[j][r][1].y));
+                    float2 r0 = make_float2(acc[j][r][0].x * a0[r].y, fmaf(acc[j][r][0].x, a0[r].x, acc[j][r][0].y));
+                    float2 r1 = make_float2(acc[j][r][1].x * a1[r].y, fmaf(acc[j][r][1].x, a1[r].x, acc[j][r][1].y));
                     if (ximg >= 0) {
-                        r0 = grad_xform(r0.x, r0.y, a0.x, a0.y, xb, xs, xis, gb[j], gs[j]);
-                        if (ow + 1 < W) r1 = grad_xform(r1.x, r1.y, a1.x, a1.y, xb, xs, xis, gb[j], gs[j]);
+                        r0 = grad_xform(r0.x, r0.y, a0[r].x, a0[r].y, xb, xs, xis, gb[j], gs[j]);
+                        if (ow + 1 < W) r1 = grad_xform(r1.x, r1.y, a1[r].x, a1[r].y, xb, xs, xis, gb[j], gs[j]);
                     }
                     if ((W & 1) == 0) {
                         *reinterpret_cast<float4*>(go + (long long)h * W) = make_float4(r0.x, r0.y, r1.x, r1.y);
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
     using C = WgCfg<CI, K>;
     using T = TileCfg<K>;
     constexpr int P = C::P, NT = C::NT;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     float2* sX = align128(smem_raw);                 // [CI] planes of {x, c} with halo
     float2* sG = sX + CI * T::PLANE;                 // [2][TH][TW] {GN, GD}
     uint64_t* bar = reinterpret_cast<uint64_t*>(sG + 2 * C::GPLANE);
@@ -150,7 +156,9 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
     }
     __syncthreads();
     if (pending) mbar_wait(bar, 0);
+    premul_planes<K, NT>(sX, CI, tid);      // {x, c} -> {x*c, c}
     if (g.tma) mbar_wait(bar2, 0);
+    __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31;
     const int role = warp % C::ROLES, grp = warp / C::ROLES;
@@ -186,8 +194,8 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
 #pragma unroll
             for (int t = 0; t < NP / 2; ++t) {
                 const float4 a = *reinterpret_cast<const float4*>(xptr + j * T::SWP + 2 * t);
-                xr[2 * t] = make_float2(a.x * a.y, a.y);
-                xr[2 * t + 1] = make_float2(a.z * a.w, a.w);
+                xr[2 * t] = make_float2(a.x, a.y);
+                xr[2 * t + 1] = make_float2(a.z, a.w);
             }
 #pragma unroll
             for (int u = 0; u < K; ++u) {
@@ -311,40 +319,71 @@ struct WgReduceArgs {
     int accumulate;
 };
 
-__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(WgReduceArgs a) {
-    const int m = blockIdx.x;
-    const int t = threadIdx.x & 127, slice = threadIdx.x >> 7;   // 8 slices x 128 entries
-    __shared__ float sh[8][kWStride + 4];
-    float acc = 0.f;
-    int n = 0, Co = 1;
-    for (int k = 0; k < a.ncalls; ++k) {
-        const WgReduceCall& c = a.call[k];
-        if (c.module != m) continue;
-        n = c.n;
-        Co = c.Co;
-        if (t < c.n)
-            for (int blk = slice; blk < c.wblocks; blk += 8) acc += c.wpart[(size_t)blk * kWStride + t];
-        else if (t >= kWBias && t < kWBias + 4)
-            for (int blk = slice; blk < c.bblocks; blk += 8) acc += c.bpart[(size_t)blk * 4 + (t - kWBias)];
+constexpr int kRedChunks = 16;   // first-stage blocks per call
+
+// Stage 1: grid (ncalls, kRedChunks) x 1024 threads = 8 row slices x 128 entries.  Each thread sums its rows with four
+// independent accumulators so the loads overlap (a single serial loop was DRAM-latency bound: 116 us for 1280 rows).
+__global__ void __launch_bounds__(1024) wgrad_reduce1_kernel(WgReduceArgs a, float* __restrict__ stage) {
+    const WgReduceCall& c = a.call[blockIdx.x];
+    const int t = threadIdx.x & 127, slice = threadIdx.x >> 7;
+    __shared__ float sh[8][kWStride];
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const int first = blockIdx.y * 8 + slice, step = kRedChunks * 8;
+    if (t < c.n) {
+        const float* p = c.wpart + t;
+        int r = first;
+        for (; r + 3 * step < c.wblocks; r += 4 * step) {
+            acc0 += p[(size_t)r * kWStride];
+            acc1 += p[(size_t)(r + step) * kWStride];
+            acc2 += p[(size_t)(r + 2 * step) * kWStride];
+            acc3 += p[(size_t)(r + 3 * step) * kWStride];
+        }
+        for (; r < c.wblocks; r += step) acc0 += p[(size_t)r * kWStride];
+    } else if (t >= kWBias && t < kWBias + 4) {
+        const float* p = c.bpart + (t - kWBias);
+        int r = first;
+        for (; r + 3 * step < c.bblocks; r += 4 * step) {
+            acc0 += p[(size_t)r * 4];
+            acc1 += p[(size_t)(r + step) * 4];
+            acc2 += p[(size_t)(r + 2 * step) * 4];
+            acc3 += p[(size_t)(r + 3 * step) * 4];
+        }
+        for (; r < c.bblocks; r += step) acc0 += p[(size_t)r * 4];
     }
-    sh[slice][t] = acc;
+    sh[slice][t] = (acc0 + acc1) + (acc2 + acc3);
     __syncthreads();
     if (slice == 0) {
         float v = 0.f;
 #pragma unroll
         for (int s = 0; s < 8; ++s) v += sh[s][t];
-        sh[0][t] = v;
+        stage[((size_t)blockIdx.x * kRedChunks + blockIdx.y) * kWStride + t] = v;
     }
+}
+
+// Stage 2: one block per module: sum the chunks of every call of the module, add gs, write / accumulate.
+__global__ void __launch_bounds__(128) wgrad_reduce2_kernel(WgReduceArgs a, const float* __restrict__ stage) {
+    const int m = blockIdx.x, t = threadIdx.x;
+    __shared__ float sh[kWStride];
+    float v = 0.f;
+    int n = 0, Co = 1;
+    for (int k = 0; k < a.ncalls; ++k) {
+        if (a.call[k].module != m) continue;
+        n = a.call[k].n;
+        Co = a.call[k].Co;
+#pragma unroll
+        for (int ch = 0; ch < kRedChunks; ++ch) v += stage[((size_t)k * kRedChunks + ch) * kWStride + t];
+    }
+    sh[t] = v;
     __syncthreads();
-    if (slice == 0 && n > 0) {
+    if (n > 0) {
         if (t < n) {
             const int co = t / (n / Co);
-            const float v = sh[0][t] + sh[0][kWBias + 2 + co];     // + gs[co]
-            a.gw[m][t] = a.accumulate ? a.gw[m][t] + v : v;
+            const float r = sh[t] + sh[kWBias + 2 + co];     // + gs[co]
+            a.gw[m][t] = a.accumulate ? a.gw[m][t] + r : r;
         }
         if (t < Co && a.gb[m]) {
-            const float v = sh[0][kWBias + t];
-            a.gb[m][t] = a.accumulate ? a.gb[m][t] + v : v;
+            const float r = sh[kWBias + t];
+            a.gb[m][t] = a.accumulate ? a.gb[m][t] + r : r;
         }
     }
 }

@@ -34,8 +34,11 @@ struct Maps2 {
     CUtensorMap m0, m1;
 };
 
-__device__ __forceinline__ float2* align128(void* p) {
-    return reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
+// 128-byte aligned start of the dynamic shared memory, computed as an OFFSET into the array so the pointer keeps its
+// shared-memory address space (a reinterpret_cast through an integer degrades every access to a generic LD).
+__device__ __forceinline__ float2* align128(uint8_t* smem) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+    return reinterpret_cast<float2*>(smem + ((128u - (a & 127u)) & 127u));
 }
 
 // Batched gather of one channel tile (generic path: upsampled / unaligned sources).  Four independent 8-byte loads are
@@ -96,8 +99,8 @@ __device__ __forceinline__ bool stage_sources(const Maps2& maps, const SrcP& s0,
 // The shared compute core.  For a thread's 2x8 patch and NOUT output maps:
 //   acc[no][row][px] += sum_{ni,u,v} in[ni](row+u, px+v) * w[(no*NIN+ni)*K*K + u*K + v]
 // where `in` and `acc` are float2 pairs (two correlations per packed FFMA2) and w is a broadcast scalar from constant
-// memory.  MULX turns a stored {x, c} pair into {x*c, c} on the fly (forward); the backward feeds {GN, GD} as is.
-template <int NIN, int NOUT, int K, bool MULX>
+// memory.  The forward feeds {x*c, c} (premul_planes below), the backward {GN, GD}.
+template <int NIN, int NOUT, int K>
 __device__ __forceinline__ void conv_patch(const float2* planes, const float* __restrict__ w, int tx, int ty,
                                            float2 (&acc)[NOUT][8][2]) {
     using C = TileCfg<K>;
@@ -110,8 +113,8 @@ __device__ __forceinline__ void conv_patch(const float2* planes, const float* __
 #pragma unroll
     for (int ni = 0; ni < NIN; ++ni) {
         const float2* row0 = planes + ni * C::PLANE + (ty * 8) * C::SWP + tx * 2;
-#pragma unroll
-        for (int ir = 0; ir < 8 + K - 1; ++ir) {
+        static_for<8 + K - 1>([&](auto ir_c) {
+            constexpr int ir = decltype(ir_c)::value;
             float2 in[NP];
 #pragma unroll
             for (int t = 0; t < NP / 2; ++t) {
@@ -119,14 +122,10 @@ __device__ __forceinline__ void conv_patch(const float2* planes, const float* __
                 in[2 * t] = make_float2(a.x, a.y);
                 in[2 * t + 1] = make_float2(a.z, a.w);
             }
-            if constexpr (MULX) {
-#pragma unroll
-                for (int t = 0; t < NP; ++t) in[t].x *= in[t].y;
-            }
-#pragma unroll
-            for (int orow = 0; orow < 8; ++orow) {
-                const int u = ir - orow;
-                if (u >= 0 && u < K) {
+            static_for<8>([&](auto orow_c) {
+                constexpr int orow = decltype(orow_c)::value;
+                constexpr int u = ir - orow;
+                if constexpr (u >= 0 && u < K) {
 #pragma unroll
                     for (int v = 0; v < K; ++v)
 #pragma unroll
@@ -136,8 +135,24 @@ __device__ __forceinline__ void conv_patch(const float2* planes, const float* __
                             acc[no][orow][1] = ffma2(in[XO + v + 1], bcast(wv), acc[no][orow][1]);
                         }
                 }
-            }
-        }
+            });
+        });
+    }
+}
+
+// {x, c} -> {x*c, c} in place over `nplanes` staged planes.  Done once per CTA in shared memory (two pairs per 16-byte
+// access) rather than per thread in registers: multiplying one half of a register pair in the FFMA2 loop made ptxas copy
+// the pairs around (1183 MOVs per 1600 FFMA2).
+template <int K, int NT>
+__device__ __forceinline__ void premul_planes(float2* planes, int nplanes, int tid) {
+    using C = TileCfg<K>;
+    float4* p = reinterpret_cast<float4*>(planes);
+    const int total = nplanes * C::PLANE / 2;
+    for (int i = tid; i < total; i += NT) {
+        float4 a = p[i];
+        a.x *= a.y;
+        a.z *= a.w;
+        p[i] = a;
     }
 }
 
@@ -146,7 +161,7 @@ template <int CI, int K>
 __global__ void __launch_bounds__(128) nconv_fwd_kernel(const __grid_constant__ Maps2 maps, SrcP s0, SrcP s1, int has1,
                                                         float2* __restrict__ out, int H, int W, int wimg) {
     using C = TileCfg<K>;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     float2* planes = align128(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(planes + CI * C::PLANE);
     const int tid = threadIdx.x;
@@ -156,13 +171,15 @@ __global__ void __launch_bounds__(128) nconv_fwd_kernel(const __grid_constant__ 
     const bool pending = stage_sources<K, 128>(maps, s0, s1, has1 != 0, n, h0, w0, H, W, planes, bar, tid);
     __syncthreads();
     if (pending) mbar_wait(bar, 0);
+    premul_planes<K, 128>(planes, CI, tid);
+    __syncthreads();
 
     const int tx = tid & 31, ty = tid >> 5;
     const int oh = h0 + ty * 8, ow = w0 + tx * 2;
     if (oh >= H || ow >= W) return;
 
     float2 acc[2][8][2];
-    conv_patch<CI, 2, K, true>(planes, wc, tx, ty, acc);
+    conv_patch<CI, 2, K>(planes, wc, tx, ty, acc);
 
     const long long plane = (long long)H * W;
     const bool vec = (W & 1) == 0;

@@ -1,0 +1,1 @@
+"""Drop-in counterparts of the hot-path pieces of the reference's ``dataloaders`` package."""

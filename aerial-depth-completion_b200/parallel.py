@@ -1,0 +1,51 @@
+"""Data-parallel training step: one process per GPU, gradients of all parameters live in ONE flat fp32 buffer that is
+all-reduced over NCCL (NVLink 5 / NVSwitch) after backward.
+
+Replaces the reference's single-process ``nn.DataParallel`` (confidence_depth_framework.py:145-159, which re-broadcasts
+every parameter and gathers every output each step) with the torch.distributed layout of SURVEY.md 8e: frames are
+independent, the only coupling is the gradient sum (1.9 MB for GED .. 65 MB for gudepthcompnet18); BatchNorm statistics
+stay per replica like under DataParallel.  The step is sync-free on the host (the loss is returned as a device tensor).
+"""
+import torch
+import torch.distributed as dist
+
+
+class DataParallelTrainer:
+    def __init__(self, model, criterion, optimizer, params, world_size=1, process_group=None):
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        self.world, self.group = int(world_size), process_group
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=self.params[0].dtype)
+        off = 0
+        for p in self.params:       # .grad of every parameter is a view into the flat buffer: backward fills the bucket
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        if hasattr(criterion, "lazy"):
+            criterion.lazy = True   # keep loss bookkeeping on the device (no .item() per step)
+        for sub in ("net_a", "net_b"):
+            if hasattr(criterion, sub) and hasattr(getattr(criterion, sub), "lazy"):
+                getattr(criterion, sub).lazy = True
+        if self.world > 1:
+            for p in list(model.parameters()) + list(model.buffers()):   # identical replicas, once (not per step)
+                dist.broadcast(p.data, 0, group=self.group)
+
+    def forward_loss(self, inp, target):
+        pred = self.model(inp)
+        target_depth = target[:, 0:1, :, :]
+        if pred[2] is not None:
+            return self.criterion(inp, pred[0][:, 0:1], pred[2][:, 0:1], target_depth), pred
+        return self.criterion(inp, pred[0][:, 0:1], target_depth), pred
+
+    def step(self, inp, target):
+        """forward + loss + zero_grad + backward + gradient all-reduce + optimizer step (trainer.py:202-216)."""
+        loss, _ = self.forward_loss(inp, target)
+        self.flat.zero_()
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat.div_(self.world)
+        self.optimizer.step()
+        return loss.detach()

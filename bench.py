@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the NConv depth-completion hot path (BASELINE.json metric: frames/sec forward+backward at NYU
+228x304, batch per GPU, 1/2/4/8 B200; NConv achieved HBM GB/s as a fraction of the measured peak).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's arm (one JSON line from rank 0)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU implementation (oracle port)
+  N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): ged_depthcompnet, --training-mode dc1_only, masked-L2, fp32, synthetic NYU-shape frames
+(SURVEY.md 8d), one step = forward + loss + zero_grad + backward (+ gradient all-reduce for N > 1) + Adam step over
+`--batch` frames per GPU.  `value` times steps whose inputs are resident in HBM; `e2e` times the same step through the
+public API with the frames coming from pinned host memory (H2D inside the timed region) and the loss read back (D2H).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 228, 304
+METRIC = "frames/sec fwd+bwd (NYU 228x304, bs per GPU)"
+WORKLOAD = "ged_depthcompnet dc1_only masked-l2 train step (fwd+loss+bwd+adam), rgbd 228x304 synthetic NYUv2-shape"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--cpu-frames", type=int, default=0, help="frames per step of the CPU arms (0 = auto)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm restated in oracle/ (the Python reference cannot travel to the GPU box)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, frames):
+    """GED dc1_only train step on the host cores with all threads: returns (frames/s, ms/step, cores, frames)."""
+    import torch
+    from oracle import loss_metrics_oracle as lm
+    from oracle import nets_oracle as nets
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    template = ged_template()
+    S = synth.seeded_state({"dc_model." + k: v for k, v in template.items()}, seed=0)
+    for k in S:
+        S[k].requires_grad_(True)
+    params = [S[k] for k in S]
+    opt = torch.optim.Adam(params, lr=1e-5)
+    inp, tgt = synth.synth_frames(frames, H, W, seed=1234)
+
+    def step():
+        d1, _, _ = nets.framework_forward(S, inp, "dc1_only", "ged_depthcompnet", 4, training=True)
+        loss = lm.masked_loss("l2", d1, tgt)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return frames * steps / dt, dt / steps * 1e3, cores, frames
+
+
+def ged_template():
+    """state_dict shapes of ged_depthcompnet with one output channel (confidence_depth_framework.py:426-452)."""
+    t = {}
+    for i, (co, ci, k) in enumerate(((2, 1, 5), (2, 2, 5), (2, 2, 5), (2, 4, 3), (2, 4, 3), (2, 4, 3), (1, 2, 1)), 1):
+        t["d_net.nconv%d.weight" % i] = (co, ci, k, k)
+        t["d_net.nconv%d.bias" % i] = (co,)
+    for i, (ci, co) in enumerate(((5, 80), (80, 80), (80, 80), (80, 80), (80, 80), (160, 64), (144, 64), (144, 32), (112, 32), (33, 1)), 1):
+        t["conv%d.weight" % i] = (co, ci, 3, 3)
+        t["conv%d.bias" % i] = (co,)
+    return t
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = args.cpu_frames or 1
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    fps, ms, cores, frames = cpu_reference_run(steps, warmup, frames)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": frames, "device": "host CPU"},
+        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d timed steps of %d frame(s) of the same workload with torch CPU ops (oracle/, the reference's "
+                                   "algorithm restated; the Python reference cannot travel to the GPU box)" % (steps, frames)},
+        "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    from aerial_depth_completion_b200 import _lib, parallel
+    from aerial_depth_completion_b200.dataloaders.dense_to_sparse import UniformSampling
+    import numpy as np
+    import contextlib
+    import io
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    # model: reference constructors' distributions under manual_seed(0) (same seed on every rank => identical replicas)
+    torch.manual_seed(0)
+    factory = mc.ConfidenceDepthFrameworkFactory()
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = factory.create_model("rgbd", "dc1_only", "ged_depthcompnet", "")
+        model, params = factory.to_device(model)
+        model.train()
+    criterion, _ = factory.create_loss("l2", False, 0.5)
+    optimizer = torch.optim.Adam(params, lr=1e-5)
+    trainer = parallel.DataParallelTrainer(model, criterion, optimizer, params, world_size=world)
+
+    # synthetic frames: a pool larger than L2 so no step finds its inputs cached
+    pool_n = 8
+    g = torch.Generator().manual_seed(1234 + rank)
+    sampler = UniformSampling(500, np.inf)
+    host_in, host_tg = [], []
+    for i in range(pool_n):
+        rgb = torch.rand(B, 3, H, W, generator=g)
+        gt = torch.rand(B, 1, H, W, generator=g) * 9.0 + 1.0
+        masks = []
+        for b in range(B):
+            np.random.seed(1234 + 1000 * rank + i * B + b)
+            masks.append(sampler.dense_to_sparse(None, gt[b, 0].numpy()))
+        mask = torch.from_numpy(np.stack(masks)).unsqueeze(1).float()
+        host_in.append(torch.cat((rgb, gt * mask, mask), 1).pin_memory())
+        host_tg.append(gt.pin_memory())
+    dev_in = [t.to(dev) for t in host_in]
+    dev_tg = [t.to(dev) for t in host_tg]
+    pool_mb = sum(t.numel() * 4 for t in dev_in + dev_tg) / 1e6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    resident = lambda i: trainer.step(dev_in[i % pool_n], dev_tg[i % pool_n])
+
+    def from_host(i):
+        x = host_in[i % pool_n].to(dev, non_blocking=True)
+        t = host_tg[i % pool_n].to(dev, non_blocking=True)
+        loss = trainer.step(x, t)
+        return float(loss)          # D2H read of the step's result
+
+    for i in range(args.warmup):
+        resident(i)
+    launches0 = _lib.lib.adc_launch_count()
+    sampler_thread = ClockSampler(local)
+    if rank == 0:
+        sampler_thread.start()
+    ms_total = timed(resident, args.steps)
+    launches = _lib.lib.adc_launch_count() - launches0
+    for i in range(min(3, args.warmup)):
+        from_host(i)
+    ms_e2e = timed(from_host, args.steps)
+    sampler_thread.stop_flag = True
+
+    # per-kernel CUDA-event timing of the same step (profiling pass after the timed region)
+    roof = kernel_roofline(trainer, dev_in, dev_tg, pool_n, B)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    frames = B * world * args.steps
+    line = {
+        "metric": METRIC, "value": round(frames / ms_total * 1e3, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": "dp%d (one process per GPU, NCCL all-reduce of flat fp32 gradients)" % world,
+                   "l2": "inputs rotate through a %.0f MB pool of distinct batches (> 126 MB L2)" % pool_mb,
+                   "dense_backend": __import__("aerial_depth_completion_b200.dense", fromlist=["BACKEND"]).BACKEND,
+                   "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
+        "clocks": sampler_thread.summary(),
+        "e2e": {"value": round(frames / ms_e2e * 1e3, 2), "unit": "frames/s", "h2d_bytes_per_step": B * 6 * H * W * 4,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+    }
+    if roof:
+        dom = roof["dominant"]
+        line["roofline"] = {"bound": "hbm", "achieved": round(dom["gbs"], 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(dom["gbs"] / peak, 4), "traffic": None, "kernel": dom["name"],
+                            "launch_us": round(dom["us"], 2), "algorithmic_mb_per_launch": round(dom["mb"], 2),
+                            "peak_source": peak_src, "nconv_kernels": roof["table"]}
+    if not args.no_cpu_baseline and world == 1:
+        fps, ms, cores, fr = cpu_reference_run(3, 1, args.cpu_frames or 1)
+        line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "3 timed steps of %d frame(s) of the same workload with torch CPU ops (oracle/)" % fr}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B):
+    """Average launch duration (CUDA events on the launching stream, recorded by the library around every kernel) and
+    algorithmic HBM bytes of each NConv kernel inside the training step."""
+    import ctypes
+    import torch
+    from aerial_depth_completion_b200._lib import lib
+    names = {0: "nconv_fwd", 1: "nconv_bwd_data", 2: "nconv_bwd_weight", 3: "pool_fwd", 4: "pool_bwd", 5: "upsample_bwd",
+             6: "head_fwd", 7: "head_bwd"}
+    calls = ("nconv1@L0", "nconv2@L0", "nconv3@L0", "nconv2@L1", "nconv3@L1", "nconv2@L2", "nconv2@L3", "nconv4@L2", "nconv5@L1",
+             "nconv6@L0", "nconv7@L0")
+    agg = {}
+    reps = 3
+    for i in range(reps):
+        lib.adc_profile_enable(1)
+        trainer.step(dev_in[i % pool_n], dev_tg[i % pool_n])
+        torch.cuda.synchronize()
+        n = ctypes.c_int(0)
+        kinds = (ctypes.c_int * 512)()
+        cl = (ctypes.c_int * 512)()
+        ms = (ctypes.c_float * 512)()
+        by = (ctypes.c_double * 512)()
+        lib.adc_profile_read(512, ctypes.byref(n), kinds, cl, ms, by)
+        lib.adc_profile_enable(0)
+        for j in range(n.value):
+            if kinds[j] not in names or by[j] <= 0:
+                continue
+            key = names[kinds[j]] + (":" + calls[cl[j]] if kinds[j] < 3 and 0 <= cl[j] < 11 else "")
+            a = agg.setdefault(key, [0.0, 0.0, 0])
+            a[0] += ms[j] * 1e3
+            a[1] += by[j]
+            a[2] += 1
+    if not agg:
+        return None
+    table = []
+    for k, (us, byts, cnt) in agg.items():
+        table.append({"name": k, "us": round(us / cnt, 2), "mb": round(byts / cnt / 1e6, 2), "gbs": round(byts / us / 1e3, 1),
+                      "launches_per_step": cnt // reps, "us_per_step": round(us / reps, 2)})
+    table.sort(key=lambda r: -r["us_per_step"])
+    d = table[0]
+    return {"dominant": {"name": d["name"], "us": d["us"], "mb": d["mb"], "gbs": d["gbs"]}, "table": table[:12]}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        b200_arm(a)

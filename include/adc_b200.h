@@ -35,6 +35,14 @@ typedef void* adc_stream_t; /* cudaStream_t */
 int adc_abi_version(void);
 const char* adc_last_error(void);
 
+/* Instrumentation (bench.py): number of kernels this library has launched so far, and optional per-kernel timing with
+ * CUDA events recorded on the launching stream around every kernel (kind: 0 nconv fwd, 1 nconv bwd data, 2 nconv bwd
+ * weight, 3 pool fwd, 4 pool bwd, 5 upsample bwd, 6 head fwd, 7 head bwd, 8 pack/unpack, 9 reduce, 10 prep; call = pyramid
+ * call index; bytes = the kernel's algorithmic HBM bytes).  adc_profile_read synchronises on the recorded events. */
+long long adc_launch_count(void);
+int adc_profile_enable(int on);
+int adc_profile_read(int max_records, int* n_out, int* kinds, int* calls, float* ms, double* bytes);
+
 /* ---- a source of input channels for one NConv2d call ------------------------------------------
  * `channels` planes of data `x` and confidence `c` of size H x W.  If (H,W) differs from the layer's
  * output size the source is read through ATen's nearest-neighbour index map, i.e. it stands for

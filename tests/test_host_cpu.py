@@ -88,3 +88,13 @@ def test_seeded_construction_equals_reference():
     assert list(a.keys()) == list(b.keys())
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_sampling_mask_bit_exact():
+    import numpy as np
+    G = gold("sampling_metrics")
+    from aerial_depth_completion_b200.dataloaders.dense_to_sparse import UniformSampling
+    depth = (np.arange(228 * 304).reshape(228, 304) % 17).astype(np.float64)
+    for s in (0, 7, 1234):
+        np.random.seed(s)
+        assert np.array_equal(np.flatnonzero(UniformSampling(500, np.inf).dense_to_sparse(None, depth)), G["mask_seed%d" % s])
