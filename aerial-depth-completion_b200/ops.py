@@ -183,10 +183,12 @@ class PyramidFunction(torch.autograd.Function):
         a.saved, a.idx, a.xout, a.cout = saved.data_ptr(), idx.data_ptr(), xout.data_ptr(), cout.data_ptr()
         check(lib.adc_pyramid_fwd(ctypes.byref(a), _stream()), "adc_pyramid_fwd")
         if training:
-            # EnforcePos (model_zoo/nconv.py:114-117): the Parameters now hold softplus^calls of what they held
+            # EnforcePos (model_zoo/nconv.py:114-117): the Parameters now hold softplus^calls of what they held.  The values
+            # are copied INTO the parameter storage (the reference rebinds .data; the observable contents are the same) so
+            # parameter addresses stay fixed -- required for CUDA-graph replay and for flat-bucket data parallelism.
             o = 0
             for i, name in enumerate(PYR_MODULES):
-                getattr(module, name).weight.data = weight_out[o:o + _PYR_WNUMEL[i]].view(_PYR_SHAPES[i])
+                getattr(module, name).weight.data.copy_(weight_out[o:o + _PYR_WNUMEL[i]].view(_PYR_SHAPES[i]))
                 o += _PYR_WNUMEL[i]
         ctx.save_for_backward(x0, c0, saved, idx, xout, cout, *bs)
         ctx.module, ctx.bs, ctx.dims = module, bsx, (n, h, w)

@@ -36,6 +36,7 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-frames", type=int, default=0, help="frames per step of the CPU arms (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     return p.parse_args()
 
 
@@ -174,7 +175,7 @@ def b200_arm(args):
         model, params = factory.to_device(model)
         model.train()
     criterion, _ = factory.create_loss("l2", False, 0.5)
-    optimizer = torch.optim.Adam(params, lr=1e-5)
+    optimizer = torch.optim.Adam(params, lr=1e-5, capturable=not args.no_graph)
     trainer = parallel.DataParallelTrainer(model, criterion, optimizer, params, world_size=world)
 
     # synthetic frames: a pool larger than L2 so no step finds its inputs cached
@@ -222,6 +223,12 @@ def b200_arm(args):
         loss = trainer.step(x, t)
         return float(loss)          # D2H read of the step's result
 
+    launches_per_step = None
+    if not args.no_graph:
+        l0 = _lib.lib.adc_launch_count()
+        trainer._eager_step(dev_in[0], dev_tg[0])
+        launches_per_step = _lib.lib.adc_launch_count() - l0      # the graph replays exactly these launches
+        trainer.capture(dev_in[0], dev_tg[0])
     for i in range(args.warmup):
         resident(i)
     launches0 = _lib.lib.adc_launch_count()
@@ -230,6 +237,8 @@ def b200_arm(args):
         sampler_thread.start()
     ms_total = timed(resident, args.steps)
     launches = _lib.lib.adc_launch_count() - launches0
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps
     for i in range(min(3, args.warmup)):
         from_host(i)
     ms_e2e = timed(from_host, args.steps)
@@ -252,6 +261,7 @@ def b200_arm(args):
                    "parallelism": "dp%d (one process per GPU, NCCL all-reduce of flat fp32 gradients)" % world,
                    "l2": "inputs rotate through a %.0f MB pool of distinct batches (> 126 MB L2)" % pool_mb,
                    "dense_backend": __import__("aerial_depth_completion_b200.dense", fromlist=["BACKEND"]).BACKEND,
+                   "launch": "eager" if args.no_graph else "one CUDA graph per step (forward+loss+backward+allreduce+adam)",
                    "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
         "clocks": sampler_thread.summary(),
         "e2e": {"value": round(frames / ms_e2e * 1e3, 2), "unit": "frames/s", "h2d_bytes_per_step": B * 6 * H * W * 4,
@@ -287,7 +297,7 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B):
     reps = 3
     for i in range(reps):
         lib.adc_profile_enable(1)
-        trainer.step(dev_in[i % pool_n], dev_tg[i % pool_n])
+        trainer._eager_step(dev_in[i % pool_n], dev_tg[i % pool_n])
         torch.cuda.synchronize()
         n = ctypes.c_int(0)
         kinds = (ctypes.c_int * 512)()
