@@ -55,6 +55,8 @@ enum { KIND_FWD = 0, KIND_BWD_DATA = 1, KIND_BWD_WEIGHT = 2, KIND_POOL_FWD = 3, 
 static int g_cur_call = -1;   // pyramid call index of the launches being issued (for the profile records)
 
 static float* g_stage = nullptr;  // [ADC_WSLOTS][2][ADC_PYR_CALLS][kWStride] device staging for the single-layer API
+static int* g_counters = nullptr; // tile-scheduler counters of the persistent kernels (self-resetting)
+static int g_persist = 1, g_sms = 148;
 static int g_use_tma = -1;
 
 static int ensure_init() {
@@ -63,6 +65,13 @@ static int ensure_init() {
         g_use_tma = (e && e[0] == '1') ? 0 : 1;
     }
     if (g_stage) return 0;
+    const char* pe = getenv("ADC_FWD_MODE");     // 0: one tile per CTA, 2: persistent, 1 (default): persistent only for gathered sources
+    g_persist = pe ? atoi(pe) : 1;
+    int dev = 0;
+    ADC_CUDA(cudaGetDevice(&dev));
+    ADC_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    ADC_CUDA(cudaMalloc(&g_counters, sizeof(int) * 64));
+    ADC_CUDA(cudaMemset(g_counters, 0, sizeof(int) * 64));
     ADC_CUDA(cudaMalloc(&g_stage, sizeof(float) * ADC_WSLOTS * 2 * ADC_PYR_CALLS * kWStride));
     return 0;
 }
@@ -135,8 +144,40 @@ static inline int tiles(int N, int H, int W) { return N * ceil_div(W, 64) * ceil
 static inline int blocks_1x1(long long plane) { return (int)ceil_div_ll(plane, 512); }
 
 template <int CI, int K>
+static int launch_fwd_persist(const SrcP& s0, const SrcP* s1, float2* out, int N, int H, int W, int wimg, cudaStream_t st) {
+    using C = TileCfg<K>;
+    static bool done = false;
+    static int ctas_per_sm = 1;
+    const int smem = C::smem_bytes(2);
+    if (!done) {
+        int rc = set_smem(nconv_fwd_persist_kernel<CI, K>, smem);
+        if (rc) return rc;
+        ADC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, nconv_fwd_persist_kernel<CI, K>, 128, smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        done = true;
+    }
+    Maps2 maps;
+    int rc = fill_maps<K>(&maps, s0, s1, N);
+    if (rc) return rc;
+    TileSched sch;
+    sch.tiles_x = ceil_div(W, C::TW);
+    sch.tiles_y = ceil_div(H, C::TH);
+    sch.ntiles = sch.tiles_x * sch.tiles_y * N;
+    sch.counters = g_counters + 2 * (wimg / (2 * ADC_PYR_CALLS));     // one counter pair per weight slot
+    const int grid = sch.ntiles < g_sms * ctas_per_sm ? sch.ntiles : g_sms * ctas_per_sm;
+    { ProfScope _p(st, KIND_FWD, g_cur_call, 8.0 * (CI + 2) * N * H * W);
+    nconv_fwd_persist_kernel<CI, K><<<grid, 128, smem, st>>>(maps, s0, s1 ? *s1 : s0, s1 ? 1 : 0, out, H, W, wimg, sch); }
+    return check_cuda(cudaGetLastError(), "nconv_fwd_persist_kernel launch");
+}
+
+template <int CI, int K>
 static int launch_fwd(const SrcP& s0, const SrcP* s1, float2* out, int N, int H, int W, int wimg, cudaStream_t st) {
     using C = TileCfg<K>;
+    // Measured (profiles/r1_forward_variants.txt): with every source TMA-fed the one-tile-per-CTA kernel is fastest (27 us vs
+    // 32 us for nconv2@L0, B=32); when a source goes through the gather path (nearest-upsampled half of nconv4-6) the
+    // persistent kernel with cp.async prefetch wins (43 us vs 61 us for nconv6@L0).
+    const bool gathered = !s0.tma || (s1 && !s1->tma);
+    if (g_persist == 2 || (g_persist == 1 && gathered)) return launch_fwd_persist<CI, K>(s0, s1, out, N, H, W, wimg, st);
     static bool done = false;
     const int smem = C::smem_bytes(CI);
     if (!done) { int rc = set_smem(nconv_fwd_kernel<CI, K>, smem); if (rc) return rc; done = true; }

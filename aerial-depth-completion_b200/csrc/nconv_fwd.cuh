@@ -204,6 +204,193 @@ __global__ void __launch_bounds__(128) nconv_fwd_kernel(const __grid_constant__ 
     }
 }
 
+// ---- persistent, double-buffered variant ---------------------------------------------------------------------------------
+// One CTA per SM slot loops over tiles handed out by an atomic counter (SM-level load balance: 1280 tiles over 148 SMs is
+// 8.65 per SM -> 9 rounds instead of the 2 partially filled waves of a one-tile-per-CTA grid) and prefetches the NEXT
+// tile (TMA boxes on a per-stage mbarrier, cp.async 8-byte gathers for mapped sources) while it computes the current one,
+// so the FMA pipe does not wait for HBM.
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool valid) {
+    const int sz = valid ? 8 : 0;   // src-size 0 => the 8 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K, int NT>
+__device__ __forceinline__ void gather_pair_tile_async(const SrcP& s, int sc, int n, int h0, int w0, int H, int W, float2* dst,
+                                                       int tid) {
+    using C = TileCfg<K>;
+    constexpr int P = C::P, TOTAL = C::SH * C::SWP;
+    const float2* base = s.p + (long long)n * s.bs + (long long)sc * s.H * s.W;
+    for (int i = tid; i < TOTAL; i += NT) {
+        const int r = i / C::SWP, col = i - r * C::SWP;
+        const int gh = h0 - P + r, gw = w0 - P - C::XOFF + col;
+        const bool ok = gh >= 0 && gh < H && gw >= 0 && gw < W;
+        const long long off = ok ? (long long)s.mh(gh) * s.W + s.mw(gw) : 0;
+        cp_async8(dst + i, base + off, ok);
+    }
+}
+
+struct TileSched {
+    int* counters;   // [0] next tile, [1] finished CTAs (self-resetting: the last CTA to leave zeroes both)
+    int tiles_x, tiles_y, ntiles;
+};
+
+// One input plane of the conv core: acc[no][row][px] += sum_{u,v} plane(row+u, px+v) * w[(no*NIN + ni)*K*K + u*K + v].
+template <int NIN, int NOUT, int K>
+__device__ __forceinline__ void conv_patch_plane(const float2* plane, const float* __restrict__ w, int ni, int tx, int ty,
+                                                 float2 (&acc)[NOUT][8][2]) {
+    using C = TileCfg<K>;
+    constexpr int XO = C::XOFF;
+    constexpr int NP = (2 + K - 1 + XO + 1) & ~1;
+    const float2* row0 = plane + (ty * 8) * C::SWP + tx * 2;
+    const float* wn = w + ni * K * K;
+    static_for<8 + K - 1>([&](auto ir_c) {
+        constexpr int ir = decltype(ir_c)::value;
+        float2 in[NP];
+#pragma unroll
+        for (int t = 0; t < NP / 2; ++t) {
+            const float4 a = *reinterpret_cast<const float4*>(row0 + ir * C::SWP + 2 * t);
+            in[2 * t] = make_float2(a.x, a.y);
+            in[2 * t + 1] = make_float2(a.z, a.w);
+        }
+        static_for<8>([&](auto orow_c) {
+            constexpr int orow = decltype(orow_c)::value;
+            constexpr int u = ir - orow;
+            if constexpr (u >= 0 && u < K) {
+#pragma unroll
+                for (int v = 0; v < K; ++v)
+#pragma unroll
+                    for (int no = 0; no < NOUT; ++no) {
+                        const float wv = wn[no * NIN * K * K + u * K + v];
+                        acc[no][orow][0] = ffma2(in[XO + v], bcast(wv), acc[no][orow][0]);
+                        acc[no][orow][1] = ffma2(in[XO + v + 1], bcast(wv), acc[no][orow][1]);
+                    }
+            }
+        });
+    });
+}
+
+// Persistent forward kernel, pipelined at the granularity of ONE input-channel plane of one tile: two plane buffers per
+// CTA (39 KB for any Ci, so 5 CTAs = 20 warps per SM stay resident); while the warps accumulate plane q, the TMA box (or the
+// cp.async gather) of plane q+1 -- the next channel of this tile or the first channel of the CTA's next tile -- is in flight.
+template <int CI, int K>
+__global__ void __launch_bounds__(128) nconv_fwd_persist_kernel(const __grid_constant__ Maps2 maps, SrcP s0, SrcP s1, int has1,
+                                                                float2* __restrict__ out, int H, int W, int wimg, TileSched sch) {
+    using C = TileCfg<K>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float2* buf0 = align128(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(buf0 + 2 * C::PLANE);
+    __shared__ int s_next[2];
+    const int tid = threadIdx.x;
+    const float* wc = &c_wimg[0][0][0][0] + (size_t)wimg * kWStride;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        s_next[0] = atomicAdd(&sch.counters[0], 1);
+    }
+    __syncthreads();
+
+    // plane `ci` of tile `tile` -> buffer `b`; returns true if the copy went through cp.async (per-thread group committed)
+    auto issue = [&](int tile, int ci, int b) -> bool {
+        const int tx_ = tile % sch.tiles_x, ty_ = (tile / sch.tiles_x) % sch.tiles_y, n = tile / (sch.tiles_x * sch.tiles_y);
+        const int h0 = ty_ * C::TH, w0 = tx_ * C::TW;
+        const bool first = ci < s0.ch;
+        const SrcP& s = first ? s0 : s1;
+        const int sc = first ? ci : ci - s0.ch;
+        float2* dst = buf0 + b * C::PLANE;
+        if (s.tma) {
+            if (tid == 0) {
+                mbar_expect_tx(&bars[b], (uint32_t)(C::SH * C::SWP * 8));
+                tma_load_plane(dst, first ? &maps.m0 : &maps.m1, &bars[b], 2 * (w0 - C::P - C::XOFF), h0 - C::P, sc, n);
+            }
+            return false;
+        }
+        gather_pair_tile_async<K, 128>(s, sc, n, h0, w0, H, W, dst, tid);
+        cp_async_commit();
+        return true;
+    };
+    auto plane_is_tma = [&](int ci) { return (ci < s0.ch ? s0.tma : s1.tma) != 0; };
+
+    int tile = s_next[0];
+    int q = 0;                     // global plane-step counter of this CTA: buffer = q & 1, mbarrier parity = (q >> 1) & 1
+    int uses0 = 0, uses1 = 0;      // completed TMA phases per buffer (parity tracking when TMA and gather planes alternate)
+    if (tile < sch.ntiles) issue(tile, 0, 0);
+    while (tile < sch.ntiles) {
+        if (tid == 0) s_next[1] = atomicAdd(&sch.counters[0], 1);
+        int next = -1;             // read after the first barrier of this tile
+        const int tx_ = tile % sch.tiles_x, ty_ = (tile / sch.tiles_x) % sch.tiles_y, n = tile / (sch.tiles_x * sch.tiles_y);
+        const int tx = tid & 31, ty = tid >> 5;
+        const int oh = ty_ * C::TH + ty * 8, ow = tx_ * C::TW + tx * 2;
+        const bool active = oh < H && ow < W;
+        float2 acc[2][8][2];
+#pragma unroll
+        for (int co = 0; co < 2; ++co)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[co][r][0] = acc[co][r][1] = make_float2(0.f, 0.f);
+
+        static_for<CI>([&](auto ci_c) {
+            constexpr int ci = decltype(ci_c)::value;
+            const int b = q & 1;
+            if constexpr (ci == 0) {
+                __syncthreads();                     // publishes s_next[1] (next write is a whole tile later)
+                next = s_next[1];
+            }
+            // prefetch the following plane into the other buffer (released by the barrier that ended the previous step)
+            bool nxt_async = false;
+            if (ci + 1 < CI) nxt_async = issue(tile, ci + 1, b ^ 1);
+            else if (next < sch.ntiles) nxt_async = issue(next, 0, b ^ 1);
+            // wait for this step's plane
+            if (plane_is_tma(ci)) {
+                if (b == 0) { mbar_wait(&bars[0], uses0 & 1); ++uses0; }
+                else        { mbar_wait(&bars[1], uses1 & 1); ++uses1; }
+            } else {
+                if (nxt_async) cp_async_wait<1>(); else cp_async_wait<0>();
+            }
+            __syncthreads();
+            premul_planes<K, 128>(buf0 + b * C::PLANE, 1, tid);
+            __syncthreads();
+            if (active) conv_patch_plane<CI, 2, K>(buf0 + b * C::PLANE, wc, ci, tx, ty, acc);
+            __syncthreads();                         // all reads of buffer b done -> it may be refilled by the next step's prefetch
+            ++q;
+        });
+
+        if (active) {
+            const long long plane = (long long)H * W;
+            const bool vec = (W & 1) == 0;
+#pragma unroll
+            for (int co = 0; co < 2; ++co) {
+                const float b = wc[kWBias + co], is = wc[kWInvSum + co];
+                float2* o = out + ((long long)n * 2 + co) * plane + ow;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int h = oh + r;
+                    if (h >= H) break;
+                    const float2 a0 = acc[co][r][0], a1 = acc[co][r][1];
+                    const float2 r0 = make_float2(fmaf(a0.x, rcp_approx(a0.y + kEps), b), a0.y * is);
+                    const float2 r1 = make_float2(fmaf(a1.x, rcp_approx(a1.y + kEps), b), a1.y * is);
+                    if (vec) {
+                        *reinterpret_cast<float4*>(o + (long long)h * W) = make_float4(r0.x, r0.y, r1.x, r1.y);
+                    } else {
+                        o[(long long)h * W] = r0;
+                        if (ow + 1 < W) o[(long long)h * W + 1] = r1;
+                    }
+                }
+            }
+        }
+        tile = next;
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&sch.counters[1], 1) == (int)gridDim.x - 1) {   // last CTA out: leave the counters clean for the next launch
+            sch.counters[0] = 0;
+            sch.counters[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // nconv7: 2 -> 1, 1x1 (model_zoo/nconv_sd.py:32).  Reads the {x,c} pairs of both channels, writes the planar
 // xout / cout tensors the caller sees.  Purely HBM-bound (AI 0.3): two pixels per thread, 16-byte loads.
 __global__ void __launch_bounds__(256) nconv_1x1_fwd_kernel(const float2* __restrict__ in, float* __restrict__ y,
