@@ -1,0 +1,466 @@
+// K5: dense 3x3 convolution as an implicit GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA), for the wide layers around the NConv pyramid (model_zoo/
+// confidence_depth_framework.py:442-452,536-607).  sm_100a only.
+//
+//   out[n, oh, ow, co] = act( bias[co] + sum_{u,v,ci} W[co,ci,u,v] * in[n, oh*s+u-1, ow*s+v-1, ci] )
+//
+// Layout: activations NHWC bf16 (channel count a multiple of 16), weights bf16 [tap][Cout_pad][Cin] (tap = u*3+v).
+// GEMM view: M = 128 output pixels (a BH x BW block of one image), N = Cout_pad (<= 256), K = 9 taps x Cin.
+// For every (tap, 64/32/16-channel block) one TMA box copy brings the shifted pixel block (hardware zero fill outside
+// the image = the convolution's padding; element strides 2 implement stride-2 convolutions) and one brings the weight
+// slice, both K-major with the 128/64/32-byte hardware swizzle that the UMMA shared-memory descriptors expect.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane; also owns the TMEM
+// allocation), warps 2-5 = epilogue (tcgen05.ld of their TMEM lane quarter -> bias + activation -> bf16/fp32 store).
+// Ring of STAGES smem slots with full/empty mbarriers; tcgen05.commit releases a slot when the MMAs that read it retire.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/adc_b200.h"
+
+namespace adc {
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+}  // namespace adc
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns of this warp's TMEM lane quarter
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major operand whose rows are ROWB bytes (= the swizzle span: 128/64/32) and whose
+// 8-row swizzle atoms are packed back to back (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version 1 <<46 | layout <<61; layout 2/4/6 = SWIZZLE_128B/64B/32B).
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);
+    constexpr uint64_t sbo = (8 * ROWB) >> 4;
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
+// N>>3 at bit 17, M>>4 at bit 24.
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct ConvParams {
+    int N, H, W;            // input image size
+    int Ho, Wo;             // output size
+    int cin, npad, cout;    // Cin (multiple of 16), Cout padded to 16, real Cout
+    int stride;             // 1 or 2
+    int BW, BH;             // output pixel block, BW*BH = 128
+    int tiles_x, tiles_y;
+    int act;                // 0 none, 1 relu, 2 leaky-relu(0.2), 3 sigmoid
+    int out_f32;            // 1: fp32 output, 0: bf16
+    long long out_pix_stride;   // elements between consecutive pixels in the output (>= cout: lets a layer write a channel slice)
+    int out_ch_off;
+    void* out;
+    const float* bias;      // may be null
+};
+
+constexpr int kStages = 4;
+
+template <int KBLK>   // channels per K step: 64 / 32 / 16  (row bytes 128 / 64 / 32)
+__global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                               const __grid_constant__ CUtensorMap map_w, ConvParams p) {
+    constexpr int ROWB = KBLK * 2;
+    constexpr int A_BYTES = 128 * ROWB;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int b_bytes = p.npad * ROWB;
+    const int stage_bytes = (A_BYTES + b_bytes + 1023) & ~1023;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);   // full[kStages], empty[kStages], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+    const int ow0 = tx * p.BW, oh0 = ty * p.BH;
+    const int kblocks = (p.cin + KBLK - 1) / KBLK;
+    const int ksteps = 9 * kblocks;
+    uint32_t ncols = 32;
+    while ((int)ncols < p.npad) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bars[s], 1);
+            mbar_init(&bars[kStages + s], 1);
+        }
+        mbar_init(&bars[2 * kStages], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int s = ks % kStages, use = ks / kStages;
+                mbar_wait(&bars[kStages + s], (use & 1) ^ 1);
+                const int kb = ks / 9, tap = ks % 9, u = tap / 3, v = tap % 3;
+                uint8_t* sa = smem + s * stage_bytes;
+                mbar_expect_tx(&bars[s], (uint32_t)(A_BYTES + b_bytes));
+                tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ow0 * p.stride + v - 1, oh0 * p.stride + u - 1, n);
+                tma_load_3d(sa + A_BYTES, &map_w, &bars[s], kb * KBLK, 0, tap);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = make_idesc(128, p.npad);
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int s = ks % kStages, use = ks / kStages;
+                mbar_wait(&bars[s], use & 1);
+                tc_fence_after();
+                const uint32_t sa = base + s * stage_bytes;
+                const uint64_t da = make_desc<ROWB>(sa), db = make_desc<ROWB>(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < KBLK / 16; ++k)    // advance 16 bf16 = 32 bytes inside the swizzled row: +2 in the >>4 address field
+                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+                umma_commit(&bars[kStages + s]);       // slot free once these MMAs have read it
+            }
+            umma_commit(&bars[2 * kStages]);           // accumulator complete
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;                      // GEMM row = pixel index in the block
+        const int oh = oh0 + m / p.BW, ow = ow0 + m % p.BW;
+        const bool valid = oh < p.Ho && ow < p.Wo;
+        mbar_wait(&bars[2 * kStages], 0);
+        tc_fence_after();
+        const long long pix = ((long long)n * p.Ho + oh) * p.Wo + ow;
+        for (int c0 = 0; c0 < p.npad; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            if (!valid) continue;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int co = c0 + j;
+                float r = v[j] + ((p.bias && co < p.cout) ? p.bias[co] : 0.f);
+                if (p.act == 1) r = fmaxf(r, 0.f);
+                else if (p.act == 2) r = r > 0.f ? r : 0.2f * r;
+                else if (p.act == 3) r = 1.f / (1.f + __expf(-r));
+                v[j] = r;
+            }
+            if (p.out_f32) {
+                float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.cout) o[j] = v[j];
+            } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
+                if (c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    __nv_bfloat162 h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(h)[0];
+                    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(h)[1];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.cout) o[j] = __float2bfloat16(v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ---- layout glue ---------------------------------------------------------------------------------------------------
+// NCHW fp32 (channel slice [c_off, c_off+C) of a tensor with Ctot channels) -> NHWC bf16 with Cpad channels (zero padded),
+// written into channels [dst_off, dst_off+Cpad) of an NHWC tensor with dst_stride channels per pixel.
+__global__ void __launch_bounds__(256) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                     int C, int Cpad, long long HW, long long src_batch_stride,
+                                                                     int dst_stride, int dst_off) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j;
+        const long long pp = p0 + tx;
+        tile[j][tx] = (c < C && pp < HW) ? src[(long long)n * src_batch_stride + (long long)c * HW + pp] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const long long pp = p0 + j;
+        const int c = c0 + tx;
+        if (pp < HW && c < Cpad) dst[((long long)n * HW + pp) * dst_stride + dst_off + c] = __float2bfloat16(tile[tx][j]);
+    }
+}
+
+// NHWC (bf16 or fp32) channel slice -> NCHW fp32
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int C,
+                                                                long long HW, int src_stride, int src_off) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const long long pp = p0 + j;
+        const int c = c0 + tx;
+        tile[j][tx] = (pp < HW && c < C) ? (float)src[((long long)n * HW + pp) * src_stride + src_off + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j;
+        const long long pp = p0 + tx;
+        if (c < C && pp < HW) dst[((long long)n * C + c) * HW + pp] = tile[tx][j];
+    }
+}
+
+// fp32 [Cout, Cin, 3, 3] -> bf16 [9][npad][cin_pad]  (zero padded)
+__global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int npad,
+                                         int cin_pad, int flip_transpose) {
+    const long long total = 9LL * npad * cin_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin_pad), co = (int)((i / cin_pad) % npad), tap = (int)(i / ((long long)cin_pad * npad));
+        float v = 0.f;
+        if (!flip_transpose) {
+            if (co < cout && ci < cin) v = w[((long long)co * cin + ci) * 9 + tap];
+        } else {   // data-gradient weights: out "channel" = original ci, in "channel" = original co, taps flipped
+            if (co < cin && ci < cout) v = w[((long long)ci * cin + co) * 9 + (8 - tap)];
+        }
+        out[i] = __float2bfloat16(v);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static CUtensorMapSwizzle swz(int kblk) {
+    return kblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+template <int KBLK>
+static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, int smem, cudaStream_t st) {
+    static bool done = false;
+    if (!done) {   // opt in once to the largest configuration of this instantiation (npad = 256)
+        const int max_smem = kStages * ((128 * KBLK * 2 + 256 * KBLK * 2 + 1023) & ~1023) + 1024 + 256;
+        int rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_fprop_tc_kernel<KBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
+                                 "cudaFuncSetAttribute(conv3x3_fprop_tc_kernel)");
+        if (rc) return rc;
+        done = true;
+    }
+    conv3x3_fprop_tc_kernel<KBLK><<<p.tiles_x * p.tiles_y * p.N, 192, smem, st>>>(mx, mw, p);
+    return adc::check_cuda(cudaGetLastError(), "conv3x3_fprop_tc_kernel launch");
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+extern "C" {
+
+int adc_nchw_to_nhwc_bf16(const float* src, void* dst, int N, int C, int Cpad, int H, int W, long long src_batch_stride,
+                          int dst_stride, int dst_off, adc_stream_t stream) {
+    if (!src || !dst || N <= 0 || C <= 0 || Cpad < C || H <= 0 || W <= 0 || dst_stride < dst_off + Cpad) {
+        adc::set_error("adc_nchw_to_nhwc_bf16: bad argument");
+        return ADC_E_BADARG;
+    }
+    const long long HW = (long long)H * W;
+    dim3 grid((unsigned)((HW + 31) / 32), (Cpad + 31) / 32, N);
+    nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, Cpad, HW, src_batch_stride,
+                                                                         dst_stride, dst_off);
+    return adc::check_cuda(cudaGetLastError(), "nchw_f32_to_nhwc_bf16_kernel launch");
+}
+
+int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int C, int H, int W, int src_stride, int src_off,
+                         adc_stream_t stream) {
+    if (!src || !dst || N <= 0 || C <= 0 || H <= 0 || W <= 0 || src_stride < src_off + C) {
+        adc::set_error("adc_nhwc_to_nchw_f32: bad argument");
+        return ADC_E_BADARG;
+    }
+    const long long HW = (long long)H * W;
+    dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
+    if (src_is_f32)
+        nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, dst, C, HW, src_stride, src_off);
+    else
+        nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, C, HW, src_stride,
+                                                                                    src_off);
+    return adc::check_cuda(cudaGetLastError(), "nhwc_to_nchw_f32_kernel launch");
+}
+
+size_t adc_conv3x3_weight_elems(int cout, int cin) {
+    const int npad = (cout + 15) / 16 * 16, cin_pad = (cin + 15) / 16 * 16;
+    return (size_t)9 * npad * cin_pad;
+}
+
+int adc_conv3x3_prep_weights(const float* w, void* out_bf16, int cout, int cin, int flip_transpose, adc_stream_t stream) {
+    if (!w || !out_bf16 || cout <= 0 || cin <= 0) {
+        adc::set_error("adc_conv3x3_prep_weights: bad argument");
+        return ADC_E_BADARG;
+    }
+    const int oc = flip_transpose ? cin : cout, ic = flip_transpose ? cout : cin;
+    const int npad = (oc + 15) / 16 * 16, cin_pad = (ic + 15) / 16 * 16;
+    prep_conv_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, cout, cin, npad, cin_pad, flip_transpose);
+    return adc::check_cuda(cudaGetLastError(), "prep_conv_weights_kernel launch");
+}
+
+// x: NHWC bf16 [N,H,W,x_stride] (channels [x_off, x_off+cin) are read, cin % 16 == 0); w: prepared bf16 [9][npad][cin];
+// out: NHWC, out_f32 ? fp32 : bf16, channel slice [out_off, out_off+cout) of a tensor with out_stride channels per pixel.
+int adc_conv3x3_fprop_tc(const void* x, int x_stride, int x_off, const void* w, const float* bias, void* out, int out_f32,
+                         int out_stride, int out_off, int N, int H, int W, int cin, int cout, int stride, int act,
+                         adc_stream_t stream) {
+    if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || (stride != 1 && stride != 2)) {
+        adc::set_error("adc_conv3x3_fprop_tc: bad argument");
+        return ADC_E_BADARG;
+    }
+    if (cin % 16 != 0 || x_stride % 8 != 0 || x_off % 8 != 0 || cout > 256) {
+        adc::set_error("adc_conv3x3_fprop_tc: needs cin %% 16 == 0, 16-byte aligned channel slices and cout <= 256 (cin=%d cout=%d)", cin, cout);
+        return ADC_E_UNSUPP;
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        adc::set_error("cuTensorMapEncodeTiled entry point not available");
+        return ADC_E_UNSUPP;
+    }
+    const int npad = (cout + 15) / 16 * 16;
+    const int kblk = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin >= 64 ? 64 : 16));
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.H = H; p.W = W;
+    p.Ho = (H + 2 - 3) / stride + 1; p.Wo = (W + 2 - 3) / stride + 1;
+    p.cin = cin; p.npad = npad; p.cout = cout; p.stride = stride;
+    p.BW = p.Wo >= 24 ? 32 : (p.Wo >= 12 ? 16 : 8);
+    p.BH = 128 / p.BW;
+    p.tiles_x = (p.Wo + p.BW - 1) / p.BW; p.tiles_y = (p.Ho + p.BH - 1) / p.BH;
+    p.act = act; p.out_f32 = out_f32; p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.bias = bias;
+
+    CUtensorMap mx, mw;
+    {
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x) + x_off;
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)x_stride * 2, (cuuint64_t)x_stride * 2 * W, (cuuint64_t)x_stride * 2 * W * H};
+        cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(xb), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            adc::set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r);
+            return ADC_E_UNSUPP;
+        }
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)npad, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2 * npad};
+        cuuint32_t box[3] = {(cuuint32_t)kblk, (cuuint32_t)npad, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            adc::set_error("cuTensorMapEncodeTiled(w) failed: %d", (int)r);
+            return ADC_E_UNSUPP;
+        }
+    }
+    const int rowb = kblk * 2;
+    const int stage_bytes = (128 * rowb + npad * rowb + 1023) & ~1023;
+    const int smem = kStages * stage_bytes + 1024 + 256;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kblk == 64) return launch<64>(mx, mw, p, smem, st);
+    if (kblk == 32) return launch<32>(mx, mw, p, smem, st);
+    return launch<16>(mx, mw, p, smem, st);
+}
+
+}  // extern "C"
