@@ -134,21 +134,28 @@ struct ConvParams {
     long long out_pix_stride;   // elements between consecutive pixels in the output (>= cout: lets a layer write a channel slice)
     int out_ch_off;
     void* out;
+    void* out_lo;           // split mode, bf16 output: the low halves (out = hi)
     const float* bias;      // may be null
+    int split;              // 1: every operand is a (hi, lo) pair of bf16 tensors and hi*hi + lo*hi + hi*lo is accumulated
 };
 
 constexpr int kStages = 4;
 
 template <int KBLK>   // channels per K step: 64 / 32 / 16  (row bytes 128 / 64 / 32)
 __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x,
-                                                               const __grid_constant__ CUtensorMap map_w, ConvParams p) {
+                                                               const __grid_constant__ CUtensorMap map_w,
+                                                               const __grid_constant__ CUtensorMap map_xl,
+                                                               const __grid_constant__ CUtensorMap map_wl, ConvParams p) {
     constexpr int ROWB = KBLK * 2;
     constexpr int A_BYTES = 128 * ROWB;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     const int b_bytes = p.npad * ROWB;
-    const int stage_bytes = (A_BYTES + b_bytes + 1023) & ~1023;
+    const int b_off = A_BYTES;                                     // B_hi
+    const int al_off = (A_BYTES + b_bytes + 1023) & ~1023;         // A_lo (split mode)
+    const int bl_off = al_off + A_BYTES;                           // B_lo
+    const int stage_bytes = p.split ? 2 * al_off : al_off;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);   // full[kStages], empty[kStages], tmem_full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
 
@@ -183,9 +190,13 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                 mbar_wait(&bars[kStages + s], (use & 1) ^ 1);
                 const int kb = ks / 9, tap = ks % 9, u = tap / 3, v = tap % 3;
                 uint8_t* sa = smem + s * stage_bytes;
-                mbar_expect_tx(&bars[s], (uint32_t)(A_BYTES + b_bytes));
+                mbar_expect_tx(&bars[s], (uint32_t)((A_BYTES + b_bytes) * (p.split ? 2 : 1)));
                 tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ow0 * p.stride + v - 1, oh0 * p.stride + u - 1, n);
-                tma_load_3d(sa + A_BYTES, &map_w, &bars[s], kb * KBLK, 0, tap);
+                tma_load_3d(sa + b_off, &map_w, &bars[s], kb * KBLK, 0, tap);
+                if (p.split) {
+                    tma_load_4d(sa + al_off, &map_xl, &bars[s], kb * KBLK, ow0 * p.stride + v - 1, oh0 * p.stride + u - 1, n);
+                    tma_load_3d(sa + bl_off, &map_wl, &bars[s], kb * KBLK, 0, tap);
+                }
             }
         }
     } else if (warp == 1) {
@@ -197,10 +208,17 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                 mbar_wait(&bars[s], use & 1);
                 tc_fence_after();
                 const uint32_t sa = base + s * stage_bytes;
-                const uint64_t da = make_desc<ROWB>(sa), db = make_desc<ROWB>(sa + A_BYTES);
+                const uint64_t da = make_desc<ROWB>(sa), db = make_desc<ROWB>(sa + b_off);
 #pragma unroll
                 for (int k = 0; k < KBLK / 16; ++k)    // advance 16 bf16 = 32 bytes inside the swizzled row: +2 in the >>4 address field
                     umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+                if (p.split) {                         // + a_lo*b_hi + a_hi*b_lo  (a_lo*b_lo ~ 2^-18 is dropped)
+                    const uint64_t dal = make_desc<ROWB>(sa + al_off), dbl = make_desc<ROWB>(sa + bl_off);
+#pragma unroll
+                    for (int k = 0; k < KBLK / 16; ++k) umma_bf16(tmem_base, dal + 2 * k, db + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < KBLK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, dbl + 2 * k, idesc, 1);
+                }
                 umma_commit(&bars[kStages + s]);       // slot free once these MMAs have read it
             }
             umma_commit(&bars[2 * kStages]);           // accumulator complete
@@ -234,7 +252,16 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                     if (c0 + j < p.cout) o[j] = v[j];
             } else {
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
-                if (c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                if (p.out_lo) {
+                    __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * p.out_pix_stride + p.out_ch_off + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.cout) {
+                            const __nv_bfloat16 hi = __float2bfloat16(v[j]);
+                            o[j] = hi;
+                            ol[j] = __float2bfloat16(v[j] - __bfloat162float(hi));
+                        }
+                } else if (c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
                     __nv_bfloat162 h[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
@@ -257,8 +284,9 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
 // NCHW fp32 (channel slice [c_off, c_off+C) of a tensor with Ctot channels) -> NHWC bf16 with Cpad channels (zero padded),
 // written into channels [dst_off, dst_off+Cpad) of an NHWC tensor with dst_stride channels per pixel.
 __global__ void __launch_bounds__(256) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                                     int C, int Cpad, long long HW, long long src_batch_stride,
-                                                                     int dst_stride, int dst_off) {
+                                                                     __nv_bfloat16* __restrict__ dst_lo, int C, int Cpad,
+                                                                     long long HW, long long src_batch_stride, int dst_stride,
+                                                                     int dst_off) {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 32;
@@ -273,7 +301,12 @@ __global__ void __launch_bounds__(256) nchw_f32_to_nhwc_bf16_kernel(const float*
     for (int j = ty; j < 32; j += 8) {
         const long long pp = p0 + j;
         const int c = c0 + tx;
-        if (pp < HW && c < Cpad) dst[((long long)n * HW + pp) * dst_stride + dst_off + c] = __float2bfloat16(tile[tx][j]);
+        if (pp < HW && c < Cpad) {
+            const long long o = ((long long)n * HW + pp) * dst_stride + dst_off + c;
+            const __nv_bfloat16 hi = __float2bfloat16(tile[tx][j]);
+            dst[o] = hi;
+            if (dst_lo) dst_lo[o] = __float2bfloat16(tile[tx][j] - __bfloat162float(hi));
+        }
     }
 }
 
@@ -300,8 +333,9 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const T* __restri
 }
 
 // fp32 [Cout, Cin, 3, 3] -> bf16 [9][npad][cin_pad]  (zero padded)
-__global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int npad,
-                                         int cin_pad, int flip_transpose) {
+__global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                         __nv_bfloat16* __restrict__ out_lo, int cout, int cin, int npad, int cin_pad,
+                                         int flip_transpose) {
     const long long total = 9LL * npad * cin_pad;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ci = (int)(i % cin_pad), co = (int)((i / cin_pad) % npad), tap = (int)(i / ((long long)cin_pad * npad));
@@ -311,7 +345,9 @@ __global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
         } else {   // data-gradient weights: out "channel" = original ci, in "channel" = original co, taps flipped
             if (co < cin && ci < cout) v = w[((long long)ci * cin + co) * 9 + (8 - tap)];
         }
-        out[i] = __float2bfloat16(v);
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        out[i] = hi;
+        if (out_lo) out_lo[i] = __float2bfloat16(v - __bfloat162float(hi));
     }
 }
 
@@ -334,16 +370,22 @@ static CUtensorMapSwizzle swz(int kblk) {
 }
 
 template <int KBLK>
-static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const ConvParams& p, int smem, cudaStream_t st) {
+static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mxl, const CUtensorMap& mwl, const ConvParams& p,
+                  int smem, cudaStream_t st) {
     static bool done = false;
     if (!done) {   // opt in once to the largest configuration of this instantiation (npad = 256)
-        const int max_smem = kStages * ((128 * KBLK * 2 + 256 * KBLK * 2 + 1023) & ~1023) + 1024 + 256;
+        int max_smem = 2 * kStages * ((128 * KBLK * 2 + 256 * KBLK * 2 + 1023) & ~1023) + 1024 + 256;
+        if (max_smem > 227 * 1024) max_smem = 227 * 1024;
         int rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_fprop_tc_kernel<KBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
                                  "cudaFuncSetAttribute(conv3x3_fprop_tc_kernel)");
         if (rc) return rc;
         done = true;
     }
-    conv3x3_fprop_tc_kernel<KBLK><<<p.tiles_x * p.tiles_y * p.N, 192, smem, st>>>(mx, mw, p);
+    if (smem > 227 * 1024) {
+        adc::set_error("conv3x3_fprop_tc: %d bytes of shared memory needed (Cout too large for the split mode)", smem);
+        return ADC_E_UNSUPP;
+    }
+    conv3x3_fprop_tc_kernel<KBLK><<<p.tiles_x * p.tiles_y * p.N, 192, smem, st>>>(mx, mw, mxl, mwl, p);
     return adc::check_cuda(cudaGetLastError(), "conv3x3_fprop_tc_kernel launch");
 }
 
@@ -353,16 +395,16 @@ using namespace tc;
 
 extern "C" {
 
-int adc_nchw_to_nhwc_bf16(const float* src, void* dst, int N, int C, int Cpad, int H, int W, long long src_batch_stride,
-                          int dst_stride, int dst_off, adc_stream_t stream) {
+int adc_nchw_to_nhwc_bf16(const float* src, void* dst, void* dst_lo, int N, int C, int Cpad, int H, int W,
+                          long long src_batch_stride, int dst_stride, int dst_off, adc_stream_t stream) {
     if (!src || !dst || N <= 0 || C <= 0 || Cpad < C || H <= 0 || W <= 0 || dst_stride < dst_off + Cpad) {
         adc::set_error("adc_nchw_to_nhwc_bf16: bad argument");
         return ADC_E_BADARG;
     }
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 31) / 32), (Cpad + 31) / 32, N);
-    nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, C, Cpad, HW, src_batch_stride,
-                                                                         dst_stride, dst_off);
+    nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo, C, Cpad, HW,
+                                                                         src_batch_stride, dst_stride, dst_off);
     return adc::check_cuda(cudaGetLastError(), "nchw_f32_to_nhwc_bf16_kernel launch");
 }
 
@@ -387,24 +429,33 @@ size_t adc_conv3x3_weight_elems(int cout, int cin) {
     return (size_t)9 * npad * cin_pad;
 }
 
-int adc_conv3x3_prep_weights(const float* w, void* out_bf16, int cout, int cin, int flip_transpose, adc_stream_t stream) {
+int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int cout, int cin, int flip_transpose,
+                             adc_stream_t stream) {
     if (!w || !out_bf16 || cout <= 0 || cin <= 0) {
         adc::set_error("adc_conv3x3_prep_weights: bad argument");
         return ADC_E_BADARG;
     }
     const int oc = flip_transpose ? cin : cout, ic = flip_transpose ? cout : cin;
     const int npad = (oc + 15) / 16 * 16, cin_pad = (ic + 15) / 16 * 16;
-    prep_conv_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, cout, cin, npad, cin_pad, flip_transpose);
+    prep_conv_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out_lo, cout, cin, npad,
+                                                                   cin_pad, flip_transpose);
     return adc::check_cuda(cudaGetLastError(), "prep_conv_weights_kernel launch");
 }
 
 // x: NHWC bf16 [N,H,W,x_stride] (channels [x_off, x_off+cin) are read, cin % 16 == 0); w: prepared bf16 [9][npad][cin];
 // out: NHWC, out_f32 ? fp32 : bf16, channel slice [out_off, out_off+cout) of a tensor with out_stride channels per pixel.
-int adc_conv3x3_fprop_tc(const void* x, int x_stride, int x_off, const void* w, const float* bias, void* out, int out_f32,
-                         int out_stride, int out_off, int N, int H, int W, int cin, int cout, int stride, int act,
-                         adc_stream_t stream) {
+// Split (bf16x3) mode when x_lo and w_lo are given: every operand is hi + lo with hi = bf16(v), lo = bf16(v - hi) and the
+// kernel accumulates hi*hi + lo*hi + hi*lo in fp32 (relative error ~1e-5: fp32-grade parity on the tensor cores); a bf16
+// output is then written as the pair (out, out_lo).
+int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
+                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
+                         int W, int cin, int cout, int stride, int act, adc_stream_t stream) {
     if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || (stride != 1 && stride != 2)) {
         adc::set_error("adc_conv3x3_fprop_tc: bad argument");
+        return ADC_E_BADARG;
+    }
+    if ((x_lo == nullptr) != (w_lo == nullptr)) {
+        adc::set_error("adc_conv3x3_fprop_tc: x_lo and w_lo must be given together (split mode)");
         return ADC_E_BADARG;
     }
     if (cin % 16 != 0 || x_stride % 8 != 0 || x_off % 8 != 0 || cout > 256) {
@@ -416,6 +467,7 @@ int adc_conv3x3_fprop_tc(const void* x, int x_stride, int x_off, const void* w, 
         adc::set_error("cuTensorMapEncodeTiled entry point not available");
         return ADC_E_UNSUPP;
     }
+    const int split = x_lo != nullptr;
     const int npad = (cout + 15) / 16 * 16;
     const int kblk = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin >= 64 ? 64 : 16));
     ConvParams p;
@@ -427,40 +479,50 @@ int adc_conv3x3_fprop_tc(const void* x, int x_stride, int x_off, const void* w, 
     p.BH = 128 / p.BW;
     p.tiles_x = (p.Wo + p.BW - 1) / p.BW; p.tiles_y = (p.Ho + p.BH - 1) / p.BH;
     p.act = act; p.out_f32 = out_f32; p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.bias = bias;
+    p.out_lo = out_f32 ? nullptr : out_lo;
+    p.split = split;
 
-    CUtensorMap mx, mw;
-    {
-        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x) + x_off;
+    CUtensorMap mx, mw, mxl, mwl;
+    memset(&mxl, 0, sizeof(mxl));
+    memset(&mwl, 0, sizeof(mwl));
+    auto make_x = [&](CUtensorMap* m, const void* base) -> int {
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(base) + x_off;
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)x_stride * 2, (cuuint64_t)x_stride * 2 * W, (cuuint64_t)x_stride * 2 * W * H};
         cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(xb), dims, strides, box, estr,
+        CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(xb), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             adc::set_error("cuTensorMapEncodeTiled(x) failed: %d", (int)r);
             return ADC_E_UNSUPP;
         }
-    }
-    {
+        return 0;
+    };
+    auto make_w = [&](CUtensorMap* m, const void* base) -> int {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)npad, 9};
         cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2 * npad};
         cuuint32_t box[3] = {(cuuint32_t)kblk, (cuuint32_t)npad, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+        CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             adc::set_error("cuTensorMapEncodeTiled(w) failed: %d", (int)r);
             return ADC_E_UNSUPP;
         }
-    }
+        return 0;
+    };
+    int rc;
+    if ((rc = make_x(&mx, x)) || (rc = make_w(&mw, w))) return rc;
+    if (split && ((rc = make_x(&mxl, x_lo)) || (rc = make_w(&mwl, w_lo)))) return rc;
     const int rowb = kblk * 2;
-    const int stage_bytes = (128 * rowb + npad * rowb + 1023) & ~1023;
+    const int al_off = (128 * rowb + npad * rowb + 1023) & ~1023;
+    const int stage_bytes = split ? 2 * al_off : al_off;
     const int smem = kStages * stage_bytes + 1024 + 256;
     cudaStream_t st = (cudaStream_t)stream;
-    if (kblk == 64) return launch<64>(mx, mw, p, smem, st);
-    if (kblk == 32) return launch<32>(mx, mw, p, smem, st);
-    return launch<16>(mx, mw, p, smem, st);
+    if (kblk == 64) return launch<64>(mx, mw, mxl, mwl, p, smem, st);
+    if (kblk == 32) return launch<32>(mx, mw, mxl, mwl, p, smem, st);
+    return launch<16>(mx, mw, mxl, mwl, p, smem, st);
 }
 
 }  // extern "C"

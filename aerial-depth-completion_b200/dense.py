@@ -12,10 +12,12 @@ PRECISION = "fp32"
 
 
 def set_precision(mode):
-    """'fp32' (strict: parity 1e-4 with the reference, TF32 off in library calls) or 'tf32' (parity 1e-2)."""
+    """'fp32' (strict: parity 1e-4 with the reference, TF32 off in library calls), 'tf32' (library TF32, parity 1e-2) or
+    'bf16' / 'bf16x3' (inference forward of the wide layers on the hand-written tcgen05 kernels, NHWC activations, fp32
+    accumulation in TMEM: plain bf16 operands, or hi+lo bf16 pairs with three MMAs per product for fp32-grade parity)."""
     global PRECISION
-    if mode not in ("fp32", "tf32"):
-        raise ValueError("precision must be 'fp32' or 'tf32'")
+    if mode not in ("fp32", "tf32", "bf16", "bf16x3"):
+        raise ValueError("precision must be 'fp32', 'tf32', 'bf16' or 'bf16x3'")
     PRECISION = mode
     torch.backends.cudnn.allow_tf32 = mode == "tf32"
     torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
@@ -57,6 +59,9 @@ class ConvTranspose2d(torch.nn.ConvTranspose2d):
 
 
 # ---- tensor-core path (tcgen05 implicit GEMM, NHWC bf16) ---------------------------------------------------------------
+# An activation is a pair (hi, lo) of NHWC bf16 tensors; lo is None in the plain 'bf16' mode.  In the 'bf16x3' mode every
+# value is hi + lo (hi = bf16(v), lo = bf16(v - hi), 16 mantissa bits together) and the kernel accumulates
+# hi*hi + lo*hi + hi*lo in fp32: fp32-grade results from the bf16 tensor cores at three MMAs per product.
 def _r16(c):
     return (c + 15) // 16 * 16
 
@@ -66,9 +71,23 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _split():
+    return PRECISION == "bf16x3"
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def new_act(n, h, w, c, device, zero=False):
+    mk = torch.zeros if zero else torch.empty
+    hi = mk((n, h, w, c), device=device, dtype=torch.bfloat16)
+    return (hi, mk((n, h, w, c), device=device, dtype=torch.bfloat16) if _split() else None)
+
+
 def to_nhwc_bf16(x, cpad=None, dst=None, dst_off=0):
-    """NCHW fp32 (any batch stride, contiguous planes) -> NHWC bf16 with the channel count padded to a multiple of 16;
-    optionally into channels [dst_off, dst_off+cpad) of an existing NHWC tensor (folds torch.cat)."""
+    """NCHW fp32 (any batch stride, contiguous planes) -> NHWC bf16 activation with the channel count padded to a multiple
+    of 16; optionally into channels [dst_off, dst_off+cpad) of an existing activation (folds torch.cat)."""
     from ._lib import lib, check
     _need_cuda(x)
     n, c, h, w = x.shape
@@ -76,43 +95,82 @@ def to_nhwc_bf16(x, cpad=None, dst=None, dst_off=0):
         x = x.contiguous()
     cpad = _r16(c) if cpad is None else cpad
     if dst is None:
-        dst = torch.empty((n, h, w, cpad), device=x.device, dtype=torch.bfloat16)
-    check(lib.adc_nchw_to_nhwc_bf16(x.data_ptr(), dst.data_ptr(), n, c, cpad, h, w, x.stride(0) if n > 1 else c * h * w,
-                                    dst.shape[3], dst_off, _stream()), "adc_nchw_to_nhwc_bf16")
+        dst = new_act(n, h, w, cpad, x.device)
+    check(lib.adc_nchw_to_nhwc_bf16(x.data_ptr(), dst[0].data_ptr(), _ptr(dst[1]), n, c, cpad, h, w,
+                                    x.stride(0) if n > 1 else c * h * w, dst[0].shape[3], dst_off, _stream()), "adc_nchw_to_nhwc_bf16")
     return dst
 
 
-def to_nchw_f32(x_nhwc, c, off=0):
+def to_nchw_f32(act, c, off=0):
+    """NHWC activation (bf16 pair, or a single fp32 NHWC tensor) channel slice -> NCHW fp32."""
     from ._lib import lib, check
-    n, h, w, cs = x_nhwc.shape
-    out = torch.empty((n, c, h, w), device=x_nhwc.device, dtype=torch.float32)
-    check(lib.adc_nhwc_to_nchw_f32(x_nhwc.data_ptr(), int(x_nhwc.dtype == torch.float32), out.data_ptr(), n, c, h, w, cs, off,
-                                   _stream()), "adc_nhwc_to_nchw_f32")
+    if torch.is_tensor(act):
+        act = (act, None)
+    hi, lo = act
+    n, h, w, cs = hi.shape
+    out = torch.empty((n, c, h, w), device=hi.device, dtype=torch.float32)
+    check(lib.adc_nhwc_to_nchw_f32(hi.data_ptr(), int(hi.dtype == torch.float32), out.data_ptr(), n, c, h, w, cs, off, _stream()),
+          "adc_nhwc_to_nchw_f32")
+    if lo is not None:
+        low = torch.empty_like(out)
+        check(lib.adc_nhwc_to_nchw_f32(lo.data_ptr(), 0, low.data_ptr(), n, c, h, w, cs, off, _stream()), "adc_nhwc_to_nchw_f32")
+        out += low
     return out
 
 
 def prep_conv3x3_weights(weight, flip_transpose=False):
-    """fp32 [Cout,Cin,3,3] -> bf16 [9][round16(Cout)][round16(Cin)] as the tensor-core kernel reads it."""
+    """fp32 [Cout,Cin,3,3] -> (hi, lo) bf16 [9][round16(Cout)][round16(Cin)] as the tensor-core kernel reads them."""
     from ._lib import lib, check
     co, ci = weight.shape[:2]
     oc, ic = (ci, co) if flip_transpose else (co, ci)
-    out = torch.empty((9, _r16(oc), _r16(ic)), device=weight.device, dtype=torch.bfloat16)
-    check(lib.adc_conv3x3_prep_weights(weight.detach().contiguous().data_ptr(), out.data_ptr(), co, ci, int(flip_transpose),
+    hi = torch.empty((9, _r16(oc), _r16(ic)), device=weight.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if _split() else None
+    check(lib.adc_conv3x3_prep_weights(weight.detach().contiguous().data_ptr(), hi.data_ptr(), _ptr(lo), co, ci, int(flip_transpose),
                                        _stream()), "adc_conv3x3_prep_weights")
-    return out
+    return (hi, lo)
 
 
-def conv3x3_tc(x_nhwc, cin, w_prep, bias, cout, stride=1, act=0, x_off=0, out=None, out_off=0, out_f32=False):
-    """3x3 / pad 1 convolution on the tensor cores.  x_nhwc: [N,H,W,Cs] bf16, channels [x_off, x_off+cin) are read
-    (cin a multiple of 16, zero padded); result written to channels [out_off, out_off+cout) of ``out`` (NHWC)."""
+def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=None, out_off=0, out_f32=False):
+    """3x3 / pad 1 convolution on the tensor cores.  act: NHWC activation, channels [x_off, x_off+cin) are read (cin a
+    multiple of 16, zero padded); result written to channels [out_off, out_off+cout) of ``out`` (an activation, or a single
+    fp32 NHWC tensor when out_f32)."""
     from ._lib import lib, check
-    n, h, w, cs = x_nhwc.shape
+    hi, lo = act
+    n, h, w, cs = hi.shape
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     if out is None:
-        out = torch.empty((n, ho, wo, _r16(cout)), device=x_nhwc.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-        if _r16(cout) != cout:
-            out.zero_()
+        if out_f32:
+            out = torch.zeros((n, ho, wo, _r16(cout)), device=hi.device, dtype=torch.float32)
+        else:
+            out = new_act(n, ho, wo, _r16(cout), hi.device, zero=_r16(cout) != cout)
+    o_hi, o_lo = (out, None) if torch.is_tensor(out) else out
     b = bias.detach().contiguous().data_ptr() if bias is not None else None
-    check(lib.adc_conv3x3_fprop_tc(x_nhwc.data_ptr(), cs, x_off, w_prep.data_ptr(), b, out.data_ptr(), int(out.dtype == torch.float32),
-                                   out.shape[3], out_off, n, h, w, cin, cout, stride, act, _stream()), "adc_conv3x3_fprop_tc")
+    check(lib.adc_conv3x3_fprop_tc(hi.data_ptr(), _ptr(lo), cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b, o_hi.data_ptr(),
+                                   _ptr(o_lo), int(o_hi.dtype == torch.float32), o_hi.shape[3], out_off, n, h, w, cin, cout, stride,
+                                   act_fn, _stream()), "adc_conv3x3_fprop_tc")
     return out
+
+
+_wcache = {}
+
+
+def cached_weights(conv, embed_1x1=False):
+    """Prepared bf16 weights of a Conv2d, re-prepared only when the Parameter changes (version counter / storage / mode)."""
+    w = conv.weight
+    key = id(conv)
+    tag = (w.data_ptr(), w._version, PRECISION)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    wt = w.detach()
+    if embed_1x1:      # a 1x1 convolution = a 3x3 one whose only non-zero tap is the centre
+        full = torch.zeros(wt.shape[0], wt.shape[1], 3, 3, device=wt.device, dtype=wt.dtype)
+        full[:, :, 1, 1] = wt[:, :, 0, 0]
+        wt = full
+    prep = prep_conv3x3_weights(wt)
+    _wcache[key] = (tag, prep)
+    return prep
+
+
+def tc_inference_enabled():
+    return PRECISION in ("bf16", "bf16x3") and not torch.is_grad_enabled()
