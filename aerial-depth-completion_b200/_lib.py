@@ -73,12 +73,14 @@ SIGNATURES = {
     "adc_pyramid_fwd": (c_int, [ctypes.POINTER(PyramidFwd), _vp]),
     "adc_pyramid_bwd_scratch_floats": (ctypes.c_size_t, [c_int] * 3),
     "adc_pyramid_bwd": (c_int, [ctypes.POINTER(PyramidBwd), _vp]),
-    "adc_nchw_to_nhwc_bf16": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_int, c_int, _vp]),
-    "adc_nhwc_to_nchw_f32": (c_int, [_vp, c_int, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_nchw_to_nhwc_bf16": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_int, c_int, c_int, _vp]),
+    "adc_nhwc_to_nchw_f32": (c_int, [_vp, c_int, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_weight_elems": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_prep_weights": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_fprop_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     c_int, c_int, c_int, c_int, _vp]),
+                                     c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_conv3x3_s1_tc_v2": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_int, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/adc_b200.h"
 
@@ -58,6 +59,16 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
             smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
@@ -137,6 +148,7 @@ struct ConvParams {
     void* out_lo;           // split mode, bf16 output: the low halves (out = hi)
     const float* bias;      // may be null
     int split;              // 1: every operand is a (hi, lo) pair of bf16 tensors and hi*hi + lo*hi + hi*lo is accumulated
+    int x_pad, out_pad;     // 1: the tensor is stored with a one-pixel zero border ([H+2][W+2] per image)
 };
 
 constexpr int kStages = 4;
@@ -191,10 +203,11 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                 const int kb = ks / 9, tap = ks % 9, u = tap / 3, v = tap % 3;
                 uint8_t* sa = smem + s * stage_bytes;
                 mbar_expect_tx(&bars[s], (uint32_t)((A_BYTES + b_bytes) * (p.split ? 2 : 1)));
-                tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ow0 * p.stride + v - 1, oh0 * p.stride + u - 1, n);
+                tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ow0 * p.stride + v - 1 + p.x_pad, oh0 * p.stride + u - 1 + p.x_pad, n);
                 tma_load_3d(sa + b_off, &map_w, &bars[s], kb * KBLK, 0, tap);
                 if (p.split) {
-                    tma_load_4d(sa + al_off, &map_xl, &bars[s], kb * KBLK, ow0 * p.stride + v - 1, oh0 * p.stride + u - 1, n);
+                    tma_load_4d(sa + al_off, &map_xl, &bars[s], kb * KBLK, ow0 * p.stride + v - 1 + p.x_pad,
+                                oh0 * p.stride + u - 1 + p.x_pad, n);
                     tma_load_3d(sa + bl_off, &map_wl, &bars[s], kb * KBLK, 0, tap);
                 }
             }
@@ -231,7 +244,8 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
         const bool valid = oh < p.Ho && ow < p.Wo;
         mbar_wait(&bars[2 * kStages], 0);
         tc_fence_after();
-        const long long pix = ((long long)n * p.Ho + oh) * p.Wo + ow;
+        const long long pix = p.out_pad ? ((long long)n * (p.Ho + 2) + oh + 1) * (p.Wo + 2) + ow + 1
+                                        : ((long long)n * p.Ho + oh) * p.Wo + ow;
         for (int c0 = 0; c0 < p.npad; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
@@ -280,13 +294,213 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
+// ---- v2: stride-1 kernel with tap reuse in shared memory, persistent CTAs and double-buffered TMEM accumulators ------
+// The 9-tap implicit GEMM above re-reads every input pixel 9 times from L2 (measured: L2-bandwidth bound, 188 TFLOP/s).
+// Here activations live in a ZERO-BORDERED NHWC layout [N][H+2][W+2][C]: with the border in memory a tap (u,v) is a pure
+// shift of (u-1)*(W+2)+(v-1) in the flat pixel index, so an M tile is ANY 128 consecutive flat pixels (no tile
+// quantisation) and one TMA row segment of 130 pixels per vertical tap u serves the three horizontal taps: the MMA
+// descriptors of v = 0,1,2 simply start 0,1,2 rows into the segment (descriptor base_offset carries the swizzle phase).
+// Pipeline step = (64-channel block, u): A segment (+ low half) and the three weight tiles of taps (u,0..2) (+ low halves);
+// 12 (36 in split mode) UMMAs per step.  CTAs are persistent over M tiles; the accumulator alternates between two TMEM
+// buffers so the epilogue of tile i overlaps the MMAs of tile i+1.  Border pixels of the output are written as zeros.
+struct ConvParamsV2 {
+    long long F;             // total flat pixels N*(H+2)*(W+2)
+    int Hp, Wp;              // H+2, W+2
+    int cin, npad, cout;
+    int act, out_f32, split;
+    long long out_pix_stride;
+    int out_ch_off;
+    void* out;
+    void* out_lo;
+    const float* bias;
+    int ntiles;
+    int boff_mode;
+};
+
+constexpr int kSegRows = 130;
+constexpr int kSegBytes = ((kSegRows * 128 + 1023) / 1024) * 1024;   // 17408
+constexpr int kStagesV2 = 2;
+
+__device__ __forceinline__ uint64_t make_desc_sw128_off(uint32_t smem_addr, int boff_mode) {
+    // Start address that is NOT aligned to the 1024-byte swizzle repeat (a row shift of v*128 bytes).  Measured on B200: the
+    // UMMA applies the 128-byte swizzle to ABSOLUTE shared-memory address bits, so the descriptor's base_offset field must
+    // stay 0 (mode 0: exact results for all nine taps; mode 1 = address bits [7,10) in base_offset: taps with v != 0 wrong).
+    const uint64_t base_off = boff_mode ? ((smem_addr >> 7) & 7) : 0;
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (base_off << 49) |
+           (2ull << 61);
+}
+
+__global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                               const __grid_constant__ CUtensorMap map_w,
+                                                               const __grid_constant__ CUtensorMap map_xl,
+                                                               const __grid_constant__ CUtensorMap map_wl, ConvParamsV2 p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int b_tile = p.npad * 128;                  // one tap's weight tile (multiple of 1024: npad % 8 == 0)
+    const int b_bytes = 3 * b_tile;
+    const int half = kSegBytes + b_bytes;             // [A seg][B 3 taps]
+    const int stage_bytes = p.split ? 2 * half : half;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesV2 * stage_bytes);
+    // bars: full[2], empty[2], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = (p.cin + 63) / 64;
+    const int steps = kblocks * 3;
+    uint32_t ncols = 32;
+    while ((int)ncols < 2 * p.npad) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStagesV2; ++s) {
+            mbar_init(&bars[s], 1);
+            mbar_init(&bars[2 + s], 1);
+            mbar_init(&bars[4 + s], 1);
+            mbar_init(&bars[6 + s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, ncols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int q = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const long long m0 = (long long)tile * 128;
+                for (int st = 0; st < steps; ++st, ++q) {
+                    const int s = q % kStagesV2, use = q / kStagesV2;
+                    const int kb = st / 3, u = st % 3;
+                    mbar_wait(&bars[2 + s], (use & 1) ^ 1);
+                    uint8_t* sa = smem + s * stage_bytes;
+                    mbar_expect_tx(&bars[s], (uint32_t)((kSegRows * 128 + b_bytes) * (p.split ? 2 : 1)));
+                    const long long f0 = m0 + (long long)(u - 1) * p.Wp - 1;
+                    tma_load_2d(sa, &map_x, &bars[s], kb * 64, (int)f0);
+                    tma_load_3d(sa + kSegBytes, &map_w, &bars[s], kb * 64, 0, 3 * u);
+                    if (p.split) {
+                        tma_load_2d(sa + half, &map_xl, &bars[s], kb * 64, (int)f0);
+                        tma_load_3d(sa + half + kSegBytes, &map_wl, &bars[s], kb * 64, 0, 3 * u);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = make_idesc(128, p.npad);
+            int q = 0, it = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+                const int a = it & 1;
+                mbar_wait(&bars[6 + a], ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(a * p.npad);
+                for (int st = 0; st < steps; ++st, ++q) {
+                    const int s = q % kStagesV2, use = q / kStagesV2;
+                    mbar_wait(&bars[s], use & 1);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * stage_bytes;
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) {
+                        const uint32_t a_hi = sa + v * 128, b_hi = sa + kSegBytes + v * b_tile;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tacc, make_desc_sw128_off(a_hi, p.boff_mode) + 2 * k, make_desc<128>(b_hi) + 2 * k, idesc, (st | v | k) != 0);
+                        if (p.split) {
+                            const uint32_t a_lo = a_hi + half, b_lo = b_hi + half;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tacc, make_desc_sw128_off(a_lo, p.boff_mode) + 2 * k, make_desc<128>(b_hi) + 2 * k, idesc, 1);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tacc, make_desc_sw128_off(a_hi, p.boff_mode) + 2 * k, make_desc<128>(b_lo) + 2 * k, idesc, 1);
+                        }
+                    }
+                    umma_commit(&bars[2 + s]);
+                }
+                umma_commit(&bars[4 + a]);
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 =====
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const int a = it & 1;
+            const long long m = (long long)tile * 128 + quarter * 32 + lane;
+            const bool inrange = m < p.F;
+            const int wp = (int)(m % p.Wp), hp = (int)((m / p.Wp) % p.Hp);
+            const bool border = wp == 0 || wp == p.Wp - 1 || hp == 0 || hp == p.Hp - 1;
+            mbar_wait(&bars[4 + a], (it >> 1) & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < p.npad; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.npad + c0), v);
+                if (!inrange) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int co = c0 + j;
+                    float r = v[j] + ((p.bias && co < p.cout) ? p.bias[co] : 0.f);
+                    if (p.act == 1) r = fmaxf(r, 0.f);
+                    else if (p.act == 2) r = r > 0.f ? r : 0.2f * r;
+                    else if (p.act == 3) r = 1.f / (1.f + __expf(-r));
+                    v[j] = border ? 0.f : r;
+                }
+                if (p.out_f32) {
+                    float* o = reinterpret_cast<float*>(p.out) + m * p.out_pix_stride + p.out_ch_off + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.cout) o[j] = v[j];
+                } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.out_pix_stride + p.out_ch_off + c0;
+                    const bool full16 = c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+                    __nv_bfloat162 h[8], l[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        l[j] = __floats2bfloat162_rn(v[2 * j] - __low2float(h[j]), v[2 * j + 1] - __high2float(h[j]));
+                    }
+                    if (full16) {
+                        reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(h)[0];
+                        reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(h)[1];
+                        if (p.out_lo) {
+                            __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + m * p.out_pix_stride + p.out_ch_off + c0;
+                            reinterpret_cast<uint4*>(ol)[0] = reinterpret_cast<uint4*>(l)[0];
+                            reinterpret_cast<uint4*>(ol)[1] = reinterpret_cast<uint4*>(l)[1];
+                        }
+                    } else {
+                        const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(h);
+                        const __nv_bfloat16* ls = reinterpret_cast<const __nv_bfloat16*>(l);
+                        __nv_bfloat16* ol = p.out_lo ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) + m * p.out_pix_stride + p.out_ch_off + c0 : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.cout) {
+                                o[j] = hs[j];
+                                if (ol) ol[j] = ls[j];
+                            }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[6 + a]);      // this warp has drained accumulator a
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
 // ---- layout glue ---------------------------------------------------------------------------------------------------
 // NCHW fp32 (channel slice [c_off, c_off+C) of a tensor with Ctot channels) -> NHWC bf16 with Cpad channels (zero padded),
 // written into channels [dst_off, dst_off+Cpad) of an NHWC tensor with dst_stride channels per pixel.
 __global__ void __launch_bounds__(256) nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                      __nv_bfloat16* __restrict__ dst_lo, int C, int Cpad,
                                                                      long long HW, long long src_batch_stride, int dst_stride,
-                                                                     int dst_off) {
+                                                                     int dst_off, int W, int pad) {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 32;
@@ -302,7 +516,9 @@ __global__ void __launch_bounds__(256) nchw_f32_to_nhwc_bf16_kernel(const float*
         const long long pp = p0 + j;
         const int c = c0 + tx;
         if (pp < HW && c < Cpad) {
-            const long long o = ((long long)n * HW + pp) * dst_stride + dst_off + c;
+            const long long H_ = HW / W;
+            const long long dp = pad ? ((long long)n * (H_ + 2) + pp / W + 1) * (W + 2) + pp % W + 1 : (long long)n * HW + pp;
+            const long long o = dp * dst_stride + dst_off + c;
             const __nv_bfloat16 hi = __float2bfloat16(tile[tx][j]);
             dst[o] = hi;
             if (dst_lo) dst_lo[o] = __float2bfloat16(tile[tx][j] - __bfloat162float(hi));
@@ -313,7 +529,7 @@ __global__ void __launch_bounds__(256) nchw_f32_to_nhwc_bf16_kernel(const float*
 // NHWC (bf16 or fp32) channel slice -> NCHW fp32
 template <typename T>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int C,
-                                                                long long HW, int src_stride, int src_off) {
+                                                                long long HW, int src_stride, int src_off, int W, int pad) {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 32;
@@ -322,7 +538,9 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const T* __restri
     for (int j = ty; j < 32; j += 8) {
         const long long pp = p0 + j;
         const int c = c0 + tx;
-        tile[j][tx] = (pp < HW && c < C) ? (float)src[((long long)n * HW + pp) * src_stride + src_off + c] : 0.f;
+        const long long H_ = HW / W;
+        const long long sp = pad ? ((long long)n * (H_ + 2) + pp / W + 1) * (W + 2) + pp % W + 1 : (long long)n * HW + pp;
+        tile[j][tx] = (pp < HW && c < C) ? (float)src[sp * src_stride + src_off + c] : 0.f;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -396,7 +614,7 @@ using namespace tc;
 extern "C" {
 
 int adc_nchw_to_nhwc_bf16(const float* src, void* dst, void* dst_lo, int N, int C, int Cpad, int H, int W,
-                          long long src_batch_stride, int dst_stride, int dst_off, adc_stream_t stream) {
+                          long long src_batch_stride, int dst_stride, int dst_off, int pad, adc_stream_t stream) {
     if (!src || !dst || N <= 0 || C <= 0 || Cpad < C || H <= 0 || W <= 0 || dst_stride < dst_off + Cpad) {
         adc::set_error("adc_nchw_to_nhwc_bf16: bad argument");
         return ADC_E_BADARG;
@@ -404,12 +622,12 @@ int adc_nchw_to_nhwc_bf16(const float* src, void* dst, void* dst_lo, int N, int 
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 31) / 32), (Cpad + 31) / 32, N);
     nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo, C, Cpad, HW,
-                                                                         src_batch_stride, dst_stride, dst_off);
+                                                                         src_batch_stride, dst_stride, dst_off, W, pad);
     return adc::check_cuda(cudaGetLastError(), "nchw_f32_to_nhwc_bf16_kernel launch");
 }
 
 int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int C, int H, int W, int src_stride, int src_off,
-                         adc_stream_t stream) {
+                         int pad, adc_stream_t stream) {
     if (!src || !dst || N <= 0 || C <= 0 || H <= 0 || W <= 0 || src_stride < src_off + C) {
         adc::set_error("adc_nhwc_to_nchw_f32: bad argument");
         return ADC_E_BADARG;
@@ -417,10 +635,10 @@ int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
     if (src_is_f32)
-        nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, dst, C, HW, src_stride, src_off);
+        nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, dst, C, HW, src_stride, src_off, W, pad);
     else
         nhwc_to_nchw_f32_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, C, HW, src_stride,
-                                                                                    src_off);
+                                                                                    src_off, W, pad);
     return adc::check_cuda(cudaGetLastError(), "nhwc_to_nchw_f32_kernel launch");
 }
 
@@ -449,7 +667,7 @@ int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int c
 // output is then written as the pair (out, out_lo).
 int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
                          const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
-                         int W, int cin, int cout, int stride, int act, adc_stream_t stream) {
+                         int W, int cin, int cout, int stride, int act, int x_pad, int out_pad, adc_stream_t stream) {
     if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || (stride != 1 && stride != 2)) {
         adc::set_error("adc_conv3x3_fprop_tc: bad argument");
         return ADC_E_BADARG;
@@ -481,14 +699,17 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
     p.act = act; p.out_f32 = out_f32; p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.bias = bias;
     p.out_lo = out_f32 ? nullptr : out_lo;
     p.split = split;
+    p.x_pad = x_pad ? 1 : 0;
+    p.out_pad = out_pad ? 1 : 0;
+    const int Wt = W + 2 * p.x_pad, Ht = H + 2 * p.x_pad;    // stored extent of the input
 
     CUtensorMap mx, mw, mxl, mwl;
     memset(&mxl, 0, sizeof(mxl));
     memset(&mwl, 0, sizeof(mwl));
     auto make_x = [&](CUtensorMap* m, const void* base) -> int {
         const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(base) + x_off;
-        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)x_stride * 2, (cuuint64_t)x_stride * 2 * W, (cuuint64_t)x_stride * 2 * W * H};
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)x_stride * 2, (cuuint64_t)x_stride * 2 * Wt, (cuuint64_t)x_stride * 2 * Wt * Ht};
         cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(xb), dims, strides, box, estr,
@@ -523,6 +744,96 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
     if (kblk == 64) return launch<64>(mx, mw, mxl, mwl, p, smem, st);
     if (kblk == 32) return launch<32>(mx, mw, mxl, mwl, p, smem, st);
     return launch<16>(mx, mw, mxl, mwl, p, smem, st);
+}
+
+
+// Stride-1 3x3 convolution, v2 kernel (shared-memory tap reuse, persistent, double-buffered TMEM).  x and out are
+// zero-bordered NHWC tensors ([N][H+2][W+2][channels]); needs cin % 64 == 0.  Same split-mode convention as above.
+int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
+                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
+                         int W, int cin, int cout, int act, adc_stream_t stream) {
+    if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) {
+        adc::set_error("adc_conv3x3_s1_tc_v2: bad argument");
+        return ADC_E_BADARG;
+    }
+    if ((x_lo == nullptr) != (w_lo == nullptr)) {
+        adc::set_error("adc_conv3x3_s1_tc_v2: x_lo and w_lo must be given together (split mode)");
+        return ADC_E_BADARG;
+    }
+    if (cin % 64 != 0 || x_stride % 8 != 0 || x_off % 8 != 0 || cout > 128) {
+        adc::set_error("adc_conv3x3_s1_tc_v2: needs cin %% 64 == 0, 16-byte aligned channel slices and cout <= 128 (cin=%d cout=%d)", cin, cout);
+        return ADC_E_UNSUPP;
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        adc::set_error("cuTensorMapEncodeTiled entry point not available");
+        return ADC_E_UNSUPP;
+    }
+    const int split = x_lo != nullptr;
+    const int npad = (cout + 15) / 16 * 16;
+    ConvParamsV2 p;
+    memset(&p, 0, sizeof(p));
+    p.Hp = H + 2; p.Wp = W + 2;
+    p.F = (long long)N * p.Hp * p.Wp;
+    p.cin = cin; p.npad = npad; p.cout = cout; p.act = act; p.out_f32 = out_f32; p.split = split;
+    p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.out_lo = out_f32 ? nullptr : out_lo; p.bias = bias;
+    p.ntiles = (int)((p.F + 127) / 128);
+    { const char* e = getenv("ADC_V2_BOFF"); p.boff_mode = e ? atoi(e) : 0; }
+    CUtensorMap mx, mw, mxl, mwl;
+    memset(&mxl, 0, sizeof(mxl));
+    memset(&mwl, 0, sizeof(mwl));
+    auto make_x = [&](CUtensorMap* m, const void* base_) -> int {
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(base_) + x_off;
+        cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)p.F};
+        cuuint64_t strides[1] = {(cuuint64_t)x_stride * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)kSegRows};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(xb), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            adc::set_error("cuTensorMapEncodeTiled(x, v2) failed: %d", (int)r);
+            return ADC_E_UNSUPP;
+        }
+        return 0;
+    };
+    auto make_w = [&](CUtensorMap* m, const void* base_) -> int {
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)npad, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2 * npad};
+        cuuint32_t box[3] = {64, (cuuint32_t)npad, 3};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base_), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            adc::set_error("cuTensorMapEncodeTiled(w, v2) failed: %d", (int)r);
+            return ADC_E_UNSUPP;
+        }
+        return 0;
+    };
+    int rc;
+    if ((rc = make_x(&mx, x)) || (rc = make_w(&mw, w))) return rc;
+    if (split && ((rc = make_x(&mxl, x_lo)) || (rc = make_w(&mwl, w_lo)))) return rc;
+    const int half = kSegBytes + 3 * npad * 128;
+    const int smem = kStagesV2 * (split ? 2 * half : half) + 1024 + 256;
+    if (smem > 227 * 1024) {
+        adc::set_error("adc_conv3x3_s1_tc_v2: %d bytes of shared memory needed", smem);
+        return ADC_E_UNSUPP;
+    }
+    static bool done = false;
+    static int sms = 148;
+    if (!done) {
+        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                             "cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel)");
+        if (rc) return rc;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        done = true;
+    }
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    conv3x3_s1_tc_v2_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mx, mw, mxl, mwl, p);
+    return adc::check_cuda(cudaGetLastError(), "conv3x3_s1_tc_v2_kernel launch");
 }
 
 }  // extern "C"

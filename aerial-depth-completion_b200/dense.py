@@ -59,9 +59,13 @@ class ConvTranspose2d(torch.nn.ConvTranspose2d):
 
 
 # ---- tensor-core path (tcgen05 implicit GEMM, NHWC bf16) ---------------------------------------------------------------
-# An activation is a pair (hi, lo) of NHWC bf16 tensors; lo is None in the plain 'bf16' mode.  In the 'bf16x3' mode every
-# value is hi + lo (hi = bf16(v), lo = bf16(v - hi), 16 mantissa bits together) and the kernel accumulates
+# An activation (class Act) is a pair (hi, lo) of NHWC bf16 tensors; lo is None in the plain 'bf16' mode.  In the 'bf16x3'
+# mode every value is hi + lo (hi = bf16(v), lo = bf16(v - hi), 16 mantissa bits together) and the kernel accumulates
 # hi*hi + lo*hi + hi*lo in fp32: fp32-grade results from the bf16 tensor cores at three MMAs per product.
+# pad=True: the tensor carries a one-pixel zero border ([N][H+2][W+2][C]), the layout of the v2 (tap-reuse) kernel.
+USE_V2 = True
+
+
 def _r16(c):
     return (c + 15) // 16 * 16
 
@@ -79,13 +83,24 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
-def new_act(n, h, w, c, device, zero=False):
-    mk = torch.zeros if zero else torch.empty
-    hi = mk((n, h, w, c), device=device, dtype=torch.bfloat16)
-    return (hi, mk((n, h, w, c), device=device, dtype=torch.bfloat16) if _split() else None)
+class Act:
+    """NHWC activation: hi (+ lo) tensors of logical size [n, h, w, cs]; stored [n, h+2, w+2, cs] when pad."""
+    __slots__ = ("hi", "lo", "n", "h", "w", "cs", "pad")
+
+    def __init__(self, hi, lo, n, h, w, cs, pad):
+        self.hi, self.lo, self.n, self.h, self.w, self.cs, self.pad = hi, lo, n, h, w, cs, pad
 
 
-def to_nhwc_bf16(x, cpad=None, dst=None, dst_off=0):
+def new_act(n, h, w, c, device, pad=False, zero=False, dtype=torch.bfloat16, split=None):
+    split = _split() if split is None else split
+    mk = torch.zeros if (zero or pad) else torch.empty       # a padded tensor's border must be zero
+    shape = (n, h + 2, w + 2, c) if pad else (n, h, w, c)
+    hi = mk(shape, device=device, dtype=dtype)
+    lo = mk(shape, device=device, dtype=dtype) if (split and dtype == torch.bfloat16) else None
+    return Act(hi, lo, n, h, w, c, pad)
+
+
+def to_nhwc_bf16(x, cpad=None, dst=None, dst_off=0, pad=False):
     """NCHW fp32 (any batch stride, contiguous planes) -> NHWC bf16 activation with the channel count padded to a multiple
     of 16; optionally into channels [dst_off, dst_off+cpad) of an existing activation (folds torch.cat)."""
     from ._lib import lib, check
@@ -95,31 +110,29 @@ def to_nhwc_bf16(x, cpad=None, dst=None, dst_off=0):
         x = x.contiguous()
     cpad = _r16(c) if cpad is None else cpad
     if dst is None:
-        dst = new_act(n, h, w, cpad, x.device)
-    check(lib.adc_nchw_to_nhwc_bf16(x.data_ptr(), dst[0].data_ptr(), _ptr(dst[1]), n, c, cpad, h, w,
-                                    x.stride(0) if n > 1 else c * h * w, dst[0].shape[3], dst_off, _stream()), "adc_nchw_to_nhwc_bf16")
+        dst = new_act(n, h, w, cpad, x.device, pad=pad)
+    check(lib.adc_nchw_to_nhwc_bf16(x.data_ptr(), dst.hi.data_ptr(), _ptr(dst.lo), n, c, cpad, h, w,
+                                    x.stride(0) if n > 1 else c * h * w, dst.cs, dst_off, int(dst.pad), _stream()),
+          "adc_nchw_to_nhwc_bf16")
     return dst
 
 
 def to_nchw_f32(act, c, off=0):
-    """NHWC activation (bf16 pair, or a single fp32 NHWC tensor) channel slice -> NCHW fp32."""
+    """Channel slice [off, off+c) of an NHWC activation -> NCHW fp32 (hi + lo in the split mode)."""
     from ._lib import lib, check
-    if torch.is_tensor(act):
-        act = (act, None)
-    hi, lo = act
-    n, h, w, cs = hi.shape
-    out = torch.empty((n, c, h, w), device=hi.device, dtype=torch.float32)
-    check(lib.adc_nhwc_to_nchw_f32(hi.data_ptr(), int(hi.dtype == torch.float32), out.data_ptr(), n, c, h, w, cs, off, _stream()),
-          "adc_nhwc_to_nchw_f32")
-    if lo is not None:
+    out = torch.empty((act.n, c, act.h, act.w), device=act.hi.device, dtype=torch.float32)
+    check(lib.adc_nhwc_to_nchw_f32(act.hi.data_ptr(), int(act.hi.dtype == torch.float32), out.data_ptr(), act.n, c, act.h, act.w,
+                                   act.cs, off, int(act.pad), _stream()), "adc_nhwc_to_nchw_f32")
+    if act.lo is not None:
         low = torch.empty_like(out)
-        check(lib.adc_nhwc_to_nchw_f32(lo.data_ptr(), 0, low.data_ptr(), n, c, h, w, cs, off, _stream()), "adc_nhwc_to_nchw_f32")
+        check(lib.adc_nhwc_to_nchw_f32(act.lo.data_ptr(), 0, low.data_ptr(), act.n, c, act.h, act.w, act.cs, off, int(act.pad),
+                                       _stream()), "adc_nhwc_to_nchw_f32")
         out += low
     return out
 
 
 def prep_conv3x3_weights(weight, flip_transpose=False):
-    """fp32 [Cout,Cin,3,3] -> (hi, lo) bf16 [9][round16(Cout)][round16(Cin)] as the tensor-core kernel reads them."""
+    """fp32 [Cout,Cin,3,3] -> (hi, lo) bf16 [9][round16(Cout)][round16(Cin)] as the tensor-core kernels read them."""
     from ._lib import lib, check
     co, ci = weight.shape[:2]
     oc, ic = (ci, co) if flip_transpose else (co, ci)
@@ -130,36 +143,35 @@ def prep_conv3x3_weights(weight, flip_transpose=False):
     return (hi, lo)
 
 
-def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=None, out_off=0, out_f32=False):
-    """3x3 / pad 1 convolution on the tensor cores.  act: NHWC activation, channels [x_off, x_off+cin) are read (cin a
-    multiple of 16, zero padded); result written to channels [out_off, out_off+cout) of ``out`` (an activation, or a single
-    fp32 NHWC tensor when out_f32)."""
+def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=None, out_off=0, out_f32=False, out_pad=None):
+    """3x3 / pad 1 convolution on the tensor cores.  Channels [x_off, x_off+cin) of ``act`` are read (cin a multiple of 16,
+    zero padded); the result goes to channels [out_off, out_off+cout) of ``out`` (allocated if None)."""
     from ._lib import lib, check
-    hi, lo = act
-    n, h, w, cs = hi.shape
+    n, h, w = act.n, act.h, act.w
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     if out is None:
-        if out_f32:
-            out = torch.zeros((n, ho, wo, _r16(cout)), device=hi.device, dtype=torch.float32)
-        else:
-            out = new_act(n, ho, wo, _r16(cout), hi.device, zero=_r16(cout) != cout)
-    o_hi, o_lo = (out, None) if torch.is_tensor(out) else out
+        out_pad = act.pad if out_pad is None else out_pad
+        out = new_act(n, ho, wo, _r16(cout), act.hi.device, pad=out_pad, zero=_r16(cout) != cout,
+                      dtype=torch.float32 if out_f32 else torch.bfloat16)
     b = bias.detach().contiguous().data_ptr() if bias is not None else None
-    check(lib.adc_conv3x3_fprop_tc(hi.data_ptr(), _ptr(lo), cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b, o_hi.data_ptr(),
-                                   _ptr(o_lo), int(o_hi.dtype == torch.float32), o_hi.shape[3], out_off, n, h, w, cin, cout, stride,
-                                   act_fn, _stream()), "adc_conv3x3_fprop_tc")
+    is_f32 = int(out.hi.dtype == torch.float32)
+    if USE_V2 and stride == 1 and act.pad and out.pad and cin % 64 == 0 and cout <= 128:
+        check(lib.adc_conv3x3_s1_tc_v2(act.hi.data_ptr(), _ptr(act.lo), act.cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b,
+                                       out.hi.data_ptr(), _ptr(out.lo), is_f32, out.cs, out_off, n, h, w, cin, cout, act_fn,
+                                       _stream()), "adc_conv3x3_s1_tc_v2")
+    else:
+        check(lib.adc_conv3x3_fprop_tc(act.hi.data_ptr(), _ptr(act.lo), act.cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b,
+                                       out.hi.data_ptr(), _ptr(out.lo), is_f32, out.cs, out_off, n, h, w, cin, cout, stride, act_fn,
+                                       int(act.pad), int(out.pad), _stream()), "adc_conv3x3_fprop_tc")
     return out
 
 
-_wcache = {}
-
-
 def cached_weights(conv, embed_1x1=False):
-    """Prepared bf16 weights of a Conv2d, re-prepared only when the Parameter changes (version counter / storage / mode)."""
+    """Prepared bf16 weights of a Conv2d, kept ON the module and re-prepared only when the Parameter changes (storage,
+    in-place version counter) or the precision mode does."""
     w = conv.weight
-    key = id(conv)
     tag = (w.data_ptr(), w._version, PRECISION)
-    hit = _wcache.get(key)
+    hit = getattr(conv, "_adc_wprep", None)
     if hit is not None and hit[0] == tag:
         return hit[1]
     wt = w.detach()
@@ -168,7 +180,7 @@ def cached_weights(conv, embed_1x1=False):
         full[:, :, 1, 1] = wt[:, :, 0, 0]
         wt = full
     prep = prep_conv3x3_weights(wt)
-    _wcache[key] = (tag, prep)
+    conv._adc_wprep = (tag, prep)
     return prep
 
 

@@ -345,32 +345,33 @@ class GMSNet(nn.Module):
         nn.init.constant_(self.last_layer.bias, 0.01)
 
     def _forward_tc(self, x0, build_conf_input):
-        """Inference forward in the bf16 tensor-core mode: every 3x3 layer is the tcgen05 implicit-GEMM kernel on NHWC bf16
-        activations, ReLU fused, both torch.cat calls folded into channel-slice writes (confidence_depth_framework.py:630-669)."""
+        """Inference forward on the tensor cores: every 3x3 layer is a tcgen05 implicit-GEMM kernel on zero-bordered NHWC
+        bf16 activations, ReLU fused, both torch.cat calls folded into channel-slice writes
+        (confidence_depth_framework.py:630-669)."""
         x0_rgb = x0[:, :3, :, :]
         x0_d, c0 = _c0_of(x0)
         xout_d, cout_d = self.d_net(x0_d, c0)
         n, _, h, w = x0.shape
         dev = x0.device
-        act = dense.to_nhwc_bf16(xout_d)                                   # [N,H,W,16], channel 0 real
-        fuse_in = dense.new_act(n, h, w, 80, dev)
+        act = dense.to_nhwc_bf16(xout_d, pad=True)                          # 16 channels, channel 0 real
+        fuse_in = dense.new_act(n, h, w, 80, dev, pad=True)
         convs = [m for m in self.d if isinstance(m, nn.Conv2d)]
         for i, m in enumerate(convs):
             last = i == len(convs) - 1
-            act = dense.conv3x3_tc(act, act[0].shape[3], dense.cached_weights(m), m.bias, 16, 1, 1,
+            act = dense.conv3x3_tc(act, act.cs, dense.cached_weights(m), m.bias, 16, 1, 1,
                                    out=fuse_in if last else None, out_off=64 if last else 0)
-        rgbc = dense.new_act(n, h, w, 16, dev, zero=True)
+        rgbc = dense.new_act(n, h, w, 16, dev, pad=True)
         dense.to_nhwc_bf16(x0_rgb, cpad=3, dst=rgbc, dst_off=0)
         dense.to_nhwc_bf16(cout_d, cpad=1, dst=rgbc, dst_off=3)
         act = rgbc
         convs = [m for m in self.rgb if isinstance(m, nn.Conv2d)]
         for i, m in enumerate(convs):
             last = i == len(convs) - 1
-            act = dense.conv3x3_tc(act, act[0].shape[3], dense.cached_weights(m), m.bias, 64, 1, 1,
+            act = dense.conv3x3_tc(act, act.cs, dense.cached_weights(m), m.bias, 64, 1, 1,
                                    out=fuse_in if last else None, out_off=0)
         act = fuse_in
         for m in [m for m in self.fuse if isinstance(m, nn.Conv2d)]:
-            act = dense.conv3x3_tc(act, act[0].shape[3], dense.cached_weights(m), m.bias, m.out_channels, 1, 1)
+            act = dense.conv3x3_tc(act, act.cs, dense.cached_weights(m), m.bias, m.out_channels, 1, 1)
         xout_n = dense.conv3x3_tc(act, 32, dense.cached_weights(self.last_layer, embed_1x1=True), self.last_layer.bias,
                                   self.out_channels, 1, 0, out_f32=True)
         xout = dense.to_nchw_f32(xout_n, self.out_channels)

@@ -150,10 +150,11 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream);
  * 536-607; F.conv2d + bias + ReLU/LeakyReLU) in the bf16 tensor-core mode (parity 1e-2, BASELINE.json north_star).
  * Activations are NHWC bf16 with a channel count that is a multiple of 16; a layer may read / write a channel slice of a
  * wider tensor (x_off / out_off, strides in channels per pixel), which is how torch.cat is folded away. */
+/* pad = 1: the NHWC tensor carries a one-pixel zero border, [N][H+2][W+2][channels] (the layout of the v2 kernel) */
 int adc_nchw_to_nhwc_bf16(const float* src, void* dst, void* dst_lo /* NULL or the low halves */, int N, int C, int Cpad,
-                          int H, int W, long long src_batch_stride, int dst_stride, int dst_off, adc_stream_t stream);
+                          int H, int W, long long src_batch_stride, int dst_stride, int dst_off, int pad, adc_stream_t stream);
 int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int C, int H, int W, int src_stride, int src_off,
-                         adc_stream_t stream);
+                         int pad, adc_stream_t stream);
 /* weights fp32 [Cout,Cin,3,3] -> bf16 [9][round16(Cout)][round16(Cin)] (+ low halves); flip_transpose=1 = data-gradient form */
 size_t adc_conv3x3_weight_elems(int cout, int cin);
 int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int cout, int cin, int flip_transpose,
@@ -162,7 +163,12 @@ int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int c
  * mode: operands are (hi, lo) bf16 pairs, hi*hi + lo*hi + hi*lo accumulated in fp32 (fp32-grade parity, 3 MMAs per product). */
 int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
                          const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
-                         int W, int cin, int cout, int stride, int act, adc_stream_t stream);
+                         int W, int cin, int cout, int stride, int act, int x_pad, int out_pad, adc_stream_t stream);
+/* Stride-1 variant with shared-memory tap reuse, persistent CTAs and double-buffered TMEM accumulators; x and out are
+ * zero-bordered NHWC tensors, cin % 64 == 0, cout <= 128. */
+int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
+                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
+                         int W, int cin, int cout, int act, adc_stream_t stream);
 
 #ifdef __cplusplus
 }

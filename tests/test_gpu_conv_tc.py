@@ -50,21 +50,58 @@ def test_conv3x3_tc_matches_reference(cfg):
         dense.set_precision("bf16")
         xn = dense.to_nhwc_bf16(x.cuda())
         wp = dense.prep_conv3x3_weights(wt.cuda())
-        out32 = dense.conv3x3_tc(xn, xn[0].shape[3], wp, b.cuda(), co, stride, act, out_f32=True)
+        out32 = dense.conv3x3_tc(xn, xn.cs, wp, b.cuda(), co, stride, act, out_f32=True)
         got = dense.to_nchw_f32(out32, co).cpu()
         assert rel(got, ref) < 2e-5, rel(got, ref)
-        out16 = dense.conv3x3_tc(xn, xn[0].shape[3], wp, b.cuda(), co, stride, act)
+        out16 = dense.conv3x3_tc(xn, xn.cs, wp, b.cuda(), co, stride, act)
         assert rel(dense.to_nchw_f32(out16, co).cpu(), ref) < 1e-2
         assert rel(got, full) < 1e-2
         dense.set_precision("bf16x3")
         xs = dense.to_nhwc_bf16(x.cuda())
         ws = dense.prep_conv3x3_weights(wt.cuda())
-        o32 = dense.conv3x3_tc(xs, xs[0].shape[3], ws, b.cuda(), co, stride, act, out_f32=True)
+        o32 = dense.conv3x3_tc(xs, xs.cs, ws, b.cuda(), co, stride, act, out_f32=True)
         e3 = rel(dense.to_nchw_f32(o32, co).cpu(), full)
         assert e3 < 2e-5, e3
-        opair = dense.conv3x3_tc(xs, xs[0].shape[3], ws, b.cuda(), co, stride, act)      # (hi, lo) bf16 output
+        opair = dense.conv3x3_tc(xs, xs.cs, ws, b.cuda(), co, stride, act)      # (hi, lo) bf16 output
         e3p = rel(dense.to_nchw_f32(opair, co).cpu(), full)
         assert e3p < 5e-5, e3p
+    finally:
+        dense.set_precision("fp32")
+
+
+@gpu
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 40, 56, 1), (1, 64, 32, 57, 76, 2), (1, 128, 64, 33, 47, 1), (1, 64, 64, 228, 304, 1),
+                                 (3, 64, 16, 9, 11, 0), (1, 64, 80, 24, 40, 3)])
+@pytest.mark.parametrize("prec", ["bf16", "bf16x3"])
+def test_conv3x3_v2_tap_reuse_kernel(cfg, prec):
+    """v2 kernel (zero-bordered layout, 3 row segments per channel block, persistent, double-buffered TMEM)."""
+    from aerial_depth_completion_b200 import dense
+    n, ci, co, h, w, act = cfg
+    g = torch.Generator().manual_seed(ci * 100 + co + h)
+    x = torch.randn(n, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g) * (2.0 / (ci * 9)) ** 0.5
+    b = torch.randn(co, generator=g) * 0.1
+    rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
+    try:
+        dense.set_precision(prec)
+        ref = _ref(x, wt, b, 1, act, rounded=(prec == "bf16"))
+        xa = dense.to_nhwc_bf16(x.cuda(), pad=True)
+        wp = dense.prep_conv3x3_weights(wt.cuda())
+        o32 = dense.conv3x3_tc(xa, xa.cs, wp, b.cuda(), co, 1, act, out_f32=True)
+        assert o32.pad
+        e = rel(dense.to_nchw_f32(o32, co).cpu(), ref)
+        assert e < 2e-5, e
+        assert float(o32.hi[:, 0].abs().max()) == 0.0 and float(o32.hi[:, :, 0].abs().max()) == 0.0      # zero border kept
+        o16 = dense.conv3x3_tc(xa, xa.cs, wp, b.cuda(), co, 1, act)
+        e16 = rel(dense.to_nchw_f32(o16, co).cpu(), ref)
+        assert e16 < (5e-5 if prec == "bf16x3" else 1e-2), e16
+        # chained second layer straight from the kernel's own padded output
+        w2 = torch.randn(32, co, 3, 3, generator=g) * (2.0 / (co * 9)) ** 0.5
+        if co % 64 == 0:
+            o2 = dense.conv3x3_tc(o16, o16.cs, dense.prep_conv3x3_weights(w2.cuda()), None, 32, 1, 0, out_f32=True)
+            mid = dense.to_nchw_f32(o16, co).cpu()
+            ref2 = _ref(mid, w2, None, 1, 0, rounded=(prec == "bf16"))
+            assert rel(dense.to_nchw_f32(o2, 32).cpu(), ref2) < 5e-5
     finally:
         dense.set_precision("fp32")
 
