@@ -76,11 +76,11 @@ SIGNATURES = {
     "adc_nchw_to_nhwc_bf16": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_int, c_int, c_int, _vp]),
     "adc_nhwc_to_nchw_f32": (c_int, [_vp, c_int, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_weight_elems": (ctypes.c_size_t, [c_int, c_int]),
-    "adc_conv3x3_prep_weights": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, _vp]),
+    "adc_conv3x3_prep_weights": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_fprop_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_s1_tc_v2": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     c_int, c_int, c_int, _vp]),
+                                     c_int, c_int, c_int, c_int, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

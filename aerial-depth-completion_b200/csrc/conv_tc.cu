@@ -67,6 +67,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -117,6 +122,55 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Epilogue arithmetic on 16 accumulator columns: + bias (staged in shared memory, zero where there is none), activation.
+// The activation is selected ONCE per chunk (warp-uniform switch); the first version tested p.act, p.bias and p.cout per
+// element and compiled to 415 instructions per chunk, which made the epilogue (not the MMAs or the stores) the critical
+// path of the persistent kernel: 706 us per 64->64 layer against 231 us with the epilogue removed (profiles/r1_tc_epilogue.txt).
+template <int ACT>
+__device__ __forceinline__ void epi_bias_act16(float (&v)[16], const float* sb) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(sb + j);
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float r = v[j + i] + bb[i];
+            if (ACT == 1) r = fmaxf(r, 0.f);
+            else if (ACT == 2) r = r > 0.f ? r : 0.2f * r;
+            else if (ACT == 3) r = 1.f / (1.f + __expf(-r));
+            v[j + i] = r;
+        }
+    }
+}
+__device__ __forceinline__ void epi_bias_act16(float (&v)[16], const float* sb, int act) {
+    switch (act) {
+        case 1: epi_bias_act16<1>(v, sb); break;
+        case 2: epi_bias_act16<2>(v, sb); break;
+        case 3: epi_bias_act16<3>(v, sb); break;
+        default: epi_bias_act16<0>(v, sb); break;
+    }
+}
+// channels >= cout of a chunk (weights and bias are zero there, so only sigmoid(0) = 0.5 needs the mask) and border pixels -> 0
+__device__ __forceinline__ void epi_mask16(float (&v)[16], int c0, int cout, bool zero_all) {
+    if (c0 + 16 > cout) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (c0 + j >= cout) ? 0.f : v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = zero_all ? 0.f : v[j];
+}
+__device__ __forceinline__ void epi_pack_hi(const float (&v)[16], uint4 (&h)[2]) {
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(h);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+}
+__device__ __forceinline__ void epi_pack_lo(const float (&v)[16], const uint4 (&h)[2], uint4 (&l)[2]) {
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(h);
+    __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ll[j] = __floats2bfloat162_rn(v[2 * j] - __low2float(hh[j]), v[2 * j + 1] - __high2float(hh[j]));
+}
+
 // Shared-memory matrix descriptor, K-major operand whose rows are ROWB bytes (= the swizzle span: 128/64/32) and whose
 // 8-row swizzle atoms are packed back to back (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
 // version 1 <<46 | layout <<61; layout 2/4/6 = SWIZZLE_128B/64B/32B).
@@ -152,6 +206,7 @@ struct ConvParams {
 };
 
 constexpr int kStages = 4;
+constexpr int kSmemCap = 227 * 1024 - 1024;   // dynamic shared memory limit: the opt-in maximum minus the static bias table
 
 template <int KBLK>   // channels per K step: 64 / 32 / 16  (row bytes 128 / 64 / 32)
 __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x,
@@ -188,6 +243,8 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
         mbar_init(&bars[2 * kStages], 1);
         fence_barrier_init();
     }
+    __shared__ __align__(16) float sbias[256];
+    for (int i = threadIdx.x; i < 256; i += 192) sbias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
     if (warp == 1) tmem_alloc(tmem_slot, ncols);
     tc_fence_before();
     __syncthreads();
@@ -250,15 +307,7 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
             if (!valid) continue;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int co = c0 + j;
-                float r = v[j] + ((p.bias && co < p.cout) ? p.bias[co] : 0.f);
-                if (p.act == 1) r = fmaxf(r, 0.f);
-                else if (p.act == 2) r = r > 0.f ? r : 0.2f * r;
-                else if (p.act == 3) r = 1.f / (1.f + __expf(-r));
-                v[j] = r;
-            }
+            epi_bias_act16(v, sbias + c0, p.act);
             if (p.out_f32) {
                 float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
 #pragma unroll
@@ -266,25 +315,26 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                     if (c0 + j < p.cout) o[j] = v[j];
             } else {
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
-                if (p.out_lo) {
-                    __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * p.out_pix_stride + p.out_ch_off + c0;
+                __nv_bfloat16* ol = p.out_lo ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * p.out_pix_stride + p.out_ch_off + c0 : nullptr;
+                uint4 h[2], l[2];
+                epi_pack_hi(v, h);
+                if (ol) epi_pack_lo(v, h, l);
+                if (c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    reinterpret_cast<uint4*>(o)[0] = h[0];
+                    reinterpret_cast<uint4*>(o)[1] = h[1];
+                    if (ol) {
+                        reinterpret_cast<uint4*>(ol)[0] = l[0];
+                        reinterpret_cast<uint4*>(ol)[1] = l[1];
+                    }
+                } else {
+                    const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(h);
+                    const __nv_bfloat16* ls = reinterpret_cast<const __nv_bfloat16*>(l);
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (c0 + j < p.cout) {
-                            const __nv_bfloat16 hi = __float2bfloat16(v[j]);
-                            o[j] = hi;
-                            ol[j] = __float2bfloat16(v[j] - __bfloat162float(hi));
+                            o[j] = hs[j];
+                            if (ol) ol[j] = ls[j];
                         }
-                } else if (c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                    __nv_bfloat162 h[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(h)[0];
-                    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(h)[1];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < p.cout) o[j] = __float2bfloat16(v[j]);
                 }
             }
         }
@@ -314,7 +364,11 @@ struct ConvParamsV2 {
     void* out_lo;
     const float* bias;
     int ntiles;
-    int boff_mode;
+    int out_zero_to;         // channels [cout, out_zero_to) of the output slice are written as zeros (keeps padded inputs exact)
+    int resident;            // 1: all weight tiles stay in shared memory for the CTA's lifetime
+    int nstages;             // 2..8 pipeline stages
+    int tma_store;           // 1: bf16 output tile staged in shared memory and written by TMA bulk stores (slice width 64)
+    int dbg;                 // timing experiments: 1 = epilogue skips its global stores, 2 = epilogue skipped entirely
 };
 
 constexpr int kSegRows = 130;
@@ -333,33 +387,47 @@ __device__ __forceinline__ uint64_t make_desc_sw128_off(uint32_t smem_addr, int 
 __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_w,
                                                                const __grid_constant__ CUtensorMap map_xl,
-                                                               const __grid_constant__ CUtensorMap map_wl, ConvParamsV2 p) {
+                                                               const __grid_constant__ CUtensorMap map_wl,
+                                                               const __grid_constant__ CUtensorMap map_o,
+                                                               const __grid_constant__ CUtensorMap map_ol, ConvParamsV2 p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    const int b_tile = p.npad * 128;                  // one tap's weight tile (multiple of 1024: npad % 8 == 0)
-    const int b_bytes = 3 * b_tile;
-    const int half = kSegBytes + b_bytes;             // [A seg][B 3 taps]
-    const int stage_bytes = p.split ? 2 * half : half;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesV2 * stage_bytes);
-    // bars: full[2], empty[2], tmem_full[2], tmem_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = (p.cin + 63) / 64;
     const int steps = kblocks * 3;
+    const int nst = p.nstages;
+    const int b_tile = p.npad * 128;                  // one tap's weight tile (multiple of 1024: npad % 8 == 0)
+    const int w_all = 9 * kblocks * b_tile;           // every weight tile of the layer (resident mode)
+    // shared memory: [resident weights hi | lo] then nst stages of [A seg hi | (B 3 taps hi) | A seg lo | (B 3 taps lo)]
+    const int res_bytes = p.resident ? w_all * (p.split ? 2 : 1) : 0;
+    const int half = kSegBytes + (p.resident ? 0 : 3 * b_tile);
+    const int stage_bytes = p.split ? 2 * half : half;
+    uint8_t* stages = smem + res_bytes;
+    // output staging for the TMA store: one (two in split mode) 128-pixel x 64-channel bf16 tile, 128-byte swizzled
+    uint8_t* ostage = stages + nst * stage_bytes;
+    const int ostage_bytes = p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + ostage_bytes);
+    // bars: full[8], empty[8], tmem_full[2], tmem_empty[2], weights
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t ncols = 32;
     while ((int)ncols < 2 * p.npad) ncols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStagesV2; ++s) {
+        for (int s = 0; s < 8; ++s) {
             mbar_init(&bars[s], 1);
-            mbar_init(&bars[2 + s], 1);
-            mbar_init(&bars[4 + s], 1);
-            mbar_init(&bars[6 + s], 4);
+            mbar_init(&bars[8 + s], 1);
         }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars[16 + a], 1);
+            mbar_init(&bars[18 + a], 4);
+        }
+        mbar_init(&bars[20], 1);
         fence_barrier_init();
     }
+    __shared__ __align__(16) float sbias[128];
+    if (threadIdx.x < 128) sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.cout) ? p.bias[threadIdx.x] : 0.f;
     if (warp == 1) tmem_alloc(tmem_slot, ncols);
     tc_fence_before();
     __syncthreads();
@@ -369,21 +437,29 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
+            if (p.resident) {      // all weight tiles once: they stay in shared memory for every tile of this CTA
+                mbar_expect_tx(&bars[20], (uint32_t)res_bytes);
+                for (int kb = 0; kb < kblocks; ++kb)
+                    for (int u = 0; u < 3; ++u) {
+                        tma_load_3d(smem + (kb * 9 + 3 * u) * b_tile, &map_w, &bars[20], kb * 64, 0, 3 * u);
+                        if (p.split) tma_load_3d(smem + w_all + (kb * 9 + 3 * u) * b_tile, &map_wl, &bars[20], kb * 64, 0, 3 * u);
+                    }
+            }
             int q = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const long long m0 = (long long)tile * 128;
                 for (int st = 0; st < steps; ++st, ++q) {
-                    const int s = q % kStagesV2, use = q / kStagesV2;
+                    const int s = q % nst, use = q / nst;
                     const int kb = st / 3, u = st % 3;
-                    mbar_wait(&bars[2 + s], (use & 1) ^ 1);
-                    uint8_t* sa = smem + s * stage_bytes;
-                    mbar_expect_tx(&bars[s], (uint32_t)((kSegRows * 128 + b_bytes) * (p.split ? 2 : 1)));
+                    mbar_wait(&bars[8 + s], (use & 1) ^ 1);
+                    uint8_t* sa = stages + s * stage_bytes;
+                    mbar_expect_tx(&bars[s], (uint32_t)((kSegRows * 128 + (p.resident ? 0 : 3 * b_tile)) * (p.split ? 2 : 1)));
                     const long long f0 = m0 + (long long)(u - 1) * p.Wp - 1;
                     tma_load_2d(sa, &map_x, &bars[s], kb * 64, (int)f0);
-                    tma_load_3d(sa + kSegBytes, &map_w, &bars[s], kb * 64, 0, 3 * u);
+                    if (!p.resident) tma_load_3d(sa + kSegBytes, &map_w, &bars[s], kb * 64, 0, 3 * u);
                     if (p.split) {
                         tma_load_2d(sa + half, &map_xl, &bars[s], kb * 64, (int)f0);
-                        tma_load_3d(sa + half + kSegBytes, &map_wl, &bars[s], kb * 64, 0, 3 * u);
+                        if (!p.resident) tma_load_3d(sa + half + kSegBytes, &map_wl, &bars[s], kb * 64, 0, 3 * u);
                     }
                 }
             }
@@ -392,36 +468,44 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
         if (lane == 0) {
             // ===== MMA issuer =====
             const uint32_t idesc = make_idesc(128, p.npad);
+            const uint32_t sbase = base + res_bytes;
+            if (p.resident) {
+                mbar_wait(&bars[20], 0);
+                tc_fence_after();
+            }
             int q = 0, it = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
                 const int a = it & 1;
-                mbar_wait(&bars[6 + a], ((it >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+                mbar_wait(&bars[18 + a], ((it >> 1) & 1) ^ 1);         // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(a * p.npad);
                 for (int st = 0; st < steps; ++st, ++q) {
-                    const int s = q % kStagesV2, use = q / kStagesV2;
+                    const int s = q % nst, use = q / nst;
+                    const int kb = st / 3, u = st % 3;
                     mbar_wait(&bars[s], use & 1);
                     tc_fence_after();
-                    const uint32_t sa = base + s * stage_bytes;
+                    const uint32_t sa = sbase + s * stage_bytes;
 #pragma unroll
                     for (int v = 0; v < 3; ++v) {
-                        const uint32_t a_hi = sa + v * 128, b_hi = sa + kSegBytes + v * b_tile;
+                        const uint32_t a_hi = sa + v * 128;
+                        const uint32_t b_hi = p.resident ? base + (kb * 9 + 3 * u + v) * b_tile : sa + kSegBytes + v * b_tile;
+                        const uint32_t b_lo = p.resident ? b_hi + w_all : b_hi + half;
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_bf16(tacc, make_desc_sw128_off(a_hi, p.boff_mode) + 2 * k, make_desc<128>(b_hi) + 2 * k, idesc, (st | v | k) != 0);
+                            umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_hi) + 2 * k, idesc, (st | v | k) != 0);
                         if (p.split) {
-                            const uint32_t a_lo = a_hi + half, b_lo = b_hi + half;
+                            const uint32_t a_lo = a_hi + half;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_bf16(tacc, make_desc_sw128_off(a_lo, p.boff_mode) + 2 * k, make_desc<128>(b_hi) + 2 * k, idesc, 1);
+                                umma_bf16(tacc, make_desc_sw128_off(a_lo, 0) + 2 * k, make_desc<128>(b_hi) + 2 * k, idesc, 1);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_bf16(tacc, make_desc_sw128_off(a_hi, p.boff_mode) + 2 * k, make_desc<128>(b_lo) + 2 * k, idesc, 1);
+                                umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_lo) + 2 * k, idesc, 1);
                         }
                     }
-                    umma_commit(&bars[2 + s]);
+                    umma_commit(&bars[8 + s]);
                 }
-                umma_commit(&bars[4 + a]);
+                umma_commit(&bars[16 + a]);
             }
         }
     } else {
@@ -434,50 +518,62 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
             const bool inrange = m < p.F;
             const int wp = (int)(m % p.Wp), hp = (int)((m / p.Wp) % p.Hp);
             const bool border = wp == 0 || wp == p.Wp - 1 || hp == 0 || hp == p.Hp - 1;
-            mbar_wait(&bars[4 + a], (it >> 1) & 1);
+            mbar_wait(&bars[16 + a], (it >> 1) & 1);
             tc_fence_after();
-            for (int c0 = 0; c0 < p.npad; c0 += 16) {
+            if (p.tma_store && it > 0) {
+                // the previous tile's bulk store must have finished READING the staging tile before it is overwritten
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            const int c_end = p.dbg == 2 ? 0 : (p.out_zero_to > p.npad ? p.out_zero_to : p.npad);
+            for (int c0 = 0; c0 < c_end; c0 += 16) {
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.npad + c0), v);
-                if (!inrange) continue;
+                if (c0 < p.npad) {
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.npad + c0), v);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int co = c0 + j;
-                    float r = v[j] + ((p.bias && co < p.cout) ? p.bias[co] : 0.f);
-                    if (p.act == 1) r = fmaxf(r, 0.f);
-                    else if (p.act == 2) r = r > 0.f ? r : 0.2f * r;
-                    else if (p.act == 3) r = 1.f / (1.f + __expf(-r));
-                    v[j] = border ? 0.f : r;
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
                 }
+                if (!inrange || p.dbg == 1) continue;
+                const int lim = p.out_zero_to > p.cout ? p.out_zero_to : p.cout;   // channels this layer owns
+                if (c0 < p.npad) epi_bias_act16(v, sbias + c0, p.act);
+                epi_mask16(v, c0, p.cout, border);
                 if (p.out_f32) {
                     float* o = reinterpret_cast<float*>(p.out) + m * p.out_pix_stride + p.out_ch_off + c0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c0 + j < p.cout) o[j] = v[j];
+                        if (c0 + j < lim) o[j] = v[j];
+                    continue;
+                }
+                uint4 h[2], l[2];
+                epi_pack_hi(v, h);
+                if (p.out_lo) epi_pack_lo(v, h, l);
+                if (p.tma_store) {
+                    // stage the row in shared memory (16-byte chunks XOR-swizzled by row & 7, as the store map expects)
+                    const int row = quarter * 32 + lane, ch0 = (c0 >> 3);        // two 16-byte chunks per 16 channels
+                    uint8_t* rowp = ostage + row * 128;
+                    *reinterpret_cast<uint4*>(rowp + (((ch0) ^ (row & 7)) << 4)) = h[0];
+                    *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ (row & 7)) << 4)) = h[1];
+                    if (p.out_lo) {
+                        *reinterpret_cast<uint4*>(rowp + 16384 + (((ch0) ^ (row & 7)) << 4)) = l[0];
+                        *reinterpret_cast<uint4*>(rowp + 16384 + (((ch0 + 1) ^ (row & 7)) << 4)) = l[1];
+                    }
                 } else {
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.out_pix_stride + p.out_ch_off + c0;
-                    const bool full16 = c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-                    __nv_bfloat162 h[8], l[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                        l[j] = __floats2bfloat162_rn(v[2 * j] - __low2float(h[j]), v[2 * j + 1] - __high2float(h[j]));
-                    }
-                    if (full16) {
-                        reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(h)[0];
-                        reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(h)[1];
-                        if (p.out_lo) {
-                            __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + m * p.out_pix_stride + p.out_ch_off + c0;
-                            reinterpret_cast<uint4*>(ol)[0] = reinterpret_cast<uint4*>(l)[0];
-                            reinterpret_cast<uint4*>(ol)[1] = reinterpret_cast<uint4*>(l)[1];
+                    __nv_bfloat16* ol = p.out_lo ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) + m * p.out_pix_stride + p.out_ch_off + c0 : nullptr;
+                    if (c0 + 16 <= lim && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                        reinterpret_cast<uint4*>(o)[0] = h[0];
+                        reinterpret_cast<uint4*>(o)[1] = h[1];
+                        if (ol) {
+                            reinterpret_cast<uint4*>(ol)[0] = l[0];
+                            reinterpret_cast<uint4*>(ol)[1] = l[1];
                         }
                     } else {
                         const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(h);
                         const __nv_bfloat16* ls = reinterpret_cast<const __nv_bfloat16*>(l);
-                        __nv_bfloat16* ol = p.out_lo ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) + m * p.out_pix_stride + p.out_ch_off + c0 : nullptr;
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (c0 + j < p.cout) {
+                            if (c0 + j < lim) {
                                 o[j] = hs[j];
                                 if (ol) ol[j] = ls[j];
                             }
@@ -486,8 +582,20 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[6 + a]);      // this warp has drained accumulator a
+            if (lane == 0) mbar_arrive(&bars[18 + a]);     // this warp has drained accumulator a
+            if (p.tma_store) {
+                // all four epilogue warps have staged their rows -> one thread issues the coalesced bulk store(s)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 2 && lane == 0) {
+                    const long long m0 = (long long)tile * 128;
+                    tma_store_2d(&map_o, ostage, 0, (int)m0);
+                    if (p.out_lo) tma_store_2d(&map_ol, ostage + 16384, 0, (int)m0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
         }
+        if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -593,13 +701,13 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMa
     static bool done = false;
     if (!done) {   // opt in once to the largest configuration of this instantiation (npad = 256)
         int max_smem = 2 * kStages * ((128 * KBLK * 2 + 256 * KBLK * 2 + 1023) & ~1023) + 1024 + 256;
-        if (max_smem > 227 * 1024) max_smem = 227 * 1024;
+        if (max_smem > kSmemCap) max_smem = kSmemCap;
         int rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_fprop_tc_kernel<KBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
                                  "cudaFuncSetAttribute(conv3x3_fprop_tc_kernel)");
         if (rc) return rc;
         done = true;
     }
-    if (smem > 227 * 1024) {
+    if (smem > kSmemCap) {
         adc::set_error("conv3x3_fprop_tc: %d bytes of shared memory needed (Cout too large for the split mode)", smem);
         return ADC_E_UNSUPP;
     }
@@ -642,19 +750,19 @@ int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int
     return adc::check_cuda(cudaGetLastError(), "nhwc_to_nchw_f32_kernel launch");
 }
 
-size_t adc_conv3x3_weight_elems(int cout, int cin) {
-    const int npad = (cout + 15) / 16 * 16, cin_pad = (cin + 15) / 16 * 16;
+size_t adc_conv3x3_weight_elems(int cout, int cin_pad) {
+    const int npad = (cout + 15) / 16 * 16;
     return (size_t)9 * npad * cin_pad;
 }
 
-int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int cout, int cin, int flip_transpose,
+int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int cout, int cin, int cin_pad, int flip_transpose,
                              adc_stream_t stream) {
-    if (!w || !out_bf16 || cout <= 0 || cin <= 0) {
+    const int oc = flip_transpose ? cin : cout, ic = flip_transpose ? cout : cin;
+    if (!w || !out_bf16 || cout <= 0 || cin <= 0 || cin_pad < ic || cin_pad % 16 != 0) {
         adc::set_error("adc_conv3x3_prep_weights: bad argument");
         return ADC_E_BADARG;
     }
-    const int oc = flip_transpose ? cin : cout, ic = flip_transpose ? cout : cin;
-    const int npad = (oc + 15) / 16 * 16, cin_pad = (ic + 15) / 16 * 16;
+    const int npad = (oc + 15) / 16 * 16;
     prep_conv_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out_lo, cout, cin, npad,
                                                                    cin_pad, flip_transpose);
     return adc::check_cuda(cudaGetLastError(), "prep_conv_weights_kernel launch");
@@ -750,8 +858,8 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
 // Stride-1 3x3 convolution, v2 kernel (shared-memory tap reuse, persistent, double-buffered TMEM).  x and out are
 // zero-bordered NHWC tensors ([N][H+2][W+2][channels]); needs cin % 64 == 0.  Same split-mode convention as above.
 int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
-                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
-                         int W, int cin, int cout, int act, adc_stream_t stream) {
+                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
+                         int N, int H, int W, int cin, int cout, int act, adc_stream_t stream) {
     if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) {
         adc::set_error("adc_conv3x3_s1_tc_v2: bad argument");
         return ADC_E_BADARG;
@@ -778,7 +886,8 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
     p.cin = cin; p.npad = npad; p.cout = cout; p.act = act; p.out_f32 = out_f32; p.split = split;
     p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.out_lo = out_f32 ? nullptr : out_lo; p.bias = bias;
     p.ntiles = (int)((p.F + 127) / 128);
-    { const char* e = getenv("ADC_V2_BOFF"); p.boff_mode = e ? atoi(e) : 0; }
+    p.out_zero_to = out_zero_to;
+    { const char* e = getenv("ADC_V2_DBG"); p.dbg = e ? atoi(e) : 0; }
     CUtensorMap mx, mw, mxl, mwl;
     memset(&mxl, 0, sizeof(mxl));
     memset(&mwl, 0, sizeof(mwl));
@@ -814,16 +923,61 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
     int rc;
     if ((rc = make_x(&mx, x)) || (rc = make_w(&mw, w))) return rc;
     if (split && ((rc = make_x(&mxl, x_lo)) || (rc = make_w(&mwl, w_lo)))) return rc;
-    const int half = kSegBytes + 3 * npad * 128;
-    const int smem = kStagesV2 * (split ? 2 * half : half) + 1024 + 256;
-    if (smem > 227 * 1024) {
+    // bf16 output whose slice is exactly 64 channels wide: coalesced TMA bulk stores from a swizzled staging tile
+    // (per-thread 16-byte stores at a 128-byte stride were measured to cost more than the MMAs: 15.7 -> 6.4 ms for GMS)
+    CUtensorMap mo, mol;
+    memset(&mo, 0, sizeof(mo));
+    memset(&mol, 0, sizeof(mol));
+    const int width = out_zero_to > npad ? out_zero_to : npad;
+    p.tma_store = (!out_f32 && width == 64 && out_stride % 8 == 0 && out_off % 8 == 0) ? 1 : 0;
+    if (p.tma_store) {
+        auto make_o = [&](CUtensorMap* m, void* base_) -> int {
+            __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(base_) + out_off;
+            cuuint64_t dims[2] = {64, (cuuint64_t)p.F};
+            cuuint64_t strides[1] = {(cuuint64_t)out_stride * 2};
+            cuuint32_t box[2] = {64, 128};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ob, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                adc::set_error("cuTensorMapEncodeTiled(out, v2) failed: %d", (int)r);
+                return ADC_E_UNSUPP;
+            }
+            return 0;
+        };
+        if ((rc = make_o(&mo, out))) return rc;
+        if (p.out_lo && (rc = make_o(&mol, p.out_lo))) return rc;
+    }
+    // weights resident in shared memory if they fit next to >= 2 activation stages; otherwise streamed with every step
+    const int kblocks = (cin + 63) / 64, mult = split ? 2 : 1;
+    const int w_all = 9 * kblocks * npad * 128;
+    const int ostage_bytes = p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0;
+    const int budget = kSmemCap - 1024 - 256 - ostage_bytes;
+    int smem;
+    {
+        const char* e = getenv("ADC_V2_NO_RESIDENT");
+        const bool allow = !(e && e[0] == '1');
+        const int a_stage = kSegBytes * mult;
+        int nst_res = (budget - w_all * mult) / a_stage;
+        if (allow && nst_res >= 2) {
+            p.resident = 1;
+            p.nstages = nst_res > 8 ? 8 : nst_res;
+            smem = w_all * mult + p.nstages * a_stage + ostage_bytes + 1024 + 256;
+        } else {
+            const int st = (kSegBytes + 3 * npad * 128) * mult;
+            p.resident = 0;
+            p.nstages = budget / st > 8 ? 8 : budget / st;
+            smem = p.nstages * st + ostage_bytes + 1024 + 256;
+        }
+    }
+    if (p.nstages < 2 || smem > kSmemCap) {
         adc::set_error("adc_conv3x3_s1_tc_v2: %d bytes of shared memory needed", smem);
         return ADC_E_UNSUPP;
     }
     static bool done = false;
     static int sms = 148;
     if (!done) {
-        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap),
                              "cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel)");
         if (rc) return rc;
         int dev = 0;
@@ -832,7 +986,7 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
         done = true;
     }
     const int grid = p.ntiles < sms ? p.ntiles : sms;
-    conv3x3_s1_tc_v2_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mx, mw, mxl, mwl, p);
+    conv3x3_s1_tc_v2_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mx, mw, mxl, mwl, mo, mol, p);
     return adc::check_cuda(cudaGetLastError(), "conv3x3_s1_tc_v2_kernel launch");
 }
 

@@ -91,13 +91,26 @@ class Act:
         self.hi, self.lo, self.n, self.h, self.w, self.cs, self.pad = hi, lo, n, h, w, cs, pad
 
 
-def new_act(n, h, w, c, device, pad=False, zero=False, dtype=torch.bfloat16, split=None):
+def _r64(c):
+    return (c + 63) // 64 * 64
+
+
+def new_act(n, h, w, c, device, pad=False, zero=False, dtype=torch.bfloat16, split=None, border_only=False):
+    """zero=True clears everything; border_only clears just the one-pixel border of a padded tensor (the v1 kernel and the
+    layout conversion write the interior, the v2 kernel writes interior AND border itself)."""
     split = _split() if split is None else split
-    mk = torch.zeros if (zero or pad) else torch.empty       # a padded tensor's border must be zero
+    mk = torch.zeros if zero else torch.empty
     shape = (n, h + 2, w + 2, c) if pad else (n, h, w, c)
-    hi = mk(shape, device=device, dtype=dtype)
-    lo = mk(shape, device=device, dtype=dtype) if (split and dtype == torch.bfloat16) else None
-    return Act(hi, lo, n, h, w, c, pad)
+    ts = [mk(shape, device=device, dtype=dtype)]
+    if split and dtype == torch.bfloat16:
+        ts.append(mk(shape, device=device, dtype=dtype))
+    if pad and border_only and not zero:
+        for t in ts:
+            t[:, 0].zero_()
+            t[:, -1].zero_()
+            t[:, :, 0].zero_()
+            t[:, :, -1].zero_()
+    return Act(ts[0], ts[1] if len(ts) > 1 else None, n, h, w, c, pad)
 
 
 def to_nhwc_bf16(x, cpad=None, dst=None, dst_off=0, pad=False):
@@ -110,7 +123,7 @@ def to_nhwc_bf16(x, cpad=None, dst=None, dst_off=0, pad=False):
         x = x.contiguous()
     cpad = _r16(c) if cpad is None else cpad
     if dst is None:
-        dst = new_act(n, h, w, cpad, x.device, pad=pad)
+        dst = new_act(n, h, w, cpad, x.device, pad=pad, border_only=True)
     check(lib.adc_nchw_to_nhwc_bf16(x.data_ptr(), dst.hi.data_ptr(), _ptr(dst.lo), n, c, cpad, h, w,
                                     x.stride(0) if n > 1 else c * h * w, dst.cs, dst_off, int(dst.pad), _stream()),
           "adc_nchw_to_nhwc_bf16")
@@ -131,33 +144,41 @@ def to_nchw_f32(act, c, off=0):
     return out
 
 
-def prep_conv3x3_weights(weight, flip_transpose=False):
-    """fp32 [Cout,Cin,3,3] -> (hi, lo) bf16 [9][round16(Cout)][round16(Cin)] as the tensor-core kernels read them."""
+def prep_conv3x3_weights(weight, flip_transpose=False, cin_pad=None):
+    """fp32 [Cout,Cin,3,3] -> (hi, lo) bf16 [9][round16(Cout)][cin_pad] as the tensor-core kernels read them (input channels
+    zero padded to ``cin_pad``, default round16(Cin))."""
     from ._lib import lib, check
     co, ci = weight.shape[:2]
     oc, ic = (ci, co) if flip_transpose else (co, ci)
-    hi = torch.empty((9, _r16(oc), _r16(ic)), device=weight.device, dtype=torch.bfloat16)
+    cin_pad = _r16(ic) if cin_pad is None else cin_pad
+    hi = torch.empty((9, _r16(oc), cin_pad), device=weight.device, dtype=torch.bfloat16)
     lo = torch.empty_like(hi) if _split() else None
-    check(lib.adc_conv3x3_prep_weights(weight.detach().contiguous().data_ptr(), hi.data_ptr(), _ptr(lo), co, ci, int(flip_transpose),
-                                       _stream()), "adc_conv3x3_prep_weights")
+    check(lib.adc_conv3x3_prep_weights(weight.detach().contiguous().data_ptr(), hi.data_ptr(), _ptr(lo), co, ci, cin_pad,
+                                       int(flip_transpose), _stream()), "adc_conv3x3_prep_weights")
     return (hi, lo)
 
 
-def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=None, out_off=0, out_f32=False, out_pad=None):
+def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=None, out_off=0, out_f32=False, out_pad=None,
+               out_zero_to=0):
     """3x3 / pad 1 convolution on the tensor cores.  Channels [x_off, x_off+cin) of ``act`` are read (cin a multiple of 16,
     zero padded); the result goes to channels [out_off, out_off+cout) of ``out`` (allocated if None)."""
     from ._lib import lib, check
     n, h, w = act.n, act.h, act.w
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    v2 = USE_V2 and stride == 1 and act.pad and cin % 64 == 0 and cout <= 128 and (out is None or out.pad)
+    zero_to = out_zero_to if v2 else 0                      # slice width the layer owns (channels past cout written as 0)
     if out is None:
         out_pad = act.pad if out_pad is None else out_pad
-        out = new_act(n, ho, wo, _r16(cout), act.hi.device, pad=out_pad, zero=_r16(cout) != cout,
+        v2 = v2 and out_pad
+        cs = _r64(cout) if v2 else _r16(cout)               # v2 chains want 64-channel blocks
+        out = new_act(n, ho, wo, cs, act.hi.device, pad=out_pad, zero=(not v2) and cs != cout, border_only=not v2,
                       dtype=torch.float32 if out_f32 else torch.bfloat16)
+        zero_to = cs                                         # v2 writes the pad channels (and the border) as zeros itself
     b = bias.detach().contiguous().data_ptr() if bias is not None else None
     is_f32 = int(out.hi.dtype == torch.float32)
-    if USE_V2 and stride == 1 and act.pad and out.pad and cin % 64 == 0 and cout <= 128:
+    if v2:
         check(lib.adc_conv3x3_s1_tc_v2(act.hi.data_ptr(), _ptr(act.lo), act.cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b,
-                                       out.hi.data_ptr(), _ptr(out.lo), is_f32, out.cs, out_off, n, h, w, cin, cout, act_fn,
+                                       out.hi.data_ptr(), _ptr(out.lo), is_f32, out.cs, out_off, zero_to, n, h, w, cin, cout, act_fn,
                                        _stream()), "adc_conv3x3_s1_tc_v2")
     else:
         check(lib.adc_conv3x3_fprop_tc(act.hi.data_ptr(), _ptr(act.lo), act.cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b,
@@ -166,11 +187,11 @@ def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=No
     return out
 
 
-def cached_weights(conv, embed_1x1=False):
+def cached_weights(conv, embed_1x1=False, cin_pad=None):
     """Prepared bf16 weights of a Conv2d, kept ON the module and re-prepared only when the Parameter changes (storage,
-    in-place version counter) or the precision mode does."""
+    in-place version counter) or the precision mode / channel padding does."""
     w = conv.weight
-    tag = (w.data_ptr(), w._version, PRECISION)
+    tag = (w.data_ptr(), w._version, PRECISION, cin_pad)
     hit = getattr(conv, "_adc_wprep", None)
     if hit is not None and hit[0] == tag:
         return hit[1]
@@ -179,7 +200,7 @@ def cached_weights(conv, embed_1x1=False):
         full = torch.zeros(wt.shape[0], wt.shape[1], 3, 3, device=wt.device, dtype=wt.dtype)
         full[:, :, 1, 1] = wt[:, :, 0, 0]
         wt = full
-    prep = prep_conv3x3_weights(wt)
+    prep = prep_conv3x3_weights(wt, cin_pad=cin_pad)
     conv._adc_wprep = (tag, prep)
     return prep
 

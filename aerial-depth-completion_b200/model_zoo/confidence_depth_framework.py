@@ -345,40 +345,44 @@ class GMSNet(nn.Module):
         nn.init.constant_(self.last_layer.bias, 0.01)
 
     def _forward_tc(self, x0, build_conf_input):
-        """Inference forward on the tensor cores: every 3x3 layer is a tcgen05 implicit-GEMM kernel on zero-bordered NHWC
-        bf16 activations, ReLU fused, both torch.cat calls folded into channel-slice writes
+        """Inference forward on the tensor cores: every 3x3 layer is the tcgen05 implicit-GEMM kernel (tap-reuse variant) on
+        zero-bordered NHWC bf16 activations whose channel count is padded to a multiple of 64 (pad channels are zeros and
+        meet zero weights); ReLU fused; both torch.cat calls folded into channel-slice writes
         (confidence_depth_framework.py:630-669)."""
         x0_rgb = x0[:, :3, :, :]
         x0_d, c0 = _c0_of(x0)
         xout_d, cout_d = self.d_net(x0_d, c0)
         n, _, h, w = x0.shape
         dev = x0.device
-        act = dense.to_nhwc_bf16(xout_d, pad=True)                          # 16 channels, channel 0 real
-        fuse_in = dense.new_act(n, h, w, 80, dev, pad=True)
+        conv = lambda a, m, cout, relu=1, **kw: dense.conv3x3_tc(a, a.cs, dense.cached_weights(m, cin_pad=a.cs), m.bias, cout, 1,
+                                                                  relu, **kw)
+        # [rgb stream 64 | depth stream 16 | zeros 48]: both 64-channel slices (borders and pad channels included) are written
+        # whole by the convolutions that produce them, so the buffer needs no zero fill
+        fuse_in = dense.new_act(n, h, w, 128, dev, pad=True, zero=False)
+        act = dense.to_nhwc_bf16(xout_d, cpad=64, pad=True)                 # channel 0 real
         convs = [m for m in self.d if isinstance(m, nn.Conv2d)]
         for i, m in enumerate(convs):
             last = i == len(convs) - 1
-            act = dense.conv3x3_tc(act, act.cs, dense.cached_weights(m), m.bias, 16, 1, 1,
-                                   out=fuse_in if last else None, out_off=64 if last else 0)
-        rgbc = dense.new_act(n, h, w, 16, dev, pad=True)
+            act = conv(act, m, 16, out=fuse_in if last else None, out_off=64 if last else 0, out_zero_to=64 if last else 0)
+        rgbc = dense.new_act(n, h, w, 64, dev, pad=True, zero=True)
         dense.to_nhwc_bf16(x0_rgb, cpad=3, dst=rgbc, dst_off=0)
         dense.to_nhwc_bf16(cout_d, cpad=1, dst=rgbc, dst_off=3)
         act = rgbc
         convs = [m for m in self.rgb if isinstance(m, nn.Conv2d)]
         for i, m in enumerate(convs):
             last = i == len(convs) - 1
-            act = dense.conv3x3_tc(act, act.cs, dense.cached_weights(m), m.bias, 64, 1, 1,
-                                   out=fuse_in if last else None, out_off=0)
+            act = conv(act, m, 64, out=fuse_in if last else None, out_off=0, out_zero_to=64 if last else 0)
         act = fuse_in
         for m in [m for m in self.fuse if isinstance(m, nn.Conv2d)]:
-            act = dense.conv3x3_tc(act, act.cs, dense.cached_weights(m), m.bias, m.out_channels, 1, 1)
-        xout_n = dense.conv3x3_tc(act, 32, dense.cached_weights(self.last_layer, embed_1x1=True), self.last_layer.bias,
-                                  self.out_channels, 1, 0, out_f32=True)
+            act = conv(act, m, m.out_channels)
+        last_in = act
+        xout_n = dense.conv3x3_tc(act, act.cs, dense.cached_weights(self.last_layer, embed_1x1=True, cin_pad=act.cs),
+                                  self.last_layer.bias, self.out_channels, 1, 0, out_f32=True)
         xout = dense.to_nchw_f32(xout_n, self.out_channels)
         features = None
         if build_conf_input:
             if self.out_channels == 1:
-                features = torch.cat((dense.to_nchw_f32(act, 32), dense.to_nchw_f32(fuse_in, 16, 64), cout_d, xout), 1)
+                features = torch.cat((dense.to_nchw_f32(last_in, 32), dense.to_nchw_f32(fuse_in, 16, 64), cout_d, xout), 1)
             else:
                 features = torch.sigmoid(xout[:, 1:2, :, :])
         return xout[:, 0:1, :, :], features

@@ -155,9 +155,10 @@ int adc_nchw_to_nhwc_bf16(const float* src, void* dst, void* dst_lo /* NULL or t
                           int H, int W, long long src_batch_stride, int dst_stride, int dst_off, int pad, adc_stream_t stream);
 int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int C, int H, int W, int src_stride, int src_off,
                          int pad, adc_stream_t stream);
-/* weights fp32 [Cout,Cin,3,3] -> bf16 [9][round16(Cout)][round16(Cin)] (+ low halves); flip_transpose=1 = data-gradient form */
-size_t adc_conv3x3_weight_elems(int cout, int cin);
-int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int cout, int cin, int flip_transpose,
+/* weights fp32 [Cout,Cin,3,3] -> bf16 [9][round16(Cout)][cin_pad] (+ low halves), input channels zero padded to cin_pad
+ * (a multiple of 16, >= Cin); flip_transpose=1 = data-gradient form */
+size_t adc_conv3x3_weight_elems(int cout, int cin_pad);
+int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int cout, int cin, int cin_pad, int flip_transpose,
                              adc_stream_t stream);
 /* act: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 sigmoid.  stride 1 or 2, padding 1.  x_lo/w_lo non-NULL selects the bf16x3 split
  * mode: operands are (hi, lo) bf16 pairs, hi*hi + lo*hi + hi*lo accumulated in fp32 (fp32-grade parity, 3 MMAs per product). */
@@ -165,10 +166,10 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
                          const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
                          int W, int cin, int cout, int stride, int act, int x_pad, int out_pad, adc_stream_t stream);
 /* Stride-1 variant with shared-memory tap reuse, persistent CTAs and double-buffered TMEM accumulators; x and out are
- * zero-bordered NHWC tensors, cin % 64 == 0, cout <= 128. */
+ * zero-bordered NHWC tensors, cin % 64 == 0, cout <= 128; channels [cout, out_zero_to) of the output slice are zeroed. */
 int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
-                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
-                         int W, int cin, int cout, int act, adc_stream_t stream);
+                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
+                         int N, int H, int W, int cin, int cout, int act, adc_stream_t stream);
 
 #ifdef __cplusplus
 }
