@@ -37,6 +37,7 @@ def parse():
     p.add_argument("--cpu-frames", type=int, default=0, help="frames per step of the CPU arms (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    p.add_argument("--no-extras", action="store_true", help="skip the extra (non-headline) measurements")
     return p.parse_args()
 
 
@@ -274,6 +275,8 @@ def b200_arm(args):
                             "frac": round(dom["gbs"] / peak, 4), "traffic": None, "kernel": dom["name"],
                             "launch_us": round(dom["us"], 2), "algorithmic_mb_per_launch": round(dom["mb"], 2),
                             "peak_source": peak_src, "nconv_kernels": roof["table"]}
+    if world == 1 and not args.no_extras:
+        line["extra"] = {"gms_inference_b32": gms_inference(dev)}
     if not args.no_cpu_baseline and world == 1:
         fps, ms, cores, fr = cpu_reference_run(3, 1, args.cpu_frames or 1)
         line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
@@ -281,6 +284,52 @@ def b200_arm(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def gms_inference(dev, B=32):
+    """BASELINE.json configs[1]: gms_depthcompnet inference, batch 32, 228x304, one GPU (49.3 GFLOP of 3x3 convolutions per
+    frame).  Three arithmetic modes of the same drop-in module: library fp32, and the hand-written tcgen05 implicit-GEMM
+    kernels in bf16x3 (hi/lo split operands, fp32-grade results: the 1e-4 parity mode) and plain bf16 (the 1e-2 mode)."""
+    import contextlib
+    import io
+    import torch
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    from aerial_depth_completion_b200 import dense
+    torch.manual_seed(0)
+    f = mc.ConfidenceDepthFrameworkFactory()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = f.create_model("rgbd", "dc1_only", "gms_depthcompnet", "")
+        m, _ = f.to_device(m)
+        m.train(False)
+    g = torch.Generator(device=dev).manual_seed(7)
+    xs = []
+    for _ in range(3):                                     # 3 x 44 MB inputs; activations (GBs per pass) flush the L2 anyway
+        x = torch.rand(B, 5, H, W, device=dev, generator=g)
+        mask = (torch.rand(B, 1, H, W, device=dev, generator=g) < 0.0072).float()
+        x[:, 3:4] = (x[:, 3:4] * 9.0 + 1.0) * mask
+        x[:, 4:5] = mask
+        xs.append(x)
+    out = {"flop_per_frame": 49.3e9}
+    prev = dense.PRECISION
+    try:
+        for prec in ("fp32", "bf16x3", "bf16"):
+            dense.set_precision(prec)
+            with torch.no_grad():
+                for i in range(3):
+                    m(xs[i % 3])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(10):
+                    m(xs[i % 3])
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            out[prec] = {"ms_per_batch": round(ms, 3), "frames_s": round(B / ms * 1e3, 1), "tflops": round(49.3e9 * B / ms / 1e9, 1),
+                         "dense_path": "library (cuDNN fp32)" if prec == "fp32" else "tcgen05 implicit GEMM (libadc_b200)"}
+    finally:
+        dense.set_precision(prev)
+    return out
 
 
 def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B):
