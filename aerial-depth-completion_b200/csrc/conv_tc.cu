@@ -23,169 +23,9 @@
 
 #include "../../include/adc_b200.h"
 
-namespace adc {
-void set_error(const char* fmt, ...);
-int check_cuda(cudaError_t e, const char* what);
-}  // namespace adc
+#include "tc_common.cuh"
 
 namespace tc {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "TC_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra TC_DONE;\n"
-        "bra TC_WAIT;\n"
-        "TC_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(phase)
-        : "memory");
-}
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-// ---- tcgen05 wrappers ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // one full warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // same warp
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on an mbarrier when all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns of this warp's TMEM lane quarter
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Epilogue arithmetic on 16 accumulator columns: + bias (staged in shared memory, zero where there is none), activation.
-// The activation is selected ONCE per chunk (warp-uniform switch); the first version tested p.act, p.bias and p.cout per
-// element and compiled to 415 instructions per chunk, which made the epilogue (not the MMAs or the stores) the critical
-// path of the persistent kernel: 706 us per 64->64 layer against 231 us with the epilogue removed (profiles/r1_tc_epilogue.txt).
-template <int ACT>
-__device__ __forceinline__ void epi_bias_act16(float (&v)[16], const float* sb) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(sb + j);
-        const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float r = v[j + i] + bb[i];
-            if (ACT == 1) r = fmaxf(r, 0.f);
-            else if (ACT == 2) r = r > 0.f ? r : 0.2f * r;
-            else if (ACT == 3) r = 1.f / (1.f + __expf(-r));
-            v[j + i] = r;
-        }
-    }
-}
-__device__ __forceinline__ void epi_bias_act16(float (&v)[16], const float* sb, int act) {
-    switch (act) {
-        case 1: epi_bias_act16<1>(v, sb); break;
-        case 2: epi_bias_act16<2>(v, sb); break;
-        case 3: epi_bias_act16<3>(v, sb); break;
-        default: epi_bias_act16<0>(v, sb); break;
-    }
-}
-// channels >= cout of a chunk (weights and bias are zero there, so only sigmoid(0) = 0.5 needs the mask) and border pixels -> 0
-__device__ __forceinline__ void epi_mask16(float (&v)[16], int c0, int cout, bool zero_all) {
-    if (c0 + 16 > cout) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (c0 + j >= cout) ? 0.f : v[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = zero_all ? 0.f : v[j];
-}
-__device__ __forceinline__ void epi_pack_hi(const float (&v)[16], uint4 (&h)[2]) {
-    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(h);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-}
-__device__ __forceinline__ void epi_pack_lo(const float (&v)[16], const uint4 (&h)[2], uint4 (&l)[2]) {
-    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(h);
-    __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(l);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ll[j] = __floats2bfloat162_rn(v[2 * j] - __low2float(hh[j]), v[2 * j + 1] - __high2float(hh[j]));
-}
-
-// Shared-memory matrix descriptor, K-major operand whose rows are ROWB bytes (= the swizzle span: 128/64/32) and whose
-// 8-row swizzle atoms are packed back to back (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
-// version 1 <<46 | layout <<61; layout 2/4/6 = SWIZZLE_128B/64B/32B).
-template <int ROWB>
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);
-    constexpr uint64_t sbo = (8 * ROWB) >> 4;
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and B,
-// N>>3 at bit 17, M>>4 at bit 24.
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 struct ConvParams {
     int N, H, W;            // input image size
@@ -206,7 +46,6 @@ struct ConvParams {
 };
 
 constexpr int kStages = 4;
-constexpr int kSmemCap = 227 * 1024 - 1024;   // dynamic shared memory limit: the opt-in maximum minus the static bias table
 
 template <int KBLK>   // channels per K step: 64 / 32 / 16  (row bytes 128 / 64 / 32)
 __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x,
@@ -675,24 +514,6 @@ __global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
         out[i] = hi;
         if (out_lo) out_lo[i] = __float2bfloat16(v - __bfloat162float(hi));
     }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-static CUtensorMapSwizzle swz(int kblk) {
-    return kblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 template <int KBLK>

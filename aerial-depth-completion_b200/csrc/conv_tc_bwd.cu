@@ -1,0 +1,271 @@
+// K6: weight gradient of a dense 3x3 / stride-1 convolution on the tcgen05 tensor cores, plus the NHWC glue kernels of the
+// tensor-core training path (the backward of confidence_depth_framework.py:464-518 and :630-669).
+//
+//   dW[co][ci][u][v] = sum_p  gy[p][co] * x[p + (u-1)*(W+2) + (v-1)][ci]          p = flat pixel of the zero-bordered layout
+//
+// Both tensors are zero-bordered NHWC bf16 ([N][H+2][W+2][C], borders of gy are zeros), so every tap is a shift of the flat
+// pixel index -- the same property the forward v2 kernel uses.  GEMM view: M = Cout (128 rows, 64-channel blocks of gy),
+// N = Cin (<= 160 columns), K = pixels.  The contraction index is the SLOW index of both operands in memory, i.e. both are
+// "MN-major" UMMA operands: a TMA box [64 channels x KP pixels] with the 128-byte swizzle is exactly the canonical
+// MN-major SWIZZLE_128B layout (8 K-rows of 128 bytes per atom, SBO = 1024 bytes between K groups, LBO = distance between
+// 64-channel blocks).  A stride-2 layer is the same contraction on a zero-dilated gy (z[2i][2j] = gy[i][j]).
+// Work split: CTA (g, u) owns vertical tap u and every G-th K tile; it keeps the three accumulators of taps (u, 0..2) in
+// TMEM for its whole life (3 x Cin columns) and feeds the three horizontal taps from ONE x segment of KP+2 pixels (B
+// descriptors start 0,1,2 rows into it).  Partial sums go to a workspace [G][9][Cout16][Cin16] and a second kernel reduces
+// them in a fixed order (deterministic, no atomics) into the Parameter layout [Cout][Cin][3][3].
+#include "tc_common.cuh"
+
+namespace tc {
+
+struct WgradParams {
+    long long F;          // flat pixels N*(H+2)*(W+2)
+    int Wp;               // W+2
+    int ncols, mrows;     // GEMM N = Cin of the slice rounded to 16; rows kept = Cout rounded to 16
+    int mb, nb;           // 64-channel blocks of gy / of x per stage
+    int kp;               // pixels per K tile (64 or 128)
+    int ktiles, groups, nstages, split;
+    int bseg;             // bytes reserved per 64-channel x block ((kp+2) rows of 128 bytes, rounded up to 1024)
+    float* part;          // [groups][9][mrows][ncols]
+};
+
+// MN-major SWIZZLE_128B operand: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout 2 <<61
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// as make_idesc, with A and B MN-major (bits 15, 16)
+__device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) { return make_idesc(M, N) | (1u << 15) | (1u << 16); }
+
+__global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_g,
+                                                               const __grid_constant__ CUtensorMap map_x,
+                                                               const __grid_constant__ CUtensorMap map_gl,
+                                                               const __grid_constant__ CUtensorMap map_xl, WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int a_bytes = p.mb * p.kp * 128, b_bytes = p.nb * p.bseg;
+    const int half = a_bytes + b_bytes;
+    const int stage_bytes = p.split ? 2 * half : half;
+    const int nst = p.nstages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);    // full[8], empty[8], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u = blockIdx.x % 3, g = blockIdx.x / 3;
+    const int my_tiles = g < p.ktiles ? (p.ktiles - g + p.groups - 1) / p.groups : 0;
+    uint32_t ncols_alloc = 32;
+    while ((int)ncols_alloc < 3 * p.ncols) ncols_alloc <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(&bars[s], 1);
+            mbar_init(&bars[8 + s], 1);
+        }
+        mbar_init(&bars[16], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, ncols_alloc);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            const uint32_t tx = (uint32_t)((p.mb * p.kp + p.nb * (p.kp + 2)) * 128 * (p.split ? 2 : 1));
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % nst, use = i / nst;
+                const long long p0 = (long long)(g + i * p.groups) * p.kp;
+                const long long x0 = p0 + (long long)(u - 1) * p.Wp - 1;
+                mbar_wait(&bars[8 + s], (use & 1) ^ 1);
+                uint8_t* sa = smem + s * stage_bytes;
+                mbar_expect_tx(&bars[s], tx);
+                for (int b = 0; b < p.mb; ++b) tma_load_2d(sa + b * p.kp * 128, &map_g, &bars[s], b * 64, (int)p0);
+                for (int b = 0; b < p.nb; ++b) tma_load_2d(sa + a_bytes + b * p.bseg, &map_x, &bars[s], b * 64, (int)x0);
+                if (p.split) {
+                    for (int b = 0; b < p.mb; ++b) tma_load_2d(sa + half + b * p.kp * 128, &map_gl, &bars[s], b * 64, (int)p0);
+                    for (int b = 0; b < p.nb; ++b) tma_load_2d(sa + half + a_bytes + b * p.bseg, &map_xl, &bars[s], b * 64, (int)x0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = make_idesc_mn(128, p.ncols);
+            const uint32_t lbo_a = p.mb > 1 ? (uint32_t)(p.kp * 128) : 0u;    // one block only: rows 64..127 replay rows 0..63 (never read back)
+            const uint32_t lbo_b = (uint32_t)p.bseg;
+            const int ksteps = p.kp / 16;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % nst, use = i / nst;
+                mbar_wait(&bars[s], use & 1);
+                tc_fence_after();
+                const uint32_t sa = base + s * stage_bytes, sb = sa + a_bytes;
+                for (int v = 0; v < 3; ++v) {
+                    const uint32_t tacc = tmem_base + (uint32_t)(v * p.ncols);
+                    for (int k = 0; k < ksteps; ++k) {       // 16 pixels = 2 swizzle atoms = 2048 bytes per K step
+                        const uint64_t da = make_desc_mn(sa + k * 2048, lbo_a);
+                        const uint64_t db = make_desc_mn(sb + v * 128 + k * 2048, lbo_b);
+                        umma_bf16(tacc, da, db, idesc, (i | k) != 0);
+                        if (p.split) {
+                            umma_bf16(tacc, make_desc_mn(sa + half + k * 2048, lbo_a), db, idesc, 1);
+                            umma_bf16(tacc, da, make_desc_mn(sb + half + v * 128 + k * 2048, lbo_b), idesc, 1);
+                        }
+                    }
+                }
+                umma_commit(&bars[8 + s]);
+            }
+            umma_commit(&bars[16]);
+        }
+    } else {
+        // ===== epilogue warps 2..5: rows (= output channels) quarter*32 + lane =====
+        const int quarter = warp & 3, row = quarter * 32 + lane;
+        if (my_tiles > 0) {
+            mbar_wait(&bars[16], 0);
+            tc_fence_after();
+        }
+        for (int v = 0; v < 3; ++v) {
+            float* dst = p.part + (((long long)g * 9 + u * 3 + v) * p.mrows + row) * p.ncols;
+            for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+                float r[16];
+                if (my_tiles > 0) {
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(v * p.ncols + c0), r);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0.f;
+                }
+                if (row < p.mrows) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols_alloc);
+}
+
+// dW[co][ci][tap] = sum_g part[g][tap][co][ci]   (fixed order; reads coalesced along ci)
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int groups, int mrows,
+                                                              int ncols, int cout, int cin) {
+    const int total = 9 * cout * cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
+        float acc = 0.f;
+        for (int g = 0; g < groups; ++g) acc += part[(((long long)g * 9 + tap) * mrows + co) * ncols + ci];
+        dw[((long long)co * cin + ci) * 9 + tap] = acc;
+    }
+}
+
+static int wgrad_groups() {
+    static int groups = 0;
+    if (!groups) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        groups = sms / 3 > 0 ? sms / 3 : 1;
+    }
+    return groups;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+extern "C" {
+
+size_t adc_conv3x3_wgrad_tc_workspace_bytes(int cin_pad, int cout) {
+    if (cin_pad <= 0 || cout <= 0) return 0;
+    const int mrows = (cout + 15) / 16 * 16;
+    return (size_t)wgrad_groups() * 9 * mrows * cin_pad * sizeof(float);
+}
+
+// gy: zero-bordered NHWC bf16 [N][H+2][W+2][gy_stride] (channels [gy_off, gy_off+cout) are read; border pixels must be 0);
+// x: zero-bordered NHWC bf16 [N][H+2][W+2][x_stride] (channels [x_off, x_off+cin_pad), cin_pad % 16 == 0, <= 160);
+// dw: fp32 [cout][cin][3][3] (the first cin of the cin_pad columns); workspace: adc_conv3x3_wgrad_tc_workspace_bytes().
+// Split (bf16x3) mode when gy_lo and x_lo are given: hi*hi + lo*hi + hi*lo accumulated in fp32.
+int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
+                         int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout,
+                         adc_stream_t stream) {
+    if (!gy || !x || !dw || !workspace || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || cin_pad < cin) {
+        adc::set_error("adc_conv3x3_wgrad_tc: bad argument");
+        return ADC_E_BADARG;
+    }
+    if ((gy_lo == nullptr) != (x_lo == nullptr)) {
+        adc::set_error("adc_conv3x3_wgrad_tc: gy_lo and x_lo must be given together (split mode)");
+        return ADC_E_BADARG;
+    }
+    if (cin_pad % 16 != 0 || cin_pad > 160 || cout > 128 || gy_stride % 8 != 0 || gy_off % 8 != 0 || x_stride % 8 != 0 || x_off % 8 != 0 ||
+        gy_off + cout > gy_stride || x_off + cin_pad > x_stride) {
+        adc::set_error("adc_conv3x3_wgrad_tc: needs cin_pad %% 16 == 0, cin_pad <= 160, cout <= 128 and 16-byte aligned channel slices "
+                       "(cin_pad=%d cout=%d)", cin_pad, cout);
+        return ADC_E_UNSUPP;
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        adc::set_error("cuTensorMapEncodeTiled entry point not available");
+        return ADC_E_UNSUPP;
+    }
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.Wp = W + 2;
+    p.F = (long long)N * (H + 2) * (W + 2);
+    p.ncols = cin_pad;
+    p.mrows = (cout + 15) / 16 * 16;
+    p.mb = cout > 64 ? 2 : 1;
+    p.nb = (cin_pad + 63) / 64;
+    p.split = gy_lo != nullptr;
+    p.groups = wgrad_groups();
+    p.part = reinterpret_cast<float*>(workspace);
+    const int budget = kSmemCap - 1024;
+    for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
+        p.bseg = ((p.kp + 2) * 128 + 1023) / 1024 * 1024;
+        const int stage = (p.mb * p.kp * 128 + p.nb * p.bseg) * (p.split ? 2 : 1);
+        p.nstages = budget / stage;
+        if (p.nstages > 8) p.nstages = 8;
+        if (p.nstages >= 3 || (p.kp == 64 && p.nstages >= 2)) break;
+    }
+    if (p.kp < 64 || p.nstages < 2) {
+        adc::set_error("adc_conv3x3_wgrad_tc: stage does not fit in shared memory (cin_pad=%d cout=%d)", cin_pad, cout);
+        return ADC_E_UNSUPP;
+    }
+    p.ktiles = (int)((p.F + p.kp - 1) / p.kp);
+    const int smem = p.nstages * (p.mb * p.kp * 128 + p.nb * p.bseg) * (p.split ? 2 : 1) + 1024 + 256;
+
+    auto make = [&](CUtensorMap* m, const void* base_, int stride, int off, int rows) -> int {
+        const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base_) + off;
+        cuuint64_t dims[2] = {(cuuint64_t)(stride - off), (cuuint64_t)p.F};
+        cuuint64_t strides[1] = {(cuuint64_t)stride * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)rows};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(b), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            adc::set_error("cuTensorMapEncodeTiled(wgrad) failed: %d", (int)r);
+            return ADC_E_UNSUPP;
+        }
+        return 0;
+    };
+    CUtensorMap mg, mx, mgl, mxl;
+    memset(&mgl, 0, sizeof(mgl));
+    memset(&mxl, 0, sizeof(mxl));
+    int rc;
+    if ((rc = make(&mg, gy, gy_stride, gy_off, p.kp)) || (rc = make(&mx, x, x_stride, x_off, p.kp + 2))) return rc;
+    if (p.split && ((rc = make(&mgl, gy_lo, gy_stride, gy_off, p.kp)) || (rc = make(&mxl, x_lo, x_stride, x_off, p.kp + 2)))) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap),
+                             "cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel)");
+        if (rc) return rc;
+        attr_done = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    conv3x3_wgrad_tc_kernel<<<3 * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
+    if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_tc_kernel launch"))) return rc;
+    const int total = 9 * cout * cin;
+    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin);
+    return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");
+}
+
+}  // extern "C"

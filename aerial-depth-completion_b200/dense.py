@@ -187,6 +187,19 @@ def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=No
     return out
 
 
+def conv3x3_wgrad_tc(gy, x, cin, cout, x_off=0, gy_off=0, cin_pad=None):
+    """Weight gradient [cout, cin, 3, 3] (fp32) of a 3x3 / stride-1 convolution from zero-bordered NHWC activations: ``x``
+    (channels [x_off, x_off+cin_pad)) and the output gradient ``gy`` (channels [gy_off, gy_off+cout), zero border)."""
+    from ._lib import lib, check
+    assert x.pad and gy.pad and (x.n, x.h, x.w) == (gy.n, gy.h, gy.w)
+    cin_pad = _r16(cin) if cin_pad is None else cin_pad
+    dw = torch.empty((cout, cin, 3, 3), device=x.hi.device, dtype=torch.float32)
+    ws = torch.empty(lib.adc_conv3x3_wgrad_tc_workspace_bytes(cin_pad, cout) // 4, device=x.hi.device, dtype=torch.float32)
+    check(lib.adc_conv3x3_wgrad_tc(gy.hi.data_ptr(), _ptr(gy.lo), gy.cs, gy_off, x.hi.data_ptr(), _ptr(x.lo), x.cs, x_off,
+                                   dw.data_ptr(), ws.data_ptr(), x.n, x.h, x.w, cin, cin_pad, cout, _stream()), "adc_conv3x3_wgrad_tc")
+    return dw
+
+
 def cached_weights(conv, embed_1x1=False, cin_pad=None):
     """Prepared bf16 weights of a Conv2d, kept ON the module and re-prepared only when the Parameter changes (storage,
     in-place version counter) or the precision mode / channel padding does."""

@@ -170,6 +170,16 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
 int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
                          const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
                          int N, int H, int W, int cin, int cout, int act, adc_stream_t stream);
+/* Weight gradient of a 3x3 / stride-1 / pad-1 convolution (the autograd backward of nn.Conv2d as used in
+ * confidence_depth_framework.py:442-452,536-607): dw[co][ci][u][v] = sum over pixels of gy[.][co] * x[. + tap shift][ci].
+ * gy and x are zero-bordered NHWC bf16 tensors of the same spatial size (gy's border pixels must be zeros); x channels
+ * [x_off, x_off+cin_pad) are read (cin_pad % 16 == 0, <= 160), the first cin of them written to dw (fp32 [cout][cin][3][3]);
+ * cout <= 128.  A stride-2 layer passes gy zero-dilated to the input resolution.  gy_lo/x_lo non-NULL = bf16x3 split mode.
+ * workspace: adc_conv3x3_wgrad_tc_workspace_bytes(cin_pad, cout) bytes; the reduction order is fixed (deterministic). */
+size_t adc_conv3x3_wgrad_tc_workspace_bytes(int cin_pad, int cout);
+int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
+                         int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout,
+                         adc_stream_t stream);
 
 #ifdef __cplusplus
 }
