@@ -81,6 +81,10 @@ SIGNATURES = {
                                      c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_s1_tc_v2": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_int, _vp]),
+    "adc_conv3x3_dgrad_s2_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, _vp]),
+    "adc_conv3x3_wgrad_box_tc": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, _vp]),
     "adc_conv3x3_wgrad_tc_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_wgrad_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      _vp]),

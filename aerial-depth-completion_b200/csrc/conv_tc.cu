@@ -43,6 +43,13 @@ struct ConvParams {
     const float* bias;      // may be null
     int split;              // 1: every operand is a (hi, lo) pair of bf16 tensors and hi*hi + lo*hi + hi*lo is accumulated
     int x_pad, out_pad;     // 1: the tensor is stored with a one-pixel zero border ([H+2][W+2] per image)
+    // Tap list: input box offset (dy, dx) and weight tap index of every tap that is summed.  The plain convolution has nine
+    // (dy = u-1, dx = v-1, tap = 3u+v); the data gradient of a stride-2 convolution is four sub-convolutions, one per
+    // parity class of the input pixel, with 1/2/2/4 taps each.
+    int ntaps;
+    signed char tdy[9], tdx[9], ttap[9];
+    // output pixel of tile-space pixel (oh, ow): (oh*omul + oay, ow*omul + oax) in an image of OutH x OutW
+    int omul, oay, oax, OutH, OutW;
 };
 
 constexpr int kStages = 4;
@@ -70,7 +77,7 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
     const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
     const int ow0 = tx * p.BW, oh0 = ty * p.BH;
     const int kblocks = (p.cin + KBLK - 1) / KBLK;
-    const int ksteps = 9 * kblocks;
+    const int ksteps = p.ntaps * kblocks;
     uint32_t ncols = 32;
     while ((int)ncols < p.npad) ncols <<= 1;
 
@@ -96,14 +103,14 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int s = ks % kStages, use = ks / kStages;
                 mbar_wait(&bars[kStages + s], (use & 1) ^ 1);
-                const int kb = ks / 9, tap = ks % 9, u = tap / 3, v = tap % 3;
+                const int kb = ks / p.ntaps, t = ks % p.ntaps, tap = p.ttap[t];
+                const int ix = ow0 * p.stride + p.tdx[t] + p.x_pad, iy = oh0 * p.stride + p.tdy[t] + p.x_pad;
                 uint8_t* sa = smem + s * stage_bytes;
                 mbar_expect_tx(&bars[s], (uint32_t)((A_BYTES + b_bytes) * (p.split ? 2 : 1)));
-                tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ow0 * p.stride + v - 1 + p.x_pad, oh0 * p.stride + u - 1 + p.x_pad, n);
+                tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ix, iy, n);
                 tma_load_3d(sa + b_off, &map_w, &bars[s], kb * KBLK, 0, tap);
                 if (p.split) {
-                    tma_load_4d(sa + al_off, &map_xl, &bars[s], kb * KBLK, ow0 * p.stride + v - 1 + p.x_pad,
-                                oh0 * p.stride + u - 1 + p.x_pad, n);
+                    tma_load_4d(sa + al_off, &map_xl, &bars[s], kb * KBLK, ix, iy, n);
                     tma_load_3d(sa + bl_off, &map_wl, &bars[s], kb * KBLK, 0, tap);
                 }
             }
@@ -140,8 +147,9 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
         const bool valid = oh < p.Ho && ow < p.Wo;
         mbar_wait(&bars[2 * kStages], 0);
         tc_fence_after();
-        const long long pix = p.out_pad ? ((long long)n * (p.Ho + 2) + oh + 1) * (p.Wo + 2) + ow + 1
-                                        : ((long long)n * p.Ho + oh) * p.Wo + ow;
+        const int qh = oh * p.omul + p.oay, qw = ow * p.omul + p.oax;
+        const long long pix = p.out_pad ? ((long long)n * (p.OutH + 2) + qh + 1) * (p.OutW + 2) + qw + 1
+                                        : ((long long)n * p.OutH + qh) * p.OutW + qw;
         for (int c0 = 0; c0 < p.npad; c0 += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
@@ -507,8 +515,9 @@ __global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
         float v = 0.f;
         if (!flip_transpose) {
             if (co < cout && ci < cin) v = w[((long long)co * cin + ci) * 9 + tap];
-        } else {   // data-gradient weights: out "channel" = original ci, in "channel" = original co, taps flipped
-            if (co < cin && ci < cout) v = w[((long long)ci * cin + co) * 9 + (8 - tap)];
+        } else {   // data-gradient weights: out "channel" = original ci, in "channel" = original co; taps flipped (mode 1:
+                   // stride-1 data gradient = a convolution of gy) or kept (mode 2: per-tap sums of the stride-2 data gradient)
+            if (co < cin && ci < cout) v = w[((long long)ci * cin + co) * 9 + (flip_transpose == 1 ? 8 - tap : tap)];
         }
         const __nv_bfloat16 hi = __float2bfloat16(v);
         out[i] = hi;
@@ -589,24 +598,21 @@ int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int c
     return adc::check_cuda(cudaGetLastError(), "prep_conv_weights_kernel launch");
 }
 
-// x: NHWC bf16 [N,H,W,x_stride] (channels [x_off, x_off+cin) are read, cin % 16 == 0); w: prepared bf16 [9][npad][cin];
-// out: NHWC, out_f32 ? fp32 : bf16, channel slice [out_off, out_off+cout) of a tensor with out_stride channels per pixel.
-// Split (bf16x3) mode when x_lo and w_lo are given: every operand is hi + lo with hi = bf16(v), lo = bf16(v - hi) and the
-// kernel accumulates hi*hi + lo*hi + hi*lo in fp32 (relative error ~1e-5: fp32-grade parity on the tensor cores); a bf16
-// output is then written as the pair (out, out_lo).
-int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
-                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
-                         int W, int cin, int cout, int stride, int act, int x_pad, int out_pad, adc_stream_t stream) {
-    if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || (stride != 1 && stride != 2)) {
-        adc::set_error("adc_conv3x3_fprop_tc: bad argument");
-        return ADC_E_BADARG;
-    }
-    if ((x_lo == nullptr) != (w_lo == nullptr)) {
-        adc::set_error("adc_conv3x3_fprop_tc: x_lo and w_lo must be given together (split mode)");
-        return ADC_E_BADARG;
-    }
-    if (cin % 16 != 0 || x_stride % 8 != 0 || x_off % 8 != 0 || cout > 256) {
-        adc::set_error("adc_conv3x3_fprop_tc: needs cin %% 16 == 0, 16-byte aligned channel slices and cout <= 256 (cin=%d cout=%d)", cin, cout);
+// One launch of the v1 kernel: a sum over a tap list of [128 pixels x Cin] x [Cin x Cout] products (see ConvParams).
+struct V1Launch {
+    const void *x, *x_lo; int x_stride, x_off;
+    const void *w, *w_lo; const float* bias;
+    void *out, *out_lo; int out_f32, out_stride, out_off;
+    int N, H, W;                 // stored input image (without border)
+    int cin, cout, stride, act, x_pad, out_pad;
+    int Ho, Wo;                  // tile-space output extent
+    int ntaps; signed char tdy[9], tdx[9], ttap[9];
+    int omul, oay, oax, OutH, OutW;
+};
+
+static int conv_v1(const V1Launch& d, const char* who, cudaStream_t st) {
+    if (d.cin % 16 != 0 || d.x_stride % 8 != 0 || d.x_off % 8 != 0 || d.cout > 256) {
+        adc::set_error("%s: needs cin %% 16 == 0, 16-byte aligned channel slices and cout <= 256 (cin=%d cout=%d)", who, d.cin, d.cout);
         return ADC_E_UNSUPP;
     }
     EncodeTiledFn enc = get_encode();
@@ -614,31 +620,35 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
         adc::set_error("cuTensorMapEncodeTiled entry point not available");
         return ADC_E_UNSUPP;
     }
-    const int split = x_lo != nullptr;
-    const int npad = (cout + 15) / 16 * 16;
+    const int split = d.x_lo != nullptr;
+    const int npad = (d.cout + 15) / 16 * 16;
+    const int cin = d.cin, stride = d.stride;
     const int kblk = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : (cin >= 64 ? 64 : 16));
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    p.N = N; p.H = H; p.W = W;
-    p.Ho = (H + 2 - 3) / stride + 1; p.Wo = (W + 2 - 3) / stride + 1;
-    p.cin = cin; p.npad = npad; p.cout = cout; p.stride = stride;
+    p.N = d.N; p.H = d.H; p.W = d.W;
+    p.Ho = d.Ho; p.Wo = d.Wo;
+    p.cin = cin; p.npad = npad; p.cout = d.cout; p.stride = stride;
     p.BW = p.Wo >= 24 ? 32 : (p.Wo >= 12 ? 16 : 8);
     p.BH = 128 / p.BW;
     p.tiles_x = (p.Wo + p.BW - 1) / p.BW; p.tiles_y = (p.Ho + p.BH - 1) / p.BH;
-    p.act = act; p.out_f32 = out_f32; p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.bias = bias;
-    p.out_lo = out_f32 ? nullptr : out_lo;
+    p.act = d.act; p.out_f32 = d.out_f32; p.out_pix_stride = d.out_stride; p.out_ch_off = d.out_off; p.out = d.out; p.bias = d.bias;
+    p.out_lo = d.out_f32 ? nullptr : d.out_lo;
     p.split = split;
-    p.x_pad = x_pad ? 1 : 0;
-    p.out_pad = out_pad ? 1 : 0;
-    const int Wt = W + 2 * p.x_pad, Ht = H + 2 * p.x_pad;    // stored extent of the input
+    p.x_pad = d.x_pad ? 1 : 0;
+    p.out_pad = d.out_pad ? 1 : 0;
+    p.ntaps = d.ntaps;
+    memcpy(p.tdy, d.tdy, 9); memcpy(p.tdx, d.tdx, 9); memcpy(p.ttap, d.ttap, 9);
+    p.omul = d.omul; p.oay = d.oay; p.oax = d.oax; p.OutH = d.OutH; p.OutW = d.OutW;
+    const int Wt = d.W + 2 * p.x_pad, Ht = d.H + 2 * p.x_pad;    // stored extent of the input
 
     CUtensorMap mx, mw, mxl, mwl;
     memset(&mxl, 0, sizeof(mxl));
     memset(&mwl, 0, sizeof(mwl));
     auto make_x = [&](CUtensorMap* m, const void* base) -> int {
-        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(base) + x_off;
-        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)x_stride * 2, (cuuint64_t)x_stride * 2 * Wt, (cuuint64_t)x_stride * 2 * Wt * Ht};
+        const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(base) + d.x_off;
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)d.N};
+        cuuint64_t strides[3] = {(cuuint64_t)d.x_stride * 2, (cuuint64_t)d.x_stride * 2 * Wt, (cuuint64_t)d.x_stride * 2 * Wt * Ht};
         cuuint32_t box[4] = {(cuuint32_t)kblk, (cuuint32_t)(p.BW * stride), (cuuint32_t)(p.BH * stride), 1};
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(xb), dims, strides, box, estr,
@@ -663,16 +673,87 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
         return 0;
     };
     int rc;
-    if ((rc = make_x(&mx, x)) || (rc = make_w(&mw, w))) return rc;
-    if (split && ((rc = make_x(&mxl, x_lo)) || (rc = make_w(&mwl, w_lo)))) return rc;
+    if ((rc = make_x(&mx, d.x)) || (rc = make_w(&mw, d.w))) return rc;
+    if (split && ((rc = make_x(&mxl, d.x_lo)) || (rc = make_w(&mwl, d.w_lo)))) return rc;
     const int rowb = kblk * 2;
     const int al_off = (128 * rowb + npad * rowb + 1023) & ~1023;
     const int stage_bytes = split ? 2 * al_off : al_off;
     const int smem = kStages * stage_bytes + 1024 + 256;
-    cudaStream_t st = (cudaStream_t)stream;
     if (kblk == 64) return launch<64>(mx, mw, mxl, mwl, p, smem, st);
     if (kblk == 32) return launch<32>(mx, mw, mxl, mwl, p, smem, st);
     return launch<16>(mx, mw, mxl, mwl, p, smem, st);
+}
+
+// x: NHWC bf16 [N,H,W,x_stride] (channels [x_off, x_off+cin) are read, cin % 16 == 0); w: prepared bf16 [9][npad][cin];
+// out: NHWC, out_f32 ? fp32 : bf16, channel slice [out_off, out_off+cout) of a tensor with out_stride channels per pixel.
+// Split (bf16x3) mode when x_lo and w_lo are given: every operand is hi + lo with hi = bf16(v), lo = bf16(v - hi) and the
+// kernel accumulates hi*hi + lo*hi + hi*lo in fp32 (relative error ~1e-5: fp32-grade parity on the tensor cores); a bf16
+// output is then written as the pair (out, out_lo).
+int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
+                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int N, int H,
+                         int W, int cin, int cout, int stride, int act, int x_pad, int out_pad, adc_stream_t stream) {
+    if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || (stride != 1 && stride != 2)) {
+        adc::set_error("adc_conv3x3_fprop_tc: bad argument");
+        return ADC_E_BADARG;
+    }
+    if ((x_lo == nullptr) != (w_lo == nullptr)) {
+        adc::set_error("adc_conv3x3_fprop_tc: x_lo and w_lo must be given together (split mode)");
+        return ADC_E_BADARG;
+    }
+    V1Launch d;
+    memset(&d, 0, sizeof(d));
+    d.x = x; d.x_lo = x_lo; d.x_stride = x_stride; d.x_off = x_off; d.w = w; d.w_lo = w_lo; d.bias = bias;
+    d.out = out; d.out_lo = out_lo; d.out_f32 = out_f32; d.out_stride = out_stride; d.out_off = out_off;
+    d.N = N; d.H = H; d.W = W; d.cin = cin; d.cout = cout; d.stride = stride; d.act = act; d.x_pad = x_pad; d.out_pad = out_pad;
+    d.Ho = (H + 2 - 3) / stride + 1; d.Wo = (W + 2 - 3) / stride + 1;
+    d.ntaps = 9;
+    for (int t = 0; t < 9; ++t) { d.tdy[t] = (signed char)(t / 3 - 1); d.tdx[t] = (signed char)(t % 3 - 1); d.ttap[t] = (signed char)t; }
+    d.omul = 1; d.oay = 0; d.oax = 0; d.OutH = d.Ho; d.OutW = d.Wo;
+    return conv_v1(d, "adc_conv3x3_fprop_tc", (cudaStream_t)stream);
+}
+
+// Data gradient of a 3x3 / stride-2 / pad-1 convolution (forward: x [H,W] -> y [Ho,Wo], Ho = (H-1)/2+1).
+//   gx[p][q][ci] = sum over (u,v) with p+1-u, q+1-v even of  W[co][ci][u][v] * gy[(p+1-u)/2][(q+1-v)/2][co]
+// Four launches of the v1 kernel, one per parity class (p%2, q%2): even rows see only u=1 (i = p/2), odd rows u=0 (i = (p+1)/2)
+// and u=2 (i = (p-1)/2); likewise for columns.  w: adc_conv3x3_prep_weights(..., flip_transpose=2) = [tap][Cin_fwd][Cout_fwd]
+// (transposed, taps NOT flipped).  gy: [N][Ho][Wo] (+border if gy_pad), channels [gy_off, gy_off+cgy) with cgy % 16 == 0;
+// gx: channels [gx_off, gx_off+cgx) of [N][H][W] (+border if gx_pad), bf16 (pair in split mode) or fp32.
+int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* w, const void* w_lo, void* gx,
+                            void* gx_lo, int gx_f32, int gx_stride, int gx_off, int N, int H, int W, int cgy, int cgx, int gy_pad,
+                            int gx_pad, adc_stream_t stream) {
+    if (!gy || !w || !gx || N <= 0 || H <= 0 || W <= 0 || cgy <= 0 || cgx <= 0) {
+        adc::set_error("adc_conv3x3_dgrad_s2_tc: bad argument");
+        return ADC_E_BADARG;
+    }
+    if ((gy_lo == nullptr) != (w_lo == nullptr)) {
+        adc::set_error("adc_conv3x3_dgrad_s2_tc: gy_lo and w_lo must be given together (split mode)");
+        return ADC_E_BADARG;
+    }
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    for (int pa = 0; pa < 2; ++pa)
+        for (int pb = 0; pb < 2; ++pb) {
+            V1Launch d;
+            memset(&d, 0, sizeof(d));
+            d.x = gy; d.x_lo = gy_lo; d.x_stride = gy_stride; d.x_off = gy_off; d.w = w; d.w_lo = w_lo; d.bias = nullptr;
+            d.out = gx; d.out_lo = gx_lo; d.out_f32 = gx_f32; d.out_stride = gx_stride; d.out_off = gx_off;
+            d.N = N; d.H = Ho; d.W = Wo; d.cin = cgy; d.cout = cgx; d.stride = 1; d.act = 0; d.x_pad = gy_pad; d.out_pad = gx_pad;
+            d.Ho = (H - pa + 1) / 2; d.Wo = (W - pb + 1) / 2;      // pixels of this parity class
+            if (d.Ho <= 0 || d.Wo <= 0) continue;
+            const int nu = pa ? 2 : 1, nv = pb ? 2 : 1;
+            const int us[2] = {pa ? 0 : 1, 2}, dys[2] = {pa ? 1 : 0, 0};
+            const int vs[2] = {pb ? 0 : 1, 2}, dxs[2] = {pb ? 1 : 0, 0};
+            d.ntaps = 0;
+            for (int a = 0; a < nu; ++a)
+                for (int b = 0; b < nv; ++b) {
+                    d.tdy[d.ntaps] = (signed char)dys[a]; d.tdx[d.ntaps] = (signed char)dxs[b];
+                    d.ttap[d.ntaps] = (signed char)(us[a] * 3 + vs[b]);
+                    ++d.ntaps;
+                }
+            d.omul = 2; d.oay = pa; d.oax = pb; d.OutH = H; d.OutW = W;
+            int rc = conv_v1(d, "adc_conv3x3_dgrad_s2_tc", (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+    return 0;
 }
 
 

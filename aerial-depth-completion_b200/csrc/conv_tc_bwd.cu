@@ -145,6 +145,122 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, ncols_alloc);
 }
 
+// Box variant for strided layers (GED conv1-5, stride 2): the flat-index trick needs equal geometry of gy and x, so here a K
+// tile is a BH x BW block of OUTPUT pixels of one image; gy comes as a 4-D TMA box and the x operand of tap (u,v) as a 4-D box
+// with element strides (stride, stride) starting at (ow0*stride + v - 1, oh0*stride + u - 1) -- out-of-bounds zero fill is
+// the padding.  One tap per CTA (CTA = (group, tap), grid 9 x SMs/9), one accumulator of Cin columns; same MN-major
+// descriptors, same partial layout and reduction as the flat kernel.
+struct WgradBoxParams {
+    int N, tiles_x, tiles_y, BW, BH;
+    int stride, gy_pad, x_pad;
+    int ncols, mrows, mb, nb, kp, ktiles, groups, nstages, split;
+    float* part;
+};
+
+__global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_constant__ CUtensorMap map_g,
+                                                                   const __grid_constant__ CUtensorMap map_x,
+                                                                   const __grid_constant__ CUtensorMap map_gl,
+                                                                   const __grid_constant__ CUtensorMap map_xl, WgradBoxParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int blk = p.kp * 128;                                   // one 64-channel block of KP pixels
+    const int a_bytes = p.mb * blk, b_bytes = p.nb * blk;
+    const int half = a_bytes + b_bytes;
+    const int stage_bytes = p.split ? 2 * half : half;
+    const int nst = p.nstages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);    // full[8], empty[8], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.x % 9, g = blockIdx.x / 9;
+    const int u = tap / 3, v = tap % 3;
+    const int my_tiles = g < p.ktiles ? (p.ktiles - g + p.groups - 1) / p.groups : 0;
+    uint32_t ncols_alloc = 32;
+    while ((int)ncols_alloc < p.ncols) ncols_alloc <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(&bars[s], 1);
+            mbar_init(&bars[8 + s], 1);
+        }
+        mbar_init(&bars[16], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, ncols_alloc);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)(half * (p.split ? 2 : 1));
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % nst, use = i / nst;
+                const int t = g + i * p.groups;
+                const int bx = t % p.tiles_x, by = (t / p.tiles_x) % p.tiles_y, n = t / (p.tiles_x * p.tiles_y);
+                const int ow0 = bx * p.BW, oh0 = by * p.BH;
+                const int gx0 = ow0 + p.gy_pad, gy0 = oh0 + p.gy_pad;
+                const int xx0 = ow0 * p.stride + v - 1 + p.x_pad, xy0 = oh0 * p.stride + u - 1 + p.x_pad;
+                mbar_wait(&bars[8 + s], (use & 1) ^ 1);
+                uint8_t* sa = smem + s * stage_bytes;
+                mbar_expect_tx(&bars[s], tx);
+                for (int b = 0; b < p.mb; ++b) tma_load_4d(sa + b * blk, &map_g, &bars[s], b * 64, gx0, gy0, n);
+                for (int b = 0; b < p.nb; ++b) tma_load_4d(sa + a_bytes + b * blk, &map_x, &bars[s], b * 64, xx0, xy0, n);
+                if (p.split) {
+                    for (int b = 0; b < p.mb; ++b) tma_load_4d(sa + half + b * blk, &map_gl, &bars[s], b * 64, gx0, gy0, n);
+                    for (int b = 0; b < p.nb; ++b) tma_load_4d(sa + half + a_bytes + b * blk, &map_xl, &bars[s], b * 64, xx0, xy0, n);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_mn(128, p.ncols);
+            const uint32_t lbo_a = p.mb > 1 ? (uint32_t)blk : 0u, lbo_b = (uint32_t)blk;
+            const int ksteps = p.kp / 16;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % nst, use = i / nst;
+                mbar_wait(&bars[s], use & 1);
+                tc_fence_after();
+                const uint32_t sa = base + s * stage_bytes, sb = sa + a_bytes;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint64_t da = make_desc_mn(sa + k * 2048, lbo_a), db = make_desc_mn(sb + k * 2048, lbo_b);
+                    umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
+                    if (p.split) {
+                        umma_bf16(tmem_base, make_desc_mn(sa + half + k * 2048, lbo_a), db, idesc, 1);
+                        umma_bf16(tmem_base, da, make_desc_mn(sb + half + k * 2048, lbo_b), idesc, 1);
+                    }
+                }
+                umma_commit(&bars[8 + s]);
+            }
+            umma_commit(&bars[16]);
+        }
+    } else {
+        const int quarter = warp & 3, row = quarter * 32 + lane;
+        if (my_tiles > 0) {
+            mbar_wait(&bars[16], 0);
+            tc_fence_after();
+        }
+        float* dst = p.part + (((long long)g * 9 + tap) * p.mrows + row) * p.ncols;
+        for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+            float r[16];
+            if (my_tiles > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0.f;
+            }
+            if (row < p.mrows) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, ncols_alloc);
+}
+
 // dW[co][ci][tap] = sum_g part[g][tap][co][ci]   (fixed order; reads coalesced along ci)
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int groups, int mrows,
                                                               int ncols, int cout, int cin) {
@@ -157,16 +273,18 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
     }
 }
 
-static int wgrad_groups() {
-    static int groups = 0;
-    if (!groups) {
-        int dev = 0, sms = 0;
+static int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        groups = sms / 3 > 0 ? sms / 3 : 1;
+        if (sms <= 0) sms = 1;
     }
-    return groups;
+    return sms;
 }
+static int wgrad_groups() { return sm_count() / 3 > 0 ? sm_count() / 3 : 1; }        // flat kernel: CTA = (group, u)
+static int wgrad_box_groups() { return sm_count() / 9 > 0 ? sm_count() / 9 : 1; }    // box kernel: CTA = (group, tap)
 
 }  // namespace tc
 
@@ -263,6 +381,96 @@ int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int g
     cudaStream_t st = (cudaStream_t)stream;
     conv3x3_wgrad_tc_kernel<<<3 * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
     if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_tc_kernel launch"))) return rc;
+    const int total = 9 * cout * cin;
+    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin);
+    return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");
+}
+
+// Strided / general-geometry variant (see conv3x3_wgrad_box_tc_kernel): gy [N][Ho][Wo] (+border if gy_pad), x [N][H][W]
+// (+border if x_pad), Ho = (H-1)/stride + 1.  Same channel-slice, split-mode, workspace and determinism rules as above.
+int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, int gy_pad, const void* x, const void* x_lo,
+                             int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
+                             int cin_pad, int cout, adc_stream_t stream) {
+    if (!gy || !x || !dw || !workspace || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || cin_pad < cin || (stride != 1 && stride != 2)) {
+        adc::set_error("adc_conv3x3_wgrad_box_tc: bad argument");
+        return ADC_E_BADARG;
+    }
+    if ((gy_lo == nullptr) != (x_lo == nullptr)) {
+        adc::set_error("adc_conv3x3_wgrad_box_tc: gy_lo and x_lo must be given together (split mode)");
+        return ADC_E_BADARG;
+    }
+    if (cin_pad % 16 != 0 || cin_pad > 256 || cout > 128 || gy_stride % 8 != 0 || gy_off % 8 != 0 || x_stride % 8 != 0 || x_off % 8 != 0 ||
+        gy_off + cout > gy_stride || x_off + cin_pad > x_stride) {
+        adc::set_error("adc_conv3x3_wgrad_box_tc: needs cin_pad %% 16 == 0, cin_pad <= 256, cout <= 128 and 16-byte aligned channel slices "
+                       "(cin_pad=%d cout=%d)", cin_pad, cout);
+        return ADC_E_UNSUPP;
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        adc::set_error("cuTensorMapEncodeTiled entry point not available");
+        return ADC_E_UNSUPP;
+    }
+    const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    WgradBoxParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.stride = stride; p.gy_pad = gy_pad ? 1 : 0; p.x_pad = x_pad ? 1 : 0;
+    p.ncols = cin_pad;
+    p.mrows = (cout + 15) / 16 * 16;
+    p.mb = cout > 64 ? 2 : 1;
+    p.nb = (cin_pad + 63) / 64;
+    p.split = gy_lo != nullptr;
+    p.groups = wgrad_box_groups();
+    p.part = reinterpret_cast<float*>(workspace);
+    const int budget = kSmemCap - 1024;
+    for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
+        const int stage = (p.mb + p.nb) * p.kp * 128 * (p.split ? 2 : 1);
+        p.nstages = budget / stage;
+        if (p.nstages > 8) p.nstages = 8;
+        if (p.nstages >= 3 || (p.kp == 64 && p.nstages >= 2)) break;
+    }
+    if (p.kp < 64 || p.nstages < 2) {
+        adc::set_error("adc_conv3x3_wgrad_box_tc: stage does not fit in shared memory (cin_pad=%d cout=%d)", cin_pad, cout);
+        return ADC_E_UNSUPP;
+    }
+    p.BW = Wo >= 24 ? 32 : (Wo >= 12 ? 16 : 8);
+    p.BH = p.kp / p.BW;
+    p.tiles_x = (Wo + p.BW - 1) / p.BW; p.tiles_y = (Ho + p.BH - 1) / p.BH;
+    p.ktiles = p.tiles_x * p.tiles_y * N;
+    const int smem = p.nstages * (p.mb + p.nb) * p.kp * 128 * (p.split ? 2 : 1) + 1024 + 256;
+
+    auto make = [&](CUtensorMap* m, const void* base_, int cstride, int off, int h, int w, int pad, int st) -> int {
+        const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base_) + off;
+        const int Wt = w + 2 * pad, Ht = h + 2 * pad;
+        cuuint64_t dims[4] = {(cuuint64_t)(cstride - off), (cuuint64_t)Wt, (cuuint64_t)Ht, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)cstride * 2, (cuuint64_t)cstride * 2 * Wt, (cuuint64_t)cstride * 2 * Wt * Ht};
+        cuuint32_t box[4] = {64, (cuuint32_t)(p.BW * st), (cuuint32_t)(p.BH * st), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)st, (cuuint32_t)st, 1};
+        CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(b), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            adc::set_error("cuTensorMapEncodeTiled(wgrad box) failed: %d", (int)r);
+            return ADC_E_UNSUPP;
+        }
+        return 0;
+    };
+    CUtensorMap mg, mx, mgl, mxl;
+    memset(&mgl, 0, sizeof(mgl));
+    memset(&mxl, 0, sizeof(mxl));
+    int rc;
+    if ((rc = make(&mg, gy, gy_stride, gy_off, Ho, Wo, p.gy_pad, 1)) || (rc = make(&mx, x, x_stride, x_off, H, W, p.x_pad, stride))) return rc;
+    if (p.split && ((rc = make(&mgl, gy_lo, gy_stride, gy_off, Ho, Wo, p.gy_pad, 1)) || (rc = make(&mxl, x_lo, x_stride, x_off, H, W, p.x_pad, stride))))
+        return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_wgrad_box_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap),
+                             "cudaFuncSetAttribute(conv3x3_wgrad_box_tc_kernel)");
+        if (rc) return rc;
+        attr_done = true;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    conv3x3_wgrad_box_tc_kernel<<<9 * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
+    if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_box_tc_kernel launch"))) return rc;
     const int total = 9 * cout * cin;
     wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin);
     return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");

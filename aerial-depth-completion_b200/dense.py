@@ -200,6 +200,32 @@ def conv3x3_wgrad_tc(gy, x, cin, cout, x_off=0, gy_off=0, cin_pad=None):
     return dw
 
 
+def conv3x3_wgrad_box_tc(gy, x, cin, cout, stride, x_off=0, gy_off=0, cin_pad=None):
+    """Weight gradient of a 3x3 / pad-1 convolution of any stride (1 or 2) from NHWC activations with or without border."""
+    from ._lib import lib, check
+    assert x.n == gy.n and gy.h == (x.h - 1) // stride + 1 and gy.w == (x.w - 1) // stride + 1
+    cin_pad = _r16(cin) if cin_pad is None else cin_pad
+    dw = torch.empty((cout, cin, 3, 3), device=x.hi.device, dtype=torch.float32)
+    ws = torch.empty(lib.adc_conv3x3_wgrad_tc_workspace_bytes(cin_pad, cout) // 4, device=x.hi.device, dtype=torch.float32)
+    check(lib.adc_conv3x3_wgrad_box_tc(gy.hi.data_ptr(), _ptr(gy.lo), gy.cs, gy_off, int(gy.pad), x.hi.data_ptr(), _ptr(x.lo), x.cs, x_off,
+                                       int(x.pad), dw.data_ptr(), ws.data_ptr(), x.n, x.h, x.w, stride, cin, cin_pad, cout, _stream()),
+          "adc_conv3x3_wgrad_box_tc")
+    return dw
+
+
+def conv3x3_dgrad_s2_tc(gy, cgy, w_prep, cgx, h, w, gy_off=0, out=None, out_off=0, out_f32=False, out_pad=True):
+    """Data gradient of a 3x3 / stride-2 / pad-1 convolution whose input was [n, h, w]: ``gy`` channels [gy_off, gy_off+cgy)
+    -> channels [out_off, out_off+cgx) of ``out``; ``w_prep`` = prep_conv3x3_weights(weight, flip_transpose=2, cin_pad=cgy)."""
+    from ._lib import lib, check
+    if out is None:
+        out = new_act(gy.n, h, w, _r16(cgx), gy.hi.device, pad=out_pad, zero=True, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    is_f32 = int(out.hi.dtype == torch.float32)
+    check(lib.adc_conv3x3_dgrad_s2_tc(gy.hi.data_ptr(), _ptr(gy.lo), gy.cs, gy_off, w_prep[0].data_ptr(), _ptr(w_prep[1]),
+                                      out.hi.data_ptr(), _ptr(out.lo), is_f32, out.cs, out_off, gy.n, h, w, cgy, cgx, int(gy.pad),
+                                      int(out.pad), _stream()), "adc_conv3x3_dgrad_s2_tc")
+    return out
+
+
 def cached_weights(conv, embed_1x1=False, cin_pad=None):
     """Prepared bf16 weights of a Conv2d, kept ON the module and re-prepared only when the Parameter changes (storage,
     in-place version counter) or the precision mode / channel padding does."""

@@ -156,7 +156,7 @@ int adc_nchw_to_nhwc_bf16(const float* src, void* dst, void* dst_lo /* NULL or t
 int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int C, int H, int W, int src_stride, int src_off,
                          int pad, adc_stream_t stream);
 /* weights fp32 [Cout,Cin,3,3] -> bf16 [9][round16(Cout)][cin_pad] (+ low halves), input channels zero padded to cin_pad
- * (a multiple of 16, >= Cin); flip_transpose=1 = data-gradient form */
+ * (a multiple of 16, >= Cin); flip_transpose=1 = data-gradient form (transposed, taps flipped), 2 = transposed only */
 size_t adc_conv3x3_weight_elems(int cout, int cin_pad);
 int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int cout, int cin, int cin_pad, int flip_transpose,
                              adc_stream_t stream);
@@ -170,6 +170,13 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
 int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
                          const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
                          int N, int H, int W, int cin, int cout, int act, adc_stream_t stream);
+/* Data gradient of a 3x3 / stride-2 / pad-1 convolution (backward of the encoder layers conv1-5 of GEDNet,
+ * confidence_depth_framework.py:442-446): four parity-class launches of the tcgen05 kernel.  gy: NHWC bf16 [N][Ho][Wo]
+ * (+ zero border if gy_pad), channels [gy_off, gy_off+cgy), cgy % 16 == 0; w from adc_conv3x3_prep_weights(flip_transpose=2);
+ * gx: channels [gx_off, gx_off+cgx) of NHWC [N][H][W] (+ border if gx_pad; the border is not written), bf16/pair or fp32. */
+int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* w, const void* w_lo, void* gx,
+                            void* gx_lo, int gx_f32, int gx_stride, int gx_off, int N, int H, int W, int cgy, int cgx, int gy_pad,
+                            int gx_pad, adc_stream_t stream);
 /* Weight gradient of a 3x3 / stride-1 / pad-1 convolution (the autograd backward of nn.Conv2d as used in
  * confidence_depth_framework.py:442-452,536-607): dw[co][ci][u][v] = sum over pixels of gy[.][co] * x[. + tap shift][ci].
  * gy and x are zero-bordered NHWC bf16 tensors of the same spatial size (gy's border pixels must be zeros); x channels
@@ -180,6 +187,11 @@ size_t adc_conv3x3_wgrad_tc_workspace_bytes(int cin_pad, int cout);
 int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
                          int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout,
                          adc_stream_t stream);
+/* General-geometry variant (stride 1 or 2; gy [N][Ho][Wo], x [N][H][W], each with or without the zero border): one tap per
+ * CTA, 4-D TMA boxes with element strides.  cin_pad <= 256.  Same workspace query. */
+int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, int gy_pad, const void* x, const void* x_lo,
+                             int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
+                             int cin_pad, int cout, adc_stream_t stream);
 
 #ifdef __cplusplus
 }
