@@ -85,6 +85,11 @@ SIGNATURES = {
                                         c_int, c_int, c_int, _vp]),
     "adc_conv3x3_wgrad_box_tc": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, _vp]),
+    "adc_nhwc_upsample_nearest": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_nhwc_grad_assemble": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int, c_int, ctypes.c_float,
+                                       _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_nhwc_colsum_workspace_bytes": (ctypes.c_size_t, [c_int]),
+    "adc_nhwc_colsum": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp]),
     "adc_conv3x3_wgrad_tc_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_wgrad_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      _vp]),

@@ -1,0 +1,241 @@
+// NHWC glue of the tensor-core training path (backward of GEDNet / GMSNet, confidence_depth_framework.py:464-518,630-669):
+// nearest up-sampling into a channel slice, the gradient "assemble" step (sum over the up-sampling children + skip gradient,
+// times the activation derivative), and per-channel sums (bias gradients).  Activations and gradients are zero-bordered NHWC
+// bf16 tensors [N][H+2][W+2][C], single (plain bf16 mode) or as a (hi, lo) pair whose sum carries 16 mantissa bits; all
+// arithmetic here is fp32 on hi + lo and results are re-split.  HBM-bound elementwise kernels, 16-byte accesses.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/adc_b200.h"
+
+namespace adc {
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+}  // namespace adc
+
+namespace glue {
+
+// ATen 'nearest' source index (same rule as adc_common.cuh NearestMap; restated here because that header owns the
+// constant-memory weight images of another translation unit)
+struct Near {
+    int in, out, mode;
+    float scale;
+    __host__ static Near make(int in, int out) {
+        Near m;
+        m.in = in; m.out = out;
+        m.mode = (in == out) ? 0 : (out == 2 * in ? 1 : 2);
+        m.scale = (float)in / (float)out;
+        return m;
+    }
+    __device__ __forceinline__ int operator()(int dst) const {
+        if (mode == 0) return dst;
+        if (mode == 1) return dst >> 1;
+        const int s = (int)floorf((float)dst * scale);
+        return s < in - 1 ? s : in - 1;
+    }
+};
+
+struct Slice {            // channel slice of a zero-bordered NHWC tensor
+    const __nv_bfloat16* hi;
+    const __nv_bfloat16* lo;   // may be null
+    int stride, off;
+};
+struct SliceW {
+    __nv_bfloat16* hi;
+    __nv_bfloat16* lo;
+    int stride, off;
+};
+
+__device__ __forceinline__ void load8(const Slice& s, long long pix, int c, float (&v)[8], bool accumulate) {
+    const uint4 h = *reinterpret_cast<const uint4*>(s.hi + pix * s.stride + s.off + c);
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&h);
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        t[2 * j] = __low2float(hh[j]);
+        t[2 * j + 1] = __high2float(hh[j]);
+    }
+    if (s.lo) {
+        const uint4 l = *reinterpret_cast<const uint4*>(s.lo + pix * s.stride + s.off + c);
+        const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            t[2 * j] += __low2float(ll[j]);
+            t[2 * j + 1] += __high2float(ll[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = accumulate ? v[j] + t[j] : t[j];
+}
+__device__ __forceinline__ void store8(const SliceW& s, long long pix, int c, const float (&v)[8]) {
+    uint4 h, l;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&h);
+    __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&l);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hh[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        ll[j] = __floats2bfloat162_rn(v[2 * j] - __low2float(hh[j]), v[2 * j + 1] - __high2float(hh[j]));
+    }
+    *reinterpret_cast<uint4*>(s.hi + pix * s.stride + s.off + c) = h;
+    if (s.lo) *reinterpret_cast<uint4*>(s.lo + pix * s.stride + s.off + c) = l;
+}
+
+// dst[n][yd][xd][c] = src[n][mh(yd)][mw(xd)][c]   (bit copy of hi and lo)
+__global__ void __launch_bounds__(256) nhwc_upsample_kernel(Slice src, SliceW dst, int N, int C8, int Hs, int Ws, int Hd, int Wd, Near mh,
+                                                            Near mw) {
+    const long long total = (long long)N * Hd * Wd * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        long long r = i / C8;
+        const int xd = (int)(r % Wd);
+        r /= Wd;
+        const int yd = (int)(r % Hd), n = (int)(r / Hd);
+        const long long sp = ((long long)n * (Hs + 2) + mh(yd) + 1) * (Ws + 2) + mw(xd) + 1;
+        const long long dp = ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1;
+        *reinterpret_cast<uint4*>(dst.hi + dp * dst.stride + dst.off + c) = *reinterpret_cast<const uint4*>(src.hi + sp * src.stride + src.off + c);
+        if (dst.lo) *reinterpret_cast<uint4*>(dst.lo + dp * dst.stride + dst.off + c) = *reinterpret_cast<const uint4*>(src.lo + sp * src.stride + src.off + c);
+    }
+}
+
+// out[n][y][x][c] = d(act)[n][y][x][c] * ( sum over the up-sampling children (yd,xd) of (y,x) of A[n][yd][xd][c]  +  B[n][y][x][c] )
+// d(act) = 1 where act > 0, else slope (ReLU: 0, LeakyReLU: 0.2); A lives at (Hd,Wd) >= (H,W) (identity map if equal), A/B/act
+// optional.  Fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) nhwc_grad_assemble_kernel(Slice A, int hasA, Slice B, int hasB, Slice act, int hasAct, float slope,
+                                                                 SliceW out, int N, int C8, int H, int W, int Hd, int Wd, Near mh, Near mw) {
+    const long long total = (long long)N * H * W * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        long long r = i / C8;
+        const int x = (int)(r % W);
+        r /= W;
+        const int y = (int)(r % H), n = (int)(r / H);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (hasA) {
+            // children of y: the yd with mh(yd) == y form a contiguous range around y*Hd/H
+            int y0 = (int)(((long long)y * Hd) / H) - 1, x0 = (int)(((long long)x * Wd) / W) - 1;
+            for (int yd = y0 < 0 ? 0 : y0; yd < Hd && yd <= y0 + 4; ++yd) {
+                if (mh(yd) != y) continue;
+                for (int xd = x0 < 0 ? 0 : x0; xd < Wd && xd <= x0 + 4; ++xd) {
+                    if (mw(xd) != x) continue;
+                    load8(A, ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1, c, v, true);
+                }
+            }
+        }
+        const long long p = ((long long)n * (H + 2) + y + 1) * (W + 2) + x + 1;
+        if (hasB) load8(B, p, c, v, true);
+        if (hasAct) {
+            const uint4 a = *reinterpret_cast<const uint4*>(act.hi + p * act.stride + act.off + c);
+            const __nv_bfloat162* aa = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[2 * j] *= __low2float(aa[j]) > 0.f ? 1.f : slope;
+                v[2 * j + 1] *= __high2float(aa[j]) > 0.f ? 1.f : slope;
+            }
+        }
+        store8(out, p, c, v);
+    }
+}
+
+// per-channel sums over all pixels (bias gradient): stage 1 = per-CTA partials [grid][C], stage 2 = fixed-order sum
+__global__ void __launch_bounds__(256) nhwc_colsum1_kernel(Slice g, long long F, int C8, float* __restrict__ part) {
+    __shared__ float red[256][8];
+    const int lanes = C8, groups = 256 / lanes;                // C8 <= 32
+    const int cl = threadIdx.x % lanes, pg = threadIdx.x / lanes;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (pg < groups)
+        for (long long p = (long long)blockIdx.x * groups + pg; p < F; p += (long long)gridDim.x * groups) load8(g, p, cl * 8, v, true);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = v[j];
+    __syncthreads();
+    if (threadIdx.x < lanes) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+        for (int q = 0; q < groups; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] += red[q * lanes + threadIdx.x][j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[(long long)blockIdx.x * C8 * 8 + threadIdx.x * 8 + j] = t[j];
+    }
+}
+__global__ void nhwc_colsum2_kernel(const float* __restrict__ part, int nparts, int Cp, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float t = 0.f;
+    for (int q = 0; q < nparts; ++q) t += part[(long long)q * Cp + c];
+    out[c] = t;
+}
+
+static int grid_for(long long total) {
+    long long b = (total + 255) / 256;
+    const long long cap = 148LL * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+static bool bad_slice(const void* hi, int stride, int off, int C) { return !hi || stride % 8 != 0 || off % 8 != 0 || C % 8 != 0 || off + C > stride; }
+
+}  // namespace glue
+
+using namespace glue;
+
+extern "C" {
+
+int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_stride, int src_off, void* dst, void* dst_lo, int dst_stride,
+                              int dst_off, int N, int C, int Hs, int Ws, int Hd, int Wd, adc_stream_t stream) {
+    if (bad_slice(src, src_stride, src_off, C) || bad_slice(dst, dst_stride, dst_off, C) || N <= 0 || Hs <= 0 || Ws <= 0 || Hd <= 0 || Wd <= 0 ||
+        ((src_lo == nullptr) != (dst_lo == nullptr))) {
+        adc::set_error("adc_nhwc_upsample_nearest: bad argument (channel slices must be multiples of 8 channels, 16-byte aligned)");
+        return ADC_E_BADARG;
+    }
+    Slice s{(const __nv_bfloat16*)src, (const __nv_bfloat16*)src_lo, src_stride, src_off};
+    SliceW d{(__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo, dst_stride, dst_off};
+    const long long total = (long long)N * Hd * Wd * (C / 8);
+    nhwc_upsample_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(s, d, N, C / 8, Hs, Ws, Hd, Wd, Near::make(Hs, Hd), Near::make(Ws, Wd));
+    return adc::check_cuda(cudaGetLastError(), "nhwc_upsample_kernel launch");
+}
+
+int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_off, int Hd, int Wd, const void* b, const void* b_lo,
+                           int b_stride, int b_off, const void* act, int act_stride, int act_off, float slope, void* out, void* out_lo,
+                           int out_stride, int out_off, int N, int C, int H, int W, adc_stream_t stream) {
+    if ((!a && !b) || bad_slice(out, out_stride, out_off, C) || (a && bad_slice(a, a_stride, a_off, C)) || (b && bad_slice(b, b_stride, b_off, C)) ||
+        (act && bad_slice(act, act_stride, act_off, C)) || N <= 0 || H <= 0 || W <= 0 || (a && (Hd < H || Wd < W))) {
+        adc::set_error("adc_nhwc_grad_assemble: bad argument");
+        return ADC_E_BADARG;
+    }
+    Slice A{(const __nv_bfloat16*)a, (const __nv_bfloat16*)a_lo, a_stride, a_off};
+    Slice B{(const __nv_bfloat16*)b, (const __nv_bfloat16*)b_lo, b_stride, b_off};
+    Slice T{(const __nv_bfloat16*)act, nullptr, act_stride, act_off};
+    SliceW O{(__nv_bfloat16*)out, (__nv_bfloat16*)out_lo, out_stride, out_off};
+    if (!a) { Hd = H; Wd = W; }
+    const long long total = (long long)N * H * W * (C / 8);
+    nhwc_grad_assemble_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(A, a != nullptr, B, b != nullptr, T, act != nullptr, slope, O, N,
+                                                                               C / 8, H, W, Hd, Wd, Near::make(H, Hd), Near::make(W, Wd));
+    return adc::check_cuda(cudaGetLastError(), "nhwc_grad_assemble_kernel launch");
+}
+
+size_t adc_nhwc_colsum_workspace_bytes(int C) { return (size_t)148 * 4 * ((C + 7) / 8 * 8) * sizeof(float); }
+
+int adc_nhwc_colsum(const void* g, const void* g_lo, int g_stride, int g_off, int N, int C, int H, int W, float* out, void* workspace,
+                    adc_stream_t stream) {
+    const int Cp = (C + 7) / 8 * 8;
+    if (!g || !out || !workspace || g_stride % 8 != 0 || g_off % 8 != 0 || g_off + Cp > g_stride || Cp > 256 || N <= 0 || H <= 0 || W <= 0) {
+        adc::set_error("adc_nhwc_colsum: bad argument");
+        return ADC_E_BADARG;
+    }
+    Slice G{(const __nv_bfloat16*)g, (const __nv_bfloat16*)g_lo, g_stride, g_off};
+    const long long F = (long long)N * (H + 2) * (W + 2);      // border pixels are zeros
+    const int nparts = 148 * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    nhwc_colsum1_kernel<<<nparts, 256, 0, st>>>(G, F, Cp / 8, reinterpret_cast<float*>(workspace));
+    int rc = adc::check_cuda(cudaGetLastError(), "nhwc_colsum1_kernel launch");
+    if (rc) return rc;
+    nhwc_colsum2_kernel<<<(C + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(workspace), nparts, Cp, C, out);
+    return adc::check_cuda(cudaGetLastError(), "nhwc_colsum2_kernel launch");
+}
+
+}  // extern "C"

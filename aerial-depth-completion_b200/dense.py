@@ -226,6 +226,39 @@ def conv3x3_dgrad_s2_tc(gy, cgy, w_prep, cgx, h, w, gy_off=0, out=None, out_off=
     return out
 
 
+def upsample_into(src, c, dst, dst_off, src_off=0):
+    """Nearest up-sampling of channels [src_off, src_off+c) of ``src`` into channels [dst_off, dst_off+c) of the (larger)
+    zero-bordered activation ``dst``: F.interpolate + torch.cat of the decoder in one pass."""
+    from ._lib import lib, check
+    assert src.pad and dst.pad and src.n == dst.n
+    check(lib.adc_nhwc_upsample_nearest(src.hi.data_ptr(), _ptr(src.lo), src.cs, src_off, dst.hi.data_ptr(), _ptr(dst.lo), dst.cs, dst_off,
+                                        src.n, c, src.h, src.w, dst.h, dst.w, _stream()), "adc_nhwc_upsample_nearest")
+    return dst
+
+
+def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None, act_off=0, slope=0.0):
+    """out[:, out_off:out_off+c] = d(act) * (sum over the up-sampling children of ``a`` + ``b``); see adc_nhwc_grad_assemble."""
+    from ._lib import lib, check
+    z = lambda t: (t.hi.data_ptr(), _ptr(t.lo), t.cs) if t is not None else (None, None, 0)
+    ah, al, ast = z(a)
+    bh, bl, bst = z(b)
+    check(lib.adc_nhwc_grad_assemble(ah, al, ast, a_off, a.h if a is not None else 0, a.w if a is not None else 0, bh, bl, bst, b_off,
+                                     act.hi.data_ptr() if act is not None else None, act.cs if act is not None else 0, act_off,
+                                     float(slope), out.hi.data_ptr(), _ptr(out.lo), out.cs, out_off, out.n, c, out.h, out.w, _stream()),
+          "adc_nhwc_grad_assemble")
+    return out
+
+
+def colsum(g, c, off=0):
+    """Per-channel sum over all pixels of channels [off, off+c) of a zero-bordered activation (fp32 [c]): the bias gradient."""
+    from ._lib import lib, check
+    out = torch.empty(c, device=g.hi.device, dtype=torch.float32)
+    ws = torch.empty(lib.adc_nhwc_colsum_workspace_bytes(c) // 4, device=g.hi.device, dtype=torch.float32)
+    check(lib.adc_nhwc_colsum(g.hi.data_ptr(), _ptr(g.lo), g.cs, off, g.n, c, g.h, g.w, out.data_ptr(), ws.data_ptr(), _stream()),
+          "adc_nhwc_colsum")
+    return out
+
+
 def cached_weights(conv, embed_1x1=False, cin_pad=None):
     """Prepared bf16 weights of a Conv2d, kept ON the module and re-prepared only when the Parameter changes (storage,
     in-place version counter) or the precision mode / channel padding does."""
@@ -242,6 +275,11 @@ def cached_weights(conv, embed_1x1=False, cin_pad=None):
     prep = prep_conv3x3_weights(wt, cin_pad=cin_pad)
     conv._adc_wprep = (tag, prep)
     return prep
+
+
+def tc_enabled():
+    """True in the tensor-core precision modes (training and inference paths of the nets that have one)."""
+    return PRECISION in ("bf16", "bf16x3")
 
 
 def tc_inference_enabled():

@@ -295,6 +295,15 @@ class GEDNet(nn.Module):
         x0_rgb = x0[:, :3, :, :]
         x0_d, c0 = _c0_of(x0)
         xout_d, cout_d = self.d_net(x0_d, c0)
+        if dense.tc_enabled():
+            # conv1..conv10 forward + backward on the hand-written tcgen05 kernels (one autograd node, NHWC bf16 / bf16x3)
+            from .. import tc_train
+            want = bool(build_conf_input) and self.out_channels == 1
+            x10, last_layer_input = tc_train.ged_dense(self, xout_d, cout_d, x0_rgb.contiguous(), x0_d.contiguous(), want)
+            features = None
+            if build_conf_input:
+                features = torch.cat((last_layer_input, xout_d, cout_d, x10), 1) if want else torch.sigmoid(x10[:, 1:2, :, :])
+            return x10[:, 0:1, :, :], features
         up = dense.upsample_nearest
         x1 = F.relu(self.conv1(torch.cat((xout_d, x0_rgb, cout_d), 1)))
         x2 = F.relu(self.conv2(x1))

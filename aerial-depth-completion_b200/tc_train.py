@@ -1,0 +1,190 @@
+"""Tensor-core training path of the dense layers of GEDNet (confidence_depth_framework.py:426-518): forward AND backward of
+conv1..conv10 on the hand-written tcgen05 kernels, one autograd node.
+
+Everything between the NConv pyramid and the loss lives in zero-bordered NHWC bf16 buffers (hi/lo pairs in the bf16x3 mode):
+
+* every encoder activation x_k is written by its convolution straight into the channel slice of the decoder's concat buffer
+  that will consume it (``cat9 = [up(x8) | x1]`` ...), the next encoder layer reads it from there: no torch.cat, no copies;
+* forward: stride-2 layers = box kernel (adc_conv3x3_fprop_tc), stride-1 layers = row-segment kernel (adc_conv3x3_s1_tc_v2),
+  ReLU / LeakyReLU(0.2) fused, nearest up-sampling = adc_nhwc_upsample_nearest into the slice;
+* backward: data gradients = the forward kernel on the output gradient with transposed+flipped weights (stride 1) or four
+  parity-class launches (stride 2, adc_conv3x3_dgrad_s2_tc); weight gradients = adc_conv3x3_wgrad_tc / _wgrad_box_tc straight
+  from the NHWC buffers (MN-major UMMA operands); up-sampling backward + skip-gradient add + activation derivative =
+  adc_nhwc_grad_assemble; bias gradients = adc_nhwc_colsum.
+
+Buffers are allocated once per (module, batch shape, precision) and zero-filled once: kernels write interiors (or interiors
+plus zero borders) only, so borders and pad channels stay zero for the lifetime of the plan, and a captured CUDA graph sees
+fixed addresses.  A second forward of the same module before the backward of the first would overwrite saved activations; the
+node checks for that and raises.
+"""
+import torch
+
+from . import dense
+
+_RELU, _LEAKY = 1, 2
+
+
+def _half(v):
+    return (v - 1) // 2 + 1
+
+
+class _Plan:
+    def __init__(self, n, h, w, out_ch, device):
+        self.n, self.h, self.w = n, h, w
+        hs, ws = [h], [w]
+        for _ in range(5):
+            hs.append(_half(hs[-1]))
+            ws.append(_half(ws[-1]))
+        self.hs, self.ws = hs, ws
+        A = lambda lvl, c, **kw: dense.new_act(n, hs[lvl], ws[lvl], c, device, pad=True, zero=True, **kw)
+        # forward
+        self.in0 = A(0, 16)            # [xout_d, r, g, b, cout_d, 0...]
+        self.cat10 = A(0, 64)          # [up(x9) 32 | x0_d 1 | 0...]
+        self.cat9 = A(1, 128)          # [up(x8) 32 | x1 80 | 0...]
+        self.cat8 = A(2, 192)          # [up(x7) 64 | x2 80 | 0...]
+        self.cat7 = A(3, 192)          # [up(x6) 64 | x3 80 | 0...]
+        self.cat6 = A(4, 192)          # [up(x5) 80 | x4 80 | 0...]
+        self.x5 = A(5, 128)
+        self.x6, self.x7, self.x8, self.x9 = A(4, 64), A(3, 64), A(2, 64), A(1, 64)
+        self.y10 = A(0, 16, dtype=torch.float32)
+        self.bwd = None
+        self.forward_id = 0
+
+    def backward_buffers(self):
+        if self.bwd is None:
+            n, hs, ws = self.n, self.hs, self.ws
+            dev = self.in0.hi.device
+            A = lambda lvl, c, **kw: dense.new_act(n, hs[lvl], ws[lvl], c, dev, pad=True, zero=True, **kw)
+            b = {}
+            b["G10"], b["gcat10"], b["glli"] = A(0, 64), A(0, 64), None
+            b["G9"], b["gcat9"] = A(1, 64), A(1, 128)
+            b["G8"], b["gcat8"] = A(2, 64), A(2, 192)
+            b["G7"], b["gcat7"] = A(3, 64), A(3, 192)
+            b["G6"], b["gcat6"] = A(4, 64), A(4, 192)
+            b["G5"] = A(5, 128)
+            for k, lvl in (("4", 4), ("3", 3), ("2", 2), ("1", 1)):
+                b["gx" + k], b["G" + k] = A(lvl, 128), A(lvl, 128)
+            b["gin0"] = A(0, 16, dtype=torch.float32)
+            self.bwd = b
+        return self.bwd
+
+
+def _plan(net, n, h, w, device):
+    plans = net.__dict__.setdefault("_tc_plans", {})
+    key = (n, h, w, dense.PRECISION, str(device))
+    if key not in plans:
+        plans[key] = _Plan(n, h, w, net.out_channels, device)
+    return plans[key]
+
+
+def _prep(weight, cin_pad, mode=0):
+    return dense.prep_conv3x3_weights(weight, flip_transpose=mode, cin_pad=cin_pad)
+
+
+def _dgrad_s1(G, weight, out, lo, hi):
+    """Channels [lo, hi) of the input gradient of a stride-1 layer with Parameter ``weight`` [Cout, Cin, 3, 3] from its output
+    gradient ``G`` (all of G's channels are contracted; pad channels are zeros)."""
+    step = 64 if dense._split() else 128
+    for a in range(lo, hi, step):
+        b = min(a + step, hi)
+        wp = _prep(weight[:, a:b], G.cs, 1)
+        dense.conv3x3_tc(G, G.cs, wp, None, b - a, 1, 0, out=out, out_off=a, out_zero_to=64 if a + 64 <= out.cs else 0)
+
+
+class GEDDenseTC(torch.autograd.Function):
+    """(xout_d, cout_d, rgb, x0_d) -> (x10, last_layer_input | None); parameters conv1..conv10 (weight, bias) as inputs."""
+
+    @staticmethod
+    def forward(ctx, xout_d, cout_d, rgb, x0_d, want_lli, net, *params):
+        n, _, h, w = xout_d.shape
+        P = _plan(net, n, h, w, xout_d.device)
+        W = params[0::2]
+        Bz = params[1::2]
+        c3 = dense.conv3x3_tc
+        dense.to_nhwc_bf16(torch.cat((xout_d, rgb, cout_d), 1), cpad=16, dst=P.in0, dst_off=0)
+        # encoder: 3x3 stride 2 + ReLU, each output lands in the concat buffer of the decoder layer that reuses it
+        c3(P.in0, 16, _prep(W[0], 16), Bz[0], 80, 2, _RELU, out=P.cat9, out_off=32)
+        c3(P.cat9, 80, _prep(W[1], 80), Bz[1], 80, 2, _RELU, x_off=32, out=P.cat8, out_off=64)
+        c3(P.cat8, 80, _prep(W[2], 80), Bz[2], 80, 2, _RELU, x_off=64, out=P.cat7, out_off=64)
+        c3(P.cat7, 80, _prep(W[3], 80), Bz[3], 80, 2, _RELU, x_off=64, out=P.cat6, out_off=80)
+        c3(P.cat6, 80, _prep(W[4], 80), Bz[4], 80, 2, _RELU, x_off=80, out=P.x5, out_off=0)
+        # decoder: nearest up-sampling into the slice, 3x3 stride 1 + LeakyReLU(0.2)
+        dense.upsample_into(P.x5, 80, P.cat6, 0)
+        c3(P.cat6, 192, _prep(W[5], 192), Bz[5], 64, 1, _LEAKY, out=P.x6, out_zero_to=64)
+        dense.upsample_into(P.x6, 64, P.cat7, 0)
+        c3(P.cat7, 192, _prep(W[6], 192), Bz[6], 64, 1, _LEAKY, out=P.x7, out_zero_to=64)
+        dense.upsample_into(P.x7, 64, P.cat8, 0)
+        c3(P.cat8, 192, _prep(W[7], 192), Bz[7], 32, 1, _LEAKY, out=P.x8, out_zero_to=64)
+        dense.upsample_into(P.x8, 32, P.cat9, 0)
+        c3(P.cat9, 128, _prep(W[8], 128), Bz[8], 32, 1, _LEAKY, out=P.x9, out_zero_to=64)
+        dense.upsample_into(P.x9, 32, P.cat10, 0)
+        dense.to_nhwc_bf16(x0_d, cpad=8, dst=P.cat10, dst_off=32)
+        oc = W[9].shape[0]
+        c3(P.cat10, 64, _prep(W[9], 64), Bz[9], oc, 1, _LEAKY, out=P.y10, out_f32=True)
+        x10 = dense.to_nchw_f32(P.y10, oc)
+        lli = dense.to_nchw_f32(P.cat10, 33) if want_lli else None
+        P.forward_id += 1
+        ctx.plan, ctx.fid, ctx.oc, ctx.want_lli = P, P.forward_id, oc, want_lli
+        ctx.save_for_backward(x10, *W)
+        return x10, lli
+
+    @staticmethod
+    def backward(ctx, g_x10, g_lli):
+        P = ctx.plan
+        if P.forward_id != ctx.fid:
+            raise RuntimeError("GEDDenseTC: the module ran another forward before this backward; its saved activations are gone")
+        x10 = ctx.saved_tensors[0]
+        W = ctx.saved_tensors[1:]
+        b = P.backward_buffers()
+        hs, ws, oc = P.hs, P.ws, ctx.oc
+        wg, wgb, asm, cs = dense.conv3x3_wgrad_tc, dense.conv3x3_wgrad_box_tc, dense.grad_assemble, dense.colsum
+        gW, gB = [None] * 10, [None] * 10
+        # conv10 (LeakyReLU on the output too, confidence_depth_framework.py:506)
+        g_pre = g_x10 * torch.where(x10 > 0, 1.0, 0.2)
+        dense.to_nhwc_bf16(g_pre.contiguous(), cpad=8, dst=b["G10"], dst_off=0)
+        gB[9] = cs(b["G10"], 8)[:oc]
+        gW[9] = wg(b["G10"], P.cat10, 33, oc, cin_pad=48)
+        # channel 32 of the last layer's input is x0_d itself: raw data for the depth-completion net, but the PREDICTED depth when
+        # this net is the loss net (confidence_depth_framework.py:230) -- then its gradient is needed too
+        need_x0d = ctx.needs_input_grad[3]
+        nch = 33 if need_x0d else 32
+        _dgrad_s1(b["G10"], W[9], b["gcat10"], 0, nch)
+        if g_lli is not None:
+            if b["glli"] is None:
+                b["glli"] = dense.new_act(P.n, hs[0], ws[0], 64, g_lli.device, pad=True, zero=True)
+            dense.to_nhwc_bf16(g_lli[:, :nch].contiguous(), cpad=40, dst=b["glli"], dst_off=0)
+            asm(b["gcat10"], 40, a=b["gcat10"], b=b["glli"])
+        g_x0d = dense.to_nchw_f32(b["gcat10"], 1, 32) if need_x0d else None
+        # decoder layers 9..6: G_k = leaky'(x_k) * sum_children(grad of up(x_k))
+        dec = ((8, "G9", "gcat10", P.x9, 32, P.cat9, 112, "gcat9"), (7, "G8", "gcat9", P.x8, 32, P.cat8, 144, "gcat8"),
+               (6, "G7", "gcat8", P.x7, 64, P.cat7, 144, "gcat7"), (5, "G6", "gcat7", P.x6, 64, P.cat6, 160, "gcat6"))
+        for i, gname, src, xk, co, catk, cin, gcat in dec:
+            G = asm(b[gname], co, a=b[src], act=xk, slope=0.2)
+            gB[i] = cs(G, co)
+            gW[i] = wg(G, catk, cin, co, cin_pad=cin)
+            _dgrad_s1(G, W[i], b[gcat], 0, cin)
+        # encoder layers 5..1 (stride 2, ReLU): G5 from the up-sampling children only, G4..G1 = relu' * (dgrad + skip gradient)
+        G = asm(b["G5"], 80, a=b["gcat6"], act=P.x5, slope=0.0)
+        enc = ((4, P.cat6, 80, 4, "gx4", "G4", "gcat6", 80), (3, P.cat7, 64, 3, "gx3", "G3", "gcat7", 64),
+               (2, P.cat8, 64, 2, "gx2", "G2", "gcat8", 64), (1, P.cat9, 32, 1, "gx1", "G1", "gcat9", 32))
+        for i, xin, xoff, lvl, gxn, gn, gcat, goff in enc:
+            gB[i] = cs(G, 80)
+            gW[i] = wgb(G, xin, 80, 80, 2, x_off=xoff, cin_pad=80)
+            dense.conv3x3_dgrad_s2_tc(G, 80, _prep(W[i], 80, 2), 80, hs[lvl], ws[lvl], out=b[gxn], out_off=0)
+            G = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0)
+        gB[0] = cs(G, 80)
+        gW[0] = wgb(G, P.in0, 5, 80, 2, cin_pad=16)
+        dense.conv3x3_dgrad_s2_tc(G, 80, _prep(W[0], 80, 2), 5, hs[0], ws[0], out=b["gin0"], out_off=0)
+        gin = dense.to_nchw_f32(b["gin0"], 5)
+        grads = []
+        for i in range(10):
+            grads += [gW[i], gB[i]]
+        return (gin[:, 0:1], gin[:, 4:5], None, g_x0d, None, None, *grads)
+
+
+def ged_dense(net, xout_d, cout_d, rgb, x0_d, want_lli):
+    params = []
+    for i in range(1, 11):
+        m = getattr(net, "conv%d" % i)
+        params += [m.weight, m.bias]
+    return GEDDenseTC.apply(xout_d, cout_d, rgb, x0_d, want_lli, net, *params)

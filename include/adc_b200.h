@@ -193,6 +193,22 @@ int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, i
                              int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
                              int cin_pad, int cout, adc_stream_t stream);
 
+/* ---- NHWC glue of the tensor-core training path (zero-bordered NHWC bf16 tensors, optional low halves) --------------------
+ * Channel slices [off, off+C) with C % 8 == 0 and 16-byte alignment.
+ * adc_nhwc_upsample_nearest: F.interpolate(mode='nearest') of a slice into a slice of a larger tensor (the decoder's
+ *   up-sample + torch.cat, confidence_depth_framework.py:488-504).
+ * adc_nhwc_grad_assemble: out = d(act) * ( sum over the up-sampling children of A (at Hd x Wd, identity if equal) + B ),
+ *   d(act) = 1 where act > 0 else slope: the backward of up-sample / cat / ReLU / LeakyReLU in one pass; a, b, act optional.
+ * adc_nhwc_colsum: per-channel sum over all pixels (bias gradient), deterministic two-stage reduction. */
+int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_stride, int src_off, void* dst, void* dst_lo, int dst_stride,
+                              int dst_off, int N, int C, int Hs, int Ws, int Hd, int Wd, adc_stream_t stream);
+int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_off, int Hd, int Wd, const void* b, const void* b_lo,
+                           int b_stride, int b_off, const void* act, int act_stride, int act_off, float slope, void* out, void* out_lo,
+                           int out_stride, int out_off, int N, int C, int H, int W, adc_stream_t stream);
+size_t adc_nhwc_colsum_workspace_bytes(int C);
+int adc_nhwc_colsum(const void* g, const void* g_lo, int g_stride, int g_off, int N, int C, int H, int W, float* out, void* workspace,
+                    adc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

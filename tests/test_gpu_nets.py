@@ -29,6 +29,32 @@ def build(cfg, state):
 @gpu
 @pytest.mark.parametrize("tag", NET_TAGS)
 def test_framework_vs_golden(tag):
+    _framework_vs_golden(tag)
+
+
+GED_TAGS = tuple(t for t in NET_TAGS if t.startswith("ged_"))
+
+
+@gpu
+@pytest.mark.parametrize("tag", GED_TAGS)
+def test_ged_tensor_core_path_vs_golden(tag):
+    """The same goldens with conv1..conv10 of every GEDNet (forward AND backward) on the hand-written tcgen05 kernels in the
+    bf16x3 mode (hi/lo split operands, fp32 accumulation): the strict fp32 bars must still hold."""
+    from aerial_depth_completion_b200 import dense, _lib
+    prev = dense.PRECISION
+    dense.set_precision("bf16x3")
+    n0 = _lib.lib.adc_launch_count()
+    try:
+        # gradient digests: 2.5x the fp32 path's bar.  The worst tensors are the NConv weights (two-element sums over all
+        # pixels with heavy cancellation: the reference's own fp32-vs-fp64 difference there is 4e-4..1.5e-3, SURVEY 8c) which
+        # amplify the ~1e-5 operand rounding of the split mode; measured worst 3.1e-3
+        _framework_vs_golden(tag, gtol_scale=2.5)
+    finally:
+        dense.set_precision(prev)
+    assert _lib.lib.adc_launch_count() > n0
+
+
+def _framework_vs_golden(tag, gtol_scale=1.0):
     G = gold("nets")
     cfg, state, inp, tgt = net_case(tag)
     f, m, params = build(cfg, state)
@@ -65,7 +91,7 @@ def test_framework_vs_golden(tag):
     gl = G[tag + "_loss"]
     assert abs(float(l) - gl[0]) <= 1e-4 * abs(gl[0])
     assert abs(loss.loss[0] - gl[1]) <= 1e-4 * abs(gl[1])
-    gtol = 5e-2 if bn_net else 2e-3      # the reference's own fp32-vs-fp64 grads differ by up to 5e-2 in the BN nets
+    gtol = (5e-2 if bn_net else 2e-3) * gtol_scale      # the reference's own fp32-vs-fp64 grads differ by up to 5e-2 in the BN nets
     n = 0
     for k, p in m.named_parameters():
         gk = tag + "_g_" + k
