@@ -90,6 +90,10 @@ SIGNATURES = {
                                        _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_nhwc_colsum_workspace_bytes": (ctypes.c_size_t, [c_int]),
     "adc_nhwc_colsum": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp]),
+    "adc_ged_head_fwd": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_ged_head_bwd_workspace_bytes": (ctypes.c_size_t, [c_int]),
+    "adc_ged_head_bwd": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp,
+                                 c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_wgrad_tc_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_wgrad_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      _vp]),

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "adc_common.cuh"
+#include "prof.h"
 #include "nconv_bwd.cuh"
 #include "nconv_fwd.cuh"
 #include "pool.cuh"
@@ -31,24 +32,29 @@ int check_cuda(cudaError_t e, const char* what) {
 // ---- instrumentation: launch counter (always on) and optional per-kernel CUDA-event timing -----------------------
 static long long g_launches = 0;
 struct ProfRec { cudaEvent_t a, b; int kind, call; double bytes; };
-static const int kProfMax = 512;
+static const int kProfMax = 1024;
 static ProfRec g_prof[kProfMax];
 static int g_prof_n = 0, g_prof_on = 0, g_prof_events = 0;
 
+int prof_begin(cudaStream_t st, int kind, int call, double work) {
+    g_launches++;
+    if (!g_prof_on || g_prof_n >= kProfMax) return -1;
+    if (g_prof_n >= g_prof_events) {
+        if (cudaEventCreate(&g_prof[g_prof_n].a) != cudaSuccess || cudaEventCreate(&g_prof[g_prof_n].b) != cudaSuccess) return -1;
+        g_prof_events = g_prof_n + 1;
+    }
+    const int idx = g_prof_n++;
+    g_prof[idx].kind = kind; g_prof[idx].call = call; g_prof[idx].bytes = work;
+    cudaEventRecord(g_prof[idx].a, st);
+    return idx;
+}
+void prof_end(cudaStream_t st, int idx) { if (idx >= 0) cudaEventRecord(g_prof[idx].b, st); }
+void count_launches(int n) { g_launches += n; }
+
 struct ProfScope {   // records an event pair around the launches made while it is alive
     cudaStream_t st; int idx;
-    ProfScope(cudaStream_t s, int kind, int call, double bytes) : st(s), idx(-1) {
-        g_launches++;
-        if (!g_prof_on || g_prof_n >= kProfMax) return;
-        if (g_prof_n >= g_prof_events) {
-            if (cudaEventCreate(&g_prof[g_prof_n].a) != cudaSuccess || cudaEventCreate(&g_prof[g_prof_n].b) != cudaSuccess) return;
-            g_prof_events = g_prof_n + 1;
-        }
-        idx = g_prof_n++;
-        g_prof[idx].kind = kind; g_prof[idx].call = call; g_prof[idx].bytes = bytes;
-        cudaEventRecord(g_prof[idx].a, st);
-    }
-    ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].b, st); }
+    ProfScope(cudaStream_t s, int kind, int call, double bytes) : st(s), idx(prof_begin(s, kind, call, bytes)) {}
+    ~ProfScope() { prof_end(st, idx); }
 };
 enum { KIND_FWD = 0, KIND_BWD_DATA = 1, KIND_BWD_WEIGHT = 2, KIND_POOL_FWD = 3, KIND_POOL_BWD = 4, KIND_UP_BWD = 5, KIND_HEAD_FWD = 6,
        KIND_HEAD_BWD = 7, KIND_PACK = 8, KIND_REDUCE = 9, KIND_PREP = 10 };

@@ -24,6 +24,7 @@
 #include "../../include/adc_b200.h"
 
 #include "tc_common.cuh"
+#include "prof.h"
 
 namespace tc {
 
@@ -541,6 +542,8 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMa
         adc::set_error("conv3x3_fprop_tc: %d bytes of shared memory needed (Cout too large for the split mode)", smem);
         return ADC_E_UNSUPP;
     }
+    adc::Prof prof(st, p.omul == 2 ? adc::KIND_TC_DGRAD_S2 : adc::KIND_TC_FPROP_V1,
+                   2.0 * p.N * p.Ho * p.Wo * p.ntaps * (double)p.cin * p.cout);
     conv3x3_fprop_tc_kernel<KBLK><<<p.tiles_x * p.tiles_y * p.N, 192, smem, st>>>(mx, mw, mxl, mwl, p);
     return adc::check_cuda(cudaGetLastError(), "conv3x3_fprop_tc_kernel launch");
 }
@@ -559,6 +562,7 @@ int adc_nchw_to_nhwc_bf16(const float* src, void* dst, void* dst_lo, int N, int 
     }
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 31) / 32), (Cpad + 31) / 32, N);
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_LAYOUT, (double)N * HW * (4.0 * C + (dst_lo ? 4.0 : 2.0) * Cpad));
     nchw_f32_to_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo, C, Cpad, HW,
                                                                          src_batch_stride, dst_stride, dst_off, W, pad);
     return adc::check_cuda(cudaGetLastError(), "nchw_f32_to_nhwc_bf16_kernel launch");
@@ -572,6 +576,7 @@ int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int
     }
     const long long HW = (long long)H * W;
     dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_LAYOUT, (double)N * HW * C * (4.0 + (src_is_f32 ? 4.0 : 2.0)));
     if (src_is_f32)
         nhwc_to_nchw_f32_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, dst, C, HW, src_stride, src_off, W, pad);
     else
@@ -593,6 +598,7 @@ int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int c
         return ADC_E_BADARG;
     }
     const int npad = (oc + 15) / 16 * 16;
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_PREP, 0.0);
     prep_conv_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out_lo, cout, cin, npad,
                                                                    cin_pad, flip_transpose);
     return adc::check_cuda(cudaGetLastError(), "prep_conv_weights_kernel launch");
@@ -888,6 +894,7 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
         done = true;
     }
     const int grid = p.ntiles < sms ? p.ntiles : sms;
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_FPROP_V2, 2.0 * N * H * W * 9.0 * cin * cout);
     conv3x3_s1_tc_v2_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mx, mw, mxl, mwl, mo, mol, p);
     return adc::check_cuda(cudaGetLastError(), "conv3x3_s1_tc_v2_kernel launch");
 }

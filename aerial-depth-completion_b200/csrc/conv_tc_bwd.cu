@@ -14,6 +14,7 @@
 // descriptors start 0,1,2 rows into it).  Partial sums go to a workspace [G][9][Cout16][Cin16] and a second kernel reduces
 // them in a fixed order (deterministic, no atomics) into the Parameter layout [Cout][Cin][3][3].
 #include "tc_common.cuh"
+#include "prof.h"
 
 namespace tc {
 
@@ -379,6 +380,8 @@ int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int g
         attr_done = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_TC_WGRAD, 2.0 * N * H * W * 9.0 * cin_pad * cout);
+    adc::count_launches(1);
     conv3x3_wgrad_tc_kernel<<<3 * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
     if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_tc_kernel launch"))) return rc;
     const int total = 9 * cout * cin;
@@ -469,6 +472,8 @@ int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, i
         attr_done = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_TC_WGRAD_BOX, 2.0 * N * Ho * Wo * 9.0 * cin_pad * cout);
+    adc::count_launches(1);
     conv3x3_wgrad_box_tc_kernel<<<9 * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
     if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_box_tc_kernel launch"))) return rc;
     const int total = 9 * cout * cin;

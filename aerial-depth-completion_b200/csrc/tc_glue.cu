@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include "../../include/adc_b200.h"
+#include "prof.h"
 
 namespace adc {
 void set_error(const char* fmt, ...);
@@ -195,6 +196,7 @@ int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_strid
     Slice s{(const __nv_bfloat16*)src, (const __nv_bfloat16*)src_lo, src_stride, src_off};
     SliceW d{(__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo, dst_stride, dst_off};
     const long long total = (long long)N * Hd * Wd * (C / 8);
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)total * 16.0 * (src_lo ? 4 : 2));
     nhwc_upsample_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(s, d, N, C / 8, Hs, Ws, Hd, Wd, Near::make(Hs, Hd), Near::make(Ws, Wd));
     return adc::check_cuda(cudaGetLastError(), "nhwc_upsample_kernel launch");
 }
@@ -213,6 +215,7 @@ int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_
     SliceW O{(__nv_bfloat16*)out, (__nv_bfloat16*)out_lo, out_stride, out_off};
     if (!a) { Hd = H; Wd = W; }
     const long long total = (long long)N * H * W * (C / 8);
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)total * 16.0 * (out_lo ? 2 : 1) * (1 + (a ? 1 : 0) + (b ? 1 : 0)));
     nhwc_grad_assemble_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(A, a != nullptr, B, b != nullptr, T, act != nullptr, slope, O, N,
                                                                                C / 8, H, W, Hd, Wd, Near::make(H, Hd), Near::make(W, Wd));
     return adc::check_cuda(cudaGetLastError(), "nhwc_grad_assemble_kernel launch");
@@ -231,6 +234,8 @@ int adc_nhwc_colsum(const void* g, const void* g_lo, int g_stride, int g_off, in
     const long long F = (long long)N * (H + 2) * (W + 2);      // border pixels are zeros
     const int nparts = 148 * 4;
     cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_TC_GLUE, (double)F * Cp * (g_lo ? 4.0 : 2.0));
+    adc::count_launches(1);
     nhwc_colsum1_kernel<<<nparts, 256, 0, st>>>(G, F, Cp / 8, reinterpret_cast<float*>(workspace));
     int rc = adc::check_cuda(cudaGetLastError(), "nhwc_colsum1_kernel launch");
     if (rc) return rc;

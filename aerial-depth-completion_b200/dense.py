@@ -259,6 +259,36 @@ def colsum(g, c, off=0):
     return out
 
 
+def ged_head_fwd(x9, x0d, weight, bias, h, w):
+    """conv10 of GEDNet + LeakyReLU(0.2) from x9 (zero-bordered NHWC activation, 32 channels, its own resolution) and x0_d
+    (NCHW fp32 [n,1,h,w]): [n, oc, h, w] fp32."""
+    from ._lib import lib, check
+    oc = weight.shape[0]
+    out = torch.empty((x9.n, oc, h, w), device=x0d.device, dtype=torch.float32)
+    check(lib.adc_ged_head_fwd(x9.hi.data_ptr(), _ptr(x9.lo), x9.cs, x9.h, x9.w, x0d.data_ptr(), weight.detach().contiguous().data_ptr(),
+                               bias.detach().contiguous().data_ptr(), out.data_ptr(), x9.n, oc, h, w, _stream()), "adc_ged_head_fwd")
+    return out
+
+
+def ged_head_bwd(x9, x0d, weight, gy, x10, glli, g9, need_x0d):
+    """Backward of ged_head_fwd: fills channels [0,32) of ``g9`` with the pre-activation gradient of conv9's output and returns
+    (gx0d | None, dweight, dbias)."""
+    from ._lib import lib, check
+    n, oc, h, w = gy.shape
+    dev = gy.device
+    dw = torch.empty_like(weight, dtype=torch.float32)
+    db = torch.empty(oc, device=dev, dtype=torch.float32)
+    gx0d = torch.empty((n, 1, h, w), device=dev, dtype=torch.float32) if need_x0d else None
+    ws = torch.empty(lib.adc_ged_head_bwd_workspace_bytes(oc) // 4, device=dev, dtype=torch.float32)
+    gy = gy.contiguous()
+    glli = glli.contiguous() if glli is not None else None
+    check(lib.adc_ged_head_bwd(x9.hi.data_ptr(), _ptr(x9.lo), x9.cs, x9.h, x9.w, x0d.data_ptr(), weight.detach().contiguous().data_ptr(),
+                               gy.data_ptr(), x10.data_ptr(), _ptr(glli), glli.shape[1] if glli is not None else 0, g9.hi.data_ptr(),
+                               _ptr(g9.lo), g9.cs, _ptr(gx0d), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n, oc, h, w, _stream()),
+          "adc_ged_head_bwd")
+    return gx0d, dw, db
+
+
 def cached_weights(conv, embed_1x1=False, cin_pad=None):
     """Prepared bf16 weights of a Conv2d, kept ON the module and re-prepared only when the Parameter changes (storage,
     in-place version counter) or the precision mode / channel padding does."""

@@ -39,14 +39,13 @@ class _Plan:
         A = lambda lvl, c, **kw: dense.new_act(n, hs[lvl], ws[lvl], c, device, pad=True, zero=True, **kw)
         # forward
         self.in0 = A(0, 16)            # [xout_d, r, g, b, cout_d, 0...]
-        self.cat10 = A(0, 64)          # [up(x9) 32 | x0_d 1 | 0...]
+        self.cat10 = None              # [up(x9) 32 | x0_d 1 | 0...]: only materialised when the confidence head wants it
         self.cat9 = A(1, 128)          # [up(x8) 32 | x1 80 | 0...]
         self.cat8 = A(2, 192)          # [up(x7) 64 | x2 80 | 0...]
         self.cat7 = A(3, 192)          # [up(x6) 64 | x3 80 | 0...]
         self.cat6 = A(4, 192)          # [up(x5) 80 | x4 80 | 0...]
         self.x5 = A(5, 128)
         self.x6, self.x7, self.x8, self.x9 = A(4, 64), A(3, 64), A(2, 64), A(1, 64)
-        self.y10 = A(0, 16, dtype=torch.float32)
         self.bwd = None
         self.forward_id = 0
 
@@ -56,7 +55,6 @@ class _Plan:
             dev = self.in0.hi.device
             A = lambda lvl, c, **kw: dense.new_act(n, hs[lvl], ws[lvl], c, dev, pad=True, zero=True, **kw)
             b = {}
-            b["G10"], b["gcat10"], b["glli"] = A(0, 64), A(0, 64), None
             b["G9"], b["gcat9"] = A(1, 64), A(1, 128)
             b["G8"], b["gcat8"] = A(2, 64), A(2, 192)
             b["G7"], b["gcat7"] = A(3, 64), A(3, 192)
@@ -117,15 +115,20 @@ class GEDDenseTC(torch.autograd.Function):
         c3(P.cat8, 192, _prep(W[7], 192), Bz[7], 32, 1, _LEAKY, out=P.x8, out_zero_to=64)
         dense.upsample_into(P.x8, 32, P.cat9, 0)
         c3(P.cat9, 128, _prep(W[8], 128), Bz[8], 32, 1, _LEAKY, out=P.x9, out_zero_to=64)
-        dense.upsample_into(P.x9, 32, P.cat10, 0)
-        dense.to_nhwc_bf16(x0_d, cpad=8, dst=P.cat10, dst_off=32)
+        # conv10 (33 -> 1 or 2 channels at full resolution): direct kernel, up-sampling folded into the addressing of x9
+        x0_d = x0_d.contiguous()
+        x10 = dense.ged_head_fwd(P.x9, x0_d, W[9], Bz[9], h, w)
         oc = W[9].shape[0]
-        c3(P.cat10, 64, _prep(W[9], 64), Bz[9], oc, 1, _LEAKY, out=P.y10, out_f32=True)
-        x10 = dense.to_nchw_f32(P.y10, oc)
-        lli = dense.to_nchw_f32(P.cat10, 33) if want_lli else None
+        lli = None
+        if want_lli:       # the confidence head wants cat(up(x9), x0_d) as features: materialise it only then
+            if P.cat10 is None:
+                P.cat10 = dense.new_act(n, h, w, 64, xout_d.device, pad=True, zero=True)
+            dense.upsample_into(P.x9, 32, P.cat10, 0)
+            dense.to_nhwc_bf16(x0_d, cpad=8, dst=P.cat10, dst_off=32)
+            lli = dense.to_nchw_f32(P.cat10, 33)
         P.forward_id += 1
         ctx.plan, ctx.fid, ctx.oc, ctx.want_lli = P, P.forward_id, oc, want_lli
-        ctx.save_for_backward(x10, *W)
+        ctx.save_for_backward(x10, x0_d, *W)
         return x10, lli
 
     @staticmethod
@@ -133,33 +136,21 @@ class GEDDenseTC(torch.autograd.Function):
         P = ctx.plan
         if P.forward_id != ctx.fid:
             raise RuntimeError("GEDDenseTC: the module ran another forward before this backward; its saved activations are gone")
-        x10 = ctx.saved_tensors[0]
-        W = ctx.saved_tensors[1:]
+        x10, x0_d = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        W = ctx.saved_tensors[2:]
         b = P.backward_buffers()
         hs, ws, oc = P.hs, P.ws, ctx.oc
         wg, wgb, asm, cs = dense.conv3x3_wgrad_tc, dense.conv3x3_wgrad_box_tc, dense.grad_assemble, dense.colsum
         gW, gB = [None] * 10, [None] * 10
-        # conv10 (LeakyReLU on the output too, confidence_depth_framework.py:506)
-        g_pre = g_x10 * torch.where(x10 > 0, 1.0, 0.2)
-        dense.to_nhwc_bf16(g_pre.contiguous(), cpad=8, dst=b["G10"], dst_off=0)
-        gB[9] = cs(b["G10"], 8)[:oc]
-        gW[9] = wg(b["G10"], P.cat10, 33, oc, cin_pad=48)
-        # channel 32 of the last layer's input is x0_d itself: raw data for the depth-completion net, but the PREDICTED depth when
-        # this net is the loss net (confidence_depth_framework.py:230) -- then its gradient is needed too
-        need_x0d = ctx.needs_input_grad[3]
-        nch = 33 if need_x0d else 32
-        _dgrad_s1(b["G10"], W[9], b["gcat10"], 0, nch)
-        if g_lli is not None:
-            if b["glli"] is None:
-                b["glli"] = dense.new_act(P.n, hs[0], ws[0], 64, g_lli.device, pad=True, zero=True)
-            dense.to_nhwc_bf16(g_lli[:, :nch].contiguous(), cpad=40, dst=b["glli"], dst_off=0)
-            asm(b["gcat10"], 40, a=b["gcat10"], b=b["glli"])
-        g_x0d = dense.to_nchw_f32(b["gcat10"], 1, 32) if need_x0d else None
+        # conv10 (LeakyReLU on the output too, confidence_depth_framework.py:506): direct kernels; produce G9 for conv9.
+        # Channel 32 of its input is x0_d itself: raw data for the depth-completion net, but the PREDICTED depth when this net is
+        # the loss net (confidence_depth_framework.py:230) -- then its gradient is needed too
+        g_x0d, gW[9], gB[9] = dense.ged_head_bwd(P.x9, x0_d, W[9], g_x10, x10, g_lli, b["G9"], ctx.needs_input_grad[3])
         # decoder layers 9..6: G_k = leaky'(x_k) * sum_children(grad of up(x_k))
-        dec = ((8, "G9", "gcat10", P.x9, 32, P.cat9, 112, "gcat9"), (7, "G8", "gcat9", P.x8, 32, P.cat8, 144, "gcat8"),
+        dec = ((8, "G9", None, P.x9, 32, P.cat9, 112, "gcat9"), (7, "G8", "gcat9", P.x8, 32, P.cat8, 144, "gcat8"),
                (6, "G7", "gcat8", P.x7, 64, P.cat7, 144, "gcat7"), (5, "G6", "gcat7", P.x6, 64, P.cat6, 160, "gcat6"))
         for i, gname, src, xk, co, catk, cin, gcat in dec:
-            G = asm(b[gname], co, a=b[src], act=xk, slope=0.2)
+            G = asm(b[gname], co, a=b[src], act=xk, slope=0.2) if src is not None else b[gname]
             gB[i] = cs(G, co)
             gW[i] = wg(G, catk, cin, co, cin_pad=cin)
             _dgrad_s1(G, W[i], b[gcat], 0, cin)

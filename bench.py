@@ -38,7 +38,21 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     p.add_argument("--no-extras", action="store_true", help="skip the extra (non-headline) measurements")
+    p.add_argument("--precision", default="bf16x3", choices=["fp32", "tf32", "bf16x3", "bf16"],
+                   help="dense-layer arithmetic: fp32/tf32 = library backend; bf16x3 (fp32-grade, hi/lo split bf16 operands) and "
+                        "bf16 = hand-written tcgen05 kernels for conv1..conv10 forward and backward")
     return p.parse_args()
+
+
+def _load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+PEAKS = _load_peaks()
 
 
 def peaks():
@@ -177,6 +191,8 @@ def b200_arm(args):
         model.train()
     criterion, _ = factory.create_loss("l2", False, 0.5)
     optimizer = torch.optim.Adam(params, lr=1e-5, capturable=not args.no_graph)
+    from aerial_depth_completion_b200 import dense as _dense
+    _dense.set_precision(args.precision)
     trainer = parallel.DataParallelTrainer(model, criterion, optimizer, params, world_size=world)
 
     # synthetic frames: a pool larger than L2 so no step finds its inputs cached
@@ -257,11 +273,14 @@ def b200_arm(args):
     line = {
         "metric": METRIC, "value": round(frames / ms_total * 1e3, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16x3": "f32 (NConv pyramid) + bf16x3 (dense 3x3 layers: "
+                                       "hi/lo split bf16 operands, fp32 accumulation, fp32-grade parity)",
+                                       "bf16": "f32 (NConv pyramid) + bf16 (dense 3x3 layers)"}[args.precision], "data": "synthetic",
+        "config": {"workload": WORKLOAD, "precision": args.precision, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": "dp%d (one process per GPU, NCCL all-reduce of flat fp32 gradients)" % world,
                    "l2": "inputs rotate through a %.0f MB pool of distinct batches (> 126 MB L2)" % pool_mb,
-                   "dense_backend": __import__("aerial_depth_completion_b200.dense", fromlist=["BACKEND"]).BACKEND,
+                   "dense_backend": ("hand-written tcgen05 implicit GEMM (conv1..conv10 forward, data and weight gradients)"
+                                     if args.precision in ("bf16", "bf16x3") else _dense.BACKEND),
                    "launch": "eager" if args.no_graph else "one CUDA graph per step (forward+loss+backward+allreduce+adam)",
                    "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
         "clocks": sampler_thread.summary(),
@@ -275,6 +294,15 @@ def b200_arm(args):
                             "frac": round(dom["gbs"] / peak, 4), "traffic": None, "kernel": dom["name"],
                             "launch_us": round(dom["us"], 2), "algorithmic_mb_per_launch": round(dom["mb"], 2),
                             "peak_source": peak_src, "nconv_kernels": roof["table"]}
+        if roof.get("tensor"):
+            mma = [r for r in roof["tensor"] if "tflops" in r]
+            tus = sum(r["us_per_step"] for r in mma)
+            tfl = sum(r["algorithmic_gflop_per_step"] for r in mma) / tus * 1e3 if tus else 0.0
+            line["roofline"]["tensor_kernels"] = {
+                "rows": roof["tensor"], "mma_kernels_us_per_step": round(tus, 1), "algorithmic_tflops": round(tfl, 1),
+                "peak_tflops_bf16_sustained": PEAKS.get("bf16_tflops_sustained"), "mma_per_product": 3 if args.precision == "bf16x3" else 1,
+                "frac_of_peak_executed": round(tfl * (3 if args.precision == "bf16x3" else 1) / PEAKS["bf16_tflops_sustained"], 4)
+                if PEAKS.get("bf16_tflops_sustained") else None}
     if world == 1 and not args.no_extras:
         line["extra"] = {"gms_inference_b32": gms_inference(dev)}
     if not args.no_cpu_baseline and world == 1:
@@ -332,30 +360,54 @@ def gms_inference(dev, B=32):
     return out
 
 
+def ged_algorithmic_flops(B):
+    """FLOPs per training step of the dense layers of GEDNet by kernel kind (2*N*Ho*Wo*9*Cin*Cout per convolution, real channel
+    counts: no padding, no bf16x3 triple counting; confidence_depth_framework.py:442-452)."""
+    hs, ws = [H], [W]
+    for _ in range(5):
+        hs.append((hs[-1] - 1) // 2 + 1)
+        ws.append((ws[-1] - 1) // 2 + 1)
+    f = lambda lvl, ci, co: 2.0 * B * hs[lvl] * ws[lvl] * 9 * ci * co
+    enc = [f(1, 5, 80), f(2, 80, 80), f(3, 80, 80), f(4, 80, 80), f(5, 80, 80)]
+    dec = [f(4, 160, 64), f(3, 144, 64), f(2, 144, 32), f(1, 112, 32)]      # conv10 runs on direct (CUDA-core) kernels
+    return {"tc_fprop_s2": sum(enc), "tc_conv_s1(fprop+dgrad)": 2 * sum(dec), "tc_dgrad_s2": sum(enc), "tc_wgrad_s1": sum(dec),
+            "tc_wgrad_s2": sum(enc)}
+
+
 def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B):
-    """Average launch duration (CUDA events on the launching stream, recorded by the library around every kernel) and
-    algorithmic HBM bytes of each NConv kernel inside the training step."""
+    """Average launch duration (CUDA events on the launching stream, recorded by the library around every kernel) of every
+    kernel of the library inside the training step; algorithmic HBM bytes for the NConv kernels, algorithmic FLOPs for the
+    tensor-core kernels."""
     import ctypes
     import torch
     from aerial_depth_completion_b200._lib import lib
     names = {0: "nconv_fwd", 1: "nconv_bwd_data", 2: "nconv_bwd_weight", 3: "pool_fwd", 4: "pool_bwd", 5: "upsample_bwd",
              6: "head_fwd", 7: "head_bwd"}
+    tc_names = {20: "tc_fprop_s2", 21: "tc_conv_s1(fprop+dgrad)", 22: "tc_dgrad_s2", 23: "tc_wgrad_s1", 24: "tc_wgrad_s2", 25: "tc_glue",
+                26: "tc_layout", 27: "tc_prep_weights", 28: "ged_head10(direct)"}
     calls = ("nconv1@L0", "nconv2@L0", "nconv3@L0", "nconv2@L1", "nconv3@L1", "nconv2@L2", "nconv2@L3", "nconv4@L2", "nconv5@L1",
              "nconv6@L0", "nconv7@L0")
-    agg = {}
+    agg, tc = {}, {}
     reps = 3
+    cap = 1024
     for i in range(reps):
         lib.adc_profile_enable(1)
         trainer._eager_step(dev_in[i % pool_n], dev_tg[i % pool_n])
         torch.cuda.synchronize()
         n = ctypes.c_int(0)
-        kinds = (ctypes.c_int * 512)()
-        cl = (ctypes.c_int * 512)()
-        ms = (ctypes.c_float * 512)()
-        by = (ctypes.c_double * 512)()
-        lib.adc_profile_read(512, ctypes.byref(n), kinds, cl, ms, by)
+        kinds = (ctypes.c_int * cap)()
+        cl = (ctypes.c_int * cap)()
+        ms = (ctypes.c_float * cap)()
+        by = (ctypes.c_double * cap)()
+        lib.adc_profile_read(cap, ctypes.byref(n), kinds, cl, ms, by)
         lib.adc_profile_enable(0)
         for j in range(n.value):
+            if kinds[j] in tc_names:
+                a = tc.setdefault(tc_names[kinds[j]], [0.0, 0.0, 0])
+                a[0] += ms[j] * 1e3
+                a[1] += by[j]
+                a[2] += 1
+                continue
             if kinds[j] not in names or by[j] <= 0:
                 continue
             key = names[kinds[j]] + (":" + calls[cl[j]] if kinds[j] < 3 and 0 <= cl[j] < 11 else "")
@@ -371,7 +423,19 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B):
                       "launches_per_step": cnt // reps, "us_per_step": round(us / reps, 2)})
     table.sort(key=lambda r: -r["us_per_step"])
     d = table[0]
-    return {"dominant": {"name": d["name"], "us": d["us"], "mb": d["mb"], "gbs": d["gbs"]}, "table": table[:12]}
+    out = {"dominant": {"name": d["name"], "us": d["us"], "mb": d["mb"], "gbs": d["gbs"]}, "table": table[:12]}
+    if tc:
+        alg = ged_algorithmic_flops(B)
+        rows = []
+        for k, (us, work, cnt) in tc.items():
+            r = {"name": k, "launches_per_step": cnt // reps, "us_per_step": round(us / reps, 1)}
+            if k in alg:
+                r["algorithmic_gflop_per_step"] = round(alg[k] / 1e9, 1)
+                r["tflops"] = round(alg[k] / (us / reps) / 1e6, 1)
+            rows.append(r)
+        rows.sort(key=lambda r: -r["us_per_step"])
+        out["tensor"] = rows
+    return out
 
 
 if __name__ == "__main__":

@@ -209,6 +209,18 @@ size_t adc_nhwc_colsum_workspace_bytes(int C);
 int adc_nhwc_colsum(const void* g, const void* g_lo, int g_stride, int g_off, int N, int C, int H, int W, float* out, void* workspace,
                     adc_stream_t stream);
 
+/* ---- thin last layer of GEDNet (conv10: cat(up(x9) 32 ch, x0_d) -> oc in {1,2}, LeakyReLU 0.2; confidence_depth_framework.py:
+ * 504-506) as direct kernels: the nearest up-sampling is folded into the addressing of x9 (zero-bordered NHWC bf16 pair at its own
+ * resolution H1 x W1), x0_d / output / their gradients stay NCHW fp32.  The backward writes G9 = leaky'(x9) * (data gradient
+ * summed over the up-sampling children [+ the feature gradient glli]) for the tensor-core kernels of conv9, optionally the
+ * gradient of x0_d, and dw [oc][33][3][3], db [oc] (deterministic two-stage reduction). */
+int adc_ged_head_fwd(const void* x9, const void* x9_lo, int x9_stride, int H1, int W1, const float* x0d, const float* w, const float* bias,
+                     float* out, int N, int oc, int H, int W, adc_stream_t stream);
+size_t adc_ged_head_bwd_workspace_bytes(int oc);
+int adc_ged_head_bwd(const void* x9, const void* x9_lo, int x9_stride, int H1, int W1, const float* x0d, const float* w, const float* gy,
+                     const float* x10, const float* glli, int glli_ch, void* g9, void* g9_lo, int g9_stride, float* gx0d, float* dw,
+                     float* db, void* workspace, int N, int oc, int H, int W, adc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
