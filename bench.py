@@ -38,6 +38,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     p.add_argument("--no-extras", action="store_true", help="skip the extra (non-headline) measurements")
+    p.add_argument("--kernel-detail", default="", help="write one step's per-launch records (kind, work, us) to this file")
     p.add_argument("--precision", default="bf16x3", choices=["fp32", "tf32", "bf16x3", "bf16"],
                    help="dense-layer arithmetic: fp32/tf32 = library backend; bf16x3 (fp32-grade, hi/lo split bf16 operands) and "
                         "bf16 = hand-written tcgen05 kernels for conv1..conv10 forward and backward")
@@ -262,7 +263,7 @@ def b200_arm(args):
     sampler_thread.stop_flag = True
 
     # per-kernel CUDA-event timing of the same step (profiling pass after the timed region)
-    roof = kernel_roofline(trainer, dev_in, dev_tg, pool_n, B)
+    roof = kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, args.kernel_detail if rank == 0 else "")
 
     if rank != 0:
         if world > 1:
@@ -374,7 +375,7 @@ def ged_algorithmic_flops(B):
             "tc_wgrad_s2": sum(enc)}
 
 
-def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B):
+def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, detail_path=""):
     """Average launch duration (CUDA events on the launching stream, recorded by the library around every kernel) of every
     kernel of the library inside the training step; algorithmic HBM bytes for the NConv kernels, algorithmic FLOPs for the
     tensor-core kernels."""
@@ -401,6 +402,12 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B):
         by = (ctypes.c_double * cap)()
         lib.adc_profile_read(cap, ctypes.byref(n), kinds, cl, ms, by)
         lib.adc_profile_enable(0)
+        if detail_path and i == reps - 1:
+            with open(detail_path, "w") as fh:
+                fh.write("# one training step, launches in issue order: kind, name, work (bytes or FLOPs as the kernel sees them), us\n")
+                for j in range(n.value):
+                    nm = tc_names.get(kinds[j]) or names.get(kinds[j]) or {8: "pack", 9: "reduce", 10: "prep"}.get(kinds[j], "?")
+                    fh.write("%d,%s,%.4g,%.2f\n" % (kinds[j], nm, by[j], ms[j] * 1e3))
         for j in range(n.value):
             if kinds[j] in tc_names:
                 a = tc.setdefault(tc_names[kinds[j]], [0.0, 0.0, 0])
