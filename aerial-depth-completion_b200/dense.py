@@ -165,7 +165,8 @@ def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=No
     from ._lib import lib, check
     n, h, w = act.n, act.h, act.w
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
-    v2 = USE_V2 and stride == 1 and act.pad and cin % 64 == 0 and cout <= 128 and (out is None or out.pad)
+    # v2 streams 3 taps x Cout16 weight rows per pipeline stage: in the split mode two stages fit only up to 64 output channels
+    v2 = USE_V2 and stride == 1 and act.pad and cin % 64 == 0 and cout <= (64 if _split() else 128) and (out is None or out.pad)
     zero_to = out_zero_to if v2 else 0                      # slice width the layer owns (channels past cout written as 0)
     if out is None:
         out_pad = act.pad if out_pad is None else out_pad

@@ -21,8 +21,10 @@ def test_dgrad_is_fprop_with_flipped_weights(case, prec):
     try:
         ga = dense.new_act(n, h, w, dense._r64(cout), "cuda", pad=True, zero=True)
         dense.to_nhwc_bf16(gy.cuda(), cpad=cout, dst=ga, dst_off=0)
-        wp = dense.prep_conv3x3_weights(wt.cuda(), flip_transpose=True, cin_pad=ga.cs)
-        gx = dense.conv3x3_tc(ga, ga.cs, wp, None, cin, 1, 0)
+        # the training path's helper: output channels in chunks the kernel's shared-memory budget takes (64 in the split mode)
+        from aerial_depth_completion_b200.tc_train import _dgrad_s1
+        gx = dense.new_act(n, h, w, dense._r64(cin), "cuda", pad=True, zero=True)
+        _dgrad_s1(ga, wt.cuda(), gx, 0, cin)
         got = dense.to_nchw_f32(gx, cin).cpu()
     finally:
         dense.set_precision(prev)
