@@ -50,6 +50,15 @@ class PyramidBwd(ctypes.Structure):
                 ("gx0", ctypes.c_void_p), ("gc0", ctypes.c_void_p), ("gweight", ctypes.c_void_p), ("gbias", ctypes.c_void_p)]
 
 
+ADC_WPREP_MAX = 40
+
+
+class WPrepItem(ctypes.Structure):
+    """adc_wprep_item_t"""
+    _fields_ = [("w", ctypes.c_void_p), ("out", ctypes.c_void_p), ("out_lo", ctypes.c_void_p), ("cout", c_int), ("cin", c_int),
+                ("ci_off", c_int), ("ci_cnt", c_int), ("cin_pad", c_int), ("mode", c_int)]
+
+
 # every symbol include/adc_b200.h declares: name -> (restype, argtypes)
 _vp, _sp = ctypes.c_void_p, ctypes.POINTER(Src)
 SIGNATURES = {
@@ -77,6 +86,7 @@ SIGNATURES = {
     "adc_nhwc_to_nchw_f32": (c_int, [_vp, c_int, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_weight_elems": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_prep_weights": (c_int, [_vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_conv3x3_prep_weights_batch": (c_int, [_vp, c_int, _vp]),
     "adc_conv3x3_fprop_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_s1_tc_v2": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -87,13 +97,20 @@ SIGNATURES = {
                                          c_int, c_int, c_int, _vp]),
     "adc_nhwc_upsample_nearest": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_nhwc_grad_assemble": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int, c_int, ctypes.c_float,
-                                       _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+                                       _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp]),
+    "adc_nhwc_grad_assemble_parts": (c_int, []),
     "adc_nhwc_colsum_workspace_bytes": (ctypes.c_size_t, [c_int]),
     "adc_nhwc_colsum": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp]),
     "adc_ged_head_fwd": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_ged_head_bwd_workspace_bytes": (ctypes.c_size_t, [c_int]),
     "adc_ged_head_bwd": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp,
                                  c_int, c_int, c_int, c_int, _vp]),
+    "adc_ged_head_bwd_x0d": (c_int, [_vp, _vp, _vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_ged_pack_input": (c_int, [_vp, _vp, _vp, c_ll, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_quad_head_finish": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_quad_head_bwd_prep_parts": (c_int, []),
+    "adc_quad_head_bwd_prep": (c_int, [_vp, _vp, _vp, _vp, _vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_quad_unshuffle": (c_int, [_vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_wgrad_tc_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_wgrad_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      _vp]),

@@ -526,6 +526,32 @@ __global__ void prep_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
     }
 }
 
+// Several weight tensors in ONE launch (a training step prepares ~28 of them: every layer's forward weights, and the
+// transposed / flipped data-gradient weights per output-channel chunk).  Item = channel slice [ci_off, ci_off+ci_cnt) of the
+// input channels of a [cout][cin][3][3] tensor, converted like prep_conv_weights_kernel does for a contiguous tensor.
+struct WPrepBatch {
+    adc_wprep_item_t it[ADC_WPREP_MAX];
+};
+__global__ void __launch_bounds__(256) prep_conv_weights_batch_kernel(const __grid_constant__ WPrepBatch b) {
+    const adc_wprep_item_t& t = b.it[blockIdx.y];
+    const int oc = t.mode ? t.ci_cnt : t.cout, npad = (oc + 15) / 16 * 16;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(t.out);
+    __nv_bfloat16* out_lo = reinterpret_cast<__nv_bfloat16*>(t.out_lo);
+    const long long total = 9LL * npad * t.cin_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % t.cin_pad), co = (int)((i / t.cin_pad) % npad), tap = (int)(i / ((long long)t.cin_pad * npad));
+        float v = 0.f;
+        if (!t.mode) {
+            if (co < t.cout && ci < t.ci_cnt) v = t.w[((long long)co * t.cin + t.ci_off + ci) * 9 + tap];
+        } else {
+            if (co < t.ci_cnt && ci < t.cout) v = t.w[((long long)ci * t.cin + t.ci_off + co) * 9 + (t.mode == 1 ? 8 - tap : tap)];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        out[i] = hi;
+        if (out_lo) out_lo[i] = __float2bfloat16(v - __bfloat162float(hi));
+    }
+}
+
 template <int KBLK>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mxl, const CUtensorMap& mwl, const ConvParams& p,
                   int smem, cudaStream_t st) {
@@ -602,6 +628,28 @@ int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int c
     prep_conv_weights_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out_lo, cout, cin, npad,
                                                                    cin_pad, flip_transpose);
     return adc::check_cuda(cudaGetLastError(), "prep_conv_weights_kernel launch");
+}
+
+int adc_conv3x3_prep_weights_batch(const adc_wprep_item_t* items, int n, adc_stream_t stream) {
+    if (!items || n <= 0 || n > ADC_WPREP_MAX) {
+        adc::set_error("adc_conv3x3_prep_weights_batch: 1..%d items", ADC_WPREP_MAX);
+        return ADC_E_BADARG;
+    }
+    WPrepBatch b;
+    memset(&b, 0, sizeof(b));
+    for (int k = 0; k < n; ++k) {
+        const adc_wprep_item_t& t = items[k];
+        const int ic = t.mode ? t.cout : t.ci_cnt;
+        if (!t.w || !t.out || t.cout <= 0 || t.cin <= 0 || t.ci_off < 0 || t.ci_cnt <= 0 || t.ci_off + t.ci_cnt > t.cin || t.cin_pad < ic ||
+            t.cin_pad % 16 != 0 || t.mode < 0 || t.mode > 2) {
+            adc::set_error("adc_conv3x3_prep_weights_batch: bad item %d", k);
+            return ADC_E_BADARG;
+        }
+        b.it[k] = t;
+    }
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_PREP, 0.0);
+    prep_conv_weights_batch_kernel<<<dim3(24, n), 256, 0, (cudaStream_t)stream>>>(b);
+    return adc::check_cuda(cudaGetLastError(), "prep_conv_weights_batch_kernel launch");
 }
 
 // One launch of the v1 kernel: a sum over a tap list of [128 pixels x Cin] x [Cin x Cout] products (see ConvParams).

@@ -430,4 +430,19 @@ int adc_ged_head_bwd(const void* x9, const void* x9_lo, int x9_stride, int H1, i
     return 0;
 }
 
+// gradient of the x0_d channel alone (the quad path computes everything else on the tensor cores): gx0d [N][1][H][W]
+int adc_ged_head_bwd_x0d(const float* gy, const float* x10, const float* glli, int glli_ch, const float* w, float* gx0d, int N, int oc,
+                         int H, int W, adc_stream_t stream) {
+    if (!gy || !x10 || !w || !gx0d || N <= 0 || H <= 0 || W <= 0 || oc < 1 || oc > kMaxOc || (glli && glli_ch < 33)) {
+        adc::set_error("adc_ged_head_bwd_x0d: bad argument");
+        return ADC_E_BADARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long t0 = (long long)N * H * W;
+    adc::Prof prof(st, adc::KIND_HEAD10, (double)t0 * (4.0 + 8.0 * oc));
+    if (oc == 1) ged_head_bwd_x0d_kernel<1><<<grid_for(t0, 256), 256, 0, st>>>(gy, x10, glli, glli_ch, w, gx0d, N, H, W);
+    else ged_head_bwd_x0d_kernel<2><<<grid_for(t0, 256), 256, 0, st>>>(gy, x10, glli, glli_ch, w, gx0d, N, H, W);
+    return adc::check_cuda(cudaGetLastError(), "ged_head_bwd_x0d_kernel launch");
+}
+
 }  // extern "C"

@@ -1,0 +1,322 @@
+// "Quad" (pixel-shuffle) forms of the two full-resolution thin layers of GEDNet (confidence_depth_framework.py:442,452,
+// 469-506) and their glue.
+//
+// conv10 reads cat(up(x9), x0_d) at full resolution, where up() is the exact 2x nearest up-sampling of x9.  The 3x3 taps of an
+// output pixel (2i+py, 2j+px) then fall on only 2x2 distinct pixels of x9, so
+//     conv10(up(x9))[2i+py][2j+px] = sum_{a,b in 3x3} Wq[(py,px)][c][a][b] * x9[i+a-1][j+b-1][c]
+// with Wq = the taps of W that land on the same x9 pixel added together: a stride-1 3x3 convolution of x9 AT ITS OWN RESOLUTION
+// with 4 output channels per original output channel (one per parity).  That convolution (and its data / weight gradients)
+// runs on the tcgen05 kernels on a quarter of the pixels; what is left at full resolution is elementwise and lives here:
+//   * quad_head_finish:   un-shuffle the 4 parity channels + the x0_d channel's own 3x3 taps + bias + LeakyReLU(0.2) -> NCHW fp32
+//   * quad_head_bwd_prep: gpre = gy * leaky'(x10) shuffled into the 4-parity NHWC bf16 (hi, lo) gradient tensor the tensor-core
+//                         kernels consume; x0_d-channel weight gradient and bias gradient partial sums
+// The same identity read backwards gives the data gradient of conv1 (3x3, stride 2): gin[2i+py][2j+px][c] is a stride-1 3x3
+// convolution of G1 (conv1's output gradient, low resolution) with 4 parity output channels per input channel:
+//   * quad_unshuffle:     [N][H1+2][W1+2][4*K] fp32 -> K planar [N][H][W] fp32 gradients
+// and the entry of the dense path:
+//   * ged_pack_input:     (xout_d, rgb, cout_d) NCHW fp32 -> zero-bordered NHWC bf16 (hi, lo) [.., 16] = torch.cat + layout in one pass
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/adc_b200.h"
+#include "prof.h"
+
+namespace adc {
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+}  // namespace adc
+
+namespace quad {
+
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : 0.2f * v; }
+
+// 4x4 neighbourhood of a planar fp32 image around the 2x2 block (2i, 2j): rows 2i-1..2i+2, columns 2j-1..2j+2, zeros outside
+__device__ __forceinline__ void load_nb4(const float* __restrict__ img, int H, int W, int i, int j, float (&d)[4][4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int y = 2 * i - 1 + r;
+        const bool yok = y >= 0 && y < H;
+        const float* row = img + (long long)(yok ? y : 0) * W;
+        const int x0 = 2 * j - 1;
+        d[r][0] = (yok && x0 >= 0) ? __ldg(row + x0) : 0.f;
+        if (yok && ((W & 1) == 0)) {        // 2j, 2j+1 are both in range and 8-byte aligned when W is even
+            const float2 m = __ldg(reinterpret_cast<const float2*>(row + x0 + 1));
+            d[r][1] = m.x; d[r][2] = m.y;
+        } else {
+            d[r][1] = (yok && x0 + 1 < W) ? __ldg(row + x0 + 1) : 0.f;
+            d[r][2] = (yok && x0 + 2 < W) ? __ldg(row + x0 + 2) : 0.f;
+        }
+        d[r][3] = (yok && x0 + 3 < W) ? __ldg(row + x0 + 3) : 0.f;
+    }
+}
+
+// out[n][o][2i+py][2j+px] = leaky( q[n][i+1][j+1][(py*2+px)*OC + o] + bias[o] + sum_{u,v} w[o][32][u][v] * x0d[n][2i+py+u-1][2j+px+v-1] )
+template <int OC>
+__global__ void __launch_bounds__(256) quad_head_finish_kernel(const float* __restrict__ q, int q_stride, const float* __restrict__ x0d,
+                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                               float* __restrict__ out, int N, int H, int W) {
+    const int H1 = H >> 1, W1 = W >> 1;
+    float wd[OC][9], b[OC];
+#pragma unroll
+    for (int o = 0; o < OC; ++o) {
+        b[o] = __ldg(bias + o);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wd[o][t] = __ldg(w + ((long long)o * 33 + 32) * 9 + t);
+    }
+    const long long total = (long long)N * H1 * W1;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % W1), i = (int)((t / W1) % H1), n = (int)(t / ((long long)W1 * H1));
+        float d[4][4];
+        load_nb4(x0d + (long long)n * H * W, H, W, i, j, d);
+        const float* qp = q + (((long long)n * (H1 + 2) + i + 1) * (W1 + 2) + j + 1) * q_stride;
+        float qv[4 * OC];
+#pragma unroll
+        for (int k = 0; k < OC; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(qp) + k);
+            qv[4 * k] = v.x; qv[4 * k + 1] = v.y; qv[4 * k + 2] = v.z; qv[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+            float r[2][2];
+#pragma unroll
+            for (int py = 0; py < 2; ++py)
+#pragma unroll
+                for (int px = 0; px < 2; ++px) {
+                    float acc = qv[(py * 2 + px) * OC + o] + b[o];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) acc = fmaf(wd[o][u * 3 + v], d[py + u][px + v], acc);
+                    r[py][px] = leaky(acc);
+                }
+            float* op = out + (((long long)n * OC + o) * H + 2 * i) * W + 2 * j;
+            *reinterpret_cast<float2*>(op) = make_float2(r[0][0], r[0][1]);
+            *reinterpret_cast<float2*>(op + W) = make_float2(r[1][0], r[1][1]);
+        }
+    }
+}
+
+// gq[n][i+1][j+1][(py*2+px)*OC + o] = gpre[n][o][2i+py][2j+px] = gy * (x10 > 0 ? 1 : 0.2)   (bf16 hi, lo; channels [4*OC, 8) zero)
+// part[block][o][t]  t < 9: sum gpre[o][y][x] * x0d[y+u-1][x+v-1] (weight gradient of the x0_d channel);  t = 9: sum gpre[o]
+template <int OC>
+__global__ void __launch_bounds__(256) quad_head_bwd_prep_kernel(const float* __restrict__ gy, const float* __restrict__ x10,
+                                                                 const float* __restrict__ x0d, __nv_bfloat16* __restrict__ gq,
+                                                                 __nv_bfloat16* __restrict__ gq_lo, int gq_stride, float* __restrict__ part,
+                                                                 int N, int H, int W) {
+    __shared__ float red[8][OC * 10];
+    const int H1 = H >> 1, W1 = W >> 1;
+    float acc[OC][10];
+#pragma unroll
+    for (int o = 0; o < OC; ++o)
+#pragma unroll
+        for (int t = 0; t < 10; ++t) acc[o][t] = 0.f;
+    const long long total = (long long)N * H1 * W1;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % W1), i = (int)((t / W1) % H1), n = (int)(t / ((long long)W1 * H1));
+        float d[4][4];
+        load_nb4(x0d + (long long)n * H * W, H, W, i, j, d);
+        float g[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = 0.f;
+#pragma unroll
+        for (int o = 0; o < OC; ++o) {
+            const long long p = (((long long)n * OC + o) * H + 2 * i) * W + 2 * j;
+            const float2 g0 = __ldg(reinterpret_cast<const float2*>(gy + p)), g1 = __ldg(reinterpret_cast<const float2*>(gy + p + W));
+            const float2 y0 = __ldg(reinterpret_cast<const float2*>(x10 + p)), y1 = __ldg(reinterpret_cast<const float2*>(x10 + p + W));
+            float gp[2][2];
+            gp[0][0] = g0.x * (y0.x > 0.f ? 1.f : 0.2f);
+            gp[0][1] = g0.y * (y0.y > 0.f ? 1.f : 0.2f);
+            gp[1][0] = g1.x * (y1.x > 0.f ? 1.f : 0.2f);
+            gp[1][1] = g1.y * (y1.y > 0.f ? 1.f : 0.2f);
+#pragma unroll
+            for (int py = 0; py < 2; ++py)
+#pragma unroll
+                for (int px = 0; px < 2; ++px) {
+                    g[(py * 2 + px) * OC + o] = gp[py][px];
+                    acc[o][9] += gp[py][px];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) acc[o][u * 3 + v] = fmaf(gp[py][px], d[py + u][px + v], acc[o][u * 3 + v]);
+                }
+        }
+        uint4 h, l;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&h);
+        __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&l);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hh[k] = __floats2bfloat162_rn(g[2 * k], g[2 * k + 1]);
+            ll[k] = __floats2bfloat162_rn(g[2 * k] - __low2float(hh[k]), g[2 * k + 1] - __high2float(hh[k]));
+        }
+        const long long pix = ((long long)n * (H1 + 2) + i + 1) * (W1 + 2) + j + 1;
+        *reinterpret_cast<uint4*>(gq + pix * gq_stride) = h;
+        if (gq_lo) *reinterpret_cast<uint4*>(gq_lo + pix * gq_stride) = l;
+    }
+    // deterministic block reduction: lanes (xor shuffles), then the 8 warps in index order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 0; o < OC; ++o)
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+            float v = acc[o][t];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if (lane == 0) red[warp][o * 10 + t] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < OC * 10) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+        part[(long long)blockIdx.x * OC * 10 + threadIdx.x] = s;
+    }
+}
+
+// out[k][n][2i+py][2j+px] = q[n][i+1][j+1][(py*2+px)*K + k]     (H1 = ceil(H/2); odd H / W: the missing row / column is skipped)
+template <int K>
+__global__ void __launch_bounds__(256) quad_unshuffle_kernel(const float* __restrict__ q, int q_stride, float* __restrict__ out, int N, int H,
+                                                             int W) {
+    const int H1 = (H + 1) >> 1, W1 = (W + 1) >> 1;
+    const long long total = (long long)N * H1 * W1, plane = (long long)N * H * W;
+    const bool vec = (W & 1) == 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % W1), i = (int)((t / W1) % H1), n = (int)(t / ((long long)W1 * H1));
+        const float* qp = q + (((long long)n * (H1 + 2) + i + 1) * (W1 + 2) + j + 1) * q_stride;
+        float qv[4 * K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(qp) + k);
+            qv[4 * k] = v.x; qv[4 * k + 1] = v.y; qv[4 * k + 2] = v.z; qv[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int py = 0; py < 2; ++py) {
+                const int y = 2 * i + py;
+                if (y >= H) continue;
+                float* op = out + k * plane + ((long long)n * H + y) * W + 2 * j;
+                const float a = qv[(py * 2) * K + k], b = qv[(py * 2 + 1) * K + k];
+                if (vec) {
+                    *reinterpret_cast<float2*>(op) = make_float2(a, b);
+                } else {
+                    op[0] = a;
+                    if (2 * j + 1 < W) op[1] = b;
+                }
+            }
+    }
+}
+
+// in0[n][y+1][x+1][0..15] = {xout_d, r, g, b, cout_d, 0 x 11} as bf16 (hi, lo)
+__global__ void __launch_bounds__(256) ged_pack_input_kernel(const float* __restrict__ xout, const float* __restrict__ cout,
+                                                             const float* __restrict__ rgb, long long rgb_bs, __nv_bfloat16* __restrict__ dst,
+                                                             __nv_bfloat16* __restrict__ dst_lo, int dst_stride, int N, int H, int W) {
+    const long long HW = (long long)H * W, total = (long long)N * HW;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long p = t % HW;
+        const int n = (int)(t / HW);
+        const int x = (int)(p % W), y = (int)(p / W);
+        float v[8];
+        v[0] = __ldg(xout + t);
+        v[1] = __ldg(rgb + n * rgb_bs + p);
+        v[2] = __ldg(rgb + n * rgb_bs + HW + p);
+        v[3] = __ldg(rgb + n * rgb_bs + 2 * HW + p);
+        v[4] = __ldg(cout + t);
+        v[5] = v[6] = v[7] = 0.f;
+        uint4 h, l;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&h);
+        __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&l);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hh[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+            ll[k] = __floats2bfloat162_rn(v[2 * k] - __low2float(hh[k]), v[2 * k + 1] - __high2float(hh[k]));
+        }
+        const long long pix = ((long long)n * (H + 2) + y + 1) * (W + 2) + x + 1;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        uint4* o = reinterpret_cast<uint4*>(dst + pix * dst_stride);
+        o[0] = h;
+        o[1] = z;
+        if (dst_lo) {
+            uint4* ol = reinterpret_cast<uint4*>(dst_lo + pix * dst_stride);
+            ol[0] = l;
+            ol[1] = z;
+        }
+    }
+}
+
+static int grid_for(long long total, int block) {
+    long long b = (total + block - 1) / block;
+    const long long cap = 148LL * 8;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+constexpr int kPrepCtas = 148 * 4;
+
+}  // namespace quad
+
+using namespace quad;
+
+extern "C" {
+
+int adc_ged_pack_input(const float* xout, const float* cout, const float* rgb, long long rgb_batch_stride, void* dst, void* dst_lo,
+                       int dst_stride, int N, int H, int W, adc_stream_t stream) {
+    if (!xout || !cout || !rgb || !dst || N <= 0 || H <= 0 || W <= 0 || dst_stride < 16 || dst_stride % 8 != 0) {
+        adc::set_error("adc_ged_pack_input: bad argument");
+        return ADC_E_BADARG;
+    }
+    const long long total = (long long)N * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_TC_LAYOUT, (double)total * (20.0 + (dst_lo ? 64.0 : 32.0)));
+    ged_pack_input_kernel<<<grid_for(total, 256), 256, 0, st>>>(xout, cout, rgb, rgb_batch_stride, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo,
+                                                                 dst_stride, N, H, W);
+    return adc::check_cuda(cudaGetLastError(), "ged_pack_input_kernel launch");
+}
+
+int adc_quad_head_finish(const float* q, int q_stride, const float* x0d, const float* w, const float* bias, float* out, int N, int oc, int H,
+                         int W, adc_stream_t stream) {
+    if (!q || !x0d || !w || !bias || !out || N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || oc < 1 || oc > 2 || q_stride < 4 * oc ||
+        q_stride % 4 != 0) {
+        adc::set_error("adc_quad_head_finish: bad argument (needs even H, W; oc in {1,2})");
+        return ADC_E_BADARG;
+    }
+    const long long total = (long long)N * (H / 2) * (W / 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_HEAD10, (double)total * (16.0 * oc + 16.0 + 16.0 * oc));
+    if (oc == 1) quad_head_finish_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(q, q_stride, x0d, w, bias, out, N, H, W);
+    else quad_head_finish_kernel<2><<<grid_for(total, 256), 256, 0, st>>>(q, q_stride, x0d, w, bias, out, N, H, W);
+    return adc::check_cuda(cudaGetLastError(), "quad_head_finish_kernel launch");
+}
+
+int adc_quad_head_bwd_prep_parts(void) { return kPrepCtas; }
+
+int adc_quad_head_bwd_prep(const float* gy, const float* x10, const float* x0d, void* gq, void* gq_lo, int gq_stride, float* part, int N,
+                           int oc, int H, int W, adc_stream_t stream) {
+    if (!gy || !x10 || !x0d || !gq || !part || N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || oc < 1 || oc > 2 || gq_stride < 8 ||
+        gq_stride % 8 != 0) {
+        adc::set_error("adc_quad_head_bwd_prep: bad argument (needs even H, W; oc in {1,2})");
+        return ADC_E_BADARG;
+    }
+    const long long total = (long long)N * (H / 2) * (W / 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_HEAD10, (double)total * (32.0 * oc + 16.0 + (gq_lo ? 32.0 : 16.0)));
+    if (oc == 1)
+        quad_head_bwd_prep_kernel<1><<<kPrepCtas, 256, 0, st>>>(gy, x10, x0d, (__nv_bfloat16*)gq, (__nv_bfloat16*)gq_lo, gq_stride, part, N, H, W);
+    else
+        quad_head_bwd_prep_kernel<2><<<kPrepCtas, 256, 0, st>>>(gy, x10, x0d, (__nv_bfloat16*)gq, (__nv_bfloat16*)gq_lo, gq_stride, part, N, H, W);
+    return adc::check_cuda(cudaGetLastError(), "quad_head_bwd_prep_kernel launch");
+}
+
+int adc_quad_unshuffle(const float* q, int q_stride, float* out, int N, int K, int H, int W, adc_stream_t stream) {
+    if (!q || !out || N <= 0 || H <= 0 || W <= 0 || K < 1 || K > 2 || q_stride < 4 * K || q_stride % 4 != 0) {
+        adc::set_error("adc_quad_unshuffle: bad argument (K in {1,2})");
+        return ADC_E_BADARG;
+    }
+    const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_TC_LAYOUT, (double)total * 32.0 * K);
+    if (K == 1) quad_unshuffle_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(q, q_stride, out, N, H, W);
+    else quad_unshuffle_kernel<2><<<grid_for(total, 256), 256, 0, st>>>(q, q_stride, out, N, H, W);
+    return adc::check_cuda(cudaGetLastError(), "quad_unshuffle_kernel launch");
+}
+
+}  // extern "C"

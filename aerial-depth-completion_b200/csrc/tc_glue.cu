@@ -101,42 +101,74 @@ __global__ void __launch_bounds__(256) nhwc_upsample_kernel(Slice src, SliceW ds
 
 // out[n][y][x][c] = d(act)[n][y][x][c] * ( sum over the up-sampling children (yd,xd) of (y,x) of A[n][yd][xd][c]  +  B[n][y][x][c] )
 // d(act) = 1 where act > 0, else slope (ReLU: 0, LeakyReLU: 0.2); A lives at (Hd,Wd) >= (H,W) (identity map if equal), A/B/act
-// optional.  Fixed summation order (deterministic).
+// optional.  Fixed summation order (deterministic).  A thread keeps ONE 8-channel group for its whole life (thread = (pixel
+// slot, group)), so the per-channel sum of the output -- the bias gradient of the layer that produced `act` -- falls out of the
+// same pass: part[block][C] partial rows, summed by the caller in index order.
 __global__ void __launch_bounds__(256) nhwc_grad_assemble_kernel(Slice A, int hasA, Slice B, int hasB, Slice act, int hasAct, float slope,
-                                                                 SliceW out, int N, int C8, int H, int W, int Hd, int Wd, Near mh, Near mw) {
-    const long long total = (long long)N * H * W * C8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C8) * 8;
-        long long r = i / C8;
-        const int x = (int)(r % W);
-        r /= W;
-        const int y = (int)(r % H), n = (int)(r / H);
-        float v[8];
+                                                                 SliceW out, int N, int C8, int H, int W, int Hd, int Wd, Near mh, Near mw,
+                                                                 float* __restrict__ part) {
+    __shared__ float red[256][8];
+    const int groups = 256 / C8;                               // C8 <= 32
+    const int cl = threadIdx.x % C8, pg = threadIdx.x / C8, c = cl * 8;
+    const long long pixels = (long long)N * H * W;
+    float s[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        if (hasA) {
-            // children of y: the yd with mh(yd) == y form a contiguous range around y*Hd/H
-            int y0 = (int)(((long long)y * Hd) / H) - 1, x0 = (int)(((long long)x * Wd) / W) - 1;
-            for (int yd = y0 < 0 ? 0 : y0; yd < Hd && yd <= y0 + 4; ++yd) {
-                if (mh(yd) != y) continue;
-                for (int xd = x0 < 0 ? 0 : x0; xd < Wd && xd <= x0 + 4; ++xd) {
-                    if (mw(xd) != x) continue;
-                    load8(A, ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1, c, v, true);
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if (pg < groups)
+        for (long long r = (long long)blockIdx.x * groups + pg; r < pixels; r += (long long)gridDim.x * groups) {
+            const int x = (int)(r % W), y = (int)((r / W) % H), n = (int)(r / ((long long)W * H));
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            if (hasA) {
+                if (Hd == 2 * H && Wd == 2 * W) {              // exact 2x: the four children, row-major
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx)
+                            load8(A, ((long long)n * (Hd + 2) + 2 * y + dy + 1) * (Wd + 2) + 2 * x + dx + 1, c, v, true);
+                } else if (Hd == H && Wd == W) {
+                    load8(A, ((long long)n * (Hd + 2) + y + 1) * (Wd + 2) + x + 1, c, v, true);
+                } else {
+                    // children of y: the yd with mh(yd) == y form a contiguous range around y*Hd/H
+                    int y0 = (int)(((long long)y * Hd) / H) - 1, x0 = (int)(((long long)x * Wd) / W) - 1;
+                    for (int yd = y0 < 0 ? 0 : y0; yd < Hd && yd <= y0 + 4; ++yd) {
+                        if (mh(yd) != y) continue;
+                        for (int xd = x0 < 0 ? 0 : x0; xd < Wd && xd <= x0 + 4; ++xd) {
+                            if (mw(xd) != x) continue;
+                            load8(A, ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1, c, v, true);
+                        }
+                    }
                 }
             }
-        }
-        const long long p = ((long long)n * (H + 2) + y + 1) * (W + 2) + x + 1;
-        if (hasB) load8(B, p, c, v, true);
-        if (hasAct) {
-            const uint4 a = *reinterpret_cast<const uint4*>(act.hi + p * act.stride + act.off + c);
-            const __nv_bfloat162* aa = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const long long p = ((long long)n * (H + 2) + y + 1) * (W + 2) + x + 1;
+            if (hasB) load8(B, p, c, v, true);
+            if (hasAct) {
+                const uint4 a = *reinterpret_cast<const uint4*>(act.hi + p * act.stride + act.off + c);
+                const __nv_bfloat162* aa = reinterpret_cast<const __nv_bfloat162*>(&a);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                v[2 * j] *= __low2float(aa[j]) > 0.f ? 1.f : slope;
-                v[2 * j + 1] *= __high2float(aa[j]) > 0.f ? 1.f : slope;
+                for (int j = 0; j < 4; ++j) {
+                    v[2 * j] *= __low2float(aa[j]) > 0.f ? 1.f : slope;
+                    v[2 * j + 1] *= __high2float(aa[j]) > 0.f ? 1.f : slope;
+                }
             }
+            store8(out, p, c, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += v[j];
         }
-        store8(out, p, c, v);
+    if (part == nullptr) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = pg < groups ? s[j] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < C8) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+        for (int q = 0; q < groups; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] += red[q * C8 + threadIdx.x][j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[(long long)blockIdx.x * C8 * 8 + threadIdx.x * 8 + j] = t[j];
     }
 }
 
@@ -178,6 +210,8 @@ static int grid_for(long long total) {
     return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+constexpr int kAssembleCtas = 148 * 8;
+
 static bool bad_slice(const void* hi, int stride, int off, int C) { return !hi || stride % 8 != 0 || off % 8 != 0 || C % 8 != 0 || off + C > stride; }
 
 }  // namespace glue
@@ -201,10 +235,12 @@ int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_strid
     return adc::check_cuda(cudaGetLastError(), "nhwc_upsample_kernel launch");
 }
 
+int adc_nhwc_grad_assemble_parts(void) { return kAssembleCtas; }
+
 int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_off, int Hd, int Wd, const void* b, const void* b_lo,
                            int b_stride, int b_off, const void* act, int act_stride, int act_off, float slope, void* out, void* out_lo,
-                           int out_stride, int out_off, int N, int C, int H, int W, adc_stream_t stream) {
-    if ((!a && !b) || bad_slice(out, out_stride, out_off, C) || (a && bad_slice(a, a_stride, a_off, C)) || (b && bad_slice(b, b_stride, b_off, C)) ||
+                           int out_stride, int out_off, int N, int C, int H, int W, float* colsum_part, adc_stream_t stream) {
+    if (C > 256 || (!a && !b) || bad_slice(out, out_stride, out_off, C) || (a && bad_slice(a, a_stride, a_off, C)) || (b && bad_slice(b, b_stride, b_off, C)) ||
         (act && bad_slice(act, act_stride, act_off, C)) || N <= 0 || H <= 0 || W <= 0 || (a && (Hd < H || Wd < W))) {
         adc::set_error("adc_nhwc_grad_assemble: bad argument");
         return ADC_E_BADARG;
@@ -216,8 +252,8 @@ int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_
     if (!a) { Hd = H; Wd = W; }
     const long long total = (long long)N * H * W * (C / 8);
     adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)total * 16.0 * (out_lo ? 2 : 1) * (1 + (a ? 1 : 0) + (b ? 1 : 0)));
-    nhwc_grad_assemble_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(A, a != nullptr, B, b != nullptr, T, act != nullptr, slope, O, N,
-                                                                               C / 8, H, W, Hd, Wd, Near::make(H, Hd), Near::make(W, Wd));
+    nhwc_grad_assemble_kernel<<<kAssembleCtas, 256, 0, (cudaStream_t)stream>>>(A, a != nullptr, B, b != nullptr, T, act != nullptr, slope, O, N,
+                                                                             C / 8, H, W, Hd, Wd, Near::make(H, Hd), Near::make(W, Wd), colsum_part);
     return adc::check_cuda(cudaGetLastError(), "nhwc_grad_assemble_kernel launch");
 }
 

@@ -158,6 +158,32 @@ def prep_conv3x3_weights(weight, flip_transpose=False, cin_pad=None):
     return (hi, lo)
 
 
+def prep_conv3x3_weights_batch(reqs):
+    """Several prep_conv3x3_weights in ONE launch.  reqs: (weight [Cout,Cin,3,3], mode, cin_pad, ci_off, ci_cnt) with mode 0 =
+    forward weights of input channels [ci_off, ci_off+ci_cnt), 1 / 2 = transposed data-gradient weights (taps flipped / kept)
+    producing those channels.  Returns [(hi, lo)] in order."""
+    import ctypes
+    from ._lib import lib, check, WPrepItem, ADC_WPREP_MAX
+    outs = []
+    for k0 in range(0, len(reqs), ADC_WPREP_MAX):
+        chunk = reqs[k0:k0 + ADC_WPREP_MAX]
+        items = (WPrepItem * len(chunk))()
+        for it, (weight, mode, cin_pad, ci_off, ci_cnt) in zip(items, chunk):
+            w = weight.detach()
+            if not w.is_contiguous():
+                w = w.contiguous()
+            co, ci = w.shape[:2]
+            oc = ci_cnt if mode else co
+            hi = torch.empty((9, _r16(oc), cin_pad), device=w.device, dtype=torch.bfloat16)
+            lo = torch.empty_like(hi) if _split() else None
+            it.w, it.out, it.out_lo = w.data_ptr(), hi.data_ptr(), _ptr(lo)
+            it.cout, it.cin, it.ci_off, it.ci_cnt, it.cin_pad, it.mode = co, ci, ci_off, ci_cnt, cin_pad, mode
+            outs.append((hi, lo, w))            # keep the (possibly copied) source alive until the launch is enqueued
+        check(lib.adc_conv3x3_prep_weights_batch(ctypes.cast(items, ctypes.c_void_p), len(chunk), _stream()),
+              "adc_conv3x3_prep_weights_batch")
+    return [(h, l) for h, l, _ in outs]
+
+
 def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=None, out_off=0, out_f32=False, out_pad=None,
                out_zero_to=0):
     """3x3 / pad 1 convolution on the tensor cores.  Channels [x_off, x_off+cin) of ``act`` are read (cin a multiple of 16,
@@ -237,17 +263,19 @@ def upsample_into(src, c, dst, dst_off, src_off=0):
     return dst
 
 
-def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None, act_off=0, slope=0.0):
-    """out[:, out_off:out_off+c] = d(act) * (sum over the up-sampling children of ``a`` + ``b``); see adc_nhwc_grad_assemble."""
+def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None, act_off=0, slope=0.0, colsum=False):
+    """out[:, out_off:out_off+c] = d(act) * (sum over the up-sampling children of ``a`` + ``b``); see adc_nhwc_grad_assemble.
+    colsum=True also returns the per-channel sum of the result over all pixels (fp32 [c]: a bias gradient) from the same pass."""
     from ._lib import lib, check
     z = lambda t: (t.hi.data_ptr(), _ptr(t.lo), t.cs) if t is not None else (None, None, 0)
     ah, al, ast = z(a)
     bh, bl, bst = z(b)
+    part = torch.empty((lib.adc_nhwc_grad_assemble_parts(), c), device=out.hi.device, dtype=torch.float32) if colsum else None
     check(lib.adc_nhwc_grad_assemble(ah, al, ast, a_off, a.h if a is not None else 0, a.w if a is not None else 0, bh, bl, bst, b_off,
                                      act.hi.data_ptr() if act is not None else None, act.cs if act is not None else 0, act_off,
-                                     float(slope), out.hi.data_ptr(), _ptr(out.lo), out.cs, out_off, out.n, c, out.h, out.w, _stream()),
-          "adc_nhwc_grad_assemble")
-    return out
+                                     float(slope), out.hi.data_ptr(), _ptr(out.lo), out.cs, out_off, out.n, c, out.h, out.w, _ptr(part),
+                                     _stream()), "adc_nhwc_grad_assemble")
+    return (out, part.sum(0)) if colsum else out
 
 
 def colsum(g, c, off=0):
@@ -288,6 +316,81 @@ def ged_head_bwd(x9, x0d, weight, gy, x10, glli, g9, need_x0d):
                                _ptr(g9.lo), g9.cs, _ptr(gx0d), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n, oc, h, w, _stream()),
           "adc_ged_head_bwd")
     return gx0d, dw, db
+
+
+# ---- "quad" (pixel-shuffle) form of the full-resolution thin layers (csrc/ged_quad.cu) ---------------------------------------
+_QUAD_MAPS = {}
+
+
+def quad_maps(device):
+    """Constant 0/1 tensors [4 parities, 9 low-resolution taps, 9 original taps] of the two quad identities:
+    'up': conv3x3(up2(x))[2i+py] tap u falls on low-resolution row i + (py+u-1)//2                     (conv10 after the up-sampling)
+    's2': d/dx of conv3x3-stride-2 at x row 2i+py receives output row i + (py+1-u)/2 when py+1-u is even  (conv1 data gradient)"""
+    key = str(device)
+    if key not in _QUAD_MAPS:
+        up = torch.zeros(4, 9, 9)
+        s2 = torch.zeros(4, 9, 9)
+        for py in range(2):
+            for px in range(2):
+                for u in range(3):
+                    for v in range(3):
+                        a, b = (py + u - 1) // 2 + 1, (px + v - 1) // 2 + 1
+                        up[py * 2 + px, a * 3 + b, u * 3 + v] = 1.0
+                        if (py + 1 - u) % 2 == 0 and (px + 1 - v) % 2 == 0:
+                            a, b = (py + 1 - u) // 2 + 1, (px + 1 - v) // 2 + 1
+                            s2[py * 2 + px, a * 3 + b, u * 3 + v] = 1.0
+        _QUAD_MAPS[key] = (up.to(device), s2.to(device))
+    return _QUAD_MAPS[key]
+
+
+def ged_pack_input(xout_d, cout_d, rgb, dst):
+    """torch.cat((xout_d, rgb, cout_d), 1) + NCHW->NHWC + bf16 (hi, lo) split in one pass, into channels [0,16) of ``dst``."""
+    from ._lib import lib, check
+    _need_cuda(xout_d)
+    n, _, h, w = xout_d.shape
+    xout_d, cout_d = xout_d.contiguous(), cout_d.contiguous()
+    if rgb.stride(3) != 1 or rgb.stride(2) != w or rgb.stride(1) != h * w:
+        rgb = rgb.contiguous()
+    check(lib.adc_ged_pack_input(xout_d.data_ptr(), cout_d.data_ptr(), rgb.data_ptr(), rgb.stride(0) if n > 1 else 3 * h * w,
+                                 dst.hi.data_ptr(), _ptr(dst.lo), dst.cs, n, h, w, _stream()), "adc_ged_pack_input")
+    return dst
+
+
+def quad_head_finish(q, x0d, weight, bias, h, w):
+    from ._lib import lib, check
+    oc = weight.shape[0]
+    out = torch.empty((q.n, oc, h, w), device=x0d.device, dtype=torch.float32)
+    check(lib.adc_quad_head_finish(q.hi.data_ptr(), q.cs, x0d.data_ptr(), weight.detach().contiguous().data_ptr(),
+                                   bias.detach().contiguous().data_ptr(), out.data_ptr(), q.n, oc, h, w, _stream()), "adc_quad_head_finish")
+    return out
+
+
+def quad_head_bwd_prep(gy, x10, x0d, gq):
+    """Fills channels [0,8) of ``gq`` (low-resolution NHWC bf16 pair) and returns the summed [oc, 10] x0_d-channel weight / bias gradient."""
+    from ._lib import lib, check
+    n, oc, h, w = gy.shape
+    parts = torch.empty((lib.adc_quad_head_bwd_prep_parts(), oc, 10), device=gy.device, dtype=torch.float32)
+    check(lib.adc_quad_head_bwd_prep(gy.contiguous().data_ptr(), x10.data_ptr(), x0d.data_ptr(), gq.hi.data_ptr(), _ptr(gq.lo), gq.cs,
+                                     parts.data_ptr(), n, oc, h, w, _stream()), "adc_quad_head_bwd_prep")
+    return parts.sum(0)
+
+
+def quad_unshuffle(q, k, h, w):
+    """[N][H1+2][W1+2][4k] fp32 parity channels -> [k, N, H, W] fp32."""
+    from ._lib import lib, check
+    out = torch.empty((k, q.n, h, w), device=q.hi.device, dtype=torch.float32)
+    check(lib.adc_quad_unshuffle(q.hi.data_ptr(), q.cs, out.data_ptr(), q.n, k, h, w, _stream()), "adc_quad_unshuffle")
+    return out
+
+
+def ged_head_bwd_x0d(gy, x10, glli, weight):
+    from ._lib import lib, check
+    n, oc, h, w = gy.shape
+    gx0d = torch.empty((n, 1, h, w), device=gy.device, dtype=torch.float32)
+    glli = glli.contiguous() if glli is not None else None
+    check(lib.adc_ged_head_bwd_x0d(gy.contiguous().data_ptr(), x10.data_ptr(), _ptr(glli), glli.shape[1] if glli is not None else 0,
+                                   weight.detach().contiguous().data_ptr(), gx0d.data_ptr(), n, oc, h, w, _stream()), "adc_ged_head_bwd_x0d")
+    return gx0d
 
 
 def cached_weights(conv, embed_1x1=False, cin_pad=None):

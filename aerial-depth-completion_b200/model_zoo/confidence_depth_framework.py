@@ -299,7 +299,7 @@ class GEDNet(nn.Module):
             # conv1..conv10 forward + backward on the hand-written tcgen05 kernels (one autograd node, NHWC bf16 / bf16x3)
             from .. import tc_train
             want = bool(build_conf_input) and self.out_channels == 1
-            x10, last_layer_input = tc_train.ged_dense(self, xout_d, cout_d, x0_rgb.contiguous(), x0_d.contiguous(), want)
+            x10, last_layer_input = tc_train.ged_dense(self, xout_d, cout_d, x0_rgb, x0_d.contiguous(), want)
             features = None
             if build_conf_input:
                 features = torch.cat((last_layer_input, xout_d, cout_d, x10), 1) if want else torch.sigmoid(x10[:, 1:2, :, :])

@@ -46,6 +46,9 @@ class _Plan:
         self.cat6 = A(4, 192)          # [up(x5) 80 | x4 80 | 0...]
         self.x5 = A(5, 128)
         self.x6, self.x7, self.x8, self.x9 = A(4, 64), A(3, 64), A(2, 64), A(1, 64)
+        # conv10 in its quad form (exact 2x up-sampling only): 4 parity channels per output channel at x9's resolution, fp32
+        self.quad = h % 2 == 0 and w % 2 == 0
+        self.q10 = A(1, 16, dtype=torch.float32) if self.quad else None
         self.bwd = None
         self.forward_id = 0
 
@@ -62,7 +65,9 @@ class _Plan:
             b["G5"] = A(5, 128)
             for k, lvl in (("4", 4), ("3", 3), ("2", 2), ("1", 1)):
                 b["gx" + k], b["G" + k] = A(lvl, 128), A(lvl, 128)
-            b["gin0"] = A(0, 16, dtype=torch.float32)
+            b["qin0"] = A(1, 16, dtype=torch.float32)      # conv1's data gradient as 4 parity channels x {xout_d, cout_d}
+            if self.quad:
+                b["gq"], b["G9pre"] = A(1, 64), A(1, 64)
             self.bwd = b
         return self.bwd
 
@@ -79,14 +84,54 @@ def _prep(weight, cin_pad, mode=0):
     return dense.prep_conv3x3_weights(weight, flip_transpose=mode, cin_pad=cin_pad)
 
 
-def _dgrad_s1(G, weight, out, lo, hi):
-    """Channels [lo, hi) of the input gradient of a stride-1 layer with Parameter ``weight`` [Cout, Cin, 3, 3] from its output
-    gradient ``G`` (all of G's channels are contracted; pad channels are zeros)."""
+def _dgrad_chunks(lo, hi):
+    """Output-channel chunks of a stride-1 data gradient: the row-segment kernel's shared-memory budget takes 64 output channels
+    in the split mode, 128 otherwise."""
     step = 64 if dense._split() else 128
-    for a in range(lo, hi, step):
-        b = min(a + step, hi)
-        wp = _prep(weight[:, a:b], G.cs, 1)
+    return [(a, min(a + step, hi)) for a in range(lo, hi, step)]
+
+
+def _dgrad_reqs(weight, cin_pad, lo, hi):
+    """Weight-preparation requests (dense.prep_conv3x3_weights_batch) of _dgrad_s1 for the same arguments."""
+    return [(weight, 1, cin_pad, a, b - a) for a, b in _dgrad_chunks(lo, hi)]
+
+
+def _dgrad_s1(G, weight, out, lo, hi, prepped=None):
+    """Channels [lo, hi) of the input gradient of a stride-1 layer with Parameter ``weight`` [Cout, Cin, 3, 3] from its output
+    gradient ``G`` (all of G's channels are contracted; pad channels are zeros).  ``prepped``: the prepared weights of
+    _dgrad_reqs(weight, G.cs, lo, hi) if the caller batched them."""
+    if prepped is None:
+        prepped = dense.prep_conv3x3_weights_batch(_dgrad_reqs(weight, G.cs, lo, hi))
+    for (a, b), wp in zip(_dgrad_chunks(lo, hi), prepped):
         dense.conv3x3_tc(G, G.cs, wp, None, b - a, 1, 0, out=out, out_off=a, out_zero_to=64 if a + 64 <= out.cs else 0)
+
+
+def _quad_head_weights(w10):
+    """[oc, 33, 3, 3] -> [4*oc, 32, 3, 3]: per parity (py, px) of the output pixel, the taps of conv10 that read the same pixel of
+    x9 through the 2x nearest up-sampling, summed (row (2py+px)*oc + o)."""
+    oc = w10.shape[0]
+    up, _ = dense.quad_maps(w10.device)
+    return torch.einsum("qst,oct->qocs", up, w10[:, :32].reshape(oc, 32, 9)).reshape(4 * oc, 32, 3, 3)
+
+
+def _quad_head_backward(P, b, w10, wq_prepped, g_x10, x10, x0_d, g_lli, need_x0d):
+    """Backward of the quad conv10: G9 (pre-activation gradient of conv9's output) into b['G9']; returns (g_x0d | None, dW, db,
+    bias gradient of conv9)."""
+    oc = w10.shape[0]
+    gq = b["gq"]
+    s = dense.quad_head_bwd_prep(g_x10, x10, x0_d, gq)                    # [oc, 10]: x0_d-channel weight gradient | bias gradient
+    _dgrad_s1(gq, None, b["G9pre"], 0, 32, prepped=wq_prepped)
+    extra = None
+    if g_lli is not None:      # gradient of the feature tensor cat(up(x9), x0_d): its first 32 channels sum over the 2x2 children
+        import torch.nn.functional as F
+        extra = dense.to_nhwc_bf16(F.avg_pool2d(g_lli[:, :32], 2) * 4.0, cpad=32, pad=True)
+    _, gb9 = dense.grad_assemble(b["G9"], 32, a=b["G9pre"], b=extra, act=P.x9, slope=0.2, colsum=True)
+    dwq = dense.conv3x3_wgrad_tc(gq, P.x9, 32, 4 * oc, cin_pad=32)         # [4*oc, 32, 3, 3]
+    up, _ = dense.quad_maps(w10.device)
+    dw = torch.einsum("qst,qocs->oct", up, dwq.reshape(4, oc, 32, 9)).reshape(oc, 32, 3, 3)
+    dw = torch.cat((dw, s[:, :9].reshape(oc, 1, 3, 3)), 1)
+    g_x0d = dense.ged_head_bwd_x0d(g_x10, x10, g_lli, w10) if need_x0d else None
+    return g_x0d, dw, s[:, 9].contiguous(), gb9
 
 
 class GEDDenseTC(torch.autograd.Function):
@@ -99,26 +144,37 @@ class GEDDenseTC(torch.autograd.Function):
         W = params[0::2]
         Bz = params[1::2]
         c3 = dense.conv3x3_tc
-        dense.to_nhwc_bf16(torch.cat((xout_d, rgb, cout_d), 1), cpad=16, dst=P.in0, dst_off=0)
+        dense.ged_pack_input(xout_d, cout_d, rgb, P.in0)
+        oc = W[9].shape[0]
+        # every layer's weights -> bf16 (hi, lo) [9][Cout16][Cin_pad] in ONE launch
+        reqs = [(W[i], 0, cp, 0, W[i].shape[1]) for i, cp in enumerate((16, 80, 80, 80, 80, 192, 192, 192, 128))]
+        if P.quad:
+            reqs.append((_quad_head_weights(W[9]), 0, 64, 0, 32))
+        wp = dense.prep_conv3x3_weights_batch(reqs)
         # encoder: 3x3 stride 2 + ReLU, each output lands in the concat buffer of the decoder layer that reuses it
-        c3(P.in0, 16, _prep(W[0], 16), Bz[0], 80, 2, _RELU, out=P.cat9, out_off=32)
-        c3(P.cat9, 80, _prep(W[1], 80), Bz[1], 80, 2, _RELU, x_off=32, out=P.cat8, out_off=64)
-        c3(P.cat8, 80, _prep(W[2], 80), Bz[2], 80, 2, _RELU, x_off=64, out=P.cat7, out_off=64)
-        c3(P.cat7, 80, _prep(W[3], 80), Bz[3], 80, 2, _RELU, x_off=64, out=P.cat6, out_off=80)
-        c3(P.cat6, 80, _prep(W[4], 80), Bz[4], 80, 2, _RELU, x_off=80, out=P.x5, out_off=0)
+        c3(P.in0, 16, wp[0], Bz[0], 80, 2, _RELU, out=P.cat9, out_off=32)
+        c3(P.cat9, 80, wp[1], Bz[1], 80, 2, _RELU, x_off=32, out=P.cat8, out_off=64)
+        c3(P.cat8, 80, wp[2], Bz[2], 80, 2, _RELU, x_off=64, out=P.cat7, out_off=64)
+        c3(P.cat7, 80, wp[3], Bz[3], 80, 2, _RELU, x_off=64, out=P.cat6, out_off=80)
+        c3(P.cat6, 80, wp[4], Bz[4], 80, 2, _RELU, x_off=80, out=P.x5, out_off=0)
         # decoder: nearest up-sampling into the slice, 3x3 stride 1 + LeakyReLU(0.2)
         dense.upsample_into(P.x5, 80, P.cat6, 0)
-        c3(P.cat6, 192, _prep(W[5], 192), Bz[5], 64, 1, _LEAKY, out=P.x6, out_zero_to=64)
+        c3(P.cat6, 192, wp[5], Bz[5], 64, 1, _LEAKY, out=P.x6, out_zero_to=64)
         dense.upsample_into(P.x6, 64, P.cat7, 0)
-        c3(P.cat7, 192, _prep(W[6], 192), Bz[6], 64, 1, _LEAKY, out=P.x7, out_zero_to=64)
+        c3(P.cat7, 192, wp[6], Bz[6], 64, 1, _LEAKY, out=P.x7, out_zero_to=64)
         dense.upsample_into(P.x7, 64, P.cat8, 0)
-        c3(P.cat8, 192, _prep(W[7], 192), Bz[7], 32, 1, _LEAKY, out=P.x8, out_zero_to=64)
+        c3(P.cat8, 192, wp[7], Bz[7], 32, 1, _LEAKY, out=P.x8, out_zero_to=64)
         dense.upsample_into(P.x8, 32, P.cat9, 0)
-        c3(P.cat9, 128, _prep(W[8], 128), Bz[8], 32, 1, _LEAKY, out=P.x9, out_zero_to=64)
+        c3(P.cat9, 128, wp[8], Bz[8], 32, 1, _LEAKY, out=P.x9, out_zero_to=64)
         # conv10 (33 -> 1 or 2 channels at full resolution): direct kernel, up-sampling folded into the addressing of x9
         x0_d = x0_d.contiguous()
-        x10 = dense.ged_head_fwd(P.x9, x0_d, W[9], Bz[9], h, w)
-        oc = W[9].shape[0]
+        if P.quad:
+            # quad form: a stride-1 convolution of x9 at its own resolution on the tensor cores (4 parity channels per output
+            # channel), then un-shuffle + x0_d taps + bias + LeakyReLU at full resolution
+            c3(P.x9, 64, wp[9], None, 4 * oc, 1, 0, out=P.q10)
+            x10 = dense.quad_head_finish(P.q10, x0_d, W[9], Bz[9], h, w)
+        else:
+            x10 = dense.ged_head_fwd(P.x9, x0_d, W[9], Bz[9], h, w)
         lli = None
         if want_lli:       # the confidence head wants cat(up(x9), x0_d) as features: materialise it only then
             if P.cat10 is None:
@@ -142,35 +198,62 @@ class GEDDenseTC(torch.autograd.Function):
         hs, ws, oc = P.hs, P.ws, ctx.oc
         wg, wgb, asm, cs = dense.conv3x3_wgrad_tc, dense.conv3x3_wgrad_box_tc, dense.grad_assemble, dense.colsum
         gW, gB = [None] * 10, [None] * 10
-        # conv10 (LeakyReLU on the output too, confidence_depth_framework.py:506): direct kernels; produce G9 for conv9.
+        dev = x10.device
+        # all data-gradient weights of the step (transposed / flipped, per output-channel chunk) in ONE launch
+        dec_cin = {8: 112, 7: 144, 6: 144, 5: 160}
+        reqs, where = [], {}
+        def add(key, rs):
+            where[key] = (len(reqs), len(reqs) + len(rs))
+            reqs.extend(rs)
+        for i in (8, 7, 6, 5):
+            add(i, _dgrad_reqs(W[i], 64, 0, dec_cin[i]))
+        for i in (4, 3, 2, 1):
+            add(i, [(W[i], 2, 80, 0, 80)])
+        # conv1's data gradient is needed for xout_d and cout_d only (channels 0 and 4 of its input): quad form = a stride-1
+        # convolution of G1 at ITS resolution with 4 parity x 2 output channels (dense.quad_maps 's2')
+        _, s2 = dense.quad_maps(dev)
+        Wd = torch.einsum("qst,ckt->qkcs", s2, torch.stack((W[0][:, 0], W[0][:, 4]), 1).reshape(80, 2, 9)).reshape(8, 80, 3, 3)
+        add(0, [(Wd, 0, 128, 0, 80)])
+        if P.quad:
+            add(9, _dgrad_reqs(_quad_head_weights(W[9]), 64, 0, 32))
+        prepped = dense.prep_conv3x3_weights_batch(reqs)
+        wp = {k: prepped[a:b_] for k, (a, b_) in where.items()}
+        # conv10 (LeakyReLU on the output too, confidence_depth_framework.py:506); produces G9 for conv9.
         # Channel 32 of its input is x0_d itself: raw data for the depth-completion net, but the PREDICTED depth when this net is
         # the loss net (confidence_depth_framework.py:230) -- then its gradient is needed too
-        g_x0d, gW[9], gB[9] = dense.ged_head_bwd(P.x9, x0_d, W[9], g_x10, x10, g_lli, b["G9"], ctx.needs_input_grad[3])
-        # decoder layers 9..6: G_k = leaky'(x_k) * sum_children(grad of up(x_k))
+        if P.quad:
+            g_x0d, gW[9], gB[9], gb9 = _quad_head_backward(P, b, W[9], wp[9], g_x10, x10, x0_d, g_lli, ctx.needs_input_grad[3])
+        else:
+            g_x0d, gW[9], gB[9] = dense.ged_head_bwd(P.x9, x0_d, W[9], g_x10, x10, g_lli, b["G9"], ctx.needs_input_grad[3])
+            gb9 = cs(b["G9"], 32)
+        # decoder layers 9..6: G_k = leaky'(x_k) * sum_children(grad of up(x_k)); the bias gradient (per-channel sum of G_k) comes
+        # out of the same pass
         dec = ((8, "G9", None, P.x9, 32, P.cat9, 112, "gcat9"), (7, "G8", "gcat9", P.x8, 32, P.cat8, 144, "gcat8"),
                (6, "G7", "gcat8", P.x7, 64, P.cat7, 144, "gcat7"), (5, "G6", "gcat7", P.x6, 64, P.cat6, 160, "gcat6"))
         for i, gname, src, xk, co, catk, cin, gcat in dec:
-            G = asm(b[gname], co, a=b[src], act=xk, slope=0.2) if src is not None else b[gname]
-            gB[i] = cs(G, co)
+            if src is not None:
+                G, gB[i] = asm(b[gname], co, a=b[src], act=xk, slope=0.2, colsum=True)
+            else:
+                G, gB[i] = b[gname], gb9
             gW[i] = wg(G, catk, cin, co, cin_pad=cin)
-            _dgrad_s1(G, W[i], b[gcat], 0, cin)
+            _dgrad_s1(G, W[i], b[gcat], 0, cin, prepped=wp[i])
         # encoder layers 5..1 (stride 2, ReLU): G5 from the up-sampling children only, G4..G1 = relu' * (dgrad + skip gradient)
-        G = asm(b["G5"], 80, a=b["gcat6"], act=P.x5, slope=0.0)
+        G, gb = asm(b["G5"], 80, a=b["gcat6"], act=P.x5, slope=0.0, colsum=True)
         enc = ((4, P.cat6, 80, 4, "gx4", "G4", "gcat6", 80), (3, P.cat7, 64, 3, "gx3", "G3", "gcat7", 64),
                (2, P.cat8, 64, 2, "gx2", "G2", "gcat8", 64), (1, P.cat9, 32, 1, "gx1", "G1", "gcat9", 32))
         for i, xin, xoff, lvl, gxn, gn, gcat, goff in enc:
-            gB[i] = cs(G, 80)
+            gB[i] = gb
             gW[i] = wgb(G, xin, 80, 80, 2, x_off=xoff, cin_pad=80)
-            dense.conv3x3_dgrad_s2_tc(G, 80, _prep(W[i], 80, 2), 80, hs[lvl], ws[lvl], out=b[gxn], out_off=0)
-            G = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0)
-        gB[0] = cs(G, 80)
+            dense.conv3x3_dgrad_s2_tc(G, 80, wp[i][0], 80, hs[lvl], ws[lvl], out=b[gxn], out_off=0)
+            G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True)
+        gB[0] = gb
         gW[0] = wgb(G, P.in0, 5, 80, 2, cin_pad=16)
-        dense.conv3x3_dgrad_s2_tc(G, 80, _prep(W[0], 80, 2), 5, hs[0], ws[0], out=b["gin0"], out_off=0)
-        gin = dense.to_nchw_f32(b["gin0"], 5)
+        dense.conv3x3_tc(G, 128, wp[0][0], None, 8, 1, 0, out=b["qin0"])
+        gin = dense.quad_unshuffle(b["qin0"], 2, hs[0], ws[0])
         grads = []
         for i in range(10):
             grads += [gW[i], gB[i]]
-        return (gin[:, 0:1], gin[:, 4:5], None, g_x0d, None, None, *grads)
+        return (gin[0].unsqueeze(1), gin[1].unsqueeze(1), None, g_x0d, None, None, *grads)
 
 
 def ged_dense(net, xout_d, cout_d, rgb, x0_d, want_lli):

@@ -160,6 +160,18 @@ int adc_nhwc_to_nchw_f32(const void* src, int src_is_f32, float* dst, int N, int
 size_t adc_conv3x3_weight_elems(int cout, int cin_pad);
 int adc_conv3x3_prep_weights(const float* w, void* out_bf16, void* out_lo, int cout, int cin, int cin_pad, int flip_transpose,
                              adc_stream_t stream);
+/* Batched form: up to ADC_WPREP_MAX conversions in one launch.  Item k converts input channels [ci_off, ci_off+ci_cnt) of the
+ * fp32 tensor w [cout][cin][3][3]; mode 0: out [9][round16(cout)][cin_pad] (forward weights); mode 1 / 2: transposed
+ * [9][round16(ci_cnt)][cin_pad] with flipped / unflipped taps (data-gradient weights, contraction over cout <= cin_pad). */
+#define ADC_WPREP_MAX 40
+typedef struct {
+    const float* w;
+    void* out;
+    void* out_lo; /* NULL: plain bf16 */
+    int cout, cin, ci_off, ci_cnt, cin_pad, mode;
+} adc_wprep_item_t;
+int adc_conv3x3_prep_weights_batch(const adc_wprep_item_t* items, int n, adc_stream_t stream);
+
 /* act: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 sigmoid.  stride 1 or 2, padding 1.  x_lo/w_lo non-NULL selects the bf16x3 split
  * mode: operands are (hi, lo) bf16 pairs, hi*hi + lo*hi + hi*lo accumulated in fp32 (fp32-grade parity, 3 MMAs per product). */
 int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
@@ -199,12 +211,15 @@ int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, i
  *   up-sample + torch.cat, confidence_depth_framework.py:488-504).
  * adc_nhwc_grad_assemble: out = d(act) * ( sum over the up-sampling children of A (at Hd x Wd, identity if equal) + B ),
  *   d(act) = 1 where act > 0 else slope: the backward of up-sample / cat / ReLU / LeakyReLU in one pass; a, b, act optional.
+ *   colsum_part (optional): [adc_nhwc_grad_assemble_parts()][C] per-block sums of the output over its pixels; their sum over
+ *   dim 0 in index order is the bias gradient of the layer whose activation is `act` (saves adc_nhwc_colsum's extra read).
  * adc_nhwc_colsum: per-channel sum over all pixels (bias gradient), deterministic two-stage reduction. */
 int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_stride, int src_off, void* dst, void* dst_lo, int dst_stride,
                               int dst_off, int N, int C, int Hs, int Ws, int Hd, int Wd, adc_stream_t stream);
 int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_off, int Hd, int Wd, const void* b, const void* b_lo,
                            int b_stride, int b_off, const void* act, int act_stride, int act_off, float slope, void* out, void* out_lo,
-                           int out_stride, int out_off, int N, int C, int H, int W, adc_stream_t stream);
+                           int out_stride, int out_off, int N, int C, int H, int W, float* colsum_part, adc_stream_t stream);
+int adc_nhwc_grad_assemble_parts(void);
 size_t adc_nhwc_colsum_workspace_bytes(int C);
 int adc_nhwc_colsum(const void* g, const void* g_lo, int g_stride, int g_off, int N, int C, int H, int W, float* out, void* workspace,
                     adc_stream_t stream);
@@ -220,6 +235,32 @@ size_t adc_ged_head_bwd_workspace_bytes(int oc);
 int adc_ged_head_bwd(const void* x9, const void* x9_lo, int x9_stride, int H1, int W1, const float* x0d, const float* w, const float* gy,
                      const float* x10, const float* glli, int glli_ch, void* g9, void* g9_lo, int g9_stride, float* gx0d, float* dw,
                      float* db, void* workspace, int N, int oc, int H, int W, adc_stream_t stream);
+int adc_ged_head_bwd_x0d(const float* gy, const float* x10, const float* glli, int glli_ch, const float* w, float* gx0d, int N, int oc,
+                         int H, int W, adc_stream_t stream);
+
+/* ---- "quad" (pixel-shuffle) form of GEDNet's two full-resolution thin layers (confidence_depth_framework.py:442,452,469-506).
+ * With the exact 2x nearest up-sampling of x9, conv10(up(x9)) at pixel (2i+py, 2j+px) only touches a 2x2 block of x9: it is a
+ * stride-1 3x3 convolution of x9 at ITS resolution with 4 parity channels per output channel (weights = taps of conv10 that fall
+ * on the same x9 pixel, summed) and runs on adc_conv3x3_s1_tc_v2 / adc_conv3x3_wgrad_tc on a quarter of the pixels.  Read
+ * backwards, the same identity turns the data gradient of conv1 (3x3, stride 2) into a stride-1 convolution of its output
+ * gradient with 4 parity channels per input channel.  These entry points are the elementwise remainder:
+ * adc_ged_pack_input:     (xout_d [N][1][H][W], rgb [N][3][H][W] with batch stride, cout_d) -> zero-bordered NHWC bf16 (hi, lo)
+ *                         channels {xout_d, r, g, b, cout_d, 0 x 11} of a tensor with dst_stride >= 16 channels per pixel.
+ * adc_quad_head_finish:   out[n][o][2i+py][2j+px] = LeakyReLU_0.2( q[n][i+1][j+1][(2py+px)*oc + o] + bias[o]
+ *                         + sum_uv w[o][32][u][v] * x0d[n][2i+py+u-1][2j+px+v-1] ); q fp32 zero-bordered NHWC, w [oc][33][3][3].
+ * adc_quad_head_bwd_prep: gpre = gy * LeakyReLU'(x10) -> gq (bf16 hi, lo; channels (2py+px)*oc + o, up to 8 written) and
+ *                         part[adc_quad_head_bwd_prep_parts()][oc][10]: [0,9) weight gradient of the x0_d channel, [9] bias
+ *                         gradient (sum over dim 0 in index order = deterministic).
+ * adc_quad_unshuffle:     out[k][n][2i+py][2j+px] = q[n][i+1][j+1][(2py+px)*K + k], K in {1,2}; any H, W (H1 = ceil(H/2)). */
+int adc_ged_pack_input(const float* xout, const float* cout, const float* rgb, long long rgb_batch_stride, void* dst, void* dst_lo,
+                       int dst_stride, int N, int H, int W, adc_stream_t stream);
+int adc_quad_head_finish(const float* q, int q_stride, const float* x0d, const float* w, const float* bias, float* out, int N, int oc, int H,
+                         int W, adc_stream_t stream);
+int adc_quad_head_bwd_prep_parts(void);
+int adc_quad_head_bwd_prep(const float* gy, const float* x10, const float* x0d, void* gq, void* gq_lo, int gq_stride, float* part, int N,
+                           int oc, int H, int W, adc_stream_t stream);
+int adc_quad_unshuffle(const float* q, int q_stride, float* out, int N, int K, int H, int W, adc_stream_t stream);
+
 
 #ifdef __cplusplus
 }
