@@ -106,6 +106,11 @@ SIGNATURES = {
     "adc_ged_head_bwd": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp,
                                  c_int, c_int, c_int, c_int, _vp]),
     "adc_ged_head_bwd_x0d": (c_int, [_vp, _vp, _vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_ged_pack_im2col": (c_int, [_vp, _vp, _vp, c_ll, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_conv1x1_tc_v2": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, _vp]),
+    "adc_conv1x1_wgrad_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     _vp]),
     "adc_ged_pack_input": (c_int, [_vp, _vp, _vp, c_ll, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_quad_head_finish": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_quad_head_bwd_prep_parts": (c_int, []),

@@ -217,6 +217,7 @@ struct ConvParamsV2 {
     int nstages;             // 2..8 pipeline stages
     int tma_store;           // 1: bf16 output tile staged in shared memory and written by TMA bulk stores (slice width 64)
     int dbg;                 // timing experiments: 1 = epilogue skips its global stores, 2 = epilogue skipped entirely
+    int taps1;               // 1: only the centre tap exists (a 1x1 convolution / plain GEMM over the flat pixels)
 };
 
 constexpr int kSegRows = 130;
@@ -242,14 +243,22 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     const int kblocks = (p.cin + 63) / 64;
-    const int steps = kblocks * 3;
+    const int tpk = p.taps1 ? 1 : 9;                  // weight tiles per 64-channel block
+    const int tps = p.taps1 ? 1 : 3;                  // ... per pipeline step
+    const int steps = kblocks * tps;
     const int nst = p.nstages;
     const int b_tile = p.npad * 128;                  // one tap's weight tile (multiple of 1024: npad % 8 == 0)
-    const int w_all = 9 * kblocks * b_tile;           // every weight tile of the layer (resident mode)
-    // shared memory: [resident weights hi | lo] then nst stages of [A seg hi | (B 3 taps hi) | A seg lo | (B 3 taps lo)]
-    const int res_bytes = p.resident ? w_all * (p.split ? 2 : 1) : 0;
-    const int half = kSegBytes + (p.resident ? 0 : 3 * b_tile);
-    const int stage_bytes = p.split ? 2 * half : half;
+    const int w_all = tpk * kblocks * b_tile;         // every weight tile of the layer (resident mode)
+    // Split (bf16x3) mode: the hi and lo tiles of a tap sit back to back ([hi rows | lo rows]) so ONE B descriptor of
+    // N = 2*npad rows covers both: A_hi x [W_hi | W_lo] and A_lo x [W_hi | W_lo] = 2 MMAs per (tap, 16 channels) into two
+    // accumulator halves (W_hi products | W_lo products) that the epilogue adds.  Measured (tools/micro/mma_rate.cu): an
+    // M = 128 MMA with shared-memory operands costs max(91, 38 + N/2) cycles whatever it computes, so 2 MMAs of N <= 128 beat
+    // the 3 MMAs (hi*hi, lo*hi, hi*lo) of the first version by ~1.45x, and the lo*lo term comes for free.
+    // shared memory: [resident weights: tile (kb, tap) = hi | lo] then nst stages of [A seg hi | A seg lo | B tap 0..2 (hi | lo)]
+    const int mult = p.split ? 2 : 1;
+    const int res_bytes = p.resident ? w_all * mult : 0;
+    const int stage_bytes = mult * (kSegBytes + (p.resident ? 0 : tps * b_tile));
+    const int b_off = mult * kSegBytes;               // weights of a streamed stage
     uint8_t* stages = smem + res_bytes;
     // output staging for the TMA store: one (two in split mode) 128-pixel x 64-channel bf16 tile, 128-byte swizzled
     uint8_t* ostage = stages + nst * stage_bytes;
@@ -259,8 +268,9 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int acc_cols = mult * p.npad;               // one accumulator buffer
     uint32_t ncols = 32;
-    while ((int)ncols < 2 * p.npad) ncols <<= 1;
+    while ((int)ncols < 2 * acc_cols) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) {
@@ -288,9 +298,11 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
             if (p.resident) {      // all weight tiles once: they stay in shared memory for every tile of this CTA
                 mbar_expect_tx(&bars[20], (uint32_t)res_bytes);
                 for (int kb = 0; kb < kblocks; ++kb)
-                    for (int u = 0; u < 3; ++u) {
-                        tma_load_3d(smem + (kb * 9 + 3 * u) * b_tile, &map_w, &bars[20], kb * 64, 0, 3 * u);
-                        if (p.split) tma_load_3d(smem + w_all + (kb * 9 + 3 * u) * b_tile, &map_wl, &bars[20], kb * 64, 0, 3 * u);
+                    for (int t = 0; t < tpk; ++t) {
+                        uint8_t* wt = smem + (kb * tpk + t) * (mult * b_tile);
+                        const int tap = p.taps1 ? 4 : t;
+                        tma_load_3d(wt, &map_w, &bars[20], kb * 64, 0, tap);
+                        if (p.split) tma_load_3d(wt + b_tile, &map_wl, &bars[20], kb * 64, 0, tap);
                     }
             }
             int q = 0;
@@ -298,24 +310,27 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 const long long m0 = (long long)tile * 128;
                 for (int st = 0; st < steps; ++st, ++q) {
                     const int s = q % nst, use = q / nst;
-                    const int kb = st / 3, u = st % 3;
+                    const int kb = st / tps, u = p.taps1 ? 1 : st % 3;
                     mbar_wait(&bars[8 + s], (use & 1) ^ 1);
                     uint8_t* sa = stages + s * stage_bytes;
-                    mbar_expect_tx(&bars[s], (uint32_t)((kSegRows * 128 + (p.resident ? 0 : 3 * b_tile)) * (p.split ? 2 : 1)));
+                    mbar_expect_tx(&bars[s], (uint32_t)((kSegRows * 128 + (p.resident ? 0 : tps * b_tile)) * mult));
                     const long long f0 = m0 + (long long)(u - 1) * p.Wp - 1;
                     tma_load_2d(sa, &map_x, &bars[s], kb * 64, (int)f0);
-                    if (!p.resident) tma_load_3d(sa + kSegBytes, &map_w, &bars[s], kb * 64, 0, 3 * u);
-                    if (p.split) {
-                        tma_load_2d(sa + half, &map_xl, &bars[s], kb * 64, (int)f0);
-                        if (!p.resident) tma_load_3d(sa + half + kSegBytes, &map_wl, &bars[s], kb * 64, 0, 3 * u);
-                    }
+                    if (p.split) tma_load_2d(sa + kSegBytes, &map_xl, &bars[s], kb * 64, (int)f0);
+                    if (!p.resident)
+                        for (int v = 0; v < tps; ++v) {
+                            uint8_t* wt = sa + b_off + v * (mult * b_tile);
+                            const int tap = p.taps1 ? 4 : 3 * u + v;
+                            tma_load_3d(wt, &map_w, &bars[s], kb * 64, 0, tap);
+                            if (p.split) tma_load_3d(wt + b_tile, &map_wl, &bars[s], kb * 64, 0, tap);
+                        }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            const uint32_t idesc = make_idesc(128, p.npad);
+            const uint32_t idesc = make_idesc(128, acc_cols);
             const uint32_t sbase = base + res_bytes;
             if (p.resident) {
                 mbar_wait(&bars[20], 0);
@@ -326,29 +341,28 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 const int a = it & 1;
                 mbar_wait(&bars[18 + a], ((it >> 1) & 1) ^ 1);         // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(a * p.npad);
+                const uint32_t tacc = tmem_base + (uint32_t)(a * acc_cols);
                 for (int st = 0; st < steps; ++st, ++q) {
                     const int s = q % nst, use = q / nst;
-                    const int kb = st / 3, u = st % 3;
+                    const int kb = st / tps, u = p.taps1 ? 1 : st % 3;
                     mbar_wait(&bars[s], use & 1);
                     tc_fence_after();
                     const uint32_t sa = sbase + s * stage_bytes;
-#pragma unroll
-                    for (int v = 0; v < 3; ++v) {
+                    const int v0 = p.taps1 ? 1 : 0, v1 = p.taps1 ? 2 : 3;      // the centre tap reads the segment one row in
+                    for (int v = v0; v < v1; ++v) {
                         const uint32_t a_hi = sa + v * 128;
-                        const uint32_t b_hi = p.resident ? base + (kb * 9 + 3 * u + v) * b_tile : sa + kSegBytes + v * b_tile;
-                        const uint32_t b_lo = p.resident ? b_hi + w_all : b_hi + half;
+                        const int wslot = p.taps1 ? 0 : v;
+                        const uint32_t b_cat = p.resident ? base + (kb * tpk + (p.taps1 ? 0 : 3 * u + v)) * (mult * b_tile)
+                                                          : sa + b_off + wslot * (mult * b_tile);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_hi) + 2 * k, idesc, (st | v | k) != 0);
+                            umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_cat) + 2 * k, idesc,
+                                      !(st == 0 && v == v0 && k == 0));
                         if (p.split) {
-                            const uint32_t a_lo = a_hi + half;
+                            const uint32_t a_lo = a_hi + kSegBytes;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_bf16(tacc, make_desc_sw128_off(a_lo, 0) + 2 * k, make_desc<128>(b_hi) + 2 * k, idesc, 1);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_lo) + 2 * k, idesc, 1);
+                                umma_bf16(tacc, make_desc_sw128_off(a_lo, 0) + 2 * k, make_desc<128>(b_cat) + 2 * k, idesc, 1);
                         }
                     }
                     umma_commit(&bars[8 + s]);
@@ -377,7 +391,13 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
             for (int c0 = 0; c0 < c_end; c0 += 16) {
                 float v[16];
                 if (c0 < p.npad) {
-                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.npad + c0), v);
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_cols + c0), v);
+                    if (p.split) {      // + the W_lo products of the second accumulator half
+                        float v2[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_cols + p.npad + c0), v2);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -813,9 +833,9 @@ int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, in
 
 // Stride-1 3x3 convolution, v2 kernel (shared-memory tap reuse, persistent, double-buffered TMEM).  x and out are
 // zero-bordered NHWC tensors ([N][H+2][W+2][channels]); needs cin % 64 == 0.  Same split-mode convention as above.
-int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
-                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
-                         int N, int H, int W, int cin, int cout, int act, adc_stream_t stream) {
+static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo, const float* bias, void* out,
+                   void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to, int N, int H, int W, int cin, int cout, int act,
+                   int taps1, adc_stream_t stream) {
     if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) {
         adc::set_error("adc_conv3x3_s1_tc_v2: bad argument");
         return ADC_E_BADARG;
@@ -843,6 +863,7 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
     p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.out_lo = out_f32 ? nullptr : out_lo; p.bias = bias;
     p.ntiles = (int)((p.F + 127) / 128);
     p.out_zero_to = out_zero_to;
+    p.taps1 = taps1;
     { const char* e = getenv("ADC_V2_DBG"); p.dbg = e ? atoi(e) : 0; }
     CUtensorMap mx, mw, mxl, mwl;
     memset(&mxl, 0, sizeof(mxl));
@@ -865,7 +886,7 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
     auto make_w = [&](CUtensorMap* m, const void* base_) -> int {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)npad, 9};
         cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2 * npad};
-        cuuint32_t box[3] = {64, (cuuint32_t)npad, 3};
+        cuuint32_t box[3] = {64, (cuuint32_t)npad, 1};      // one tap per copy: hi and lo tiles interleave in shared memory
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base_), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -906,7 +927,7 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
     }
     // weights resident in shared memory if they fit next to >= 2 activation stages; otherwise streamed with every step
     const int kblocks = (cin + 63) / 64, mult = split ? 2 : 1;
-    const int w_all = 9 * kblocks * npad * 128;
+    const int w_all = (taps1 ? 1 : 9) * kblocks * npad * 128;
     const int ostage_bytes = p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0;
     const int budget = kSmemCap - 1024 - 256 - ostage_bytes;
     int smem;
@@ -920,7 +941,7 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
             p.nstages = nst_res > 8 ? 8 : nst_res;
             smem = w_all * mult + p.nstages * a_stage + ostage_bytes + 1024 + 256;
         } else {
-            const int st = (kSegBytes + 3 * npad * 128) * mult;
+            const int st = (kSegBytes + (taps1 ? 1 : 3) * npad * 128) * mult;
             p.resident = 0;
             p.nstages = budget / st > 8 ? 8 : budget / st;
             smem = p.nstages * st + ostage_bytes + 1024 + 256;
@@ -942,9 +963,25 @@ int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_of
         done = true;
     }
     const int grid = p.ntiles < sms ? p.ntiles : sms;
-    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_FPROP_V2, 2.0 * N * H * W * 9.0 * cin * cout);
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_FPROP_V2, 2.0 * N * H * W * (taps1 ? 1.0 : 9.0) * cin * cout);
     conv3x3_s1_tc_v2_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mx, mw, mxl, mwl, mo, mol, p);
     return adc::check_cuda(cudaGetLastError(), "conv3x3_s1_tc_v2_kernel launch");
+}
+
+int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
+                         const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
+                         int N, int H, int W, int cin, int cout, int act, adc_stream_t stream) {
+    return conv_v2(x, x_lo, x_stride, x_off, w, w_lo, bias, out, out_lo, out_f32, out_stride, out_off, out_zero_to, N, H, W, cin, cout, act, 0,
+                   stream);
+}
+
+// 1x1 convolution (a plain GEMM over the flat pixels of a zero-bordered NHWC tensor) on the same persistent kernel: only the
+// centre tap of the prepared [9][Cout16][Cin] weights is read (adc_conv3x3_prep_weights of a tensor whose other taps are zero).
+int adc_conv1x1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo, const float* bias, void* out,
+                      void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to, int N, int H, int W, int cin, int cout, int act,
+                      adc_stream_t stream) {
+    return conv_v2(x, x_lo, x_stride, x_off, w, w_lo, bias, out, out_lo, out_f32, out_stride, out_off, out_zero_to, N, H, W, cin, cout, act, 1,
+                   stream);
 }
 
 }  // extern "C"

@@ -26,7 +26,8 @@ struct WgradParams {
     int kp;               // pixels per K tile (64 or 128)
     int ktiles, groups, nstages, split;
     int bseg;             // bytes reserved per 64-channel x block ((kp+2) rows of 128 bytes, rounded up to 1024)
-    float* part;          // [groups][9][mrows][ncols]
+    float* part;          // [groups][9][mrows][ncols]  (single: [groups][1][mrows][ncols])
+    int single;           // 1: only the centre tap (dW[co][ci] = sum_p gy[p][co] * x[p][ci]: the weight gradient of a 1x1 convolution)
 };
 
 // MN-major SWIZZLE_128B operand: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout 2 <<61
@@ -51,7 +52,8 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);    // full[8], empty[8], done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int u = blockIdx.x % 3, g = blockIdx.x / 3;
+    const int u = p.single ? 1 : blockIdx.x % 3, g = p.single ? blockIdx.x : blockIdx.x / 3;
+    const int v0 = p.single ? 1 : 0, v1 = p.single ? 2 : 3, ntw = p.single ? 1 : 9;
     const int my_tiles = g < p.ktiles ? (p.ktiles - g + p.groups - 1) / p.groups : 0;
     uint32_t ncols_alloc = 32;
     while ((int)ncols_alloc < 3 * p.ncols) ncols_alloc <<= 1;
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
                 mbar_wait(&bars[s], use & 1);
                 tc_fence_after();
                 const uint32_t sa = base + s * stage_bytes, sb = sa + a_bytes;
-                for (int v = 0; v < 3; ++v) {
+                for (int v = v0; v < v1; ++v) {
                     const uint32_t tacc = tmem_base + (uint32_t)(v * p.ncols);
                     for (int k = 0; k < ksteps; ++k) {       // 16 pixels = 2 swizzle atoms = 2048 bytes per K step
                         const uint64_t da = make_desc_mn(sa + k * 2048, lbo_a);
@@ -124,8 +126,8 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
             mbar_wait(&bars[16], 0);
             tc_fence_after();
         }
-        for (int v = 0; v < 3; ++v) {
-            float* dst = p.part + (((long long)g * 9 + u * 3 + v) * p.mrows + row) * p.ncols;
+        for (int v = v0; v < v1; ++v) {
+            float* dst = p.part + (((long long)g * ntw + (p.single ? 0 : u * 3 + v)) * p.mrows + row) * p.ncols;
             for (int c0 = 0; c0 < p.ncols; c0 += 16) {
                 float r[16];
                 if (my_tiles > 0) {
@@ -264,13 +266,13 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
 
 // dW[co][ci][tap] = sum_g part[g][tap][co][ci]   (fixed order; reads coalesced along ci)
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int groups, int mrows,
-                                                              int ncols, int cout, int cin) {
-    const int total = 9 * cout * cin;
+                                                              int ncols, int cout, int cin, int ntaps) {
+    const int total = ntaps * cout * cin;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
         float acc = 0.f;
-        for (int g = 0; g < groups; ++g) acc += part[(((long long)g * 9 + tap) * mrows + co) * ncols + ci];
-        dw[((long long)co * cin + ci) * 9 + tap] = acc;
+        for (int g = 0; g < groups; ++g) acc += part[(((long long)g * ntaps + tap) * mrows + co) * ncols + ci];
+        dw[((long long)co * cin + ci) * ntaps + tap] = acc;
     }
 }
 
@@ -303,9 +305,9 @@ size_t adc_conv3x3_wgrad_tc_workspace_bytes(int cin_pad, int cout) {
 // x: zero-bordered NHWC bf16 [N][H+2][W+2][x_stride] (channels [x_off, x_off+cin_pad), cin_pad % 16 == 0, <= 160);
 // dw: fp32 [cout][cin][3][3] (the first cin of the cin_pad columns); workspace: adc_conv3x3_wgrad_tc_workspace_bytes().
 // Split (bf16x3) mode when gy_lo and x_lo are given: hi*hi + lo*hi + hi*lo accumulated in fp32.
-int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
-                         int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout,
-                         adc_stream_t stream) {
+static int wgrad_flat(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
+                      int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout, int single,
+                      adc_stream_t stream) {
     if (!gy || !x || !dw || !workspace || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || cin_pad < cin) {
         adc::set_error("adc_conv3x3_wgrad_tc: bad argument");
         return ADC_E_BADARG;
@@ -334,7 +336,8 @@ int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int g
     p.mb = cout > 64 ? 2 : 1;
     p.nb = (cin_pad + 63) / 64;
     p.split = gy_lo != nullptr;
-    p.groups = wgrad_groups();
+    p.single = single;
+    p.groups = single ? sm_count() : wgrad_groups();
     p.part = reinterpret_cast<float*>(workspace);
     const int budget = kSmemCap - 1024;
     for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
@@ -380,13 +383,27 @@ int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int g
         attr_done = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    adc::Prof prof(st, adc::KIND_TC_WGRAD, 2.0 * N * H * W * 9.0 * cin_pad * cout);
+    adc::Prof prof(st, adc::KIND_TC_WGRAD, 2.0 * N * H * W * (single ? 1.0 : 9.0) * cin_pad * cout);
     adc::count_launches(1);
-    conv3x3_wgrad_tc_kernel<<<3 * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
+    conv3x3_wgrad_tc_kernel<<<(single ? 1 : 3) * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
     if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_tc_kernel launch"))) return rc;
-    const int total = 9 * cout * cin;
-    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin);
+    const int total = (single ? 1 : 9) * cout * cin;
+    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin, single ? 1 : 9);
     return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");
+}
+
+int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
+                         int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout,
+                         adc_stream_t stream) {
+    return wgrad_flat(gy, gy_lo, gy_stride, gy_off, x, x_lo, x_stride, x_off, dw, workspace, N, H, W, cin, cin_pad, cout, 0, stream);
+}
+
+// Weight gradient of a 1x1 convolution (plain GEMM over the flat pixels): dw fp32 [cout][cin].  Same tensors, workspace query and
+// determinism rules as adc_conv3x3_wgrad_tc; every SM owns a share of the pixels.
+int adc_conv1x1_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
+                         int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout,
+                         adc_stream_t stream) {
+    return wgrad_flat(gy, gy_lo, gy_stride, gy_off, x, x_lo, x_stride, x_off, dw, workspace, N, H, W, cin, cin_pad, cout, 1, stream);
 }
 
 // Strided / general-geometry variant (see conv3x3_wgrad_box_tc_kernel): gy [N][Ho][Wo] (+border if gy_pad), x [N][H][W]
@@ -477,7 +494,7 @@ int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, i
     conv3x3_wgrad_box_tc_kernel<<<9 * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
     if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_box_tc_kernel launch"))) return rc;
     const int total = 9 * cout * cin;
-    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin);
+    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin, 9);
     return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");
 }
 

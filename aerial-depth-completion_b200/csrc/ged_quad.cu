@@ -244,6 +244,55 @@ __global__ void __launch_bounds__(256) ged_pack_input_kernel(const float* __rest
     }
 }
 
+// conv1 (3x3, stride 2, 5 -> 80 channels) as a GEMM: im2col of its input at the OUTPUT resolution.
+// x45[n][i+1][j+1][(u*3+v)*5 + c] = in[n][c][2i+u-1][2j+v-1] (0 outside), c = {xout_d, r, g, b, cout_d}; 45 of 48 written channels
+// are real, bf16 (hi, lo).  The layer's forward is then a 1x1 convolution of x45 and its weight gradient a plain GEMM of the
+// output gradient with x45, both at a quarter of the pixels and without strided tensor-map boxes.
+__global__ void __launch_bounds__(128) ged_pack_im2col_kernel(const float* __restrict__ xout, const float* __restrict__ cout,
+                                                              const float* __restrict__ rgb, long long rgb_bs, __nv_bfloat16* __restrict__ dst,
+                                                              __nv_bfloat16* __restrict__ dst_lo, int dst_stride, int N, int H, int W) {
+    const int H1 = (H + 1) >> 1, W1 = (W + 1) >> 1;
+    const long long HW = (long long)H * W, total = (long long)N * H1 * W1;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % W1), i = (int)((t / W1) % H1), n = (int)(t / ((long long)W1 * H1));
+        const float* pl[5] = {xout + n * HW, rgb + n * rgb_bs, rgb + n * rgb_bs + HW, rgb + n * rgb_bs + 2 * HW, cout + n * HW};
+        float v[48];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int y = 2 * i + u - 1;
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                const int x = 2 * j + w - 1;
+                const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+                const long long o = ok ? (long long)y * W + x : 0;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    const float f = __ldg(pl[c] + o);
+                    v[(u * 3 + w) * 5 + c] = ok ? f : 0.f;
+                }
+            }
+        }
+        v[45] = v[46] = v[47] = 0.f;
+        const long long pix = ((long long)n * (H1 + 2) + i + 1) * (W1 + 2) + j + 1;
+        uint4* oh = reinterpret_cast<uint4*>(dst + pix * dst_stride);
+        uint4* ol = dst_lo ? reinterpret_cast<uint4*>(dst_lo + pix * dst_stride) : nullptr;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            uint4 h, l;
+            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&h);
+            __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&l);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = v[q * 8 + 2 * k], b = v[q * 8 + 2 * k + 1];
+                hh[k] = __floats2bfloat162_rn(a, b);
+                ll[k] = __floats2bfloat162_rn(a - __low2float(hh[k]), b - __high2float(hh[k]));
+            }
+            oh[q] = h;
+            if (ol) ol[q] = l;
+        }
+    }
+}
+
 static int grid_for(long long total, int block) {
     long long b = (total + block - 1) / block;
     const long long cap = 148LL * 8;
@@ -270,6 +319,20 @@ int adc_ged_pack_input(const float* xout, const float* cout, const float* rgb, l
     ged_pack_input_kernel<<<grid_for(total, 256), 256, 0, st>>>(xout, cout, rgb, rgb_batch_stride, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo,
                                                                  dst_stride, N, H, W);
     return adc::check_cuda(cudaGetLastError(), "ged_pack_input_kernel launch");
+}
+
+int adc_ged_pack_im2col(const float* xout, const float* cout, const float* rgb, long long rgb_batch_stride, void* dst, void* dst_lo,
+                        int dst_stride, int N, int H, int W, adc_stream_t stream) {
+    if (!xout || !cout || !rgb || !dst || N <= 0 || H <= 0 || W <= 0 || dst_stride < 48 || dst_stride % 8 != 0) {
+        adc::set_error("adc_ged_pack_im2col: bad argument");
+        return ADC_E_BADARG;
+    }
+    const long long total = (long long)N * ((H + 1) / 2) * ((W + 1) / 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_TC_LAYOUT, (double)N * H * W * 20.0 + (double)total * (dst_lo ? 192.0 : 96.0));
+    ged_pack_im2col_kernel<<<grid_for(total, 128) * 2, 128, 0, st>>>(xout, cout, rgb, rgb_batch_stride, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo,
+                                                                      dst_stride, N, H, W);
+    return adc::check_cuda(cudaGetLastError(), "ged_pack_im2col_kernel launch");
 }
 
 int adc_quad_head_finish(const float* q, int q_stride, const float* x0d, const float* w, const float* bias, float* out, int N, int oc, int H,

@@ -356,6 +356,44 @@ def ged_pack_input(xout_d, cout_d, rgb, dst):
     return dst
 
 
+def ged_pack_im2col(xout_d, cout_d, rgb, dst):
+    """im2col of conv1's input (cat(xout_d, rgb, cout_d), 3x3 window, stride 2) at the output resolution into channels [0,48) of
+    ``dst`` (channel (3u+v)*5 + c): conv1 becomes a 1x1 convolution / GEMM at a quarter of the pixels."""
+    from ._lib import lib, check
+    _need_cuda(xout_d)
+    n, _, h, w = xout_d.shape
+    xout_d, cout_d = xout_d.contiguous(), cout_d.contiguous()
+    if rgb.stride(3) != 1 or rgb.stride(2) != w or rgb.stride(1) != h * w:
+        rgb = rgb.contiguous()
+    check(lib.adc_ged_pack_im2col(xout_d.data_ptr(), cout_d.data_ptr(), rgb.data_ptr(), rgb.stride(0) if n > 1 else 3 * h * w,
+                                  dst.hi.data_ptr(), _ptr(dst.lo), dst.cs, n, h, w, _stream()), "adc_ged_pack_im2col")
+    return dst
+
+
+def conv1x1_tc(act, cin, w_prep, bias, cout, act_fn=0, x_off=0, out=None, out_off=0, out_zero_to=0):
+    """1x1 convolution of channels [x_off, x_off+cin) of a zero-bordered activation (cin % 64 == 0) into a channel slice of
+    ``out``; ``w_prep`` = prepared weights of a [cout, cin, 3, 3] tensor whose only non-zero tap is the centre."""
+    from ._lib import lib, check
+    assert act.pad and out.pad and (act.n, act.h, act.w) == (out.n, out.h, out.w)
+    b = bias.detach().contiguous().data_ptr() if bias is not None else None
+    check(lib.adc_conv1x1_tc_v2(act.hi.data_ptr(), _ptr(act.lo), act.cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b,
+                                out.hi.data_ptr(), _ptr(out.lo), int(out.hi.dtype == torch.float32), out.cs, out_off, out_zero_to,
+                                act.n, act.h, act.w, cin, cout, act_fn, _stream()), "adc_conv1x1_tc_v2")
+    return out
+
+
+def conv1x1_wgrad_tc(gy, x, cin, cout, x_off=0, gy_off=0, cin_pad=None):
+    """dW [cout, cin] (fp32) = sum over pixels of gy[p][co] * x[p][ci] from zero-bordered NHWC activations."""
+    from ._lib import lib, check
+    assert x.pad and gy.pad and (x.n, x.h, x.w) == (gy.n, gy.h, gy.w)
+    cin_pad = _r16(cin) if cin_pad is None else cin_pad
+    dw = torch.empty((cout, cin), device=x.hi.device, dtype=torch.float32)
+    ws = torch.empty(lib.adc_conv3x3_wgrad_tc_workspace_bytes(cin_pad, cout) // 4, device=x.hi.device, dtype=torch.float32)
+    check(lib.adc_conv1x1_wgrad_tc(gy.hi.data_ptr(), _ptr(gy.lo), gy.cs, gy_off, x.hi.data_ptr(), _ptr(x.lo), x.cs, x_off,
+                                   dw.data_ptr(), ws.data_ptr(), x.n, x.h, x.w, cin, cin_pad, cout, _stream()), "adc_conv1x1_wgrad_tc")
+    return dw
+
+
 def quad_head_finish(q, x0d, weight, bias, h, w):
     from ._lib import lib, check
     oc = weight.shape[0]

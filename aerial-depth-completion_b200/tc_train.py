@@ -38,7 +38,7 @@ class _Plan:
         self.hs, self.ws = hs, ws
         A = lambda lvl, c, **kw: dense.new_act(n, hs[lvl], ws[lvl], c, device, pad=True, zero=True, **kw)
         # forward
-        self.in0 = A(0, 16)            # [xout_d, r, g, b, cout_d, 0...]
+        self.x45 = A(1, 64)            # im2col of conv1's input at conv1's output resolution: channel (3u+v)*5 + c, 45 real
         self.cat10 = None              # [up(x9) 32 | x0_d 1 | 0...]: only materialised when the confidence head wants it
         self.cat9 = A(1, 128)          # [up(x8) 32 | x1 80 | 0...]
         self.cat8 = A(2, 192)          # [up(x7) 64 | x2 80 | 0...]
@@ -55,7 +55,7 @@ class _Plan:
     def backward_buffers(self):
         if self.bwd is None:
             n, hs, ws = self.n, self.hs, self.ws
-            dev = self.in0.hi.device
+            dev = self.x45.hi.device
             A = lambda lvl, c, **kw: dense.new_act(n, hs[lvl], ws[lvl], c, dev, pad=True, zero=True, **kw)
             b = {}
             b["G9"], b["gcat9"] = A(1, 64), A(1, 128)
@@ -144,15 +144,19 @@ class GEDDenseTC(torch.autograd.Function):
         W = params[0::2]
         Bz = params[1::2]
         c3 = dense.conv3x3_tc
-        dense.ged_pack_input(xout_d, cout_d, rgb, P.in0)
+        dense.ged_pack_im2col(xout_d, cout_d, rgb, P.x45)
         oc = W[9].shape[0]
         # every layer's weights -> bf16 (hi, lo) [9][Cout16][Cin_pad] in ONE launch
-        reqs = [(W[i], 0, cp, 0, W[i].shape[1]) for i, cp in enumerate((16, 80, 80, 80, 80, 192, 192, 192, 128))]
+        # conv1 as a GEMM over the im2col tensor: [80, 45] weights in the centre tap of a 3x3 tensor (the 1x1 kernel reads only it)
+        w1 = torch.zeros((80, 45, 3, 3), device=W[0].device, dtype=torch.float32)
+        w1[:, :, 1, 1] = W[0].permute(0, 2, 3, 1).reshape(80, 45)
+        reqs = [(w1, 0, 64, 0, 45)] + [(W[i], 0, cp, 0, W[i].shape[1]) for i, cp in ((1, 80), (2, 80), (3, 80), (4, 80), (5, 192), (6, 192),
+                                                                                   (7, 192), (8, 128))]
         if P.quad:
             reqs.append((_quad_head_weights(W[9]), 0, 64, 0, 32))
         wp = dense.prep_conv3x3_weights_batch(reqs)
         # encoder: 3x3 stride 2 + ReLU, each output lands in the concat buffer of the decoder layer that reuses it
-        c3(P.in0, 16, wp[0], Bz[0], 80, 2, _RELU, out=P.cat9, out_off=32)
+        dense.conv1x1_tc(P.x45, 64, wp[0], Bz[0], 80, _RELU, out=P.cat9, out_off=32)
         c3(P.cat9, 80, wp[1], Bz[1], 80, 2, _RELU, x_off=32, out=P.cat8, out_off=64)
         c3(P.cat8, 80, wp[2], Bz[2], 80, 2, _RELU, x_off=64, out=P.cat7, out_off=64)
         c3(P.cat7, 80, wp[3], Bz[3], 80, 2, _RELU, x_off=64, out=P.cat6, out_off=80)
@@ -247,7 +251,7 @@ class GEDDenseTC(torch.autograd.Function):
             dense.conv3x3_dgrad_s2_tc(G, 80, wp[i][0], 80, hs[lvl], ws[lvl], out=b[gxn], out_off=0)
             G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True)
         gB[0] = gb
-        gW[0] = wgb(G, P.in0, 5, 80, 2, cin_pad=16)
+        gW[0] = dense.conv1x1_wgrad_tc(G, P.x45, 45, 80, cin_pad=48).reshape(80, 3, 3, 5).permute(0, 3, 1, 2).contiguous()
         dense.conv3x3_tc(G, 128, wp[0][0], None, 8, 1, 0, out=b["qin0"])
         gin = dense.quad_unshuffle(b["qin0"], 2, hs[0], ws[0])
         grads = []

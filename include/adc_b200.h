@@ -182,6 +182,10 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
 int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
                          const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
                          int N, int H, int W, int cin, int cout, int act, adc_stream_t stream);
+/* 1x1 convolution (plain GEMM over the flat pixels) on the same kernel: only the centre tap of the prepared weights is read. */
+int adc_conv1x1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo, const float* bias, void* out,
+                      void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to, int N, int H, int W, int cin, int cout, int act,
+                      adc_stream_t stream);
 /* Data gradient of a 3x3 / stride-2 / pad-1 convolution (backward of the encoder layers conv1-5 of GEDNet,
  * confidence_depth_framework.py:442-446): four parity-class launches of the tcgen05 kernel.  gy: NHWC bf16 [N][Ho][Wo]
  * (+ zero border if gy_pad), channels [gy_off, gy_off+cgy), cgy % 16 == 0; w from adc_conv3x3_prep_weights(flip_transpose=2);
@@ -197,6 +201,10 @@ int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, in
  * workspace: adc_conv3x3_wgrad_tc_workspace_bytes(cin_pad, cout) bytes; the reduction order is fixed (deterministic). */
 size_t adc_conv3x3_wgrad_tc_workspace_bytes(int cin_pad, int cout);
 int adc_conv3x3_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
+                         int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout,
+                         adc_stream_t stream);
+/* Weight gradient of a 1x1 convolution: dw fp32 [cout][cin] = sum over pixels of gy[p][co] * x[p][ci]; same workspace query. */
+int adc_conv1x1_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* x, const void* x_lo, int x_stride,
                          int x_off, float* dw, void* workspace, int N, int H, int W, int cin, int cin_pad, int cout,
                          adc_stream_t stream);
 /* General-geometry variant (stride 1 or 2; gy [N][Ho][Wo], x [N][H][W], each with or without the zero border): one tap per
@@ -254,6 +262,10 @@ int adc_ged_head_bwd_x0d(const float* gy, const float* x10, const float* glli, i
  * adc_quad_unshuffle:     out[k][n][2i+py][2j+px] = q[n][i+1][j+1][(2py+px)*K + k], K in {1,2}; any H, W (H1 = ceil(H/2)). */
 int adc_ged_pack_input(const float* xout, const float* cout, const float* rgb, long long rgb_batch_stride, void* dst, void* dst_lo,
                        int dst_stride, int N, int H, int W, adc_stream_t stream);
+/* conv1 (3x3, stride 2) as a GEMM: im2col at the output resolution, x45[n][i+1][j+1][(3u+v)*5 + c] = in[n][c][2i+u-1][2j+v-1],
+ * channels [0,48) of a zero-bordered NHWC bf16 (hi, lo) tensor [N][H1+2][W1+2][dst_stride], H1 = ceil(H/2). */
+int adc_ged_pack_im2col(const float* xout, const float* cout, const float* rgb, long long rgb_batch_stride, void* dst, void* dst_lo,
+                        int dst_stride, int N, int H, int W, adc_stream_t stream);
 int adc_quad_head_finish(const float* q, int q_stride, const float* x0d, const float* w, const float* bias, float* out, int N, int oc, int H,
                          int W, adc_stream_t stream);
 int adc_quad_head_bwd_prep_parts(void);
