@@ -90,14 +90,14 @@ SIGNATURES = {
     "adc_conv3x3_fprop_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_s1_tc_v2": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
-                                     c_int, c_int, c_int, c_int, _vp]),
+                                     c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_dgrad_s2_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_int, c_int, c_int, _vp]),
     "adc_conv3x3_wgrad_box_tc": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, _vp]),
     "adc_nhwc_upsample_nearest": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_nhwc_grad_assemble": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int, c_int, ctypes.c_float,
-                                       _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp]),
+                                       _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, c_int, _vp]),
     "adc_nhwc_grad_assemble_parts": (c_int, []),
     "adc_nhwc_colsum_workspace_bytes": (ctypes.c_size_t, [c_int]),
     "adc_nhwc_colsum": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp]),
@@ -114,7 +114,9 @@ SIGNATURES = {
     "adc_ged_pack_input": (c_int, [_vp, _vp, _vp, c_ll, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_quad_head_finish": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_quad_head_bwd_prep_parts": (c_int, []),
-    "adc_quad_head_bwd_prep": (c_int, [_vp, _vp, _vp, _vp, _vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_quad_head_bwd_prep": (c_int, [_vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_quad_head_wgrad": (c_int, [_vp, _vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_quad_head_dgrad": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_quad_unshuffle": (c_int, [_vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_conv3x3_wgrad_tc_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_wgrad_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -218,6 +218,7 @@ struct ConvParamsV2 {
     int tma_store;           // 1: bf16 output tile staged in shared memory and written by TMA bulk stores (slice width 64)
     int dbg;                 // timing experiments: 1 = epilogue skips its global stores, 2 = epilogue skipped entirely
     int taps1;               // 1: only the centre tap exists (a 1x1 convolution / plain GEMM over the flat pixels)
+    int tap_mask;            // bit 3u+v set = tap (u,v) has non-zero weights; rows of taps that are all clear are never loaded
 };
 
 constexpr int kSegRows = 130;
@@ -245,7 +246,11 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
     const int kblocks = (p.cin + 63) / 64;
     const int tpk = p.taps1 ? 1 : 9;                  // weight tiles per 64-channel block
     const int tps = p.taps1 ? 1 : 3;                  // ... per pipeline step
-    const int steps = kblocks * tps;
+    // active tap rows (the quad forms of the stride-2 data gradients have whole rows / columns of zero taps)
+    int rows[3], nrows = 0;
+    for (int u = 0; u < 3; ++u)
+        if (p.taps1 ? u == 1 : ((p.tap_mask >> (3 * u)) & 7) != 0) rows[nrows++] = u;
+    const int steps = kblocks * nrows;
     const int nst = p.nstages;
     const int b_tile = p.npad * 128;                  // one tap's weight tile (multiple of 1024: npad % 8 == 0)
     const int w_all = tpk * kblocks * b_tile;         // every weight tile of the layer (resident mode)
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 const long long m0 = (long long)tile * 128;
                 for (int st = 0; st < steps; ++st, ++q) {
                     const int s = q % nst, use = q / nst;
-                    const int kb = st / tps, u = p.taps1 ? 1 : st % 3;
+                    const int kb = st / nrows, u = rows[st % nrows];
                     mbar_wait(&bars[8 + s], (use & 1) ^ 1);
                     uint8_t* sa = stages + s * stage_bytes;
                     mbar_expect_tx(&bars[s], (uint32_t)((kSegRows * 128 + (p.resident ? 0 : tps * b_tile)) * mult));
@@ -342,22 +347,24 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 mbar_wait(&bars[18 + a], ((it >> 1) & 1) ^ 1);         // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(a * acc_cols);
+                uint32_t accumulate = 0;
                 for (int st = 0; st < steps; ++st, ++q) {
                     const int s = q % nst, use = q / nst;
-                    const int kb = st / tps, u = p.taps1 ? 1 : st % 3;
+                    const int kb = st / nrows, u = rows[st % nrows];
                     mbar_wait(&bars[s], use & 1);
                     tc_fence_after();
                     const uint32_t sa = sbase + s * stage_bytes;
                     const int v0 = p.taps1 ? 1 : 0, v1 = p.taps1 ? 2 : 3;      // the centre tap reads the segment one row in
                     for (int v = v0; v < v1; ++v) {
+                        if (!p.taps1 && !((p.tap_mask >> (3 * u + v)) & 1)) continue;
                         const uint32_t a_hi = sa + v * 128;
                         const int wslot = p.taps1 ? 0 : v;
                         const uint32_t b_cat = p.resident ? base + (kb * tpk + (p.taps1 ? 0 : 3 * u + v)) * (mult * b_tile)
                                                           : sa + b_off + wslot * (mult * b_tile);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_cat) + 2 * k, idesc,
-                                      !(st == 0 && v == v0 && k == 0));
+                            umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_cat) + 2 * k, idesc, accumulate | (uint32_t)k);
+                        accumulate = 1;
                         if (p.split) {
                             const uint32_t a_lo = a_hi + kSegBytes;
 #pragma unroll
@@ -835,7 +842,7 @@ int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, in
 // zero-bordered NHWC tensors ([N][H+2][W+2][channels]); needs cin % 64 == 0.  Same split-mode convention as above.
 static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo, const float* bias, void* out,
                    void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to, int N, int H, int W, int cin, int cout, int act,
-                   int taps1, adc_stream_t stream) {
+                   int taps1, int tap_mask, adc_stream_t stream) {
     if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) {
         adc::set_error("adc_conv3x3_s1_tc_v2: bad argument");
         return ADC_E_BADARG;
@@ -864,6 +871,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     p.ntiles = (int)((p.F + 127) / 128);
     p.out_zero_to = out_zero_to;
     p.taps1 = taps1;
+    p.tap_mask = (tap_mask & 0x1FF) ? (tap_mask & 0x1FF) : 0x1FF;
     { const char* e = getenv("ADC_V2_DBG"); p.dbg = e ? atoi(e) : 0; }
     CUtensorMap mx, mw, mxl, mwl;
     memset(&mxl, 0, sizeof(mxl));
@@ -970,9 +978,9 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
 
 int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
                          const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
-                         int N, int H, int W, int cin, int cout, int act, adc_stream_t stream) {
+                         int N, int H, int W, int cin, int cout, int act, int tap_mask, adc_stream_t stream) {
     return conv_v2(x, x_lo, x_stride, x_off, w, w_lo, bias, out, out_lo, out_f32, out_stride, out_off, out_zero_to, N, H, W, cin, cout, act, 0,
-                   stream);
+                   tap_mask, stream);
 }
 
 // 1x1 convolution (a plain GEMM over the flat pixels of a zero-bordered NHWC tensor) on the same persistent kernel: only the
@@ -981,7 +989,7 @@ int adc_conv1x1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, 
                       void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to, int N, int H, int W, int cin, int cout, int act,
                       adc_stream_t stream) {
     return conv_v2(x, x_lo, x_stride, x_off, w, w_lo, bias, out, out_lo, out_f32, out_stride, out_off, out_zero_to, N, H, W, cin, cout, act, 1,
-                   stream);
+                   0, stream);
 }
 
 }  // extern "C"

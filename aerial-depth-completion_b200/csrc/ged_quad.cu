@@ -97,12 +97,11 @@ __global__ void __launch_bounds__(256) quad_head_finish_kernel(const float* __re
     }
 }
 
-// gq[n][i+1][j+1][(py*2+px)*OC + o] = gpre[n][o][2i+py][2j+px] = gy * (x10 > 0 ? 1 : 0.2)   (bf16 hi, lo; channels [4*OC, 8) zero)
+// gq[n][i+1][j+1][(py*2+px)*OC + o] = gpre[n][o][2i+py][2j+px] = gy * (x10 > 0 ? 1 : 0.2)   (fp32, 4*OC channels per pixel)
 // part[block][o][t]  t < 9: sum gpre[o][y][x] * x0d[y+u-1][x+v-1] (weight gradient of the x0_d channel);  t = 9: sum gpre[o]
 template <int OC>
 __global__ void __launch_bounds__(256) quad_head_bwd_prep_kernel(const float* __restrict__ gy, const float* __restrict__ x10,
-                                                                 const float* __restrict__ x0d, __nv_bfloat16* __restrict__ gq,
-                                                                 __nv_bfloat16* __restrict__ gq_lo, int gq_stride, float* __restrict__ part,
+                                                                 const float* __restrict__ x0d, float* __restrict__ gq, float* __restrict__ part,
                                                                  int N, int H, int W) {
     __shared__ float red[8][OC * 10];
     const int H1 = H >> 1, W1 = W >> 1;
@@ -141,17 +140,10 @@ __global__ void __launch_bounds__(256) quad_head_bwd_prep_kernel(const float* __
                         for (int v = 0; v < 3; ++v) acc[o][u * 3 + v] = fmaf(gp[py][px], d[py + u][px + v], acc[o][u * 3 + v]);
                 }
         }
-        uint4 h, l;
-        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&h);
-        __nv_bfloat162* ll = reinterpret_cast<__nv_bfloat162*>(&l);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            hh[k] = __floats2bfloat162_rn(g[2 * k], g[2 * k + 1]);
-            ll[k] = __floats2bfloat162_rn(g[2 * k] - __low2float(hh[k]), g[2 * k + 1] - __high2float(hh[k]));
-        }
         const long long pix = ((long long)n * (H1 + 2) + i + 1) * (W1 + 2) + j + 1;
-        *reinterpret_cast<uint4*>(gq + pix * gq_stride) = h;
-        if (gq_lo) *reinterpret_cast<uint4*>(gq_lo + pix * gq_stride) = l;
+        float4* o4 = reinterpret_cast<float4*>(gq + pix * (4 * OC));
+#pragma unroll
+        for (int k = 0; k < OC; ++k) o4[k] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
     }
     // deterministic block reduction: lanes (xor shuffles), then the 8 warps in index order
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,6 +162,159 @@ __global__ void __launch_bounds__(256) quad_head_bwd_prep_kernel(const float* __
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
         part[(long long)blockIdx.x * OC * 10 + threadIdx.x] = s;
+    }
+}
+
+// ---- backward of the quad conv10 on the CUDA cores ----------------------------------------------------------------------------
+// With 4*OC <= 8 "output channels" the two gradient contractions are far too thin for the tensor pipe (an M = 128 MMA costs ~90
+// cycles whatever its N: measured 298 us / 133 us as tcgen05 GEMMs) -- as direct kernels they are 36*OC FMAs per (pixel, channel):
+// warp = a run of 32 pixels of one row of x9's grid, lane = one of x9's 32 channels, a 3x3 register window slides along the row.
+struct X9v {
+    const __nv_bfloat16* hi;
+    const __nv_bfloat16* lo;    // may be null
+    int stride;
+};
+__device__ __forceinline__ float ld_x9(const X9v& x, long long pix, int c) {
+    float v = __bfloat162float(x.hi[pix * x.stride + c]);
+    if (x.lo) v += __bfloat162float(x.lo[pix * x.stride + c]);
+    return v;
+}
+
+// dWq[qo][c][a*3+b] = sum_p gq[p][qo] * x9[p + (a-1, b-1)][c]   -> part[block][4*OC][32][9]
+template <int OC>
+__global__ void __launch_bounds__(256) quad_head_wgrad_kernel(X9v x9, const float* __restrict__ gq, float* __restrict__ part, int N, int H1,
+                                                              int W1) {
+    constexpr int Q = 4 * OC;
+    __shared__ float red[8][9][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[Q][9];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[q][t] = 0.f;
+    const int chunks = (W1 + 31) / 32;
+    const long long items = (long long)N * H1 * chunks;
+    for (long long it = (long long)blockIdx.x * 8 + warp; it < items; it += (long long)gridDim.x * 8) {
+        const int jc = (int)(it % chunks), i = (int)((it / chunks) % H1), n = (int)(it / ((long long)chunks * H1));
+        const int j0 = jc * 32, j1 = j0 + 32 < W1 ? j0 + 32 : W1;
+        long long row[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) row[a] = ((long long)n * (H1 + 2) + i + a) * (W1 + 2);      // padded row of x9 row i-1+a
+        float xw[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            xw[a][0] = ld_x9(x9, row[a] + j0, lane);
+            xw[a][1] = ld_x9(x9, row[a] + j0 + 1, lane);
+        }
+        for (int j = j0; j < j1; ++j) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) xw[a][2] = ld_x9(x9, row[a] + j + 2, lane);
+            const float4* g4 = reinterpret_cast<const float4*>(gq + (row[1] + j + 1) * Q);
+            float g[Q];
+#pragma unroll
+            for (int k = 0; k < OC; ++k) {
+                const float4 t = __ldg(g4 + k);
+                g[4 * k] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w;
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) acc[q][a * 3 + b] = fmaf(g[q], xw[a][b], acc[q][a * 3 + b]);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { xw[a][0] = xw[a][1]; xw[a][1] = xw[a][2]; }
+        }
+    }
+    // the 8 warps of the CTA in index order, one parity channel at a time
+    for (int q = 0; q < Q; ++q) {
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < Q; ++k) v = (k == q) ? acc[k][t] : v;      // keeps acc in registers (no dynamic indexing)
+            red[warp][t][lane] = v;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 9 * 32; e += 256) {
+            const int t = e / 32, c = e % 32;
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += red[k][t][c];
+            part[(((long long)blockIdx.x * Q + q) * 32 + c) * 9 + t] = sum;
+        }
+    }
+}
+
+// G9[p][c] = leaky'(x9[p][c]) * ( sum_{qo,a,b} Wq[qo][c][a][b] * gq[p - (a-1, b-1)][qo]  +  extra[p][c] )     (bf16 hi, lo)
+// part[block][32]: per-channel sums of G9 (the bias gradient of conv9).  Wq: fp32 [4*OC][32][3][3].
+template <int OC>
+__global__ void __launch_bounds__(256) quad_head_dgrad_kernel(X9v x9, const float* __restrict__ gq, const float* __restrict__ wq, X9v extra,
+                                                              __nv_bfloat16* __restrict__ g9, __nv_bfloat16* __restrict__ g9_lo, int g9_stride,
+                                                              float* __restrict__ part, int N, int H1, int W1) {
+    constexpr int Q = 4 * OC;
+    __shared__ float red[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float w[Q][9];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w[q][t] = __ldg(wq + ((long long)q * 32 + lane) * 9 + t);
+    float csum = 0.f;
+    const int chunks = (W1 + 31) / 32;
+    const long long items = (long long)N * H1 * chunks;
+    for (long long it = (long long)blockIdx.x * 8 + warp; it < items; it += (long long)gridDim.x * 8) {
+        const int jc = (int)(it % chunks), i = (int)((it / chunks) % H1), n = (int)(it / ((long long)chunks * H1));
+        const int j0 = jc * 32, j1 = j0 + 32 < W1 ? j0 + 32 : W1;
+        long long row[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) row[a] = ((long long)n * (H1 + 2) + i + a) * (W1 + 2);
+        // window gw[r][col][q] = gq at padded (i + r, j + col): output pixel (i, j) = padded (i+1, j+1) reads p - (a-1, b-1)
+        // = padded (i + 2 - a, j + 2 - b)
+        float gw[3][3][Q];
+        auto load_col = [&](int col, int jj) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float4* g4 = reinterpret_cast<const float4*>(gq + (row[r] + jj + col) * Q);
+#pragma unroll
+                for (int k = 0; k < OC; ++k) {
+                    const float4 t = __ldg(g4 + k);
+                    gw[r][col][4 * k] = t.x; gw[r][col][4 * k + 1] = t.y; gw[r][col][4 * k + 2] = t.z; gw[r][col][4 * k + 3] = t.w;
+                }
+            }
+        };
+        load_col(0, j0);
+        load_col(1, j0);
+        for (int j = j0; j < j1; ++j) {
+            load_col(2, j);
+            const long long pix = row[1] + j + 1;
+            float acc = extra.hi ? ld_x9(extra, pix, lane) : 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) acc = fmaf(w[q][a * 3 + b], gw[2 - a][2 - b][q], acc);
+            const float xv = __bfloat162float(x9.hi[pix * x9.stride + lane]);
+            acc *= xv > 0.f ? 1.f : 0.2f;
+            csum += acc;
+            const __nv_bfloat16 h = __float2bfloat16(acc);
+            g9[pix * g9_stride + lane] = h;
+            if (g9_lo) g9_lo[pix * g9_stride + lane] = __float2bfloat16(acc - __bfloat162float(h));
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < Q; ++q) { gw[r][0][q] = gw[r][1][q]; gw[r][1][q] = gw[r][2][q]; }
+        }
+    }
+    red[warp][lane] = csum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += red[k][threadIdx.x];
+        part[(long long)blockIdx.x * 32 + threadIdx.x] = sum;
     }
 }
 
@@ -352,21 +497,51 @@ int adc_quad_head_finish(const float* q, int q_stride, const float* x0d, const f
 
 int adc_quad_head_bwd_prep_parts(void) { return kPrepCtas; }
 
-int adc_quad_head_bwd_prep(const float* gy, const float* x10, const float* x0d, void* gq, void* gq_lo, int gq_stride, float* part, int N,
-                           int oc, int H, int W, adc_stream_t stream) {
-    if (!gy || !x10 || !x0d || !gq || !part || N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || oc < 1 || oc > 2 || gq_stride < 8 ||
-        gq_stride % 8 != 0) {
+int adc_quad_head_bwd_prep(const float* gy, const float* x10, const float* x0d, float* gq, float* part, int N, int oc, int H, int W,
+                           adc_stream_t stream) {
+    if (!gy || !x10 || !x0d || !gq || !part || N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || oc < 1 || oc > 2) {
         adc::set_error("adc_quad_head_bwd_prep: bad argument (needs even H, W; oc in {1,2})");
         return ADC_E_BADARG;
     }
     const long long total = (long long)N * (H / 2) * (W / 2);
     cudaStream_t st = (cudaStream_t)stream;
-    adc::Prof prof(st, adc::KIND_HEAD10, (double)total * (32.0 * oc + 16.0 + (gq_lo ? 32.0 : 16.0)));
-    if (oc == 1)
-        quad_head_bwd_prep_kernel<1><<<kPrepCtas, 256, 0, st>>>(gy, x10, x0d, (__nv_bfloat16*)gq, (__nv_bfloat16*)gq_lo, gq_stride, part, N, H, W);
-    else
-        quad_head_bwd_prep_kernel<2><<<kPrepCtas, 256, 0, st>>>(gy, x10, x0d, (__nv_bfloat16*)gq, (__nv_bfloat16*)gq_lo, gq_stride, part, N, H, W);
+    adc::Prof prof(st, adc::KIND_HEAD10, (double)total * (32.0 * oc + 16.0 + 16.0 * oc));
+    if (oc == 1) quad_head_bwd_prep_kernel<1><<<kPrepCtas, 256, 0, st>>>(gy, x10, x0d, gq, part, N, H, W);
+    else quad_head_bwd_prep_kernel<2><<<kPrepCtas, 256, 0, st>>>(gy, x10, x0d, gq, part, N, H, W);
     return adc::check_cuda(cudaGetLastError(), "quad_head_bwd_prep_kernel launch");
+}
+
+int adc_quad_head_wgrad(const void* x9, const void* x9_lo, int x9_stride, const float* gq, float* part, int N, int oc, int H1, int W1,
+                        adc_stream_t stream) {
+    if (!x9 || !gq || !part || N <= 0 || H1 <= 0 || W1 <= 0 || oc < 1 || oc > 2 || x9_stride < 32) {
+        adc::set_error("adc_quad_head_wgrad: bad argument");
+        return ADC_E_BADARG;
+    }
+    X9v x{(const __nv_bfloat16*)x9, (const __nv_bfloat16*)x9_lo, x9_stride};
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_HEAD10, (double)N * H1 * W1 * (32.0 * (x9_lo ? 4.0 : 2.0) + 16.0 * oc));
+    if (oc == 1) quad_head_wgrad_kernel<1><<<kPrepCtas, 256, 0, st>>>(x, gq, part, N, H1, W1);
+    else quad_head_wgrad_kernel<2><<<kPrepCtas, 256, 0, st>>>(x, gq, part, N, H1, W1);
+    return adc::check_cuda(cudaGetLastError(), "quad_head_wgrad_kernel launch");
+}
+
+int adc_quad_head_dgrad(const void* x9, int x9_stride, const float* gq, const float* wq, const void* extra, const void* extra_lo,
+                        int extra_stride, void* g9, void* g9_lo, int g9_stride, float* part, int N, int oc, int H1, int W1,
+                        adc_stream_t stream) {
+    if (!x9 || !gq || !wq || !g9 || !part || N <= 0 || H1 <= 0 || W1 <= 0 || oc < 1 || oc > 2 || x9_stride < 32 || g9_stride < 32 ||
+        (extra && extra_stride < 32)) {
+        adc::set_error("adc_quad_head_dgrad: bad argument");
+        return ADC_E_BADARG;
+    }
+    X9v x{(const __nv_bfloat16*)x9, nullptr, x9_stride};
+    X9v e{(const __nv_bfloat16*)extra, (const __nv_bfloat16*)extra_lo, extra_stride};
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_HEAD10, (double)N * H1 * W1 * (32.0 * (2.0 + (g9_lo ? 4.0 : 2.0)) + 16.0 * oc));
+    if (oc == 1)
+        quad_head_dgrad_kernel<1><<<kPrepCtas, 256, 0, st>>>(x, gq, wq, e, (__nv_bfloat16*)g9, (__nv_bfloat16*)g9_lo, g9_stride, part, N, H1, W1);
+    else
+        quad_head_dgrad_kernel<2><<<kPrepCtas, 256, 0, st>>>(x, gq, wq, e, (__nv_bfloat16*)g9, (__nv_bfloat16*)g9_lo, g9_stride, part, N, H1, W1);
+    return adc::check_cuda(cudaGetLastError(), "quad_head_dgrad_kernel launch");
 }
 
 int adc_quad_unshuffle(const float* q, int q_stride, float* out, int N, int K, int H, int W, adc_stream_t stream) {

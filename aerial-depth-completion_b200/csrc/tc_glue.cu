@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) nhwc_upsample_kernel(Slice src, SliceW ds
 // same pass: part[block][C] partial rows, summed by the caller in index order.
 __global__ void __launch_bounds__(256) nhwc_grad_assemble_kernel(Slice A, int hasA, Slice B, int hasB, Slice act, int hasAct, float slope,
                                                                  SliceW out, int N, int C8, int H, int W, int Hd, int Wd, Near mh, Near mw,
-                                                                 float* __restrict__ part) {
+                                                                 float* __restrict__ part, int a_quad) {
     __shared__ float red[256][8];
     const int groups = 256 / C8;                               // C8 <= 32
     const int cl = threadIdx.x % C8, pg = threadIdx.x / C8, c = cl * 8;
@@ -120,7 +120,11 @@ __global__ void __launch_bounds__(256) nhwc_grad_assemble_kernel(Slice A, int ha
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
-            if (hasA) {
+            if (hasA && a_quad) {
+                // A holds the data gradient of a stride-2 layer in quad form: pixel (y/2, x/2) of a (Hd, Wd) = ceil(H/2, W/2)
+                // tensor, channel block (2*(y&1) + (x&1)) * C
+                load8(A, ((long long)n * (Hd + 2) + (y >> 1) + 1) * (Wd + 2) + (x >> 1) + 1, ((y & 1) * 2 + (x & 1)) * C8 * 8 + c, v, true);
+            } else if (hasA) {
                 if (Hd == 2 * H && Wd == 2 * W) {              // exact 2x: the four children, row-major
 #pragma unroll
                     for (int dy = 0; dy < 2; ++dy)
@@ -239,9 +243,10 @@ int adc_nhwc_grad_assemble_parts(void) { return kAssembleCtas; }
 
 int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_off, int Hd, int Wd, const void* b, const void* b_lo,
                            int b_stride, int b_off, const void* act, int act_stride, int act_off, float slope, void* out, void* out_lo,
-                           int out_stride, int out_off, int N, int C, int H, int W, float* colsum_part, adc_stream_t stream) {
-    if (C > 256 || (!a && !b) || bad_slice(out, out_stride, out_off, C) || (a && bad_slice(a, a_stride, a_off, C)) || (b && bad_slice(b, b_stride, b_off, C)) ||
-        (act && bad_slice(act, act_stride, act_off, C)) || N <= 0 || H <= 0 || W <= 0 || (a && (Hd < H || Wd < W))) {
+                           int out_stride, int out_off, int N, int C, int H, int W, float* colsum_part, int a_quad, adc_stream_t stream) {
+    if (C > 256 || (!a && !b) || bad_slice(out, out_stride, out_off, C) || (a && bad_slice(a, a_stride, a_off, a_quad ? 4 * C : C)) ||
+        (b && bad_slice(b, b_stride, b_off, C)) || (act && bad_slice(act, act_stride, act_off, C)) || N <= 0 || H <= 0 || W <= 0 ||
+        (a && !a_quad && (Hd < H || Wd < W)) || (a && a_quad && (Hd != (H + 1) / 2 || Wd != (W + 1) / 2))) {
         adc::set_error("adc_nhwc_grad_assemble: bad argument");
         return ADC_E_BADARG;
     }
@@ -253,7 +258,7 @@ int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_
     const long long total = (long long)N * H * W * (C / 8);
     adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)total * 16.0 * (out_lo ? 2 : 1) * (1 + (a ? 1 : 0) + (b ? 1 : 0)));
     nhwc_grad_assemble_kernel<<<kAssembleCtas, 256, 0, (cudaStream_t)stream>>>(A, a != nullptr, B, b != nullptr, T, act != nullptr, slope, O, N,
-                                                                             C / 8, H, W, Hd, Wd, Near::make(H, Hd), Near::make(W, Wd), colsum_part);
+                                                                             C / 8, H, W, Hd, Wd, Near::make(H, Hd), Near::make(W, Wd), colsum_part, a_quad);
     return adc::check_cuda(cudaGetLastError(), "nhwc_grad_assemble_kernel launch");
 }
 

@@ -185,14 +185,15 @@ def prep_conv3x3_weights_batch(reqs):
 
 
 def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=None, out_off=0, out_f32=False, out_pad=None,
-               out_zero_to=0):
+               out_zero_to=0, tap_mask=0):
     """3x3 / pad 1 convolution on the tensor cores.  Channels [x_off, x_off+cin) of ``act`` are read (cin a multiple of 16,
     zero padded); the result goes to channels [out_off, out_off+cout) of ``out`` (allocated if None)."""
     from ._lib import lib, check
     n, h, w = act.n, act.h, act.w
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
-    # v2 streams 3 taps x Cout16 weight rows per pipeline stage: in the split mode two stages fit only up to 64 output channels
-    v2 = USE_V2 and stride == 1 and act.pad and cin % 64 == 0 and cout <= (64 if _split() else 128) and (out is None or out.pad)
+    # v2 streams 3 taps x Cout16 weight rows per pipeline stage: in the split mode two stages fit only up to 80 output channels
+    v2 = USE_V2 and stride == 1 and act.pad and cin % 64 == 0 and cout <= (80 if _split() else 128) and (out is None or out.pad)
+    assert v2 or not tap_mask, "tap masks are a feature of the row-segment kernel"
     zero_to = out_zero_to if v2 else 0                      # slice width the layer owns (channels past cout written as 0)
     if out is None:
         out_pad = act.pad if out_pad is None else out_pad
@@ -206,7 +207,7 @@ def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=No
     if v2:
         check(lib.adc_conv3x3_s1_tc_v2(act.hi.data_ptr(), _ptr(act.lo), act.cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b,
                                        out.hi.data_ptr(), _ptr(out.lo), is_f32, out.cs, out_off, zero_to, n, h, w, cin, cout, act_fn,
-                                       _stream()), "adc_conv3x3_s1_tc_v2")
+                                       tap_mask, _stream()), "adc_conv3x3_s1_tc_v2")
     else:
         check(lib.adc_conv3x3_fprop_tc(act.hi.data_ptr(), _ptr(act.lo), act.cs, x_off, w_prep[0].data_ptr(), _ptr(w_prep[1]), b,
                                        out.hi.data_ptr(), _ptr(out.lo), is_f32, out.cs, out_off, n, h, w, cin, cout, stride, act_fn,
@@ -263,8 +264,9 @@ def upsample_into(src, c, dst, dst_off, src_off=0):
     return dst
 
 
-def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None, act_off=0, slope=0.0, colsum=False):
+def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None, act_off=0, slope=0.0, colsum=False, a_quad=False):
     """out[:, out_off:out_off+c] = d(act) * (sum over the up-sampling children of ``a`` + ``b``); see adc_nhwc_grad_assemble.
+    a_quad: ``a`` is the quad form of a stride-2 data gradient (4 parity blocks of c channels at half resolution).
     colsum=True also returns the per-channel sum of the result over all pixels (fp32 [c]: a bias gradient) from the same pass."""
     from ._lib import lib, check
     z = lambda t: (t.hi.data_ptr(), _ptr(t.lo), t.cs) if t is not None else (None, None, 0)
@@ -274,7 +276,7 @@ def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None,
     check(lib.adc_nhwc_grad_assemble(ah, al, ast, a_off, a.h if a is not None else 0, a.w if a is not None else 0, bh, bl, bst, b_off,
                                      act.hi.data_ptr() if act is not None else None, act.cs if act is not None else 0, act_off,
                                      float(slope), out.hi.data_ptr(), _ptr(out.lo), out.cs, out_off, out.n, c, out.h, out.w, _ptr(part),
-                                     _stream()), "adc_nhwc_grad_assemble")
+                                     int(a_quad), _stream()), "adc_nhwc_grad_assemble")
     return (out, part.sum(0)) if colsum else out
 
 
@@ -343,6 +345,20 @@ def quad_maps(device):
     return _QUAD_MAPS[key]
 
 
+def quad_s2_tap_masks():
+    """tap_mask (bit 3a+b) of the low-resolution taps each parity block of a quad stride-2 data gradient uses, and their union."""
+    masks = []
+    for py in range(2):
+        for px in range(2):
+            m = 0
+            for u in range(3):
+                for v in range(3):
+                    if (py + 1 - u) % 2 == 0 and (px + 1 - v) % 2 == 0:
+                        m |= 1 << (((py + 1 - u) // 2 + 1) * 3 + (px + 1 - v) // 2 + 1)
+            masks.append(m)
+    return masks, masks[0] | masks[1] | masks[2] | masks[3]
+
+
 def ged_pack_input(xout_d, cout_d, rgb, dst):
     """torch.cat((xout_d, rgb, cout_d), 1) + NCHW->NHWC + bf16 (hi, lo) split in one pass, into channels [0,16) of ``dst``."""
     from ._lib import lib, check
@@ -404,12 +420,34 @@ def quad_head_finish(q, x0d, weight, bias, h, w):
 
 
 def quad_head_bwd_prep(gy, x10, x0d, gq):
-    """Fills channels [0,8) of ``gq`` (low-resolution NHWC bf16 pair) and returns the summed [oc, 10] x0_d-channel weight / bias gradient."""
+    """Fills ``gq`` (fp32 [n, h/2+2, w/2+2, 4*oc], zero border kept) with the pre-activation gradient of conv10 in quad layout and
+    returns the summed [oc, 10] x0_d-channel weight / bias gradient."""
     from ._lib import lib, check
     n, oc, h, w = gy.shape
     parts = torch.empty((lib.adc_quad_head_bwd_prep_parts(), oc, 10), device=gy.device, dtype=torch.float32)
-    check(lib.adc_quad_head_bwd_prep(gy.contiguous().data_ptr(), x10.data_ptr(), x0d.data_ptr(), gq.hi.data_ptr(), _ptr(gq.lo), gq.cs,
-                                     parts.data_ptr(), n, oc, h, w, _stream()), "adc_quad_head_bwd_prep")
+    check(lib.adc_quad_head_bwd_prep(gy.contiguous().data_ptr(), x10.data_ptr(), x0d.data_ptr(), gq.data_ptr(), parts.data_ptr(), n, oc, h, w,
+                                     _stream()), "adc_quad_head_bwd_prep")
+    return parts.sum(0)
+
+
+def quad_head_wgrad(x9, gq, oc):
+    """dWq [4*oc, 32, 3, 3] = weight gradient of the quad conv10 with respect to its parity weights."""
+    from ._lib import lib, check
+    parts = torch.empty((lib.adc_quad_head_bwd_prep_parts(), 4 * oc, 32, 9), device=gq.device, dtype=torch.float32)
+    check(lib.adc_quad_head_wgrad(x9.hi.data_ptr(), _ptr(x9.lo), x9.cs, gq.data_ptr(), parts.data_ptr(), x9.n, oc, x9.h, x9.w, _stream()),
+          "adc_quad_head_wgrad")
+    return parts.sum(0).reshape(4 * oc, 32, 3, 3)
+
+
+def quad_head_dgrad(x9, gq, wq, g9, extra=None):
+    """G9 = LeakyReLU'(x9) * (data gradient of the quad conv10 [+ extra]) into channels [0,32) of ``g9``; returns its per-channel
+    sums (the bias gradient of conv9)."""
+    from ._lib import lib, check
+    oc = wq.shape[0] // 4
+    parts = torch.empty((lib.adc_quad_head_bwd_prep_parts(), 32), device=gq.device, dtype=torch.float32)
+    eh, el, es = (extra.hi.data_ptr(), _ptr(extra.lo), extra.cs) if extra is not None else (None, None, 0)
+    check(lib.adc_quad_head_dgrad(x9.hi.data_ptr(), x9.cs, gq.data_ptr(), wq.contiguous().data_ptr(), eh, el, es, g9.hi.data_ptr(), _ptr(g9.lo),
+                                  g9.cs, parts.data_ptr(), x9.n, oc, x9.h, x9.w, _stream()), "adc_quad_head_dgrad")
     return parts.sum(0)
 
 

@@ -30,7 +30,7 @@ def _half(v):
 
 class _Plan:
     def __init__(self, n, h, w, out_ch, device):
-        self.n, self.h, self.w = n, h, w
+        self.n, self.h, self.w, self.out_ch = n, h, w, out_ch
         hs, ws = [h], [w]
         for _ in range(5):
             hs.append(_half(hs[-1]))
@@ -64,10 +64,12 @@ class _Plan:
             b["G6"], b["gcat6"] = A(4, 64), A(4, 192)
             b["G5"] = A(5, 128)
             for k, lvl in (("4", 4), ("3", 3), ("2", 2), ("1", 1)):
-                b["gx" + k], b["G" + k] = A(lvl, 128), A(lvl, 128)
+                # gx_k: data gradient of the stride-2 layer that reads x_k, in quad form (4 parity blocks of 80 channels at the
+                # layer's OUTPUT resolution); G_k: pre-activation gradient of x_k
+                b["gx" + k], b["G" + k] = A(lvl + 1, 320), A(lvl, 128)
             b["qin0"] = A(1, 16, dtype=torch.float32)      # conv1's data gradient as 4 parity channels x {xout_d, cout_d}
-            if self.quad:
-                b["gq"], b["G9pre"] = A(1, 64), A(1, 64)
+            if self.quad:      # conv10's pre-activation gradient in quad layout, fp32, zero border
+                b["gq"] = torch.zeros((n, hs[1] + 2, ws[1] + 2, 4 * self.out_ch), device=dev, dtype=torch.float32)
             self.bwd = b
         return self.bwd
 
@@ -114,19 +116,18 @@ def _quad_head_weights(w10):
     return torch.einsum("qst,oct->qocs", up, w10[:, :32].reshape(oc, 32, 9)).reshape(4 * oc, 32, 3, 3)
 
 
-def _quad_head_backward(P, b, w10, wq_prepped, g_x10, x10, x0_d, g_lli, need_x0d):
+def _quad_head_backward(P, b, w10, g_x10, x10, x0_d, g_lli, need_x0d):
     """Backward of the quad conv10: G9 (pre-activation gradient of conv9's output) into b['G9']; returns (g_x0d | None, dW, db,
-    bias gradient of conv9)."""
+    bias gradient of conv9).  With 4*oc parity channels both contractions are direct CUDA-core kernels (csrc/ged_quad.cu)."""
     oc = w10.shape[0]
     gq = b["gq"]
     s = dense.quad_head_bwd_prep(g_x10, x10, x0_d, gq)                    # [oc, 10]: x0_d-channel weight gradient | bias gradient
-    _dgrad_s1(gq, None, b["G9pre"], 0, 32, prepped=wq_prepped)
     extra = None
     if g_lli is not None:      # gradient of the feature tensor cat(up(x9), x0_d): its first 32 channels sum over the 2x2 children
         import torch.nn.functional as F
         extra = dense.to_nhwc_bf16(F.avg_pool2d(g_lli[:, :32], 2) * 4.0, cpad=32, pad=True)
-    _, gb9 = dense.grad_assemble(b["G9"], 32, a=b["G9pre"], b=extra, act=P.x9, slope=0.2, colsum=True)
-    dwq = dense.conv3x3_wgrad_tc(gq, P.x9, 32, 4 * oc, cin_pad=32)         # [4*oc, 32, 3, 3]
+    gb9 = dense.quad_head_dgrad(P.x9, gq, _quad_head_weights(w10), b["G9"], extra)
+    dwq = dense.quad_head_wgrad(P.x9, gq, oc)                             # [4*oc, 32, 3, 3]
     up, _ = dense.quad_maps(w10.device)
     dw = torch.einsum("qst,qocs->oct", up, dwq.reshape(4, oc, 32, 9)).reshape(oc, 32, 3, 3)
     dw = torch.cat((dw, s[:, :9].reshape(oc, 1, 3, 3)), 1)
@@ -211,22 +212,24 @@ class GEDDenseTC(torch.autograd.Function):
             reqs.extend(rs)
         for i in (8, 7, 6, 5):
             add(i, _dgrad_reqs(W[i], 64, 0, dec_cin[i]))
+        # stride-2 layers conv5..conv2: quad form of the data gradient (dense.quad_maps 's2'): per parity block q a stride-1
+        # convolution of the output gradient with the taps of W that reach that parity, [q][ci][co][3x3]
+        _, s2 = dense.quad_maps(dev)
+        masks, mask_all = dense.quad_s2_tap_masks()
         for i in (4, 3, 2, 1):
-            add(i, [(W[i], 2, 80, 0, 80)])
+            wq = torch.einsum("qst,oit->qios", s2, W[i].reshape(80, 80, 9)).reshape(4, 80, 80, 3, 3)
+            add(i, [(wq[q], 0, 128, 0, 80) for q in range(4)])
         # conv1's data gradient is needed for xout_d and cout_d only (channels 0 and 4 of its input): quad form = a stride-1
         # convolution of G1 at ITS resolution with 4 parity x 2 output channels (dense.quad_maps 's2')
-        _, s2 = dense.quad_maps(dev)
         Wd = torch.einsum("qst,ckt->qkcs", s2, torch.stack((W[0][:, 0], W[0][:, 4]), 1).reshape(80, 2, 9)).reshape(8, 80, 3, 3)
         add(0, [(Wd, 0, 128, 0, 80)])
-        if P.quad:
-            add(9, _dgrad_reqs(_quad_head_weights(W[9]), 64, 0, 32))
         prepped = dense.prep_conv3x3_weights_batch(reqs)
         wp = {k: prepped[a:b_] for k, (a, b_) in where.items()}
         # conv10 (LeakyReLU on the output too, confidence_depth_framework.py:506); produces G9 for conv9.
         # Channel 32 of its input is x0_d itself: raw data for the depth-completion net, but the PREDICTED depth when this net is
         # the loss net (confidence_depth_framework.py:230) -- then its gradient is needed too
         if P.quad:
-            g_x0d, gW[9], gB[9], gb9 = _quad_head_backward(P, b, W[9], wp[9], g_x10, x10, x0_d, g_lli, ctx.needs_input_grad[3])
+            g_x0d, gW[9], gB[9], gb9 = _quad_head_backward(P, b, W[9], g_x10, x10, x0_d, g_lli, ctx.needs_input_grad[3])
         else:
             g_x0d, gW[9], gB[9] = dense.ged_head_bwd(P.x9, x0_d, W[9], g_x10, x10, g_lli, b["G9"], ctx.needs_input_grad[3])
             gb9 = cs(b["G9"], 32)
@@ -248,11 +251,12 @@ class GEDDenseTC(torch.autograd.Function):
         for i, xin, xoff, lvl, gxn, gn, gcat, goff in enc:
             gB[i] = gb
             gW[i] = wgb(G, xin, 80, 80, 2, x_off=xoff, cin_pad=80)
-            dense.conv3x3_dgrad_s2_tc(G, 80, wp[i][0], 80, hs[lvl], ws[lvl], out=b[gxn], out_off=0)
-            G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True)
+            for q in range(4):
+                dense.conv3x3_tc(G, 128, wp[i][q], None, 80, 1, 0, out=b[gxn], out_off=80 * q, tap_mask=masks[q])
+            G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True, a_quad=True)
         gB[0] = gb
         gW[0] = dense.conv1x1_wgrad_tc(G, P.x45, 45, 80, cin_pad=48).reshape(80, 3, 3, 5).permute(0, 3, 1, 2).contiguous()
-        dense.conv3x3_tc(G, 128, wp[0][0], None, 8, 1, 0, out=b["qin0"])
+        dense.conv3x3_tc(G, 128, wp[0][0], None, 8, 1, 0, out=b["qin0"], tap_mask=mask_all)
         gin = dense.quad_unshuffle(b["qin0"], 2, hs[0], ws[0])
         grads = []
         for i in range(10):

@@ -181,8 +181,9 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
  * zero-bordered NHWC tensors, cin % 64 == 0, cout <= 128; channels [cout, out_zero_to) of the output slice are zeroed. */
 int adc_conv3x3_s1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo,
                          const float* bias, void* out, void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to,
-                         int N, int H, int W, int cin, int cout, int act, adc_stream_t stream);
-/* 1x1 convolution (plain GEMM over the flat pixels) on the same kernel: only the centre tap of the prepared weights is read. */
+                         int N, int H, int W, int cin, int cout, int act, int tap_mask, adc_stream_t stream);
+/* tap_mask of adc_conv3x3_s1_tc_v2: bit 3u+v set = tap (u,v) may be non-zero (0 = all nine); rows of clear taps are never loaded.
+ * 1x1 convolution (plain GEMM over the flat pixels) on the same kernel: only the centre tap of the prepared weights is read. */
 int adc_conv1x1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo, const float* bias, void* out,
                       void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to, int N, int H, int W, int cin, int cout, int act,
                       adc_stream_t stream);
@@ -219,6 +220,8 @@ int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, i
  *   up-sample + torch.cat, confidence_depth_framework.py:488-504).
  * adc_nhwc_grad_assemble: out = d(act) * ( sum over the up-sampling children of A (at Hd x Wd, identity if equal) + B ),
  *   d(act) = 1 where act > 0 else slope: the backward of up-sample / cat / ReLU / LeakyReLU in one pass; a, b, act optional.
+ *   a_quad: `a` is the quad form of a stride-2 data gradient instead: [N][ceil(H/2)+2][ceil(W/2)+2][4*C], pixel (y,x) reads pixel
+ *   (y/2, x/2), channel block (2*(y&1) + (x&1)) * C (Hd, Wd = its size).
  *   colsum_part (optional): [adc_nhwc_grad_assemble_parts()][C] per-block sums of the output over its pixels; their sum over
  *   dim 0 in index order is the bias gradient of the layer whose activation is `act` (saves adc_nhwc_colsum's extra read).
  * adc_nhwc_colsum: per-channel sum over all pixels (bias gradient), deterministic two-stage reduction. */
@@ -226,7 +229,7 @@ int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_strid
                               int dst_off, int N, int C, int Hs, int Ws, int Hd, int Wd, adc_stream_t stream);
 int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_off, int Hd, int Wd, const void* b, const void* b_lo,
                            int b_stride, int b_off, const void* act, int act_stride, int act_off, float slope, void* out, void* out_lo,
-                           int out_stride, int out_off, int N, int C, int H, int W, float* colsum_part, adc_stream_t stream);
+                           int out_stride, int out_off, int N, int C, int H, int W, float* colsum_part, int a_quad, adc_stream_t stream);
 int adc_nhwc_grad_assemble_parts(void);
 size_t adc_nhwc_colsum_workspace_bytes(int C);
 int adc_nhwc_colsum(const void* g, const void* g_lo, int g_stride, int g_off, int N, int C, int H, int W, float* out, void* workspace,
@@ -256,7 +259,7 @@ int adc_ged_head_bwd_x0d(const float* gy, const float* x10, const float* glli, i
  *                         channels {xout_d, r, g, b, cout_d, 0 x 11} of a tensor with dst_stride >= 16 channels per pixel.
  * adc_quad_head_finish:   out[n][o][2i+py][2j+px] = LeakyReLU_0.2( q[n][i+1][j+1][(2py+px)*oc + o] + bias[o]
  *                         + sum_uv w[o][32][u][v] * x0d[n][2i+py+u-1][2j+px+v-1] ); q fp32 zero-bordered NHWC, w [oc][33][3][3].
- * adc_quad_head_bwd_prep: gpre = gy * LeakyReLU'(x10) -> gq (bf16 hi, lo; channels (2py+px)*oc + o, up to 8 written) and
+ * adc_quad_head_bwd_prep: gpre = gy * LeakyReLU'(x10) -> gq (fp32 zero-bordered [N][H/2+2][W/2+2][4*oc], channel (2py+px)*oc + o) and
  *                         part[adc_quad_head_bwd_prep_parts()][oc][10]: [0,9) weight gradient of the x0_d channel, [9] bias
  *                         gradient (sum over dim 0 in index order = deterministic).
  * adc_quad_unshuffle:     out[k][n][2i+py][2j+px] = q[n][i+1][j+1][(2py+px)*K + k], K in {1,2}; any H, W (H1 = ceil(H/2)). */
@@ -269,8 +272,18 @@ int adc_ged_pack_im2col(const float* xout, const float* cout, const float* rgb, 
 int adc_quad_head_finish(const float* q, int q_stride, const float* x0d, const float* w, const float* bias, float* out, int N, int oc, int H,
                          int W, adc_stream_t stream);
 int adc_quad_head_bwd_prep_parts(void);
-int adc_quad_head_bwd_prep(const float* gy, const float* x10, const float* x0d, void* gq, void* gq_lo, int gq_stride, float* part, int N,
-                           int oc, int H, int W, adc_stream_t stream);
+int adc_quad_head_bwd_prep(const float* gy, const float* x10, const float* x0d, float* gq, float* part, int N, int oc, int H, int W,
+                           adc_stream_t stream);
+/* Backward contractions of the quad conv10 as direct kernels (4*oc parity channels are too thin for the tensor pipe); every
+ * output comes with adc_quad_head_bwd_prep_parts() per-block partial rows to be summed over dim 0 in index order.
+ * adc_quad_head_wgrad: part[.][4*oc][32][9]: dWq[qo][c][3a+b] = sum_p gq[p][qo] * x9[p + (a-1, b-1)][c].
+ * adc_quad_head_dgrad: G9[p][c] = LeakyReLU'(x9[p][c]) * ( sum Wq[qo][c][a][b] * gq[p - (a-1, b-1)][qo] + extra[p][c] ) as bf16
+ *   (hi, lo), part[.][32] = per-channel sums of G9 (bias gradient of conv9); gq fp32 zero-bordered [N][H1+2][W1+2][4*oc]. */
+int adc_quad_head_wgrad(const void* x9, const void* x9_lo, int x9_stride, const float* gq, float* part, int N, int oc, int H1, int W1,
+                        adc_stream_t stream);
+int adc_quad_head_dgrad(const void* x9, int x9_stride, const float* gq, const float* wq, const void* extra, const void* extra_lo,
+                        int extra_stride, void* g9, void* g9_lo, int g9_stride, float* part, int N, int oc, int H1, int W1,
+                        adc_stream_t stream);
 int adc_quad_unshuffle(const float* q, int q_stride, float* out, int N, int K, int H, int W, adc_stream_t stream);
 
 
