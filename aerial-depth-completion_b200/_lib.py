@@ -95,6 +95,7 @@ SIGNATURES = {
                                         c_int, c_int, c_int, _vp]),
     "adc_conv3x3_wgrad_box_tc": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, _vp]),
+    "adc_sum_rows": (c_int, [_vp, c_int, c_int, _vp, _vp]),
     "adc_nhwc_upsample_nearest": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_nhwc_grad_assemble": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int, c_int, ctypes.c_float,
                                        _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, c_int, _vp]),

@@ -208,6 +208,25 @@ __global__ void nhwc_colsum2_kernel(const float* __restrict__ part, int nparts, 
     out[c] = t;
 }
 
+// out[c] = sum_r part[r][c] in a fixed order (rows strided over 8 groups per thread column, then the groups in index order):
+// the second stage of every deterministic reduction of this library (a library reduce over dim 0 of a [~1000, C] tensor
+// launches 1-2 CTAs and measured 26 us).
+__global__ void __launch_bounds__(256) sum_rows_kernel(const float* __restrict__ part, int rows, int C, float* __restrict__ out) {
+    __shared__ float red[8][32];
+    const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
+    float s = 0.f;
+    if (c < C)
+        for (int r = rg; r < rows; r += 8) s += part[(long long)r * C + c];
+    red[rg][cl] = s;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][cl];
+        out[c] = t;
+    }
+}
+
 static int grid_for(long long total) {
     long long b = (total + 255) / 256;
     const long long cap = 148LL * 16;
@@ -223,6 +242,16 @@ static bool bad_slice(const void* hi, int stride, int off, int C) { return !hi |
 using namespace glue;
 
 extern "C" {
+
+int adc_sum_rows(const float* part, int rows, int C, float* out, adc_stream_t stream) {
+    if (!part || !out || rows <= 0 || C <= 0) {
+        adc::set_error("adc_sum_rows: bad argument");
+        return ADC_E_BADARG;
+    }
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)rows * C * 4.0);
+    sum_rows_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(part, rows, C, out);
+    return adc::check_cuda(cudaGetLastError(), "sum_rows_kernel launch");
+}
 
 int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_stride, int src_off, void* dst, void* dst_lo, int dst_stride,
                               int dst_off, int N, int C, int Hs, int Ws, int Hd, int Wd, adc_stream_t stream) {

@@ -264,6 +264,15 @@ def upsample_into(src, c, dst, dst_off, src_off=0):
     return dst
 
 
+def sum_rows(part):
+    """Sum over dim 0 of a contiguous fp32 tensor [rows, ...] in a fixed order (second stage of the two-stage reductions)."""
+    from ._lib import lib, check
+    rows = part.shape[0]
+    out = torch.empty(part.shape[1:], device=part.device, dtype=torch.float32)
+    check(lib.adc_sum_rows(part.data_ptr(), rows, out.numel(), out.data_ptr(), _stream()), "adc_sum_rows")
+    return out
+
+
 def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None, act_off=0, slope=0.0, colsum=False, a_quad=False):
     """out[:, out_off:out_off+c] = d(act) * (sum over the up-sampling children of ``a`` + ``b``); see adc_nhwc_grad_assemble.
     a_quad: ``a`` is the quad form of a stride-2 data gradient (4 parity blocks of c channels at half resolution).
@@ -277,7 +286,7 @@ def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None,
                                      act.hi.data_ptr() if act is not None else None, act.cs if act is not None else 0, act_off,
                                      float(slope), out.hi.data_ptr(), _ptr(out.lo), out.cs, out_off, out.n, c, out.h, out.w, _ptr(part),
                                      int(a_quad), _stream()), "adc_nhwc_grad_assemble")
-    return (out, part.sum(0)) if colsum else out
+    return (out, sum_rows(part)) if colsum else out
 
 
 def colsum(g, c, off=0):
@@ -427,7 +436,7 @@ def quad_head_bwd_prep(gy, x10, x0d, gq):
     parts = torch.empty((lib.adc_quad_head_bwd_prep_parts(), oc, 10), device=gy.device, dtype=torch.float32)
     check(lib.adc_quad_head_bwd_prep(gy.contiguous().data_ptr(), x10.data_ptr(), x0d.data_ptr(), gq.data_ptr(), parts.data_ptr(), n, oc, h, w,
                                      _stream()), "adc_quad_head_bwd_prep")
-    return parts.sum(0)
+    return sum_rows(parts)
 
 
 def quad_head_wgrad(x9, gq, oc):
@@ -436,7 +445,7 @@ def quad_head_wgrad(x9, gq, oc):
     parts = torch.empty((lib.adc_quad_head_bwd_prep_parts(), 4 * oc, 32, 9), device=gq.device, dtype=torch.float32)
     check(lib.adc_quad_head_wgrad(x9.hi.data_ptr(), _ptr(x9.lo), x9.cs, gq.data_ptr(), parts.data_ptr(), x9.n, oc, x9.h, x9.w, _stream()),
           "adc_quad_head_wgrad")
-    return parts.sum(0).reshape(4 * oc, 32, 3, 3)
+    return sum_rows(parts).reshape(4 * oc, 32, 3, 3)
 
 
 def quad_head_dgrad(x9, gq, wq, g9, extra=None):
@@ -448,7 +457,7 @@ def quad_head_dgrad(x9, gq, wq, g9, extra=None):
     eh, el, es = (extra.hi.data_ptr(), _ptr(extra.lo), extra.cs) if extra is not None else (None, None, 0)
     check(lib.adc_quad_head_dgrad(x9.hi.data_ptr(), x9.cs, gq.data_ptr(), wq.contiguous().data_ptr(), eh, el, es, g9.hi.data_ptr(), _ptr(g9.lo),
                                   g9.cs, parts.data_ptr(), x9.n, oc, x9.h, x9.w, _stream()), "adc_quad_head_dgrad")
-    return parts.sum(0)
+    return sum_rows(parts)
 
 
 def quad_unshuffle(q, k, h, w):

@@ -17,11 +17,14 @@ plus zero borders) only, so borders and pad channels stay zero for the lifetime 
 fixed addresses.  A second forward of the same module before the backward of the first would overwrite saved activations; the
 node checks for that and raises.
 """
+import os
+
 import torch
 
 from . import dense
 
 _RELU, _LEAKY = 1, 2
+_SIDE_STREAM = os.environ.get("ADC_TC_SIDE_STREAM", "1") != "0"
 
 
 def _half(v):
@@ -51,6 +54,7 @@ class _Plan:
         self.q10 = A(1, 16, dtype=torch.float32) if self.quad else None
         self.bwd = None
         self.forward_id = 0
+        self.side = None               # second stream: weight gradients run beside the data-gradient chain
 
     def backward_buffers(self):
         if self.bwd is None:
@@ -201,9 +205,26 @@ class GEDDenseTC(torch.autograd.Function):
         W = ctx.saved_tensors[2:]
         b = P.backward_buffers()
         hs, ws, oc = P.hs, P.ws, ctx.oc
-        wg, wgb, asm, cs = dense.conv3x3_wgrad_tc, dense.conv3x3_wgrad_box_tc, dense.grad_assemble, dense.colsum
+        asm, cs = dense.grad_assemble, dense.colsum
         gW, gB = [None] * 10, [None] * 10
         dev = x10.device
+        # Weight gradients leave the critical path: each is enqueued on a second stream as soon as its output gradient exists and
+        # overlaps the data-gradient chain of the layers below (the small levels launch far fewer CTAs than there are SMs).
+        main = torch.cuda.current_stream()
+        if P.side is None:
+            P.side = torch.cuda.Stream()
+        side = P.side if _SIDE_STREAM else main
+
+        def off_path(fn, *a, **kw):
+            if side is main:
+                return fn(*a, **kw)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = fn(*a, **kw)
+            out.record_stream(main)
+            return out
+        wg = lambda *a, **kw: off_path(dense.conv3x3_wgrad_tc, *a, **kw)
+        wgb = lambda *a, **kw: off_path(dense.conv3x3_wgrad_box_tc, *a, **kw)
         # all data-gradient weights of the step (transposed / flipped, per output-channel chunk) in ONE launch
         dec_cin = {8: 112, 7: 144, 6: 144, 5: 160}
         reqs, where = [], {}
@@ -217,7 +238,7 @@ class GEDDenseTC(torch.autograd.Function):
         _, s2 = dense.quad_maps(dev)
         masks, mask_all = dense.quad_s2_tap_masks()
         for i in (4, 3, 2, 1):
-            wq = torch.einsum("qst,oit->qios", s2, W[i].reshape(80, 80, 9)).reshape(4, 80, 80, 3, 3)
+            wq = torch.einsum("qst,oit->qios", s2, W[i].reshape(80, 80, 9)).contiguous().reshape(4, 80, 80, 3, 3)
             add(i, [(wq[q], 0, 128, 0, 80) for q in range(4)])
         # conv1's data gradient is needed for xout_d and cout_d only (channels 0 and 4 of its input): quad form = a stride-1
         # convolution of G1 at ITS resolution with 4 parity x 2 output channels (dense.quad_maps 's2')
@@ -255,9 +276,12 @@ class GEDDenseTC(torch.autograd.Function):
                 dense.conv3x3_tc(G, 128, wp[i][q], None, 80, 1, 0, out=b[gxn], out_off=80 * q, tap_mask=masks[q])
             G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True, a_quad=True)
         gB[0] = gb
-        gW[0] = dense.conv1x1_wgrad_tc(G, P.x45, 45, 80, cin_pad=48).reshape(80, 3, 3, 5).permute(0, 3, 1, 2).contiguous()
+        gw1 = off_path(dense.conv1x1_wgrad_tc, G, P.x45, 45, 80, cin_pad=48)       # [80, 45], channel (3u+v)*5 + c
         dense.conv3x3_tc(G, 128, wp[0][0], None, 8, 1, 0, out=b["qin0"], tap_mask=mask_all)
         gin = dense.quad_unshuffle(b["qin0"], 2, hs[0], ws[0])
+        if side is not main:
+            main.wait_stream(side)
+        gW[0] = gw1.reshape(80, 3, 3, 5).permute(0, 3, 1, 2).contiguous()
         grads = []
         for i in range(10):
             grads += [gW[i], gB[i]]

@@ -56,6 +56,18 @@ def _load_peaks():
 PEAKS = _load_peaks()
 
 
+def _load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the NConv kernels from the committed `ncu --set full` capture
+    (profiles/r1_nconv_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep): kernel name as in the roofline table."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_nconv_traffic.json")))
+    except Exception:
+        return {}
+
+
+TRAFFIC = _load_traffic()
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -280,7 +292,8 @@ def b200_arm(args):
         "config": {"workload": WORKLOAD, "precision": args.precision, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": "dp%d (one process per GPU, NCCL all-reduce of flat fp32 gradients)" % world,
                    "l2": "inputs rotate through a %.0f MB pool of distinct batches (> 126 MB L2)" % pool_mb,
-                   "dense_backend": ("hand-written tcgen05 implicit GEMM (conv1..conv10 forward, data and weight gradients)"
+                   "dense_backend": ("hand-written tcgen05 implicit GEMM (conv1..conv9 forward, data and weight gradients; conv10 = quad-form "
+                                     "tensor-core forward + direct CUDA-core backward)"
                                      if args.precision in ("bf16", "bf16x3") else _dense.BACKEND),
                    "launch": "eager" if args.no_graph else "one CUDA graph per step (forward+loss+backward+allreduce+adam)",
                    "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
@@ -292,18 +305,21 @@ def b200_arm(args):
     if roof:
         dom = roof["dominant"]
         line["roofline"] = {"bound": "hbm", "achieved": round(dom["gbs"], 1), "peak": peak, "unit": "GB/s",
-                            "frac": round(dom["gbs"] / peak, 4), "traffic": None, "kernel": dom["name"],
+                            "frac": round(dom["gbs"] / peak, 4), "traffic": (TRAFFIC.get(dom["name"]) or {}).get("dram_bytes_per_launch"),
+                            "traffic_source": (TRAFFIC.get(dom["name"]) or {}).get("source"), "kernel": dom["name"],
                             "launch_us": round(dom["us"], 2), "algorithmic_mb_per_launch": round(dom["mb"], 2),
                             "peak_source": peak_src, "nconv_kernels": roof["table"]}
         if roof.get("tensor"):
-            mma = [r for r in roof["tensor"] if "tflops" in r]
-            tus = sum(r["us_per_step"] for r in mma)
-            tfl = sum(r["algorithmic_gflop_per_step"] for r in mma) / tus * 1e3 if tus else 0.0
+            alg = ged_algorithmic_flops(B)
+            mult = 2 if args.precision == "bf16x3" else 1
             line["roofline"]["tensor_kernels"] = {
-                "rows": roof["tensor"], "mma_kernels_us_per_step": round(tus, 1), "algorithmic_tflops": round(tfl, 1),
-                "peak_tflops_bf16_sustained": PEAKS.get("bf16_tflops_sustained"), "mma_per_product": 3 if args.precision == "bf16x3" else 1,
-                "frac_of_peak_executed": round(tfl * (3 if args.precision == "bf16x3" else 1) / PEAKS["bf16_tflops_sustained"], 4)
-                if PEAKS.get("bf16_tflops_sustained") else None}
+                "rows": roof["tensor"], "mma_kernels_us_per_step": round(roof["mma_us"], 1),
+                "dense_path_us_per_step": round(roof["dense_us"], 1),
+                "algorithmic_gflop_per_step": round(alg / 1e9, 1),
+                "algorithmic_tflops_over_mma_kernels": round(alg / roof["mma_us"] / 1e6, 1),
+                "peak_tflops_bf16_sustained": PEAKS.get("bf16_tflops_sustained"), "mma_per_product": mult,
+                "note": "bf16x3 executes 2 MMAs per product (hi and lo activations against concatenated [W_hi | W_lo]); padded channels and the "
+                        "zero taps of the quad forms are executed but not counted as algorithmic FLOPs"}
     if world == 1 and not args.no_extras:
         line["extra"] = {"gms_inference_b32": gms_inference(dev)}
     if not args.no_cpu_baseline and world == 1:
@@ -362,17 +378,17 @@ def gms_inference(dev, B=32):
 
 
 def ged_algorithmic_flops(B):
-    """FLOPs per training step of the dense layers of GEDNet by kernel kind (2*N*Ho*Wo*9*Cin*Cout per convolution, real channel
-    counts: no padding, no bf16x3 triple counting; confidence_depth_framework.py:442-452)."""
+    """FLOPs per training step of GEDNet's dense layers conv1..conv10 (2*N*Ho*Wo*9*Cin*Cout per convolution, real channel counts:
+    no padding, no quad-form zero taps, no bf16x3 double counting; confidence_depth_framework.py:442-452): forward + data gradient
+    + weight gradient = 3x the forward, minus conv1's data gradient for the three rgb channels nobody needs."""
     hs, ws = [H], [W]
     for _ in range(5):
         hs.append((hs[-1] - 1) // 2 + 1)
         ws.append((ws[-1] - 1) // 2 + 1)
     f = lambda lvl, ci, co: 2.0 * B * hs[lvl] * ws[lvl] * 9 * ci * co
-    enc = [f(1, 5, 80), f(2, 80, 80), f(3, 80, 80), f(4, 80, 80), f(5, 80, 80)]
-    dec = [f(4, 160, 64), f(3, 144, 64), f(2, 144, 32), f(1, 112, 32)]      # conv10 runs on direct (CUDA-core) kernels
-    return {"tc_fprop_s2": sum(enc), "tc_conv_s1(fprop+dgrad)": 2 * sum(dec), "tc_dgrad_s2": sum(enc), "tc_wgrad_s1": sum(dec),
-            "tc_wgrad_s2": sum(enc)}
+    fwd = [f(1, 5, 80), f(2, 80, 80), f(3, 80, 80), f(4, 80, 80), f(5, 80, 80), f(4, 160, 64), f(3, 144, 64), f(2, 144, 32), f(1, 112, 32),
+           f(0, 33, 1)]
+    return 3.0 * sum(fwd) - f(1, 3, 80)
 
 
 def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, detail_path=""):
@@ -384,8 +400,10 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, detail_path=""):
     from aerial_depth_completion_b200._lib import lib
     names = {0: "nconv_fwd", 1: "nconv_bwd_data", 2: "nconv_bwd_weight", 3: "pool_fwd", 4: "pool_bwd", 5: "upsample_bwd",
              6: "head_fwd", 7: "head_bwd"}
-    tc_names = {20: "tc_fprop_s2", 21: "tc_conv_s1(fprop+dgrad)", 22: "tc_dgrad_s2", 23: "tc_wgrad_s1", 24: "tc_wgrad_s2", 25: "tc_glue",
-                26: "tc_layout", 27: "tc_prep_weights", 28: "ged_head10(direct)"}
+    tc_names = {20: "tc_conv_box(stride-2 fprop)", 21: "tc_conv_rowseg(fprop, 1x1, data gradients incl. quad forms)", 22: "tc_dgrad_s2_parity",
+                23: "tc_wgrad_flat(stride-1, 1x1)", 24: "tc_wgrad_box(stride-2)", 25: "tc_glue(upsample, grad assemble + bias grad)",
+                26: "tc_layout(im2col pack, unshuffle)", 27: "tc_prep_weights", 28: "conv10 quad head (direct kernels)"}
+    mma_kinds = (20, 21, 22, 23, 24)
     calls = ("nconv1@L0", "nconv2@L0", "nconv3@L0", "nconv2@L1", "nconv3@L1", "nconv2@L2", "nconv2@L3", "nconv4@L2", "nconv5@L1",
              "nconv6@L0", "nconv7@L0")
     agg, tc = {}, {}
@@ -432,16 +450,13 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, detail_path=""):
     d = table[0]
     out = {"dominant": {"name": d["name"], "us": d["us"], "mb": d["mb"], "gbs": d["gbs"]}, "table": table[:12]}
     if tc:
-        alg = ged_algorithmic_flops(B)
         rows = []
         for k, (us, work, cnt) in tc.items():
-            r = {"name": k, "launches_per_step": cnt // reps, "us_per_step": round(us / reps, 1)}
-            if k in alg:
-                r["algorithmic_gflop_per_step"] = round(alg[k] / 1e9, 1)
-                r["tflops"] = round(alg[k] / (us / reps) / 1e6, 1)
-            rows.append(r)
+            rows.append({"name": k, "launches_per_step": cnt // reps, "us_per_step": round(us / reps, 1)})
         rows.sort(key=lambda r: -r["us_per_step"])
         out["tensor"] = rows
+        out["mma_us"] = sum(us for k, (us, work, cnt) in tc.items() if k in [tc_names[q] for q in mma_kinds]) / reps
+        out["dense_us"] = sum(us for us, work, cnt in tc.values()) / reps
     return out
 
 

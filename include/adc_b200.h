@@ -225,6 +225,9 @@ int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, i
  *   colsum_part (optional): [adc_nhwc_grad_assemble_parts()][C] per-block sums of the output over its pixels; their sum over
  *   dim 0 in index order is the bias gradient of the layer whose activation is `act` (saves adc_nhwc_colsum's extra read).
  * adc_nhwc_colsum: per-channel sum over all pixels (bias gradient), deterministic two-stage reduction. */
+/* out[c] = sum over r of part[r][c], fixed order: second stage of the deterministic two-stage reductions (partial rows written by
+ * adc_nhwc_grad_assemble, adc_quad_head_*). */
+int adc_sum_rows(const float* part, int rows, int C, float* out, adc_stream_t stream);
 int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_stride, int src_off, void* dst, void* dst_lo, int dst_stride,
                               int dst_off, int N, int C, int Hs, int Ws, int Hd, int Wd, adc_stream_t stream);
 int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_off, int Hd, int Wd, const void* b, const void* b_lo,
