@@ -122,6 +122,13 @@ SIGNATURES = {
     "adc_conv3x3_wgrad_tc_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_wgrad_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      _vp]),
+    "adc_conf_head_workspace_bytes": (ctypes.c_size_t, [c_int]),
+    "adc_conf_head_coef_floats": (c_int, []),
+    "adc_conf_bn_stats": (c_int, [_vp, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, c_int, _vp,
+                                  _vp, _vp]),
+    "adc_conf_head_apply": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_conf_head_bwd": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int,
+                                  _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -478,6 +478,42 @@ def ged_head_bwd_x0d(gy, x10, glli, weight):
     return gx0d
 
 
+# ---- cbr3-c1 confidence head behind its 3x3 convolution (csrc/conf_head.cu) -----------------------------------------------------
+def conf_bn_stats(y, c, gamma, beta, running_mean, running_var, momentum, eps, training):
+    """Batch (training) or running (eval) statistics of conv1's fp32 NHWC output -> the coefficient block the other conf_head calls
+    read; in training mode the running statistics are updated in place like nn.BatchNorm2d does."""
+    from ._lib import lib, check
+    dev = y.hi.device
+    coef = torch.empty(lib.adc_conf_head_coef_floats(), device=dev, dtype=torch.float32)
+    ws = torch.empty(lib.adc_conf_head_workspace_bytes(c) // 8, device=dev, dtype=torch.float64)
+    check(lib.adc_conf_bn_stats(y.hi.data_ptr(), y.cs, y.n, c, y.h, y.w, gamma.detach().data_ptr(), beta.detach().data_ptr(),
+                                _ptr(running_mean), _ptr(running_var), float(momentum), float(eps), int(training), coef.data_ptr(),
+                                ws.data_ptr(), _stream()), "adc_conf_bn_stats")
+    return coef, ws
+
+
+def conf_head_apply(y, c, coef, w2, b2):
+    """sigmoid(conv1x1(LeakyReLU_0.2(BN(y)))) in one pass: [n, 1, h, w] fp32."""
+    from ._lib import lib, check
+    conf = torch.empty((y.n, 1, y.h, y.w), device=y.hi.device, dtype=torch.float32)
+    check(lib.adc_conf_head_apply(y.hi.data_ptr(), y.cs, coef.data_ptr(), w2.detach().contiguous().data_ptr(), b2.detach().data_ptr(),
+                                  conf.data_ptr(), y.n, c, y.h, y.w, _stream()), "adc_conf_head_apply")
+    return conf
+
+
+def conf_head_bwd(y, c, coef, ws, w2, gconf, conf, training, gy):
+    """Backward of conf_head_apply + BatchNorm: fills ``gy`` (zero-bordered NHWC bf16 activation) with dL/dy and returns
+    (gw2 [c], gb2 [1], ggamma [c], gbeta [c])."""
+    from ._lib import lib, check
+    dev = y.hi.device
+    gw2, gg, gb = (torch.empty(c, device=dev, dtype=torch.float32) for _ in range(3))
+    gb2 = torch.empty(1, device=dev, dtype=torch.float32)
+    check(lib.adc_conf_head_bwd(y.hi.data_ptr(), y.cs, coef.data_ptr(), w2.detach().contiguous().data_ptr(), gconf.data_ptr(), conf.data_ptr(),
+                                int(training), gy.hi.data_ptr(), _ptr(gy.lo), gy.cs, gw2.data_ptr(), gb2.data_ptr(), gg.data_ptr(),
+                                gb.data_ptr(), ws.data_ptr(), y.n, c, y.h, y.w, _stream()), "adc_conf_head_bwd")
+    return gw2, gb2, gg, gb
+
+
 def cached_weights(conv, embed_1x1=False, cin_pad=None):
     """Prepared bf16 weights of a Conv2d, kept ON the module and re-prepared only when the Parameter changes (storage,
     in-place version counter) or the precision mode / channel padding does."""

@@ -224,6 +224,10 @@ class CBR3C1Confidence(nn.Module):
             init_weights(m)
 
     def forward(self, x):
+        if dense.tc_enabled() and x.is_cuda and self.conv1.in_channels <= 80:
+            # conv1 + its gradients on the tcgen05 kernels, BN + LeakyReLU + conv2 + sigmoid fused (csrc/conf_head.cu)
+            from .. import tc_train
+            return tc_train.conf_head(self, x)
         return torch.sigmoid(self.conv2(self.relu1(self.bn1(self.conv1(x)))))
 
 

@@ -294,3 +294,47 @@ def ged_dense(net, xout_d, cout_d, rgb, x0_d, want_lli):
         m = getattr(net, "conv%d" % i)
         params += [m.weight, m.bias]
     return GEDDenseTC.apply(xout_d, cout_d, rgb, x0_d, want_lli, net, *params)
+
+
+class ConfHeadTC(torch.autograd.Function):
+    """cbr3-c1 confidence head (confidence_depth_framework.py:299-329) on the B200 path: features [N,C,H,W] fp32 -> conf [N,1,H,W].
+    conv1 (3x3, no bias), its data gradient and its weight gradient = tcgen05 kernels on zero-bordered NHWC bf16 (hi, lo) tensors;
+    BatchNorm (batch statistics + running-statistics update in train mode) + LeakyReLU(0.2) + conv2 (1x1) + sigmoid and their
+    backward = the four fused passes of csrc/conf_head.cu over conv1's fp32 output."""
+
+    @staticmethod
+    def forward(ctx, feat, w1, gamma, beta, w2, b2, bn):
+        n, c, h, w = feat.shape
+        training = bool(bn.training or bn.running_mean is None)
+        cpad = dense._r64(c)
+        X = dense.to_nhwc_bf16(feat, cpad=cpad, pad=True)
+        Y = dense.conv3x3_tc(X, cpad, dense.prep_conv3x3_weights(w1, cin_pad=cpad), None, c, 1, 0, out_f32=True)
+        momentum = bn.momentum if bn.momentum is not None else 0.1
+        coef, ws = dense.conf_bn_stats(Y, c, gamma, beta, bn.running_mean, bn.running_var, momentum, bn.eps, training)
+        conf = dense.conf_head_apply(Y, c, coef, w2, b2)
+        if training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        ctx.X, ctx.Y, ctx.coef, ctx.ws, ctx.training = X, Y, coef, ws, training
+        ctx.save_for_backward(conf, w1, w2)
+        return conf
+
+    @staticmethod
+    def backward(ctx, gconf):
+        conf, w1, w2 = ctx.saved_tensors
+        X, Y = ctx.X, ctx.Y
+        n, c, h, w = X.n, w1.shape[0], X.h, X.w
+        G = dense.new_act(n, h, w, X.cs, conf.device, pad=True, border_only=True)
+        gw2, gb2, gg, gb = dense.conf_head_bwd(Y, c, ctx.coef, ctx.ws, w2, gconf.contiguous(), conf, ctx.training, G)
+        gw1 = dense.conv3x3_wgrad_tc(G, X, c, c, cin_pad=X.cs)
+        gfeat = None
+        if ctx.needs_input_grad[0]:
+            out = dense.new_act(n, h, w, dense._r64(c), conf.device, pad=True, border_only=True, dtype=torch.float32)
+            _dgrad_s1(G, w1, out, 0, c)
+            gfeat = dense.to_nchw_f32(out, c)
+        ctx.X = ctx.Y = None
+        return gfeat, gw1, gg, gb, gw2.view_as(w2), gb2, None
+
+
+def conf_head(head, feat):
+    """CBR3C1Confidence.forward on the tensor-core path."""
+    return ConfHeadTC.apply(feat, head.conv1.weight, head.bn1.weight, head.bn1.bias, head.conv2.weight, head.conv2.bias, head.bn1)

@@ -175,6 +175,21 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
+def _finish(world):
+    """End of a multi-rank run.  Measured on 2xB200: dist.destroy_process_group() after the step graph (which holds the captured
+    NCCL all-reduce) has been replayed never returns, so the ranks meet at a last barrier, flush and leave without tearing the
+    communicator down (the process exit releases it)."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -278,8 +293,7 @@ def b200_arm(args):
     roof = kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, args.kernel_detail if rank == 0 else "")
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     peak, peak_src = peaks()
     frames = B * world * args.steps
@@ -327,8 +341,7 @@ def b200_arm(args):
         line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "3 timed steps of %d frame(s) of the same workload with torch CPU ops (oracle/)" % fr}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
 
 
 def gms_inference(dev, B=32):

@@ -289,6 +289,28 @@ int adc_quad_head_dgrad(const void* x9, int x9_stride, const float* gq, const fl
                         adc_stream_t stream);
 int adc_quad_unshuffle(const float* q, int q_stride, float* out, int N, int K, int H, int W, adc_stream_t stream);
 
+/* ---- cbr3-c1 confidence head behind its 3x3 convolution (confidence_depth_framework.py:299-329: conv1 -> bn1 -> LeakyReLU(0.2) ->
+ * conv2 1x1 + bias -> sigmoid).  conv1, its data gradient and its weight gradient run on the tensor-core kernels above; these
+ * entry points replace nn.BatchNorm2d + nn.LeakyReLU + the 1x1 nn.Conv2d + torch.sigmoid and their autograd nodes.
+ * y: conv1's output, fp32 zero-bordered NHWC [N][H+2][W+2][y_stride], channels [0,C), C <= 128, pad channels zero.
+ * coef: adc_conf_head_coef_floats() floats, rows of 128: a = gamma*rstd | b = beta - mean*a | mean | rstd | k1 | k2 (backward).
+ * adc_conf_bn_stats: training != 0: batch statistics (biased variance, like F.batch_norm) and, if running_mean/var are non-NULL,
+ *   their momentum update with the unbiased variance; training == 0: the running statistics.  Fills coef rows 0..3.
+ * adc_conf_head_apply: conf [N][1][H][W] = sigmoid(b2 + sum_c w2[c] * lrelu_0.2(a[c]*y[c] + b[c])).
+ * adc_conf_head_bwd: from gconf = dL/dconf: gw2 [C], gb2 [1], ggamma [C], gbeta [C] (deterministic two-stage reductions) and
+ *   gy = dL/dy as zero-bordered NHWC bf16 (hi, lo; lo may be NULL) [N][H+2][W+2][gy_stride] (interior pixels, ALL gy_stride
+ *   channels written, zeros past C; the border is not touched).  workspace: adc_conf_head_workspace_bytes(C) bytes. */
+size_t adc_conf_head_workspace_bytes(int C);
+int adc_conf_head_coef_floats(void);
+int adc_conf_bn_stats(const float* y, int y_stride, int N, int C, int H, int W, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float eps, int training, float* coef, void* workspace,
+                      adc_stream_t stream);
+int adc_conf_head_apply(const float* y, int y_stride, const float* coef, const float* w2, const float* b2, float* conf, int N, int C, int H,
+                        int W, adc_stream_t stream);
+int adc_conf_head_bwd(const float* y, int y_stride, float* coef, const float* w2, const float* gconf, const float* conf, int training,
+                      void* gy, void* gy_lo, int gy_stride, float* gw2, float* gb2, float* ggamma, float* gbeta, void* workspace, int N, int C,
+                      int H, int W, adc_stream_t stream);
+
 
 #ifdef __cplusplus
 }
