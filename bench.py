@@ -336,6 +336,10 @@ def b200_arm(args):
                         "zero taps of the quad forms are executed but not counted as algorithmic FLOPs"}
     if world == 1 and not args.no_extras:
         line["extra"] = {"gms_inference_b32": gms_inference(dev)}
+        try:
+            line["extra"]["full_framework_dc1_cf1_ln1_480x752"] = full_framework_training(dev)
+        except Exception as e:       # an extra measurement must never cost the headline line
+            line["extra"]["full_framework_dc1_cf1_ln1_480x752"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if not args.no_cpu_baseline and world == 1:
         fps, ms, cores, fr = cpu_reference_run(3, 1, args.cpu_frames or 1)
         line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
@@ -388,6 +392,60 @@ def gms_inference(dev, B=32):
     finally:
         dense.set_precision(prev)
     return out
+
+
+def full_framework_training(dev, B=8, HH=480, WW=752, steps=8):
+    """BASELINE.json configs[3]: ged_depthcompnet dc + cbr3-c1 confidence head + ged_depthcompnet loss net, training mode
+    dc1-cf1-ln1, DualLoss(l2, 0.5), rgbdw frames of the aerial shape 480x752, one GPU of the box.  Every convolution of the three
+    nets (NConv pyramids, both encoder-decoders, the head's 3x3) and the head's BN/LeakyReLU/1x1/sigmoid run on the library's
+    kernels (bf16x3 mode); one CUDA graph per step."""
+    import contextlib
+    import io
+    import torch
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    from aerial_depth_completion_b200 import dense, parallel, _lib
+    torch.manual_seed(0)
+    f = mc.ConfidenceDepthFrameworkFactory()
+    prev = dense.PRECISION
+    try:
+        dense.set_precision("bf16x3")
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = f.create_model("rgbdw", "dc1-cf1-ln1", "ged_depthcompnet", "", "cbr3-c1", "", "ged_depthcompnet", "")
+            m, params = f.to_device(m)
+            m.train()
+        crit, _ = f.create_loss("l2", True, 0.5)
+        opt = torch.optim.Adam(params, lr=1e-5, capturable=True)
+        tr = parallel.DataParallelTrainer(m, crit, opt, params, world_size=1)
+        g = torch.Generator(device=dev).manual_seed(11)
+        xs, ts = [], []
+        for _ in range(3):
+            x = torch.rand(B, 5, HH, WW, device=dev, generator=g)
+            gt = torch.rand(B, 1, HH, WW, device=dev, generator=g) * 9.0 + 1.0
+            mask = (torch.rand(B, 1, HH, WW, device=dev, generator=g) < 500.0 / (HH * WW)).float()
+            x[:, 3:4] = gt * mask
+            x[:, 4:5] = mask
+            xs.append(x)
+            ts.append(gt)
+        l0 = _lib.lib.adc_launch_count()
+        tr._eager_step(xs[0], ts[0])
+        launches = _lib.lib.adc_launch_count() - l0
+        tr.capture(xs[0], ts[0])
+        for i in range(3):
+            tr.step(xs[i % 3], ts[i % 3])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss = tr.step(xs[i % 3], ts[i % 3])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"workload": "ged_depthcompnet + cbr3-c1 + ged_depthcompnet loss net, dc1-cf1-ln1, DualLoss(l2, 0.5), rgbdw %dx%d" % (HH, WW),
+                "batch": B, "ms_per_step": round(ms, 3), "frames_s": round(B / ms * 1e3, 1), "library_launches_per_step": int(launches),
+                "trainable_parameters": int(sum(p.numel() for p in params)), "loss": round(float(loss), 5), "precision": "bf16x3",
+                "launch": "one CUDA graph per step"}
+    finally:
+        dense.set_precision(prev)
 
 
 def ged_algorithmic_flops(B):
