@@ -129,6 +129,10 @@ SIGNATURES = {
     "adc_conf_head_apply": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_conf_head_bwd": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp, _vp, c_int, c_int, c_int, c_int,
                                   _vp]),
+    "adc_loss_metrics_workspace_bytes": (ctypes.c_size_t, []),
+    "adc_masked_loss_fwd": (c_int, [_vp, _vp, c_ll, c_int, _vp, _vp, _vp]),
+    "adc_masked_loss_bwd": (c_int, [_vp, _vp, _vp, _vp, c_ll, c_int, _vp, _vp]),
+    "adc_depth_metrics": (c_int, [_vp, _vp, _vp, ctypes.c_float, c_ll, _vp, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

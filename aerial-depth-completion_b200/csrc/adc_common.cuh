@@ -73,6 +73,8 @@ struct SrcP {
     NearestMap mh, mw; // dst(row/col of the layer) -> src index
     int up;            // 1 if (H,W) differs from the layer size (nearest-upsampled on the fly)
     int tma;           // 1 if the tile is fetched with a TMA box copy (map passed separately)
+    int up2;           // 1 if the source is EXACTLY 2x nearest-upsampled and TMA-able: the low-resolution box is fetched by TMA
+                       // into the tail of the plane and expanded in shared memory (expand_up2_planes)
 };
 
 // Compile-time loop: f(std::integral_constant<int, 0>{}) ... f(<N-1>).  The row loops of the convolution cores MUST be

@@ -64,11 +64,17 @@ static float* g_stage = nullptr;  // [ADC_WSLOTS][2][ADC_PYR_CALLS][kWStride] de
 static int* g_counters = nullptr; // tile-scheduler counters of the persistent kernels (self-resetting)
 static int g_persist = 1, g_sms = 148;
 static int g_use_tma = -1;
+static int g_side_on = 1;        // weight-gradient kernels of adc_pyramid_bwd on a second stream (ADC_NO_SIDE_STREAM=1 disables)
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_ev_fork[ADC_PYR_CALLS], g_ev_join[ADC_PYR_CALLS];
+static int g_up2 = 1;           // exact-2x upsampled sources through TMA + in-place expansion (ADC_NO_UP2=1 disables)
 
 static int ensure_init() {
     if (g_use_tma < 0) {
         const char* e = getenv("ADC_NO_TMA");   // testing aid: force the gather loaders everywhere
         g_use_tma = (e && e[0] == '1') ? 0 : 1;
+        const char* u = getenv("ADC_NO_UP2");
+        g_up2 = (u && u[0] == '1') ? 0 : 1;
     }
     if (g_stage) return 0;
     const char* pe = getenv("ADC_FWD_MODE");     // 0: one tile per CTA, 2: persistent, 1 (default): persistent only for gathered sources
@@ -79,6 +85,15 @@ static int ensure_init() {
     ADC_CUDA(cudaMalloc(&g_counters, sizeof(int) * 64));
     ADC_CUDA(cudaMemset(g_counters, 0, sizeof(int) * 64));
     ADC_CUDA(cudaMalloc(&g_stage, sizeof(float) * ADC_WSLOTS * 2 * ADC_PYR_CALLS * kWStride));
+    const char* se = getenv("ADC_NO_SIDE_STREAM");
+    g_side_on = (se && se[0] == '1') ? 0 : 1;
+    if (g_side_on) {
+        ADC_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+        for (int k = 0; k < ADC_PYR_CALLS; ++k) {
+            ADC_CUDA(cudaEventCreateWithFlags(&g_ev_fork[k], cudaEventDisableTiming));
+            ADC_CUDA(cudaEventCreateWithFlags(&g_ev_join[k], cudaEventDisableTiming));
+        }
+    }
     return 0;
 }
 
@@ -104,7 +119,9 @@ static SrcP make_srcp(const float2* p, long long bs, int ch, int Hs, int Ws, int
     r.mw = NearestMap::make(Ws, W);
     r.up = (Hs != H || Ws != W) ? 1 : 0;
     // TMA needs a 16-byte aligned base and 16-byte multiples for every stride: even width, even batch stride
-    r.tma = (g_use_tma == 1 && !r.up && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (Ws % 2 == 0) && (bs % 2 == 0)) ? 1 : 0;
+    const bool tma_able = g_use_tma == 1 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (Ws % 2 == 0) && (bs % 2 == 0);
+    r.tma = (tma_able && !r.up) ? 1 : 0;
+    r.up2 = (tma_able && g_up2 && H == 2 * Hs && W == 2 * Ws) ? 1 : 0;
     return r;
 }
 
@@ -135,8 +152,11 @@ static int fill_maps(Maps2* maps, const SrcP& s0, const SrcP* s1, int N) {
     memset(maps, 0, sizeof(*maps));
     using C = TileCfg<K>;
     int rc = 0;
+    using U = Up2Cfg<K>;
     if (s0.tma && (rc = make_pair_map(&maps->m0, s0, N, C::SWP, C::SH))) return rc;
+    if (s0.up2 && (rc = make_pair_map(&maps->m0, s0, N, U::LW, U::LH))) return rc;
     if (s1 && s1->tma && (rc = make_pair_map(&maps->m1, *s1, N, C::SWP, C::SH))) return rc;
+    if (s1 && s1->up2 && (rc = make_pair_map(&maps->m1, *s1, N, U::LW, U::LH))) return rc;
     return 0;
 }
 
@@ -182,7 +202,7 @@ static int launch_fwd(const SrcP& s0, const SrcP* s1, float2* out, int N, int H,
     // Measured (profiles/r1_forward_variants.txt): with every source TMA-fed the one-tile-per-CTA kernel is fastest (27 us vs
     // 32 us for nconv2@L0, B=32); when a source goes through the gather path (nearest-upsampled half of nconv4-6) the
     // persistent kernel with cp.async prefetch wins (43 us vs 61 us for nconv6@L0).
-    const bool gathered = !s0.tma || (s1 && !s1->tma);
+    const bool gathered = !(s0.tma || s0.up2) || (s1 && !(s1->tma || s1->up2));
     if (g_persist == 2 || (g_persist == 1 && gathered)) return launch_fwd_persist<CI, K>(s0, s1, out, N, H, W, wimg, st);
     static bool done = false;
     const int smem = C::smem_bytes(CI);
@@ -771,6 +791,9 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
     auto upb = [&](int l) { return reinterpret_cast<float2*>(X + B.up[l]); };
     auto fimg = [&](int call) { return wimg_index(a->slot, 0, call); };
     auto bimg = [&](int call) { return wimg_index(a->slot, 1, call); };
+    // profiling runs keep everything on one stream so that the per-kernel event pairs time each kernel alone
+    const bool side = need_w && g_side_on && g_side != nullptr && !g_prof_on;
+    int seq = 0, last_join = -1;
     // one layer: G (transformed gradient of the call's output) -> weight partials + gradients of its sources
     auto layer_bwd = [&](int call, const float2* G, int in0, int in1, float2* out0, float2* out1, int xcall, bool need_data) -> int {
         g_cur_call = call;
@@ -779,9 +802,26 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
         SrcP s0 = src_of(in0, l), s1;
         if (in1 >= 0) s1 = src_of(in1, l);
         int r = 0;
-        if (need_w && (r = dispatch_bwd_weight(kModCi[m], kModK[m], gsrc, s0, in1 >= 0 ? &s1 : nullptr, X + B.wpart[call], g.N, g.h[l],
-                                               g.w[l], st)))
-            return r;
+        if (need_w) {
+            // The weight gradient only feeds the final reduction: with `side` it runs on the second stream beside the data-gradient
+            // chain (fork after the producer of G, join before the reduction).  G buffers are recycled two layers later at the
+            // earliest (gbuf map below), and the side stream is in order, so the main stream waits for the weight gradient issued two
+            // layers earlier before it launches a kernel that may overwrite that layer's G.
+            cudaStream_t ws = st;
+            if (side) {
+                ADC_CUDA(cudaEventRecord(g_ev_fork[seq], st));
+                ADC_CUDA(cudaStreamWaitEvent(g_side, g_ev_fork[seq], 0));
+                ws = g_side;
+            }
+            if ((r = dispatch_bwd_weight(kModCi[m], kModK[m], gsrc, s0, in1 >= 0 ? &s1 : nullptr, X + B.wpart[call], g.N, g.h[l], g.w[l], ws)))
+                return r;
+            if (side) {
+                ADC_CUDA(cudaEventRecord(g_ev_join[seq], g_side));
+                if (seq >= 2) ADC_CUDA(cudaStreamWaitEvent(st, g_ev_join[seq - 2], 0));
+                last_join = seq;
+            }
+            ++seq;
+        }
         if (need_data)
             r = dispatch_bwd_data(kModCi[m], kModK[m], gsrc, s0, in1 >= 0 ? &s1 : nullptr, out0, out1,
                                   xcall >= 0 ? X + B.bpart[xcall] : nullptr, g.N, g.h[l], g.w[l], bimg(call),
@@ -850,6 +890,7 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
         }
     }
 #undef RUN
+    if (side && last_join >= 0) ADC_CUDA(cudaStreamWaitEvent(st, g_ev_join[last_join], 0));
     if (need_w) {
         WgReduceArgs ra;
         memset(&ra, 0, sizeof(ra));

@@ -1,0 +1,186 @@
+// Masked losses (confidence_depth_framework.py:829-914) and Result.evaluate (metrics.py:38-66) as single-pass kernels.
+// The reference compacts (target - pred)[mask] and reduces with a host sync per scalar (2 per loss, ~12 per evaluate); here one
+// kernel accumulates every sum over target > 0 (per-thread double accumulators, per-CTA partial rows, a one-CTA fixed-order
+// finalize: deterministic) and nothing leaves the device until the caller reads the result tensor.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/adc_b200.h"
+#include "prof.h"
+
+namespace adc {
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+}  // namespace adc
+
+namespace lossm {
+
+constexpr int kParts = 148 * 4;
+constexpr int kNV = 10;              // values per partial row (loss: 2 used, metrics: 10)
+
+// per-element error of the masked losses: 0 l2 (t-p)^2 | 1 l1 |t-p| | 2 il1 |1/t - 1/p| | 3 absrel |(t-p)/t|
+__device__ __forceinline__ float loss_err(int kind, float p, float t) {
+    switch (kind) {
+        case 0: { const float d = t - p; return d * d; }
+        case 1: return fabsf(t - p);
+        case 2: return fabsf(1.0f / t - 1.0f / p);
+        default: return fabsf((t - p) / t);
+    }
+}
+__device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }   // torch.abs backward: sign(x)
+__device__ __forceinline__ float loss_derr(int kind, float p, float t) {
+    switch (kind) {
+        case 0: return -2.0f * (t - p);
+        case 1: return -sgn(t - p);
+        case 2: return sgn(1.0f / t - 1.0f / p) * (1.0f / (p * p));
+        default: return sgn((t - p) / t) * (-1.0f / t);
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void block_store(double (&v)[NV], double* __restrict__ row) {
+    __shared__ double red[8][kNV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if (lane == 0) red[warp][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        row[threadIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) masked_loss_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                                  long long n, int kind, double* __restrict__ part) {
+    double v[2] = {0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float t = __ldg(target + i);
+        if (t > 0.f) {
+            v[0] += (double)loss_err(kind, __ldg(pred + i), t);
+            v[1] += 1.0;
+        }
+    }
+    block_store<2>(v, part + (long long)blockIdx.x * kNV);
+}
+
+// sums the partial rows in index order; out[k] = sum_k / count for k < nmean, out[nv-1] = count
+__global__ void __launch_bounds__(32) finalize_kernel(const double* __restrict__ part, int rows, int nv, float* __restrict__ out) {
+    __shared__ double s[kNV];
+    const int k = threadIdx.x;
+    if (k < nv) {
+        double t = 0.0;
+        for (int r = 0; r < rows; ++r) t += part[(long long)r * kNV + k];
+        s[k] = t;
+    }
+    __syncwarp();
+    if (k < nv) out[k] = (k == nv - 1) ? (float)s[nv - 1] : (float)(s[k] / s[nv - 1]);
+}
+
+__global__ void __launch_bounds__(256) masked_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                              const float* __restrict__ gloss, const float* __restrict__ count,
+                                                              long long n, int kind, float* __restrict__ gpred) {
+    const float scale = gloss[0] / count[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float t = __ldg(target + i);
+        gpred[i] = t > 0.f ? scale * loss_derr(kind, __ldg(pred + i), t) : 0.f;
+    }
+}
+
+// sums over (target > 0 [and confidence > thr]): |d|^2, |d|, |log10 o - log10 t|, |d|/t, [r<1.25], [r<1.25^2], [r<1.25^3],
+// |1/o - 1/t|^2, |1/o - 1/t|, 1   with d = o - t, r = max(o/t, t/o); per-element arithmetic in fp32 like the reference
+__global__ void __launch_bounds__(256) depth_metrics_partial_kernel(const float* __restrict__ output, const float* __restrict__ target,
+                                                                    const float* __restrict__ conf, float thr, long long n,
+                                                                    double* __restrict__ part) {
+    double v[kNV];
+#pragma unroll
+    for (int k = 0; k < kNV; ++k) v[k] = 0.0;
+    const float inv_ln10 = 1.0f / 2.302585092994046f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float t = __ldg(target + i);
+        if (!(t > 0.f) || (conf && !(__ldg(conf + i) > thr))) continue;
+        const float o = __ldg(output + i);
+        const float ad = fabsf(o - t);
+        const float r = fmaxf(o / t, t / o);
+        const float ai = fabsf(1.0f / o - 1.0f / t);
+        const float lg = fabsf(logf(o) * inv_ln10 - logf(t) * inv_ln10);
+        const bool rnan = (o / t) != (o / t) || (t / o) != (t / o);      // torch.max propagates NaN; NaN < x is false either way
+        v[0] += (double)(ad * ad);
+        v[1] += (double)ad;
+        v[2] += (double)lg;
+        v[3] += (double)(ad / t);
+        v[4] += (!rnan && r < 1.25f) ? 1.0 : 0.0;
+        v[5] += (!rnan && r < 1.25f * 1.25f) ? 1.0 : 0.0;
+        v[6] += (!rnan && r < 1.25f * 1.25f * 1.25f) ? 1.0 : 0.0;
+        v[7] += (double)(ai * ai);
+        v[8] += (double)ai;
+        v[9] += 1.0;
+    }
+    block_store<kNV>(v, part + (long long)blockIdx.x * kNV);
+}
+
+static int grid_for(long long n) {
+    long long b = (n + 255) / 256;
+    return (int)(b < kParts ? (b > 0 ? b : 1) : kParts);
+}
+
+}  // namespace lossm
+
+using namespace lossm;
+
+extern "C" {
+
+size_t adc_loss_metrics_workspace_bytes(void) { return (size_t)kParts * kNV * sizeof(double); }
+
+int adc_masked_loss_fwd(const float* pred, const float* target, long long n, int kind, void* workspace, float* out, adc_stream_t stream) {
+    if (!pred || !target || !workspace || !out || n <= 0 || kind < 0 || kind > 3) {
+        adc::set_error("adc_masked_loss_fwd: bad argument (kind 0 l2, 1 l1, 2 il1, 3 absrel)");
+        return ADC_E_BADARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(n);
+    adc::Prof prof(st, adc::KIND_TC_GLUE, (double)n * 8.0);
+    adc::count_launches(1);
+    masked_loss_partial_kernel<<<grid, 256, 0, st>>>(pred, target, n, kind, reinterpret_cast<double*>(workspace));
+    int rc = adc::check_cuda(cudaGetLastError(), "masked_loss_partial_kernel launch");
+    if (rc) return rc;
+    finalize_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, 2, out);
+    return adc::check_cuda(cudaGetLastError(), "finalize_kernel launch");
+}
+
+int adc_masked_loss_bwd(const float* pred, const float* target, const float* gloss, const float* count, long long n, int kind, float* gpred,
+                        adc_stream_t stream) {
+    if (!pred || !target || !gloss || !count || !gpred || n <= 0 || kind < 0 || kind > 3) {
+        adc::set_error("adc_masked_loss_bwd: bad argument");
+        return ADC_E_BADARG;
+    }
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)n * 12.0);
+    long long b = (n + 255) / 256;
+    masked_loss_bwd_kernel<<<(int)(b < 148 * 16 ? b : 148 * 16), 256, 0, (cudaStream_t)stream>>>(pred, target, gloss, count, n, kind, gpred);
+    return adc::check_cuda(cudaGetLastError(), "masked_loss_bwd_kernel launch");
+}
+
+int adc_depth_metrics(const float* output, const float* target, const float* confidence, float threshold, long long n, void* workspace,
+                      float* out, adc_stream_t stream) {
+    if (!output || !target || !workspace || !out || n <= 0) {
+        adc::set_error("adc_depth_metrics: bad argument");
+        return ADC_E_BADARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(n);
+    adc::Prof prof(st, adc::KIND_TC_GLUE, (double)n * (confidence ? 12.0 : 8.0));
+    adc::count_launches(1);
+    depth_metrics_partial_kernel<<<grid, 256, 0, st>>>(output, target, confidence, threshold, n, reinterpret_cast<double*>(workspace));
+    int rc = adc::check_cuda(cudaGetLastError(), "depth_metrics_partial_kernel launch");
+    if (rc) return rc;
+    finalize_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, kNV, out);
+    return adc::check_cuda(cudaGetLastError(), "finalize_kernel launch");
+}
+
+}  // extern "C"

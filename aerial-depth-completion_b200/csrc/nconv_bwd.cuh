@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
     }
     __syncthreads();
     if (pending) mbar_wait(bar, 0);
+    expand_up2_planes<K, NT>(s0, s1, has1 != 0, sX, tid);
     premul_planes<K, NT>(sX, CI, tid);      // {x, c} -> {x*c, c}
     if (g.tma) mbar_wait(bar2, 0);
     __syncthreads();

@@ -69,31 +69,95 @@ __device__ __forceinline__ void gather_pair_tile(const SrcP& s, int sc, int n, i
     }
 }
 
+// Exact 2x nearest up-sampling through TMA: tile row r / pair column c of the layer reads low-resolution row
+// ((h0-P+r) >> 1) and column ((w0-P-XOFF+c) >> 1).  h0 and w0-P-XOFF are even, so relative to the box origin
+// (floor((h0-P)/2), (w0-P-XOFF)/2) that is row (r + (P&1)) >> 1, column c >> 1.  Rows/columns outside the low-resolution
+// image are the hardware's zero fill and coincide with the layer's own zero padding because H = 2*Hs, W = 2*Ws.
+template <int K>
+struct Up2Cfg {
+    using C = TileCfg<K>;
+    // The box must start on an even pair (16-byte) offset of the row like every TMA box here; (w0-P-XOFF)/2 = w0/2 - 1 is odd, so
+    // the box starts one low-resolution pair further left (LXO) and is two pairs wider.
+    static constexpr int LXO = 1;
+    static constexpr int LW = C::SWP / 2 + 2;                              // pairs per low-resolution box row (16-byte multiple)
+    static constexpr int LH = ((C::SH - 1 + (C::P & 1)) >> 1) + 1;         // low-resolution rows
+    static constexpr int OFF = (C::PLANE - LW * LH) & ~15;                 // box lands in the plane's tail (128-byte aligned)
+    static_assert((C::SWP & 3) == 0 && ((LW * 8) % 16) == 0 && OFF >= 0 && OFF + LW * LH <= C::PLANE, "TMA box rows are 16-byte multiples");
+};
+
 // Stage all input-channel tiles of up to two sources.  Returns true if a TMA transaction is pending on `bar`.
 template <int K, int NT>
 __device__ __forceinline__ bool stage_sources(const Maps2& maps, const SrcP& s0, const SrcP& s1, bool has1, int n, int h0, int w0,
                                               int H, int W, float2* planes, uint64_t* bar, int tid) {
     using C = TileCfg<K>;
-    const bool any_tma = s0.tma || (has1 && s1.tma);
+    using U = Up2Cfg<K>;
+    const bool t0 = s0.tma || s0.up2, t1 = has1 && (s1.tma || s1.up2);
+    const bool any_tma = t0 || t1;
     if (any_tma) {
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
         if (tid == 0) {
-            const int nplanes = (s0.tma ? s0.ch : 0) + ((has1 && s1.tma) ? s1.ch : 0);
-            mbar_expect_tx(bar, (uint32_t)(nplanes * C::SH * C::SWP * 8));
+            const int full = C::SH * C::SWP * 8, low = U::LW * U::LH * 8;
+            const int bytes = (s0.tma ? s0.ch * full : 0) + (s0.up2 ? s0.ch * low : 0) +
+                              ((has1 && s1.tma) ? s1.ch * full : 0) + ((has1 && s1.up2) ? s1.ch * low : 0);
+            mbar_expect_tx(bar, (uint32_t)bytes);
+            const int x0 = 2 * (w0 - C::P - C::XOFF), y0 = h0 - C::P;
             if (s0.tma)
-                for (int c = 0; c < s0.ch; ++c)
-                    tma_load_plane(planes + c * C::PLANE, &maps.m0, bar, 2 * (w0 - C::P - C::XOFF), h0 - C::P, c, n);
+                for (int c = 0; c < s0.ch; ++c) tma_load_plane(planes + c * C::PLANE, &maps.m0, bar, x0, y0, c, n);
+            if (s0.up2)      // low-resolution coordinates: pairs (w0-P-XOFF)/2 -> floats w0-P-XOFF; rows floor(y0/2)
+                for (int c = 0; c < s0.ch; ++c) tma_load_plane(planes + c * C::PLANE + U::OFF, &maps.m0, bar, (x0 >> 1) - 2 * U::LXO, y0 >> 1, c, n);
             if (has1 && s1.tma)
+                for (int c = 0; c < s1.ch; ++c) tma_load_plane(planes + (s0.ch + c) * C::PLANE, &maps.m1, bar, x0, y0, c, n);
+            if (has1 && s1.up2)
                 for (int c = 0; c < s1.ch; ++c)
-                    tma_load_plane(planes + (s0.ch + c) * C::PLANE, &maps.m1, bar, 2 * (w0 - C::P - C::XOFF), h0 - C::P, c, n);
+                    tma_load_plane(planes + (s0.ch + c) * C::PLANE + U::OFF, &maps.m1, bar, (x0 >> 1) - 2 * U::LXO, y0 >> 1, c, n);
         }
     }
-    if (!s0.tma)
+    if (!t0)
         for (int c = 0; c < s0.ch; ++c) gather_pair_tile<K, NT>(s0, c, n, h0, w0, H, W, planes + c * C::PLANE, tid);
-    if (has1 && !s1.tma)
+    if (has1 && !t1)
         for (int c = 0; c < s1.ch; ++c) gather_pair_tile<K, NT>(s1, c, n, h0, w0, H, W, planes + (s0.ch + c) * C::PLANE, tid);
     return any_tma;
+}
+
+// In-place expansion of the up2 planes after their TMA boxes have landed: every thread first reads ALL its low-resolution
+// pairs into registers, the CTA synchronises, then each pair is written twice (one 16-byte store) at its two full-resolution
+// columns -- reads complete before any write, so the box may overlap the rows it expands into.  Must be called by all
+// threads of the CTA (contains a barrier); no-op when no source is up2.
+template <int K, int NT>
+__device__ __forceinline__ void expand_up2_planes(const SrcP& s0, const SrcP& s1, bool has1, float2* planes, int tid) {
+    using C = TileCfg<K>;
+    using U = Up2Cfg<K>;
+    const int n0 = s0.up2 ? s0.ch : 0, n1 = (has1 && s1.up2) ? s1.ch : 0;
+    if (n0 + n1 == 0) return;
+    const int first = s0.up2 ? 0 : s0.ch;              // the up2 planes are contiguous: [first, first + nup)
+    const int nup = n0 + n1;
+    // (s0 only: planes [0, s0.ch); s1 only: planes [s0.ch, s0.ch + s1.ch); both: all of them)
+    constexpr int LC = C::SWP / 2;                     // low-resolution columns a plane row expands from
+    constexpr int ITEMS = C::SH * LC;                  // (row, low column) items per plane
+    constexpr int PER = (ITEMS + NT - 1) / NT;
+    for (int q = 0; q < nup; ++q) {
+        float2* pl = planes + (first + q) * C::PLANE;
+        float2 v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * NT;
+            if (i < ITEMS) {
+                const int r = i / LC, j = i - r * LC;
+                v[k] = pl[U::OFF + ((r + (C::P & 1)) >> 1) * U::LW + U::LXO + j];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * NT;
+            if (i < ITEMS) {
+                const int r = i / LC, j = i - r * LC;
+                *reinterpret_cast<float4*>(pl + r * C::SWP + 2 * j) = make_float4(v[k].x, v[k].y, v[k].x, v[k].y);
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // The shared compute core.  For a thread's 2x8 patch and NOUT output maps:
@@ -171,6 +235,7 @@ __global__ void __launch_bounds__(128) nconv_fwd_kernel(const __grid_constant__ 
     const bool pending = stage_sources<K, 128>(maps, s0, s1, has1 != 0, n, h0, w0, H, W, planes, bar, tid);
     __syncthreads();
     if (pending) mbar_wait(bar, 0);
+    expand_up2_planes<K, 128>(s0, s1, has1 != 0, planes, tid);
     premul_planes<K, 128>(planes, CI, tid);
     __syncthreads();
 

@@ -439,6 +439,17 @@ class _MaskedLoss(nn.Module):
 
     def forward(self, depth_input, depth_prediction, depth_target, epoch=None):
         assert depth_prediction.dim() == depth_target.dim(), "inconsistent dimensions"
+        if depth_prediction.is_cuda:
+            # one reduction kernel forward, one elementwise kernel backward (csrc/loss_metrics.cu); no boolean-index compaction
+            from .. import ops
+            final_loss, num_valids = ops.masked_loss(depth_prediction, depth_target.detach(), self.kind)
+            if self.lazy:
+                torch._assert_async(num_valids > 100, 'training image has less than 100 valid pixels')
+            else:
+                assert (num_valids > 100), 'training image has less than 100 valid pixels'
+            self.loss = [final_loss.detach() if self.lazy else final_loss.item(), 0, 0]
+            return final_loss
+        # host tensors (the gloo host-logic tests): the same definition with torch ops
         mask = (depth_target > 0).detach()
         num_valids = mask.sum()
         if self.lazy:
@@ -467,22 +478,30 @@ class DualLoss(nn.Module):
 
 
 class MaskedMSELoss(_MaskedLoss):
+    kind = 'l2'
+
     def _error(self, pred, target, mask):
         return (target - pred) ** 2
 
 
 class InvertedMaskedL1Loss(_MaskedLoss):
+    kind = 'il1'
+
     def _error(self, pred, target, mask):
         safe_t = torch.where(mask, target, torch.ones_like(target))
         return ((1.0 / safe_t) - (1.0 / pred)).abs()
 
 
 class MaskedAbsRelLoss(_MaskedLoss):
+    kind = 'absrel'
+
     def _error(self, pred, target, mask):
         safe_t = torch.where(mask, target, torch.ones_like(target))
         return ((target - pred) / safe_t).abs()
 
 
 class MaskedL1Loss(_MaskedLoss):
+    kind = 'l1'
+
     def _error(self, pred, target, mask):
         return (target - pred).abs()

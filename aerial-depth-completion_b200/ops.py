@@ -238,3 +238,63 @@ class PyramidFunction(torch.autograd.Function):
             ow += _PYR_WNUMEL[i]
             ob += _PYR_BNUMEL[i]
         return (gx0, gc0, None, None, *grads)
+
+
+# ---- masked losses / depth metrics (csrc/loss_metrics.cu) -------------------------------------------------------------------------
+LOSS_KINDS = {"l2": 0, "l1": 1, "il1": 2, "absrel": 3}
+
+
+def _lm_workspace(dev):
+    return torch.empty(lib.adc_loss_metrics_workspace_bytes() // 8, device=dev, dtype=torch.float64)
+
+
+class MaskedLossFunction(torch.autograd.Function):
+    """(pred, target) -> [mean error over target > 0, number of valid pixels] (one 2-element tensor); one reduction kernel
+    forward, one elementwise kernel backward (confidence_depth_framework.py:829-914)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, kind):
+        _require_cuda_f32("depth_prediction", pred)
+        _require_cuda_f32("depth_target", target)
+        if pred.shape != target.shape:
+            raise RuntimeError("masked loss: prediction %s and target %s differ in shape" % (tuple(pred.shape), tuple(target.shape)))
+        p, t = pred.contiguous(), target.contiguous()
+        out = torch.empty(2, device=p.device, dtype=torch.float32)
+        check(lib.adc_masked_loss_fwd(p.data_ptr(), t.data_ptr(), p.numel(), kind, _lm_workspace(p.device).data_ptr(), out.data_ptr(),
+                                      _stream()), "adc_masked_loss_fwd")
+        ctx.kind = kind
+        ctx.save_for_backward(p, t, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        p, t, out = ctx.saved_tensors
+        g = torch.empty_like(p)
+        gl = gout.contiguous()          # element 0 is dL/dloss; the count output carries no gradient
+        check(lib.adc_masked_loss_bwd(p.data_ptr(), t.data_ptr(), gl.data_ptr(), out[1:].data_ptr(), p.numel(), ctx.kind, g.data_ptr(),
+                                      _stream()), "adc_masked_loss_bwd")
+        return g, None, None
+
+
+def masked_loss(pred, target, kind):
+    """(loss, number of valid pixels): 0-dim tensors; only the loss is differentiable."""
+    out = MaskedLossFunction.apply(pred, target, LOSS_KINDS[kind])
+    return out[0], out[1].detach()
+
+
+def depth_metrics(output, target, confidence=None, threshold=0.0):
+    """[mse, mae, lg10, absrel, delta1, delta2, delta3, imse, imae, count] (fp32 device tensor) over target > 0
+    [& confidence > threshold] in one pass (metrics.py:38-66)."""
+    _require_cuda_f32("output", output)
+    _require_cuda_f32("target", target)
+    o, t = output.contiguous(), target.contiguous()
+    c = None
+    if confidence is not None:
+        _require_cuda_f32("confidence", confidence)
+        c = confidence.contiguous()
+    if o.shape != t.shape or (c is not None and c.shape != t.shape):
+        raise RuntimeError("depth_metrics: tensors differ in shape")
+    out = torch.empty(10, device=o.device, dtype=torch.float32)
+    check(lib.adc_depth_metrics(o.data_ptr(), t.data_ptr(), c.data_ptr() if c is not None else None, float(threshold), o.numel(),
+                                _lm_workspace(o.device).data_ptr(), out.data_ptr(), _stream()), "adc_depth_metrics")
+    return out

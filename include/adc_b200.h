@@ -311,6 +311,21 @@ int adc_conf_head_bwd(const float* y, int y_stride, float* coef, const float* w2
                       void* gy, void* gy_lo, int gy_stride, float* gw2, float* gb2, float* ggamma, float* gbeta, void* workspace, int N, int C,
                       int H, int W, adc_stream_t stream);
 
+/* ---- masked losses and depth metrics (confidence_depth_framework.py:829-914 MaskedMSELoss / MaskedL1Loss / InvertedMaskedL1Loss /
+ * MaskedAbsRelLoss; metrics.py:38-66 Result.evaluate).  pred / target / output / confidence: contiguous fp32 tensors of n elements.
+ * kind: 0 l2 (t-p)^2, 1 l1 |t-p|, 2 il1 |1/t - 1/p|, 3 absrel |(t-p)/t|; the mask is target > 0.
+ * adc_masked_loss_fwd: out[0] = mean of the error over the mask, out[1] = number of valid pixels (as float).
+ * adc_masked_loss_bwd: gpred[i] = gloss[0] / count[0] * d err / d pred on the mask, 0 elsewhere (gloss, count: device scalars).
+ * adc_depth_metrics: out[0..9] = mse, mae, lg10, absrel, delta1, delta2, delta3, imse, imae (means over target > 0 [and
+ *   confidence > threshold if confidence != NULL]) and the number of valid pixels.
+ * workspace: adc_loss_metrics_workspace_bytes() bytes.  Deterministic (fixed-order two-stage reduction in double). */
+size_t adc_loss_metrics_workspace_bytes(void);
+int adc_masked_loss_fwd(const float* pred, const float* target, long long n, int kind, void* workspace, float* out, adc_stream_t stream);
+int adc_masked_loss_bwd(const float* pred, const float* target, const float* gloss, const float* count, long long n, int kind, float* gpred,
+                        adc_stream_t stream);
+int adc_depth_metrics(const float* output, const float* target, const float* confidence, float threshold, long long n, void* workspace,
+                      float* out, adc_stream_t stream);
+
 
 #ifdef __cplusplus
 }
