@@ -18,11 +18,15 @@ class DataParallelTrainer:
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=self.params[0].dtype)
-        off = 0
-        for p in self.params:       # .grad of every parameter is a view into the flat buffer: backward fills the bucket
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        own = getattr(optimizer, "flat_grad", None)
+        if own is not None and [id(p) for p in getattr(optimizer, "_params", [])] == [id(p) for p in self.params]:
+            self.flat = own          # optim.FlatAdam already keeps every .grad as a view into one bucket: all-reduce that one
+        else:
+            self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=self.params[0].dtype)
+            off = 0
+            for p in self.params:   # .grad of every parameter is a view into the flat buffer: backward fills the bucket
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
         if hasattr(criterion, "lazy"):
             criterion.lazy = True   # keep loss bookkeeping on the device (no .item() per step)
         for sub in ("net_a", "net_b"):
@@ -43,7 +47,7 @@ class DataParallelTrainer:
         """Record the whole training step (forward, loss, backward, all-reduce, optimizer) into ONE CUDA graph.
         The step has static shapes and no host synchronisation, so every later ``step`` is a single graph launch: the
         ~450 kernel launches and the Python between them (4.4 ms of a 15 ms step at batch 32) disappear.
-        Requires an optimizer created with ``capturable=True``.  Inputs of later steps are copied into the static buffers."""
+        Requires a capturable optimizer (optim.FlatAdam, or torch.optim.Adam(capturable=True)).  Inputs of later steps are copied into the static buffers."""
         self._static_in, self._static_tg = inp.clone(), target.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -63,6 +67,8 @@ class DataParallelTrainer:
             self._static_in.copy_(inp, non_blocking=True)
             self._static_tg.copy_(target, non_blocking=True)
             self._graph.replay()
+            for p in self.params:      # the replay updated the parameters behind autograd's back: caches keyed on the version
+                torch.autograd.graph.increment_version(p)     # counter (dense.cached_weights) must see it
             return self._static_loss
         return self._eager_step(inp, target)
 

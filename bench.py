@@ -218,7 +218,8 @@ def b200_arm(args):
         model, params = factory.to_device(model)
         model.train()
     criterion, _ = factory.create_loss("l2", False, 0.5)
-    optimizer = torch.optim.Adam(params, lr=1e-5, capturable=not args.no_graph)
+    from aerial_depth_completion_b200.optim import FlatAdam
+    optimizer = FlatAdam(params, lr=1e-5)       # torch.optim.Adam's update as ONE kernel over flat buffers (device-side step counter)
     from aerial_depth_completion_b200 import dense as _dense
     _dense.set_precision(args.precision)
     trainer = parallel.DataParallelTrainer(model, criterion, optimizer, params, world_size=world)
@@ -414,7 +415,8 @@ def full_framework_training(dev, B=8, HH=480, WW=752, steps=8):
             m, params = f.to_device(m)
             m.train()
         crit, _ = f.create_loss("l2", True, 0.5)
-        opt = torch.optim.Adam(params, lr=1e-5, capturable=True)
+        from aerial_depth_completion_b200.optim import FlatAdam
+        opt = FlatAdam(params, lr=1e-5)
         tr = parallel.DataParallelTrainer(m, crit, opt, params, world_size=1)
         g = torch.Generator(device=dev).manual_seed(11)
         xs, ts = [], []

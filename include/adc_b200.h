@@ -326,6 +326,14 @@ int adc_masked_loss_bwd(const float* pred, const float* target, const float* glo
 int adc_depth_metrics(const float* output, const float* target, const float* confidence, float threshold, long long n, void* workspace,
                       float* out, adc_stream_t stream);
 
+/* ---- optimizer step of the trainer (trainer.py:134-146, torch.optim.Adam over the trainable parameters) on flat buffers: every
+ * parameter / gradient / moment is a view into one fp32 vector of n elements (16-byte aligned).  `step` is a device scalar holding the
+ * number of updates done so far; the call increments it first (so a replayed CUDA graph advances the bias correction) and applies
+ * torch.optim.Adam's update (amsgrad=False): g' = g + wd*p; m += (g'-m)(1-b1); v = b2 v + (1-b2) g'^2;
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). */
+int adc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step, long long n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, adc_stream_t stream);
+
 
 #ifdef __cplusplus
 }
