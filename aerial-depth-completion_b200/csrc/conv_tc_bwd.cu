@@ -270,9 +270,19 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
     const int total = ntaps * cout * cin;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
-        float acc = 0.f;
-        for (int g = 0; g < groups; ++g) acc += part[(((long long)g * ntaps + tap) * mrows + co) * ncols + ci];
-        dw[((long long)co * cin + ci) * ntaps + tap] = acc;
+        // four partial sums: the loads of one thread overlap (a single serial chain over 148 groups was latency-bound: 40 us)
+        const long long gs = (long long)ntaps * mrows * ncols;
+        const float* q = part + ((long long)tap * mrows + co) * ncols + ci;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int g = 0;
+        for (; g + 3 < groups; g += 4) {
+            a0 += q[(long long)g * gs];
+            a1 += q[(long long)(g + 1) * gs];
+            a2 += q[(long long)(g + 2) * gs];
+            a3 += q[(long long)(g + 3) * gs];
+        }
+        for (; g < groups; ++g) a0 += q[(long long)g * gs];
+        dw[((long long)co * cin + ci) * ntaps + tap] = (a0 + a1) + (a2 + a3);
     }
 }
 

@@ -70,17 +70,20 @@ __global__ void __launch_bounds__(256) masked_loss_partial_kernel(const float* _
     block_store<2>(v, part + (long long)blockIdx.x * kNV);
 }
 
-// sums the partial rows in index order; out[k] = sum_k / count for k < nmean, out[nv-1] = count
-__global__ void __launch_bounds__(32) finalize_kernel(const double* __restrict__ part, int rows, int nv, float* __restrict__ out) {
+// warp k sums column k of the partial rows (lane-strided rows, then a fixed shuffle tree: deterministic);
+// out[k] = sum_k / count for k < nv-1, out[nv-1] = count
+__global__ void __launch_bounds__(32 * kNV) finalize_kernel(const double* __restrict__ part, int rows, int nv, float* __restrict__ out) {
     __shared__ double s[kNV];
-    const int k = threadIdx.x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k < nv) {
         double t = 0.0;
-        for (int r = 0; r < rows; ++r) t += part[(long long)r * kNV + k];
-        s[k] = t;
+        for (int r = lane; r < rows; r += 32) t += part[(long long)r * kNV + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s[k] = t;
     }
-    __syncwarp();
-    if (k < nv) out[k] = (k == nv - 1) ? (float)s[nv - 1] : (float)(s[k] / s[nv - 1]);
+    __syncthreads();
+    if (threadIdx.x < nv) out[threadIdx.x] = (threadIdx.x == nv - 1) ? (float)s[nv - 1] : (float)(s[threadIdx.x] / s[nv - 1]);
 }
 
 __global__ void __launch_bounds__(256) masked_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
@@ -150,7 +153,7 @@ int adc_masked_loss_fwd(const float* pred, const float* target, long long n, int
     masked_loss_partial_kernel<<<grid, 256, 0, st>>>(pred, target, n, kind, reinterpret_cast<double*>(workspace));
     int rc = adc::check_cuda(cudaGetLastError(), "masked_loss_partial_kernel launch");
     if (rc) return rc;
-    finalize_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, 2, out);
+    finalize_kernel<<<1, 32 * kNV, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, 2, out);
     return adc::check_cuda(cudaGetLastError(), "finalize_kernel launch");
 }
 
@@ -179,7 +182,7 @@ int adc_depth_metrics(const float* output, const float* target, const float* con
     depth_metrics_partial_kernel<<<grid, 256, 0, st>>>(output, target, confidence, threshold, n, reinterpret_cast<double*>(workspace));
     int rc = adc::check_cuda(cudaGetLastError(), "depth_metrics_partial_kernel launch");
     if (rc) return rc;
-    finalize_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, kNV, out);
+    finalize_kernel<<<1, 32 * kNV, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, kNV, out);
     return adc::check_cuda(cudaGetLastError(), "finalize_kernel launch");
 }
 

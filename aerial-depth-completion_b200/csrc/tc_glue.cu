@@ -208,21 +208,29 @@ __global__ void nhwc_colsum2_kernel(const float* __restrict__ part, int nparts, 
     out[c] = t;
 }
 
-// out[c] = sum_r part[r][c] in a fixed order (rows strided over 8 groups per thread column, then the groups in index order):
+// out[c] = sum_r part[r][c] in a fixed order (rows strided over 32 groups per thread column, then the groups in index order):
 // the second stage of every deterministic reduction of this library (a library reduce over dim 0 of a [~1000, C] tensor
 // launches 1-2 CTAs and measured 26 us).
-__global__ void __launch_bounds__(256) sum_rows_kernel(const float* __restrict__ part, int rows, int C, float* __restrict__ out) {
-    __shared__ float red[8][32];
+__global__ void __launch_bounds__(1024) sum_rows_kernel(const float* __restrict__ part, int rows, int C, float* __restrict__ out) {
+    __shared__ float red[32][33];
     const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
-    float s = 0.f;
-    if (c < C)
-        for (int r = rg; r < rows; r += 8) s += part[(long long)r * C + c];
-    red[rg][cl] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // four loads in flight per thread (the serial version was latency-bound: 18 us)
+    if (c < C) {
+        int r = rg;
+        for (; r + 96 < rows; r += 128) {
+            s0 += part[(long long)r * C + c];
+            s1 += part[(long long)(r + 32) * C + c];
+            s2 += part[(long long)(r + 64) * C + c];
+            s3 += part[(long long)(r + 96) * C + c];
+        }
+        for (; r < rows; r += 32) s0 += part[(long long)r * C + c];
+    }
+    red[rg][cl] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (rg == 0 && c < C) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][cl];
+        for (int k = 0; k < 32; ++k) t += red[k][cl];
         out[c] = t;
     }
 }
@@ -249,7 +257,7 @@ int adc_sum_rows(const float* part, int rows, int C, float* out, adc_stream_t st
         return ADC_E_BADARG;
     }
     adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)rows * C * 4.0);
-    sum_rows_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(part, rows, C, out);
+    sum_rows_kernel<<<(C + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(part, rows, C, out);
     return adc::check_cuda(cudaGetLastError(), "sum_rows_kernel launch");
 }
 
