@@ -1,5 +1,5 @@
 """Data-parallel training step: one process per GPU, gradients of all parameters live in ONE flat fp32 buffer that is
-all-reduced over NCCL (NVLink 5 / NVSwitch) after backward.
+all-reduced over NCCL (NVLink 5 / NVSwitch), bucket by bucket WHILE backward is still producing the upstream gradients.
 
 Replaces the reference's single-process ``nn.DataParallel`` (confidence_depth_framework.py:145-159, which re-broadcasts
 every parameter and gathers every output each step) with the torch.distributed layout of SURVEY.md 8e: frames are
@@ -32,9 +32,44 @@ class DataParallelTrainer:
         for sub in ("net_a", "net_b"):
             if hasattr(criterion, sub) and hasattr(getattr(criterion, sub), "lazy"):
                 getattr(criterion, sub).lazy = True
+        self._buckets, self._left, self._works = [], [], []
         if self.world > 1:
             for p in list(model.parameters()) + list(model.buffers()):   # identical replicas, once (not per step)
                 dist.broadcast(p.data, 0, group=self.group)
+            self._avg = dist.get_backend(self.group) == "nccl"           # NCCL averages in the collective; gloo sums, then one div
+            self._make_buckets()
+
+    def _make_buckets(self):
+        """Gradient buckets = contiguous slices of the flat buffer, one per sub-net part in parameter order (dc_model.d_net |
+        dc_model body | conf_model | loss_dc_model.d_net | loss_dc_model body).  Backward produces them in the reverse order; a
+        bucket's all-reduce is launched (async, NCCL's own stream) by the hook of its last gradient, so the exchange of the loss
+        net's and the encoder-decoder's gradients overlaps the backward of everything upstream of them."""
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        off, cur = 0, None
+        for p in self.params:
+            parts = names.get(id(p), "").split(".")
+            key = (parts[0], parts[1] if len(parts) > 1 and parts[1] in ("d_net", "unguidednet") else "body")
+            if key != cur:
+                self._buckets.append([off, off, 0])
+                cur = key
+            b = len(self._buckets) - 1
+            self._buckets[b][1] = off + p.numel()
+            self._buckets[b][2] += 1
+            p.register_post_accumulate_grad_hook(lambda _p, b=b: self._on_grad(b))
+            off += p.numel()
+        self._left = [0] * len(self._buckets)
+
+    def _reduce_bucket(self, b, async_op):
+        lo, hi, _ = self._buckets[b]
+        return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, group=self.group,
+                               async_op=async_op)
+
+    def _on_grad(self, b):
+        if not self._left or self._left[b] <= 0:
+            return
+        self._left[b] -= 1
+        if self._left[b] == 0:
+            self._works.append(self._reduce_bucket(b, True))
 
     def forward_loss(self, inp, target):
         pred = self.model(inp)
@@ -75,9 +110,19 @@ class DataParallelTrainer:
     def _eager_step(self, inp, target):
         loss, _ = self.forward_loss(inp, target)
         self.flat.zero_()
+        if self.world > 1:
+            self._left = [n for _, _, n in self._buckets]
+            self._works = []
         loss.backward()
         if self.world > 1:
-            dist.all_reduce(self.flat, group=self.group)
-            self.flat.div_(self.world)
+            for b, left in enumerate(self._left):      # a bucket with a parameter that got no gradient this step: reduce it now
+                if left > 0:
+                    self._reduce_bucket(b, False)
+            self._left = [0] * len(self._buckets)
+            for w in self._works:
+                w.wait()                                # the compute stream waits for the collectives (no host synchronisation)
+            self._works = []
+            if not self._avg:
+                self.flat.div_(self.world)
         self.optimizer.step()
         return loss.detach()

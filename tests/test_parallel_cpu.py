@@ -8,25 +8,42 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
+def _tiny_model():
+    """Shaped like the framework model: dc_model with a d_net part and a body, plus a parameter no gradient ever reaches (its
+    bucket must still be reduced)."""
+    class DC(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.d_net = torch.nn.Conv2d(5, 2, 3, 1, 1)
+            self.conv1 = torch.nn.Conv2d(2, 4, 3, 1, 1)
+            self.conv2 = torch.nn.Conv2d(4, 1, 3, 1, 1)
+
+        def forward(self, x):
+            return self.conv2(torch.relu(self.conv1(self.d_net(x))))
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dc_model = DC()
+            self.conf_model = torch.nn.Conv2d(1, 1, 1)         # never used in forward: no gradient
+
+        def forward(self, x):
+            return self.dc_model(x), None, None
+    return Tiny()
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from aerial_depth_completion_b200 import parallel
     import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
 
-    class Tiny(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.c = torch.nn.Conv2d(5, 1, 3, 1, 1)
-
-        def forward(self, x):
-            return self.c(x), None, None
-
     torch.manual_seed(rank)                       # deliberately different init: the trainer must broadcast rank 0's
-    model = Tiny()
+    model = _tiny_model()
     params = list(model.parameters())
     opt = torch.optim.SGD(params, lr=0.1)
     tr = parallel.DataParallelTrainer(model, mc.MaskedMSELoss(), opt, params, world_size=world)
+    out["buckets%d" % rank] = [(lo, hi, n) for lo, hi, n in tr._buckets]
     g = torch.Generator().manual_seed(100)
     x = torch.rand(4, 5, 16, 16, generator=g)
     t = torch.rand(4, 1, 16, 16, generator=g) + 0.5
@@ -45,7 +62,7 @@ def test_two_rank_step_equals_single_process_on_concatenated_batch():
     # single process, full batch, same initial weights as rank 0
     import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
     torch.manual_seed(0)
-    c = torch.nn.Conv2d(5, 1, 3, 1, 1)
+    c = _tiny_model()
     opt = torch.optim.SGD(c.parameters(), lr=0.1)
     g = torch.Generator().manual_seed(100)
     x = torch.rand(4, 5, 16, 16, generator=g)
@@ -53,9 +70,11 @@ def test_two_rank_step_equals_single_process_on_concatenated_batch():
     crit = mc.MaskedMSELoss()
     for _ in range(3):
         opt.zero_grad()
-        crit(x, c(x), t).backward()
+        crit(x, c(x)[0], t).backward()
         opt.step()
     ref = [p.detach() for p in c.parameters()]
+    # three gradient buckets: dc_model.d_net | dc_model body (conv1, conv2) | conf_model
+    assert [n for _, _, n in out["buckets0"]] == [2, 4, 2] and out["buckets0"] == out["buckets1"]
     for r in (0, 1):
         for a, b in zip(out[r], ref):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), "rank %d diverged from the single-process run" % r
