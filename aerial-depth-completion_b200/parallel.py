@@ -126,3 +126,53 @@ class DataParallelTrainer:
                 self.flat.div_(self.world)
         self.optimizer.step()
         return loss.detach()
+
+
+class HostFeeder:
+    """Feeds a ``DataParallelTrainer`` from pinned HOST batches the way a loader thread would (trainer.py:194-233 copies each batch
+    with ``.cuda()`` and reads ``loss.item()`` before it touches the next one: copy, step and read-back are serialised).  Here the
+    host->device copy of batch i+1 runs on a copy stream while the GPU computes step i (two device buffer pairs, events both ways),
+    and the loss of step i is copied to pinned host memory asynchronously and read one step later, so the only thing the host waits
+    for is a step that has already finished.  Every batch is still copied and every loss is still read."""
+
+    def __init__(self, trainer, example_in, example_tg):
+        dev = trainer.params[0].device
+        self.trainer = trainer
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.buf = [(torch.empty_like(example_in, device=dev), torch.empty_like(example_tg, device=dev)) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]      # H2D copy into buffer b finished
+        self.free = [torch.cuda.Event() for _ in range(2)]       # the step that read buffer b finished
+        self.host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.loss_done = [torch.cuda.Event() for _ in range(2)]
+
+    def _prefetch(self, b, host_in, host_tg, first_use):
+        with torch.cuda.stream(self.copy_stream):
+            if not first_use:
+                self.copy_stream.wait_event(self.free[b])
+            self.buf[b][0].copy_(host_in, non_blocking=True)
+            self.buf[b][1].copy_(host_tg, non_blocking=True)
+            self.ready[b].record(self.copy_stream)
+
+    def run(self, batches):
+        """batches: sequence of (pinned host input, pinned host target).  Returns the list of per-step losses (python floats)."""
+        main = torch.cuda.current_stream()
+        losses, n = [], len(batches)
+        if n == 0:
+            return losses
+        self._prefetch(0, batches[0][0], batches[0][1], True)
+        for i in range(n):
+            b = i & 1
+            if i + 1 < n:
+                self._prefetch(b ^ 1, batches[i + 1][0], batches[i + 1][1], i == 0)
+            main.wait_event(self.ready[b])
+            loss = self.trainer.step(self.buf[b][0], self.buf[b][1])
+            self.free[b].record(main)
+            self.host_loss[b].copy_(loss.detach().reshape(1), non_blocking=True)
+            self.loss_done[b].record(main)
+            if i > 0:                                            # read the PREVIOUS step's loss: it finished while this one was enqueued
+                self.loss_done[b ^ 1].synchronize()
+                losses.append(float(self.host_loss[b ^ 1][0]))
+        last = (n - 1) & 1
+        self.loss_done[last].synchronize()
+        losses.append(float(self.host_loss[last][0]))
+        return losses
