@@ -357,6 +357,10 @@ def b200_arm(args):
             line["extra"]["full_framework_dc1_cf1_ln1_480x752"] = full_framework_training(dev)
         except Exception as e:       # an extra measurement must never cost the headline line
             line["extra"]["full_framework_dc1_cf1_ln1_480x752"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        try:
+            line["extra"]["gudepthcompnet18_dc1_cf1_ln0_240x320"] = gudepthcompnet_training(dev)
+        except Exception as e:
+            line["extra"]["gudepthcompnet18_dc1_cf1_ln0_240x320"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if not args.no_cpu_baseline and world == 1:
         fps, ms, cores, fr = cpu_reference_run(3, 1, args.cpu_frames or 1)
         line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
@@ -462,6 +466,53 @@ def full_framework_training(dev, B=8, HH=480, WW=752, steps=8):
                 "batch": B, "ms_per_step": round(ms, 3), "frames_s": round(B / ms * 1e3, 1), "library_launches_per_step": int(launches),
                 "trainable_parameters": int(sum(p.numel() for p in params)), "loss": round(float(loss), 5), "precision": "bf16x3",
                 "launch": "one CUDA graph per step"}
+    finally:
+        dense.set_precision(prev)
+
+
+def gudepthcompnet_training(dev, B=16, HH=240, WW=320, steps=5):
+    """BASELINE.json configs[2]: gudepthcompnet18 + cbr3-c1 confidence head + frozen ged_depthcompnet loss net, training mode
+    dc1-cf1-ln0, DualLoss(l2, 0.5), batch 16 per GPU at 240x320 (the net needs H, W = 0 mod 16: SURVEY.md 0.4).  The NConv pyramids,
+    the loss net, the losses and the optimizer run on this library's kernels; the ResNet-18 body and the 129-channel head are still
+    on the library (cuDNN fp32) backend -- DESIGN.md 8 (1) -- so this line is a status report, not a headline."""
+    import contextlib
+    import io
+    import torch
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    from aerial_depth_completion_b200 import dense, parallel
+    from aerial_depth_completion_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    f = mc.ConfidenceDepthFrameworkFactory()
+    prev = dense.PRECISION
+    try:
+        dense.set_precision("bf16x3")
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = f.create_model("rgbd", "dc1-cf1-ln0", "gudepthcompnet18", "", "cbr3-c1", "", "ged_depthcompnet", "")
+            m, params = f.to_device(m)
+            m.train()
+        crit, _ = f.create_loss("l2", True, 0.5)
+        tr = parallel.DataParallelTrainer(m, crit, FlatAdam(params, lr=1e-5), params, world_size=1)
+        g = torch.Generator(device=dev).manual_seed(13)
+        x = torch.rand(B, 5, HH, WW, device=dev, generator=g)
+        gt = torch.rand(B, 1, HH, WW, device=dev, generator=g) * 9.0 + 1.0
+        mask = (torch.rand(B, 1, HH, WW, device=dev, generator=g) < 500.0 / (HH * WW)).float()
+        x[:, 3:4] = gt * mask
+        x[:, 4:5] = mask
+        for _ in range(2):
+            tr.step(x, gt)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = tr.step(x, gt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"workload": "gudepthcompnet18 + cbr3-c1 + frozen ged_depthcompnet loss net, dc1-cf1-ln0, DualLoss(l2, 0.5), rgbd %dx%d" % (HH, WW),
+                "batch": B, "ms_per_step": round(ms, 2), "frames_s": round(B / ms * 1e3, 1),
+                "trainable_parameters": int(sum(p.numel() for p in params)), "loss": round(float(loss), 5),
+                "dense_path": "ResNet-18 body and 129-channel head: library (cuDNN fp32); pyramids, loss net, losses, optimizer: libadc_b200",
+                "launch": "eager"}
     finally:
         dense.set_precision(prev)
 
