@@ -377,10 +377,9 @@ class GMSNet(nn.Module):
         for i, m in enumerate(convs):
             last = i == len(convs) - 1
             act = conv(act, m, 16, out=fuse_in if last else None, out_off=64 if last else 0, out_zero_to=64 if last else 0)
-        rgbc = dense.new_act(n, h, w, 64, dev, pad=True, zero=True)
-        dense.to_nhwc_bf16(x0_rgb, cpad=3, dst=rgbc, dst_off=0)
-        dense.to_nhwc_bf16(cout_d, cpad=1, dst=rgbc, dst_off=3)
-        act = rgbc
+        # cat(rgb, cout_d) (confidence_depth_framework.py:648) as ONE conversion that writes the whole 64-channel block (pad channels
+        # as zeros) with 16-byte stores: no zero fill of the buffer, no 2-byte scattered writes
+        act = dense.to_nhwc_bf16(torch.cat((x0_rgb, cout_d), 1), cpad=64, pad=True)
         convs = [m for m in self.rgb if isinstance(m, nn.Conv2d)]
         for i, m in enumerate(convs):
             last = i == len(convs) - 1
