@@ -371,12 +371,15 @@ class GMSNet(nn.Module):
                                                                   relu, **kw)
         # [rgb stream 64 | depth stream 16 | zeros 48]: both 64-channel slices (borders and pad channels included) are written
         # whole by the convolutions that produce them, so the buffer needs no zero fill
-        fuse_in = dense.new_act(n, h, w, 128, dev, pad=True, zero=False)
-        act = dense.to_nhwc_bf16(xout_d, cpad=64, pad=True)                 # channel 0 real
         convs = [m for m in self.d if isinstance(m, nn.Conv2d)]
-        for i, m in enumerate(convs):
-            last = i == len(convs) - 1
-            act = conv(act, m, 16, out=fuse_in if last else None, out_off=64 if last else 0, out_zero_to=64 if last else 0)
+        if w % 4 == 0:
+            fuse_in = self._d_branch_packed(xout_d, convs, n, h, w, dev)
+        else:
+            fuse_in = dense.new_act(n, h, w, 128, dev, pad=True, zero=False)
+            act = dense.to_nhwc_bf16(xout_d, cpad=64, pad=True)                 # channel 0 real
+            for i, m in enumerate(convs):
+                last = i == len(convs) - 1
+                act = conv(act, m, 16, out=fuse_in if last else None, out_off=64 if last else 0, out_zero_to=64 if last else 0)
         # cat(rgb, cout_d) (confidence_depth_framework.py:648) as ONE conversion that writes the whole 64-channel block (pad channels
         # as zeros) with 16-byte stores: no zero fill of the buffer, no 2-byte scattered writes
         act = dense.to_nhwc_bf16(torch.cat((x0_rgb, cout_d), 1), cpad=64, pad=True)
@@ -388,8 +391,10 @@ class GMSNet(nn.Module):
         for m in [m for m in self.fuse if isinstance(m, nn.Conv2d)]:
             act = conv(act, m, m.out_channels)
         last_in = act
-        xout_n = dense.conv3x3_tc(act, act.cs, dense.cached_weights(self.last_layer, embed_1x1=True, cin_pad=act.cs),
-                                  self.last_layer.bias, self.out_channels, 1, 0, out_f32=True)
+        # last_layer is 1x1: the GEMM mode of the row-segment kernel reads the centre tap only (1/9 of the MMAs of the 3x3 form)
+        xout_n = dense.new_act(n, h, w, 16, dev, pad=True, border_only=True, dtype=torch.float32)
+        dense.conv1x1_tc(act, act.cs, dense.cached_weights(self.last_layer, embed_1x1=True, cin_pad=act.cs), self.last_layer.bias,
+                         self.out_channels, 0, out=xout_n)
         xout = dense.to_nchw_f32(xout_n, self.out_channels)
         features = None
         if build_conf_input:
@@ -398,6 +403,52 @@ class GMSNet(nn.Module):
             else:
                 features = torch.sigmoid(xout[:, 1:2, :, :])
         return xout[:, 0:1, :, :], features
+
+    def _d_branch_packed(self, xout_d, convs, n, h, w, dev):
+        """The depth stream (1 -> 16 -> ... -> 16 channels at full resolution) in PACKED form.  One tcgen05.mma of the row-segment
+        kernel costs ~91 cycles whatever its N, and a 16-channel tensor padded to the kernel's 64-channel blocks
+        spends 4 K-steps on one real one: the 16 -> 16 layers cost as much as 64 -> 64 ones (476 us each at B=32).  Packing 4
+        horizontally adjacent pixels into the channel dimension (channel = c*4 + q for pixel 4g+q) turns the layer into a 3x3
+        convolution on the [H, W/4] grid with 64 -> 64 block-structured weights: Wp[(co,q)][(ci,r)][u][dj] = W[co][ci][u][4dj+r-q]
+        where that tap exists -- the same kernel on a quarter of the pixels.  Returns the fuse input buffer with channels [64,80)
+        filled (its pad channels and border are zeroed once: the buffer is cached per shape)."""
+        key = (n, h, w, dense.PRECISION, str(dev))
+        cache = self.__dict__.setdefault("_adc_fuse_in", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = dense.new_act(n, h, w, 128, dev, pad=True, zero=True)
+        fuse_in = cache[key]
+        xp = xout_d.reshape(n, h, w // 4, 4).permute(0, 3, 1, 2).contiguous()       # [n, q, h, w/4]
+        act = dense.to_nhwc_bf16(xp, cpad=64, pad=True)
+        for m in convs:
+            wp, bp = self._packed_weights(m)
+            act = dense.conv3x3_tc(act, 64, wp, bp, 64, 1, 1)
+        for src, dst in ((act.hi, fuse_in.hi), (act.lo, fuse_in.lo)):
+            if src is not None:
+                dst[:, 1:-1, 1:-1, 64:80] = src[:, 1:-1, 1:-1, :].reshape(n, h, w // 4, 16, 4).permute(0, 1, 2, 4, 3).reshape(n, h, w, 16)
+        return fuse_in
+
+    @staticmethod
+    def _packed_weights(conv):
+        """Prepared weights / bias of one depth-stream layer in the packed form above, cached until the Parameter changes."""
+        wt = conv.weight
+        tag = (wt.data_ptr(), wt._version, conv.bias._version, dense.PRECISION)
+        hit = getattr(conv, "_adc_packed", None)
+        if hit is not None and hit[0] == tag:
+            return hit[1], hit[2]
+        W = wt.detach()
+        co, ci = W.shape[:2]
+        Wp = torch.zeros(co, 4, ci, 4, 3, 3, device=W.device, dtype=W.dtype)
+        for q in range(4):
+            for r in range(4):
+                for dj in (-1, 0, 1):
+                    v = 4 * dj + r - q
+                    if -1 <= v <= 1:
+                        Wp[:, q, :, r, :, dj + 1] = W[:, :, :, v + 1]
+        wp = dense.prep_conv3x3_weights(Wp.reshape(co * 4, ci * 4, 3, 3), cin_pad=64)
+        bp = conv.bias.detach().repeat_interleave(4).contiguous()
+        conv._adc_packed = (tag, wp, bp)
+        return wp, bp
 
     def forward(self, x0, build_conf_input):
         assert x0.shape[1] > 3, "The input is not RGB-D or rgb-dc"
