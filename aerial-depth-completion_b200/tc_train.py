@@ -10,7 +10,7 @@ Everything between the NConv pyramid and the loss lives in zero-bordered NHWC bf
 * backward: data gradients = the forward kernel on the output gradient with transposed+flipped weights (stride 1) or four
   parity-class launches (stride 2, adc_conv3x3_dgrad_s2_tc); weight gradients = adc_conv3x3_wgrad_tc / _wgrad_box_tc straight
   from the NHWC buffers (MN-major UMMA operands); up-sampling backward + skip-gradient add + activation derivative =
-  adc_nhwc_grad_assemble; bias gradients = adc_nhwc_colsum.
+  adc_nhwc_grad_assemble, whose per-channel sums are the bias gradients.
 
 Buffers are allocated once per (module, batch shape, precision) and zero-filled once: kernels write interiors (or interiors
 plus zero borders) only, so borders and pad channels stay zero for the lifetime of the plan, and a captured CUDA graph sees
