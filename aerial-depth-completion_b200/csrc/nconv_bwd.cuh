@@ -19,8 +19,10 @@
 
 namespace adc {
 
+// 4 CTAs per SM (<= 128 registers) for the single-pass instantiations: measured 39.3 -> 37.6 us for <2,5> at L0 (28 bytes of spills);
+// the two-pass <4,3> body spills 444 bytes under that cap and slows down (47.5 -> 64 us), so it keeps 3 CTAs per SM.
 template <int CI, int K>
-__global__ void __launch_bounds__(128) nconv_bwd_data_kernel(const __grid_constant__ Maps2 maps, SrcP g, SrcP s0, SrcP s1, int has1,
+__global__ void __launch_bounds__(128, (CI > 2 ? 3 : 4)) nconv_bwd_data_kernel(const __grid_constant__ Maps2 maps, SrcP g, SrcP s0, SrcP s1, int has1,
                                                              float2* __restrict__ out0, float2* __restrict__ out1,
                                                              float* __restrict__ bpart, int H, int W, int wimg, int ximg) {
     using C = TileCfg<K>;

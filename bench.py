@@ -101,7 +101,7 @@ def cpu_reference_run(steps, warmup, frames):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()
