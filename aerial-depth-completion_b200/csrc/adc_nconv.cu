@@ -147,12 +147,12 @@ static int make_pair_map(CUtensorMap* m, const SrcP& s, int N, int box_w_pairs, 
     return 0;
 }
 
-template <int K>
+template <int K, int TH_ = 32>
 static int fill_maps(Maps2* maps, const SrcP& s0, const SrcP* s1, int N) {
     memset(maps, 0, sizeof(*maps));
-    using C = TileCfg<K>;
+    using C = TileCfg<K, TH_>;
     int rc = 0;
-    using U = Up2Cfg<K>;
+    using U = Up2Cfg<K, TH_>;
     if (s0.tma && (rc = make_pair_map(&maps->m0, s0, N, C::SWP, C::SH))) return rc;
     if (s0.up2 && (rc = make_pair_map(&maps->m0, s0, N, U::LW, U::LH))) return rc;
     if (s1 && s1->tma && (rc = make_pair_map(&maps->m1, *s1, N, C::SWP, C::SH))) return rc;
@@ -167,6 +167,9 @@ static int set_smem(Kern kern, int bytes) {
 
 static inline dim3 tile_grid(int N, int H, int W) { return dim3(ceil_div(W, 64), ceil_div(H, 32), N); }
 static inline int tiles(int N, int H, int W) { return N * ceil_div(W, 64) * ceil_div(H, 32); }
+// the weight-gradient kernel works on 64 x 16 tiles (WgCfg::TH): its grid and its per-CTA partial rows
+static inline dim3 wg_grid(int N, int H, int W) { return dim3(ceil_div(W, 64), ceil_div(H, 16), N); }
+static inline int wg_tiles(int N, int H, int W) { return N * ceil_div(W, 64) * ceil_div(H, 16); }
 static inline int blocks_1x1(long long plane) { return (int)ceil_div_ll(plane, 512); }
 
 template <int CI, int K>
@@ -238,13 +241,13 @@ static int launch_bwd_weight(const SrcP& g, const SrcP& s0, const SrcP* s1, floa
     const int smem = C::smem_bytes();
     if (!done) { int rc = set_smem(nconv_bwd_weight_kernel<CI, K>, smem); if (rc) return rc; done = true; }
     Maps2 maps;
-    int rc = fill_maps<K>(&maps, s0, s1, N);
+    int rc = fill_maps<K, C::TH>(&maps, s0, s1, N);
     if (rc) return rc;
     CUtensorMap gmap;
     memset(&gmap, 0, sizeof(gmap));
     if (g.tma && (rc = make_pair_map(&gmap, g, N, C::TW, C::TH))) return rc;
     { ProfScope _p(st, KIND_BWD_WEIGHT, g_cur_call, 8.0 * (2 + CI) * N * H * W);
-    nconv_bwd_weight_kernel<CI, K><<<tile_grid(N, H, W), C::NT, smem, st>>>(maps, gmap, g, s0, s1 ? *s1 : s0, s1 ? 1 : 0, wpart, H, W); }
+    nconv_bwd_weight_kernel<CI, K><<<wg_grid(N, H, W), C::NT, smem, st>>>(maps, gmap, g, s0, s1 ? *s1 : s0, s1 ? 1 : 0, wpart, H, W); }
     return check_cuda(cudaGetLastError(), "nconv_bwd_weight_kernel launch");
 }
 
@@ -476,7 +479,7 @@ struct LayerBwdLayout {
         r1 = o; o += s1 ? 2LL * N * s1->channels * plane : 0;
         l0 = o; o += 2 * src_pairs(s0, N);
         l1 = o; o += 2 * src_pairs(s1, N);
-        wblocks = Co == 1 ? N * blocks_1x1(plane) : tiles(N, H, W);
+        wblocks = Co == 1 ? N * blocks_1x1(plane) : wg_tiles(N, H, W);
         bblocks = Co == 1 ? wblocks : N * (int)ceil_div_ll(plane, 256);
         wpart = o; o += (long long)wblocks * kWStride;
         bpart = o; o += (long long)bblocks * 4;
@@ -730,7 +733,7 @@ struct BwdLayout {
         bblk[3] = tiles(g.N, g.h[1], g.w[1]); bblk[1] = tiles(g.N, g.h[0], g.w[0]); bblk[0] = tiles(g.N, g.h[0], g.w[0]);
         for (int k = 0; k < ADC_PYR_CALLS; ++k) {
             const int l = kCallLevel[k];
-            wblk[k] = k == 10 ? b1 : tiles(g.N, g.h[l], g.w[l]);
+            wblk[k] = k == 10 ? b1 : wg_tiles(g.N, g.h[l], g.w[l]);
             wpart[k] = o; o += (long long)wblk[k] * kWStride;
             bpart[k] = o; o += (long long)bblk[k] * 4;
         }

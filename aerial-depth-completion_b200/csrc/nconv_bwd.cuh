@@ -106,9 +106,13 @@ __global__ void __launch_bounds__(128, (CI > 2 ? 3 : 4)) nconv_bwd_data_kernel(c
 
 template <int CI, int K>
 struct WgCfg {
-    using T = TileCfg<K>;
+    // 16-row tiles (one row group): 38 KB (2->2, 5x5) / 56 KB (4->2, 3x3) of shared memory per CTA instead of 72 / 106 KB, so 5 / 4 CTAs
+    // share an SM and the TMA phase of one overlaps the FFMA2 phase of the others (with 2 CTAs per SM load time ~ compute time and
+    // the FMA pipe sat at ~50 %)
+    static constexpr int TH = 16;
+    using T = TileCfg<K, TH>;
     static constexpr int P = K / 2;
-    static constexpr int TW = 64, TH = 32, RG = 2, RH = TH / RG;   // two row groups of 16 rows
+    static constexpr int TW = 64, RG = 1, RH = TH / RG;
     static constexpr int ROLES = 2 * CI;                           // (o,i), Co = 2
     static constexpr int NT = 32 * ROLES * RG;
     static constexpr int STEPS = RH + K - 1;                       // 20 (K=5), 18 (K=3): multiples of K
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
                                                                             SrcP s0, SrcP s1, int has1,
                                                                             float* __restrict__ partial, int H, int W) {
     using C = WgCfg<CI, K>;
-    using T = TileCfg<K>;
+    using T = typename C::T;
     constexpr int P = C::P, NT = C::NT;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float2* sX = align128(smem_raw);                 // [CI] planes of {x, c} with halo
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
     if (g.tma) {
         if (tid == 0) mbar_init(bar2, 1);
     }
-    const bool pending = stage_sources<K, NT>(maps, s0, s1, has1 != 0, n, h0, w0, H, W, sX, bar, tid);
+    const bool pending = stage_sources<K, NT, C::TH>(maps, s0, s1, has1 != 0, n, h0, w0, H, W, sX, bar, tid);
     if (g.tma) {
         __syncthreads();
         if (tid == 0) {
@@ -158,8 +162,8 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
     }
     __syncthreads();
     if (pending) mbar_wait(bar, 0);
-    expand_up2_planes<K, NT>(s0, s1, has1 != 0, sX, tid);
-    premul_planes<K, NT>(sX, CI, tid);      // {x, c} -> {x*c, c}
+    expand_up2_planes<K, NT, C::TH>(s0, s1, has1 != 0, sX, tid);
+    premul_planes<K, NT, C::TH>(sX, CI, tid);      // {x, c} -> {x*c, c}
     if (g.tma) mbar_wait(bar2, 0);
     __syncthreads();
 

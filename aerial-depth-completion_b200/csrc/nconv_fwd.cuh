@@ -16,10 +16,10 @@
 
 namespace adc {
 
-template <int K>
+template <int K, int TH_ = 32>      // TH_: tile height (32 for the forward / data-gradient kernels, 16 for the weight gradient)
 struct TileCfg {
     static constexpr int P = K / 2;
-    static constexpr int TW = 64, TH = 32, NT = 128;
+    static constexpr int TW = 64, TH = TH_, NT = 128;
     // A TMA box must start on a 16-byte boundary of the innermost dimension (measured: an odd pair offset raises
     // 'illegal instruction'), so for odd halos the tile keeps XOFF spare pair(s) on the left.
     static constexpr int XOFF = P & 1;
@@ -43,10 +43,10 @@ __device__ __forceinline__ float2* align128(uint8_t* smem) {
 
 // Batched gather of one channel tile (generic path: upsampled / unaligned sources).  Four independent 8-byte loads are
 // issued per thread before any is consumed, so the loop is not serialised on DRAM latency.
-template <int K, int NT>
+template <int K, int NT, int TH_ = 32>
 __device__ __forceinline__ void gather_pair_tile(const SrcP& s, int sc, int n, int h0, int w0, int H, int W, float2* dst,
                                                  int tid) {
-    using C = TileCfg<K>;
+    using C = TileCfg<K, TH_>;
     constexpr int P = C::P, TOTAL = C::SH * C::SWP, U = 4;
     const float2* base = s.p + (long long)n * s.bs + (long long)sc * s.H * s.W;
     for (int i0 = tid; i0 < TOTAL; i0 += NT * U) {
@@ -73,9 +73,9 @@ __device__ __forceinline__ void gather_pair_tile(const SrcP& s, int sc, int n, i
 // ((h0-P+r) >> 1) and column ((w0-P-XOFF+c) >> 1).  h0 and w0-P-XOFF are even, so relative to the box origin
 // (floor((h0-P)/2), (w0-P-XOFF)/2) that is row (r + (P&1)) >> 1, column c >> 1.  Rows/columns outside the low-resolution
 // image are the hardware's zero fill and coincide with the layer's own zero padding because H = 2*Hs, W = 2*Ws.
-template <int K>
+template <int K, int TH_ = 32>
 struct Up2Cfg {
-    using C = TileCfg<K>;
+    using C = TileCfg<K, TH_>;
     // The box must start on an even pair (16-byte) offset of the row like every TMA box here; (w0-P-XOFF)/2 = w0/2 - 1 is odd, so
     // the box starts one low-resolution pair further left (LXO) and is two pairs wider.
     static constexpr int LXO = 1;
@@ -86,11 +86,11 @@ struct Up2Cfg {
 };
 
 // Stage all input-channel tiles of up to two sources.  Returns true if a TMA transaction is pending on `bar`.
-template <int K, int NT>
+template <int K, int NT, int TH_ = 32>
 __device__ __forceinline__ bool stage_sources(const Maps2& maps, const SrcP& s0, const SrcP& s1, bool has1, int n, int h0, int w0,
                                               int H, int W, float2* planes, uint64_t* bar, int tid) {
-    using C = TileCfg<K>;
-    using U = Up2Cfg<K>;
+    using C = TileCfg<K, TH_>;
+    using U = Up2Cfg<K, TH_>;
     const bool t0 = s0.tma || s0.up2, t1 = has1 && (s1.tma || s1.up2);
     const bool any_tma = t0 || t1;
     if (any_tma) {
@@ -114,9 +114,9 @@ __device__ __forceinline__ bool stage_sources(const Maps2& maps, const SrcP& s0,
         }
     }
     if (!t0)
-        for (int c = 0; c < s0.ch; ++c) gather_pair_tile<K, NT>(s0, c, n, h0, w0, H, W, planes + c * C::PLANE, tid);
+        for (int c = 0; c < s0.ch; ++c) gather_pair_tile<K, NT, TH_>(s0, c, n, h0, w0, H, W, planes + c * C::PLANE, tid);
     if (has1 && !t1)
-        for (int c = 0; c < s1.ch; ++c) gather_pair_tile<K, NT>(s1, c, n, h0, w0, H, W, planes + (s0.ch + c) * C::PLANE, tid);
+        for (int c = 0; c < s1.ch; ++c) gather_pair_tile<K, NT, TH_>(s1, c, n, h0, w0, H, W, planes + (s0.ch + c) * C::PLANE, tid);
     return any_tma;
 }
 
@@ -124,10 +124,10 @@ __device__ __forceinline__ bool stage_sources(const Maps2& maps, const SrcP& s0,
 // pairs into registers, the CTA synchronises, then each pair is written twice (one 16-byte store) at its two full-resolution
 // columns -- reads complete before any write, so the box may overlap the rows it expands into.  Must be called by all
 // threads of the CTA (contains a barrier); no-op when no source is up2.
-template <int K, int NT>
+template <int K, int NT, int TH_ = 32>
 __device__ __forceinline__ void expand_up2_planes(const SrcP& s0, const SrcP& s1, bool has1, float2* planes, int tid) {
-    using C = TileCfg<K>;
-    using U = Up2Cfg<K>;
+    using C = TileCfg<K, TH_>;
+    using U = Up2Cfg<K, TH_>;
     const int n0 = s0.up2 ? s0.ch : 0, n1 = (has1 && s1.up2) ? s1.ch : 0;
     if (n0 + n1 == 0) return;
     const int first = s0.up2 ? 0 : s0.ch;              // the up2 planes are contiguous: [first, first + nup)
@@ -207,9 +207,9 @@ __device__ __forceinline__ void conv_patch(const float2* planes, const float* __
 // {x, c} -> {x*c, c} in place over `nplanes` staged planes.  Done once per CTA in shared memory (two pairs per 16-byte
 // access) rather than per thread in registers: multiplying one half of a register pair in the FFMA2 loop made ptxas copy
 // the pairs around (1183 MOVs per 1600 FFMA2).
-template <int K, int NT>
+template <int K, int NT, int TH_ = 32>
 __device__ __forceinline__ void premul_planes(float2* planes, int nplanes, int tid) {
-    using C = TileCfg<K>;
+    using C = TileCfg<K, TH_>;
     float4* p = reinterpret_cast<float4*>(planes);
     const int total = nplanes * C::PLANE / 2;
     for (int i = tid; i < total; i += NT) {
