@@ -549,9 +549,15 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, detail_path=""):
     agg, tc = {}, {}
     reps = 3
     cap = 1024
-    for i in range(reps):
+    from aerial_depth_completion_b200 import tc_train
+    side_prev = tc_train._SIDE_STREAM
+    tc_train._SIDE_STREAM = False       # one stream while profiling: an event pair must time its kernel alone (the library does the
+    for i in range(reps):               # same for the pyramid's weight-gradient stream when profiling is enabled)
         lib.adc_profile_enable(1)
-        trainer._eager_step(dev_in[i % pool_n], dev_tg[i % pool_n])
+        try:
+            trainer._eager_step(dev_in[i % pool_n], dev_tg[i % pool_n])
+        finally:
+            tc_train._SIDE_STREAM = side_prev if i == reps - 1 else False
         torch.cuda.synchronize()
         n = ctypes.c_int(0)
         kinds = (ctypes.c_int * cap)()
