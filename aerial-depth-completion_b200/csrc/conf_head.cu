@@ -299,7 +299,7 @@ int adc_conf_bn_stats(const float* y, int y_stride, int N, int C, int H, int W, 
     cudaStream_t st = (cudaStream_t)stream;
     const int C4 = (C + 3) / 4;
     const double M = (double)N * H * W;
-    adc::Prof prof(st, adc::KIND_TC_GLUE, training ? M * C * 4.0 : 0.0);
+    adc::Prof prof(st, adc::KIND_CONF_HEAD, training ? M * C * 4.0 : 0.0);
     int rc = 0;
     if (training) {
         adc::count_launches(1);
@@ -319,7 +319,7 @@ int adc_conf_head_apply(const float* y, int y_stride, const float* coef, const f
         return ADC_E_BADARG;
     }
     const long long pixels = (long long)N * H * W;
-    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)pixels * (C + 1) * 4.0);
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_CONF_HEAD, (double)pixels * (C + 1) * 4.0);
     conf_apply_kernel<<<grid_for(pixels), 256, 0, (cudaStream_t)stream>>>(y, y_stride, coef, w2, b2, conf, N, C, (C + 3) / 4, H, W);
     return adc::check_cuda(cudaGetLastError(), "conf_apply_kernel launch");
 }
@@ -335,7 +335,7 @@ int adc_conf_head_bwd(const float* y, int y_stride, float* coef, const float* w2
     cudaStream_t st = (cudaStream_t)stream;
     const int C4 = (C + 3) / 4;
     const long long pixels = (long long)N * H * W;
-    adc::Prof prof(st, adc::KIND_TC_GLUE, (double)pixels * (2.0 * C * 4.0 + 16.0 + gy_stride * (gy_lo ? 4.0 : 2.0)));
+    adc::Prof prof(st, adc::KIND_CONF_HEAD, (double)pixels * (2.0 * C * 4.0 + 16.0 + gy_stride * (gy_lo ? 4.0 : 2.0)));
     adc::count_launches(2);
     conf_bwd_sums_kernel<<<kParts, 256, 0, st>>>(y, y_stride, coef, w2, gconf, conf, N, C, C4, H, W, reinterpret_cast<double*>(workspace));
     int rc = adc::check_cuda(cudaGetLastError(), "conf_bwd_sums_kernel launch");

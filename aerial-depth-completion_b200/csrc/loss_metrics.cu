@@ -148,7 +148,7 @@ int adc_masked_loss_fwd(const float* pred, const float* target, long long n, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(n);
-    adc::Prof prof(st, adc::KIND_TC_GLUE, (double)n * 8.0);
+    adc::Prof prof(st, adc::KIND_TRAIN, (double)n * 8.0);
     adc::count_launches(1);
     masked_loss_partial_kernel<<<grid, 256, 0, st>>>(pred, target, n, kind, reinterpret_cast<double*>(workspace));
     int rc = adc::check_cuda(cudaGetLastError(), "masked_loss_partial_kernel launch");
@@ -163,7 +163,7 @@ int adc_masked_loss_bwd(const float* pred, const float* target, const float* glo
         adc::set_error("adc_masked_loss_bwd: bad argument");
         return ADC_E_BADARG;
     }
-    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)n * 12.0);
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TRAIN, (double)n * 12.0);
     long long b = (n + 255) / 256;
     masked_loss_bwd_kernel<<<(int)(b < 148 * 16 ? b : 148 * 16), 256, 0, (cudaStream_t)stream>>>(pred, target, gloss, count, n, kind, gpred);
     return adc::check_cuda(cudaGetLastError(), "masked_loss_bwd_kernel launch");
@@ -177,7 +177,7 @@ int adc_depth_metrics(const float* output, const float* target, const float* con
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(n);
-    adc::Prof prof(st, adc::KIND_TC_GLUE, (double)n * (confidence ? 12.0 : 8.0));
+    adc::Prof prof(st, adc::KIND_TRAIN, (double)n * (confidence ? 12.0 : 8.0));
     adc::count_launches(1);
     depth_metrics_partial_kernel<<<grid, 256, 0, st>>>(output, target, confidence, threshold, n, reinterpret_cast<double*>(workspace));
     int rc = adc::check_cuda(cudaGetLastError(), "depth_metrics_partial_kernel launch");

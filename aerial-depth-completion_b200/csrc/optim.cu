@@ -68,7 +68,7 @@ int adc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
         return ADC_E_BADARG;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    adc::Prof prof(st, adc::KIND_TC_GLUE, (double)n * 28.0);
+    adc::Prof prof(st, adc::KIND_TRAIN, (double)n * 28.0);
     adc::count_launches(1);
     optim::adam_advance_kernel<<<1, 1, 0, st>>>(step);
     int rc = adc::check_cuda(cudaGetLastError(), "adam_advance_kernel launch");

@@ -542,7 +542,8 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, detail_path=""):
              6: "head_fwd", 7: "head_bwd"}
     tc_names = {20: "tc_conv_box(stride-2 fprop)", 21: "tc_conv_rowseg(fprop, 1x1, data gradients incl. quad forms)", 22: "tc_dgrad_s2_parity",
                 23: "tc_wgrad_flat(stride-1, 1x1)", 24: "tc_wgrad_box(stride-2)", 25: "tc_glue(upsample, grad assemble + bias grad)",
-                26: "tc_layout(im2col pack, unshuffle)", 27: "tc_prep_weights", 28: "conv10 quad head (direct kernels)"}
+                26: "tc_layout(im2col pack, unshuffle)", 27: "tc_prep_weights", 28: "conv10 quad head (direct kernels)",
+                29: "loss + optimizer (masked loss fwd/bwd, flat Adam)", 30: "confidence head (BN/LeakyReLU/1x1/sigmoid passes)"}
     mma_kinds = (20, 21, 22, 23, 24)
     calls = ("nconv1@L0", "nconv2@L0", "nconv3@L0", "nconv2@L1", "nconv3@L1", "nconv2@L2", "nconv2@L3", "nconv4@L2", "nconv5@L1",
              "nconv6@L0", "nconv7@L0")
