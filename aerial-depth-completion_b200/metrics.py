@@ -7,10 +7,6 @@ import numpy as np
 import torch
 
 
-def log10(x):
-    return torch.log(x) / math.log(10)
-
-
 class Result(object):
     def __init__(self, threshold=0):
         self.irmse, self.imae = 0, 0
@@ -38,29 +34,14 @@ class Result(object):
         self.loss0, self.loss1, self.loss2 = loss0, loss1, loss2
 
     def evaluate(self, output, target, confidence=None):
-        if output.is_cuda:
-            # every sum in ONE kernel pass, one transfer of the ten scalars (csrc/loss_metrics.cu: adc_depth_metrics)
-            from . import ops
-            vals = ops.depth_metrics(output.detach().float(), target.detach().float(),
-                                     None if confidence is None else confidence.detach().float(), self.threshold).tolist()
-            self.mse, self.mae, self.lg10, self.absrel, self.delta1, self.delta2, self.delta3, imse, self.imae = vals[:9]
-            self.rmse = math.sqrt(self.mse) if self.mse == self.mse else float('nan')
-            self.irmse = math.sqrt(imse) if imse == imse else float('nan')
-            self.data_time = 0
-            self.gpu_time = 0
-            return
-        valid_mask = target > 0 if confidence is None else (target > 0) & (confidence > self.threshold)
-        output, target = output[valid_mask], target[valid_mask]
-        abs_diff = (output - target).abs()
-        max_ratio = torch.max(output / target, target / output)
-        abs_inv_diff = (1 / output - 1 / target).abs()
-        vals = torch.stack([
-            torch.pow(abs_diff, 2).mean(), abs_diff.mean(), (log10(output) - log10(target)).abs().mean(),
-            (abs_diff / target).mean(), (max_ratio < 1.25).float().mean(), (max_ratio < 1.25 ** 2).float().mean(),
-            (max_ratio < 1.25 ** 3).float().mean(), torch.pow(abs_inv_diff, 2).mean(), abs_inv_diff.mean()]).tolist()
-        self.mse, self.mae, self.lg10, self.absrel, self.delta1, self.delta2, self.delta3, imse, self.imae = vals
-        self.rmse = math.sqrt(self.mse)
-        self.irmse = math.sqrt(imse)
+        """Every sum in ONE kernel pass, one transfer of the ten scalars (csrc/loss_metrics.cu: adc_depth_metrics).  CUDA tensors
+        only: the B200 path has no CPU fallback."""
+        from . import ops
+        vals = ops.depth_metrics(output.detach().float(), target.detach().float(),
+                                 None if confidence is None else confidence.detach().float(), self.threshold).tolist()
+        self.mse, self.mae, self.lg10, self.absrel, self.delta1, self.delta2, self.delta3, imse, self.imae = vals[:9]
+        self.rmse = math.sqrt(self.mse) if self.mse == self.mse else float('nan')
+        self.irmse = math.sqrt(imse) if imse == imse else float('nan')
         self.data_time = 0
         self.gpu_time = 0
 

@@ -475,39 +475,25 @@ class GMSNet(nn.Module):
 ################################################
 
 class _MaskedLoss(nn.Module):
-    """Mean of a per-pixel error over ``target > 0`` (confidence_depth_framework.py:829-914).  Computed as a masked sum /
-    count in one pass (no boolean-index compaction).  ``lazy`` = keep ``self.loss`` and the >100-valid-pixels check on the
-    device, so a training step has no host synchronisation; the default mirrors the reference (python floats, assert)."""
+    """Mean of a per-pixel error over ``target > 0`` (confidence_depth_framework.py:829-914): one reduction kernel forward, one
+    elementwise kernel backward (csrc/loss_metrics.cu), no boolean-index compaction.  CUDA tensors only (no CPU fallback).
+    ``lazy`` = keep ``self.loss`` and the >100-valid-pixels check on the device, so a training step has no host synchronisation;
+    the default mirrors the reference (python floats, assert)."""
     lazy = False
+    kind = None
 
     def __init__(self):
         super(_MaskedLoss, self).__init__()
         self.loss = -1
 
-    def _error(self, pred, target, mask):
-        raise NotImplementedError
-
     def forward(self, depth_input, depth_prediction, depth_target, epoch=None):
         assert depth_prediction.dim() == depth_target.dim(), "inconsistent dimensions"
-        if depth_prediction.is_cuda:
-            # one reduction kernel forward, one elementwise kernel backward (csrc/loss_metrics.cu); no boolean-index compaction
-            from .. import ops
-            final_loss, num_valids = ops.masked_loss(depth_prediction, depth_target.detach(), self.kind)
-            if self.lazy:
-                torch._assert_async(num_valids > 100, 'training image has less than 100 valid pixels')
-            else:
-                assert (num_valids > 100), 'training image has less than 100 valid pixels'
-            self.loss = [final_loss.detach() if self.lazy else final_loss.item(), 0, 0]
-            return final_loss
-        # host tensors (the gloo host-logic tests): the same definition with torch ops
-        mask = (depth_target > 0).detach()
-        num_valids = mask.sum()
+        from .. import ops
+        final_loss, num_valids = ops.masked_loss(depth_prediction, depth_target.detach(), self.kind)
         if self.lazy:
             torch._assert_async(num_valids > 100, 'training image has less than 100 valid pixels')
         else:
             assert (num_valids > 100), 'training image has less than 100 valid pixels'
-        err = torch.where(mask, self._error(depth_prediction, depth_target, mask), torch.zeros_like(depth_target))
-        final_loss = err.sum() / num_valids
         self.loss = [final_loss.detach() if self.lazy else final_loss.item(), 0, 0]
         return final_loss
 
@@ -530,28 +516,14 @@ class DualLoss(nn.Module):
 class MaskedMSELoss(_MaskedLoss):
     kind = 'l2'
 
-    def _error(self, pred, target, mask):
-        return (target - pred) ** 2
-
 
 class InvertedMaskedL1Loss(_MaskedLoss):
     kind = 'il1'
-
-    def _error(self, pred, target, mask):
-        safe_t = torch.where(mask, target, torch.ones_like(target))
-        return ((1.0 / safe_t) - (1.0 / pred)).abs()
 
 
 class MaskedAbsRelLoss(_MaskedLoss):
     kind = 'absrel'
 
-    def _error(self, pred, target, mask):
-        safe_t = torch.where(mask, target, torch.ones_like(target))
-        return ((target - pred) / safe_t).abs()
-
 
 class MaskedL1Loss(_MaskedLoss):
     kind = 'l1'
-
-    def _error(self, pred, target, mask):
-        return (target - pred).abs()

@@ -65,3 +65,48 @@ def test_depth_metrics_vs_oracle(with_conf):
     r.evaluate(pred.cuda(), target.cuda(), None if conf is None else conf.cuda())
     for k in ("mse", "rmse", "mae", "lg10", "absrel", "delta1", "delta2", "delta3", "irmse", "imae"):
         assert abs(getattr(r, k) - ref[k]) <= 2e-5 * abs(ref[k]) + 1e-9, (k, getattr(r, k), ref[k])
+
+
+@gpu
+def test_lazy_loss_matches_eager():
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    g = torch.Generator().manual_seed(3)
+    t = torch.rand(2, 1, 24, 32, generator=g) * 5
+    t[t < 1] = 0
+    t = t.cuda()
+    p = (t * 1.1 + 0.2).requires_grad_(True)
+    for cls in (mc.MaskedMSELoss, mc.MaskedL1Loss, mc.InvertedMaskedL1Loss, mc.MaskedAbsRelLoss):
+        a, b = cls(), cls()
+        b.lazy = True                 # device-side bookkeeping: no .item(), asynchronous assert
+        la, lb = a(None, p, t), b(None, p, t)
+        assert torch.equal(la, lb) and isinstance(a.loss[0], float) and torch.is_tensor(b.loss[0])
+
+
+@gpu
+def test_losses_vs_reference_golden():
+    """Loss values and gradients produced by the unmodified reference (tests/golden/make_golden.py)."""
+    from golden_util import gold
+    from oracle import synth
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    G = gold("sampling_metrics")
+    for kind, cls in (("l2", mc.MaskedMSELoss), ("l1", mc.MaskedL1Loss), ("il1", mc.InvertedMaskedL1Loss), ("absrel", mc.MaskedAbsRelLoss)):
+        inp, tgt = synth.synth_frames(1, 24, 32, seed=9)
+        tgt = (tgt * (tgt > 2).float()).float().cuda()
+        pred = (tgt * 1.1 + 0.3).requires_grad_(True)
+        l = cls()(None, pred, tgt)
+        l.backward()
+        assert abs(float(l) - G["loss_" + kind][0]) < 1e-5 * abs(G["loss_" + kind][0])
+        assert relmax(pred.grad.cpu(), G["loss_" + kind + "_grad"]) < 1e-5
+
+
+@gpu
+def test_metrics_vs_reference_golden():
+    """KAT-6 of SURVEY.md 8c: Result.evaluate on five hand-checked pixels."""
+    import numpy as np
+    from golden_util import gold
+    from aerial_depth_completion_b200.metrics import Result
+    G = gold("sampling_metrics")
+    r = Result()
+    r.evaluate(torch.tensor([1., 2., 4., 8., 3.]).cuda(), torch.tensor([1.1, 0, 5.5, 8., 2.]).cuda())
+    got = [r.rmse, r.mae, r.delta1, r.delta2, r.delta3, r.absrel, r.lg10, r.irmse, r.imae, r.mse]
+    assert np.allclose(got, G["kat6_metrics"], rtol=1e-5)
