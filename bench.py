@@ -148,15 +148,44 @@ def reference_arm(args):
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed regions run: through NVML (nvidia_ml_py, ~10 ms per sample) when it
+    loads, else one nvidia-smi call per sample (~100 ms)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    BITS = (0x8, 0x40, 0x20, 0x4)          # NVML clocks-event-reason bits, in the order of NAMES
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.source = index, [], False, "nvidia-smi"
+
+    def _nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain list of indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            ids = [int(t) for t in vis.split(",")]
+            if self.index < len(ids):
+                idx = ids[self.index]
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        return pynvml, h, reasons, mx
 
     def run(self):
+        try:
+            nv, h, reasons, mx = self._nvml()
+            self.source = "nvml"
+            while not self.stop_flag:
+                mask = int(reasons(h))
+                self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
+                                 ["Active" if mask & b else "Not Active" for b in self.BITS])
+                time.sleep(0.01)
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
@@ -165,14 +194,14 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({self.NAMES[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm),
+                "source": self.source}
 
 
 def _finish(world):
