@@ -134,6 +134,7 @@ SIGNATURES = {
     "adc_masked_loss_bwd": (c_int, [_vp, _vp, _vp, _vp, c_ll, c_int, _vp, _vp]),
     "adc_depth_metrics": (c_int, [_vp, _vp, _vp, ctypes.c_float, c_ll, _vp, _vp, _vp]),
     "adc_adam_step": (c_int, [_vp, _vp, _vp, _vp, _vp, c_ll] + [ctypes.c_double] * 5 + [_vp]),
+    "adc_uniform_sampling": (c_int, [_vp, _vp, c_int, ctypes.c_float, c_int, _vp, c_int, c_ll, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -334,6 +334,13 @@ int adc_depth_metrics(const float* output, const float* target, const float* con
 int adc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step, long long n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, adc_stream_t stream);
 
+/* ---- sparse-depth sampling (dataloaders/dense_to_sparse.py:29-48, UniformSampling.dense_to_sparse) on the device, bit-exact with
+ * the reference's numpy stream: frame n draws np.random.uniform(0, 1, HW) after np.random.seed(seeds[n]) (MT19937, 53-bit doubles)
+ * and keeps mask = (depth > 0 [& depth <= max_depth]) & (u < num_samples / count(keep)).  depth: fp32 [N][HW]; seeds: device
+ * uint32 [N]; mask: uint8 [N][HW] (0 / 1).  num_samples = 0 or no valid pixel: mask = keep, like the reference. */
+int adc_uniform_sampling(const float* depth, const unsigned int* seeds, int num_samples, float max_depth, int use_max_depth,
+                         unsigned char* mask, int N, long long HW, adc_stream_t stream);
+
 
 #ifdef __cplusplus
 }
