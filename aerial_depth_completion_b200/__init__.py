@@ -1,12 +1,9 @@
-"""Importable alias of the package directory ``aerial-depth-completion_b200/`` (a hyphen cannot be imported).
+"""B200-native (sm_100a) hot path of aerial-depth-completion behind the reference's own module API.
 
-``import aerial_depth_completion_b200`` executes ``aerial-depth-completion_b200/__init__.py`` with this module's
-``__path__`` pointing there, so sub-modules (``.model_zoo``, ``.metrics`` ...) resolve to the real package.
+Drop-in for the reference's ``model_zoo`` / ``metrics`` / ``dataloaders.dense_to_sparse`` modules on the
+NConv depth-completion path: same class names, constructor arguments, ``state_dict`` keys and error behaviour.
+The compute is hand-written CUDA reached through the C ABI in ``include/adc_b200.h`` (``libadc_b200.so``);
+there is no CPU fallback -- importing ``_lib`` without the built library, or calling an op on a non-CUDA
+tensor, raises.
 """
-import os as _os
-
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "aerial-depth-completion_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
-del _f
+__version__ = "0.1.0"

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libadc_b200.so")
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "aerial_depth_completion_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-        "(or `make -C aerial-depth-completion_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+        "(or `make -C aerial_depth_completion_b200/csrc`). There is no CPU fallback." % LIB_PATH)
 
 lib = ctypes.CDLL(LIB_PATH)
 

@@ -67,7 +67,7 @@ def test_cpu_tensors_raise_no_fallback():
 
 
 def test_product_does_not_import_oracle():
-    pkg = os.path.join(ROOT, "aerial-depth-completion_b200")
+    pkg = os.path.join(ROOT, "aerial_depth_completion_b200")
     for d, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):

@@ -1,6 +1,6 @@
 // Microbenchmark: cycles per tcgen05.mma (cta_group::1, kind::f16, M=128, K=16, operands in shared memory) as a function of N,
 // for K-major SWIZZLE_128B and MN-major operands, issued back to back by one thread into the same / alternating accumulators.
-// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../aerial-depth-completion_b200/csrc -o mma_rate mma_rate.cu -lcuda
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../aerial_depth_completion_b200/csrc -o mma_rate mma_rate.cu -lcuda
 #include "tc_common.cuh"
 namespace adc { void set_error(const char*, ...) {} int check_cuda(cudaError_t e, const char*) { return (int)e; } }
 using namespace tc;
