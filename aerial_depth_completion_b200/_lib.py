@@ -66,6 +66,7 @@ SIGNATURES = {
     "adc_last_error": (ctypes.c_char_p, []),
     "adc_launch_count": (c_ll, []),
     "adc_profile_enable": (c_int, [c_int]),
+    "adc_set_side_stream": (c_int, [c_int]),
     "adc_profile_read": (c_int, [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int),
                                  ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
     "adc_nconv2d_fwd_scratch_floats": (ctypes.c_size_t, [_sp, _sp] + [c_int] * 4),
@@ -134,6 +135,7 @@ SIGNATURES = {
     "adc_masked_loss_bwd": (c_int, [_vp, _vp, _vp, _vp, c_ll, c_int, _vp, _vp]),
     "adc_depth_metrics": (c_int, [_vp, _vp, _vp, ctypes.c_float, c_ll, _vp, _vp, _vp]),
     "adc_adam_step": (c_int, [_vp, _vp, _vp, _vp, _vp, c_ll] + [ctypes.c_double] * 5 + [_vp]),
+    "adc_adam_step_dev": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_ll, _vp]),
     "adc_uniform_sampling": (c_int, [_vp, _vp, c_int, ctypes.c_float, c_int, _vp, c_int, c_ll, _vp]),
 }
 

@@ -65,6 +65,7 @@ static int* g_counters = nullptr; // tile-scheduler counters of the persistent k
 static int g_persist = 1, g_sms = 148;
 static int g_use_tma = -1;
 static int g_side_on = 1;        // weight-gradient kernels of adc_pyramid_bwd on a second stream (ADC_NO_SIDE_STREAM=1 disables)
+static int g_side_user = 1;      // run-time switch (adc_set_side_stream): parity tests compare the two-stream schedule with the serial one
 static cudaStream_t g_side = nullptr;
 static cudaEvent_t g_ev_fork[ADC_PYR_CALLS], g_ev_join[ADC_PYR_CALLS];
 static int g_up2 = 1;           // exact-2x upsampled sources through TMA + in-place expansion (ADC_NO_UP2=1 disables)
@@ -339,6 +340,12 @@ extern "C" {
 int adc_abi_version(void) { return 2; }
 
 long long adc_launch_count(void) { return g_launches; }
+
+int adc_set_side_stream(int on) {
+    const int prev = g_side_user;
+    g_side_user = on ? 1 : 0;
+    return prev;
+}
 
 int adc_profile_enable(int on) {
     g_prof_on = on ? 1 : 0;
@@ -795,7 +802,7 @@ int adc_pyramid_bwd(const adc_pyramid_bwd_t* a, adc_stream_t stream) {
     auto fimg = [&](int call) { return wimg_index(a->slot, 0, call); };
     auto bimg = [&](int call) { return wimg_index(a->slot, 1, call); };
     // profiling runs keep everything on one stream so that the per-kernel event pairs time each kernel alone
-    const bool side = need_w && g_side_on && g_side != nullptr && !g_prof_on;
+    const bool side = need_w && g_side_on && g_side_user && g_side != nullptr && !g_prof_on;
     int seq = 0, last_join = -1;
     // one layer: G (transformed gradient of the call's output) -> weight partials + gradients of its sources
     auto layer_bwd = [&](int call, const float2* G, int in0, int in1, float2* out0, float2* out1, int xcall, bool need_data) -> int {

@@ -8,13 +8,14 @@ import torch
 import torch.nn.functional as F
 
 BACKEND = "cudnn"
-PRECISION = "fp32"
+PRECISION = "bf16x3"
 
 
 def set_precision(mode):
-    """'fp32' (strict: parity 1e-4 with the reference, TF32 off in library calls), 'tf32' (library TF32, parity 1e-2) or
-    'bf16' / 'bf16x3' (inference forward of the wide layers on the hand-written tcgen05 kernels, NHWC activations, fp32
-    accumulation in TMEM: plain bf16 operands, or hi+lo bf16 pairs with three MMAs per product for fp32-grade parity)."""
+    """'bf16x3' (DEFAULT) / 'bf16': the dense layers run on the hand-written tcgen05 kernels (NHWC activations, fp32 accumulation
+    in TMEM) with hi+lo bf16 operand pairs (fp32-grade results, the 1e-4 parity mode) or plain bf16 operands (the 1e-2 mode).
+    'fp32' / 'tf32' route the dense layers to the ATen/cuDNN library instead -- the baseline the kernels are measured against, kept
+    as a debugging aid; the NConv pyramid, losses, metrics and optimizer are this library's kernels in every mode."""
     global PRECISION
     if mode not in ("fp32", "tf32", "bf16", "bf16x3"):
         raise ValueError("precision must be 'fp32', 'tf32', 'bf16' or 'bf16x3'")
@@ -23,7 +24,7 @@ def set_precision(mode):
     torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
 
 
-set_precision("fp32")
+set_precision("bf16x3")      # the B200 path is the default: hand-written tcgen05 kernels, fp32-grade results (hi/lo split operands)
 
 
 def _need_cuda(x):

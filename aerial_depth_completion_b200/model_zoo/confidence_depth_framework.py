@@ -477,8 +477,10 @@ class GMSNet(nn.Module):
 class _MaskedLoss(nn.Module):
     """Mean of a per-pixel error over ``target > 0`` (confidence_depth_framework.py:829-914): one reduction kernel forward, one
     elementwise kernel backward (csrc/loss_metrics.cu), no boolean-index compaction.  CUDA tensors only (no CPU fallback).
-    ``lazy`` = keep ``self.loss`` and the >100-valid-pixels check on the device, so a training step has no host synchronisation;
-    the default mirrors the reference (python floats, assert)."""
+    ``lazy`` = keep ``self.loss`` and the >100-valid-pixels check on the device, so a training step has no host synchronisation:
+    a batch with <= 100 valid pixels then yields a NaN loss, which ``optim.FlatAdam``'s guard turns into a skipped update (the
+    reference raises an AssertionError on the host; a device-side assert would kill the CUDA context).  The default mirrors the
+    reference (python floats, assert).  ``num_valid`` keeps the valid-pixel count of the last call on the device."""
     lazy = False
     kind = None
 
@@ -490,8 +492,12 @@ class _MaskedLoss(nn.Module):
         assert depth_prediction.dim() == depth_target.dim(), "inconsistent dimensions"
         from .. import ops
         final_loss, num_valids = ops.masked_loss(depth_prediction, depth_target.detach(), self.kind)
+        self.num_valid = num_valids
         if self.lazy:
-            torch._assert_async(num_valids > 100, 'training image has less than 100 valid pixels')
+            nan = self.__dict__.get('_nan')
+            if nan is None or nan.device != final_loss.device:
+                nan = self.__dict__['_nan'] = final_loss.new_full((), float('nan'))
+            final_loss = torch.where(num_valids > 100, final_loss, nan)
         else:
             assert (num_valids > 100), 'training image has less than 100 valid pixels'
         self.loss = [final_loss.detach() if self.lazy else final_loss.item(), 0, 0]

@@ -82,13 +82,15 @@ class EnforcePos(object):
 
     def __call__(self, module, inputs):
         if module.training:
+            # the reference rebinds ``weight.data``; the values are copied INTO the parameter's storage here so that flat
+            # parameter buckets (optim.FlatAdam, parallel.DataParallelTrainer) and captured CUDA graphs keep their addresses
             weight = getattr(module, self.name)
-            weight.data = self._pos(weight).data
+            weight.data.copy_(self._pos(weight).data)
 
     def _pos(self, p):
         pos_fn = self.pos_fn.lower()
         if pos_fn == 'softplus':
-            return ops.softplus_pow(p.detach(), 1) if p.is_cuda else F.softplus(p, beta=10)
+            return ops.softplus_pow(p.detach(), 1)          # CUDA kernel; a CPU tensor raises (no CPU path)
         if pos_fn == 'softmax':
             sz = p.size()
             return F.softmax(p.view(sz[0], sz[1], -1), -1).view(sz)

@@ -76,7 +76,7 @@ class NConv2dFunction(torch.autograd.Function):
         co, ci_w, k, k2 = weight.shape
         if ci_w != ci or k != k2 or c.shape != x.shape:
             raise RuntimeError("NConv2d: shape mismatch data %s conf %s weight %s" % (tuple(x.shape), tuple(c.shape), tuple(weight.shape)))
-        wv = weight.detach().contiguous()
+        wv = weight.detach().clone()     # forward-time values (s = sum of w): a later call's EnforcePos hook rewrites the Parameter in place
         bv = bias.detach().contiguous()
         y = torch.empty((n, co, h, w), device=x.device, dtype=torch.float32)
         cout = torch.empty_like(y)

@@ -4,7 +4,12 @@ The reference trainer builds ``torch.optim.Adam(params, lr, weight_decay)`` over
 foreach implementation launches seven multi-tensor kernels of ~27 us each for GEDNet's thirty small tensors.  ``FlatAdam`` has the
 same constructor and ``step`` / ``zero_grad`` / ``state_dict`` surface, but re-homes every parameter, its gradient and both moments as
 views into four flat fp32 buffers, so the update is ONE elementwise kernel (adc_adam_step) and the gradient buffer is exactly the
-bucket the data-parallel trainer all-reduces.  The step counter lives on the device: a captured CUDA graph advances it on replay.
+bucket the data-parallel trainer all-reduces.  The step counter AND the hyper-parameters (lr, betas, eps, weight_decay) live on the
+device: a captured CUDA graph advances the bias correction on replay and follows a learning-rate schedule (``refresh_hyper`` copies
+changed ``param_groups`` values before a replay; trainer.py:236-241 decays lr every 5 epochs).  ``guard`` (a device scalar, normally
+the step's loss) makes the update a no-op when it is not finite -- the reference trainer skips such batches (trainer.py:206-208).
+It subclasses ``torch.optim.Adam`` so the reference's checkpoint tagging ``isinstance(optimizer, torch.optim.Adam)``
+(trainer.py:147) keeps saying 'adam'.
 """
 import ctypes
 
@@ -13,14 +18,14 @@ import torch
 from ._lib import lib, check
 
 
-class FlatAdam(torch.optim.Optimizer):
+class FlatAdam(torch.optim.Adam):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False):
         if amsgrad:
             raise ValueError("FlatAdam: amsgrad is not supported (the reference trainer does not use it)")
         params = list(params)
         if params and isinstance(params[0], dict):
             raise ValueError("FlatAdam takes one flat list of parameters (one group), like the reference trainer passes")
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         ps = [p for p in self.param_groups[0]["params"] if p.requires_grad]
         if not ps:
             raise ValueError("FlatAdam: no trainable parameters")
@@ -34,7 +39,12 @@ class FlatAdam(torch.optim.Optimizer):
         self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
         self.flat_exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.step_t = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._state4 = torch.zeros(4, device=dev, dtype=torch.float32)      # {t, step_size, 1/sqrt(1-b2^t), apply}
+        self.step_t = self._state4[0:1]
+        self._hyper = torch.zeros(5, device=dev, dtype=torch.float64)       # {lr, beta1, beta2, eps, weight_decay}
+        self._hyper_host = torch.zeros(5, dtype=torch.float64).pin_memory() if torch.cuda.is_available() else torch.zeros(5, dtype=torch.float64)
+        self._hyper_seen = None
+        self.guard = None            # device float scalar: the update is skipped while it is not finite
         self._views, off = [], 0
         with torch.no_grad():
             for p in ps:
@@ -70,15 +80,30 @@ class FlatAdam(torch.optim.Optimizer):
             elif p.grad.data_ptr() != g.data_ptr():
                 g.copy_(p.grad)
                 p.grad = g
-        grp = self.param_groups[0]
-        b1, b2 = grp["betas"]
-        check(lib.adc_adam_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.flat_exp_avg.data_ptr(),
-                                self.flat_exp_avg_sq.data_ptr(), self.step_t.data_ptr(), self.flat_param.numel(), float(grp["lr"]),
-                                float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]),
-                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "adc_adam_step")
+        for p, (_, off, k) in zip(self._params, self._views):   # a Parameter re-homed behind our back would be silently left behind
+            if p.data_ptr() != self.flat_param.data_ptr() + 4 * off:
+                raise RuntimeError("FlatAdam: a parameter's storage was rebound (p.data = ...) after construction; its updates would be "
+                                   "lost.  Write into parameters with .data.copy_() instead")
+        if not torch.cuda.is_current_stream_capturing():
+            self.refresh_hyper()
+        guard = self.guard
+        check(lib.adc_adam_step_dev(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.flat_exp_avg.data_ptr(),
+                                    self.flat_exp_avg_sq.data_ptr(), self._state4.data_ptr(), self._hyper.data_ptr(),
+                                    guard.data_ptr() if guard is not None else None, self.flat_param.numel(),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "adc_adam_step_dev")
         for p in self._params:                                  # the kernel wrote the storage behind torch's back: caches keyed on
             torch.autograd.graph.increment_version(p)           # the version counter (dense.cached_weights) must see the update
         return loss
+
+    def refresh_hyper(self):
+        """Copies lr / betas / eps / weight_decay of ``param_groups[0]`` to the device when they changed (a scheduler wrote them).
+        Called by ``step`` outside graph capture and by the trainer before every graph replay."""
+        grp = self.param_groups[0]
+        cur = (float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]))
+        if cur != self._hyper_seen:
+            self._hyper_host.copy_(torch.tensor(cur, dtype=torch.float64))
+            self._hyper.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_seen = cur
 
     def load_state_dict(self, state_dict):
         """Accepts a torch.optim.Adam / FlatAdam state dict (per-parameter 'step', 'exp_avg', 'exp_avg_sq'): the moments are copied

@@ -33,6 +33,7 @@ class DataParallelTrainer:
             if hasattr(criterion, sub) and hasattr(getattr(criterion, sub), "lazy"):
                 getattr(criterion, sub).lazy = True
         self._buckets, self._left, self._works = [], [], []
+        self._scale = self._scale_work = None
         if self.world > 1:
             for p in list(model.parameters()) + list(model.buffers()):   # identical replicas, once (not per step)
                 dist.broadcast(p.data, 0, group=self.group)
@@ -61,6 +62,15 @@ class DataParallelTrainer:
 
     def _reduce_bucket(self, b, async_op):
         lo, hi, _ = self._buckets[b]
+        if self._scale_work is not None:
+            # Global masked mean (trainer.py:204-208 computes ONE loss over the gathered outputs of all replicas): this rank's
+            # gradients were produced for its local mean S_r / n_r; the global one is sum_r S_r / sum_r n_r, so they are weighted by
+            # n_r * world / sum n (exactly 1.0 when every rank holds the same number of valid pixels) before the average.
+            self._scale_work.wait()
+            self._scale_work = None
+            self._scale = self._cnt * float(self.world) / self._stats[0]
+        if self._scale is not None:
+            self.flat[lo:hi].mul_(self._scale)
         return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM, group=self.group,
                                async_op=async_op)
 
@@ -78,12 +88,24 @@ class DataParallelTrainer:
             return self.criterion(inp, pred[0][:, 0:1], pred[2][:, 0:1], target_depth), pred
         return self.criterion(inp, pred[0][:, 0:1], target_depth), pred
 
+    def _valid_count(self, target):
+        """Number of valid target pixels of this rank's batch as a device scalar (the product's losses leave it in ``num_valid``)."""
+        for c in (self.criterion, getattr(self.criterion, "net_a", None)):
+            n = getattr(c, "num_valid", None)
+            if n is not None:
+                return n.detach().float().reshape(())
+        return (target[:, 0:1] > 0).sum().float()
+
     def capture(self, inp, target, warmup=3):
         """Record the whole training step (forward, loss, backward, all-reduce, optimizer) into ONE CUDA graph.
         The step has static shapes and no host synchronisation, so every later ``step`` is a single graph launch: the
         ~450 kernel launches and the Python between them (4.4 ms of a 15 ms step at batch 32) disappear.
-        Requires a capturable optimizer (optim.FlatAdam, or torch.optim.Adam(capturable=True)).  Inputs of later steps are copied into the static buffers."""
+        Requires a capturable optimizer (optim.FlatAdam, or torch.optim.Adam(capturable=True)).  Inputs of later steps are copied
+        into the static buffers; optim.FlatAdam reads lr / betas / weight_decay from a device buffer that ``step`` refreshes from
+        ``param_groups`` before every replay, so learning-rate schedulers keep working (trainer.py:236-241)."""
         self._static_in, self._static_tg = inp.clone(), target.clone()
+        if hasattr(self.optimizer, "refresh_hyper"):
+            self.optimizer.refresh_hyper()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -101,6 +123,8 @@ class DataParallelTrainer:
         if getattr(self, "_graph", None) is not None:
             self._static_in.copy_(inp, non_blocking=True)
             self._static_tg.copy_(target, non_blocking=True)
+            if hasattr(self.optimizer, "refresh_hyper"):
+                self.optimizer.refresh_hyper()     # a scheduler may have changed lr since the last replay
             self._graph.replay()
             for p in self.params:      # the replay updated the parameters behind autograd's back: caches keyed on the version
                 torch.autograd.graph.increment_version(p)     # counter (dense.cached_weights) must see it
@@ -110,9 +134,16 @@ class DataParallelTrainer:
     def _eager_step(self, inp, target):
         loss, _ = self.forward_loss(inp, target)
         self.flat.zero_()
+        out = loss.detach()
+        self._scale = self._scale_work = None
         if self.world > 1:
             self._left = [n for _, _, n in self._buckets]
             self._works = []
+            # [n_r, S_r = n_r * loss_r] summed over the ranks while backward runs: the global loss, the per-rank gradient weight
+            # and the collective "is the loss finite" verdict (a NaN on any rank reaches every rank)
+            self._cnt = self._valid_count(target)
+            self._stats = torch.stack((self._cnt, out * self._cnt))
+            self._scale_work = dist.all_reduce(self._stats, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         loss.backward()
         if self.world > 1:
             for b, left in enumerate(self._left):      # a bucket with a parameter that got no gradient this step: reduce it now
@@ -124,8 +155,11 @@ class DataParallelTrainer:
             self._works = []
             if not self._avg:
                 self.flat.div_(self.world)
+            out = self._stats[1] / self._stats[0]       # the loss of the global batch, identical on every rank
+        if hasattr(self.optimizer, "guard"):
+            self.optimizer.guard = out                  # non-finite loss (any rank): the update is skipped on the device
         self.optimizer.step()
-        return loss.detach()
+        return out
 
 
 class HostFeeder:

@@ -128,14 +128,15 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frames = args.cpu_frames or 1
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    # same workload, same batch per step, exactly --steps / --warmup steps (32 frames take ~1.5 s on 16 cores)
+    frames = args.cpu_frames or args.batch
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     fps, ms, cores, frames = cpu_reference_run(steps, warmup, frames)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": frames, "device": "host CPU"},
+        "config": {"workload": WORKLOAD, "precision": "fp32", "batch_per_gpu": frames, "global_batch": frames, "device": "host CPU"},
         "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d timed steps of %d frame(s) of the same workload with torch CPU ops (oracle/, the reference's "
                                    "algorithm restated; the Python reference cannot travel to the GPU box)" % (steps, frames)},
@@ -391,7 +392,7 @@ def b200_arm(args):
         except Exception as e:
             line["extra"]["gudepthcompnet18_dc1_cf1_ln0_240x320"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if not args.no_cpu_baseline and world == 1:
-        fps, ms, cores, fr = cpu_reference_run(3, 1, args.cpu_frames or 1)
+        fps, ms, cores, fr = cpu_reference_run(3, 1, args.cpu_frames or 4)
         line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "3 timed steps of %d frame(s) of the same workload with torch CPU ops (oracle/)" % fr}
     print(json.dumps(line), flush=True)

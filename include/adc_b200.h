@@ -41,6 +41,10 @@ const char* adc_last_error(void);
  * call index; bytes = the kernel's algorithmic HBM bytes).  adc_profile_read synchronises on the recorded events. */
 long long adc_launch_count(void);
 int adc_profile_enable(int on);
+/* adc_pyramid_bwd issues its weight-gradient kernels on a second stream beside the data-gradient chain (fork / join inside the call,
+ * CUDA-graph capturable).  0 keeps every kernel on the caller's stream (what the parity tests compare the two-stream schedule with);
+ * returns the previous setting. */
+int adc_set_side_stream(int on);
 int adc_profile_read(int max_records, int* n_out, int* kinds, int* calls, float* ms, double* bytes);
 
 /* ---- a source of input channels for one NConv2d call ------------------------------------------
@@ -333,6 +337,14 @@ int adc_depth_metrics(const float* output, const float* target, const float* con
  * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). */
 int adc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* step, long long n, double lr, double beta1,
                   double beta2, double eps, double weight_decay, adc_stream_t stream);
+
+/* Same update with the hyper-parameters resident on the device: hyper = double[5] {lr, beta1, beta2, eps, weight_decay}, state =
+ * float[4] {t, step_size, 1/sqrt(1-beta2^t), apply} (only t is an input).  A captured CUDA graph follows a learning-rate schedule
+ * (trainer.py:236-241 multiplies lr by 0.1 every 5 epochs) because the host rewrites `hyper` between replays.  guard (may be NULL):
+ * device scalar, normally the step's loss; when it is not finite the call changes nothing, t included -- the reference trainer skips
+ * such a batch on the host (trainer.py:206-208). */
+int adc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* state, const double* hyper,
+                      const float* guard, long long n, adc_stream_t stream);
 
 /* ---- sparse-depth sampling (dataloaders/dense_to_sparse.py:29-48, UniformSampling.dense_to_sparse) on the device, bit-exact with
  * the reference's numpy stream: frame n draws np.random.uniform(0, 1, HW) after np.random.seed(seeds[n]) (MT19937, 53-bit doubles)

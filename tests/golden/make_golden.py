@@ -119,6 +119,7 @@ def run_framework(out, tag, mode, dc_arch, hw, batch=2, conf_arch=None, ln_arch=
         for k_, p in model.named_parameters():
             if p.grad is not None:
                 out[tag + "_g_" + k_] = digest(p.grad)
+        GERR_TODO.append((tag, {k_: p.grad.detach().clone() for k_, p in model.named_parameters() if p.grad is not None}))
         for k_, v in model.state_dict().items():
             if "nconv" in k_ and k_.endswith("weight"):
                 out[tag + "_w_" + k_] = digest(v)
@@ -132,7 +133,27 @@ def run_framework(out, tag, mode, dc_arch, hw, batch=2, conf_arch=None, ln_arch=
     out[tag + "_metrics"] = np.array([m.rmse, m.mae, m.delta1, m.delta2, m.delta3, m.absrel, m.lg10, m.irmse, m.imae, m.mse])
 
 
+GERR_TODO = []
+
+
+def grad_noise_floor(out):
+    """Per parameter tensor: max|g32 - g64| / max|g64| of the reference's OWN fp32 gradients against the fp64 oracle (which equals
+    the reference to 1e-11 in fp64, tests/test_oracle_golden.py) -- the floor of the k-times-floor gradient rule."""
+    import golden_util
+    golden_util._cache["nets"] = {k: v for k, v in out.items()}           # the cases were just produced: read them from memory
+    golden_util._cache["nets"] = type("G", (dict,), {"files": property(lambda self: list(self.keys()))})(out)
+    for tag, grads in GERR_TODO:
+        _, S, *_ = golden_util.run_oracle_case(tag, torch.float64)
+        err = {}
+        for k_, g in grads.items():
+            g64 = S[k_].grad
+            den = float(g64.abs().max())
+            err[k_] = float((g.double() - g64).abs().max()) / (den if den > 0 else 1.0)
+        out[tag + "_gerr"] = np.array(json.dumps(err))
+
+
 def case_nets(out):
+    run_framework(out, "ged_nyu", "dc1_only", "ged_depthcompnet", (228, 304), seed=5)
     run_framework(out, "ged_only", "dc1_only", "ged_depthcompnet", (64, 80))
     run_framework(out, "ged_only_eval", "dc1_only", "ged_depthcompnet", (64, 80), train=False)
     run_framework(out, "ged_dc1", "dc1", "ged_depthcompnet", (64, 80))
@@ -154,6 +175,7 @@ def case_nets(out):
     run_framework(out, "ud_only", "dc1_only", "udepthcompnet18", (32, 48), input_type="rgbdw")
     run_framework(out, "s2d_only", "dc1_only", "resnet18", (64, 80))
     run_framework(out, "s2d_cf", "dc1-cf1-ln0", "resnet18", (64, 80), conf_arch="cbr3-c1", ln_arch="ged_depthcompnet")
+    grad_noise_floor(out)
 
 
 def case_sampling_metrics(out):

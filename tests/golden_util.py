@@ -33,7 +33,7 @@ def g_like(t, seed):
     return torch.randn(t.shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float64).to(t.dtype)
 
 
-NET_TAGS = ("ged_only", "ged_only_eval", "ged_dc1", "ged_full", "ged_ln0", "ged_dc0", "ged_dcln", "ged_odd",
+NET_TAGS = ("ged_nyu", "ged_only", "ged_only_eval", "ged_dc1", "ged_full", "ged_ln0", "ged_dc0", "ged_dcln", "ged_odd",
             "gms_only", "gms_full", "gud_only", "gud_only_eval", "gud_ln0", "ud_only", "s2d_only", "s2d_cf")
 
 
@@ -46,3 +46,37 @@ def net_case(tag, dtype=torch.float32):
     h, w = cfg["hw"]
     inp, tgt = synth.synth_frames(cfg["batch"], h, w, seed=100 + cfg["seed"], num_samples=max(60, h * w // 140), dtype=dtype)
     return cfg, state, inp, tgt
+
+
+def run_oracle_case(tag, dtype=torch.float32):
+    """The nets.npz case ``tag`` through the CPU oracle in ``dtype`` (forward, loss, backward): returns (cfg, S, inp, tgt, d1, c1, d2,
+    loss, parts) with the gradients in ``S[k].grad``.  In float64 this is the gradient reference of the k-times-floor rule
+    (SURVEY.md 8c): the oracle equals the reference to 1e-11 in fp64 (tests/test_oracle_golden.py)."""
+    from oracle import loss_metrics_oracle as lm
+    from oracle import nets_oracle as nets
+    cfg, S, inp, tgt = net_case(tag, dtype)
+    for k in S:
+        if S[k].dtype.is_floating_point and not k.endswith(("running_mean", "running_var")):
+            S[k].requires_grad_(True)
+    frozen = [p for p, f in (("dc_model.", "dc0"), ("conf_model.", "cf0"), ("loss_dc_model.", "ln0")) if f in cfg["mode"]]
+    for k in S:
+        if any(k.startswith(p) for p in frozen) and S[k].requires_grad:
+            S[k].requires_grad_(False)
+    d1, c1, d2 = nets.framework_forward(S, inp, cfg["mode"], cfg["dc_arch"], len(cfg["input_type"]), cfg["conf_arch"],
+                                        cfg["ln_arch"], cfg["train"])
+    loss = parts = None
+    if cfg["train"]:
+        if d2 is not None:
+            loss, parts = lm.dual_loss(cfg["criterion"], d1, d2, tgt, 0.5 if "dc1" in cfg["mode"] else 1.0)
+        else:
+            loss = lm.masked_loss(cfg["criterion"], d1, tgt)
+            parts = [float(loss), 0, 0]
+        loss.backward()
+    return cfg, S, inp, tgt, d1, c1, d2, loss, parts
+
+
+def ref_grad_errors(tag):
+    """{parameter name: max|g32 - g64| / max|g64|} of the REFERENCE's own fp32 gradients against the fp64 oracle, measured when the
+    fixtures were generated (tests/golden/make_golden.py): the noise floor the k-times-floor rule multiplies."""
+    G = gold("nets")
+    return json.loads(str(G[tag + "_gerr"])) if (tag + "_gerr") in G.files else {}

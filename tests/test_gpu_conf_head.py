@@ -49,7 +49,7 @@ def test_conf_head_tc_vs_fp64_reference(c, shape, training):
         yg = dev(xg)
         yg.backward(gout.cuda())
     finally:
-        dense.set_precision("fp32")
+        dense.set_precision("bf16x3")
     assert _lib.lib.adc_launch_count() - n0 >= 8, "the confidence head did not run on the library's kernels"
     assert relmax(yg.detach().cpu(), yr.detach()) < 1e-4
     assert relmax(xg.grad.cpu(), xr.grad) < 2e-3
@@ -77,6 +77,6 @@ def test_conf_head_no_input_grad_and_no_grad_mode():
         y2 = dev(x.cuda())          # input without requires_grad: only parameter gradients
         y2.sum().backward()
     finally:
-        dense.set_precision("fp32")
+        dense.set_precision("bf16x3")
     assert relmax(y.cpu(), _ref_forward(ref, x.double()).detach()) < 1e-4
     assert dev.conv1.weight.grad is not None and torch.isfinite(dev.conv1.weight.grad).all()

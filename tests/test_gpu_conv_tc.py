@@ -66,7 +66,7 @@ def test_conv3x3_tc_matches_reference(cfg):
         e3p = rel(dense.to_nchw_f32(opair, co).cpu(), full)
         assert e3p < 5e-5, e3p
     finally:
-        dense.set_precision("fp32")
+        dense.set_precision("bf16x3")
 
 
 @gpu
@@ -103,7 +103,7 @@ def test_conv3x3_v2_tap_reuse_kernel(cfg, prec):
             ref2 = _ref(mid, w2, None, 1, 0, rounded=(prec == "bf16"))
             assert rel(dense.to_nchw_f32(o2, 32).cpu(), ref2) < 5e-5
     finally:
-        dense.set_precision("fp32")
+        dense.set_precision("bf16x3")
 
 
 @gpu
@@ -129,4 +129,4 @@ def test_channel_slices_fold_concat():
         ref3 = _ref(got[:, 16:48], w3, None, 1, 0)
         assert rel(dense.to_nchw_f32(o, 16).cpu(), ref3) < 2e-5
     finally:
-        dense.set_precision("fp32")
+        dense.set_precision("bf16x3")

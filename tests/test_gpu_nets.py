@@ -1,16 +1,19 @@
 """GPU parity tests of the full nets / framework modes (drop-in modules on the B200 path) against the golden
 fixtures produced by the unmodified reference and against the CPU oracle on the same seeded weights and frames.
 
-Outputs: max|a-b|/max|b| <= 1e-4 (fp32).  Gradients: abs-sum digest within 2e-3 of the reference's
-(the reference's own fp32 noise floor is up to 1.3e-3 median / 5e-2 worst tensor for the BN nets -> 2e-2 there)."""
+Outputs: max|a-b|/max|b| <= 1e-4.  Gradients, PER TENSOR and over the whole tensor: the error against the fp64 oracle
+(max|g - g64| / max|g64|) may not exceed GRAD_K times the error the reference's own fp32 run has against the same fp64 gradients
+(stored per tensor in nets.npz by make_golden.py), with an absolute floor for tensors where the reference happens to be exact to
+1e-7.  The modules run in the default precision mode (bf16x3: hand-written tcgen05 kernels wherever the net has them)."""
 import numpy as np
 import pytest
 import torch
 
-from golden_util import NET_TAGS, digest, gold, net_case, relmax
+from golden_util import NET_TAGS, digest, gold, net_case, ref_grad_errors, relmax, run_oracle_case
 
 gpu = pytest.mark.gpu
 OUT_TOL = 1e-4
+GRAD_K, GRAD_FLOOR = 4.0, 2e-5
 
 
 def build(cfg, state):
@@ -32,29 +35,23 @@ def test_framework_vs_golden(tag):
     _framework_vs_golden(tag)
 
 
-GED_TAGS = tuple(t for t in NET_TAGS if t.startswith("ged_"))
-
-
 @gpu
-@pytest.mark.parametrize("tag", GED_TAGS)
-def test_ged_tensor_core_path_vs_golden(tag):
-    """The same goldens with conv1..conv10 of every GEDNet (forward AND backward) on the hand-written tcgen05 kernels in the
-    bf16x3 mode (hi/lo split operands, fp32 accumulation): the strict fp32 bars must still hold."""
-    from aerial_depth_completion_b200 import dense, _lib
+def test_ged_plain_bf16_mode_vs_golden():
+    """The 1e-2 mode of north_star (plain bf16 operands, one MMA per product) on the same kernels."""
+    from aerial_depth_completion_b200 import dense
     prev = dense.PRECISION
-    dense.set_precision("bf16x3")
-    n0 = _lib.lib.adc_launch_count()
+    dense.set_precision("bf16")
     try:
-        # gradient digests: 2.5x the fp32 path's bar.  The worst tensors are the NConv weights (two-element sums over all
-        # pixels with heavy cancellation: the reference's own fp32-vs-fp64 difference there is 4e-4..1.5e-3, SURVEY 8c) which
-        # amplify the ~1e-5 operand rounding of the split mode; measured worst 3.1e-3
-        _framework_vs_golden(tag, gtol_scale=2.5)
+        G = gold("nets")
+        cfg, state, inp, tgt = net_case("ged_only")
+        f, m, params = build(cfg, state)
+        d1, _, _ = m(inp.cuda())
+        assert relmax(d1.detach().cpu(), G["ged_only_d1"]) < 1e-2
     finally:
         dense.set_precision(prev)
-    assert _lib.lib.adc_launch_count() > n0
 
 
-def _framework_vs_golden(tag, gtol_scale=1.0):
+def _framework_vs_golden(tag):
     G = gold("nets")
     cfg, state, inp, tgt = net_case(tag)
     f, m, params = build(cfg, state)
@@ -91,18 +88,21 @@ def _framework_vs_golden(tag, gtol_scale=1.0):
     gl = G[tag + "_loss"]
     assert abs(float(l) - gl[0]) <= 1e-4 * abs(gl[0])
     assert abs(loss.loss[0] - gl[1]) <= 1e-4 * abs(gl[1])
-    gtol = (5e-2 if bn_net else 2e-3) * gtol_scale      # the reference's own fp32-vs-fp64 grads differ by up to 5e-2 in the BN nets
-    n = 0
+    # k-times-floor rule, per tensor, full tensors
+    _, S, *_ = run_oracle_case(tag, torch.float64)
+    floor = ref_grad_errors(tag)
+    n, bad = 0, []
     for k, p in m.named_parameters():
-        gk = tag + "_g_" + k
-        if gk in G.files:
+        if k in floor:
             assert p.grad is not None, k
-            d = digest(p.grad)
-            assert abs(d[1] - G[gk][1]) <= gtol * max(G[gk][1], 1e-30), (k, d[1], G[gk][1])
+            err = relmax(p.grad.cpu(), S[k].grad)
+            if err > max(GRAD_K * floor[k], GRAD_FLOOR):
+                bad.append((k, "%.2e" % err, "%.2e" % floor[k]))
             n += 1
         else:
             assert p.grad is None or float(p.grad.abs().sum()) == 0.0, k
     assert n > 0
+    assert not bad, bad
     sd = m.state_dict()
     for k in sd:
         wk = tag + "_w_" + k

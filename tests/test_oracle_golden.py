@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import reference_shim
-from golden_util import NET_TAGS, digest, g_like, gold, net_case, relmax
+from golden_util import NET_TAGS, digest, g_like, gold, net_case, relmax, run_oracle_case
 from oracle import loss_metrics_oracle as lm
 from oracle import nconv_oracle as no
 from oracle import nets_oracle as nets
@@ -71,28 +71,6 @@ def test_softplus_iteration_counts():
         for _ in range(n):
             w = no.softplus_pos(w)
         assert torch.equal(w, cache["final"][m])
-
-
-def run_oracle_case(tag, dtype=torch.float32):
-    cfg, S, inp, tgt = net_case(tag, dtype)
-    for k in S:
-        if S[k].dtype.is_floating_point and not k.endswith(("running_mean", "running_var")):
-            S[k].requires_grad_(True)
-    frozen = [p for p, f in (("dc_model.", "dc0"), ("conf_model.", "cf0"), ("loss_dc_model.", "ln0")) if f in cfg["mode"]]
-    for k in S:
-        if any(k.startswith(p) for p in frozen) and S[k].requires_grad:
-            S[k].requires_grad_(False)
-    d1, c1, d2 = nets.framework_forward(S, inp, cfg["mode"], cfg["dc_arch"], len(cfg["input_type"]), cfg["conf_arch"],
-                                        cfg["ln_arch"], cfg["train"])
-    loss = parts = None
-    if cfg["train"]:
-        if d2 is not None:
-            loss, parts = lm.dual_loss(cfg["criterion"], d1, d2, tgt, 0.5 if "dc1" in cfg["mode"] else 1.0)
-        else:
-            loss = lm.masked_loss(cfg["criterion"], d1, tgt)
-            parts = [float(loss), 0, 0]
-        loss.backward()
-    return cfg, S, inp, tgt, d1, c1, d2, loss, parts
 
 
 @pytest.mark.parametrize("tag", NET_TAGS)

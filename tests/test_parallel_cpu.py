@@ -40,6 +40,17 @@ def _tiny_model():
     return Tiny()
 
 
+def _data():
+    """Sparse targets with DIFFERENT numbers of valid pixels per shard (frames 0-1: ~80 %, frames 2-3: ~25 %): the mean of the
+    per-rank masked means is then not the masked mean of the whole batch, which is what the reference's DataParallel computes
+    (trainer.py:204-208)."""
+    g = torch.Generator().manual_seed(100)
+    x = torch.rand(4, 5, 16, 16, generator=g)
+    t = torch.rand(4, 1, 16, 16, generator=g) + 0.5
+    keep = torch.rand(4, 1, 16, 16, generator=g) < torch.tensor([0.8, 0.8, 0.25, 0.25]).view(4, 1, 1, 1)
+    return x, t * keep
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -50,13 +61,13 @@ def _worker(rank, world, port, out):
     opt = torch.optim.SGD(params, lr=0.1)
     tr = parallel.DataParallelTrainer(model, _MaskedMSE(), opt, params, world_size=world)
     out["buckets%d" % rank] = [(lo, hi, n) for lo, hi, n in tr._buckets]
-    g = torch.Generator().manual_seed(100)
-    x = torch.rand(4, 5, 16, 16, generator=g)
-    t = torch.rand(4, 1, 16, 16, generator=g) + 0.5
+    x, t = _data()
     shard = slice(rank * 2, rank * 2 + 2)
+    losses = []
     for _ in range(3):
-        tr.step(x[shard], t[shard])
+        losses.append(float(tr.step(x[shard], t[shard])))
     out[rank] = [p.detach().clone() for p in model.parameters()]
+    out["loss%d" % rank] = losses
     dist.destroy_process_group()
 
 
@@ -69,20 +80,24 @@ def test_two_rank_step_equals_single_process_on_concatenated_batch():
     torch.manual_seed(0)
     c = _tiny_model()
     opt = torch.optim.SGD(c.parameters(), lr=0.1)
-    g = torch.Generator().manual_seed(100)
-    x = torch.rand(4, 5, 16, 16, generator=g)
-    t = torch.rand(4, 1, 16, 16, generator=g) + 0.5
+    x, t = _data()
+    assert int((t[:2] > 0).sum()) != int((t[2:] > 0).sum())
     crit = _MaskedMSE()
+    ref_losses = []
     for _ in range(3):
         opt.zero_grad()
-        crit(x, c(x)[0], t).backward()
+        loss = crit(x, c(x)[0], t)
+        loss.backward()
         opt.step()
+        ref_losses.append(float(loss))
     ref = [p.detach() for p in c.parameters()]
     # three gradient buckets: dc_model.d_net | dc_model body (conv1, conv2) | conf_model
     assert [n for _, _, n in out["buckets0"]] == [2, 4, 2] and out["buckets0"] == out["buckets1"]
     for r in (0, 1):
         for a, b in zip(out[r], ref):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), "rank %d diverged from the single-process run" % r
+        # the returned loss is the masked mean over the GLOBAL batch, identical on both ranks
+        assert all(abs(a - b) <= 1e-5 * abs(b) for a, b in zip(out["loss%d" % r], ref_losses))
 
 
 def test_product_losses_and_metrics_refuse_host_tensors():
