@@ -50,6 +50,17 @@ class PyramidBwd(ctypes.Structure):
                 ("gx0", ctypes.c_void_p), ("gc0", ctypes.c_void_p), ("gweight", ctypes.c_void_p), ("gbias", ctypes.c_void_p)]
 
 
+class ConvDesc(ctypes.Structure):
+    """adc_conv_t"""
+    _fields_ = [("kind", c_int),
+                ("x", ctypes.c_void_p), ("x_lo", ctypes.c_void_p), ("x_stride", c_int), ("x_off", c_int), ("x_pad", c_int),
+                ("w", ctypes.c_void_p), ("w_lo", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("out", ctypes.c_void_p), ("out_lo", ctypes.c_void_p), ("out_f32", c_int), ("out_stride", c_int), ("out_off", c_int),
+                ("out_pad", c_int), ("out_zero_to", c_int), ("accumulate", c_int),
+                ("N", c_int), ("H", c_int), ("W", c_int), ("cin", c_int), ("cout", c_int), ("stride", c_int), ("act", c_int),
+                ("tap_mask", c_int)]
+
+
 ADC_WPREP_MAX = 40
 
 
@@ -96,6 +107,8 @@ SIGNATURES = {
                                         c_int, c_int, c_int, _vp]),
     "adc_conv3x3_wgrad_box_tc": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int,
                                          c_int, c_int, c_int, _vp]),
+    "adc_conv1x1_wgrad_box_tc": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int,
+                                         c_int, c_int, c_int, _vp]),
     "adc_sum_rows": (c_int, [_vp, c_int, c_int, _vp, _vp]),
     "adc_nhwc_upsample_nearest": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_nhwc_grad_assemble": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int, c_int, ctypes.c_float,
@@ -135,6 +148,18 @@ SIGNATURES = {
     "adc_masked_loss_bwd": (c_int, [_vp, _vp, _vp, _vp, c_ll, c_int, _vp, _vp]),
     "adc_depth_metrics": (c_int, [_vp, _vp, _vp, ctypes.c_float, c_ll, _vp, _vp, _vp]),
     "adc_adam_step": (c_int, [_vp, _vp, _vp, _vp, _vp, c_ll] + [ctypes.c_double] * 5 + [_vp]),
+    "adc_conv_tc": (c_int, [ctypes.POINTER(ConvDesc), _vp]),
+    "adc_bn_workspace_bytes": (ctypes.c_size_t, [c_int]),
+    "adc_bn_coef_floats": (c_int, [c_int]),
+    "adc_bn_stats": (c_int, [_vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, c_int, _vp, _vp,
+                             _vp]),
+    "adc_bn_apply": (c_int, [_vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_bn_bwd": (c_int, [_vp, c_int, c_int, _vp, c_int, c_int, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int,
+                           c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_dot_head_fwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_dot_head_bwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_im2col3x3_pack": (c_int, [_vp, c_int, c_ll, _vp, c_int, c_ll, _vp, c_int, c_ll, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_nchw_to_nhwc_f32": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_adam_step_dev": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_ll, _vp]),
     "adc_uniform_sampling": (c_int, [_vp, _vp, c_int, ctypes.c_float, c_int, _vp, c_int, c_ll, _vp]),
 }

@@ -51,6 +51,7 @@ struct ConvParams {
     signed char tdy[9], tdx[9], ttap[9];
     // output pixel of tile-space pixel (oh, ow): (oh*omul + oay, ow*omul + oax) in an image of OutH x OutW
     int omul, oay, oax, OutH, OutW;
+    int accum;              // fp32 output: out += result (a gradient buffer with several producers)
 };
 
 constexpr int kStages = 4;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                 float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c0 + j < p.cout) o[j] = v[j];
+                    if (c0 + j < p.cout) o[j] = p.accum ? o[j] + v[j] : v[j];
             } else {
                 __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
                 __nv_bfloat16* ol = p.out_lo ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * p.out_pix_stride + p.out_ch_off + c0 : nullptr;
@@ -219,6 +220,8 @@ struct ConvParamsV2 {
     int dbg;                 // timing experiments: 1 = epilogue skips its global stores, 2 = epilogue skipped entirely
     int taps1;               // 1: only the centre tap exists (a 1x1 convolution / plain GEMM over the flat pixels)
     int tap_mask;            // bit 3u+v set = tap (u,v) has non-zero weights; rows of taps that are all clear are never loaded
+    int accum;               // fp32 output: out += result (a gradient buffer with several producers)
+    int ktail;               // 16-channel K steps of the LAST 64-channel block that hold real channels (1..4): cin = 64*(kblocks-1) + 16*ktail
 };
 
 constexpr int kSegRows = 130;
@@ -361,14 +364,15 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                         const int wslot = p.taps1 ? 0 : v;
                         const uint32_t b_cat = p.resident ? base + (kb * tpk + (p.taps1 ? 0 : 3 * u + v)) * (mult * b_tile)
                                                           : sa + b_off + wslot * (mult * b_tile);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        const int kn = kb == kblocks - 1 ? p.ktail : 4;      // a 129-channel input is 2 blocks + ONE K step, not 3 blocks
+#pragma unroll 4
+                        for (int k = 0; k < kn; ++k)
                             umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_cat) + 2 * k, idesc, accumulate | (uint32_t)k);
                         accumulate = 1;
                         if (p.split) {
                             const uint32_t a_lo = a_hi + kSegBytes;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
+#pragma unroll 4
+                            for (int k = 0; k < kn; ++k)
                                 umma_bf16(tacc, make_desc_sw128_off(a_lo, 0) + 2 * k, make_desc<128>(b_cat) + 2 * k, idesc, 1);
                         }
                     }
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     float* o = reinterpret_cast<float*>(p.out) + m * p.out_pix_stride + p.out_ch_off + c0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c0 + j < lim) o[j] = v[j];
+                        if (c0 + j < lim) o[j] = p.accum ? o[j] + v[j] : v[j];
                     continue;
                 }
                 uint4 h[2], l[2];
@@ -793,6 +797,7 @@ struct V1Launch {
     int Ho, Wo;                  // tile-space output extent
     int ntaps; signed char tdy[9], tdx[9], ttap[9];
     int omul, oay, oax, OutH, OutW;
+    int accum;
 };
 
 static int conv_v1(const V1Launch& d, const char* who, cudaStream_t st) {
@@ -825,6 +830,7 @@ static int conv_v1(const V1Launch& d, const char* who, cudaStream_t st) {
     p.ntaps = d.ntaps;
     memcpy(p.tdy, d.tdy, 9); memcpy(p.tdx, d.tdx, 9); memcpy(p.ttap, d.ttap, 9);
     p.omul = d.omul; p.oay = d.oay; p.oax = d.oax; p.OutH = d.OutH; p.OutW = d.OutW;
+    p.accum = (d.accum && d.out_f32) ? 1 : 0;
     const int Wt = d.W + 2 * p.x_pad, Ht = d.H + 2 * p.x_pad;    // stored extent of the input
 
     CUtensorMap mx, mw, mxl, mwl;
@@ -903,9 +909,9 @@ int adc_conv3x3_fprop_tc(const void* x, const void* x_lo, int x_stride, int x_of
 // and u=2 (i = (p-1)/2); likewise for columns.  w: adc_conv3x3_prep_weights(..., flip_transpose=2) = [tap][Cin_fwd][Cout_fwd]
 // (transposed, taps NOT flipped).  gy: [N][Ho][Wo] (+border if gy_pad), channels [gy_off, gy_off+cgy) with cgy % 16 == 0;
 // gx: channels [gx_off, gx_off+cgx) of [N][H][W] (+border if gx_pad), bf16 (pair in split mode) or fp32.
-int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* w, const void* w_lo, void* gx,
-                            void* gx_lo, int gx_f32, int gx_stride, int gx_off, int N, int H, int W, int cgy, int cgx, int gy_pad,
-                            int gx_pad, adc_stream_t stream) {
+static int dgrad_s2_impl(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* w, const void* w_lo, void* gx,
+                         void* gx_lo, int gx_f32, int gx_stride, int gx_off, int N, int H, int W, int cgy, int cgx, int gy_pad,
+                         int gx_pad, adc_stream_t stream, int accum, int only_center) {
     if (!gy || !w || !gx || N <= 0 || H <= 0 || W <= 0 || cgy <= 0 || cgx <= 0) {
         adc::set_error("adc_conv3x3_dgrad_s2_tc: bad argument");
         return ADC_E_BADARG;
@@ -915,10 +921,11 @@ int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, in
         return ADC_E_BADARG;
     }
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    for (int pa = 0; pa < 2; ++pa)
-        for (int pb = 0; pb < 2; ++pb) {
+    for (int pa = 0; pa < (only_center ? 1 : 2); ++pa)       // a 1x1 / stride-2 layer reaches the even pixels only
+        for (int pb = 0; pb < (only_center ? 1 : 2); ++pb) {
             V1Launch d;
             memset(&d, 0, sizeof(d));
+            d.accum = accum;
             d.x = gy; d.x_lo = gy_lo; d.x_stride = gy_stride; d.x_off = gy_off; d.w = w; d.w_lo = w_lo; d.bias = nullptr;
             d.out = gx; d.out_lo = gx_lo; d.out_f32 = gx_f32; d.out_stride = gx_stride; d.out_off = gx_off;
             d.N = N; d.H = Ho; d.W = Wo; d.cin = cgy; d.cout = cgx; d.stride = 1; d.act = 0; d.x_pad = gy_pad; d.out_pad = gx_pad;
@@ -941,12 +948,19 @@ int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, in
     return 0;
 }
 
+int adc_conv3x3_dgrad_s2_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, const void* w, const void* w_lo, void* gx,
+                            void* gx_lo, int gx_f32, int gx_stride, int gx_off, int N, int H, int W, int cgy, int cgx, int gy_pad,
+                            int gx_pad, adc_stream_t stream) {
+    return dgrad_s2_impl(gy, gy_lo, gy_stride, gy_off, w, w_lo, gx, gx_lo, gx_f32, gx_stride, gx_off, N, H, W, cgy, cgx, gy_pad, gx_pad, stream,
+                         0, 0);
+}
+
 
 // Stride-1 3x3 convolution, v2 kernel (shared-memory tap reuse, persistent, double-buffered TMEM).  x and out are
 // zero-bordered NHWC tensors ([N][H+2][W+2][channels]); needs cin % 64 == 0.  Same split-mode convention as above.
 static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, const void* w, const void* w_lo, const float* bias, void* out,
                    void* out_lo, int out_f32, int out_stride, int out_off, int out_zero_to, int N, int H, int W, int cin, int cout, int act,
-                   int taps1, int tap_mask, adc_stream_t stream) {
+                   int taps1, int tap_mask, adc_stream_t stream, int accum = 0) {
     if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) {
         adc::set_error("adc_conv3x3_s1_tc_v2: bad argument");
         return ADC_E_BADARG;
@@ -955,8 +969,8 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
         adc::set_error("adc_conv3x3_s1_tc_v2: x_lo and w_lo must be given together (split mode)");
         return ADC_E_BADARG;
     }
-    if (cin % 64 != 0 || x_stride % 8 != 0 || x_off % 8 != 0 || cout > 128) {
-        adc::set_error("adc_conv3x3_s1_tc_v2: needs cin %% 64 == 0, 16-byte aligned channel slices and cout <= 128 (cin=%d cout=%d)", cin, cout);
+    if (cin % 16 != 0 || x_stride % 8 != 0 || x_off % 8 != 0 || cout > 128) {
+        adc::set_error("adc_conv3x3_s1_tc_v2: needs cin %% 16 == 0, 16-byte aligned channel slices and cout <= 128 (cin=%d cout=%d)", cin, cout);
         return ADC_E_UNSUPP;
     }
     EncodeTiledFn enc = get_encode();
@@ -975,6 +989,8 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     p.ntiles = (int)((p.F + 127) / 128);
     p.out_zero_to = out_zero_to;
     p.taps1 = taps1;
+    p.accum = (accum && out_f32) ? 1 : 0;
+    p.ktail = cin % 64 ? (cin % 64) / 16 : 4;
     p.tap_mask = (tap_mask & 0x1FF) ? (tap_mask & 0x1FF) : 0x1FF;
     { const char* e = getenv("ADC_V2_DBG"); p.dbg = e ? atoi(e) : 0; }
     CUtensorMap mx, mw, mxl, mwl;
@@ -1094,6 +1110,55 @@ int adc_conv1x1_tc_v2(const void* x, const void* x_lo, int x_stride, int x_off, 
                       adc_stream_t stream) {
     return conv_v2(x, x_lo, x_stride, x_off, w, w_lo, bias, out, out_lo, out_f32, out_stride, out_off, out_zero_to, N, H, W, cin, cout, act, 1,
                    0, stream);
+}
+
+// Descriptor form of the convolution entry points above (one struct instead of 20 positional arguments) with the two options the BN
+// nets need: `accumulate` (fp32 output += result: a gradient buffer that several layers feed) and input-channel counts that are a
+// multiple of 16 but not of 64 (the row-segment kernel then issues only the K steps of the last 64-channel block that hold channels).
+// kind 0: 3x3 stride 1 on the row-segment kernel (zero-bordered tensors); 1: 1x1 on the same kernel; 2: 3x3 of any stride on the box
+// kernel; 3: 1x1 of stride 2 on the box kernel (ResNet down-sampling shortcut: the centre tap of prepared [9][Cout16][Cin] weights);
+// 4: data gradient of a 3x3 / stride-2 / pad-1 convolution = ConvTranspose2d(3, stride 2, padding 1, output_padding 1) forward
+// (H, W = the LARGER tensor; w prepared with mode 2); 5: data gradient of a 1x1 / stride-2 convolution (even pixels of the larger tensor
+// only: accumulate into a buffer another layer has written, or into zeros).
+int adc_conv_tc(const adc_conv_t* d, adc_stream_t stream) {
+    if (!d) {
+        adc::set_error("adc_conv_tc: null descriptor");
+        return ADC_E_BADARG;
+    }
+    if (d->kind == 0 || d->kind == 1)
+        return conv_v2(d->x, d->x_lo, d->x_stride, d->x_off, d->w, d->w_lo, d->bias, d->out, d->out_lo, d->out_f32, d->out_stride, d->out_off,
+                       d->out_zero_to, d->N, d->H, d->W, d->cin, d->cout, d->act, d->kind == 1, d->tap_mask, stream, d->accumulate);
+    if (!d->x || !d->w || !d->out || d->N <= 0 || d->H <= 0 || d->W <= 0 || d->cin <= 0 || d->cout <= 0 || (d->x_lo == nullptr) != (d->w_lo == nullptr)) {
+        adc::set_error("adc_conv_tc: bad argument");
+        return ADC_E_BADARG;
+    }
+    if (d->kind == 2 || d->kind == 3) {
+        if (d->stride != 1 && d->stride != 2) {
+            adc::set_error("adc_conv_tc: stride must be 1 or 2");
+            return ADC_E_BADARG;
+        }
+        V1Launch v;
+        memset(&v, 0, sizeof(v));
+        v.x = d->x; v.x_lo = d->x_lo; v.x_stride = d->x_stride; v.x_off = d->x_off; v.w = d->w; v.w_lo = d->w_lo; v.bias = d->bias;
+        v.out = d->out; v.out_lo = d->out_lo; v.out_f32 = d->out_f32; v.out_stride = d->out_stride; v.out_off = d->out_off;
+        v.N = d->N; v.H = d->H; v.W = d->W; v.cin = d->cin; v.cout = d->cout; v.stride = d->stride; v.act = d->act;
+        v.x_pad = d->x_pad; v.out_pad = d->out_pad; v.accum = d->accumulate;
+        v.Ho = (d->H - 1) / d->stride + 1; v.Wo = (d->W - 1) / d->stride + 1;
+        if (d->kind == 2) {
+            v.ntaps = 9;
+            for (int t = 0; t < 9; ++t) { v.tdy[t] = (signed char)(t / 3 - 1); v.tdx[t] = (signed char)(t % 3 - 1); v.ttap[t] = (signed char)t; }
+        } else {
+            v.ntaps = 1;
+            v.tdy[0] = 0; v.tdx[0] = 0; v.ttap[0] = 4;
+        }
+        v.omul = 1; v.oay = 0; v.oax = 0; v.OutH = v.Ho; v.OutW = v.Wo;
+        return conv_v1(v, "adc_conv_tc", (cudaStream_t)stream);
+    }
+    if (d->kind == 4 || d->kind == 5)
+        return dgrad_s2_impl(d->x, d->x_lo, d->x_stride, d->x_off, d->w, d->w_lo, d->out, d->out_lo, d->out_f32, d->out_stride, d->out_off, d->N,
+                             d->H, d->W, d->cin, d->cout, d->x_pad, d->out_pad, stream, d->accumulate, d->kind == 5);
+    adc::set_error("adc_conv_tc: unknown kind %d", d->kind);
+    return ADC_E_BADARG;
 }
 
 }  // extern "C"

@@ -158,6 +158,7 @@ struct WgradBoxParams {
     int stride, gy_pad, x_pad;
     int ncols, mrows, mb, nb, kp, ktiles, groups, nstages, split;
     float* part;
+    int single;           // 1: the centre tap only (weight gradient of a 1x1 convolution of the same stride, no padding)
 };
 
 __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_constant__ CUtensorMap map_g,
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);    // full[8], empty[8], done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tap = blockIdx.x % 9, g = blockIdx.x / 9;
+    const int tap = p.single ? 4 : blockIdx.x % 9, g = p.single ? blockIdx.x : blockIdx.x / 9;
     const int u = tap / 3, v = tap % 3;
     const int my_tiles = g < p.ktiles ? (p.ktiles - g + p.groups - 1) / p.groups : 0;
     uint32_t ncols_alloc = 32;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
             mbar_wait(&bars[16], 0);
             tc_fence_after();
         }
-        float* dst = p.part + (((long long)g * 9 + tap) * p.mrows + row) * p.ncols;
+        float* dst = p.part + (p.single ? (long long)g * p.mrows + row : ((long long)g * 9 + tap) * p.mrows + row) * p.ncols;
         for (int c0 = 0; c0 < p.ncols; c0 += 16) {
             float r[16];
             if (my_tiles > 0) {
@@ -418,9 +419,9 @@ int adc_conv1x1_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int g
 
 // Strided / general-geometry variant (see conv3x3_wgrad_box_tc_kernel): gy [N][Ho][Wo] (+border if gy_pad), x [N][H][W]
 // (+border if x_pad), Ho = (H-1)/stride + 1.  Same channel-slice, split-mode, workspace and determinism rules as above.
-int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, int gy_pad, const void* x, const void* x_lo,
-                             int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
-                             int cin_pad, int cout, adc_stream_t stream) {
+static int wgrad_box(const void* gy, const void* gy_lo, int gy_stride, int gy_off, int gy_pad, const void* x, const void* x_lo,
+                     int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
+                     int cin_pad, int cout, int single, adc_stream_t stream) {
     if (!gy || !x || !dw || !workspace || N <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || cin_pad < cin || (stride != 1 && stride != 2)) {
         adc::set_error("adc_conv3x3_wgrad_box_tc: bad argument");
         return ADC_E_BADARG;
@@ -449,7 +450,8 @@ int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, i
     p.mb = cout > 64 ? 2 : 1;
     p.nb = (cin_pad + 63) / 64;
     p.split = gy_lo != nullptr;
-    p.groups = wgrad_box_groups();
+    p.single = single ? 1 : 0;
+    p.groups = single ? sm_count() : wgrad_box_groups();
     p.part = reinterpret_cast<float*>(workspace);
     const int budget = kSmemCap - 1024;
     for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
@@ -501,11 +503,27 @@ int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, i
     cudaStream_t st = (cudaStream_t)stream;
     adc::Prof prof(st, adc::KIND_TC_WGRAD_BOX, 2.0 * N * Ho * Wo * 9.0 * cin_pad * cout);
     adc::count_launches(1);
-    conv3x3_wgrad_box_tc_kernel<<<9 * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
+    conv3x3_wgrad_box_tc_kernel<<<(single ? 1 : 9) * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
     if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_box_tc_kernel launch"))) return rc;
-    const int total = 9 * cout * cin;
-    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin, 9);
+    const int total = (single ? 1 : 9) * cout * cin;
+    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin, single ? 1 : 9);
     return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");
+}
+
+int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, int gy_pad, const void* x, const void* x_lo,
+                             int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
+                             int cin_pad, int cout, adc_stream_t stream) {
+    return wgrad_box(gy, gy_lo, gy_stride, gy_off, gy_pad, x, x_lo, x_stride, x_off, x_pad, dw, workspace, N, H, W, stride, cin, cin_pad, cout, 0,
+                     stream);
+}
+
+// Weight gradient dw fp32 [cout][cin] of a 1x1 convolution of stride 1 or 2 (no padding) from NHWC activations of different geometry
+// (the ResNet down-sampling shortcut, s2d_u_resnet.py:99-107): the centre tap of the box kernel, every SM on a share of the pixels.
+int adc_conv1x1_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, int gy_pad, const void* x, const void* x_lo,
+                             int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
+                             int cin_pad, int cout, adc_stream_t stream) {
+    return wgrad_box(gy, gy_lo, gy_stride, gy_off, gy_pad, x, x_lo, x_stride, x_off, x_pad, dw, workspace, N, H, W, stride, cin, cin_pad, cout, 1,
+                     stream);
 }
 
 }  // extern "C"

@@ -16,5 +16,5 @@ struct Prof {
 // record kinds of the tensor-core translation units (0..10 are the NConv kernels, adc_nconv.cu); `work` = FLOPs for the
 // MMA kernels, bytes for the glue
 enum { KIND_TC_FPROP_V1 = 20, KIND_TC_FPROP_V2 = 21, KIND_TC_DGRAD_S2 = 22, KIND_TC_WGRAD = 23, KIND_TC_WGRAD_BOX = 24, KIND_TC_GLUE = 25,
-       KIND_TC_LAYOUT = 26, KIND_TC_PREP = 27, KIND_HEAD10 = 28, KIND_TRAIN = 29, KIND_CONF_HEAD = 30 };
+       KIND_TC_LAYOUT = 26, KIND_TC_PREP = 27, KIND_HEAD10 = 28, KIND_TRAIN = 29, KIND_CONF_HEAD = 30, KIND_BN = 31 };
 }  // namespace adc

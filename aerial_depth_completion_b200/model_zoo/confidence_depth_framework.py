@@ -224,10 +224,15 @@ class CBR3C1Confidence(nn.Module):
             init_weights(m)
 
     def forward(self, x):
-        if dense.tc_enabled() and x.is_cuda and self.conv1.in_channels <= 80:
-            # conv1 + its gradients on the tcgen05 kernels, BN + LeakyReLU + conv2 + sigmoid fused (csrc/conf_head.cu)
-            from .. import tc_train
-            return tc_train.conf_head(self, x)
+        if dense.tc_enabled():
+            dense._need_cuda(x)
+            if self.conv1.in_channels <= 80:
+                # conv1 + its gradients on the tcgen05 kernels, BN + LeakyReLU + conv2 + sigmoid fused (csrc/conf_head.cu)
+                from .. import tc_train
+                return tc_train.conf_head(self, x)
+            # wider features (129 channels behind gudepthcompnet18): output-channel chunks + K tail, general BN passes (tc_bn.py)
+            from .. import tc_bn
+            return tc_bn.conf_head(self, x)
         return torch.sigmoid(self.conv2(self.relu1(self.bn1(self.conv1(x)))))
 
 

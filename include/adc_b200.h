@@ -217,6 +217,11 @@ int adc_conv1x1_wgrad_tc(const void* gy, const void* gy_lo, int gy_stride, int g
 int adc_conv3x3_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, int gy_pad, const void* x, const void* x_lo,
                              int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
                              int cin_pad, int cout, adc_stream_t stream);
+/* dw fp32 [cout][cin] of a 1x1 convolution of stride 1 or 2 (no padding): the centre tap of the kernel above, every SM on a share of
+ * the pixels (ResNet down-sampling shortcut).  Same tensors, workspace and determinism rules. */
+int adc_conv1x1_wgrad_box_tc(const void* gy, const void* gy_lo, int gy_stride, int gy_off, int gy_pad, const void* x, const void* x_lo,
+                             int x_stride, int x_off, int x_pad, float* dw, void* workspace, int N, int H, int W, int stride, int cin,
+                             int cin_pad, int cout, adc_stream_t stream);
 
 /* ---- NHWC glue of the tensor-core training path (zero-bordered NHWC bf16 tensors, optional low halves) --------------------
  * Channel slices [off, off+C) with C % 8 == 0 and 16-byte alignment.
@@ -329,6 +334,55 @@ int adc_masked_loss_bwd(const float* pred, const float* target, const float* glo
                         adc_stream_t stream);
 int adc_depth_metrics(const float* output, const float* target, const float* confidence, float threshold, long long n, void* workspace,
                       float* out, adc_stream_t stream);
+
+/* ---- descriptor form of the tensor-core convolutions (csrc/conv_tc.cu), used by the BN nets (model_zoo/s2d_u_resnet.py:64-190)
+ * kind 0: 3x3 / stride 1 (row-segment kernel, zero-bordered tensors, cin % 16 == 0, cout <= 128; 64 in split mode);
+ * kind 1: 1x1 on the same kernel; kind 2: 3x3 of stride 1 or 2 (box kernel, tensors with or without border, cout <= 256);
+ * kind 3: 1x1 / stride 2 (the ResNet shortcut, s2d_u_resnet.py:99-107); kind 4: ConvTranspose2d(3, stride 2, padding 1,
+ * output_padding 1) forward = data gradient of a stride-2 convolution (H, W = the larger tensor, w prepared with mode 2);
+ * kind 5: data gradient of a 1x1 / stride-2 convolution (touches the even pixels of the larger tensor only).
+ * accumulate: fp32 output += result.  Split (bf16x3) mode when x_lo and w_lo are set. */
+typedef struct {
+    int kind;
+    const void *x, *x_lo; int x_stride, x_off, x_pad;
+    const void *w, *w_lo; const float* bias;
+    void *out, *out_lo; int out_f32, out_stride, out_off, out_pad, out_zero_to, accumulate;
+    int N, H, W, cin, cout, stride, act, tap_mask;
+} adc_conv_t;
+int adc_conv_tc(const adc_conv_t* d, adc_stream_t stream);
+
+/* ---- BatchNorm2d (+ residual) + ReLU / LeakyReLU(0.2) behind a convolution, forward and backward (csrc/bn_act.cu), replacing
+ * nn.BatchNorm2d + activation modules of model_zoo/s2d_u_resnet.py:26-61, torchvision BasicBlock (:99-107) and the bias + ReLU layers of
+ * GMSNet (confidence_depth_framework.py:536-607; gamma == NULL = identity affine).  y: raw convolution output, fp32 zero-bordered NHWC;
+ * activations / gradient operands: zero-bordered NHWC bf16 (hi, lo) pairs (lo may be NULL); raw gradients: fp32 zero-bordered NHWC.
+ * Every tensor is a channel slice [off, off + C) of `stride` channels per pixel.  coef: adc_bn_coef_floats(C) floats written by
+ * adc_bn_stats, read by the others (adc_bn_bwd adds its two means); workspace: adc_bn_workspace_bytes(C).  act: 0 none, 1 ReLU,
+ * 2 LeakyReLU(0.2).  adc_bn_bwd: g = gradient of the activation output -> dy (operand of the gradient GEMMs), ggamma / gbeta (may be
+ * NULL), and gres (may be NULL) = gradient of the residual input, written or accumulated. */
+size_t adc_bn_workspace_bytes(int C);
+int adc_bn_coef_floats(int C);
+int adc_bn_stats(const float* y, int y_stride, int y_off, int N, int C, int H, int W, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, float momentum, float eps, int training, float* coef, void* workspace,
+                 adc_stream_t stream);
+int adc_bn_apply(const float* y, int y_stride, int y_off, const float* coef, const void* res_hi, const void* res_lo, int res_stride, int res_off,
+                 int act, void* out_hi, void* out_lo, int out_stride, int out_off, int N, int C, int H, int W, adc_stream_t stream);
+int adc_bn_bwd(const float* g, int g_stride, int g_off, const float* y, int y_stride, int y_off, const void* out_hi, int out_stride, int out_off,
+               float* coef, int act, int training, void* dy_hi, void* dy_lo, int dy_stride, int dy_off, float* gres, int gres_stride,
+               int gres_off, int gres_accum, float* ggamma, float* gbeta, void* workspace, int N, int C, int H, int W, adc_stream_t stream);
+/* 1x1 convolution to ONE channel over a (hi, lo) NHWC slice and its backward (s2d_u_resnet.py:128 convtf): y fp32 [N][H][W] planar;
+ * gx: fp32 zero-bordered NHWC gradient slice (written or accumulated), gw [C], gb [1]; workspace: adc_bn_workspace_bytes(C). */
+int adc_dot_head_fwd(const void* x_hi, const void* x_lo, int x_stride, int x_off, const float* w, const float* bias, float* y, int relu, int N,
+                     int C, int H, int W, adc_stream_t stream);
+int adc_dot_head_bwd(const void* x_hi, const void* x_lo, int x_stride, int x_off, const float* w, const float* gy, float* gx, int gx_stride,
+                     int gx_off, int gx_accum, float* gw, float* gb, void* workspace, int N, int C, int H, int W, adc_stream_t stream);
+/* im2col of a 3x3 / pad-1 window (stride 1 or 2) over the C = c0 + c1 + c2 <= 7 fp32 planes of up to three NCHW sources (s1, s2 may be
+ * NULL; bs = batch stride in floats) at the output resolution: channel (3u+v)*C + c of a 64-channel (hi, lo) zero-bordered NHWC pixel.
+ * The thin stems of s2d_u_resnet.py:91-97 (3 -> 48, 2 -> 16) become one GEMM launch. */
+int adc_im2col3x3_pack(const float* s0, int c0, long long bs0, const float* s1, int c1, long long bs1, const float* s2, int c2, long long bs2,
+                       void* dst, void* dst_lo, int dst_stride, int N, int H, int W, int stride, adc_stream_t stream);
+/* fp32 NCHW planes -> channels [dst_off, dst_off + C) of a fp32 zero-bordered NHWC tensor (written or accumulated). */
+int adc_nchw_to_nhwc_f32(const float* src, float* dst, int dst_stride, int dst_off, int accumulate, int N, int C, int H, int W,
+                         adc_stream_t stream);
 
 /* ---- optimizer step of the trainer (trainer.py:134-146, torch.optim.Adam over the trainable parameters) on flat buffers: every
  * parameter / gradient / moment is a view into one fp32 vector of n elements (16-byte aligned).  `step` is a device scalar holding the

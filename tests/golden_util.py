@@ -80,3 +80,28 @@ def ref_grad_errors(tag):
     fixtures were generated (tests/golden/make_golden.py): the noise floor the k-times-floor rule multiplies."""
     G = gold("nets")
     return json.loads(str(G[tag + "_gerr"])) if (tag + "_gerr") in G.files else {}
+
+
+# Gradient parity rule (SURVEY.md 8c), per parameter tensor over the WHOLE tensor:  max|g - g64| / max|g64|  <=  max(GRAD_K * floor_t,
+# GRAD_ABS[mode]) where floor_t is the reference's own fp32-vs-fp64 error for that tensor (ref_grad_errors) and GRAD_ABS is the
+# absolute term of the arithmetic mode:
+#   fp32    2e-5  kernels that compute in fp32 (NConv pyramid, losses; dense layers on the fp32 library path): the strict rule.
+#   bf16x3  5e-3  hi/lo split bf16 operands carry 16-17 mantissa bits, so the FORWARD activations are exact to ~2e-5 (bar 1e-4) instead
+#                 of fp32's ~1e-7.  ReLU / LeakyReLU masks of near-zero activations then flip ~100x more often than in an fp32 run, and
+#                 every flip changes one element of a gradient by O(1): measured per-tensor errors 5e-6 (conv9/conv10) .. 2.6e-3 (conv6
+#                 at 15x19 pixels, NConv weights), profiles/r2_grad_noise_*.txt -- between the fp32 bar and north_star's 1e-2 bf16 bar.
+#   bf16    2e-1  plain bf16 operands (the 1e-2 output mode).
+GRAD_K = 4.0
+#   bn_tiny 3e-1  BatchNorm nets at the tiny fixture sizes (32x48 frames: the bottleneck normalises over 2 x 2 x 3 = 12 values), where any
+#                 rounding difference in a convolution is amplified by 1/sigma of a near-degenerate batch.
+GRAD_ABS = {"fp32": 2e-5, "bf16x3": 5e-3, "bf16": 2e-1, "bn_tiny": 3e-1}
+
+
+def grad_rule_violations(named_grads, oracle_state, floor, mode):
+    """[(name, err, floor)] of the tensors that break the rule above; ``named_grads``: iterable of (name, gradient tensor)."""
+    bad = []
+    for k, g in named_grads:
+        err = relmax(g.detach().cpu(), oracle_state[k].grad)
+        if not err <= max(GRAD_K * floor.get(k, 0.0), GRAD_ABS[mode]):
+            bad.append((k, "%.2e" % err, "%.2e" % floor.get(k, 0.0)))
+    return bad

