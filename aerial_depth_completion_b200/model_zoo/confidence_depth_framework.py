@@ -459,6 +459,17 @@ class GMSNet(nn.Module):
         assert x0.shape[1] > 3, "The input is not RGB-D or rgb-dc"
         if dense.tc_inference_enabled():
             return self._forward_tc(x0, build_conf_input)
+        if dense.tc_enabled():
+            # training: the three stacks + last_layer forward and backward on the tcgen05 kernels, one autograd node (tc_gms.py)
+            from .. import tc_gms
+            x0_d, c0 = _c0_of(x0)
+            xout_d, cout_d = self.d_net(x0_d, c0)
+            want = bool(build_conf_input) and self.out_channels == 1
+            xout, lli, d16 = tc_gms.gms_dense(self, xout_d, cout_d, x0[:, :3, :, :], want)
+            features = None
+            if build_conf_input:
+                features = torch.cat((lli, d16, cout_d, xout), 1) if want else torch.sigmoid(xout[:, 1:2, :, :])
+            return xout[:, 0:1, :, :], features
         x0_rgb = x0[:, :3, :, :]
         x0_d, c0 = _c0_of(x0)
         xout_d, cout_d = self.d_net(x0_d, c0)

@@ -500,16 +500,17 @@ def full_framework_training(dev, B=8, HH=480, WW=752, steps=8):
         dense.set_precision(prev)
 
 
-def gudepthcompnet_training(dev, B=16, HH=240, WW=320, steps=5):
+def gudepthcompnet_training(dev, B=16, HH=240, WW=320, steps=5, graph=True):
     """BASELINE.json configs[2]: gudepthcompnet18 + cbr3-c1 confidence head + frozen ged_depthcompnet loss net, training mode
-    dc1-cf1-ln0, DualLoss(l2, 0.5), batch 16 per GPU at 240x320 (the net needs H, W = 0 mod 16: SURVEY.md 0.4).  The NConv pyramids,
-    the loss net, the losses and the optimizer run on this library's kernels; the ResNet-18 body and the 129-channel head are still
-    on the library (cuDNN fp32) backend -- DESIGN.md 8 (1) -- so this line is a status report, not a headline."""
+    dc1-cf1-ln0, DualLoss(l2, 0.5), batch 16 per GPU at 240x320 (the net needs H, W = 0 mod 16: SURVEY.md 0.4).  Every layer of the three
+    nets runs on this library's kernels in the bf16x3 mode: the ResNet-18 U-Net body (tc_bn.S2DUBodyTC: tcgen05 convolutions and
+    transposed convolutions, BatchNorm / residual / activation passes), the 129-channel head (tc_bn.ConfHeadBN), the NConv pyramids, the
+    loss net (tc_train.GEDDenseTC), the losses and the optimizer; one CUDA graph per step."""
     import contextlib
     import io
     import torch
     import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
-    from aerial_depth_completion_b200 import dense, parallel
+    from aerial_depth_completion_b200 import dense, parallel, _lib
     from aerial_depth_completion_b200.optim import FlatAdam
     torch.manual_seed(0)
     f = mc.ConfidenceDepthFrameworkFactory()
@@ -523,26 +524,38 @@ def gudepthcompnet_training(dev, B=16, HH=240, WW=320, steps=5):
         crit, _ = f.create_loss("l2", True, 0.5)
         tr = parallel.DataParallelTrainer(m, crit, FlatAdam(params, lr=1e-5), params, world_size=1)
         g = torch.Generator(device=dev).manual_seed(13)
-        x = torch.rand(B, 5, HH, WW, device=dev, generator=g)
-        gt = torch.rand(B, 1, HH, WW, device=dev, generator=g) * 9.0 + 1.0
-        mask = (torch.rand(B, 1, HH, WW, device=dev, generator=g) < 500.0 / (HH * WW)).float()
-        x[:, 3:4] = gt * mask
-        x[:, 4:5] = mask
+        xs, ts = [], []
         for _ in range(2):
-            tr.step(x, gt)
+            x = torch.rand(B, 5, HH, WW, device=dev, generator=g)
+            gt = torch.rand(B, 1, HH, WW, device=dev, generator=g) * 9.0 + 1.0
+            mask = (torch.rand(B, 1, HH, WW, device=dev, generator=g) < 500.0 / (HH * WW)).float()
+            x[:, 3:4] = gt * mask
+            x[:, 4:5] = mask
+            xs.append(x)
+            ts.append(gt)
+        l0 = _lib.lib.adc_launch_count()
+        tr._eager_step(xs[0], ts[0])
+        launches = _lib.lib.adc_launch_count() - l0
+        if graph:
+            tr.capture(xs[0], ts[0], warmup=1)
+        for i in range(2):
+            tr.step(xs[i % 2], ts[i % 2])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            loss = tr.step(x, gt)
+        for i in range(steps):
+            loss = tr.step(xs[i % 2], ts[i % 2])
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
+        flop = 3.0 * (105.0e9 + 23.0e9) * B + 2.0 * 2.95e9 * B       # trained body + head (fwd, dgrad, wgrad) + frozen loss net (fwd, dgrad)
         return {"workload": "gudepthcompnet18 + cbr3-c1 + frozen ged_depthcompnet loss net, dc1-cf1-ln0, DualLoss(l2, 0.5), rgbd %dx%d" % (HH, WW),
-                "batch": B, "ms_per_step": round(ms, 2), "frames_s": round(B / ms * 1e3, 1),
-                "trainable_parameters": int(sum(p.numel() for p in params)), "loss": round(float(loss), 5),
-                "dense_path": "ResNet-18 body and 129-channel head: library (cuDNN fp32); pyramids, loss net, losses, optimizer: libadc_b200",
-                "launch": "eager"}
+                "batch": B, "ms_per_step": round(ms, 2), "frames_s": round(B / ms * 1e3, 1), "library_launches_per_step": int(launches),
+                "algorithmic_tflops": round(flop / ms / 1e9, 1),
+                "trainable_parameters": int(sum(p.numel() for p in params)), "loss": round(float(loss), 5), "precision": "bf16x3",
+                "dense_path": "every convolution / transposed convolution / BatchNorm / activation of the ResNet-18 U-Net and the 129-channel "
+                              "head: libadc_b200 (tcgen05 implicit GEMM + fused BN passes); no cuDNN kernel in the step",
+                "launch": "one CUDA graph per step" if graph else "eager"}
     finally:
         dense.set_precision(prev)
 

