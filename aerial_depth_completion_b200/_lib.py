@@ -156,8 +156,9 @@ SIGNATURES = {
     "adc_bn_apply": (c_int, [_vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_bn_bwd": (c_int, [_vp, c_int, c_int, _vp, c_int, c_int, _vp, c_int, c_int, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int,
                            c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
-    "adc_dot_head_fwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
-    "adc_dot_head_bwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_dot_head_fwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, _vp]),
+    "adc_dot_head_bwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, _vp, _vp, _vp, c_int, c_int, c_int, c_int, _vp,
+                                 c_int, _vp]),
     "adc_im2col3x3_pack": (c_int, [_vp, c_int, c_ll, _vp, c_int, c_ll, _vp, c_int, c_ll, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_nchw_to_nhwc_f32": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_adam_step_dev": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_ll, _vp]),

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const float* __restrict_
 // y[n][0][h][w] = bias + sum_c w[c] * x[c] over a (hi, lo) NHWC slice: the 1x1 head of the BN nets (s2d_u_resnet.py:128 convtf, 128 -> 1)
 __global__ void __launch_bounds__(256) dot_head_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl, int xstride,
                                                        const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
-                                                       int relu, int N, int C, int H, int W) {
+                                                       int relu, int N, int C, int H, int W, __nv_bfloat16* __restrict__ yh,
+                                                       __nv_bfloat16* __restrict__ yl, int ystride) {
     extern __shared__ float sw[];
     const int C8 = (C + 7) / 8;
     for (int c = threadIdx.x; c < C8 * 8; c += blockDim.x) sw[c] = c < C ? w[c] : 0.f;
@@ -335,6 +336,11 @@ __global__ void __launch_bounds__(256) dot_head_kernel(const __nv_bfloat16* __re
         }
         const float s = (s0 + s1) + b0;
         y[r] = relu ? fmaxf(s, 0.f) : s;
+        if (yh) {        // the raw result also as one (hi, lo) channel of an NHWC tensor: the 129th feature channel of the confidence head
+            const __nv_bfloat16 h = __float2bfloat16(s);
+            yh[p * ystride] = h;
+            if (yl) yl[p * ystride] = __float2bfloat16(s - __bfloat162float(h));
+        }
     }
 }
 
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(256) dot_head_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) dot_head_bwd_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
                                                            int xstride, const float* __restrict__ w, const float* __restrict__ gy,
                                                            float* __restrict__ GX, int gxstride, int gx_accum, int N, int C, int C4, int H,
-                                                           int W, double* __restrict__ part) {
+                                                           int W, double* __restrict__ part, const float* __restrict__ gy2, int gy2stride) {
     __shared__ double red[256];
     const int groups = 256 / C4, cl = threadIdx.x % C4, pg = threadIdx.x / C4;
     const long long pixels = (long long)N * H * W;
@@ -352,7 +358,8 @@ __global__ void __launch_bounds__(256) dot_head_bwd_kernel(const __nv_bfloat16* 
     if (pg < groups)
         for (long long r = (long long)blockIdx.x * groups + pg; r < pixels; r += (long long)gridDim.x * groups) {
             const long long p = pix_of(r, H, W);
-            const float g = __ldg(gy + r);
+            float g = __ldg(gy + r);
+            if (gy2) g += gy2[p * gy2stride];      // + the gradient another consumer left in an NHWC gradient channel
             const uint2 raw = __ldg(reinterpret_cast<const uint2*>(xh + p * xstride + cl * 4));
             const __nv_bfloat162* xx = reinterpret_cast<const __nv_bfloat162*>(&raw);
             float x[4] = {__low2float(xx[0]), __high2float(xx[0]), __low2float(xx[1]), __high2float(xx[1])};
@@ -565,7 +572,7 @@ int adc_bn_bwd(const float* g, int g_stride, int g_off, const float* y, int y_st
 }
 
 int adc_dot_head_fwd(const void* x_hi, const void* x_lo, int x_stride, int x_off, const float* w, const float* bias, float* y, int relu, int N,
-                     int C, int H, int W, adc_stream_t stream) {
+                     int C, int H, int W, void* y_hi, void* y_lo, int y_stride, int y_off, adc_stream_t stream) {
     if (bad_slice(x_hi, x_stride, x_off, C, 8) || !w || !y || C <= 0 || C > kCMax || N <= 0 || H <= 0 || W <= 0) {
         adc::set_error("adc_dot_head_fwd: bad argument");
         return ADC_E_BADARG;
@@ -574,12 +581,16 @@ int adc_dot_head_fwd(const void* x_hi, const void* x_lo, int x_stride, int x_off
     adc::Prof prof((cudaStream_t)stream, adc::KIND_BN, (double)pixels * (C * (x_lo ? 4.0 : 2.0) + 4.0));
     const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(x_hi) + x_off;
     const __nv_bfloat16* xl = x_lo ? reinterpret_cast<const __nv_bfloat16*>(x_lo) + x_off : nullptr;
-    dot_head_kernel<<<grid_for(pixels), 256, (C + 7) / 8 * 8 * sizeof(float), (cudaStream_t)stream>>>(xh, xl, x_stride, w, bias, y, relu, N, C, H, W);
+    __nv_bfloat16* yh = y_hi ? reinterpret_cast<__nv_bfloat16*>(y_hi) + y_off : nullptr;
+    __nv_bfloat16* yl = (y_hi && y_lo) ? reinterpret_cast<__nv_bfloat16*>(y_lo) + y_off : nullptr;
+    dot_head_kernel<<<grid_for(pixels), 256, (C + 7) / 8 * 8 * sizeof(float), (cudaStream_t)stream>>>(xh, xl, x_stride, w, bias, y, relu, N, C, H, W,
+                                                                                                     yh, yl, y_stride);
     return adc::check_cuda(cudaGetLastError(), "dot_head_kernel launch");
 }
 
 int adc_dot_head_bwd(const void* x_hi, const void* x_lo, int x_stride, int x_off, const float* w, const float* gy, float* gx, int gx_stride,
-                     int gx_off, int gx_accum, float* gw, float* gb, void* workspace, int N, int C, int H, int W, adc_stream_t stream) {
+                     int gx_off, int gx_accum, float* gw, float* gb, void* workspace, int N, int C, int H, int W, const float* gy_extra,
+                     int gy_extra_stride, adc_stream_t stream) {
     if (bad_slice(x_hi, x_stride, x_off, C, 4) || (gx && bad_slice(gx, gx_stride, gx_off, C, 4)) || !w || !gy || !gw || !workspace || C <= 0 ||
         C > kCMax || N <= 0 || H <= 0 || W <= 0) {
         adc::set_error("adc_dot_head_bwd: bad argument");
@@ -593,7 +604,8 @@ int adc_dot_head_bwd(const void* x_hi, const void* x_lo, int x_stride, int x_off
     const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(x_hi) + x_off;
     const __nv_bfloat16* xl = x_lo ? reinterpret_cast<const __nv_bfloat16*>(x_lo) + x_off : nullptr;
     double* part = reinterpret_cast<double*>(workspace);
-    dot_head_bwd_kernel<<<kParts, 256, 0, st>>>(xh, xl, x_stride, w, gy, gx ? gx + gx_off : nullptr, gx_stride, gx_accum, N, C, C4, H, W, part);
+    dot_head_bwd_kernel<<<kParts, 256, 0, st>>>(xh, xl, x_stride, w, gy, gx ? gx + gx_off : nullptr, gx_stride, gx_accum, N, C, C4, H, W, part,
+                                                gy_extra, gy_extra_stride);
     int rc = adc::check_cuda(cudaGetLastError(), "dot_head_bwd_kernel launch");
     if (rc) return rc;
     dot_head_bwd_finalize_kernel<<<(Cp + 127) / 128, 128, 0, st>>>(part, kParts, Cp, C, gw, gb);

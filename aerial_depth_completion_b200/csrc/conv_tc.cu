@@ -216,7 +216,8 @@ struct ConvParamsV2 {
     int out_zero_to;         // channels [cout, out_zero_to) of the output slice are written as zeros (keeps padded inputs exact)
     int resident;            // 1: all weight tiles stay in shared memory for the CTA's lifetime
     int nstages;             // 2..8 pipeline stages
-    int tma_store;           // 1: bf16 output tile staged in shared memory and written by TMA bulk stores (slice width 64)
+    int tma_store;           // 1: bf16 output tile staged in shared memory and written by TMA bulk stores (slice width 64); 2: fp32 output
+                             // (<= 64 channels) staged as two 32-channel boxes, written by bulk stores or, with accum, bulk reduce-adds
     int dbg;                 // timing experiments: 1 = epilogue skips its global stores, 2 = epilogue skipped entirely
     int taps1;               // 1: only the centre tap exists (a 1x1 convolution / plain GEMM over the flat pixels)
     int tap_mask;            // bit 3u+v set = tap (u,v) has non-zero weights; rows of taps that are all clear are never loaded
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
     uint8_t* stages = smem + res_bytes;
     // output staging for the TMA store: one (two in split mode) 128-pixel x 64-channel bf16 tile, 128-byte swizzled
     uint8_t* ostage = stages + nst * stage_bytes;
-    const int ostage_bytes = p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0;
+    const int ostage_bytes = p.tma_store == 2 ? 32768 : (p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + ostage_bytes);
     // bars: full[8], empty[8], tmem_full[2], tmem_empty[2], weights
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
@@ -417,6 +418,17 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 const int lim = p.out_zero_to > p.cout ? p.out_zero_to : p.cout;   // channels this layer owns
                 if (c0 < p.npad) epi_bias_act16(v, sbias + c0, p.act);
                 epi_mask16(v, c0, p.cout, border);
+                if (p.tma_store == 2) {
+                    // fp32 tile staged as 32-channel boxes of 128 rows x 128 bytes (16-byte chunks XOR-swizzled by row & 7): per-thread
+                    // stores of a 256-byte pixel row are 32 sectors per instruction, the bulk store / reduce-add is one coalesced copy
+                    const int row = quarter * 32 + lane;
+                    uint8_t* rowp = ostage + (c0 >> 5) * 16384 + row * 128;
+                    const int ch0 = (c0 & 31) >> 2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<float4*>(rowp + (((ch0 + k) ^ (row & 7)) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    continue;
+                }
                 if (p.out_f32) {
                     float* o = reinterpret_cast<float*>(p.out) + m * p.out_pix_stride + p.out_ch_off + c0;
 #pragma unroll
@@ -468,8 +480,15 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (warp == 2 && lane == 0) {
                     const long long m0 = (long long)tile * 128;
-                    tma_store_2d(&map_o, ostage, 0, (int)m0);
-                    if (p.out_lo) tma_store_2d(&map_ol, ostage + 16384, 0, (int)m0);
+                    if (p.tma_store == 2) {
+                        for (int b = 0; b * 32 < c_end && b < 2; ++b) {
+                            if (p.accum) tma_reduce_add_2d(&map_o, ostage + b * 16384, b * 32, (int)m0);
+                            else tma_store_2d(&map_o, ostage + b * 16384, b * 32, (int)m0);
+                        }
+                    } else {
+                        tma_store_2d(&map_o, ostage, 0, (int)m0);
+                        if (p.out_lo) tma_store_2d(&map_ol, ostage + 16384, 0, (int)m0);
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -1035,7 +1054,27 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     memset(&mol, 0, sizeof(mol));
     const int width = out_zero_to > npad ? out_zero_to : npad;
     p.tma_store = (!out_f32 && width == 64 && out_stride % 8 == 0 && out_off % 8 == 0) ? 1 : 0;
-    if (p.tma_store) {
+    {
+        const char* e = getenv("ADC_V2_NO_F32_TMA");
+        if (out_f32 && width <= 64 && out_stride % 4 == 0 && out_off % 4 == 0 && !(e && e[0] == '1')) {
+            // fp32 result (the BN nets' raw convolution outputs and gradient buffers): one map of 32-channel x 128-row boxes over the
+            // channels this launch owns (dims[0] clips the rest), stores or reduce-adds
+            float* ob = reinterpret_cast<float*>(out) + out_off;
+            const int lim = out_zero_to > cout ? out_zero_to : cout;
+            cuuint64_t dims[2] = {(cuuint64_t)lim, (cuuint64_t)p.F};
+            cuuint64_t strides[1] = {(cuuint64_t)out_stride * 4};
+            cuuint32_t box[2] = {32, 128};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ob, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                adc::set_error("cuTensorMapEncodeTiled(out f32, v2) failed: %d", (int)r);
+                return ADC_E_UNSUPP;
+            }
+            p.tma_store = 2;
+        }
+    }
+    if (p.tma_store == 1) {
         auto make_o = [&](CUtensorMap* m, void* base_) -> int {
             __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(base_) + out_off;
             cuuint64_t dims[2] = {64, (cuuint64_t)p.F};
@@ -1056,7 +1095,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     // weights resident in shared memory if they fit next to >= 2 activation stages; otherwise streamed with every step
     const int kblocks = (cin + 63) / 64, mult = split ? 2 : 1;
     const int w_all = (taps1 ? 1 : 9) * kblocks * npad * 128;
-    const int ostage_bytes = p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0;
+    const int ostage_bytes = p.tma_store == 2 ? 32768 : (p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0);
     const int budget = kSmemCap - 1024 - 256 - ostage_bytes;
     int smem;
     {

@@ -61,6 +61,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                  "r"(smem_u32(src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// global[map tile] += shared tile (fp32): the accumulate form of the bulk store
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

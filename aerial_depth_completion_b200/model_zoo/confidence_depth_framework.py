@@ -168,6 +168,9 @@ class ConfidenceDepthFrameworkModel(torch.nn.Module):
 
     def forward(self, input):
         dc_x = input[:, :self.input_size, :, :]
+        if hasattr(self.dc_model, '_adc_lazy_features'):
+            # a cbr3-c1 head behind a BN net reads the 129 feature channels in place from the net's NHWC buffer (tc_bn.LazyFeatures)
+            self.dc_model._adc_lazy_features = isinstance(self.conf_model, CBR3C1Confidence) and dense.tc_enabled()
         depth1, conf_x = self.dc_model(dc_x, (self.loss_dc_model is not None))
         if self.conf_model is not None:
             assert (conf_x is not None), 'dc_model does not support extern confidence net'
@@ -225,13 +228,15 @@ class CBR3C1Confidence(nn.Module):
 
     def forward(self, x):
         if dense.tc_enabled():
+            from .. import tc_bn
+            if isinstance(x, tc_bn.LazyFeatures):
+                return tc_bn.conf_head(self, x)
             dense._need_cuda(x)
             if self.conv1.in_channels <= 80:
                 # conv1 + its gradients on the tcgen05 kernels, BN + LeakyReLU + conv2 + sigmoid fused (csrc/conf_head.cu)
                 from .. import tc_train
                 return tc_train.conf_head(self, x)
             # wider features (129 channels behind gudepthcompnet18): output-channel chunks + K tail, general BN passes (tc_bn.py)
-            from .. import tc_bn
             return tc_bn.conf_head(self, x)
         return torch.sigmoid(self.conv2(self.relu1(self.bn1(self.conv1(x)))))
 

@@ -67,6 +67,7 @@ class S2DUResNet(nn.Module):
         super(S2DUResNet, self).__init__()
         self.in_channels, self.out_channels, self.unguided = in_channels, out_channels, unguided
         self.out_feature_channels = 1 if out_channels == 2 else 129
+        self._adc_lazy_features = False      # set by the framework model when a cbr3-c1 head consumes the features in place
         if unguided:
             self.unguidednet = unguided_net()
         if in_channels == 3:

@@ -238,27 +238,30 @@ def wgrad_1x1_box(dY, dy_off, cout, x, x_off, cin, stride):
 
 
 # ---- 1x1 head to one / two channels ---------------------------------------------------------------------------------------------------
-def dot_head(x, x_off, C, weight, bias, relu=False):
-    """[oc, C, 1, 1] convolution over a (hi, lo) slice -> fp32 NCHW [n, oc, h, w]."""
+def dot_head(x, x_off, C, weight, bias, relu=False, y_act=None, y_off=0):
+    """[oc, C, 1, 1] convolution over a (hi, lo) slice -> fp32 NCHW [n, oc, h, w]; with ``y_act`` (oc == 1) the result is also written
+    as channel ``y_off`` of that NHWC activation."""
     oc = weight.shape[0]
     y = torch.empty((x.n, oc, x.h, x.w), device=x.hi.device, dtype=torch.float32)
     w2 = weight.detach().reshape(oc, C).contiguous()
     b = bias.detach() if bias is not None else None
     if oc == 1:
+        yh, yl, ys = (y_act.hi.data_ptr(), _ptr(y_act.lo), y_act.cs) if y_act is not None else (None, None, 0)
         check(lib.adc_dot_head_fwd(x.hi.data_ptr(), _ptr(x.lo), x.cs, x_off, w2.data_ptr(), _ptr(b), y.data_ptr(), int(relu), x.n, C, x.h, x.w,
-                                   dense._stream()), "adc_dot_head_fwd")
+                                   yh, yl, ys, y_off, dense._stream()), "adc_dot_head_fwd")
         return y
     planes = []
     for o in range(oc):
         yo = torch.empty((x.n, 1, x.h, x.w), device=x.hi.device, dtype=torch.float32)
         check(lib.adc_dot_head_fwd(x.hi.data_ptr(), _ptr(x.lo), x.cs, x_off, w2[o].data_ptr(), b[o:o + 1].data_ptr() if b is not None else None,
-                                   yo.data_ptr(), int(relu), x.n, C, x.h, x.w, dense._stream()), "adc_dot_head_fwd")
+                                   yo.data_ptr(), int(relu), x.n, C, x.h, x.w, None, None, 0, 0, dense._stream()), "adc_dot_head_fwd")
         planes.append(yo)
     return torch.cat(planes, 1)
 
 
-def dot_head_backward(x, x_off, C, weight, gy, G, g_off, accumulate):
-    """Backward of dot_head: G[:, g_off:g_off+C] (+)= gy * w; returns (dweight [oc, C, 1, 1], dbias [oc])."""
+def dot_head_backward(x, x_off, C, weight, gy, G, g_off, accumulate, gy_extra=None):
+    """Backward of dot_head: G[:, g_off:g_off+C] (+)= gy * w; returns (dweight [oc, C, 1, 1], dbias [oc]).  gy_extra = (fp32 NHWC
+    activation, channel): a second gradient of y sitting in that channel (added to gy; oc == 1)."""
     oc = weight.shape[0]
     dev = x.hi.device
     w2 = weight.detach().reshape(oc, C).contiguous()
@@ -268,9 +271,10 @@ def dot_head_backward(x, x_off, C, weight, gy, G, g_off, accumulate):
     ws = torch.empty(lib.adc_bn_workspace_bytes(C) // 8, device=dev, dtype=torch.float64)
     for o in range(oc):
         g_o = gy[:, o].contiguous() if oc > 1 else gy
+        ex, exs = (gy_extra[0].hi.data_ptr() + 4 * gy_extra[1], gy_extra[0].cs) if (gy_extra is not None and oc == 1) else (None, 0)
         check(lib.adc_dot_head_bwd(x.hi.data_ptr(), _ptr(x.lo), x.cs, x_off, w2[o].data_ptr(), g_o.data_ptr(), G.hi.data_ptr(), G.cs, g_off,
                                    int(bool(accumulate) or o > 0), gw[o].data_ptr(), gb[o:o + 1].data_ptr(), ws.data_ptr(), x.n, C, x.h, x.w,
-                                   dense._stream()), "adc_dot_head_bwd")
+                                   ex, exs, dense._stream()), "adc_dot_head_bwd")
     return gw.reshape(oc, C, 1, 1), gb
 
 
@@ -288,13 +292,14 @@ class _Plan:
         F = lambda lvl, c: f32_act(n, hs[lvl], ws[lvl], c, dev)
         self.P, self.F = P, F
         self.x45 = P(0, 64)                       # im2col of the stems' inputs
-        self.cat_last = P(0, 128)                 # [convt1 out 64 | conv1 64]
+        self.cat_last = P(0, 192)                 # [convt1 out 64 | conv1 64 | y 1 | zeros]: the 129 feature channels of the confidence head
         self.cat = {2: P(0, 128), 3: P(1, 192), 4: P(2, 384), 5: P(3, 768)}   # cat_k = [convt_k out | conv_k (encoder stage output)]
         self.c6 = P(4, 512)
         self.Y, self.X, self.S = {}, {}, {}       # fp32 conv results, block-internal activations, BN states
         self.G = {}                               # fp32 gradient buffers (allocated at the first backward)
         self.D = {}                               # (hi, lo) dY operands of the gradient GEMMs
         self.forward_id = 0
+        self.head_grad_id = -1                    # forward_id whose confidence-head data gradient is in G["cat_last"]
 
     def y(self, key, lvl, c):
         if key not in self.Y:
@@ -451,10 +456,13 @@ class S2DUBodyTC(torch.autograd.Function):
         Yt1 = P.y("convt1", 0, 64)
         fwd_s1(P.cat[2], 0, 128, W, "convt1", Yt1, 0, 64)
         P.S["convt1"] = bn_forward(Yt1, 0, 64, net.convt1[1], training, P.cat_last, 0, LEAKY)
-        y = dot_head(P.cat_last, 0, 128, net.convtf[0].weight, net.convtf[0].bias)
-        lli = dense.to_nchw_f32(P.cat_last, 128) if want_lli else None
+        oc = net.convtf[0].weight.shape[0]
+        y = dot_head(P.cat_last, 0, 128, net.convtf[0].weight, net.convtf[0].bias, y_act=P.cat_last if oc == 1 else None, y_off=128)
+        # want_lli: 1 = materialise last_layer_input as an NCHW tensor; 2 = hand the NHWC buffer to the confidence head through a token
+        # (no NCHW round trip: the head reads cat_last[0:129] in place and leaves its input gradient in this plan's gradient buffer)
+        lli = dense.to_nchw_f32(P.cat_last, 128) if want_lli == 1 else (torch.zeros(1, device=dev) if want_lli == 2 else None)
         P.forward_id += 1
-        ctx.net, ctx.plan, ctx.fid, ctx.nsrc, ctx.training = net, P, P.forward_id, nsrc, training
+        ctx.net, ctx.plan, ctx.fid, ctx.nsrc, ctx.training, ctx.want_lli = net, P, P.forward_id, nsrc, training, want_lli
         ctx.src_ch = [s.shape[1] for s in srcs]
         ctx.save_for_backward(*params)
         return y, lli
@@ -488,10 +496,14 @@ class S2DUBodyTC(torch.autograd.Function):
         wp.fwd("convt1", net.convt1[0].weight, 64)
         W = wp.run()
         # ---- head: 1x1 convolution + the features' gradient
-        Gl = P.g("cat_last", 0, 128)
-        if g_lli is not None:
+        Gl = P.g("cat_last", 0, 192)
+        head_wrote = ctx.want_lli == 2 and P.head_grad_id == ctx.fid     # the confidence head's data gradient already sits in Gl[0:129]
+        if g_lli is not None and ctx.want_lli == 1:
             nchw_into(g_lli, Gl, 0, False)
-        gw, gb = dot_head_backward(P.cat_last, 0, 128, net.convtf[0].weight, g_y, Gl, 0, g_lli is not None)
+        if g_y is None:
+            g_y = torch.zeros((n, net.convtf[0].weight.shape[0], h, w), device=Gl.hi.device)
+        have = (g_lli is not None and ctx.want_lli == 1) or head_wrote
+        gw, gb = dot_head_backward(P.cat_last, 0, 128, net.convtf[0].weight, g_y, Gl, 0, have, gy_extra=(Gl, 128) if head_wrote else None)
         grads["convtf.0.weight"], grads["convtf.0.bias"] = gw, gb
         # ---- convt1 (stride-1 transposed convolution = convolution with flipped weights)
         D = P.d("convt1", 0, 64)
@@ -627,15 +639,74 @@ def s2du_forward(net, x, build_conf_input):
     names = _param_names(net)
     pd = dict(net.named_parameters())
     want = bool(build_conf_input) and net.out_channels == 1
-    y, lli = S2DUBodyTC.apply(net, want, len(srcs), *srcs, *[pd[k] for k in names])
+    lazy = want and getattr(net, "_adc_lazy_features", False)
+    y, lli = S2DUBodyTC.apply(net, (2 if lazy else 1) if want else 0, len(srcs), *srcs, *[pd[k] for k in names])
     features = None
     if build_conf_input:
-        features = torch.cat((lli, y), 1) if want else torch.sigmoid(y[:, 1:2, :, :])
+        if lazy:
+            features = LazyFeatures(lli, net, 129)
+        else:
+            features = torch.cat((lli, y), 1) if want else torch.sigmoid(y[:, 1:2, :, :])
     depth = y[:, 0:1, :, :] if net.training else torch.relu(y[:, 0:1, :, :])
     return depth, features
 
 
 # ---- cbr3-c1 confidence head, any channel count -----------------------------------------------------------------------------------------
+class LazyFeatures:
+    """The feature tensor of a depth-completion net (s2d_u_resnet.py:179: cat(last_layer_input, y), 129 channels) left where it was
+    computed: channels [0, 129) of the net's NHWC (hi, lo) concat buffer.  ``CBR3C1Confidence`` consumes it in place; autograd sees the
+    1-element ``token``.  Handed out only when the framework model asks for it (``net._adc_lazy_features``), so a direct caller of
+    ``S2DUResNet.forward`` still receives the NCHW tensor of the reference."""
+
+    def __init__(self, token, net, channels):
+        self.token, self.net, self.channels = token, net, channels
+
+    def size(self):
+        P = _current_plan(self.net)
+        return torch.Size((P.n, self.channels, P.h, P.w))
+
+
+def _current_plan(net):
+    return next(iter(net.__dict__["_tc_plans"].values()))
+
+
+def _head_forward(X, c, head, w1, w2, b2):
+    """Shared core: X = (hi, lo) activation holding the c feature channels at offset 0 (contraction width round16(c))."""
+    n, h, w, dev = X.n, X.h, X.w, X.hi.device
+    bn = head.bn1
+    cp, cs = dense._r16(c), dense._r64(c)
+    step = 80 if dense._split() else 128               # the row-segment kernel takes 80 output channels in split mode: 129 = 80 + 49
+    wp = WPrep()
+    wp.fwd("c1", w1, cp, step)
+    W = wp.run()
+    Y = f32_act(n, h, w, cs, dev)
+    fwd_s1(X, 0, cp, W, "c1", Y, 0, c, step=step)
+    Z = pair_act(n, h, w, cs, dev)
+    state = bn_forward(Y, 0, c, bn, bn.training, Z, 0, LEAKY)
+    conf = torch.sigmoid(dot_head(Z, 0, c, w2, b2))
+    return conf, (Y, Z, state)
+
+
+def _head_backward(X, c, saved, conf, gconf, w1, w2, Gx):
+    """Returns (gw1, dgamma, dbeta, gw2, gb2); with ``Gx`` (fp32 NHWC) the input gradient is WRITTEN into its channels [0, c)."""
+    Y, Z, state = saved
+    n, h, w, dev = X.n, X.h, X.w, X.hi.device
+    cs, cp = dense._r64(c), dense._r16(c)
+    gs = (gconf * conf * (1.0 - conf)).contiguous()
+    Gz = f32_act(n, h, w, cs, dev)
+    gw2, gb2 = dot_head_backward(Z, 0, c, w2, gs, Gz, 0, False)
+    D = pair_act(n, h, w, cs, dev)
+    gg, gbeta = bn_backward(Gz, 0, Y, 0, Z, 0, state, LEAKY, D, 0, c)
+    gw1 = wgrad_s1(D, 0, c, X, 0, c)
+    if Gx is not None:
+        step = 80 if dense._split() else 128
+        wp = WPrep()
+        wp.transposed("c1", w1, cp, flip=True, step=step)
+        W = wp.run()
+        dgrad_s1(D, cp, W, "c1", Gx, 0, c, False, step=step)
+    return gw1, gg, gbeta, gw2, gb2
+
+
 class ConfHeadBN(torch.autograd.Function):
     """conv3x3 (no bias) -> BatchNorm -> LeakyReLU(0.2) -> conv1x1 -> sigmoid (confidence_depth_framework.py:299-329) for channel counts
     beyond tc_train.ConfHeadTC's fused 80-channel path (129 for the S2DU features): the 3x3 convolution in output-channel chunks with a
@@ -644,50 +715,52 @@ class ConfHeadBN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, w1, gamma, beta, w2, b2, head):
         n, c, h, w = feat.shape
-        dev = feat.device
-        bn = head.bn1
-        cp = dense._r16(c)                             # contraction width (16-channel K steps)
-        cs = dense._r64(c)
-        X = dense.to_nhwc_bf16(feat, cpad=cs, pad=True)
-        step = 80 if dense._split() else 128           # the row-segment kernel takes 80 output channels in split mode: 129 = 80 + 49
-        wp = WPrep()
-        wp.fwd("c1", w1, cp, step)
-        W = wp.run()
-        Y = f32_act(n, h, w, cs, dev)
-        fwd_s1(X, 0, cp, W, "c1", Y, 0, c, step=step)
-        Z = pair_act(n, h, w, cs, dev)
-        state = bn_forward(Y, 0, c, bn, bn.training, Z, 0, LEAKY)
-        s = dot_head(Z, 0, c, w2, b2)
-        conf = torch.sigmoid(s)
-        ctx.X, ctx.Y, ctx.Z, ctx.state, ctx.c = X, Y, Z, state, c
+        X = dense.to_nhwc_bf16(feat, cpad=dense._r64(c), pad=True)
+        conf, saved = _head_forward(X, c, head, w1, w2, b2)
+        ctx.X, ctx.saved, ctx.c = X, saved, c
         ctx.save_for_backward(conf, w1, w2)
         return conf
 
     @staticmethod
     def backward(ctx, gconf):
         conf, w1, w2 = ctx.saved_tensors
-        X, Y, Z, c = ctx.X, ctx.Y, ctx.Z, ctx.c
-        n, h, w = X.n, X.h, X.w
-        dev = conf.device
-        cs, cp = X.cs, dense._r16(c)
-        gs = (gconf * conf * (1.0 - conf)).contiguous()
-        Gz = f32_act(n, h, w, cs, dev)
-        gw2, gb2 = dot_head_backward(Z, 0, c, w2, gs, Gz, 0, False)
-        D = pair_act(n, h, w, cs, dev)
-        gg, gbeta = bn_backward(Gz, 0, Y, 0, Z, 0, ctx.state, LEAKY, D, 0, c)
-        gw1 = wgrad_s1(D, 0, c, X, 0, c)
-        gfeat = None
-        if ctx.needs_input_grad[0]:
-            step = 80 if dense._split() else 128
-            wp = WPrep()
-            wp.transposed("c1", w1, cp, flip=True, step=step)
-            W = wp.run()
-            Gx = f32_act(n, h, w, cs, dev)
-            dgrad_s1(D, cp, W, "c1", Gx, 0, c, False, step=step)
-            gfeat = dense.to_nchw_f32(Gx, c)
-        ctx.X = ctx.Y = ctx.Z = None
+        X, c = ctx.X, ctx.c
+        Gx = f32_act(X.n, X.h, X.w, X.cs, conf.device) if ctx.needs_input_grad[0] else None
+        gw1, gg, gbeta, gw2, gb2 = _head_backward(X, c, ctx.saved, conf, gconf, w1, w2, Gx)
+        gfeat = dense.to_nchw_f32(Gx, c) if Gx is not None else None
+        ctx.X = ctx.saved = None
         return gfeat, gw1, gg, gbeta, gw2, gb2, None
 
 
+class ConfHeadLazy(torch.autograd.Function):
+    """The same head reading its features in place from the depth-completion net's NHWC buffer (LazyFeatures); its input gradient goes
+    straight into that net's fp32 gradient buffer, where the net's own backward (which autograd runs afterwards) accumulates onto it."""
+
+    @staticmethod
+    def forward(ctx, token, w1, gamma, beta, w2, b2, head, feats):
+        P = _current_plan(feats.net)
+        conf, saved = _head_forward(P.cat_last, feats.channels, head, w1, w2, b2)
+        ctx.plan, ctx.fid, ctx.saved, ctx.c = P, P.forward_id, saved, feats.channels
+        ctx.save_for_backward(conf, w1, w2)
+        return conf
+
+    @staticmethod
+    def backward(ctx, gconf):
+        conf, w1, w2 = ctx.saved_tensors
+        P = ctx.plan
+        if P.forward_id != ctx.fid:
+            raise RuntimeError("ConfHeadLazy: the depth-completion net ran another forward before this backward; its features are gone")
+        Gx = None
+        if ctx.needs_input_grad[0]:
+            Gx = P.g("cat_last", 0, 192)
+            P.head_grad_id = ctx.fid
+        gw1, gg, gbeta, gw2, gb2 = _head_backward(P.cat_last, ctx.c, ctx.saved, conf, gconf, w1, w2, Gx)
+        ctx.saved = None
+        return (torch.zeros_like(conf[:1, 0, 0, :1]).reshape(1) if Gx is not None else None), gw1, gg, gbeta, gw2, gb2, None, None
+
+
 def conf_head(head, feat):
-    return ConfHeadBN.apply(feat, head.conv1.weight, head.bn1.weight, head.bn1.bias, head.conv2.weight, head.conv2.bias, head)
+    p = (head.conv1.weight, head.bn1.weight, head.bn1.bias, head.conv2.weight, head.conv2.bias)
+    if isinstance(feat, LazyFeatures):
+        return ConfHeadLazy.apply(feat.token, *p, head, feat)
+    return ConfHeadBN.apply(feat, *p, head)

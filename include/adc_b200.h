@@ -370,11 +370,15 @@ int adc_bn_bwd(const float* g, int g_stride, int g_off, const float* y, int y_st
                float* coef, int act, int training, void* dy_hi, void* dy_lo, int dy_stride, int dy_off, float* gres, int gres_stride,
                int gres_off, int gres_accum, float* ggamma, float* gbeta, void* workspace, int N, int C, int H, int W, adc_stream_t stream);
 /* 1x1 convolution to ONE channel over a (hi, lo) NHWC slice and its backward (s2d_u_resnet.py:128 convtf): y fp32 [N][H][W] planar;
- * gx: fp32 zero-bordered NHWC gradient slice (written or accumulated), gw [C], gb [1]; workspace: adc_bn_workspace_bytes(C). */
+ * y_hi / y_lo (may be NULL): the raw result also as channel y_off of a zero-bordered NHWC (hi, lo) tensor -- cat(last_layer_input, y)
+ * of s2d_u_resnet.py:179 without a copy.  gx: fp32 zero-bordered NHWC gradient slice (written or accumulated), gw [C], gb [1];
+ * gy_extra (may be NULL): a gradient of y that another consumer left at gy_extra[pixel * gy_extra_stride] of an NHWC gradient tensor
+ * (added to gy); workspace: adc_bn_workspace_bytes(C). */
 int adc_dot_head_fwd(const void* x_hi, const void* x_lo, int x_stride, int x_off, const float* w, const float* bias, float* y, int relu, int N,
-                     int C, int H, int W, adc_stream_t stream);
+                     int C, int H, int W, void* y_hi, void* y_lo, int y_stride, int y_off, adc_stream_t stream);
 int adc_dot_head_bwd(const void* x_hi, const void* x_lo, int x_stride, int x_off, const float* w, const float* gy, float* gx, int gx_stride,
-                     int gx_off, int gx_accum, float* gw, float* gb, void* workspace, int N, int C, int H, int W, adc_stream_t stream);
+                     int gx_off, int gx_accum, float* gw, float* gb, void* workspace, int N, int C, int H, int W, const float* gy_extra,
+                     int gy_extra_stride, adc_stream_t stream);
 /* im2col of a 3x3 / pad-1 window (stride 1 or 2) over the C = c0 + c1 + c2 <= 7 fp32 planes of up to three NCHW sources (s1, s2 may be
  * NULL; bs = batch stride in floats) at the output resolution: channel (3u+v)*C + c of a 64-channel (hi, lo) zero-bordered NHWC pixel.
  * The thin stems of s2d_u_resnet.py:91-97 (3 -> 48, 2 -> 16) become one GEMM launch. */
