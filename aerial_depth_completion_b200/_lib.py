@@ -163,6 +163,8 @@ SIGNATURES = {
     "adc_nchw_to_nhwc_f32": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_adam_step_dev": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_ll, _vp]),
     "adc_uniform_sampling": (c_int, [_vp, _vp, c_int, ctypes.c_float, c_int, _vp, c_int, c_ll, _vp]),
+    "adc_sample_assemble": (c_int, [_vp, _vp, c_int, ctypes.c_float, c_int, _vp, c_int, c_ll, _vp]),
+    "adc_conf_pr_histogram": (c_int, [_vp, _vp, _vp, c_ll, _vp, c_int, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

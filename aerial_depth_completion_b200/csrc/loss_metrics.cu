@@ -128,6 +128,40 @@ __global__ void __launch_bounds__(256) depth_metrics_partial_kernel(const float*
     block_store<kNV>(v, part + (long long)blockIdx.x * kNV);
 }
 
+// ConfidencePixelwiseThrAverageMeter.evaluate (metrics.py:103-131) asks, for each of num_bins thresholds, for the mean of
+// absrel = |d - t| / t * 1000 and the number of valid pixels (t > 0) whose confidence exceeds the threshold: 500 boolean-index
+// passes with two host synchronisations each in the reference.  One pass here: a pixel with k = #{j : conf > thr[j]} (thresholds
+// ascending, compared in fp32 like `confidence > curr_conf`) counts for exactly the thresholds j < k, so it lands in bin k of a
+// (num_bins + 1)-bin histogram and the per-threshold figures are suffix sums over the bins.  Integer accumulators (pixel counts and
+// absrel in 2^-16 fixed point) keep the result independent of the atomics' order.  hist: [3][num_bins + 1] unsigned 64-bit =
+// count, fixed-point absrel sum, count of pixels whose absrel is not finite (their thresholds have no finite mean, as in the reference).
+__global__ void __launch_bounds__(256) conf_pr_hist_kernel(const float* __restrict__ depth, const float* __restrict__ conf,
+                                                           const float* __restrict__ target, long long n, const float* __restrict__ thr,
+                                                           int nb, unsigned long long* __restrict__ hist) {
+    extern __shared__ unsigned long long sh[];      // [3][nb + 1]
+    float* sthr = reinterpret_cast<float*>(sh + 3 * (nb + 1));
+    for (int i = threadIdx.x; i < 3 * (nb + 1); i += blockDim.x) sh[i] = 0ull;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) sthr[i] = thr[i];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float t = __ldg(target + i);
+        if (!(t > 0.f)) continue;
+        const float c = __ldg(conf + i);
+        const float ar = (fabsf(__ldg(depth + i) - t) / t) * 1000.0f;
+        int lo = 0, hi = nb;                         // first j with !(c > thr[j]); NaN confidence: 0
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (c > sthr[mid]) lo = mid + 1; else hi = mid;
+        }
+        atomicAdd(sh + lo, 1ull);
+        if (isfinite(ar)) atomicAdd(sh + (nb + 1) + lo, __double2ull_rn((double)ar * 65536.0));
+        else atomicAdd(sh + 2 * (nb + 1) + lo, 1ull);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * (nb + 1); i += blockDim.x)
+        if (sh[i]) atomicAdd(hist + i, sh[i]);
+}
+
 static int grid_for(long long n) {
     long long b = (n + 255) / 256;
     return (int)(b < kParts ? (b > 0 ? b : 1) : kParts);
@@ -184,6 +218,22 @@ int adc_depth_metrics(const float* output, const float* target, const float* con
     if (rc) return rc;
     finalize_kernel<<<1, 32 * kNV, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, kNV, out);
     return adc::check_cuda(cudaGetLastError(), "finalize_kernel launch");
+}
+
+int adc_conf_pr_histogram(const float* depth, const float* confidence, const float* target, long long n, const float* thresholds,
+                          int num_bins, unsigned long long* hist, adc_stream_t stream) {
+    if (!depth || !confidence || !target || !thresholds || !hist || n <= 0 || num_bins <= 0 || num_bins > 1500) {
+        adc::set_error("adc_conf_pr_histogram: bad argument (1 <= num_bins <= 1500)");
+        return ADC_E_BADARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = adc::check_cuda(cudaMemsetAsync(hist, 0, 3 * (size_t)(num_bins + 1) * sizeof(unsigned long long), st), "histogram memset");
+    if (rc) return rc;
+    adc::Prof prof(st, adc::KIND_TRAIN, (double)n * 12.0);
+    const size_t smem = 3 * (size_t)(num_bins + 1) * sizeof(unsigned long long) + (size_t)num_bins * sizeof(float);
+    long long b = (n + 255) / 256;
+    conf_pr_hist_kernel<<<(int)(b < 148 * 4 ? (b > 0 ? b : 1) : 148 * 4), 256, smem, st>>>(depth, confidence, target, n, thresholds, num_bins, hist);
+    return adc::check_cuda(cudaGetLastError(), "conf_pr_hist_kernel launch");
 }
 
 }  // extern "C"

@@ -51,16 +51,33 @@ __device__ __forceinline__ void regen_range(uint32_t* mt, int lo, int hi, bool c
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads) uniform_sampling_kernel(const float* __restrict__ depth, const unsigned int* __restrict__ seeds,
+// Where a pixel's decision goes: the uint8 mask of adc_uniform_sampling, or -- adc_sample_assemble -- straight into the network input:
+// d = gt * mask and w = mask as fp32 planes (dataloader_ext.py:544-566 builds exactly these two channels from the mask on the host).
+struct Sink {
+    unsigned char* mask;      // [HW] or nullptr
+    float* d;                 // [HW] or nullptr
+    float* w;
+    __device__ __forceinline__ void put(long long p, bool on, float v) const {
+        if (mask) mask[p] = on ? 1 : 0;
+        if (d) { d[p] = on ? v : 0.f; w[p] = on ? 1.f : 0.f; }
+    }
+};
+
+__global__ void __launch_bounds__(kThreads) uniform_sampling_kernel(const float* __restrict__ depth, long long depth_frame_stride,
+                                                                    const unsigned int* __restrict__ seeds,
                                                                     int num_samples, float max_depth, int use_max,
-                                                                    unsigned char* __restrict__ mask, long long HW) {
+                                                                    unsigned char* __restrict__ mask, float* __restrict__ dw_out,
+                                                                    long long out_frame_stride, long long HW) {
     __shared__ uint32_t mt[kN];
     __shared__ uint32_t out[kN];
     __shared__ int warp_cnt[kThreads / 32];
     __shared__ long long s_keep;
     const int n = blockIdx.x, tid = threadIdx.x;
-    const float* d = depth + (long long)n * HW;
-    unsigned char* m = mask + (long long)n * HW;
+    const float* d = depth + (long long)n * depth_frame_stride;
+    Sink m;
+    m.mask = mask ? mask + (long long)n * HW : nullptr;
+    m.d = dw_out ? dw_out + (long long)n * out_frame_stride : nullptr;
+    m.w = dw_out ? m.d + HW : nullptr;
 
     // n_keep = count(depth > 0 [& depth <= max_depth])
     long long cnt = 0;
@@ -89,7 +106,7 @@ __global__ void __launch_bounds__(kThreads) uniform_sampling_kernel(const float*
     if (n_keep == 0 || num_samples == 0) {                // the reference returns mask_keep without touching the generator
         for (long long p = tid; p < HW; p += kThreads) {
             const float v = d[p];
-            m[p] = (v > 0.f && (!use_max || v <= max_depth)) ? 1 : 0;
+            m.put(p, v > 0.f && (!use_max || v <= max_depth), v);
         }
         return;
     }
@@ -108,10 +125,26 @@ __global__ void __launch_bounds__(kThreads) uniform_sampling_kernel(const float*
                 const uint32_t a = out[2 * t] >> 5, b = out[2 * t + 1] >> 6;
                 const double u = ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
                 const float v = d[p];
-                m[p] = (v > 0.f && (!use_max || v <= max_depth) && u < prob) ? 1 : 0;
+                m.put(p, v > 0.f && (!use_max || v <= max_depth) && u < prob, v);
             }
         }
         __syncthreads();                                  // `out` is rewritten by the next round
+    }
+}
+
+// rgb planes of the [N][4][HW] (r, g, b, gt) upload into channels 0..2 of the [N][5][HW] network input: 16-byte copies when HW % 4 == 0
+__global__ void __launch_bounds__(256) copy_rgb_kernel(const float* __restrict__ src, float* __restrict__ dst, long long HW3, long long src_fs,
+                                                       long long dst_fs, int vec) {
+    const int n = blockIdx.y;
+    const float* s = src + (long long)n * src_fs;
+    float* o = dst + (long long)n * dst_fs;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    if (vec) {
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        float4* o4 = reinterpret_cast<float4*>(o);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW3 / 4; i += step) o4[i] = __ldg(s4 + i);
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW3; i += step) o[i] = __ldg(s + i);
     }
 }
 
@@ -126,8 +159,28 @@ int adc_uniform_sampling(const float* depth, const unsigned int* seeds, int num_
         return ADC_E_BADARG;
     }
     adc::Prof prof((cudaStream_t)stream, adc::KIND_TRAIN, (double)N * HW * 5.0);
-    sampler::uniform_sampling_kernel<<<N, sampler::kThreads, 0, (cudaStream_t)stream>>>(depth, seeds, num_samples, max_depth, use_max_depth,
-                                                                                      mask, HW);
+    sampler::uniform_sampling_kernel<<<N, sampler::kThreads, 0, (cudaStream_t)stream>>>(depth, HW, seeds, num_samples, max_depth, use_max_depth,
+                                                                                      mask, nullptr, 0, HW);
+    return adc::check_cuda(cudaGetLastError(), "uniform_sampling_kernel launch");
+}
+
+int adc_sample_assemble(const float* rgbgt, const unsigned int* seeds, int num_samples, float max_depth, int use_max_depth, float* input5,
+                        int N, long long HW, adc_stream_t stream) {
+    if (!rgbgt || !seeds || !input5 || N <= 0 || HW <= 0 || num_samples < 0) {
+        adc::set_error("adc_sample_assemble: bad argument (num_samples >= 0)");
+        return ADC_E_BADARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_TRAIN, (double)N * HW * (4.0 + 8.0 + 24.0));
+    adc::count_launches(1);
+    const int vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(rgbgt) | reinterpret_cast<uintptr_t>(input5)) % 16 == 0);
+    long long blocks = (3 * HW / (vec ? 4 : 1) + 255) / 256;
+    dim3 grid((unsigned)(blocks < 148 ? (blocks > 0 ? blocks : 1) : 148), (unsigned)N);
+    sampler::copy_rgb_kernel<<<grid, 256, 0, st>>>(rgbgt, input5, 3 * HW, 4 * HW, 5 * HW, vec);
+    int rc = adc::check_cuda(cudaGetLastError(), "copy_rgb_kernel launch");
+    if (rc) return rc;
+    sampler::uniform_sampling_kernel<<<N, sampler::kThreads, 0, st>>>(rgbgt + 3 * HW, 4 * HW, seeds, num_samples, max_depth, use_max_depth,
+                                                                     nullptr, input5 + 3 * HW, 5 * HW, HW);
     return adc::check_cuda(cudaGetLastError(), "uniform_sampling_kernel launch");
 }
 

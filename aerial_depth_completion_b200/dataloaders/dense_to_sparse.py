@@ -68,3 +68,37 @@ def uniform_sampling_cuda(depth, seeds, num_samples, max_depth=np.inf):
     check(lib.adc_uniform_sampling(d.data_ptr(), sd.data_ptr(), int(num_samples), float(max_depth) if use_max else 0.0, int(use_max),
                                    mask.data_ptr(), n, hw, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "adc_uniform_sampling")
     return mask.bool()
+
+
+def sample_assemble_cuda(rgbgt, seeds, num_samples, max_depth=np.inf, out=None):
+    """The loader's sparse-depth synthesis and modality assembly on the device (dense_to_sparse.py:29-48 +
+    dataloader_ext.py:544-566): ``rgbgt`` CUDA float32 [N, 4, H, W] = (r, g, b, ground-truth depth); returns the network input
+    [N, 5, H, W] = (r, g, b, d, w) with d = gt * mask, w = mask, mask = the reference's ``UniformSampling(num_samples, max_depth)`` mask of
+    frame n after ``np.random.seed(seeds[n])`` (bit-exact; adc_sample_assemble).  ``seeds``: N integers in [0, 2**32) or a CUDA int32
+    tensor holding the same 32 bits.  The training target is the view ``rgbgt[:, 3:4]``."""
+    import ctypes
+    import torch
+    from .._lib import lib, check
+    if not torch.is_tensor(rgbgt) or not rgbgt.is_cuda or rgbgt.dtype != torch.float32 or rgbgt.dim() != 4 or rgbgt.shape[1] != 4:
+        raise RuntimeError("sample_assemble_cuda needs a CUDA float32 [N, 4, H, W] tensor: the B200 path has no CPU fallback")
+    if num_samples < 0:
+        raise ValueError("sample_assemble_cuda: num_samples must be >= 0")
+    x = rgbgt.contiguous()
+    n, _, h, w = x.shape
+    if torch.is_tensor(seeds):
+        sd = seeds
+        if not sd.is_cuda or sd.dtype != torch.int32 or sd.numel() != n:
+            raise ValueError("sample_assemble_cuda: seeds tensor must be CUDA int32 with one entry per frame")
+    else:
+        seeds = [int(v) for v in seeds]
+        if len(seeds) != n or any(v < 0 or v > 0xFFFFFFFF for v in seeds):
+            raise ValueError("sample_assemble_cuda: one seed in [0, 2**32) per frame")
+        sd = torch.from_numpy(np.array(seeds, dtype=np.uint32).view(np.int32)).to(x.device)
+    if out is None:
+        out = torch.empty(n, 5, h, w, device=x.device, dtype=torch.float32)
+    elif out.shape != (n, 5, h, w) or not out.is_contiguous() or out.dtype != torch.float32 or out.device != x.device:
+        raise ValueError("sample_assemble_cuda: out must be a contiguous CUDA float32 [N, 5, H, W] tensor")
+    use_max = max_depth is not np.inf and np.isfinite(max_depth)
+    check(lib.adc_sample_assemble(x.data_ptr(), sd.data_ptr(), int(num_samples), float(max_depth) if use_max else 0.0, int(use_max),
+                                  out.data_ptr(), n, h * w, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "adc_sample_assemble")
+    return out

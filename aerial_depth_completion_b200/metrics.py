@@ -78,6 +78,7 @@ class ConfidencePixelwiseThrAverageMeter(object):
     def __init__(self, num_bins=500, top=1.0):
         self.num_bins = num_bins
         self.thresholds = np.linspace(0, top, num_bins, endpoint=True)
+        self._thr_dev = {}
         self.reset()
 
     def reset(self):
@@ -86,21 +87,34 @@ class ConfidencePixelwiseThrAverageMeter(object):
         self.recall = np.zeros([self.num_bins], np.uint64)
 
     def evaluate(self, depth, confidence, target):
-        valid_mask = target > 0
-        depth, target, confidence = depth[valid_mask], target[valid_mask], confidence[valid_mask]
-        absrel = ((depth - target).abs() / target) * 1000.0
-        num_valids = valid_mask.sum() / 1000.0
-        thr = torch.as_tensor(self.thresholds, device=confidence.device, dtype=confidence.dtype)
-        mask = confidence.unsqueeze(0) > thr.unsqueeze(1)                  # [bins, valid]
-        cnt = mask.sum(1)
-        mean = (absrel.unsqueeze(0) * mask).sum(1) / cnt
-        valids = cnt / num_valids
-        mean, valids = mean.cpu().numpy(), valids.cpu().numpy()
+        """metrics.py:115-131 loops over the thresholds with a boolean-index pass and two host reads each (1 000 synchronisations
+        per call at the default 500 bins).  Here: one histogram kernel over the pixels (adc_conf_pr_histogram), one 12 KB transfer,
+        suffix sums on the host.  Threshold comparison in fp32 like the reference's ``confidence > curr_conf``; the masked mean is
+        formed from exact integer sums (the reference's is an fp32 reduction), so the truncated ``int(mean)`` can differ by one
+        unit when the mean sits within fp32 round-off of an integer."""
+        from . import ops
+        thr = self._thr_dev.get(confidence.device)
+        if thr is None:
+            thr = self._thr_dev[confidence.device] = torch.as_tensor(self.thresholds, dtype=torch.float32, device=confidence.device)
+        hist = ops.conf_pr_histogram(depth.detach().float(), confidence.detach().float(), target.detach().float(), thr).cpu().numpy()
+        cnt_bin, sum_bin, bad_bin = hist[0], hist[1], hist[2]
+        total = np.float32(int(cnt_bin.sum()))                             # valid_mask.sum()
+        # `valid_mask.sum() / 1000.0` on a CUDA tensor: ATen divides by a host scalar as a multiplication with its fp32 reciprocal
+        num_valids = total * (np.float32(1.0) / np.float32(1000.0))
+        # threshold j sees the bins k > j
+        cnt = np.cumsum(cnt_bin[::-1])[::-1][1:]
+        ssum = np.cumsum(sum_bin[::-1])[::-1][1:]
+        bad = np.cumsum(bad_bin[::-1])[::-1][1:]
         for i in range(self.num_bins):
-            if math.isfinite(mean[i]) and math.isfinite(valids[i]):
+            if cnt[i] == 0 or bad[i] > 0:                                  # mean of an empty selection / with a non-finite term: not finite
+                continue
+            mean = float(ssum[i]) / 65536.0 / float(cnt[i])
+            with np.errstate(divide='ignore', invalid='ignore'):
+                valids = np.float32(int(cnt[i])) / num_valids
+            if math.isfinite(mean) and math.isfinite(valids):
                 self.count[i] += 1
-                self.absrel[i] += int(mean[i])
-                self.recall[i] += int(valids[i])
+                self.absrel[i] += int(mean)
+                self.recall[i] += int(valids)
 
     def result(self):
         res = [(None, None, None)] * self.num_bins

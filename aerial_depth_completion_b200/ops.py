@@ -298,3 +298,19 @@ def depth_metrics(output, target, confidence=None, threshold=0.0):
     check(lib.adc_depth_metrics(o.data_ptr(), t.data_ptr(), c.data_ptr() if c is not None else None, float(threshold), o.numel(),
                                 _lm_workspace(o.device).data_ptr(), out.data_ptr(), _stream()), "adc_depth_metrics")
     return out
+
+
+def conf_pr_histogram(depth, confidence, target, thresholds):
+    """Histogram behind ConfidencePixelwiseThrAverageMeter.evaluate (metrics.py:103-131): int64 tensor [3][bins + 1] on the device
+    (pixel count, absrel sum in 2^-16 fixed point, count of non-finite absrel) -- see adc_conf_pr_histogram.  thresholds: ascending
+    fp32 CUDA tensor."""
+    for name, t in (("depth", depth), ("confidence", confidence), ("target", target), ("thresholds", thresholds)):
+        _require_cuda_f32(name, t)
+    d, c, t = depth.contiguous(), confidence.contiguous(), target.contiguous()
+    if d.shape != t.shape or c.shape != t.shape:
+        raise RuntimeError("conf_pr_histogram: tensors differ in shape")
+    thr = thresholds.contiguous()
+    hist = torch.empty(3, thr.numel() + 1, device=d.device, dtype=torch.int64)
+    check(lib.adc_conf_pr_histogram(d.data_ptr(), c.data_ptr(), t.data_ptr(), d.numel(), thr.data_ptr(), thr.numel(), hist.data_ptr(),
+                                    _stream()), "adc_conf_pr_histogram")
+    return hist

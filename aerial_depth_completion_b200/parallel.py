@@ -210,3 +210,32 @@ class HostFeeder:
         self.loss_done[last].synchronize()
         losses.append(float(self.host_loss[last][0]))
         return losses
+
+
+class DeviceAssemblyFeeder(HostFeeder):
+    """``HostFeeder`` with the loader's sparse-depth synthesis moved to the device.  A host batch is
+    ``(rgbgt, seeds)``: pinned float32 [B, 4, H, W] = (r, g, b, ground-truth depth) and pinned int32 [B] (the per-frame
+    ``np.random.seed`` values as 32-bit patterns).  Only these 4 planes cross PCIe (the reference's loader ships 5 input planes + the
+    target = 6); on the copy stream, behind the copy, ``adc_sample_assemble`` draws the bit-exact ``UniformSampling`` mask of every frame
+    and writes the 5-channel network input, so the assembly of batch i+1 also overlaps step i.  The target is the gt plane."""
+
+    def __init__(self, trainer, example_rgbgt, num_samples, max_depth=float("inf")):
+        dev = trainer.params[0].device
+        n, _, h, w = example_rgbgt.shape
+        super().__init__(trainer, torch.empty(n, 5, h, w), torch.empty(n, 1, h, w))
+        self.num_samples, self.max_depth = num_samples, max_depth
+        self.raw = [(torch.empty(n, 4, h, w, device=dev), torch.empty(n, dtype=torch.int32, device=dev)) for _ in range(2)]
+        self.buf = [(self.buf[i][0], self.raw[i][0][:, 3:4]) for i in range(2)]      # the target is the uploaded gt plane itself
+
+    def _prefetch(self, b, host_rgbgt, host_seeds, first_use):
+        from .dataloaders.dense_to_sparse import sample_assemble_cuda
+        import numpy as _np
+        with torch.cuda.stream(self.copy_stream):
+            if not first_use:
+                self.copy_stream.wait_event(self.free[b])
+            raw, seeds = self.raw[b]
+            raw.copy_(host_rgbgt, non_blocking=True)
+            seeds.copy_(host_seeds, non_blocking=True)
+            sample_assemble_cuda(raw, seeds, self.num_samples, _np.inf if self.max_depth == float("inf") else self.max_depth,
+                                 out=self.buf[b][0])
+            self.ready[b].record(self.copy_stream)

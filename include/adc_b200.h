@@ -334,6 +334,13 @@ int adc_masked_loss_bwd(const float* pred, const float* target, const float* glo
                         adc_stream_t stream);
 int adc_depth_metrics(const float* output, const float* target, const float* confidence, float threshold, long long n, void* workspace,
                       float* out, adc_stream_t stream);
+/* Precision/recall table of the confidence (metrics.py:103-131 ConfidencePixelwiseThrAverageMeter.evaluate): one pass instead of
+ * num_bins boolean-index passes.  thresholds: device fp32 [num_bins], ascending.  hist: device uint64 [3][num_bins + 1] (zeroed by the
+ * call): bin k collects the valid pixels (target > 0) with exactly k thresholds below their confidence -- [0] pixel count, [1] sum of
+ * absrel = |d - t| / t * 1000 in 2^-16 fixed point, [2] pixels whose absrel is not finite.  Threshold j's figures are the sums over
+ * bins k > j.  Integer accumulation: deterministic. */
+int adc_conf_pr_histogram(const float* depth, const float* confidence, const float* target, long long n, const float* thresholds,
+                          int num_bins, unsigned long long* hist, adc_stream_t stream);
 
 /* ---- descriptor form of the tensor-core convolutions (csrc/conv_tc.cu), used by the BN nets (model_zoo/s2d_u_resnet.py:64-190)
  * kind 0: 3x3 / stride 1 (row-segment kernel, zero-bordered tensors, cin % 16 == 0, cout <= 128; 64 in split mode);
@@ -410,6 +417,12 @@ int adc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* ex
  * uint32 [N]; mask: uint8 [N][HW] (0 / 1).  num_samples = 0 or no valid pixel: mask = keep, like the reference. */
 int adc_uniform_sampling(const float* depth, const unsigned int* seeds, int num_samples, float max_depth, int use_max_depth,
                          unsigned char* mask, int N, long long HW, adc_stream_t stream);
+/* The loader's modality assembly on the device (dataloaders/dataloader_ext.py:544-566 after dense_to_sparse.py:29-48): from the
+ * uploaded frames rgbgt [N][4][HW] = (r, g, b, ground-truth depth) builds the network input input5 [N][5][HW] = (r, g, b, d, w) with
+ * d = gt * mask, w = mask (1.0 / 0.0), mask = the bit-exact UniformSampling mask of frame n under seeds[n].  Only 4 of the 6 planes a
+ * host-side loader ships (5 input + 1 target) cross PCIe; the target is the gt plane of rgbgt. */
+int adc_sample_assemble(const float* rgbgt, const unsigned int* seeds, int num_samples, float max_depth, int use_max_depth, float* input5,
+                        int N, long long HW, adc_stream_t stream);
 
 
 #ifdef __cplusplus

@@ -5,14 +5,16 @@ Two compatibility patches, neither touching reference files:
     ``model_zoo/nconv.py:23`` passes 10 positionals with int padding.
  2. ``model_zoo/nconv_sd.py:45,59,72`` and ``s2d_resnet.py:20`` call ``.cuda()``; on a CPU-only
     box that is made a no-op.
-``/root/reference`` does not exist on the GPU box, so everything that uses this module is
-skipped there (``have_reference()``).
+``/root/reference`` does not exist on the GPU box; there the byte-identical copy staged by ``oracle/make_ref.py`` under
+``oracle/_ref`` (git-ignored, travels with the snapshot) is used.  With neither, everything that uses this module is skipped
+(``have_reference()``).
 """
 import os
 import sys
 import types
 
-REF = "/root/reference"
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+REF = "/root/reference" if os.path.isdir("/root/reference/model_zoo") else _STAGED
 
 
 def have_reference():
@@ -50,3 +52,24 @@ def load():
     import metrics
     import dataloaders.dense_to_sparse as d2s
     return types.SimpleNamespace(nconv=nconv, nconv_sd=nconv_sd, cdf=cdf, s2du=s2du, s2d=s2d, metrics=metrics, d2s=d2s)
+
+
+def load_trainer():
+    """The reference's ``trainer`` module (trainer.py imports utils.py, which imports matplotlib: absent in this image and only used
+    for the validation image grids, so it is stubbed in sys.modules).  Also returns the namespace of ``load()``."""
+    ns = load()
+    import importlib.machinery
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.figure", "matplotlib.backends", "matplotlib.backends.backend_agg"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+            sys.modules[name] = m
+    plt = sys.modules["matplotlib.pyplot"]
+    if not hasattr(plt, "cm"):
+        plt.cm = types.SimpleNamespace(viridis=None, jet=None, binary=None)
+    sys.modules["matplotlib"].use = lambda *a, **k: None
+    sys.modules["matplotlib.backends.backend_agg"].FigureCanvasAgg = type("FigureCanvasAgg", (), {})
+    sys.modules["matplotlib.figure"].Figure = type("Figure", (), {})
+    sys.modules["matplotlib"].pyplot = plt
+    import trainer
+    return trainer, ns

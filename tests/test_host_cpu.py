@@ -98,3 +98,48 @@ def test_sampling_mask_bit_exact():
     for s in (0, 7, 1234):
         np.random.seed(s)
         assert np.array_equal(np.flatnonzero(UniformSampling(500, np.inf).dense_to_sparse(None, depth)), G["mask_seed%d" % s])
+
+
+@pytest.mark.skipif(not reference_shim.have_reference(), reason="reference not available")
+@pytest.mark.parametrize("args", [
+    ("rgbd", "dc1_only", "ged_depthcompnet", ""),
+    ("rgbdw", "dc1-cf1-ln1", "ged_depthcompnet", "", "cbr3-c1", "", "ged_depthcompnet", ""),
+    ("rgbd", "dc1-cf1-ln0", "gudepthcompnet18", "", "cbr3-c1", "", "ged_depthcompnet", ""),
+    ("rgbd", "dc1_only", "gms_depthcompnet", ""),
+    ("rgbd", "dc1_only", "resnet18", ""),
+], ids=["ged", "ged_cf_ln", "gud_cf_ln0", "gms", "resnet18"])
+def test_checkpoint_wire_format_round_trip(tmp_path, args):
+    """SURVEY 8f-3 (trainer.py:175-184, confidence_depth_framework.py:84-110,161-187, utils.py:17-26): the reference's get_state ->
+    torch.save -> this package's create_model_from_state restores every tensor bit for bit (post-softplus NConv weights, BN buffers
+    and num_batches_tracked included), the reverse direction too, and `file:key` partial loading picks one sub-net."""
+    import contextlib
+    import io
+    import torch
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    ns = reference_shim.load()
+    q = contextlib.redirect_stdout(io.StringIO())
+    with q:
+        torch.manual_seed(3)
+        fr, fn = ns.cdf.ConfidenceDepthFrameworkFactory(), mc.ConfidenceDepthFrameworkFactory()
+        mr = fr.create_model(*args)
+        for p in mr.parameters():                       # a "trained" state: every tensor distinct from its initialisation
+            p.data.add_(0.01 * torch.randn_like(p))
+        ck = str(tmp_path / "model_best.pth.tar")
+        torch.save({"model_state": fr.get_state(mr), "epoch": 3}, ck)
+        mn = fn.create_model_from_state(torch.load(ck)["model_state"])
+    sr, sn = mr.state_dict(), mn.state_dict()
+    assert list(sr.keys()) == list(sn.keys())
+    for k in sr:
+        assert sr[k].dtype == sn[k].dtype and torch.equal(sr[k], sn[k]), k
+    for attr in ("input_type", "overall_arch", "dc_arch", "conf_arch", "loss_dc_arch", "input_size"):
+        assert getattr(mr, attr) == getattr(mn, attr), attr
+    with q:
+        ck2 = str(tmp_path / "from_new.pth.tar")
+        torch.save({"model_state": fn.get_state(mn)}, ck2)
+        back = fr.create_model_from_state(torch.load(ck2)["model_state"])
+        part = fn.create_model(args[0], "dc1_only", args[2], ck + ":dc_weights")
+    for k, v in back.state_dict().items():
+        assert torch.equal(v, sr[k]), k
+    for k, v in part.dc_model.state_dict().items():
+        if v.shape == mr.dc_model.state_dict()[k].shape:
+            assert torch.equal(v, mr.dc_model.state_dict()[k]), k
