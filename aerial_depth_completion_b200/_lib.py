@@ -162,6 +162,13 @@ SIGNATURES = {
     "adc_im2col3x3_pack": (c_int, [_vp, c_int, c_ll, _vp, c_int, c_ll, _vp, c_int, c_ll, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_nchw_to_nhwc_f32": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_adam_step_dev": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_ll, _vp]),
+    "adc_im2col_kxk_pack": (c_int, [_vp, c_ll, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_maxpool3x3s2_fwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_maxpool3x3s2_bwd": (c_int, [_vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_pixel_shuffle_f32": (c_int, [_vp, c_int, c_int, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_pixel_unshuffle_pair": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_bilinear_ac_fwd": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp, c_int, c_int, _vp]),
+    "adc_bilinear_ac_bwd": (c_int, [_vp, c_int, c_int, c_int, c_int, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_uniform_sampling": (c_int, [_vp, _vp, c_int, ctypes.c_float, c_int, _vp, c_int, c_ll, _vp]),
     "adc_sample_assemble": (c_int, [_vp, _vp, c_int, ctypes.c_float, c_int, _vp, c_int, c_ll, _vp]),
     "adc_conf_pr_histogram": (c_int, [_vp, _vp, _vp, c_ll, _vp, c_int, _vp, _vp]),

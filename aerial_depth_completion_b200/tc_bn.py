@@ -278,6 +278,109 @@ def dot_head_backward(x, x_off, C, weight, gy, G, g_off, accumulate, gy_extra=No
     return gw.reshape(oc, C, 1, 1), gb
 
 
+# ---- a ResNet stage of two BasicBlocks (torchvision names conv1 / bn1 / conv2 / bn2 / downsample.{0,1}) ----------------------------------
+# Shared by the U-Net body below and by tc_s2d (S2DResNet).  ``P`` is a plan: P.y / P.x / P.g / P.d hand out the fp32 result, activation,
+# fp32 gradient and gradient-operand buffers of a (key, level); P.S keeps the BatchNorm states.
+def stage_prep_fwd(wp, st, name, cin, cout):
+    for bi in (0, 1):
+        blk = st[bi]
+        wp.fwd((name, bi, 1), blk.conv1.weight, cin if bi == 0 else cout)
+        wp.fwd((name, bi, 2), blk.conv2.weight, cout)
+        if blk.downsample is not None:
+            wp.fwd((name, bi, "d"), embed_1x1(blk.downsample[0].weight), cin)
+
+
+def stage_forward(P, st, name, lvl, cin, cout, stride, xin, xoff, dst, doff, W, training):
+    """xin[:, xoff:xoff+cin] -> dst[:, doff:doff+cout] (level ``lvl`` = the stage's OUTPUT level)."""
+    for bi in (0, 1):
+        blk = st[bi]
+        ci = cin if bi == 0 else cout
+        s_ = stride if bi == 0 else 1
+        Ya = P.y((name, bi, 1), lvl, cout)
+        if s_ == 1:
+            fwd_s1(xin, xoff, ci, W, (name, bi, 1), Ya, 0, cout)
+        else:
+            fwd_box(xin, xoff, ci, W, (name, bi, 1), Ya, 0, cout, 2)
+        hmid = P.x((name, bi, "h"), lvl, cout)
+        P.S[(name, bi, 1)] = bn_forward(Ya, 0, cout, blk.bn1, training, hmid, 0, RELU)
+        Yb = P.y((name, bi, 2), lvl, cout)
+        fwd_s1(hmid, 0, cout, W, (name, bi, 2), Yb, 0, cout)
+        if blk.downsample is not None:
+            Yd = P.y((name, bi, "d"), lvl, cout)
+            fwd_box(xin, xoff, ci, W, (name, bi, "d"), Yd, 0, cout, s_, kind=K_1X1S2 if s_ == 2 else K_BOX)
+            sc = P.x((name, bi, "sc"), lvl, cout)
+            P.S[(name, bi, "d")] = bn_forward(Yd, 0, cout, blk.downsample[1], training, sc, 0, NONE)
+            res, roff = sc, 0
+        else:
+            res, roff = xin, xoff
+        if bi == 0:
+            o, ooff = P.x((name, "b0"), lvl, cout), 0
+        else:
+            o, ooff = dst, doff
+        P.S[(name, bi, 2)] = bn_forward(Yb, 0, cout, blk.bn2, training, o, ooff, RELU, res=res, res_off=roff)
+        xin, xoff = o, ooff
+
+
+def stage_prep_bwd(wp, st, name, cin, cout, stride):
+    for bi in (0, 1):
+        blk = st[bi]
+        s_ = stride if bi == 0 else 1
+        wp.transposed((name, bi, 1), blk.conv1.weight, dense._r64(cout), flip=(s_ == 1))
+        wp.transposed((name, bi, 2), blk.conv2.weight, dense._r64(cout), flip=True)
+        if blk.downsample is not None:
+            wp.transposed((name, bi, "d"), embed_1x1(blk.downsample[0].weight), dense._r64(cout), flip=False)
+
+
+def stage_backward(P, st, name, lvl, cin, cout, stride, xin0, xoff0, Gin0, goff0, gin0_written, out, ooff_last, Gout, gooff_last, W, grads,
+                   prefix):
+    """Backward of stage_forward.  Gout[:, gooff_last:...] holds dL/d(stage output); the input gradient is written (or, when
+    ``gin0_written``, accumulated) into Gin0[:, goff0:goff0+cin]; parameter gradients land in ``grads`` under ``prefix``."""
+    for bi in (1, 0):
+        blk = st[bi]
+        ci = cin if bi == 0 else cout
+        s_ = stride if bi == 0 else 1
+        if bi == 1:
+            o, ooff, Go, gooff = out, ooff_last, Gout, gooff_last
+            xin, xoff = P.X[(name, "b0")], 0
+            Gin, goff, gin_written = P.g((name, "b0"), lvl, cout), 0, False
+        else:
+            o, ooff, Go, gooff = P.X[(name, "b0")], 0, P.G[(name, "b0")], 0
+            xin, xoff, Gin, goff, gin_written = xin0, xoff0, Gin0, goff0, gin0_written
+        pre = prefix + "%d." % bi
+        # bn2 (+ residual) + ReLU
+        Db = P.d((name, bi, 2), lvl, cout)
+        if blk.downsample is not None:
+            Gsc = P.g((name, bi, "sc"), lvl, cout)
+            gg, gbeta = bn_backward(Go, gooff, P.Y[(name, bi, 2)], 0, o, ooff, P.S[(name, bi, 2)], RELU, Db, 0, cout, gres=Gsc, gres_off=0,
+                                    gres_accum=False)
+        else:
+            gg, gbeta = bn_backward(Go, gooff, P.Y[(name, bi, 2)], 0, o, ooff, P.S[(name, bi, 2)], RELU, Db, 0, cout, gres=Gin, gres_off=goff,
+                                    gres_accum=gin_written)
+            gin_written = True
+        grads[pre + "bn2.weight"], grads[pre + "bn2.bias"] = gg, gbeta
+        hmid = P.X[(name, bi, "h")]
+        grads[pre + "conv2.weight"] = wgrad_s1(Db, 0, cout, hmid, 0, cout)
+        Gh = P.g((name, bi, "h"), lvl, cout)
+        dgrad_s1(Db, dense._r64(cout), W, (name, bi, 2), Gh, 0, cout, False)
+        # bn1 + ReLU
+        Da = P.d((name, bi, 1), lvl, cout)
+        gg, gbeta = bn_backward(Gh, 0, P.Y[(name, bi, 1)], 0, hmid, 0, P.S[(name, bi, 1)], RELU, Da, 0, cout)
+        grads[pre + "bn1.weight"], grads[pre + "bn1.bias"] = gg, gbeta
+        if s_ == 1:
+            grads[pre + "conv1.weight"] = wgrad_s1(Da, 0, cout, xin, xoff, ci)
+            dgrad_s1(Da, dense._r64(cout), W, (name, bi, 1), Gin, goff, ci, gin_written)
+        else:
+            grads[pre + "conv1.weight"] = wgrad_box(Da, 0, cout, xin, xoff, ci, 2)
+            dgrad_s2(Da, dense._r64(cout), W, (name, bi, 1), Gin, goff, ci, gin_written)
+        gin_written = True
+        if blk.downsample is not None:
+            Dd = P.d((name, bi, "d"), lvl, cout)
+            gg, gbeta = bn_backward(P.G[(name, bi, "sc")], 0, P.Y[(name, bi, "d")], 0, None, 0, P.S[(name, bi, "d")], NONE, Dd, 0, cout)
+            grads[pre + "downsample.1.weight"], grads[pre + "downsample.1.bias"] = gg, gbeta
+            grads[pre + "downsample.0.weight"] = wgrad_1x1_box(Dd, 0, cout, xin, xoff, ci, s_)
+            dgrad_s2(Dd, dense._r64(cout), W, (name, bi, "d"), Gin, goff, ci, True, kind=K_1X1S2_DGRAD)
+
+
 # ---- the ResNet-18 U-Net body ---------------------------------------------------------------------------------------------------------
 class _Plan:
     """Every buffer of one (batch, height, width, precision) configuration of an S2DUResNet."""
@@ -385,13 +488,7 @@ class S2DUBodyTC(torch.autograd.Function):
         w1e[:, :9 * C5, 1, 1] = w1.reshape(64, 9 * C5)
         wp.fwd("stem", w1e, 64)
         for name, lvl, cin, cout, stride in _STAGES:
-            st = getattr(net, name)
-            for bi in (0, 1):
-                blk = st[bi]
-                wp.fwd((name, bi, 1), blk.conv1.weight, cin if bi == 0 else cout)
-                wp.fwd((name, bi, 2), blk.conv2.weight, cout)
-                if blk.downsample is not None:
-                    wp.fwd((name, bi, "d"), embed_1x1(blk.downsample[0].weight), cin)
+            stage_prep_fwd(wp, getattr(net, name), name, cin, cout)
         wp.fwd("conv6", net.conv6[0].weight, 512)
         for name, lvl, cin, cout in _CONVT:
             # the ConvTranspose2d weight [in][out][3][3] IS the weight of the stride-2 convolution this layer is the data gradient of
@@ -413,35 +510,9 @@ class S2DUBodyTC(torch.autograd.Function):
         # ---- encoder: four stages of two BasicBlocks; stage output lands in the decoder's concat buffer
         xin, xoff = P.cat_last, 64
         for name, lvl, cin, cout, stride in _STAGES:
-            st = getattr(net, name)
             dst, doff = P.cat[int(name[-1])], {2: 64, 3: 64, 4: 128, 5: 256}[int(name[-1])]
-            for bi in (0, 1):
-                blk = st[bi]
-                ci = cin if bi == 0 else cout
-                s_ = stride if bi == 0 else 1
-                Ya = P.y((name, bi, 1), lvl, cout)
-                if s_ == 1:
-                    fwd_s1(xin, xoff, ci, W, (name, bi, 1), Ya, 0, cout)
-                else:
-                    fwd_box(xin, xoff, ci, W, (name, bi, 1), Ya, 0, cout, 2)
-                hmid = P.x((name, bi, "h"), lvl, cout)
-                P.S[(name, bi, 1)] = bn_forward(Ya, 0, cout, blk.bn1, training, hmid, 0, RELU)
-                Yb = P.y((name, bi, 2), lvl, cout)
-                fwd_s1(hmid, 0, cout, W, (name, bi, 2), Yb, 0, cout)
-                if blk.downsample is not None:
-                    Yd = P.y((name, bi, "d"), lvl, cout)
-                    fwd_box(xin, xoff, ci, W, (name, bi, "d"), Yd, 0, cout, s_, kind=K_1X1S2 if s_ == 2 else K_BOX)
-                    sc = P.x((name, bi, "sc"), lvl, cout)
-                    P.S[(name, bi, "d")] = bn_forward(Yd, 0, cout, blk.downsample[1], training, sc, 0, NONE)
-                    res, roff = sc, 0
-                else:
-                    res, roff = xin, xoff
-                if bi == 0:
-                    o, ooff = P.x((name, "b0"), lvl, cout), 0
-                else:
-                    o, ooff = dst, doff
-                P.S[(name, bi, 2)] = bn_forward(Yb, 0, cout, blk.bn2, training, o, ooff, RELU, res=res, res_off=roff)
-                xin, xoff = o, ooff
+            stage_forward(P, getattr(net, name), name, lvl, cin, cout, stride, xin, xoff, dst, doff, W, training)
+            xin, xoff = dst, doff
         # ---- bottleneck and decoder
         Y6 = P.y("conv6", 4, 512)
         fwd_box(P.cat[5], 256, 512, W, "conv6", Y6, 0, 512, 2)
@@ -481,15 +552,7 @@ class S2DUBodyTC(torch.autograd.Function):
         # ---- weights of every data gradient: transposed views of the same Parameters
         wp = WPrep()
         for name, lvl, cin, cout, stride in _STAGES:
-            st = getattr(net, name)
-            for bi in (0, 1):
-                blk = st[bi]
-                ci = cin if bi == 0 else cout
-                s_ = stride if bi == 0 else 1
-                wp.transposed((name, bi, 1), blk.conv1.weight, dense._r64(cout), flip=(s_ == 1))
-                wp.transposed((name, bi, 2), blk.conv2.weight, dense._r64(cout), flip=True)
-                if blk.downsample is not None:
-                    wp.transposed((name, bi, "d"), embed_1x1(blk.downsample[0].weight), dense._r64(cout), flip=False)
+            stage_prep_bwd(wp, getattr(net, name), name, cin, cout, stride)
         wp.transposed("conv6", net.conv6[0].weight, 512, flip=False)
         for name, lvl, cin, cout in _CONVT:
             wp.fwd(name, getattr(net, name)[0].weight, dense._r64(cout))       # ConvT weight [in][out] read as a convolution [Cout = in][Cin = out]
@@ -539,56 +602,13 @@ class S2DUBodyTC(torch.autograd.Function):
         # ---- encoder stages, deepest first
         for name, lvl, cin, cout, stride in reversed(_STAGES):
             k = int(name[-1])
-            st = getattr(net, name)
             doff = {2: 64, 3: 64, 4: 128, 5: 256}[k]
             if k == 2:
                 xin0, xoff0, Gin0, goff0 = P.cat_last, 64, Gl, 64
             else:
                 xin0, xoff0, Gin0, goff0 = P.cat[k - 1], {3: 64, 4: 64, 5: 128}[k], Gk[k - 1], {3: 64, 4: 64, 5: 128}[k]
-            for bi in (1, 0):
-                blk = st[bi]
-                ci = cin if bi == 0 else cout
-                s_ = stride if bi == 0 else 1
-                if bi == 1:
-                    o, ooff, Go, gooff = P.cat[k], doff, Gk[k], doff
-                    xin, xoff = P.X[(name, "b0")], 0
-                    Gin, goff, gin_written = P.g((name, "b0"), lvl, cout), 0, False
-                else:
-                    o, ooff, Go, gooff = P.X[(name, "b0")], 0, P.G[(name, "b0")], 0
-                    xin, xoff, Gin, goff, gin_written = xin0, xoff0, Gin0, goff0, True
-                pre = name + ".%d." % bi
-                # bn2 (+ residual) + ReLU
-                Db = P.d((name, bi, 2), lvl, cout)
-                if blk.downsample is not None:
-                    Gsc = P.g((name, bi, "sc"), lvl, cout)
-                    gg, gbeta = bn_backward(Go, gooff, P.Y[(name, bi, 2)], 0, o, ooff, P.S[(name, bi, 2)], RELU, Db, 0, cout, gres=Gsc, gres_off=0,
-                                            gres_accum=False)
-                else:
-                    gg, gbeta = bn_backward(Go, gooff, P.Y[(name, bi, 2)], 0, o, ooff, P.S[(name, bi, 2)], RELU, Db, 0, cout, gres=Gin, gres_off=goff,
-                                            gres_accum=gin_written)
-                    gin_written = True
-                grads[pre + "bn2.weight"], grads[pre + "bn2.bias"] = gg, gbeta
-                hmid = P.X[(name, bi, "h")]
-                grads[pre + "conv2.weight"] = wgrad_s1(Db, 0, cout, hmid, 0, cout)
-                Gh = P.g((name, bi, "h"), lvl, cout)
-                dgrad_s1(Db, dense._r64(cout), W, (name, bi, 2), Gh, 0, cout, False)
-                # bn1 + ReLU
-                Da = P.d((name, bi, 1), lvl, cout)
-                gg, gbeta = bn_backward(Gh, 0, P.Y[(name, bi, 1)], 0, hmid, 0, P.S[(name, bi, 1)], RELU, Da, 0, cout)
-                grads[pre + "bn1.weight"], grads[pre + "bn1.bias"] = gg, gbeta
-                if s_ == 1:
-                    grads[pre + "conv1.weight"] = wgrad_s1(Da, 0, cout, xin, xoff, ci)
-                    dgrad_s1(Da, dense._r64(cout), W, (name, bi, 1), Gin, goff, ci, gin_written)
-                else:
-                    grads[pre + "conv1.weight"] = wgrad_box(Da, 0, cout, xin, xoff, ci, 2)
-                    dgrad_s2(Da, dense._r64(cout), W, (name, bi, 1), Gin, goff, ci, gin_written)
-                gin_written = True
-                if blk.downsample is not None:
-                    Dd = P.d((name, bi, "d"), lvl, cout)
-                    gg, gbeta = bn_backward(P.G[(name, bi, "sc")], 0, P.Y[(name, bi, "d")], 0, None, 0, P.S[(name, bi, "d")], NONE, Dd, 0, cout)
-                    grads[pre + "downsample.1.weight"], grads[pre + "downsample.1.bias"] = gg, gbeta
-                    grads[pre + "downsample.0.weight"] = wgrad_1x1_box(Dd, 0, cout, xin, xoff, ci, s_)
-                    dgrad_s2(Dd, dense._r64(cout), W, (name, bi, "d"), Gin, goff, ci, True, kind=K_1X1S2_DGRAD)
+            stage_backward(P, getattr(net, name), name, lvl, cin, cout, stride, xin0, xoff0, Gin0, goff0, True, P.cat[k], doff, Gk[k], doff, W,
+                           grads, name + ".")
         # ---- stems
         D1 = P.d("stem", 0, 64)
         ro = 0

@@ -112,12 +112,20 @@ def _dgrad_s1(G, weight, out, lo, hi, prepped=None):
         dense.conv3x3_tc(G, G.cs, wp, None, b - a, 1, 0, out=out, out_off=a, out_zero_to=64 if a + 64 <= out.cs else 0)
 
 
+def _tap_mix(maps, w):
+    """out[q, ..., s] = sum_t maps[q, s, t] * w[..., t] for the constant 0/1 tap maps of dense.quad_maps ([4, 9, 9]) and a weight tensor
+    whose last dimension is the 9 original taps: a broadcast product and a reduction over <= 4 live terms (not a GEMM)."""
+    lead = w.dim() - 1
+    m = maps.reshape((4,) + (1,) * lead + (9, 9))
+    return (w.reshape((1,) + tuple(w.shape[:-1]) + (1, 9)) * m).sum(-1)
+
+
 def _quad_head_weights(w10):
     """[oc, 33, 3, 3] -> [4*oc, 32, 3, 3]: per parity (py, px) of the output pixel, the taps of conv10 that read the same pixel of
     x9 through the 2x nearest up-sampling, summed (row (2py+px)*oc + o)."""
     oc = w10.shape[0]
     up, _ = dense.quad_maps(w10.device)
-    return torch.einsum("qst,oct->qocs", up, w10[:, :32].reshape(oc, 32, 9)).reshape(4 * oc, 32, 3, 3)
+    return _tap_mix(up, w10[:, :32].reshape(oc, 32, 9)).reshape(4 * oc, 32, 3, 3)
 
 
 def _quad_head_backward(P, b, w10, g_x10, x10, x0_d, g_lli, need_x0d):
@@ -133,7 +141,7 @@ def _quad_head_backward(P, b, w10, g_x10, x10, x0_d, g_lli, need_x0d):
     gb9 = dense.quad_head_dgrad(P.x9, gq, _quad_head_weights(w10), b["G9"], extra)
     dwq = dense.quad_head_wgrad(P.x9, gq, oc)                             # [4*oc, 32, 3, 3]
     up, _ = dense.quad_maps(w10.device)
-    dw = torch.einsum("qst,qocs->oct", up, dwq.reshape(4, oc, 32, 9)).reshape(oc, 32, 3, 3)
+    dw = (dwq.reshape(4, oc, 32, 9, 1) * up.reshape(4, 1, 1, 9, 9)).sum((0, 3)).reshape(oc, 32, 3, 3)      # adjoint of _tap_mix
     dw = torch.cat((dw, s[:, :9].reshape(oc, 1, 3, 3)), 1)
     g_x0d = dense.ged_head_bwd_x0d(g_x10, x10, g_lli, w10) if need_x0d else None
     return g_x0d, dw, s[:, 9].contiguous(), gb9
@@ -238,11 +246,11 @@ class GEDDenseTC(torch.autograd.Function):
         _, s2 = dense.quad_maps(dev)
         masks, mask_all = dense.quad_s2_tap_masks()
         for i in (4, 3, 2, 1):
-            wq = torch.einsum("qst,oit->qios", s2, W[i].reshape(80, 80, 9)).contiguous().reshape(4, 80, 80, 3, 3)
+            wq = _tap_mix(s2, W[i].reshape(80, 80, 9)).permute(0, 2, 1, 3).contiguous().reshape(4, 80, 80, 3, 3)
             add(i, [(wq[q], 0, 128, 0, 80) for q in range(4)])
         # conv1's data gradient is needed for xout_d and cout_d only (channels 0 and 4 of its input): quad form = a stride-1
         # convolution of G1 at ITS resolution with 4 parity x 2 output channels (dense.quad_maps 's2')
-        Wd = torch.einsum("qst,ckt->qkcs", s2, torch.stack((W[0][:, 0], W[0][:, 4]), 1).reshape(80, 2, 9)).reshape(8, 80, 3, 3)
+        Wd = _tap_mix(s2, torch.stack((W[0][:, 0], W[0][:, 4]), 1).reshape(80, 2, 9)).permute(0, 2, 1, 3).reshape(8, 80, 3, 3)
         add(0, [(Wd, 0, 128, 0, 80)])
         prepped = dense.prep_conv3x3_weights_batch(reqs)
         wp = {k: prepped[a:b_] for k, (a, b_) in where.items()}

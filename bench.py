@@ -79,29 +79,71 @@ def peaks():
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm restated in oracle/ (the Python reference cannot travel to the GPU box)
 # ---------------------------------------------------------------------------------------------------------------------
+def _reference_root():
+    """/root/reference (build container) or the byte-identical copy staged by oracle/make_ref.py (oracle/_ref: travels to the GPU box)."""
+    for p in ("/root/reference", os.path.join(ROOT, "oracle", "_ref")):
+        if os.path.isdir(os.path.join(p, "model_zoo")):
+            return p
+    return None
+
+
+def _load_reference():
+    """The unmodified reference modules through the two-patch shim of SURVEY.md 8c (tests/reference_shim.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import reference_shim
+    return reference_shim.load()
+
+
 def cpu_reference_run(steps, warmup, frames):
-    """GED dc1_only train step on the host cores with all threads: returns (frames/s, ms/step, cores, frames)."""
+    """GED dc1_only train step (forward + masked-L2 + zero_grad + backward + Adam) on the host cores with all threads: returns
+    (frames/s, ms/step, cores, frames, kind).  kind "reference" = the UNMODIFIED reference modules (model_zoo/*, MaskedMSELoss) on CPU
+    torch when the reference is present (/root/reference or oracle/_ref); "port" = the oracle's restatement otherwise."""
+    import contextlib
+    import io
     import torch
-    from oracle import loss_metrics_oracle as lm
-    from oracle import nets_oracle as nets
     from oracle import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    template = ged_template()
-    S = synth.seeded_state({"dc_model." + k: v for k, v in template.items()}, seed=0)
-    for k in S:
-        S[k].requires_grad_(True)
-    params = [S[k] for k in S]
-    opt = torch.optim.Adam(params, lr=1e-5)
     inp, tgt = synth.synth_frames(frames, H, W, seed=1234)
+    if _reference_root() is not None:
+        assert not torch.cuda.is_available(), "the CPU arm runs with CUDA_VISIBLE_DEVICES='' (the reference hard-codes .cuda())"
+        ns = _load_reference()
+        torch.manual_seed(0)
+        f = ns.cdf.ConfidenceDepthFrameworkFactory()
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = f.create_model("rgbd", "dc1_only", "ged_depthcompnet", "")
+            model, params = f.to_device(model)
+            model.train()
+        crit, _ = f.create_loss("l2", False, 0.5)
+        opt = torch.optim.Adam(params, lr=1e-5)
+        inp, tgt = inp.float(), tgt.float()
 
-    def step():
-        d1, _, _ = nets.framework_forward(S, inp, "dc1_only", "ged_depthcompnet", 4, training=True)
-        loss = lm.masked_loss("l2", d1, tgt)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
-        return float(loss.detach())
+        def step():
+            with contextlib.redirect_stdout(io.StringIO()):
+                d1, _, _ = model(inp)
+            loss = crit(inp, d1[:, 0:1], tgt, 0)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        kind = "reference"
+    else:
+        from oracle import loss_metrics_oracle as lm
+        from oracle import nets_oracle as nets
+        template = ged_template()
+        S = synth.seeded_state({"dc_model." + k: v for k, v in template.items()}, seed=0)
+        for k in S:
+            S[k].requires_grad_(True)
+        opt = torch.optim.Adam([S[k] for k in S], lr=1e-5)
+
+        def step():
+            d1, _, _ = nets.framework_forward(S, inp, "dc1_only", "ged_depthcompnet", 4, training=True)
+            loss = lm.masked_loss("l2", d1, tgt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        kind = "port"
 
     for _ in range(warmup):
         step()
@@ -109,7 +151,12 @@ def cpu_reference_run(steps, warmup, frames):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return frames * steps / dt, dt / steps * 1e3, cores, frames
+    return frames * steps / dt, dt / steps * 1e3, cores, frames, kind
+
+
+_KIND_NOTE = {"reference": "the UNMODIFIED reference (model_zoo.ConfidenceDepthFrameworkFactory, MaskedMSELoss, torch.optim.Adam) on CPU torch, "
+                           "all host threads",
+              "port": "torch CPU ops (oracle/, the reference's algorithm restated; no staged reference on this box)"}
 
 
 def ged_template():
@@ -131,18 +178,34 @@ def reference_arm(args):
     # same workload, same batch per step, exactly --steps / --warmup steps (32 frames take ~1.5 s on 16 cores)
     frames = args.cpu_frames or args.batch
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    fps, ms, cores, frames = cpu_reference_run(steps, warmup, frames)
+    fps, ms, cores, frames, kind = cpu_reference_run(steps, warmup, frames)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "precision": "fp32", "batch_per_gpu": frames, "global_batch": frames, "device": "host CPU"},
-        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d timed steps of %d frame(s) of the same workload with torch CPU ops (oracle/, the reference's "
-                                   "algorithm restated; the Python reference cannot travel to the GPU box)" % (steps, frames)},
+        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": "%d timed steps of %d frame(s) of the same workload: %s" % (steps, frames, _KIND_NOTE[kind])},
         "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(frames, steps=3, warmup=1):
+    """The CPU arm in its own process with CUDA hidden (the reference's pyramid hard-codes .cuda(); the shim makes it a no-op only when
+    no device is visible): returns the parsed cpu_baseline object of that run, or None."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
+                            "--cpu-frames", str(frames)], capture_output=True, text=True, timeout=600, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+    except Exception:
+        pass
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -258,17 +321,20 @@ def b200_arm(args):
     pool_n = 8
     g = torch.Generator().manual_seed(1234 + rank)
     sampler = UniformSampling(500, np.inf)
-    host_in, host_tg = [], []
+    host_in, host_tg, host_raw = [], [], []
     for i in range(pool_n):
         rgb = torch.rand(B, 3, H, W, generator=g)
         gt = torch.rand(B, 1, H, W, generator=g) * 9.0 + 1.0
-        masks = []
+        masks, seeds = [], []
         for b in range(B):
-            np.random.seed(1234 + 1000 * rank + i * B + b)
+            seeds.append(1234 + 1000 * rank + i * B + b)
+            np.random.seed(seeds[-1])
             masks.append(sampler.dense_to_sparse(None, gt[b, 0].numpy()))
         mask = torch.from_numpy(np.stack(masks)).unsqueeze(1).float()
         host_in.append(torch.cat((rgb, gt * mask, mask), 1).pin_memory())
         host_tg.append(gt.pin_memory())
+        # what a loader has to ship when the sparse depth is drawn on the device: rgb + gt + one seed per frame
+        host_raw.append((torch.cat((rgb, gt), 1).pin_memory(), torch.tensor(seeds, dtype=torch.int32).pin_memory()))
     dev_in = [t.to(dev) for t in host_in]
     dev_tg = [t.to(dev) for t in host_tg]
     pool_mb = sum(t.numel() * 4 for t in dev_in + dev_tg) / 1e6
@@ -317,19 +383,25 @@ def b200_arm(args):
         launches = launches_per_step * args.steps
     # e2e: every step's frames come from pinned host memory and every step's loss is read back on the host, through the public
     # feeder (parallel.HostFeeder: copy of batch i+1 overlaps step i, the loss of step i is read one step later)
-    feeder = parallel.HostFeeder(trainer, host_in[0], host_tg[0])
-    feeder.run([(host_in[i % pool_n], host_tg[i % pool_n]) for i in range(min(3, args.warmup))])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_losses = feeder.run([(host_in[i % pool_n], host_tg[i % pool_n]) for i in range(args.steps)])
-    e1.record()
-    barrier()
-    t_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t_e2e.item())
-    assert len(e2e_losses) == args.steps and all(v == v for v in e2e_losses), "e2e: a step's loss was not read back"
+    def run_feeder(feeder, batches):
+        feeder.run([batches[i % pool_n] for i in range(min(3, args.warmup))])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        losses = feeder.run([batches[i % pool_n] for i in range(args.steps)])
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert len(losses) == args.steps and all(v == v for v in losses), "e2e: a step's loss was not read back"
+        return float(t.item()), losses
+
+    # headline e2e: DeviceAssemblyFeeder -- rgb + gt + seeds cross PCIe, the UniformSampling masks and the 5-channel input are built
+    # on the device (bit-identical to the host-assembled batches: tests/test_gpu_feeder.py), copy + assembly of batch i+1 overlap step i
+    ms_e2e, e2e_losses = run_feeder(parallel.DeviceAssemblyFeeder(trainer, host_raw[0][0], 500), host_raw)
+    # the same with the loader doing the assembly on the host (6 planes per frame over PCIe), for comparison
+    ms_e2e_host, _ = run_feeder(parallel.HostFeeder(trainer, host_in[0], host_tg[0]), list(zip(host_in, host_tg)))
     ms_serial = timed(from_host, min(args.steps, 5)) / min(args.steps, 5)      # the reference trainer's order: copy, step, read, next
     sampler_thread.stop_flag = True
 
@@ -356,10 +428,15 @@ def b200_arm(args):
                    "launch": "eager" if args.no_graph else "one CUDA graph per step (forward+loss+backward+allreduce+adam)",
                    "timing": "CUDA events, barrier + synchronize on both sides, max over ranks"},
         "clocks": sampler_thread.summary(),
-        "e2e": {"value": round(frames / ms_e2e * 1e3, 2), "unit": "frames/s", "h2d_bytes_per_step": B * 6 * H * W * 4,
+        "e2e": {"value": round(frames / ms_e2e * 1e3, 2), "unit": "frames/s", "h2d_bytes_per_step": B * 4 * H * W * 4 + B * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4),
-                "how": "parallel.HostFeeder: pinned-host batch i+1 copied on a copy stream while step i runs, loss of step i read "
-                       "on the host one step later; every batch copied, every loss read, all inside the timed region",
+                "how": "parallel.DeviceAssemblyFeeder: pinned-host (r, g, b, gt) planes + one int32 seed per frame copied on a copy stream "
+                       "while step i runs; adc_sample_assemble draws the reference-exact UniformSampling(500) masks and builds the 5-channel "
+                       "input on the device behind the copy; loss of step i read on the host one step later; every batch copied, every "
+                       "loss read, all inside the timed region",
+                "host_assembled": {"value": round(frames / ms_e2e_host * 1e3, 2), "ms_per_step": round(ms_e2e_host / args.steps, 4),
+                                   "h2d_bytes_per_step": B * 6 * H * W * 4,
+                                   "how": "parallel.HostFeeder: 5 input planes + target assembled by the loader on the host"},
                 "serialised_ms_per_step": round(ms_serial, 4)},
         "gpu_launches": int(launches),
     }
@@ -369,7 +446,17 @@ def b200_arm(args):
                             "frac": round(dom["gbs"] / peak, 4), "traffic": (TRAFFIC.get(dom["name"]) or {}).get("dram_bytes_per_launch"),
                             "traffic_source": (TRAFFIC.get(dom["name"]) or {}).get("source"), "kernel": dom["name"],
                             "launch_us": round(dom["us"], 2), "algorithmic_mb_per_launch": round(dom["mb"], 2),
-                            "peak_source": peak_src, "nconv_kernels": roof["table"]}
+                            "peak_source": peak_src, "nconv_kernels": roof["table"],
+                            "nconv_layers_survey_byte_model": roof.get("layers")}
+        td = roof.get("tensor_dominant")
+        if td:
+            pk = PEAKS.get("bf16_tflops_sustained") or 1389.3
+            ach = td["flop_per_step"] / td["us_per_step"] / 1e6
+            line["roofline"]["tensor"] = {
+                "bound": "tensor", "kernel": td["name"], "achieved": round(ach, 1), "peak": pk, "unit": "TFLOP/s", "frac": round(ach / pk, 4),
+                "us_per_step": round(td["us_per_step"], 1),
+                "basis": "FLOPs of the launched problem (2*M*9*Cin_padded*Cout per launch, one per product: the second MMA of bf16x3 is not "
+                         "counted) over the CUDA-event time of the step-dominant kernel; peak = sustained bf16 (MEASURED_PEAKS.json)"}
         if roof.get("tensor"):
             alg = ged_algorithmic_flops(B)
             mult = 2 if args.precision == "bf16x3" else 1
@@ -391,12 +478,101 @@ def b200_arm(args):
             line["extra"]["gudepthcompnet18_dc1_cf1_ln0_240x320"] = gudepthcompnet_training(dev)
         except Exception as e:
             line["extra"]["gudepthcompnet18_dc1_cf1_ln0_240x320"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    if world == 1 and not args.no_extras:
+        try:
+            line["extra"]["reference_on_gpu_cudnn"] = reference_on_gpu(dev, B)
+        except Exception as e:
+            line["extra"]["reference_on_gpu_cudnn"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if not args.no_cpu_baseline and world == 1:
-        fps, ms, cores, fr = cpu_reference_run(3, 1, args.cpu_frames or 4)
-        line["cpu_baseline"] = {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": "3 timed steps of %d frame(s) of the same workload with torch CPU ops (oracle/)" % fr}
+        cb = cpu_baseline_subprocess(args.cpu_frames or 8)
+        if cb is not None:
+            line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def reference_on_gpu(dev, B):
+    """The "kernel to beat" of BASELINE.md 3: the UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) on this B200 through
+    PyTorch/cuDNN with the reference's own settings (cudnn.benchmark = True, trainer.py:9; TF32 convolutions allowed = PyTorch's
+    default), same workloads, same batch sizes, eager launches as trainer.py runs them.  Never on the product path."""
+    import contextlib
+    import io
+    import torch
+    if _reference_root() is None:
+        return {"unavailable": "reference not staged on this box (oracle/make_ref.py)"}
+    ns = _load_reference()
+    torch.backends.cudnn.benchmark = True
+    q = lambda: contextlib.redirect_stdout(io.StringIO())
+    out = {"settings": "unmodified reference modules, cudnn.benchmark=True, TF32 convolutions allowed (PyTorch default), eager"}
+
+    def frames(b, hh, ww, seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        x = torch.rand(b, 5, hh, ww, device=dev, generator=g)
+        gt = torch.rand(b, 1, hh, ww, device=dev, generator=g) * 9.0 + 1.0
+        mask = (torch.rand(b, 1, hh, ww, device=dev, generator=g) < 500.0 / (hh * ww)).float()
+        x[:, 3:4] = gt * mask
+        x[:, 4:5] = mask
+        return x, gt
+
+    def train_case(args, dual, b, hh, ww, steps):
+        torch.manual_seed(0)
+        f = ns.cdf.ConfidenceDepthFrameworkFactory()
+        with q():
+            m = f.create_model(*args)
+            m, params = f.to_device(m)
+            m.train()
+        crit, _ = f.create_loss("l2", dual, 0.5)
+        opt = torch.optim.Adam(params, lr=1e-5)
+        x, gt = frames(b, hh, ww, 21)
+
+        def step():
+            with q():
+                pred = m(x)
+            loss = crit(x, pred[0][:, 0:1], pred[2][:, 0:1], gt, 0) if dual else crit(x, pred[0][:, 0:1], gt, 0)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del m, opt
+        torch.cuda.empty_cache()
+        return {"batch": b, "ms_per_step": round(ms, 2), "frames_s": round(b / ms * 1e3, 1)}
+
+    out["ged_dc1_only_228x304_train"] = train_case(("rgbd", "dc1_only", "ged_depthcompnet", ""), False, B, H, W, 5)
+    out["gudepthcompnet18_dc1_cf1_ln0_240x320_train"] = train_case(
+        ("rgbd", "dc1-cf1-ln0", "gudepthcompnet18", "", "cbr3-c1", "", "ged_depthcompnet", ""), True, 16, 240, 320, 3)
+    out["full_framework_dc1_cf1_ln1_480x752_train"] = train_case(
+        ("rgbdw", "dc1-cf1-ln1", "ged_depthcompnet", "", "cbr3-c1", "", "ged_depthcompnet", ""), True, 8, 480, 752, 3)
+    torch.manual_seed(0)
+    f = ns.cdf.ConfidenceDepthFrameworkFactory()
+    with q():
+        m = f.create_model("rgbd", "dc1_only", "gms_depthcompnet", "")
+        m, _ = f.to_device(m)
+        m.eval()
+    x, _ = frames(32, H, W, 22)
+    with torch.no_grad():
+        for _ in range(3):
+            with q():
+                m(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            with q():
+                m(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out["gms_inference_228x304"] = {"batch": 32, "ms_per_batch": round(ms, 2), "frames_s": round(32 / ms * 1e3, 1)}
+    return out
 
 
 def gms_inference(dev, B=32):
@@ -641,12 +817,35 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, detail_path=""):
     # the step; pooling / up-sampling rows aggregate three pyramid levels of very different sizes and stay in the table only
     d = next((r for r in table if r["name"].startswith("nconv_")), table[0])
     out = {"dominant": {"name": d["name"], "us": d["us"], "mb": d["mb"], "gbs": d["gbs"]}, "table": table[:12]}
+    # per LAYER on SURVEY.md 8(d)'s byte model: forward 8*(Ci+Co) B/px, backward (data + weight gradient kernels together)
+    # 16*(Ci+Co) B/px -- no credit for the split of the backward into two kernels that both read x, c and G
+    chan = {"nconv1": (1, 2), "nconv2": (2, 2), "nconv3": (2, 2), "nconv4": (4, 2), "nconv5": (4, 2), "nconv6": (4, 2)}
+    px = [B * 228 * 304, B * 114 * 152, B * 57 * 76, B * 28 * 38]
+    hbm = peaks()[0]
+    layers = []
+    for call in calls[:10]:
+        mod, lvl = call.split("@L")
+        ci, co = chan[mod]
+        f, bd, bw = agg.get("nconv_fwd:" + call), agg.get("nconv_bwd_data:" + call), agg.get("nconv_bwd_weight:" + call)
+        if not f:
+            continue
+        row = {"layer": call, "fwd_us": round(f[0] / f[2], 2),
+               "fwd_frac": round(8.0 * (ci + co) * px[int(lvl)] / (f[0] / f[2]) / 1e3 / hbm, 3)}
+        if bw:
+            bus = bw[0] / bw[2] + (bd[0] / bd[2] if bd else 0.0)      # nconv1 has no data gradient (x0, c0 need none)
+            row["bwd_us"] = round(bus, 2)
+            row["bwd_frac"] = round(16.0 * (ci + co) * px[int(lvl)] / bus / 1e3 / hbm, 3)
+        layers.append(row)
+    out["layers"] = layers
     if tc:
         rows = []
         for k, (us, work, cnt) in tc.items():
             rows.append({"name": k, "launches_per_step": cnt // reps, "us_per_step": round(us / reps, 1)})
         rows.sort(key=lambda r: -r["us_per_step"])
         out["tensor"] = rows
+        top = max(tc.items(), key=lambda kv: kv[1][0])
+        if top[1][1] > 0 and top[0] in [tc_names[q] for q in mma_kinds]:
+            out["tensor_dominant"] = {"name": top[0], "us_per_step": top[1][0] / reps, "flop_per_step": top[1][1] / reps}
         out["mma_us"] = sum(us for k, (us, work, cnt) in tc.items() if k in [tc_names[q] for q in mma_kinds]) / reps
         out["dense_us"] = sum(us for us, work, cnt in tc.values()) / reps
     return out
@@ -655,6 +854,7 @@ def kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, detail_path=""):
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""      # host cores only (set before torch initialises CUDA)
         reference_arm(a)
     else:
         b200_arm(a)

@@ -411,6 +411,35 @@ int adc_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int adc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* state, const double* hyper,
                       const float* guard, long long n, adc_stream_t stream);
 
+/* ---- S2DResNet (model_zoo/s2d_resnet.py:159-242, resnet18) around the tensor-core convolutions: csrc/s2d_ops.cu ------------------------
+ * Activations: zero-bordered NHWC bf16 (hi, lo) pairs (lo NULL in the plain bf16 mode); raw results / gradients: zero-bordered NHWC
+ * fp32; channel slices [off, off + C) of `stride` channels per pixel.
+ * adc_im2col_kxk_pack:   im2col of a K x K window (stride 1 / 2, zero padding `pad`) over the C planes of an fp32 NCHW source at the
+ *                        OUTPUT resolution: channel (u*K + v)*C + c, zeros up to dst_channels (multiple of 8).  The 7x7 / stride-2 stem
+ *                        (s2d_resnet.py:175) becomes one GEMM.
+ * adc_maxpool3x3s2_fwd:  nn.MaxPool2d(3, 2, 1) (:181) with ATen's scan order and tie rule; idx: uint8 [N][Ho][Wo][C] window position
+ *                        3u + v of the maximum.  _bwd: gin (written) = scatter of g by idx, computed as a deterministic gather.
+ * adc_pixel_shuffle_f32 / adc_pixel_unshuffle_pair: Y[n][2i+py][2j+px][c] <-> Q[n][i][j][(2py+px)*C + c], the parity-block form in
+ *                        which UpProj's 5x5 convolutions over the zero-stuffed Unpool output (:11-24, :105-143) are 3x3 stride-1
+ *                        convolutions of the low-resolution tensor.
+ * adc_bilinear_ac_fwd:   F.interpolate(mode='bilinear', align_corners=True) (:230-234) of an NHWC slice (fp32, or a bf16 pair when
+ *                        src_is_pair) to fp32 NCHW [N][C][Hd][Wd], ATen's index / weight arithmetic.  _bwd: gsrc (written or
+ *                        accumulated) = its adjoint, computed as a deterministic gather. */
+int adc_im2col_kxk_pack(const float* src, long long batch_stride, int C, int K, int stride, int pad, void* dst, void* dst_lo, int dst_stride,
+                        int dst_channels, int N, int H, int W, adc_stream_t stream);
+int adc_maxpool3x3s2_fwd(const void* x, const void* x_lo, int x_stride, int x_off, void* out, void* out_lo, int out_stride, int out_off,
+                         unsigned char* idx, int N, int C, int H, int W, adc_stream_t stream);
+int adc_maxpool3x3s2_bwd(const float* g, int g_stride, int g_off, const unsigned char* idx, float* gin, int gin_stride, int gin_off, int N, int C,
+                         int H, int W, adc_stream_t stream);
+int adc_pixel_shuffle_f32(const float* q, int q_stride, int q_off, float* y, int y_stride, int y_off, int N, int C, int h, int w,
+                          adc_stream_t stream);
+int adc_pixel_unshuffle_pair(const void* d, const void* d_lo, int d_stride, int d_off, void* q, void* q_lo, int q_stride, int q_off, int N, int C,
+                             int h, int w, adc_stream_t stream);
+int adc_bilinear_ac_fwd(const void* src, const void* src_lo, int src_is_pair, int src_stride, int src_off, int N, int C, int hs, int ws, float* dst,
+                        int Hd, int Wd, adc_stream_t stream);
+int adc_bilinear_ac_bwd(const float* g, int N, int C, int Hd, int Wd, float* gsrc, int gsrc_stride, int gsrc_off, int hs, int ws, int accumulate,
+                        adc_stream_t stream);
+
 /* ---- sparse-depth sampling (dataloaders/dense_to_sparse.py:29-48, UniformSampling.dense_to_sparse) on the device, bit-exact with
  * the reference's numpy stream: frame n draws np.random.uniform(0, 1, HW) after np.random.seed(seeds[n]) (MT19937, 53-bit doubles)
  * and keeps mask = (depth > 0 [& depth <= max_depth]) & (u < num_samples / count(keep)).  depth: fp32 [N][HW]; seeds: device

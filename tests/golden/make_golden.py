@@ -178,6 +178,8 @@ def case_nets(out):
     run_framework(out, "gud_mid", "dc1-cf1-ln0", "gudepthcompnet18", (96, 128), conf_arch="cbr3-c1", ln_arch="ged_depthcompnet", seed=7)
     run_framework(out, "s2d_only", "dc1_only", "resnet18", (64, 80))
     run_framework(out, "s2d_cf", "dc1-cf1-ln0", "resnet18", (64, 80), conf_arch="cbr3-c1", ln_arch="ged_depthcompnet")
+    # BASELINE config 5's shape (odd sizes all the way down: 114x152 -> 57x76 -> 29x38 -> 15x19 -> 8x10, bilinear 128x160 -> 228x304)
+    run_framework(out, "s2d_nyu", "dc1_only", "resnet18", (228, 304), seed=11)
     grad_noise_floor(out)
 
 
