@@ -165,7 +165,7 @@ SIGNATURES = {
     "adc_im2col_kxk_pack": (c_int, [_vp, c_ll, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_maxpool3x3s2_fwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_maxpool3x3s2_bwd": (c_int, [_vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
-    "adc_pixel_shuffle_f32": (c_int, [_vp, c_int, c_int, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_pixel_shuffle_f32": (c_int, [_vp, c_int, c_int, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_pixel_unshuffle_pair": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_bilinear_ac_fwd": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp, c_int, c_int, _vp]),
     "adc_bilinear_ac_bwd": (c_int, [_vp, c_int, c_int, c_int, c_int, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),

@@ -65,6 +65,27 @@ __device__ __forceinline__ double col_sum(const double* __restrict__ part, int r
     return (t0 + t1) + (t2 + t3);
 }
 
+// The same sum by one WARP per column (lane l takes rows l, l + 32, ...; fixed-order shuffle tree): the second stage of the statistics
+// used to be one thread per channel walking all 592 partial rows, a 150-load dependent chain that put a ~100-150 us floor under every
+// BatchNorm pass of the small deep layers (8x10 ... 29x38 pixels at 128-512 channels: most launches of the ResNet bodies).
+__device__ __forceinline__ double col_sum_warp(const double* __restrict__ part, int rows, int width, int col, int lane) {
+    double t0 = 0.0, t1 = 0.0;
+    int r = lane;
+    for (; r + 32 < rows; r += 64) {
+        t0 += part[(long long)r * width + col];
+        t1 += part[(long long)(r + 32) * width + col];
+    }
+    if (r < rows) t0 += part[(long long)r * width + col];
+    double t = t0 + t1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
+
+// First-stage CTAs for `pixels` pixels at C4 four-channel groups: every pixel slot of a CTA should see >= 8 pixels, so small tensors
+// produce few partial rows (1 ... kParts).
+static int parts_for(long long pixels, int C4);
+
 // part[blk][2][Cp]: sum y, sum y^2 of channels [0,Cp) over this CTA's pixels.  Thread = (pixel slot, 4-channel group).
 __global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ Y, int stride, int N, int C4, int H, int W,
                                                     double* __restrict__ part) {
@@ -91,7 +112,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                                        float eps, int training, float* __restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;      // one warp per channel
     if (c >= Cp) return;
     float a = 0.f, b = 0.f, mean = 0.f, rstd = 0.f;
     if (c < C) {
@@ -100,10 +121,10 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
         } else {
             double mu, var;
             if (training) {
-                mu = col_sum(part, rows, 2 * Cp, c) / M;
-                var = col_sum(part, rows, 2 * Cp, Cp + c) / M - mu * mu;
+                mu = col_sum_warp(part, rows, 2 * Cp, c, lane) / M;
+                var = col_sum_warp(part, rows, 2 * Cp, Cp + c, lane) / M - mu * mu;
                 if (var < 0.0) var = 0.0;
-                if (running_mean) {
+                if (running_mean && lane == 0) {
                     running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mu);
                     running_var[c] =
                         (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * var * (M / (M > 1.0 ? M - 1.0 : 1.0)));
@@ -118,6 +139,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
             b = beta[c] - mean * a;
         }
     }
+    if (lane != 0) return;
     coef[c] = a;
     coef[Cp + c] = b;
     coef[2 * Cp + c] = mean;
@@ -233,11 +255,12 @@ __global__ void __launch_bounds__(256) bwd_sums_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(128) bwd_finalize_kernel(const double* __restrict__ part, int rows, int Cp, int C, double M, int training,
                                                            float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;      // one warp per channel
     if (c >= Cp) return;
     float k1 = 0.f, k2 = 0.f;
     if (c < C) {
-        const double g = col_sum(part, rows, 2 * Cp, c), h = col_sum(part, rows, 2 * Cp, Cp + c);
+        const double g = col_sum_warp(part, rows, 2 * Cp, c, lane), h = col_sum_warp(part, rows, 2 * Cp, Cp + c, lane);
+        if (lane != 0) return;
         if (gbeta) gbeta[c] = (float)g;
         if (ggamma) ggamma[c] = (float)h;
         if (training) {
@@ -245,6 +268,7 @@ __global__ void __launch_bounds__(128) bwd_finalize_kernel(const double* __restr
             k2 = (float)(h / M);
         }
     }
+    if (lane != 0) return;
     coef[4 * Cp + c] = k1;
     coef[5 * Cp + c] = k2;
 }
@@ -461,6 +485,12 @@ __global__ void __launch_bounds__(128) im2col_pack_kernel(const __grid_constant_
     }
 }
 
+static int parts_for(long long pixels, int C4) {
+    const int groups = 256 / C4 > 0 ? 256 / C4 : 1;
+    long long p = (pixels + (long long)groups * 8 - 1) / ((long long)groups * 8);
+    return (int)(p < 1 ? 1 : (p > kParts ? kParts : p));
+}
+
 static int grid_for(long long total) {
     long long b = (total + 255) / 256;
     const long long cap = 148LL * 16;
@@ -497,15 +527,16 @@ int adc_bn_stats(const float* y, int y_stride, int y_off, int N, int C, int H, i
     const int C4 = (C + 3) / 4, Cp = C4 * 4;
     const double M = (double)N * H * W;
     const bool pass = gamma && training;
+    const int parts = parts_for((long long)N * H * W, C4);
     adc::Prof prof(st, adc::KIND_BN, pass ? M * C * 4.0 : 0.0);
     int rc = 0;
     if (pass) {
         adc::count_launches(1);
-        stats_kernel<<<kParts, 256, 0, st>>>(y + y_off, y_stride, N, C4, H, W, reinterpret_cast<double*>(workspace));
+        stats_kernel<<<parts, 256, 0, st>>>(y + y_off, y_stride, N, C4, H, W, reinterpret_cast<double*>(workspace));
         if ((rc = adc::check_cuda(cudaGetLastError(), "bn stats_kernel launch"))) return rc;
     }
-    finalize_kernel<<<(Cp + 127) / 128, 128, 0, st>>>(reinterpret_cast<const double*>(workspace), kParts, Cp, C, M, gamma, beta, running_mean,
-                                                      running_var, momentum, eps, training, coef);
+    finalize_kernel<<<(Cp + 3) / 4, 128, 0, st>>>(reinterpret_cast<const double*>(workspace), parts, Cp, C, M, gamma, beta, running_mean,
+                                                  running_var, momentum, eps, training, coef);
     return adc::check_cuda(cudaGetLastError(), "bn finalize_kernel launch");
 }
 
@@ -550,12 +581,13 @@ int adc_bn_bwd(const float* g, int g_stride, int g_off, const float* y, int y_st
     const float* Y = y + y_off;
     const __nv_bfloat16* O = act ? reinterpret_cast<const __nv_bfloat16*>(out_hi) + out_off : nullptr;
     double* part = reinterpret_cast<double*>(workspace);
-    if (act == 0) bwd_sums_kernel<0><<<kParts, 256, 0, st>>>(G, g_stride, Y, y_stride, O, out_stride, coef, Cp, N, C4, H, W, part);
-    else if (act == 1) bwd_sums_kernel<1><<<kParts, 256, 0, st>>>(G, g_stride, Y, y_stride, O, out_stride, coef, Cp, N, C4, H, W, part);
-    else bwd_sums_kernel<2><<<kParts, 256, 0, st>>>(G, g_stride, Y, y_stride, O, out_stride, coef, Cp, N, C4, H, W, part);
+    const int parts = parts_for((long long)N * H * W, C4);
+    if (act == 0) bwd_sums_kernel<0><<<parts, 256, 0, st>>>(G, g_stride, Y, y_stride, O, out_stride, coef, Cp, N, C4, H, W, part);
+    else if (act == 1) bwd_sums_kernel<1><<<parts, 256, 0, st>>>(G, g_stride, Y, y_stride, O, out_stride, coef, Cp, N, C4, H, W, part);
+    else bwd_sums_kernel<2><<<parts, 256, 0, st>>>(G, g_stride, Y, y_stride, O, out_stride, coef, Cp, N, C4, H, W, part);
     int rc = adc::check_cuda(cudaGetLastError(), "bn bwd_sums_kernel launch");
     if (rc) return rc;
-    bwd_finalize_kernel<<<(Cp + 127) / 128, 128, 0, st>>>(part, kParts, Cp, C, M, training, ggamma, gbeta, coef);
+    bwd_finalize_kernel<<<(Cp + 3) / 4, 128, 0, st>>>(part, parts, Cp, C, M, training, ggamma, gbeta, coef);
     if ((rc = adc::check_cuda(cudaGetLastError(), "bn bwd_finalize_kernel launch"))) return rc;
     __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(dy_hi) + dy_off;
     __nv_bfloat16* dl = dy_lo ? reinterpret_cast<__nv_bfloat16*>(dy_lo) + dy_off : nullptr;

@@ -171,10 +171,10 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
 }
 
 // ---- parity-block layout <-> full resolution ---------------------------------------------------------------------------------------------
-// Y[n][2i+py][2j+px][c] = Q[n][i][j][(2py+px)*C + c]   (fp32, 4 channels per thread)
+// Y[n][2i+py][2j+px][c] (+)= Q[n][i][j][(2py+px)*C + c]   (fp32, 4 channels per thread); Y is H x W with H in {2h-1, 2h}, W likewise
+// (the larger tensor of a stride-2 layer with an odd size)
 __global__ void __launch_bounds__(256) shuffle_f32_kernel(const float* __restrict__ q, int qs, float* __restrict__ y, int ys, int C4, int N,
-                                                          int h, int w) {
-    const int H = 2 * h, W = 2 * w;
+                                                          int h, int w, int H, int W, int accumulate) {
     const long long total = (long long)N * H * W * C4;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int g = (int)(t % C4);
@@ -182,8 +182,13 @@ __global__ void __launch_bounds__(256) shuffle_f32_kernel(const float* __restric
         const int X = (int)(r % W), Y = (int)((r / W) % H);
         const long long n = r / ((long long)W * H);
         const int par = 2 * (Y & 1) + (X & 1);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(q + bpix(n, Y >> 1, X >> 1, h, w) * qs + (par * C4 + g) * 4));
-        *reinterpret_cast<float4*>(y + bpix(n, Y, X, H, W) * ys + g * 4) = v;
+        float4 v = __ldg(reinterpret_cast<const float4*>(q + bpix(n, Y >> 1, X >> 1, h, w) * qs + (par * C4 + g) * 4));
+        float4* o = reinterpret_cast<float4*>(y + bpix(n, Y, X, H, W) * ys + g * 4);
+        if (accumulate) {
+            const float4 a = *o;
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+        *o = v;
     }
 }
 // Q[n][i][j][(2py+px)*C + c] = D[n][2i+py][2j+px][c]   (bf16 pair, 8 channels per thread)
@@ -342,16 +347,17 @@ int adc_maxpool3x3s2_bwd(const float* g, int g_stride, int g_off, const unsigned
     return adc::check_cuda(cudaGetLastError(), "maxpool_bwd_kernel launch");
 }
 
-int adc_pixel_shuffle_f32(const float* q, int q_stride, int q_off, float* y, int y_stride, int y_off, int N, int C, int h, int w,
-                          adc_stream_t stream) {
-    if (!q || !y || C <= 0 || C % 4 != 0 || q_off % 4 != 0 || y_off % 4 != 0 || q_stride % 4 != 0 || y_stride % 4 != 0 || N <= 0 || h <= 0 || w <= 0) {
-        adc::set_error("adc_pixel_shuffle_f32: bad argument (C, offsets and strides multiples of 4)");
+int adc_pixel_shuffle_f32(const float* q, int q_stride, int q_off, float* y, int y_stride, int y_off, int N, int C, int h, int w, int H, int W,
+                          int accumulate, adc_stream_t stream) {
+    if (!q || !y || C <= 0 || C % 4 != 0 || q_off % 4 != 0 || y_off % 4 != 0 || q_stride % 4 != 0 || y_stride % 4 != 0 || N <= 0 || h <= 0 || w <= 0 ||
+        (H != 2 * h && H != 2 * h - 1) || (W != 2 * w && W != 2 * w - 1)) {
+        adc::set_error("adc_pixel_shuffle_f32: bad argument (C, offsets and strides multiples of 4; H in {2h-1, 2h}, W in {2w-1, 2w})");
         return ADC_E_BADARG;
     }
-    const long long total = (long long)N * 4 * h * w * (C / 4);
+    const long long total = (long long)N * H * W * (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
-    adc::Prof prof(st, adc::KIND_TC_LAYOUT, (double)total * 32.0);
-    shuffle_f32_kernel<<<grid_for(total), 256, 0, st>>>(q + q_off, q_stride, y + y_off, y_stride, C / 4, N, h, w);
+    adc::Prof prof(st, adc::KIND_TC_LAYOUT, (double)total * (accumulate ? 48.0 : 32.0));
+    shuffle_f32_kernel<<<grid_for(total), 256, 0, st>>>(q + q_off, q_stride, y + y_off, y_stride, C / 4, N, h, w, H, W, accumulate);
     return adc::check_cuda(cudaGetLastError(), "shuffle_f32_kernel launch");
 }
 

@@ -59,7 +59,7 @@ def pair_act(n, h, w, c, dev):
     return dense.new_act(n, h, w, c, dev, pad=True, zero=True)
 
 
-def conv(kind, x, x_off, cin, wp, out, out_off, cout, H, W, stride=1, bias=None, act=NONE, accumulate=False, out_zero_to=0):
+def conv(kind, x, x_off, cin, wp, out, out_off, cout, H, W, stride=1, bias=None, act=NONE, accumulate=False, out_zero_to=0, tap_mask=0):
     """One launch of adc_conv_tc.  x / out: dense.Act (out fp32 or a bf16 pair); H, W: input size (kinds 0-3) or the size of the LARGER
     tensor (kinds 4, 5)."""
     d = ConvDesc()
@@ -70,7 +70,7 @@ def conv(kind, x, x_off, cin, wp, out, out_off, cout, H, W, stride=1, bias=None,
     f32 = out.hi.dtype == torch.float32
     d.out, d.out_lo, d.out_f32 = out.hi.data_ptr(), (None if f32 else _ptr(out.lo)), int(f32)
     d.out_stride, d.out_off, d.out_pad, d.out_zero_to, d.accumulate = out.cs, out_off, int(out.pad), out_zero_to, int(bool(accumulate))
-    d.N, d.H, d.W, d.cin, d.cout, d.stride, d.act, d.tap_mask = x.n, H, W, cin, cout, stride, act, 0
+    d.N, d.H, d.W, d.cin, d.cout, d.stride, d.act, d.tap_mask = x.n, H, W, cin, cout, stride, act, tap_mask
     check(lib.adc_conv_tc(ctypes.byref(d), dense._stream()), "adc_conv_tc")
     return out
 
@@ -103,6 +103,11 @@ class WPrep:
         w = weight.detach()
         for a, b in _chunks(w.shape[1], step or _chunk()):
             self.add((key, a), w, 1 if flip else 2, cin_pad, a, b - a)
+
+    def quad_s2(self, key, w_io, cin_pad):
+        """Parity-block weights of a stride-2 transposed convolution / stride-2 data gradient (``quad_s2_weights``), one item per chunk."""
+        wq = quad_s2_weights(w_io)
+        self.fwd(key, wq, cin_pad, step=min(_chunk(), w_io.shape[1]))
 
     def run(self):
         if self.reqs:
@@ -173,10 +178,49 @@ def fwd_box(x, x_off, cin, wp, key, Y, y_off, cout, stride, kind=K_BOX):
         conv(kind, x, x_off, cin, wp[(key, a)], Y, y_off + a, b - a, x.h, x.w, stride=stride)
 
 
+# ---- stride-2 transposed convolutions and stride-2 data gradients in parity-block form -------------------------------------------------
+# out[2m+py][2n+px][o] = sum over (di, dj), c of x[m+di][n+dj][c] * w_io[c][o][u][v]  with  u = py + 1 - 2*di, v = px + 1 - 2*dj  in 0..2
+# (ConvTranspose2d(3, 2, 1, 1) with weight [in][out]; equally the data gradient of a 3x3 / stride-2 / pad-1 convolution with weight
+# [Cout][Cin] = [in][out]).  Per parity (py, px) that is a stride-1 3x3 convolution of the LOW-resolution tensor using 1, 2, 2 or 4 of
+# its nine taps (dense.quad_maps 's2'): the row-segment kernel with a tap mask per parity block of output channels writes a
+# [N][h][w][4*out] tensor, adc_pixel_shuffle_f32 scatters (or accumulates) it into the 2x larger tensor.  Measured on the config-3 step
+# (B = 16, 240x320): the per-tap box kernel this replaces ran at 49 TFLOP/s, the row-segment kernel runs these layers at 190-250.
+_SCRATCH = {}
+
+
+def _scratch_f32(n, h, w, c, dev):
+    key = (n, h, w, c, str(dev))
+    if key not in _SCRATCH:
+        _SCRATCH[key] = f32_act(n, h, w, c, dev)
+    return _SCRATCH[key]
+
+
+def quad_s2_weights(w_io):
+    """[in, out, 3, 3] (contracted over ``in``) -> [4*out, in, 3, 3]: row (2py+px)*out + o holds, at low-resolution tap (di+1, dj+1), the
+    original tap (py+1-2di, px+1-2dj) where it exists."""
+    cin, cout = w_io.shape[:2]
+    _, s2 = dense.quad_maps(w_io.device)
+    w = w_io.detach().reshape(1, cin, cout, 1, 9)
+    return (w * s2.reshape(4, 1, 1, 9, 9)).sum(-1).permute(0, 2, 1, 3).reshape(4 * cout, cin, 3, 3)
+
+
+def quad_s2(x, x_off, cin, wp, key, Y, y_off, cout, accumulate=False):
+    """x (low resolution) -> Y[:, y_off:y_off+cout] (the 2x larger tensor, fp32; odd sizes allowed), written or accumulated."""
+    masks, _ = dense.quad_s2_tap_masks()
+    step = min(_chunk(), cout)
+    Yq = _scratch_f32(x.n, x.h, x.w, dense._r64(4 * cout), x.hi.device)
+    for a, b in _chunks(4 * cout, step):
+        m = 0
+        for q in range(a // cout, (b - 1) // cout + 1):
+            m |= masks[q]
+        conv(K_S1, x, x_off, cin, wp[(key, a)], Yq, a, b - a, x.h, x.w, tap_mask=m)
+    check(lib.adc_pixel_shuffle_f32(Yq.hi.data_ptr(), Yq.cs, 0, Y.hi.data_ptr(), Y.cs, y_off, x.n, cout, x.h, x.w, Y.h, Y.w, int(bool(accumulate)),
+                                    dense._stream()), "adc_pixel_shuffle_f32")
+
+
 def fwd_convt2(x, x_off, cin, wp, key, Y, y_off, cout):
     """ConvTranspose2d(3, stride 2, padding 1, output_padding 1): Y is the 2x larger tensor."""
-    for a, b in _chunks(cout, _chunk()):
-        conv(K_CONVT2, x, x_off, cin, wp[(key, a)], Y, y_off + a, b - a, Y.h, Y.w)
+    quad_s2(x, x_off, cin, wp, key, Y, y_off, cout, False)
 
 
 # ---- data gradients into an fp32 gradient buffer (first producer writes, later ones accumulate) --------------------------------------
@@ -186,7 +230,10 @@ def dgrad_s1(dY, cy, wp, key, G, g_off, cin, accumulate, step=None):
 
 
 def dgrad_s2(dY, cy, wp, key, G, g_off, cin, accumulate, kind=K_CONVT2):
-    """Data gradient of a stride-2 3x3 (kind 4) or 1x1 (kind 5) convolution: G is the 2x larger tensor."""
+    """Data gradient of a stride-2 3x3 convolution (parity-block form, weights from WPrep.quad_s2) or of a 1x1 / stride-2 convolution
+    (kind 5: box kernel on the even pixels, weights from WPrep.transposed): G is the 2x larger tensor."""
+    if kind == K_CONVT2:
+        return quad_s2(dY, 0, cy, wp, key, G, g_off, cin, accumulate)
     for a, b in _chunks(cin, _chunk()):
         conv(kind, dY, 0, cy, wp[(key, a)], G, g_off + a, b - a, G.h, G.w, accumulate=accumulate)
 
@@ -325,7 +372,10 @@ def stage_prep_bwd(wp, st, name, cin, cout, stride):
     for bi in (0, 1):
         blk = st[bi]
         s_ = stride if bi == 0 else 1
-        wp.transposed((name, bi, 1), blk.conv1.weight, dense._r64(cout), flip=(s_ == 1))
+        if s_ == 1:
+            wp.transposed((name, bi, 1), blk.conv1.weight, dense._r64(cout), flip=True)
+        else:
+            wp.quad_s2((name, bi, 1), blk.conv1.weight, dense._r64(cout))
         wp.transposed((name, bi, 2), blk.conv2.weight, dense._r64(cout), flip=True)
         if blk.downsample is not None:
             wp.transposed((name, bi, "d"), embed_1x1(blk.downsample[0].weight), dense._r64(cout), flip=False)
@@ -493,7 +543,7 @@ class S2DUBodyTC(torch.autograd.Function):
         for name, lvl, cin, cout in _CONVT:
             # the ConvTranspose2d weight [in][out][3][3] IS the weight of the stride-2 convolution this layer is the data gradient of
             # ([Cout_conv = in][Cin_conv = out]): prep mode 2 (transposed, taps kept) gives rows = out chunk, columns = in
-            wp.transposed(name, getattr(net, name)[0].weight, cin, flip=False)
+            wp.quad_s2(name, getattr(net, name)[0].weight, cin)
         wp.transposed("convt1", net.convt1[0].weight, 128, flip=True)            # Wc[o][i][tap] = Wt[i][o][8-tap]: prep mode 1
         W = wp.run()
         # ---- stems: im2col + ONE GEMM, then BatchNorm + LeakyReLU per stem into cat_last[64:128] (= conv1 of the reference)
@@ -553,7 +603,7 @@ class S2DUBodyTC(torch.autograd.Function):
         wp = WPrep()
         for name, lvl, cin, cout, stride in _STAGES:
             stage_prep_bwd(wp, getattr(net, name), name, cin, cout, stride)
-        wp.transposed("conv6", net.conv6[0].weight, 512, flip=False)
+        wp.quad_s2("conv6", net.conv6[0].weight, 512)
         for name, lvl, cin, cout in _CONVT:
             wp.fwd(name, getattr(net, name)[0].weight, dense._r64(cout))       # ConvT weight [in][out] read as a convolution [Cout = in][Cin = out]
         wp.fwd("convt1", net.convt1[0].weight, 64)

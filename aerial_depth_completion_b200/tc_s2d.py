@@ -120,7 +120,7 @@ def quad5_weight_grad(dwq, co):
 
 
 def _shuffle(Yq, q_off, Y, C):
-    check(lib.adc_pixel_shuffle_f32(Yq.hi.data_ptr(), Yq.cs, q_off, Y.hi.data_ptr(), Y.cs, 0, Yq.n, C, Yq.h, Yq.w, dense._stream()),
+    check(lib.adc_pixel_shuffle_f32(Yq.hi.data_ptr(), Yq.cs, q_off, Y.hi.data_ptr(), Y.cs, 0, Yq.n, C, Yq.h, Yq.w, Y.h, Y.w, 0, dense._stream()),
           "adc_pixel_shuffle_f32")
 
 

@@ -399,9 +399,9 @@ def b200_arm(args):
 
     # headline e2e: DeviceAssemblyFeeder -- rgb + gt + seeds cross PCIe, the UniformSampling masks and the 5-channel input are built
     # on the device (bit-identical to the host-assembled batches: tests/test_gpu_feeder.py), copy + assembly of batch i+1 overlap step i
-    ms_e2e, e2e_losses = run_feeder(parallel.DeviceAssemblyFeeder(trainer, host_raw[0][0], 500), host_raw)
-    # the same with the loader doing the assembly on the host (6 planes per frame over PCIe), for comparison
+    # (measured after the host-assembled variant: 6 planes per frame over PCIe, the loader doing the assembly on the host)
     ms_e2e_host, _ = run_feeder(parallel.HostFeeder(trainer, host_in[0], host_tg[0]), list(zip(host_in, host_tg)))
+    ms_e2e, e2e_losses = run_feeder(parallel.DeviceAssemblyFeeder(trainer, host_raw[0][0], 500), host_raw)
     ms_serial = timed(from_host, min(args.steps, 5)) / min(args.steps, 5)      # the reference trainer's order: copy, step, read, next
     sampler_thread.stop_flag = True
 
@@ -480,6 +480,10 @@ def b200_arm(args):
             line["extra"]["gudepthcompnet18_dc1_cf1_ln0_240x320"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if world == 1 and not args.no_extras:
         try:
+            line["extra"]["baseline_nets_dc1_only_train_sweep"] = baseline_nets_sweep(dev)
+        except Exception as e:
+            line["extra"]["baseline_nets_dc1_only_train_sweep"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        try:
             line["extra"]["reference_on_gpu_cudnn"] = reference_on_gpu(dev, B)
         except Exception as e:
             line["extra"]["reference_on_gpu_cudnn"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
@@ -551,6 +555,8 @@ def reference_on_gpu(dev, B):
         ("rgbd", "dc1-cf1-ln0", "gudepthcompnet18", "", "cbr3-c1", "", "ged_depthcompnet", ""), True, 16, 240, 320, 3)
     out["full_framework_dc1_cf1_ln1_480x752_train"] = train_case(
         ("rgbdw", "dc1-cf1-ln1", "ged_depthcompnet", "", "cbr3-c1", "", "ged_depthcompnet", ""), True, 8, 480, 752, 3)
+    out["resnet18_dc1_only_228x304_train"] = train_case(("rgbd", "dc1_only", "resnet18", ""), False, 64, H, W, 3)
+    out["udepthcompnet18_dc1_only_240x320_train"] = train_case(("rgbdw", "dc1_only", "udepthcompnet18", ""), False, 32, 240, 320, 3)
     torch.manual_seed(0)
     f = ns.cdf.ConfidenceDepthFrameworkFactory()
     with q():
@@ -734,6 +740,67 @@ def gudepthcompnet_training(dev, B=16, HH=240, WW=320, steps=5, graph=True):
                 "launch": "one CUDA graph per step" if graph else "eager"}
     finally:
         dense.set_precision(prev)
+
+
+def baseline_nets_sweep(dev):
+    """BASELINE.json configs[4]: the sparse-to-dense baseline nets -- resnet18 (S2DResNet, 228x304) and udepthcompnet18 (S2DUResNet
+    on the NConv pyramid's output, 240x320: the net needs H, W = 0 mod 16) -- dc1_only, masked-L2, forward + backward + Adam, batch sweep up
+    to 64 frames.  Every layer on this library's kernels (tc_s2d.S2DBodyTC / tc_bn.S2DUBodyTC, bf16x3), one CUDA graph per step."""
+    import contextlib
+    import io
+    import torch
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    from aerial_depth_completion_b200 import dense, parallel, _lib
+    from aerial_depth_completion_b200.optim import FlatAdam
+    out = {}
+    prev = dense.PRECISION
+    try:
+        dense.set_precision("bf16x3")
+        for arch, itype, HH, WW, gflop, batches in (("resnet18", "rgbd", 228, 304, 10.0, (16, 32, 64)),
+                                                    ("udepthcompnet18", "rgbdw", 240, 320, 105.0, (16, 32, 64))):
+            rows = {}
+            for B in batches:
+                try:
+                    torch.manual_seed(0)
+                    f = mc.ConfidenceDepthFrameworkFactory()
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        m = f.create_model(itype, "dc1_only", arch, "")
+                        m, params = f.to_device(m)
+                        m.train()
+                    crit, _ = f.create_loss("l2", False, 0.5)
+                    tr = parallel.DataParallelTrainer(m, crit, FlatAdam(params, lr=1e-5), params, world_size=1)
+                    g = torch.Generator(device=dev).manual_seed(17)
+                    x = torch.rand(B, 5, HH, WW, device=dev, generator=g)
+                    gt = torch.rand(B, 1, HH, WW, device=dev, generator=g) * 9.0 + 1.0
+                    mask = (torch.rand(B, 1, HH, WW, device=dev, generator=g) < 500.0 / (HH * WW)).float()
+                    x[:, 3:4] = gt * mask
+                    x[:, 4:5] = mask
+                    l0 = _lib.lib.adc_launch_count()
+                    tr._eager_step(x, gt)
+                    launches = _lib.lib.adc_launch_count() - l0
+                    tr.capture(x, gt, warmup=1)
+                    for _ in range(2):
+                        tr.step(x, gt)
+                    torch.cuda.synchronize()
+                    steps = 4
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        loss = tr.step(x, gt)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / steps
+                    rows["b%d" % B] = {"ms_per_step": round(ms, 2), "frames_s": round(B / ms * 1e3, 1), "library_launches_per_step": int(launches),
+                                       "algorithmic_tflops": round(3.0 * gflop * B / ms, 1), "loss": round(float(loss), 4)}
+                    del tr, m, params, x, gt, mask
+                    torch.cuda.empty_cache()
+                except Exception as e:
+                    rows["b%d" % B] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+                    torch.cuda.empty_cache()
+            out[arch + "_%dx%d" % (HH, WW)] = rows
+    finally:
+        dense.set_precision(prev)
+    return out
 
 
 def ged_algorithmic_flops(B):

@@ -420,8 +420,10 @@ int adc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* ex
  * adc_maxpool3x3s2_fwd:  nn.MaxPool2d(3, 2, 1) (:181) with ATen's scan order and tie rule; idx: uint8 [N][Ho][Wo][C] window position
  *                        3u + v of the maximum.  _bwd: gin (written) = scatter of g by idx, computed as a deterministic gather.
  * adc_pixel_shuffle_f32 / adc_pixel_unshuffle_pair: Y[n][2i+py][2j+px][c] <-> Q[n][i][j][(2py+px)*C + c], the parity-block form in
- *                        which UpProj's 5x5 convolutions over the zero-stuffed Unpool output (:11-24, :105-143) are 3x3 stride-1
- *                        convolutions of the low-resolution tensor.
+ *                        which UpProj's 5x5 convolutions over the zero-stuffed Unpool output (:11-24, :105-143), the stride-2
+ *                        ConvTranspose2d layers of s2d_u_resnet.py:45-61 and the data gradients of stride-2 convolutions are 3x3 stride-1
+ *                        convolutions of the low-resolution tensor.  The shuffle writes or accumulates into an H x W tensor with
+ *                        H in {2h-1, 2h} (odd sizes of a stride-2 layer's larger tensor).
  * adc_bilinear_ac_fwd:   F.interpolate(mode='bilinear', align_corners=True) (:230-234) of an NHWC slice (fp32, or a bf16 pair when
  *                        src_is_pair) to fp32 NCHW [N][C][Hd][Wd], ATen's index / weight arithmetic.  _bwd: gsrc (written or
  *                        accumulated) = its adjoint, computed as a deterministic gather. */
@@ -431,8 +433,8 @@ int adc_maxpool3x3s2_fwd(const void* x, const void* x_lo, int x_stride, int x_of
                          unsigned char* idx, int N, int C, int H, int W, adc_stream_t stream);
 int adc_maxpool3x3s2_bwd(const float* g, int g_stride, int g_off, const unsigned char* idx, float* gin, int gin_stride, int gin_off, int N, int C,
                          int H, int W, adc_stream_t stream);
-int adc_pixel_shuffle_f32(const float* q, int q_stride, int q_off, float* y, int y_stride, int y_off, int N, int C, int h, int w,
-                          adc_stream_t stream);
+int adc_pixel_shuffle_f32(const float* q, int q_stride, int q_off, float* y, int y_stride, int y_off, int N, int C, int h, int w, int H, int W,
+                          int accumulate, adc_stream_t stream);
 int adc_pixel_unshuffle_pair(const void* d, const void* d_lo, int d_stride, int d_off, void* q, void* q_lo, int q_stride, int q_off, int N, int C,
                              int h, int w, adc_stream_t stream);
 int adc_bilinear_ac_fwd(const void* src, const void* src_lo, int src_is_pair, int src_stride, int src_off, int N, int C, int hs, int ws, float* dst,

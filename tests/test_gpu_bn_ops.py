@@ -131,7 +131,7 @@ def test_stride2_conv_and_shortcut_with_gradients(cin, cout, h, w):
     # gradients
     D3, D1 = _to_pair(g3), _to_pair(g1)
     W = tc_bn.WPrep()
-    W.transposed("c3", w3.detach().float().cuda(), dense._r64(cout), flip=False)
+    W.quad_s2("c3", w3.detach().float().cuda(), dense._r64(cout))          # parity-block form on the row-segment kernel
     W.transposed("c1", tc_bn.embed_1x1(w1.detach().float().cuda()), dense._r64(cout), flip=False)
     Wb = W.run()
     Gx = tc_bn.f32_act(n, h, w, cin, "cuda")
@@ -154,7 +154,7 @@ def test_conv_transpose_stride2_with_gradients(cin, cout, h, w):
     X = _to_pair(x.detach())
     wd = wt.detach().float().cuda()
     W = tc_bn.WPrep()
-    W.transposed("t", wd, cin, flip=False)
+    W.quad_s2("t", wd, cin)
     Wf = W.run()
     Y = tc_bn.f32_act(n, 2 * h, 2 * w, dense._r64(cout), "cuda")
     tc_bn.fwd_convt2(X, 0, cin, Wf, "t", Y, 0, cout)

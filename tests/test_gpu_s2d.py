@@ -84,7 +84,8 @@ def test_pixel_shuffle_and_unshuffle(C):
     Q = _f32(q)
     for blk in (0, 1):                                                     # the two branches of an UpProj module share one buffer
         Y = tc_bn.f32_act(n, 2 * h, 2 * w, dense._r64(C), "cuda")
-        check(lib.adc_pixel_shuffle_f32(Q.hi.data_ptr(), Q.cs, blk * 4 * C, Y.hi.data_ptr(), Y.cs, 0, n, C, h, w, dense._stream()), "shuffle")
+        check(lib.adc_pixel_shuffle_f32(Q.hi.data_ptr(), Q.cs, blk * 4 * C, Y.hi.data_ptr(), Y.cs, 0, n, C, h, w, 2 * h, 2 * w, 0, dense._stream()),
+              "shuffle")
         got = _nchw(Y, C)
         want = torch.zeros(n, C, 2 * h, 2 * w, dtype=torch.float64)
         for py in range(2):

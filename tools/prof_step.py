@@ -1,5 +1,5 @@
 """Per-kernel CUDA-event profile (the library's own instrumentation) of ONE eager training step of a framework configuration.
-Usage: python tools/prof_step.py gud|ged|gms|full [batch] > gpurun_out/prof_<cfg>.txt"""
+Usage: python tools/prof_step.py gud|ged|gms|full|s2d|ud [batch] > gpurun_out/prof_<cfg>.txt"""
 import contextlib, ctypes, io, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,10 +10,12 @@ from aerial_depth_completion_b200._lib import lib
 from aerial_depth_completion_b200.optim import FlatAdam
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "gud"
-B = int(sys.argv[2]) if len(sys.argv) > 2 else {"gud": 16, "ged": 32, "gms": 32, "full": 8}[cfg]
+B = int(sys.argv[2]) if len(sys.argv) > 2 else {"gud": 16, "ged": 32, "gms": 32, "full": 8, "s2d": 64, "ud": 32}[cfg]
 H, W, args, dual = {"gud": (240, 320, ("rgbd", "dc1-cf1-ln0", "gudepthcompnet18", "", "cbr3-c1", "", "ged_depthcompnet", ""), True),
                     "ged": (228, 304, ("rgbd", "dc1_only", "ged_depthcompnet", ""), False),
                     "gms": (228, 304, ("rgbd", "dc1_only", "gms_depthcompnet", ""), False),
+                    "s2d": (228, 304, ("rgbd", "dc1_only", "resnet18", ""), False),
+                    "ud": (240, 320, ("rgbdw", "dc1_only", "udepthcompnet18", ""), False),
                     "full": (480, 752, ("rgbdw", "dc1-cf1-ln1", "ged_depthcompnet", "", "cbr3-c1", "", "ged_depthcompnet", ""), True)}[cfg]
 torch.manual_seed(0)
 f = mc.ConfidenceDepthFrameworkFactory()
