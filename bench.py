@@ -32,7 +32,7 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=30)
     p.add_argument("--warmup", type=int, default=5)
-    p.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    p.add_argument("--batch", type=int, default=128, help="frames per GPU per step (extra.batch_sweep reports 8 = the reference's default, 32, 64)")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-frames", type=int, default=0, help="frames per step of the CPU arms (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -58,11 +58,14 @@ PEAKS = _load_peaks()
 
 def _load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the NConv kernels from the committed `ncu --set full` capture
-    (profiles/r1_nconv_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep): kernel name as in the roofline table."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_nconv_traffic.json")))
-    except Exception:
-        return {}
+    (profiles/r2_nconv_traffic.json at the default batch, written by tools/ncu_traffic.py from the .ncu-rep): kernel name as in the roofline
+    table.  Only reported when the capture's batch size is this run's (the source string names it)."""
+    for name in ("r2_nconv_traffic.json", "r1_nconv_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            continue
+    return {}
 
 
 TRAFFIC = _load_traffic()
@@ -318,7 +321,7 @@ def b200_arm(args):
     trainer = parallel.DataParallelTrainer(model, criterion, optimizer, params, world_size=world)
 
     # synthetic frames: a pool larger than L2 so no step finds its inputs cached
-    pool_n = 8
+    pool_n = max(2, min(8, (512 << 20) // (B * 6 * H * W * 4) + 1))      # distinct batches: > 400 MB in total, well beyond the 126 MB L2
     g = torch.Generator().manual_seed(1234 + rank)
     sampler = UniformSampling(500, np.inf)
     host_in, host_tg, host_raw = [], [], []
@@ -442,9 +445,12 @@ def b200_arm(args):
     }
     if roof:
         dom = roof["dominant"]
+        tr_ = TRAFFIC.get(dom["name"]) or {}
+        if ("(B=%d," % B) not in (tr_.get("source") or ""):      # a capture at another batch size says nothing about this launch
+            tr_ = {}
         line["roofline"] = {"bound": "hbm", "achieved": round(dom["gbs"], 1), "peak": peak, "unit": "GB/s",
-                            "frac": round(dom["gbs"] / peak, 4), "traffic": (TRAFFIC.get(dom["name"]) or {}).get("dram_bytes_per_launch"),
-                            "traffic_source": (TRAFFIC.get(dom["name"]) or {}).get("source"), "kernel": dom["name"],
+                            "frac": round(dom["gbs"] / peak, 4), "traffic": tr_.get("dram_bytes_per_launch"),
+                            "traffic_source": tr_.get("source"), "kernel": dom["name"],
                             "launch_us": round(dom["us"], 2), "algorithmic_mb_per_launch": round(dom["mb"], 2),
                             "peak_source": peak_src, "nconv_kernels": roof["table"],
                             "nconv_layers_survey_byte_model": roof.get("layers")}
@@ -470,6 +476,10 @@ def b200_arm(args):
                         "zero taps of the quad forms are executed but not counted as algorithmic FLOPs"}
     if world == 1 and not args.no_extras:
         line["extra"] = {"gms_inference_b32": gms_inference(dev)}
+        try:
+            line["extra"]["batch_sweep_headline_workload"] = batch_sweep(dev, args.precision)
+        except Exception as e:
+            line["extra"]["batch_sweep_headline_workload"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
         try:
             line["extra"]["full_framework_dc1_cf1_ln1_480x752"] = full_framework_training(dev)
         except Exception as e:       # an extra measurement must never cost the headline line
@@ -740,6 +750,55 @@ def gudepthcompnet_training(dev, B=16, HH=240, WW=320, steps=5, graph=True):
                 "launch": "one CUDA graph per step" if graph else "eager"}
     finally:
         dense.set_precision(prev)
+
+
+def batch_sweep(dev, precision, batches=(8, 32, 64)):
+    """The headline workload (GED dc1_only train step, resident inputs, one CUDA graph per step) at other batch sizes per GPU: 8 is the
+    reference's --batch-size default (trainer.py:101).  Small batches leave the 148 SMs partly idle in the pyramid's kernels (1280 tiles
+    at B = 32 are 1.7 waves of the resident CTAs) and pay the launch latency of the small pyramid levels once per step."""
+    import contextlib
+    import io
+    import torch
+    import aerial_depth_completion_b200.model_zoo.confidence_depth_framework as mc
+    from aerial_depth_completion_b200 import dense, parallel
+    from aerial_depth_completion_b200.optim import FlatAdam
+    out = {}
+    for B in batches:
+        torch.manual_seed(0)
+        f = mc.ConfidenceDepthFrameworkFactory()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = f.create_model("rgbd", "dc1_only", "ged_depthcompnet", "")
+            m, params = f.to_device(m)
+            m.train()
+        crit, _ = f.create_loss("l2", False, 0.5)
+        tr = parallel.DataParallelTrainer(m, crit, FlatAdam(params, lr=1e-5), params, world_size=1)
+        g = torch.Generator(device=dev).manual_seed(19)
+        xs, ts = [], []
+        for _ in range(max(2, min(8, (256 << 20) // (B * 6 * H * W * 4) + 1))):
+            x = torch.rand(B, 5, H, W, device=dev, generator=g)
+            gt = torch.rand(B, 1, H, W, device=dev, generator=g) * 9.0 + 1.0
+            mask = (torch.rand(B, 1, H, W, device=dev, generator=g) < 500.0 / (H * W)).float()
+            x[:, 3:4] = gt * mask
+            x[:, 4:5] = mask
+            xs.append(x)
+            ts.append(gt)
+        tr._eager_step(xs[0], ts[0])
+        tr.capture(xs[0], ts[0])
+        for i in range(3):
+            tr.step(xs[i % len(xs)], ts[i % len(xs)])
+        torch.cuda.synchronize()
+        steps = 12
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            tr.step(xs[i % len(xs)], ts[i % len(xs)])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["b%d" % B] = {"ms_per_step": round(ms, 3), "frames_s": round(B / ms * 1e3, 1)}
+        del tr, m, params, xs, ts
+        torch.cuda.empty_cache()
+    return out
 
 
 def baseline_nets_sweep(dev):

@@ -1,7 +1,7 @@
-"""profiles/r1_nconv_traffic.json from an `ncu --set full` report of one training step: DRAM bytes (read + write) and duration per
+"""profiles/r<round>_nconv_traffic.json from an `ncu --set full` report of one training step: DRAM bytes (read + write) and duration per
 launch of the NConv kernels, keyed like bench.py's roofline table (kernel:call@level).  Usage: ncu_traffic.py report.ncu-rep out.json
 Capture: STEPS=3 MARK=2 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:nconv_ -o rep python tools/prof_bench_step.py"""
-import csv, json, subprocess, sys
+import csv, json, os, subprocess, sys
 
 rep, out = sys.argv[1], sys.argv[2]
 txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -34,8 +34,8 @@ for r in rows[2:]:
     res[key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "ncu_us": float(r[col["gpu__time_duration.sum"]]),
                 "grid": r[col["Grid Size"]], "kernel": name.split("(")[0][-60:],
                 "fma_pipe_pct": float(r[col["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]]),
-                "source": "ncu --set full --clock-control none --profile-from-start off, tools/prof_bench_step.py MARK=2 (B=32, 228x304, one "
-                          "steady-state step), " + rep.split("/")[-1]}
+                "source": "ncu --set full --clock-control none --profile-from-start off, tools/prof_bench_step.py MARK=2 (B=%s, 228x304, one "
+                          "steady-state step), " % os.environ.get("B", "32") + rep.split("/")[-1]}
 assert seen == {"fwd": 10, "bwd_weight": 10, "bwd_data": 9}, "the capture is not exactly one training step: %s" % seen
 json.dump(res, open(out, "w"), indent=1)
 for k, v in res.items():
