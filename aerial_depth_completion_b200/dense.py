@@ -193,7 +193,7 @@ def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=No
     n, h, w = act.n, act.h, act.w
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     # v2 streams 3 taps x Cout16 weight rows per pipeline stage: in the split mode two stages fit only up to 80 output channels
-    v2 = USE_V2 and stride == 1 and act.pad and cin % 64 == 0 and cout <= (80 if _split() else 128) and (out is None or out.pad)
+    v2 = USE_V2 and stride == 1 and act.pad and cin % 16 == 0 and cout <= (80 if _split() else 128) and (out is None or out.pad)
     assert v2 or not tap_mask, "tap masks are a feature of the row-segment kernel"
     zero_to = out_zero_to if v2 else 0                      # slice width the layer owns (channels past cout written as 0)
     if out is None:
@@ -397,7 +397,7 @@ def ged_pack_im2col(xout_d, cout_d, rgb, dst):
 
 
 def conv1x1_tc(act, cin, w_prep, bias, cout, act_fn=0, x_off=0, out=None, out_off=0, out_zero_to=0):
-    """1x1 convolution of channels [x_off, x_off+cin) of a zero-bordered activation (cin % 64 == 0) into a channel slice of
+    """1x1 convolution of channels [x_off, x_off+cin) of a zero-bordered activation (cin % 16 == 0) into a channel slice of
     ``out``; ``w_prep`` = prepared weights of a [cout, cin, 3, 3] tensor whose only non-zero tap is the centre."""
     from ._lib import lib, check
     assert act.pad and out.pad and (act.n, act.h, act.w) == (out.n, out.h, out.w)

@@ -102,14 +102,15 @@ def _dgrad_reqs(weight, cin_pad, lo, hi):
     return [(weight, 1, cin_pad, a, b - a) for a, b in _dgrad_chunks(lo, hi)]
 
 
-def _dgrad_s1(G, weight, out, lo, hi, prepped=None):
+def _dgrad_s1(G, weight, out, lo, hi, prepped=None, cy=None):
     """Channels [lo, hi) of the input gradient of a stride-1 layer with Parameter ``weight`` [Cout, Cin, 3, 3] from its output
     gradient ``G`` (all of G's channels are contracted; pad channels are zeros).  ``prepped``: the prepared weights of
     _dgrad_reqs(weight, G.cs, lo, hi) if the caller batched them."""
+    cy = G.cs if cy is None else cy          # contraction width: the layer's real output channels rounded up to 16
     if prepped is None:
-        prepped = dense.prep_conv3x3_weights_batch(_dgrad_reqs(weight, G.cs, lo, hi))
+        prepped = dense.prep_conv3x3_weights_batch(_dgrad_reqs(weight, cy, lo, hi))
     for (a, b), wp in zip(_dgrad_chunks(lo, hi), prepped):
-        dense.conv3x3_tc(G, G.cs, wp, None, b - a, 1, 0, out=out, out_off=a, out_zero_to=64 if a + 64 <= out.cs else 0)
+        dense.conv3x3_tc(G, cy, wp, None, b - a, 1, 0, out=out, out_off=a, out_zero_to=64 if a + 64 <= out.cs else 0)
 
 
 def _tap_mix(maps, w):
@@ -163,32 +164,34 @@ class GEDDenseTC(torch.autograd.Function):
         # conv1 as a GEMM over the im2col tensor: [80, 45] weights in the centre tap of a 3x3 tensor (the 1x1 kernel reads only it)
         w1 = torch.zeros((80, 45, 3, 3), device=W[0].device, dtype=torch.float32)
         w1[:, :, 1, 1] = W[0].permute(0, 2, 3, 1).reshape(80, 45)
-        reqs = [(w1, 0, 64, 0, 45)] + [(W[i], 0, cp, 0, W[i].shape[1]) for i, cp in ((1, 80), (2, 80), (3, 80), (4, 80), (5, 192), (6, 192),
-                                                                                   (7, 192), (8, 128))]
+        # contraction widths = the REAL channel counts rounded to the MMA's K = 16 (the row-segment kernel takes a K tail): 48 of the
+        # 64-channel im2col pixel, 160 / 144 / 144 / 112 of the 192 / 192 / 192 / 128-channel concat buffers, 32 of x9's 64
+        reqs = [(w1, 0, 48, 0, 45)] + [(W[i], 0, cp, 0, W[i].shape[1]) for i, cp in ((1, 80), (2, 80), (3, 80), (4, 80), (5, 160), (6, 144),
+                                                                                   (7, 144), (8, 112))]
         if P.quad:
-            reqs.append((_quad_head_weights(W[9]), 0, 64, 0, 32))
+            reqs.append((_quad_head_weights(W[9]), 0, 32, 0, 32))
         wp = dense.prep_conv3x3_weights_batch(reqs)
         # encoder: 3x3 stride 2 + ReLU, each output lands in the concat buffer of the decoder layer that reuses it
-        dense.conv1x1_tc(P.x45, 64, wp[0], Bz[0], 80, _RELU, out=P.cat9, out_off=32)
+        dense.conv1x1_tc(P.x45, 48, wp[0], Bz[0], 80, _RELU, out=P.cat9, out_off=32)
         c3(P.cat9, 80, wp[1], Bz[1], 80, 2, _RELU, x_off=32, out=P.cat8, out_off=64)
         c3(P.cat8, 80, wp[2], Bz[2], 80, 2, _RELU, x_off=64, out=P.cat7, out_off=64)
         c3(P.cat7, 80, wp[3], Bz[3], 80, 2, _RELU, x_off=64, out=P.cat6, out_off=80)
         c3(P.cat6, 80, wp[4], Bz[4], 80, 2, _RELU, x_off=80, out=P.x5, out_off=0)
         # decoder: nearest up-sampling into the slice, 3x3 stride 1 + LeakyReLU(0.2)
         dense.upsample_into(P.x5, 80, P.cat6, 0)
-        c3(P.cat6, 192, wp[5], Bz[5], 64, 1, _LEAKY, out=P.x6, out_zero_to=64)
+        c3(P.cat6, 160, wp[5], Bz[5], 64, 1, _LEAKY, out=P.x6, out_zero_to=64)
         dense.upsample_into(P.x6, 64, P.cat7, 0)
-        c3(P.cat7, 192, wp[6], Bz[6], 64, 1, _LEAKY, out=P.x7, out_zero_to=64)
+        c3(P.cat7, 144, wp[6], Bz[6], 64, 1, _LEAKY, out=P.x7, out_zero_to=64)
         dense.upsample_into(P.x7, 64, P.cat8, 0)
-        c3(P.cat8, 192, wp[7], Bz[7], 32, 1, _LEAKY, out=P.x8, out_zero_to=64)
+        c3(P.cat8, 144, wp[7], Bz[7], 32, 1, _LEAKY, out=P.x8, out_zero_to=64)
         dense.upsample_into(P.x8, 32, P.cat9, 0)
-        c3(P.cat9, 128, wp[8], Bz[8], 32, 1, _LEAKY, out=P.x9, out_zero_to=64)
+        c3(P.cat9, 112, wp[8], Bz[8], 32, 1, _LEAKY, out=P.x9, out_zero_to=64)
         # conv10 (33 -> 1 or 2 channels at full resolution): direct kernel, up-sampling folded into the addressing of x9
         x0_d = x0_d.contiguous()
         if P.quad:
             # quad form: a stride-1 convolution of x9 at its own resolution on the tensor cores (4 parity channels per output
             # channel), then un-shuffle + x0_d taps + bias + LeakyReLU at full resolution
-            c3(P.x9, 64, wp[9], None, 4 * oc, 1, 0, out=P.q10)
+            c3(P.x9, 32, wp[9], None, 4 * oc, 1, 0, out=P.q10)
             x10 = dense.quad_head_finish(P.q10, x0_d, W[9], Bz[9], h, w)
         else:
             x10 = dense.ged_head_fwd(P.x9, x0_d, W[9], Bz[9], h, w)
@@ -239,19 +242,20 @@ class GEDDenseTC(torch.autograd.Function):
         def add(key, rs):
             where[key] = (len(reqs), len(reqs) + len(rs))
             reqs.extend(rs)
+        dec_cy = {8: 32, 7: 32, 6: 64, 5: 64}        # contraction widths of the decoder data gradients = the layers' output channels
         for i in (8, 7, 6, 5):
-            add(i, _dgrad_reqs(W[i], 64, 0, dec_cin[i]))
+            add(i, _dgrad_reqs(W[i], dec_cy[i], 0, dec_cin[i]))
         # stride-2 layers conv5..conv2: quad form of the data gradient (dense.quad_maps 's2'): per parity block q a stride-1
         # convolution of the output gradient with the taps of W that reach that parity, [q][ci][co][3x3]
         _, s2 = dense.quad_maps(dev)
         masks, mask_all = dense.quad_s2_tap_masks()
         for i in (4, 3, 2, 1):
             wq = _tap_mix(s2, W[i].reshape(80, 80, 9)).permute(0, 2, 1, 3).contiguous().reshape(4, 80, 80, 3, 3)
-            add(i, [(wq[q], 0, 128, 0, 80) for q in range(4)])
+            add(i, [(wq[q], 0, 80, 0, 80) for q in range(4)])
         # conv1's data gradient is needed for xout_d and cout_d only (channels 0 and 4 of its input): quad form = a stride-1
         # convolution of G1 at ITS resolution with 4 parity x 2 output channels (dense.quad_maps 's2')
         Wd = _tap_mix(s2, torch.stack((W[0][:, 0], W[0][:, 4]), 1).reshape(80, 2, 9)).permute(0, 2, 1, 3).reshape(8, 80, 3, 3)
-        add(0, [(Wd, 0, 128, 0, 80)])
+        add(0, [(Wd, 0, 80, 0, 80)])
         prepped = dense.prep_conv3x3_weights_batch(reqs)
         wp = {k: prepped[a:b_] for k, (a, b_) in where.items()}
         # conv10 (LeakyReLU on the output too, confidence_depth_framework.py:506); produces G9 for conv9.
@@ -272,7 +276,7 @@ class GEDDenseTC(torch.autograd.Function):
             else:
                 G, gB[i] = b[gname], gb9
             gW[i] = wg(G, catk, cin, co, cin_pad=cin)
-            _dgrad_s1(G, W[i], b[gcat], 0, cin, prepped=wp[i])
+            _dgrad_s1(G, W[i], b[gcat], 0, cin, prepped=wp[i], cy=dec_cy[i])
         # encoder layers 5..1 (stride 2, ReLU): G5 from the up-sampling children only, G4..G1 = relu' * (dgrad + skip gradient)
         G, gb = asm(b["G5"], 80, a=b["gcat6"], act=P.x5, slope=0.0, colsum=True)
         enc = ((4, P.cat6, 80, 4, "gx4", "G4", "gcat6", 80), (3, P.cat7, 64, 3, "gx3", "G3", "gcat7", 64),
@@ -281,11 +285,11 @@ class GEDDenseTC(torch.autograd.Function):
             gB[i] = gb
             gW[i] = wgb(G, xin, 80, 80, 2, x_off=xoff, cin_pad=80)
             for q in range(4):
-                dense.conv3x3_tc(G, 128, wp[i][q], None, 80, 1, 0, out=b[gxn], out_off=80 * q, tap_mask=masks[q])
+                dense.conv3x3_tc(G, 80, wp[i][q], None, 80, 1, 0, out=b[gxn], out_off=80 * q, tap_mask=masks[q])
             G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True, a_quad=True)
         gB[0] = gb
         gw1 = off_path(dense.conv1x1_wgrad_tc, G, P.x45, 45, 80, cin_pad=48)       # [80, 45], channel (3u+v)*5 + c
-        dense.conv3x3_tc(G, 128, wp[0][0], None, 8, 1, 0, out=b["qin0"], tap_mask=mask_all)
+        dense.conv3x3_tc(G, 80, wp[0][0], None, 8, 1, 0, out=b["qin0"], tap_mask=mask_all)
         gin = dense.quad_unshuffle(b["qin0"], 2, hs[0], ws[0])
         if side is not main:
             main.wait_stream(side)
@@ -316,7 +320,8 @@ class ConfHeadTC(torch.autograd.Function):
         training = bool(bn.training or bn.running_mean is None)
         cpad = dense._r64(c)
         X = dense.to_nhwc_bf16(feat, cpad=cpad, pad=True)
-        Y = dense.conv3x3_tc(X, cpad, dense.prep_conv3x3_weights(w1, cin_pad=cpad), None, c, 1, 0, out_f32=True)
+        ck = dense._r16(c)                     # contraction width: 48 of the 64-channel pixel for the 36 GED features
+        Y = dense.conv3x3_tc(X, ck, dense.prep_conv3x3_weights(w1, cin_pad=ck), None, c, 1, 0, out_f32=True)
         momentum = bn.momentum if bn.momentum is not None else 0.1
         coef, ws = dense.conf_bn_stats(Y, c, gamma, beta, bn.running_mean, bn.running_var, momentum, bn.eps, training)
         conf = dense.conf_head_apply(Y, c, coef, w2, b2)
@@ -337,7 +342,7 @@ class ConfHeadTC(torch.autograd.Function):
         gfeat = None
         if ctx.needs_input_grad[0]:
             out = dense.new_act(n, h, w, dense._r64(c), conf.device, pad=True, border_only=True, dtype=torch.float32)
-            _dgrad_s1(G, w1, out, 0, c)
+            _dgrad_s1(G, w1, out, 0, c, cy=dense._r16(c))
             gfeat = dense.to_nchw_f32(out, c)
         ctx.X = ctx.Y = None
         return gfeat, gw1, gg, gb, gw2.view_as(w2), gb2, None
