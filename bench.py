@@ -408,6 +408,15 @@ def b200_arm(args):
     ms_serial = timed(from_host, min(args.steps, 5)) / min(args.steps, 5)      # the reference trainer's order: copy, step, read, next
     sampler_thread.stop_flag = True
 
+    # replicas must still be identical after the timed steps: every rank applied the same all-reduced gradients to the same weights
+    ranks_agree = None
+    if world > 1:
+        cs = torch.stack([p.detach().double().sum() for p in params]).sum().reshape(1)
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        ranks_agree = all(bool(torch.equal(c, allcs[0])) for c in allcs)
+        assert ranks_agree, "parameter checksums differ across ranks after the timed steps: %s" % [float(c) for c in allcs]
+
     # per-kernel CUDA-event timing of the same step (profiling pass after the timed region)
     roof = kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, args.kernel_detail if rank == 0 else "")
 
@@ -443,6 +452,8 @@ def b200_arm(args):
                 "serialised_ms_per_step": round(ms_serial, 4)},
         "gpu_launches": int(launches),
     }
+    if ranks_agree is not None:
+        line["param_checksum_equal_across_ranks"] = ranks_agree
     if roof:
         dom = roof["dominant"]
         tr_ = TRAFFIC.get(dom["name"]) or {}
