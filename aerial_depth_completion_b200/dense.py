@@ -1,8 +1,8 @@
-"""Dense (wide-channel) layers around the NConv pyramid: one dispatch point per op.
-
-BACKEND 'cudnn' routes to the ATen/cuDNN library call (what the reference itself executes on a GPU); it is the
-baseline these layers are measured against and is replaced op by op by the hand-written sm_100a kernels
-('native').  Nothing here runs on the CPU: inputs must be CUDA tensors (no CPU fallback).
+"""Host side of the tensor-core path of the dense (wide-channel) layers around the NConv pyramid: the arithmetic-mode switch, the
+NHWC activation container and thin typed wrappers of the C-ABI entry points (layout conversions, weight preparation, the tcgen05
+convolution / weight-gradient / glue kernels).  The nets' modules are plain ``nn.Conv2d`` / ``nn.BatchNorm2d`` parameter containers
+(identical ``state_dict`` keys); in the modes 'bf16x3' / 'bf16' their parameters are consumed by tc_train / tc_gms / tc_bn / tc_s2d, in
+'fp32' / 'tf32' the modules' own ATen forward runs (``BACKEND``: the measurement baseline).  Nothing here runs on the CPU.
 """
 import torch
 import torch.nn.functional as F
@@ -30,33 +30,6 @@ set_precision("bf16x3")      # the B200 path is the default: hand-written tcgen0
 def _need_cuda(x):
     if not x.is_cuda:
         raise RuntimeError("dense layer input must be a CUDA tensor: the B200 path has no CPU fallback")
-
-
-def conv2d(x, weight, bias=None, stride=1, padding=0):
-    _need_cuda(x)
-    return F.conv2d(x, weight, bias, stride, padding)
-
-
-def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, output_padding=0):
-    _need_cuda(x)
-    return F.conv_transpose2d(x, weight, bias, stride, padding, output_padding)
-
-
-def upsample_nearest(x, size):
-    _need_cuda(x)
-    return F.interpolate(x, size, mode="nearest")
-
-
-class Conv2d(torch.nn.Conv2d):
-    """nn.Conv2d with identical parameters / state_dict keys whose forward goes through the dispatch above."""
-
-    def forward(self, x):
-        return conv2d(x, self.weight, self.bias, self.stride, self.padding)
-
-
-class ConvTranspose2d(torch.nn.ConvTranspose2d):
-    def forward(self, x, output_size=None):
-        return conv_transpose2d(x, self.weight, self.bias, self.stride, self.padding, self.output_padding)
 
 
 # ---- tensor-core path (tcgen05 implicit GEMM, NHWC bf16) ---------------------------------------------------------------

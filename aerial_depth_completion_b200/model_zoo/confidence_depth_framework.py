@@ -219,10 +219,10 @@ class CBR3C1Confidence(nn.Module):
 
     def __init__(self, in_channels):
         super(CBR3C1Confidence, self).__init__()
-        self.conv1 = dense.Conv2d(in_channels, in_channels, 3, 1, 1, bias=False)
+        self.conv1 = nn.Conv2d(in_channels, in_channels, 3, 1, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(in_channels)
         self.relu1 = nn.LeakyReLU(0.2, inplace=True)
-        self.conv2 = dense.Conv2d(in_channels, 1, 1, 1, 0, bias=True)
+        self.conv2 = nn.Conv2d(in_channels, 1, 1, 1, 0, bias=True)
         for m in (self.conv1, self.bn1, self.conv2):
             init_weights(m)
 
@@ -242,17 +242,19 @@ class CBR3C1Confidence(nn.Module):
 
 
 class CBR3CBR1C1ResConfidence(nn.Module):
-    """(:372-409) conv3-BN-LReLU -> conv1-BN-LReLU -> conv1 over cat(second, first) -> sigmoid."""
+    """(:372-409) conv3-BN-LReLU -> conv1-BN-LReLU -> conv1 over cat(second, first) -> sigmoid.  Outside the hot-path scope (SURVEY 8a
+    lists cbr3-c1 only): kept so that --confnet-arch cbr3-cbr1-c1 / cbr3-cbr1-c1res resolve as in the reference (:51-54); it runs on ATen
+    modules, not on this library's kernels, and no measurement or parity claim covers it."""
 
     def __init__(self, in_channels):
         super(CBR3CBR1C1ResConfidence, self).__init__()
-        self.conv1 = dense.Conv2d(in_channels, in_channels, 3, 1, 1, bias=False)
+        self.conv1 = nn.Conv2d(in_channels, in_channels, 3, 1, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(in_channels)
         self.relu1 = nn.LeakyReLU(0.2, inplace=True)
-        self.conv2 = dense.Conv2d(in_channels, in_channels // 2, 1, 1, 0, bias=False)
+        self.conv2 = nn.Conv2d(in_channels, in_channels // 2, 1, 1, 0, bias=False)
         self.bn2 = nn.BatchNorm2d(in_channels // 2)
         self.relu2 = nn.LeakyReLU(0.2, inplace=True)
-        self.conv3 = dense.Conv2d(in_channels + (in_channels // 2), 1, 1, 1, 0, bias=True)
+        self.conv3 = nn.Conv2d(in_channels + (in_channels // 2), 1, 1, 1, 0, bias=True)
         for m in (self.conv1, self.bn1, self.conv2, self.bn2, self.conv3):
             init_weights(m)
 
@@ -290,16 +292,16 @@ class GEDNet(nn.Module):
         self.out_channels = out_channels
         self.out_feature_channels = 1 if out_channels == 2 else 36
         self.d_net = unguided_net(pos_fn)
-        self.conv1 = dense.Conv2d(5, 80, (3, 3), 2, 1, bias=True)
-        self.conv2 = dense.Conv2d(80, 80, (3, 3), 2, 1, bias=True)
-        self.conv3 = dense.Conv2d(80, 80, (3, 3), 2, 1, bias=True)
-        self.conv4 = dense.Conv2d(80, 80, (3, 3), 2, 1, bias=True)
-        self.conv5 = dense.Conv2d(80, 80, (3, 3), 2, 1, bias=True)
-        self.conv6 = dense.Conv2d(80 + 80, 64, (3, 3), 1, 1, bias=True)
-        self.conv7 = dense.Conv2d(64 + 80, 64, (3, 3), 1, 1, bias=True)
-        self.conv8 = dense.Conv2d(64 + 80, 32, (3, 3), 1, 1, bias=True)
-        self.conv9 = dense.Conv2d(32 + 80, 32, (3, 3), 1, 1, bias=True)
-        self.conv10 = dense.Conv2d(32 + 1, self.out_channels, (3, 3), 1, 1, bias=True)
+        self.conv1 = nn.Conv2d(5, 80, (3, 3), 2, 1, bias=True)
+        self.conv2 = nn.Conv2d(80, 80, (3, 3), 2, 1, bias=True)
+        self.conv3 = nn.Conv2d(80, 80, (3, 3), 2, 1, bias=True)
+        self.conv4 = nn.Conv2d(80, 80, (3, 3), 2, 1, bias=True)
+        self.conv5 = nn.Conv2d(80, 80, (3, 3), 2, 1, bias=True)
+        self.conv6 = nn.Conv2d(80 + 80, 64, (3, 3), 1, 1, bias=True)
+        self.conv7 = nn.Conv2d(64 + 80, 64, (3, 3), 1, 1, bias=True)
+        self.conv8 = nn.Conv2d(64 + 80, 32, (3, 3), 1, 1, bias=True)
+        self.conv9 = nn.Conv2d(32 + 80, 32, (3, 3), 1, 1, bias=True)
+        self.conv10 = nn.Conv2d(32 + 1, self.out_channels, (3, 3), 1, 1, bias=True)
         for i in range(1, 11):
             m = getattr(self, 'conv%d' % i)
             nn.init.kaiming_normal_(m.weight)
@@ -318,7 +320,8 @@ class GEDNet(nn.Module):
             if build_conf_input:
                 features = torch.cat((last_layer_input, xout_d, cout_d, x10), 1) if want else torch.sigmoid(x10[:, 1:2, :, :])
             return x10[:, 0:1, :, :], features
-        up = dense.upsample_nearest
+        dense._need_cuda(x0)
+        up = lambda t, size: F.interpolate(t, size, mode='nearest')      # library baseline path (precision 'fp32' / 'tf32')
         x1 = F.relu(self.conv1(torch.cat((xout_d, x0_rgb, cout_d), 1)))
         x2 = F.relu(self.conv2(x1))
         x3 = F.relu(self.conv3(x2))
@@ -342,7 +345,7 @@ class GEDNet(nn.Module):
 def _conv_stack(first_in, widths):
     layers, cin = [], first_in
     for cout in widths:
-        layers += [dense.Conv2d(cin, cout, 3, 1, 1), nn.ReLU()]
+        layers += [nn.Conv2d(cin, cout, 3, 1, 1), nn.ReLU()]
         cin = cout
     return nn.Sequential(*layers)
 
@@ -358,7 +361,7 @@ class GMSNet(nn.Module):
         self.d = _conv_stack(1, [16] * 6)
         self.rgb = _conv_stack(4, [64] * 6)
         self.fuse = _conv_stack(80, [64, 64, 64, 32, 32, 32])
-        self.last_layer = dense.Conv2d(32, out_channels, 1, 1)
+        self.last_layer = nn.Conv2d(32, out_channels, 1, 1)
         for seq in (self.d, self.rgb, self.fuse):
             for p in seq:
                 if isinstance(p, nn.Conv2d):
