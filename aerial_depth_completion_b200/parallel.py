@@ -118,6 +118,13 @@ class DataParallelTrainer:
             self._static_loss = self._eager_step(self._static_in, self._static_tg)
         return self
 
+    def release(self):
+        """Drop the captured step graph and its static buffers (later steps run eagerly again).  A graph that recorded NCCL
+        collectives keeps the communicator's work alive; release it -- and synchronise -- before ``dist.destroy_process_group()``."""
+        self._graph = None
+        self._static_in = self._static_tg = self._static_loss = None
+        torch.cuda.synchronize()
+
     def step(self, inp, target):
         """forward + loss + zero_grad + backward + gradient all-reduce + optimizer step (trainer.py:202-216)."""
         if getattr(self, "_graph", None) is not None:

@@ -271,17 +271,30 @@ class ClockSampler(threading.Thread):
                 "source": self.source}
 
 
-def _finish(world):
-    """End of a multi-rank run.  Measured on 2xB200: dist.destroy_process_group() after the step graph (which holds the captured
-    NCCL all-reduce) has been replayed never returns, so the ranks meet at a last barrier, flush and leave without tearing the
-    communicator down (the process exit releases it)."""
+def _finish(world, trainer=None):
+    """End of a multi-rank run.  Round 1 measured that dist.destroy_process_group() never returned after the step graph (which holds
+    the captured NCCL all-reduces) had been replayed.  The ranks now release the graph first (parallel.DataParallelTrainer.release),
+    meet at a barrier and tear the communicator down under a watchdog: if the teardown has not returned after 20 s the process
+    leaves with os._exit(0) as before (the JSON line is already flushed either way); the outcome is printed on stderr."""
     if world <= 1:
         return
     import torch
     import torch.distributed as dist
+    if trainer is not None:
+        trainer.release()
     dist.barrier()
     torch.cuda.synchronize()
     sys.stdout.flush()
+    sys.stderr.flush()
+    timer = threading.Timer(20.0, lambda: (sys.stderr.write("bench: destroy_process_group() did not return within 20 s; leaving\n"),
+                                           sys.stderr.flush(), os._exit(0)))
+    timer.daemon = True
+    timer.start()
+    t0 = time.perf_counter()
+    dist.destroy_process_group()
+    timer.cancel()
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("bench: destroy_process_group() returned after %.2f s\n" % (time.perf_counter() - t0))
     sys.stderr.flush()
     os._exit(0)
 
@@ -421,7 +434,7 @@ def b200_arm(args):
     roof = kernel_roofline(trainer, dev_in, dev_tg, pool_n, B, args.kernel_detail if rank == 0 else "")
 
     if rank != 0:
-        _finish(world)
+        _finish(world, trainer)
         return
     peak, peak_src = peaks()
     frames = B * world * args.steps
@@ -513,7 +526,7 @@ def b200_arm(args):
         if cb is not None:
             line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
-    _finish(world)
+    _finish(world, trainer)
 
 
 def reference_on_gpu(dev, B):
