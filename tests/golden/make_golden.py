@@ -180,6 +180,8 @@ def case_nets(out):
     run_framework(out, "s2d_cf", "dc1-cf1-ln0", "resnet18", (64, 80), conf_arch="cbr3-c1", ln_arch="ged_depthcompnet")
     # BASELINE config 5's shape (odd sizes all the way down: 114x152 -> 57x76 -> 29x38 -> 15x19 -> 8x10, bilinear 128x160 -> 228x304)
     run_framework(out, "s2d_nyu", "dc1_only", "resnet18", (228, 304), seed=11)
+    run_framework(out, "s2d_eval", "dc1_only", "resnet18", (64, 80), train=False, seed=3)       # running statistics, no batch pass
+    run_framework(out, "s2d_odd", "dc1_only", "resnet18", (93, 121), batch=3, criterion="l1", seed=4)   # odd at every level
     grad_noise_floor(out)
 
 
