@@ -180,6 +180,9 @@ def case_nets(out):
     run_framework(out, "s2d_cf", "dc1-cf1-ln0", "resnet18", (64, 80), conf_arch="cbr3-c1", ln_arch="ged_depthcompnet")
     # BASELINE config 5's shape (odd sizes all the way down: 114x152 -> 57x76 -> 29x38 -> 15x19 -> 8x10, bilinear 128x160 -> 228x304)
     run_framework(out, "s2d_nyu", "dc1_only", "resnet18", (228, 304), seed=11)
+    # two-channel depth-completion nets (depth + own confidence, confidence_depth_framework.py:512 / s2d_u_resnet.py:181 / s2d_resnet.py:239)
+    run_framework(out, "s2d_dc1ln0", "dc1-ln0", "resnet18", (64, 80), ln_arch="ged_depthcompnet", seed=5)
+    run_framework(out, "gud_dc1ln0", "dc1-ln0", "gudepthcompnet18", (32, 48), ln_arch="ged_depthcompnet", seed=6)
     run_framework(out, "s2d_eval", "dc1_only", "resnet18", (64, 80), train=False, seed=3)       # running statistics, no batch pass
     run_framework(out, "s2d_odd", "dc1_only", "resnet18", (93, 121), batch=3, criterion="l1", seed=4)   # odd at every level
     grad_noise_floor(out)
