@@ -163,6 +163,7 @@ SIGNATURES = {
     "adc_nchw_to_nhwc_f32": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_adam_step_dev": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, c_ll, _vp]),
     "adc_im2col_kxk_pack": (c_int, [_vp, c_ll, c_int, c_int, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, _vp]),
+    "adc_col2im_kxk": (c_int, [_vp, c_int, c_int, c_int, c_int, c_int, _vp, c_int, c_int, c_int, _vp]),
     "adc_maxpool3x3s2_fwd": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_maxpool3x3s2_bwd": (c_int, [_vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),
     "adc_pixel_shuffle_f32": (c_int, [_vp, c_int, c_int, _vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp]),

@@ -88,6 +88,31 @@ __global__ void __launch_bounds__(256) im2col_kxk_kernel(const float* __restrict
     }
 }
 
+// Adjoint of im2col_kxk: gx[n][c][y][x] = sum over the taps (u, v) and output pixels (i, j) with stride*i + u - pad == y, stride*j + v - pad == x
+// of gcol[n][i][j][(u*K + v)*C + c].  A gather (every input pixel visits the <= ceil(K/stride)^2 windows that contain it): no atomics.
+// thread = one input pixel (x fastest: coalesced NCHW stores), loops over the C planes.
+__global__ void __launch_bounds__(256) col2im_kxk_kernel(const float* __restrict__ gcol, int gs, int C, int K, int stride, int pad,
+                                                         float* __restrict__ gx, int N, int H, int W, int Ho, int Wo) {
+    const long long total = (long long)N * H * W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(t % W), y = (int)((t / W) % H);
+        const long long n = t / ((long long)W * H);
+        for (int c = 0; c < C; ++c) {
+            float acc = 0.f;
+            for (int u = (y + pad) % stride; u < K; u += stride) {
+                const int i = (y + pad - u) / stride;
+                if (y + pad - u < 0 || i >= Ho) continue;
+                for (int v = (x + pad) % stride; v < K; v += stride) {
+                    const int j = (x + pad - v) / stride;
+                    if (x + pad - v < 0 || j >= Wo) continue;
+                    acc += __ldg(gcol + bpix(n, i, j, Ho, Wo) * gs + (u * K + v) * C + c);
+                }
+            }
+            gx[((n * C + c) * H + y) * W + x] = acc;
+        }
+    }
+}
+
 // ---- MaxPool2d(3, 2, 1) ----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const bf16* __restrict__ xh, const bf16* __restrict__ xl, int xs,
                                                           bf16* __restrict__ oh, bf16* __restrict__ ol, int os, unsigned char* __restrict__ idx,
@@ -313,6 +338,20 @@ int adc_im2col_kxk_pack(const float* src, long long batch_stride, int C, int K, 
     im2col_kxk_kernel<<<grid_for(total), 256, 0, st>>>(src, batch_stride, C, K, stride, pad, reinterpret_cast<bf16*>(dst),
                                                       reinterpret_cast<bf16*>(dst_lo), dst_stride, groups, N, H, W, Ho, Wo);
     return adc::check_cuda(cudaGetLastError(), "im2col_kxk_kernel launch");
+}
+
+int adc_col2im_kxk(const float* gcol, int gcol_stride, int C, int K, int stride, int pad, float* gx, int N, int H, int W, adc_stream_t stream) {
+    if (!gcol || !gx || C <= 0 || K <= 0 || K > 11 || (stride != 1 && stride != 2) || pad < 0 || gcol_stride < K * K * C || N <= 0 || H <= 0 ||
+        W <= 0) {
+        adc::set_error("adc_col2im_kxk: bad argument");
+        return ADC_E_BADARG;
+    }
+    const int Ho = (H + 2 * pad - K) / stride + 1, Wo = (W + 2 * pad - K) / stride + 1;
+    const long long total = (long long)N * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    adc::Prof prof(st, adc::KIND_TC_LAYOUT, (double)N * Ho * Wo * K * K * C * 4.0 + (double)total * C * 4.0);
+    col2im_kxk_kernel<<<grid_for(total), 256, 0, st>>>(gcol, gcol_stride, C, K, stride, pad, gx, N, H, W, Ho, Wo);
+    return adc::check_cuda(cudaGetLastError(), "col2im_kxk_kernel launch");
 }
 
 int adc_maxpool3x3s2_fwd(const void* x, const void* x_lo, int x_stride, int x_off, void* out, void* out_lo, int out_stride, int out_off,

@@ -248,9 +248,6 @@ class S2DBodyTC(torch.autograd.Function):
         net, P = ctx.net, ctx.plan
         if P.forward_id != ctx.fid:
             raise RuntimeError("S2DBodyTC: the module ran another forward before this backward; its saved activations are gone")
-        if ctx.needs_input_grad[2]:
-            raise NotImplementedError("S2DResNet on the tensor-core path does not return a gradient for its input frames (no configuration of "
-                                      "the reference's factory asks for one: the loss nets are NConv nets)")
         names = _param_names(net)
         grads = {}
         n, h, w = P.n, P.h, P.w
@@ -268,6 +265,11 @@ class S2DBodyTC(torch.autograd.Function):
         wp.transposed("conv2", T.embed_1x1(net.conv2.weight), 256, flip=False)
         for name, lvl, ci, co, stride in _STAGES:
             T.stage_prep_bwd(wp, getattr(net, name), name, ci, co, stride)
+        cin0 = net.in_channels
+        if ctx.needs_input_grad[2]:      # S2DResNet as a loss net: rgb | depth1 | conf1 -> the last two need their gradient
+            w1e = torch.zeros((64, P.kc, 3, 3), device=P.dev, dtype=torch.float32)
+            w1e[:, :49 * cin0, 1, 1] = net.conv1.weight.detach().permute(0, 2, 3, 1).reshape(64, 49 * cin0)
+            wp.transposed("stem", w1e, 64, flip=False)
         W = wp.run()
         # ---- bilinear + conv3
         F_ = P.X[("up", 3, "out")]
@@ -338,10 +340,17 @@ class S2DBodyTC(torch.autograd.Function):
         D1 = P.d("stem", 0, 64)
         gg, gbeta = bn_backward(Ga, 0, P.Y["stem"], 0, A, 0, P.S["stem"], RELU, D1, 0, 64)
         grads["bn1.weight"], grads["bn1.bias"] = gg, gbeta
-        cin0 = net.in_channels
         dw1 = _wgrad_1x1(D1, 64, P.x49, 0, 49 * cin0)
         grads["conv1.weight"] = dw1.reshape(64, 7, 7, cin0).permute(0, 3, 1, 2).contiguous()
-        return (None, None, None, *[grads.get(nm) for nm in names])
+        gx = None
+        if ctx.needs_input_grad[2]:
+            # data gradient of the stem: the GEMM's transpose gives the gradient of the im2col tensor, col2im gathers it back
+            Gcol = P.g("col", 0, P.kc)
+            for a, b in _chunks(P.kc, _chunk()):
+                conv(K_1X1, D1, 0, 64, W[("stem", a)], Gcol, a, b - a, hs[0], ws[0])
+            gx = torch.empty((n, cin0, h, w), device=P.dev, dtype=torch.float32)
+            check(lib.adc_col2im_kxk(Gcol.hi.data_ptr(), Gcol.cs, cin0, 7, 2, 3, gx.data_ptr(), n, h, w, dense._stream()), "adc_col2im_kxk")
+        return (None, None, gx, *[grads.get(nm) for nm in names])
 
 
 def _param_names(net):

@@ -429,6 +429,9 @@ int adc_adam_step_dev(float* param, const float* grad, float* exp_avg, float* ex
  *                        accumulated) = its adjoint, computed as a deterministic gather. */
 int adc_im2col_kxk_pack(const float* src, long long batch_stride, int C, int K, int stride, int pad, void* dst, void* dst_lo, int dst_stride,
                         int dst_channels, int N, int H, int W, adc_stream_t stream);
+/* Adjoint of adc_im2col_kxk_pack: gcol fp32 zero-bordered NHWC [N][Ho+2][Wo+2][gcol_stride] (channel (u*K + v)*C + c) -> gx fp32 NCHW
+ * [N][C][H][W]: the data gradient of the im2col'ed stem convolution (deterministic gather). */
+int adc_col2im_kxk(const float* gcol, int gcol_stride, int C, int K, int stride, int pad, float* gx, int N, int H, int W, adc_stream_t stream);
 int adc_maxpool3x3s2_fwd(const void* x, const void* x_lo, int x_stride, int x_off, void* out, void* out_lo, int out_stride, int out_off,
                          unsigned char* idx, int N, int C, int H, int W, adc_stream_t stream);
 int adc_maxpool3x3s2_bwd(const float* g, int g_stride, int g_off, const unsigned char* idx, float* gin, int gin_stride, int gin_off, int N, int C,

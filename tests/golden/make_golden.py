@@ -183,6 +183,8 @@ def case_nets(out):
     # two-channel depth-completion nets (depth + own confidence, confidence_depth_framework.py:512 / s2d_u_resnet.py:181 / s2d_resnet.py:239)
     run_framework(out, "s2d_dc1ln0", "dc1-ln0", "resnet18", (64, 80), ln_arch="ged_depthcompnet", seed=5)
     run_framework(out, "gud_dc1ln0", "dc1-ln0", "gudepthcompnet18", (32, 48), ln_arch="ged_depthcompnet", seed=6)
+    # S2DResNet as the loss net (--lossnet-arch resnet18): its input rgb | depth1 | conf1 needs a gradient (5-channel 7x7 stem)
+    run_framework(out, "ged_s2dln", "dc1-ln1", "ged_depthcompnet", (64, 80), ln_arch="resnet18", seed=8)
     run_framework(out, "s2d_eval", "dc1_only", "resnet18", (64, 80), train=False, seed=3)       # running statistics, no batch pass
     run_framework(out, "s2d_odd", "dc1_only", "resnet18", (93, 121), batch=3, criterion="l1", seed=4)   # odd at every level
     grad_noise_floor(out)

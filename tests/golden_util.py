@@ -34,7 +34,7 @@ def g_like(t, seed):
 
 
 NET_TAGS = ("ged_nyu", "ged_only", "ged_only_eval", "ged_dc1", "ged_full", "ged_ln0", "ged_dc0", "ged_dcln", "ged_odd",
-            "gms_only", "gms_full", "gud_only", "gud_only_eval", "gud_ln0", "gud_mid", "ud_only", "s2d_only", "s2d_cf", "s2d_nyu", "s2d_eval", "s2d_odd", "s2d_dc1ln0", "gud_dc1ln0")
+            "gms_only", "gms_full", "gud_only", "gud_only_eval", "gud_ln0", "gud_mid", "ud_only", "s2d_only", "s2d_cf", "s2d_nyu", "s2d_eval", "s2d_odd", "s2d_dc1ln0", "gud_dc1ln0", "ged_s2dln")
 
 
 def net_case(tag, dtype=torch.float32):

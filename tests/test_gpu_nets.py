@@ -68,7 +68,8 @@ def _framework_vs_golden(tag, mode=None):
     G = gold("nets")
     cfg, state, inp, tgt = net_case(tag)
     f, m, params = build(cfg, state)
-    bn_net = cfg["dc_arch"] in ("gudepthcompnet18", "udepthcompnet18", "resnet18")
+    _bn = ("gudepthcompnet18", "udepthcompnet18", "resnet18")
+    bn_net = cfg["dc_arch"] in _bn or cfg["ln_arch"] in _bn
     d1, c1, d2 = m(inp.cuda())
     for name, v in (("d1", d1), ("c1", c1), ("d2", d2)):
         if v is None:

@@ -265,3 +265,29 @@ def test_bn_net_vs_golden_at_a_well_conditioned_size(tag):
     assert floor
     bad = grad_rule_violations([(k, p.grad) for k, p in m.named_parameters() if k in floor], S, floor, "bf16x3")
     assert not bad, bad
+
+
+@pytest.mark.parametrize("cin,hw", [(5, (21, 30)), (4, (16, 24))])
+def test_stem_data_gradient_col2im(cin, hw):
+    """Data gradient of the 7x7 / stride-2 stem (S2DResNet as a loss net): transpose GEMM + adc_col2im_kxk vs fp64 autograd."""
+    from aerial_depth_completion_b200 import dense, tc_bn
+    from aerial_depth_completion_b200._lib import lib, check
+    n, (h, w) = 2, hw
+    x = _rand(n, cin, h, w, seed=14).requires_grad_(True)
+    wt = _rand(64, cin, 7, 7, seed=15, scale=0.1)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    g = _rand(n, 64, ho, wo, seed=16)
+    (F.conv2d(x, wt, stride=2, padding=3) * g).sum().backward()
+    kc = dense._r16(49 * cin)
+    w1e = torch.zeros((64, kc, 3, 3), device="cuda")
+    w1e[:, :49 * cin, 1, 1] = wt.float().cuda().permute(0, 2, 3, 1).reshape(64, 49 * cin)
+    wp = tc_bn.WPrep()
+    wp.transposed("stem", w1e, 64, flip=False)
+    W = wp.run()
+    D = _pair(g)
+    Gcol = tc_bn.f32_act(n, ho, wo, dense._r64(kc), "cuda")
+    for a, b in tc_bn._chunks(kc, tc_bn._chunk()):
+        tc_bn.conv(tc_bn.K_1X1, D, 0, 64, W[("stem", a)], Gcol, a, b - a, ho, wo)
+    gx = torch.empty((n, cin, h, w), device="cuda")
+    check(lib.adc_col2im_kxk(Gcol.hi.data_ptr(), Gcol.cs, cin, 7, 2, 3, gx.data_ptr(), n, h, w, dense._stream()), "col2im")
+    assert relmax(gx.cpu(), x.grad) < 1e-4
