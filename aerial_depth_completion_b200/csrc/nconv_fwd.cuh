@@ -27,7 +27,7 @@ struct TileCfg {
     static constexpr int SH = TH + 2 * P;
     static constexpr int PLANE_BYTES = ((SH * SWP * 8 + 127) / 128) * 128;  // TMA destinations are 128-B aligned
     static constexpr int PLANE = PLANE_BYTES / 8;                           // in pairs
-    static constexpr int smem_bytes(int planes) { return planes * PLANE_BYTES + 128 + 16; }
+    static constexpr int smem_bytes(int planes) { return planes * PLANE_BYTES + 128 + 64; }      // + alignment slack + up to 8 mbarriers
 };
 
 struct Maps2 {
@@ -220,6 +220,41 @@ __device__ __forceinline__ void premul_planes(float2* planes, int nplanes, int t
     }
 }
 
+// One input plane of the conv core: acc[no][row][px] += sum_{u,v} plane(row+u, px+v) * w[(no*NIN + ni)*K*K + u*K + v].
+template <int NIN, int NOUT, int K>
+__device__ __forceinline__ void conv_patch_plane(const float2* plane, const float* __restrict__ w, int ni, int tx, int ty,
+                                                 float2 (&acc)[NOUT][8][2]) {
+    using C = TileCfg<K>;
+    constexpr int XO = C::XOFF;
+    constexpr int NP = (2 + K - 1 + XO + 1) & ~1;
+    const float2* row0 = plane + (ty * 8) * C::SWP + tx * 2;
+    const float* wn = w + ni * K * K;
+    static_for<8 + K - 1>([&](auto ir_c) {
+        constexpr int ir = decltype(ir_c)::value;
+        float2 in[NP];
+#pragma unroll
+        for (int t = 0; t < NP / 2; ++t) {
+            const float4 a = *reinterpret_cast<const float4*>(row0 + ir * C::SWP + 2 * t);
+            in[2 * t] = make_float2(a.x, a.y);
+            in[2 * t + 1] = make_float2(a.z, a.w);
+        }
+        static_for<8>([&](auto orow_c) {
+            constexpr int orow = decltype(orow_c)::value;
+            constexpr int u = ir - orow;
+            if constexpr (u >= 0 && u < K) {
+#pragma unroll
+                for (int v = 0; v < K; ++v)
+#pragma unroll
+                    for (int no = 0; no < NOUT; ++no) {
+                        const float wv = wn[no * NIN * K * K + u * K + v];
+                        acc[no][orow][0] = ffma2(in[XO + v], bcast(wv), acc[no][orow][0]);
+                        acc[no][orow][1] = ffma2(in[XO + v + 1], bcast(wv), acc[no][orow][1]);
+                    }
+            }
+        });
+    });
+}
+
 // Co = 2 (the float4 store packs two pixels of one channel); the 1x1 2->1 head has its own kernel below.
 template <int CI, int K>
 __global__ void __launch_bounds__(128) nconv_fwd_kernel(const __grid_constant__ Maps2 maps, SrcP s0, SrcP s1, int has1,
@@ -232,19 +267,49 @@ __global__ void __launch_bounds__(128) nconv_fwd_kernel(const __grid_constant__ 
     const int n = blockIdx.z, h0 = blockIdx.y * C::TH, w0 = blockIdx.x * C::TW;
     const float* wc = &c_wimg[0][0][0][0] + (size_t)wimg * kWStride;
 
-    const bool pending = stage_sources<K, 128>(maps, s0, s1, has1 != 0, n, h0, w0, H, W, planes, bar, tid);
-    __syncthreads();
-    if (pending) mbar_wait(bar, 0);
-    expand_up2_planes<K, 128>(s0, s1, has1 != 0, planes, tid);
-    premul_planes<K, 128>(planes, CI, tid);
-    __syncthreads();
-
     const int tx = tid & 31, ty = tid >> 5;
     const int oh = h0 + ty * 8, ow = w0 + tx * 2;
-    if (oh >= H || ow >= W) return;
-
     float2 acc[2][8][2];
-    conv_patch<CI, 2, K>(planes, wc, tx, ty, acc);
+    if (s0.tma && (!has1 || s1.tma)) {
+        // Every plane arrives by its own TMA box on its own mbarrier: the warps start accumulating plane 0 while the boxes of the
+        // other planes are still in flight (the five resident CTAs of an SM tend to run their load / compute / store phases in step,
+        // so the overlap has to come from inside the CTA too).
+        if (tid == 0)
+            for (int c = 0; c < CI; ++c) mbar_init(bar + c, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const int x0 = 2 * (w0 - C::P - C::XOFF), y0 = h0 - C::P;
+            for (int c = 0; c < CI; ++c) {
+                mbar_expect_tx(bar + c, (uint32_t)(C::SH * C::SWP * 8));
+                const bool first = c < s0.ch;
+                tma_load_plane(planes + c * C::PLANE, first ? &maps.m0 : &maps.m1, bar + c, x0, y0, first ? c : c - s0.ch, n);
+            }
+        }
+        const bool active = oh < H && ow < W;
+#pragma unroll
+        for (int co = 0; co < 2; ++co)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[co][r][0] = acc[co][r][1] = make_float2(0.f, 0.f);
+        // a real loop over the planes (weights indexed through a uniform register): half the code of the unrolled form, which
+        // spent 0.8 stall cycles per issue waiting for instructions (ncu no_instruction) with five CTAs in different phases
+#pragma unroll 1
+        for (int ci = 0; ci < CI; ++ci) {
+            mbar_wait(bar + ci, 0);
+            premul_planes<K, 128>(planes + ci * C::PLANE, 1, tid);
+            __syncthreads();
+            if (active) conv_patch_plane<CI, 2, K>(planes + ci * C::PLANE, wc, ci, tx, ty, acc);
+        }
+        if (!active) return;
+    } else {
+        const bool pending = stage_sources<K, 128>(maps, s0, s1, has1 != 0, n, h0, w0, H, W, planes, bar, tid);
+        __syncthreads();
+        if (pending) mbar_wait(bar, 0);
+        expand_up2_planes<K, 128>(s0, s1, has1 != 0, planes, tid);
+        premul_planes<K, 128>(planes, CI, tid);
+        __syncthreads();
+        if (oh >= H || ow >= W) return;
+        conv_patch<CI, 2, K>(planes, wc, tx, ty, acc);
+    }
 
     const long long plane = (long long)H * W;
     const bool vec = (W & 1) == 0;
@@ -301,41 +366,6 @@ struct TileSched {
     int* counters;   // [0] next tile, [1] finished CTAs (self-resetting: the last CTA to leave zeroes both)
     int tiles_x, tiles_y, ntiles;
 };
-
-// One input plane of the conv core: acc[no][row][px] += sum_{u,v} plane(row+u, px+v) * w[(no*NIN + ni)*K*K + u*K + v].
-template <int NIN, int NOUT, int K>
-__device__ __forceinline__ void conv_patch_plane(const float2* plane, const float* __restrict__ w, int ni, int tx, int ty,
-                                                 float2 (&acc)[NOUT][8][2]) {
-    using C = TileCfg<K>;
-    constexpr int XO = C::XOFF;
-    constexpr int NP = (2 + K - 1 + XO + 1) & ~1;
-    const float2* row0 = plane + (ty * 8) * C::SWP + tx * 2;
-    const float* wn = w + ni * K * K;
-    static_for<8 + K - 1>([&](auto ir_c) {
-        constexpr int ir = decltype(ir_c)::value;
-        float2 in[NP];
-#pragma unroll
-        for (int t = 0; t < NP / 2; ++t) {
-            const float4 a = *reinterpret_cast<const float4*>(row0 + ir * C::SWP + 2 * t);
-            in[2 * t] = make_float2(a.x, a.y);
-            in[2 * t + 1] = make_float2(a.z, a.w);
-        }
-        static_for<8>([&](auto orow_c) {
-            constexpr int orow = decltype(orow_c)::value;
-            constexpr int u = ir - orow;
-            if constexpr (u >= 0 && u < K) {
-#pragma unroll
-                for (int v = 0; v < K; ++v)
-#pragma unroll
-                    for (int no = 0; no < NOUT; ++no) {
-                        const float wv = wn[no * NIN * K * K + u * K + v];
-                        acc[no][orow][0] = ffma2(in[XO + v], bcast(wv), acc[no][orow][0]);
-                        acc[no][orow][1] = ffma2(in[XO + v + 1], bcast(wv), acc[no][orow][1]);
-                    }
-            }
-        });
-    });
-}
 
 // Persistent forward kernel, pipelined at the granularity of ONE input-channel plane of one tile: two plane buffers per
 // CTA (39 KB for any Ci, so 5 CTAs = 20 warps per SM stay resident); while the warps accumulate plane q, the TMA box (or the
