@@ -191,8 +191,6 @@ _SCRATCH = {}
 def _scratch_f32(n, h, w, c, dev):
     key = (n, h, w, c, str(dev))
     if key not in _SCRATCH:
-        if len(_SCRATCH) >= 12:          # a net needs <= 6 shapes; another batch size / resolution starts over (buffers of a live CUDA
-            _SCRATCH.clear()             # graph stay alive through the graph's own references)
         _SCRATCH[key] = f32_act(n, h, w, c, dev)
     return _SCRATCH[key]
 
