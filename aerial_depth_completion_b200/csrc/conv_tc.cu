@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== TMA producer =====
             for (int ks = 0; ks < ksteps; ++ks) {
                 const int s = ks % kStages, use = ks / kStages;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== MMA issuer =====
             const uint32_t idesc = make_idesc(128, p.npad);
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== TMA producer =====
             if (p.resident) {      // all weight tiles once: they stay in shared memory for every tile of this CTA
                 mbar_expect_tx(&bars[20], (uint32_t)res_bytes);
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== MMA issuer =====
             const uint32_t idesc = make_idesc(128, acc_cols);
             const uint32_t sbase = base + res_bytes;

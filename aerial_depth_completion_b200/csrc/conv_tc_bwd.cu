@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== TMA producer =====
             const uint32_t tx = (uint32_t)((p.mb * p.kp + p.nb * (p.kp + 2)) * 128 * (p.split ? 2 : 1));
             for (int i = 0; i < my_tiles; ++i) {
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== MMA issuer =====
             const uint32_t idesc = make_idesc_mn(128, p.ncols);
             const uint32_t lbo_a = p.mb > 1 ? (uint32_t)(p.kp * 128) : 0u;    // one block only: rows 64..127 replay rows 0..63 (never read back)
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t tx = (uint32_t)(half * (p.split ? 2 : 1));
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % nst, use = i / nst;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_mn(128, p.ncols);
             const uint32_t lbo_a = p.mb > 1 ? (uint32_t)blk : 0u, lbo_b = (uint32_t)blk;
             const int ksteps = p.kp / 16;

@@ -91,6 +91,21 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA
+// elect.sync: exactly one lane of the (converged) warp gets `true`.  Unlike `lane == 0` the compiler KNOWS the region behind it runs on
+// a single thread, so the uniform-register operands of UTCHMMA / UTMALDG need no per-instruction ELECT / BRA.U.ANY "waterfall" loop:
+// ncu's source view showed the issuing warp spending its time in that loop, 135 cycles per MMA (profiles/r2_ncu_rowseg_forward_b128.txt).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
