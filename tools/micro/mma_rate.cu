@@ -11,7 +11,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
 
 // mode 0: K-major A and B, same accumulator; 1: alternate 2 accumulators; 2: MN-major A and B; 3: K-major, A fixed / B fixed but
 // 4 different k offsets (like the conv loop)
-__global__ void __launch_bounds__(192) mma_rate_kernel(int N, int reps, int mode, long long* out) {
+__global__ void __launch_bounds__(192) mma_rate_kernel(int N, int reps, int mode, long long* out, int elect_mode) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(192) mma_rate_kernel(int N, int reps, int mode
                 if (blockIdx.x == 0) out[0] = t1 - t0;
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1 && (elect_mode ? elect_one() : lane == 0)) {
         uint32_t idesc = make_idesc(128, N);
         if (mode == 2) idesc |= (1u << 15) | (1u << 16);
         const uint32_t a = base, b = base + 32768;
@@ -74,14 +74,16 @@ int main() {
     cudaMalloc(&d, 8);
     cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     const int reps = 2000;
-    for (int mode = 4; mode < 5; ++mode)
+    // issuer selected by lane == 0 (the compiler wraps every UTCHMMA in an ELECT / BRA.U.ANY loop) vs elect.sync (modes 0..2)
+    for (int elect_mode = 0; elect_mode < 2; ++elect_mode)
+    for (int mode = 0; mode < 3; ++mode)
         for (int N : {16, 32, 64, 96, 128, 192, 256}) {
             for (int grid : {148}) {
-                mma_rate_kernel<<<grid, 192, 100 * 1024>>>(N, reps, mode, d);
+                mma_rate_kernel<<<grid, 192, 100 * 1024>>>(N, reps, mode, d, elect_mode);
                 cudaError_t e = cudaDeviceSynchronize();
                 long long h = 0;
                 cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-                printf("mode %d N %3d grid %3d: %6.1f clk/MMA  (floor %d)  %s\n", mode, N, grid, (double)h / (reps * 4), 128 * N / 256,
+                printf("issuer %s mode %d N %3d grid %3d: %6.1f clk/MMA  (floor %d)  %s\n", elect_mode ? "elect.sync" : "lane==0   ", mode, N, grid, (double)h / (reps * 4), 128 * N / 256,
                        e == cudaSuccess ? "" : cudaGetErrorString(e)); fflush(stdout);
             }
         }
