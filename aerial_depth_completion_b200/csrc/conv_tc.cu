@@ -341,12 +341,20 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
             // ===== MMA issuer =====
             const uint32_t idesc = make_idesc(128, acc_cols);
             const uint32_t sbase = base + res_bytes;
-            if (p.resident) {
+            // Everything that does not change from MMA to MMA is computed once: the asm of an MMA clobbers "memory", so the compiler
+            // re-read kernel parameters and rebuilt both 64-bit descriptors after every instruction -- ~25 scalar instructions per MMA,
+            // which at two K steps per tap (K = 32 layers) made the issuing thread the bottleneck (176 cycles per MMA, ncu source view).
+            // A descriptor's low field is the shared-memory address / 16, so a byte offset is one 64-bit add of offset / 16.
+            const int taps1 = p.taps1, tap_mask = p.tap_mask, split = p.split, resident = p.resident, ktail = p.ktail, ntiles = p.ntiles;
+            const uint64_t dA0 = make_desc_sw128_off(sbase, 0);
+            const uint64_t dB0 = make_desc<128>(resident ? base : sbase + b_off);
+            const uint32_t wstep = (uint32_t)(mult * b_tile) >> 4, lo_off = (uint32_t)kSegBytes >> 4, sstep = (uint32_t)stage_bytes >> 4;
+            if (resident) {
                 mbar_wait(&bars[20], 0);
                 tc_fence_after();
             }
             int q = 0, it = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int a = it & 1;
                 mbar_wait(&bars[18 + a], ((it >> 1) & 1) ^ 1);         // epilogue has drained this accumulator
                 tc_fence_after();
@@ -357,24 +365,24 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     const int kb = st / nrows, u = rows[st % nrows];
                     mbar_wait(&bars[s], use & 1);
                     tc_fence_after();
-                    const uint32_t sa = sbase + s * stage_bytes;
-                    const int v0 = p.taps1 ? 1 : 0, v1 = p.taps1 ? 2 : 3;      // the centre tap reads the segment one row in
-                    for (int v = v0; v < v1; ++v) {
-                        if (!p.taps1 && !((p.tap_mask >> (3 * u + v)) & 1)) continue;
-                        const uint32_t a_hi = sa + v * 128;
-                        const int wslot = p.taps1 ? 0 : v;
-                        const uint32_t b_cat = p.resident ? base + (kb * tpk + (p.taps1 ? 0 : 3 * u + v)) * (mult * b_tile)
-                                                          : sa + b_off + wslot * (mult * b_tile);
-                        const int kn = kb == kblocks - 1 ? p.ktail : 4;      // a 129-channel input is 2 blocks + ONE K step, not 3 blocks
-#pragma unroll 4
-                        for (int k = 0; k < kn; ++k)
-                            umma_bf16(tacc, make_desc_sw128_off(a_hi, 0) + 2 * k, make_desc<128>(b_cat) + 2 * k, idesc, accumulate | (uint32_t)k);
+                    const uint32_t soff = (uint32_t)s * sstep;
+                    const int kn = kb == kblocks - 1 ? ktail : 4;      // a 129-channel input is 2 blocks + ONE K step, not 3 blocks
+                    const int vmask = taps1 ? 2 : ((tap_mask >> (3 * u)) & 7);     // the centre tap reads the segment one row in
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) {
+                        if (!((vmask >> v) & 1)) continue;
+                        const uint64_t da = dA0 + (uint64_t)(soff + (uint32_t)(v * 8));            // + v * 128 bytes
+                        const uint32_t widx = resident ? (uint32_t)(kb * tpk + (taps1 ? 0 : 3 * u + v)) : (uint32_t)(taps1 ? 0 : v);
+                        const uint64_t db = dB0 + (uint64_t)((resident ? 0u : soff) + widx * wstep);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < kn) umma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
                         accumulate = 1;
-                        if (p.split) {
-                            const uint32_t a_lo = a_hi + kSegBytes;
-#pragma unroll 4
-                            for (int k = 0; k < kn; ++k)
-                                umma_bf16(tacc, make_desc_sw128_off(a_lo, 0) + 2 * k, make_desc<128>(b_cat) + 2 * k, idesc, 1);
+                        if (split) {
+                            const uint64_t dl = da + lo_off;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < kn) umma_bf16(tacc, dl + 2 * k, db + 2 * k, idesc, 1);
                         }
                     }
                     umma_commit(&bars[8 + s]);
