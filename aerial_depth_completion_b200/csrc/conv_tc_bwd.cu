@@ -98,20 +98,25 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
             const uint32_t lbo_a = p.mb > 1 ? (uint32_t)(p.kp * 128) : 0u;    // one block only: rows 64..127 replay rows 0..63 (never read back)
             const uint32_t lbo_b = (uint32_t)p.bseg;
             const int ksteps = p.kp / 16;
+            // descriptors by 64-bit adds from two bases (low field = shared-memory address / 16) and loop invariants in registers: the
+            // MMA asm's memory clobber otherwise makes the compiler rebuild both descriptors and re-read parameters for every MMA
+            const uint64_t dA0 = make_desc_mn(base, lbo_a), dB0 = make_desc_mn(base + a_bytes, lbo_b);
+            const uint32_t sstep = (uint32_t)stage_bytes >> 4, hoff = (uint32_t)half >> 4;
+            const int split = p.split, ncols = p.ncols;
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % nst, use = i / nst;
                 mbar_wait(&bars[s], use & 1);
                 tc_fence_after();
-                const uint32_t sa = base + s * stage_bytes, sb = sa + a_bytes;
+                const uint32_t soff = (uint32_t)s * sstep;
                 for (int v = v0; v < v1; ++v) {
-                    const uint32_t tacc = tmem_base + (uint32_t)(v * p.ncols);
+                    const uint32_t tacc = tmem_base + (uint32_t)(v * ncols);
+                    const uint64_t dav = dA0 + soff, dbv = dB0 + (uint64_t)(soff + (uint32_t)(v * 8));     // + v * 128 bytes
                     for (int k = 0; k < ksteps; ++k) {       // 16 pixels = 2 swizzle atoms = 2048 bytes per K step
-                        const uint64_t da = make_desc_mn(sa + k * 2048, lbo_a);
-                        const uint64_t db = make_desc_mn(sb + v * 128 + k * 2048, lbo_b);
+                        const uint64_t da = dav + (uint32_t)(k * 128), db = dbv + (uint32_t)(k * 128);
                         umma_bf16(tacc, da, db, idesc, (i | k) != 0);
-                        if (p.split) {
-                            umma_bf16(tacc, make_desc_mn(sa + half + k * 2048, lbo_a), db, idesc, 1);
-                            umma_bf16(tacc, da, make_desc_mn(sb + half + v * 128 + k * 2048, lbo_b), idesc, 1);
+                        if (split) {
+                            umma_bf16(tacc, da + hoff, db, idesc, 1);
+                            umma_bf16(tacc, da, db + hoff, idesc, 1);
                         }
                     }
                 }
@@ -222,17 +227,20 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
             const uint32_t idesc = make_idesc_mn(128, p.ncols);
             const uint32_t lbo_a = p.mb > 1 ? (uint32_t)blk : 0u, lbo_b = (uint32_t)blk;
             const int ksteps = p.kp / 16;
+            const uint64_t dA0 = make_desc_mn(base, lbo_a), dB0 = make_desc_mn(base + a_bytes, lbo_b);      // (see the flat kernel)
+            const uint32_t sstep = (uint32_t)stage_bytes >> 4, hoff = (uint32_t)half >> 4;
+            const int split = p.split;
             for (int i = 0; i < my_tiles; ++i) {
                 const int s = i % nst, use = i / nst;
                 mbar_wait(&bars[s], use & 1);
                 tc_fence_after();
-                const uint32_t sa = base + s * stage_bytes, sb = sa + a_bytes;
+                const uint32_t soff = (uint32_t)s * sstep;
                 for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t da = make_desc_mn(sa + k * 2048, lbo_a), db = make_desc_mn(sb + k * 2048, lbo_b);
+                    const uint64_t da = dA0 + (uint64_t)(soff + (uint32_t)(k * 128)), db = dB0 + (uint64_t)(soff + (uint32_t)(k * 128));
                     umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
-                    if (p.split) {
-                        umma_bf16(tmem_base, make_desc_mn(sa + half + k * 2048, lbo_a), db, idesc, 1);
-                        umma_bf16(tmem_base, da, make_desc_mn(sb + half + k * 2048, lbo_b), idesc, 1);
+                    if (split) {
+                        umma_bf16(tmem_base, da + hoff, db, idesc, 1);
+                        umma_bf16(tmem_base, da, db + hoff, idesc, 1);
                     }
                 }
                 umma_commit(&bars[8 + s]);
