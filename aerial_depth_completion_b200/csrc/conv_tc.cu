@@ -223,6 +223,9 @@ struct ConvParamsV2 {
     int tap_mask;            // bit 3u+v set = tap (u,v) has non-zero weights; rows of taps that are all clear are never loaded
     int accum;               // fp32 output: out += result (a gradient buffer with several producers)
     int ktail;               // 16-channel K steps of the LAST 64-channel block that hold real channels (1..4): cin = 64*(kblocks-1) + 16*ktail
+    int ostage_blocks;       // bf16 bulk stores: 64-channel column blocks the staging buffer holds (all of them, or 1 = staged in turn)
+    int pf;                  // L2 prefetch distance in tiles of this CTA (0 = off): the segments of tile + pf * grid are requested early
+    int hstack;              // 1: the three horizontal taps of a tap row are ONE MMA of N = 3 * (accumulator width) (see the kernel)
 };
 
 constexpr int kSegRows = 130;
@@ -238,7 +241,14 @@ __device__ __forceinline__ uint64_t make_desc_sw128_off(uint32_t smem_addr, int 
            (2ull << 61);
 }
 
-__global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_constant__ CUtensorMap map_x,
+// PAIR: the kernel runs as clusters of two CTAs (the two SMs of a TPC) that execute every MMA together (tcgen05.mma.cta_group::2,
+// M = 256 = the two CTAs' 128-pixel tiles).  Split mode only: CTA 0 holds the W_hi tile of a tap and CTA 1 the W_lo tile -- the two
+// halves of the N = 2 * npad operand -- so a CTA keeps HALF the weight bytes (layers with one 64-channel block and 64 output channels
+// become resident) and fetches half of B per MMA: N = 128 costs 64 cycles for 256 pixels against 102 for 128 (tc_common.cuh).  Both
+// CTAs' TMA loads count on the leader's `full` barrier; the leader's tcgen05.commit multicasts to both CTAs' `empty` / `tmem_full`
+// barriers; both CTAs' epilogue warps arrive on the leader's `tmem_empty`.
+template <bool PAIR>
+__global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_w,
                                                                const __grid_constant__ CUtensorMap map_xl,
                                                                const __grid_constant__ CUtensorMap map_wl,
@@ -265,21 +275,37 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
     // the 3 MMAs (hi*hi, lo*hi, hi*lo) of the first version by ~1.45x, and the lo*lo term comes for free.
     // shared memory: [resident weights: tile (kb, tap) = hi | lo] then nst stages of [A seg hi | A seg lo | B tap 0..2 (hi | lo)]
     const int mult = p.split ? 2 : 1;
-    const int res_bytes = p.resident ? w_all * mult : 0;
-    const int stage_bytes = mult * (kSegBytes + (p.resident ? 0 : tps * b_tile));
+    const int wmult = PAIR ? 1 : mult;                // weight tiles of a tap held by THIS CTA (pair: hi in CTA 0, lo in CTA 1)
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int res_bytes = p.resident ? w_all * wmult : 0;
+    const int stage_bytes = mult * kSegBytes + (p.resident ? 0 : wmult * tps * b_tile);
     const int b_off = mult * kSegBytes;               // weights of a streamed stage
     uint8_t* stages = smem + res_bytes;
     // output staging for the TMA store: one (two in split mode) 128-pixel x 64-channel bf16 tile, 128-byte swizzled
     uint8_t* ostage = stages + nst * stage_bytes;
-    const int ostage_bytes = p.tma_store == 2 ? 32768 : (p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0);
+    const int oblk_bytes = 16384 * (p.out_lo ? 2 : 1);
+    const int ostage_bytes = p.tma_store == 2 ? 32768 : (p.tma_store ? oblk_bytes * p.ostage_blocks : 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + ostage_bytes);
     // bars: full[8], empty[8], tmem_full[2], tmem_empty[2], weights
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    float* xch = reinterpret_cast<float*>(bars + 32);     // hstack: rows 0, 1 of every epilogue warp for its neighbour, [2][2][4][48]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int acc_cols = mult * p.npad;               // one accumulator buffer
+    // Epilogue warps: 4 (192 threads) or 8 (320 threads).  A warp may only read the TMEM lane quarter (warp % 4); with 8 warps the two
+    // warps of a quarter take alternate 16-column chunks (short-K layers were bound by the four warps' TMEM loads + conversions).
+    const int nhalf = blockDim.x > 192 ? 2 : 1;
+    const int epi_threads = 128 * nhalf;
+    const int acc_cols = mult * p.npad;               // accumulator columns of one tap (split: W_hi products | W_lo products)
+    // hstack (thin layers: 3 * acc_cols <= 256).  An MMA costs max(91, 38 + N/2) cycles whatever it computes, so with Cout <= 32 the
+    // three horizontal taps (N = 64 each) run at a quarter of the tensor pipe's rate.  Their A operands are the SAME segment shifted
+    // by v rows; instead of shifting A, one MMA of N = 3 * acc_cols multiplies rows 0..127 of the segment with [W(u,0) | W(u,1) |
+    // W(u,2)] (the tap tiles are adjacent in shared memory) and the epilogue adds the three column blocks across lanes:
+    // out[m0 + t] = D0[t] + D1[t + 1] + D2[t + 2].  A tile then yields 126 output pixels (tiles advance by 126 flat pixels).
+    const int hst = p.hstack;
+    const int acc_all = hst ? 3 * acc_cols : acc_cols;   // one accumulator buffer
+    const int tile_m = hst ? 126 : 128;
     uint32_t ncols = 32;
-    while ((int)ncols < 2 * acc_cols) ncols <<= 1;
+    while ((int)ncols < 2 * acc_all) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) {
@@ -288,22 +314,61 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars[16 + a], 1);
-            mbar_init(&bars[18 + a], 4);
+            mbar_init(&bars[18 + a], (PAIR ? 8 : 4) * nhalf);
         }
         mbar_init(&bars[20], 1);
         fence_barrier_init();
     }
     __shared__ __align__(16) float sbias[128];
     if (threadIdx.x < 128) sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.cout) ? p.bias[threadIdx.x] : 0.f;
-    if (warp == 1) tmem_alloc(tmem_slot, ncols);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_pair(tmem_slot, ncols);
+        else tmem_alloc(tmem_slot, ncols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers must be initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Tiles: CTA b handles tiles b, b + grid, ...; in a pair (grid even, rank = b & 1) both CTAs run the same number of iterations (the odd
+    // tile past the end is all out of range: its loads are zero-filled, its stores clipped).
+    const int ntiles = p.ntiles;
 
     if (warp == 0) {
         if (elect_one()) {
             // ===== TMA producer =====
+            if (PAIR) {
+                const CUtensorMap* mapw = rank ? &map_wl : &map_w;
+                const uint32_t wbar = mapa_u32(smem_u32(&bars[20]), 0);
+                if (p.resident) {
+                    if (rank == 0) mbar_expect_tx(&bars[20], (uint32_t)(2 * res_bytes));
+                    for (int kb = 0; kb < kblocks; ++kb)
+                        for (int t = 0; t < tpk; ++t)
+                            tma_load_3d_pair(smem + (kb * tpk + t) * b_tile, mapw, wbar, kb * 64, 0, p.taps1 ? 4 : t);
+                }
+                int q = 0;
+                for (int tile = blockIdx.x; tile - (int)rank < ntiles; tile += gridDim.x) {
+                    const long long m0 = (long long)tile * tile_m;
+                    for (int st = 0; st < steps; ++st, ++q) {
+                        const int s = q % nst, use = q / nst;
+                        const int kb = st / nrows, u = rows[st % nrows];
+                        mbar_wait(&bars[8 + s], (use & 1) ^ 1);
+                        uint8_t* sa = stages + s * stage_bytes;
+                        const uint32_t fbar = mapa_u32(smem_u32(&bars[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&bars[s], (uint32_t)(2 * (2 * kSegRows * 128 + (p.resident ? 0 : tps * b_tile))));
+                        const long long f0 = m0 + (long long)(u - 1) * p.Wp - 1;
+                        tma_load_2d_pair(sa, &map_x, fbar, kb * 64, (int)f0);
+                        tma_load_2d_pair(sa + kSegBytes, &map_xl, fbar, kb * 64, (int)f0);
+                        if (p.pf && tile + p.pf * (int)gridDim.x < ntiles) {
+                            const long long fp = f0 + (long long)p.pf * gridDim.x * tile_m;
+                            tma_prefetch_2d(&map_x, kb * 64, (int)fp);
+                            tma_prefetch_2d(&map_xl, kb * 64, (int)fp);
+                        }
+                        if (!p.resident)
+                            for (int v = 0; v < tps; ++v) tma_load_3d_pair(sa + b_off + v * b_tile, mapw, fbar, kb * 64, 0, p.taps1 ? 4 : 3 * u + v);
+                    }
+                }
+            } else {
             if (p.resident) {      // all weight tiles once: they stay in shared memory for every tile of this CTA
                 mbar_expect_tx(&bars[20], (uint32_t)res_bytes);
                 for (int kb = 0; kb < kblocks; ++kb)
@@ -315,8 +380,8 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     }
             }
             int q = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                const long long m0 = (long long)tile * 128;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const long long m0 = (long long)tile * tile_m;
                 for (int st = 0; st < steps; ++st, ++q) {
                     const int s = q % nst, use = q / nst;
                     const int kb = st / nrows, u = rows[st % nrows];
@@ -326,6 +391,11 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     const long long f0 = m0 + (long long)(u - 1) * p.Wp - 1;
                     tma_load_2d(sa, &map_x, &bars[s], kb * 64, (int)f0);
                     if (p.split) tma_load_2d(sa + kSegBytes, &map_xl, &bars[s], kb * 64, (int)f0);
+                    if (p.pf && tile + p.pf * (int)gridDim.x < ntiles) {
+                        const long long fp = f0 + (long long)p.pf * gridDim.x * tile_m;
+                        tma_prefetch_2d(&map_x, kb * 64, (int)fp);
+                        if (p.split) tma_prefetch_2d(&map_xl, kb * 64, (int)fp);
+                    }
                     if (!p.resident)
                         for (int v = 0; v < tps; ++v) {
                             uint8_t* wt = sa + b_off + v * (mult * b_tile);
@@ -335,30 +405,40 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                         }
                 }
             }
+            }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
+        if (rank == 0 && elect_one()) {
             // ===== MMA issuer =====
-            const uint32_t idesc = make_idesc(128, acc_cols);
+            const uint32_t idesc = make_idesc(PAIR ? 256 : 128, acc_all);
+            auto mma = [](uint32_t d, uint64_t a_, uint64_t b_, uint32_t id, uint32_t acc) {
+                if (PAIR) umma_bf16_pair(d, a_, b_, id, acc);
+                else umma_bf16(d, a_, b_, id, acc);
+            };
+            auto commit = [](uint64_t* bar) {
+                if (PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
             const uint32_t sbase = base + res_bytes;
             // Everything that does not change from MMA to MMA is computed once: the asm of an MMA clobbers "memory", so the compiler
             // re-read kernel parameters and rebuilt both 64-bit descriptors after every instruction -- ~25 scalar instructions per MMA,
             // which at two K steps per tap (K = 32 layers) made the issuing thread the bottleneck (176 cycles per MMA, ncu source view).
             // A descriptor's low field is the shared-memory address / 16, so a byte offset is one 64-bit add of offset / 16.
-            const int taps1 = p.taps1, tap_mask = p.tap_mask, split = p.split, resident = p.resident, ktail = p.ktail, ntiles = p.ntiles;
+            const int taps1 = p.taps1, tap_mask = p.tap_mask, split = p.split, resident = p.resident, ktail = p.ktail;
             const uint64_t dA0 = make_desc_sw128_off(sbase, 0);
             const uint64_t dB0 = make_desc<128>(resident ? base : sbase + b_off);
-            const uint32_t wstep = (uint32_t)(mult * b_tile) >> 4, lo_off = (uint32_t)kSegBytes >> 4, sstep = (uint32_t)stage_bytes >> 4;
+            const uint32_t wstep = (uint32_t)(wmult * b_tile) >> 4, lo_off = (uint32_t)kSegBytes >> 4, sstep = (uint32_t)stage_bytes >> 4;
             if (resident) {
                 mbar_wait(&bars[20], 0);
                 tc_fence_after();
             }
             int q = 0, it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {      // (leader: rank 0)
                 const int a = it & 1;
-                mbar_wait(&bars[18 + a], ((it >> 1) & 1) ^ 1);         // epilogue has drained this accumulator
+                if (PAIR) mbar_wait_cluster(&bars[18 + a], ((it >> 1) & 1) ^ 1);   // both CTAs' epilogues have drained this accumulator
+                else mbar_wait(&bars[18 + a], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(a * acc_cols);
+                const uint32_t tacc = tmem_base + (uint32_t)(a * acc_all);
                 uint32_t accumulate = 0;
                 for (int st = 0; st < steps; ++st, ++q) {
                     const int s = q % nst, use = q / nst;
@@ -368,6 +448,23 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     const uint32_t soff = (uint32_t)s * sstep;
                     const int kn = kb == kblocks - 1 ? ktail : 4;      // a 129-channel input is 2 blocks + ONE K step, not 3 blocks
                     const int vmask = taps1 ? 2 : ((tap_mask >> (3 * u)) & 7);     // the centre tap reads the segment one row in
+                    if (hst) {       // one MMA per K step over the three adjacent tap tiles (masked taps hold zero weights)
+                        const uint64_t da = dA0 + (uint64_t)soff;
+                        const uint32_t widx = resident ? (uint32_t)(kb * tpk + 3 * u) : 0u;
+                        const uint64_t db = dB0 + (uint64_t)((resident ? 0u : soff) + widx * wstep);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < kn) mma(tacc, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
+                        accumulate = 1;
+                        if (split) {
+                            const uint64_t dl = da + lo_off;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < kn) mma(tacc, dl + 2 * k, db + 2 * k, idesc, 1);
+                        }
+                        commit(&bars[8 + s]);
+                        continue;
+                    }
 #pragma unroll
                     for (int v = 0; v < 3; ++v) {
                         if (!((vmask >> v) & 1)) continue;
@@ -376,41 +473,95 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                         const uint64_t db = dB0 + (uint64_t)((resident ? 0u : soff) + widx * wstep);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < kn) umma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
+                            if (k < kn) mma(tacc, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
                         accumulate = 1;
                         if (split) {
                             const uint64_t dl = da + lo_off;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                if (k < kn) umma_bf16(tacc, dl + 2 * k, db + 2 * k, idesc, 1);
+                                if (k < kn) mma(tacc, dl + 2 * k, db + 2 * k, idesc, 1);
                         }
                     }
-                    umma_commit(&bars[8 + s]);
+                    commit(&bars[8 + s]);
                 }
-                umma_commit(&bars[16 + a]);
+                commit(&bars[16 + a]);
             }
         }
     } else {
         // ===== epilogue warps 2..5 =====
-        const int quarter = warp & 3;
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        uint32_t cc = 0;                                   // hstack: exchange-buffer parity, one per accumulator chunk
+        const uint32_t tmem_empty_remote = PAIR ? mapa_u32(smem_u32(&bars[18]), 0) : 0u;
+        // accumulator columns of horizontal tap v, W_hi / W_lo products: single CTA [v][hi | lo], pair [hi: v0 v1 v2 | lo: v0 v1 v2]
+        const uint32_t vstr = (uint32_t)(PAIR ? p.npad : acc_cols), hstr = (uint32_t)(PAIR && hst ? 3 * p.npad : p.npad);
+        for (int tile = blockIdx.x; tile - (int)rank < ntiles; tile += gridDim.x, ++it) {
             const int a = it & 1;
-            const long long m = (long long)tile * 128 + quarter * 32 + lane;
-            const bool inrange = m < p.F;
+            const long long m = (long long)tile * tile_m + quarter * 32 + lane;
+            const bool inrange = m < p.F && quarter * 32 + lane < tile_m;
             const int wp = (int)(m % p.Wp), hp = (int)((m / p.Wp) % p.Hp);
             const bool border = wp == 0 || wp == p.Wp - 1 || hp == 0 || hp == p.Hp - 1;
             mbar_wait(&bars[16 + a], (it >> 1) & 1);
             tc_fence_after();
-            if (p.tma_store && it > 0) {
-                // the previous tile's bulk store must have finished READING the staging tile before it is overwritten
-                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
             const int c_end = p.dbg == 2 ? 0 : (p.out_zero_to > p.npad ? p.out_zero_to : p.npad);
-            for (int c0 = 0; c0 < c_end; c0 += 16) {
+            // bf16 outputs are staged and stored one 64-channel column block at a time (an 80-channel slice = a 64- and a 16-channel box;
+            // per-thread 16-byte stores at the pixel stride were measured at 3x the cost of the whole rest of a K = 48 layer)
+            const int nblk = (p.tma_store == 1 && c_end > 64) ? (c_end + 63) >> 6 : 1;
+            const bool multi = p.ostage_blocks > 1;          // every column block has its own staging tile: one store phase per tile
+            for (int blk = 0; blk < nblk; ++blk) {
+            const int cb0 = p.tma_store == 1 ? blk * 64 : 0, cb1 = p.tma_store == 1 ? (c_end < cb0 + 64 ? c_end : cb0 + 64) : c_end;
+            uint8_t* ost = ostage + (multi ? blk * oblk_bytes : 0);
+            if (p.tma_store && ((blk == 0 && it > 0) || (blk > 0 && !multi))) {
+                // the previous bulk store must have finished READING the staging tile before it is overwritten
+                if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
+            }
+            for (int c0 = cb0 + 16 * half; c0 < cb1; c0 += 16 * nhalf) {
                 float v[16];
-                if (c0 < p.npad) {
+                if (c0 < p.npad && hst) {
+                    const uint32_t tb = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_all + c0);
+                    float s1[16], s2[16], t2[16];
+                    tmem_ld16(tb, v);
+                    tmem_ld16(tb + vstr, s1);
+                    tmem_ld16(tb + 2 * vstr, s2);
+                    if (p.split) {
+                        tmem_ld16(tb + hstr, t2);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += t2[j];
+                        tmem_ld16(tb + vstr + hstr, t2);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) s1[j] += t2[j];
+                        tmem_ld16(tb + 2 * vstr + hstr, t2);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) s2[j] += t2[j];
+                    }
+                    // rows 0 and 1 of this warp are rows 32, 33 of the warp below it
+                    float* xq = xch + (((cc & 1) * 2 + half) * 4 + quarter) * 48;
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { xq[j] = s1[j]; xq[16 + j] = s2[j]; }
+                    } else if (lane == 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xq[32 + j] = s2[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        s1[j] = __shfl_down_sync(0xffffffffu, s1[j], 1);
+                        s2[j] = __shfl_down_sync(0xffffffffu, s2[j], 2);
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");     // the four warps of this half
+                    const float* xn = xch + (((cc & 1) * 2 + half) * 4 + ((quarter + 1) & 3)) * 48;
+                    ++cc;
+                    if (lane == 31) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { s1[j] = xn[j]; s2[j] = xn[32 + j]; }
+                    } else if (lane == 30) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) s2[j] = xn[16 + j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += s1[j] + s2[j];
+                } else if (c0 < p.npad) {
                     tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_cols + c0), v);
                     if (p.split) {      // + the W_lo products of the second accumulator half
                         float v2[16];
@@ -449,8 +600,8 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 if (p.out_lo) epi_pack_lo(v, h, l);
                 if (p.tma_store) {
                     // stage the row in shared memory (16-byte chunks XOR-swizzled by row & 7, as the store map expects)
-                    const int row = quarter * 32 + lane, ch0 = (c0 >> 3);        // two 16-byte chunks per 16 channels
-                    uint8_t* rowp = ostage + row * 128;
+                    const int row = quarter * 32 + lane, ch0 = ((c0 - cb0) >> 3);        // two 16-byte chunks per 16 channels
+                    uint8_t* rowp = ost + row * 128;
                     *reinterpret_cast<uint4*>(rowp + (((ch0) ^ (row & 7)) << 4)) = h[0];
                     *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ (row & 7)) << 4)) = h[1];
                     if (p.out_lo) {
@@ -479,33 +630,46 @@ __global__ void __launch_bounds__(192) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[18 + a]);     // this warp has drained accumulator a
-            if (p.tma_store) {
+            if (blk == nblk - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {                               // this warp has drained accumulator a
+                    if (PAIR) mbar_arrive_cluster(tmem_empty_remote + (uint32_t)(a * 8));
+                    else mbar_arrive(&bars[18 + a]);
+                }
+            }
+            if (p.tma_store && (!multi || blk == nblk - 1)) {
                 // all four epilogue warps have staged their rows -> one thread issues the coalesced bulk store(s)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
                 if (warp == 2 && lane == 0) {
-                    const long long m0 = (long long)tile * 128;
+                    const long long m0 = (long long)tile * tile_m;
                     if (p.tma_store == 2) {
                         for (int b = 0; b * 32 < c_end && b < 2; ++b) {
                             if (p.accum) tma_reduce_add_2d(&map_o, ostage + b * 16384, b * 32, (int)m0);
                             else tma_store_2d(&map_o, ostage + b * 16384, b * 32, (int)m0);
                         }
                     } else {
-                        tma_store_2d(&map_o, ostage, 0, (int)m0);
-                        if (p.out_lo) tma_store_2d(&map_ol, ostage + 16384, 0, (int)m0);
+                        for (int b = multi ? 0 : blk; b <= blk; ++b) {
+                            const uint8_t* src = ostage + (multi ? b * oblk_bytes : 0);
+                            tma_store_2d(&map_o, src, b * 64, (int)m0);
+                            if (p.out_lo) tma_store_2d(&map_ol, src + 16384, b * 64, (int)m0);
+                        }
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
+            }
             }
         }
         if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+    if (PAIR) cluster_sync_all();      // the peer may not exit (or free TMEM) while MMAs read its shared memory
+    else __syncthreads();
+    if (warp == 1) {
+        if (PAIR) tmem_dealloc_pair(tmem_base, ncols);
+        else tmem_dealloc(tmem_base, ncols);
+    }
 }
 
 // ---- layout glue ---------------------------------------------------------------------------------------------------
@@ -1013,7 +1177,13 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     p.F = (long long)N * p.Hp * p.Wp;
     p.cin = cin; p.npad = npad; p.cout = cout; p.act = act; p.out_f32 = out_f32; p.split = split;
     p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.out_lo = out_f32 ? nullptr : out_lo; p.bias = bias;
-    p.ntiles = (int)((p.F + 127) / 128);
+    {   // thin layers: the three horizontal taps as one MMA (see the kernel); a tile is then 126 output pixels
+        const char* e = getenv("ADC_V2_NO_HSTACK");
+        p.hstack = (!taps1 && 3 * (split ? 2 : 1) * npad <= 256 && !(e && e[0] == '1')) ? 1 : 0;
+    }
+    { const char* e = getenv("ADC_V2_PF"); p.pf = e ? atoi(e) : 0; }      // measured: no gain (the loads are not DRAM-latency bound), kept as a switch
+    const int tile_m = p.hstack ? 126 : 128;
+    p.ntiles = (int)((p.F + tile_m - 1) / tile_m);
     p.out_zero_to = out_zero_to;
     p.taps1 = taps1;
     p.accum = (accum && out_f32) ? 1 : 0;
@@ -1061,7 +1231,11 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     memset(&mo, 0, sizeof(mo));
     memset(&mol, 0, sizeof(mol));
     const int width = out_zero_to > npad ? out_zero_to : npad;
-    p.tma_store = (!out_f32 && width == 64 && out_stride % 8 == 0 && out_off % 8 == 0) ? 1 : 0;
+    {
+        const char* e = getenv("ADC_V2_NO_WIDE_TMA");     // (experiment: only 64-channel slices through the bulk store, as before)
+        const bool wide = !(e && e[0] == '1');
+        p.tma_store = (!out_f32 && (wide || width == 64) && out_stride % 8 == 0 && out_off % 8 == 0) ? 1 : 0;
+    }
     {
         const char* e = getenv("ADC_V2_NO_F32_TMA");
         if (out_f32 && width <= 64 && out_stride % 4 == 0 && out_off % 4 == 0 && !(e && e[0] == '1')) {
@@ -1071,7 +1245,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
             const int lim = out_zero_to > cout ? out_zero_to : cout;
             cuuint64_t dims[2] = {(cuuint64_t)lim, (cuuint64_t)p.F};
             cuuint64_t strides[1] = {(cuuint64_t)out_stride * 4};
-            cuuint32_t box[2] = {32, 128};
+            cuuint32_t box[2] = {32, (cuuint32_t)tile_m};
             cuuint32_t estr[2] = {1, 1};
             CUresult r = enc(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ob, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1085,9 +1259,10 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     if (p.tma_store == 1) {
         auto make_o = [&](CUtensorMap* m, void* base_) -> int {
             __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(base_) + out_off;
-            cuuint64_t dims[2] = {64, (cuuint64_t)p.F};
+            const int lim = out_zero_to > cout ? out_zero_to : cout;      // channels this launch owns: the boxes are clipped there
+            cuuint64_t dims[2] = {(cuuint64_t)lim, (cuuint64_t)p.F};
             cuuint64_t strides[1] = {(cuuint64_t)out_stride * 2};
-            cuuint32_t box[2] = {64, 128};
+            cuuint32_t box[2] = {64, (cuuint32_t)tile_m};
             cuuint32_t estr[2] = {1, 1};
             CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ob, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1102,25 +1277,45 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     }
     // weights resident in shared memory if they fit next to >= 2 activation stages; otherwise streamed with every step
     const int kblocks = (cin + 63) / 64, mult = split ? 2 : 1;
-    const int w_all = (taps1 ? 1 : 9) * kblocks * npad * 128;
-    const int ostage_bytes = p.tma_store == 2 ? 32768 : (p.tma_store ? 16384 * (p.out_lo ? 2 : 1) : 0);
-    const int budget = kSmemCap - 1024 - 256 - ostage_bytes;
-    int smem;
+    // CTA pairs (cta_group::2) in the split mode: each CTA holds the hi OR the lo weight tiles
+    bool pair = false;
     {
+        const char* e = getenv("ADC_V2_NO_PAIR");
+        // measured (tools/time_rowseg.py): the pair wins wherever a tile carries enough MMAs to hide the cross-CTA handshakes; the 1x1 form
+        // (one step per tile) and the thinnest stacked layers (16 accumulator columns per tap) are faster on single CTAs
+        pair = split && p.ntiles >= 2 && !taps1 && !(p.hstack && npad <= 16) && !(e && e[0] == '1');
+    }
+    const int wmult = pair ? 1 : mult;
+    const int w_all = (taps1 ? 1 : 9) * kblocks * npad * 128;
+    // Shared-memory plan: weights resident if they fit next to >= 2 activation stages, otherwise streamed with every step.  A bf16
+    // result wider than 64 channels stages all its column blocks at once if the pipeline keeps >= 3 stages, else one block in turn.
+    const int oblk_bytes = 16384 * (p.out_lo ? 2 : 1), oblocks = (width + 63) / 64;
+    const int kTail = 256 + 3072;          // mbarriers + TMEM slot, hstack exchange rows
+    int smem = 0, ostage_bytes = 0;
+    auto plan = [&](int oblk) {
+        p.ostage_blocks = oblk;
+        ostage_bytes = p.tma_store == 2 ? 32768 : (p.tma_store ? oblk_bytes * oblk : 0);
+        const int budget = kSmemCap - 1024 - kTail - ostage_bytes;
         const char* e = getenv("ADC_V2_NO_RESIDENT");
         const bool allow = !(e && e[0] == '1');
         const int a_stage = kSegBytes * mult;
-        int nst_res = (budget - w_all * mult) / a_stage;
+        int nst_res = (budget - w_all * wmult) / a_stage;
         if (allow && nst_res >= 2) {
             p.resident = 1;
             p.nstages = nst_res > 8 ? 8 : nst_res;
-            smem = w_all * mult + p.nstages * a_stage + ostage_bytes + 1024 + 256;
+            smem = w_all * wmult + p.nstages * a_stage + ostage_bytes + 1024 + kTail;
         } else {
-            const int st = (kSegBytes + (taps1 ? 1 : 3) * npad * 128) * mult;
+            const int st = kSegBytes * mult + (taps1 ? 1 : 3) * npad * 128 * wmult;
             p.resident = 0;
             p.nstages = budget / st > 8 ? 8 : budget / st;
-            smem = p.nstages * st + ostage_bytes + 1024 + 256;
+            smem = p.nstages * st + ostage_bytes + 1024 + kTail;
         }
+    };
+    plan(p.tma_store == 1 ? oblocks : 1);
+    if (p.ostage_blocks > 1 && p.nstages < 3) plan(1);
+    {
+        const char* e = getenv("ADC_V2_MAXST");
+        if (e && atoi(e) >= 2 && atoi(e) < p.nstages) p.nstages = atoi(e);     // (experiment: the shared memory stays allocated)
     }
     if (p.nstages < 2 || smem > kSmemCap) {
         adc::set_error("adc_conv3x3_s1_tc_v2: %d bytes of shared memory needed", smem);
@@ -1129,17 +1324,43 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     static bool done = false;
     static int sms = 148;
     if (!done) {
-        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap),
+        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap),
                              "cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel)");
+        if (rc) return rc;
+        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap),
+                             "cudaFuncSetAttribute(conv3x3_s1_tc_v2_kernel<pair>)");
         if (rc) return rc;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         done = true;
     }
-    const int grid = p.ntiles < sms ? p.ntiles : sms;
     adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_FPROP_V2, 2.0 * N * H * W * (taps1 ? 1.0 : 9.0) * cin * cout);
-    conv3x3_s1_tc_v2_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mx, mw, mxl, mwl, mo, mol, p);
+    int threads = 320;      // 8 epilogue warps when there are at least two 16-column chunks to share
+    {
+        const char* e = getenv("ADC_V2_EPI4");
+        if ((e && e[0] == '1') || (out_zero_to > npad ? out_zero_to : npad) < 32) threads = 192;
+    }
+    if (pair) {
+        const int pairs = (p.ntiles + 1) / 2, max_pairs = sms / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return adc::check_cuda(cudaLaunchKernelEx(&cfg, conv3x3_s1_tc_v2_kernel<true>, mx, mw, mxl, mwl, mo, mol, p),
+                               "conv3x3_s1_tc_v2_kernel<pair> launch");
+    }
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
+    conv3x3_s1_tc_v2_kernel<false><<<grid, threads, smem, (cudaStream_t)stream>>>(mx, mw, mxl, mwl, mo, mol, p);
     return adc::check_cuda(cudaGetLastError(), "conv3x3_s1_tc_v2_kernel launch");
 }
 

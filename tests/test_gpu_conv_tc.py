@@ -130,3 +130,67 @@ def test_channel_slices_fold_concat():
         assert rel(dense.to_nchw_f32(o, 16).cpu(), ref3) < 2e-5
     finally:
         dense.set_precision("bf16x3")
+
+
+@gpu
+@pytest.mark.parametrize("cfg", [(2, 112, 32, 57, 76, 2, "bf16x3"), (1, 32, 8, 64, 80, 0, "bf16x3"), (3, 80, 8, 29, 39, 0, "bf16x3"),
+                                 (1, 144, 32, 15, 19, 2, "bf16x3"), (2, 16, 16, 33, 47, 1, "bf16x3"), (1, 64, 64, 57, 76, 1, "bf16"),
+                                 (2, 48, 80, 24, 41, 3, "bf16"), (1, 64, 16, 130, 126, 0, "bf16x3")])
+def test_row_segment_kernel_stacked_horizontal_taps(cfg):
+    """Thin layers (3 * accumulator width <= 256 columns) run the three horizontal taps of a tap row as ONE MMA and add the column
+    blocks across lanes in the epilogue (tiles of 126 pixels).  Same results as the one-MMA-per-tap form (ADC_V2_NO_HSTACK=1) and as
+    the fp64 convolution, for fp32 / bf16-pair outputs, channel slices, accumulation into a gradient buffer and masked taps."""
+    import os
+    from aerial_depth_completion_b200 import dense
+    n, ci, co, h, w, act, prec = cfg
+    g = torch.Generator().manual_seed(ci * 7 + co + h)
+    x = torch.randn(n, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g) * (2.0 / (ci * 9)) ** 0.5
+    b = torch.randn(co, generator=g) * 0.1
+    rel = lambda a, r: float((a - r).abs().max() / r.abs().max())
+    try:
+        dense.set_precision(prec)
+        bar = 2e-5
+        ref = _ref(x, wt, b, 1, act, rounded=(prec == "bf16"))
+        xa = dense.to_nhwc_bf16(x.cuda(), pad=True)
+        wp = dense.prep_conv3x3_weights(wt.cuda(), cin_pad=ci)
+        outs = {}
+        for flag in ("0", "1"):
+            os.environ["ADC_V2_NO_HSTACK"] = flag
+            o32 = dense.conv3x3_tc(xa, ci, wp, b.cuda(), co, 1, act, out_f32=True)
+            o16 = dense.conv3x3_tc(xa, ci, wp, b.cuda(), co, 1, act)
+            outs[flag] = (dense.to_nchw_f32(o32, co).cpu(), dense.to_nchw_f32(o16, co).cpu(), o32)
+        os.environ["ADC_V2_NO_HSTACK"] = "0"
+        # the CTA-pair form (cta_group::2, split mode) against the single-CTA form of the same kernel
+        os.environ["ADC_V2_NO_PAIR"] = "1"
+        single = dense.to_nchw_f32(dense.conv3x3_tc(xa, ci, wp, b.cuda(), co, 1, act, out_f32=True), co).cpu()
+        os.environ["ADC_V2_NO_PAIR"] = "0"
+        assert rel(outs["0"][0], single) < 5e-6
+        e = rel(outs["0"][0], ref)
+        assert e < bar, e
+        assert rel(outs["0"][0], outs["1"][0]) < 5e-6
+        assert rel(outs["0"][1], ref) < (5e-5 if prec == "bf16x3" else 1e-2)
+        o32 = outs["0"][2]
+        assert float(o32.hi[:, 0].abs().max()) == 0.0 and float(o32.hi[:, :, -1].abs().max()) == 0.0 and float(o32.hi[:, -1].abs().max()) == 0.0
+        # accumulate into an fp32 gradient buffer that already holds a term
+        acc = dense.new_act(n, h, w, dense._r64(co), "cuda", pad=True, zero=True, dtype=torch.float32)
+        from aerial_depth_completion_b200 import tc_bn
+        for rep in range(2):
+            tc_bn.conv(0, xa, 0, ci, wp, acc, 0, co, h, w, accumulate=True)
+        ref0 = _ref(x, wt, None, 1, 0, rounded=(prec == "bf16"))
+        assert rel(dense.to_nchw_f32(acc, co).cpu(), 2 * ref0) < bar
+        # masked taps (zero weights, whole tap row 0 and tap (1, 2) absent)
+        wm = wt.clone()
+        wm[:, :, 0] = 0
+        wm[:, :, 1, 2] = 0
+        mask = 0
+        for u in range(3):
+            for v in range(3):
+                if float(wm[:, :, u, v].abs().max()) > 0:
+                    mask |= 1 << (3 * u + v)
+        om = dense.conv3x3_tc(xa, ci, dense.prep_conv3x3_weights(wm.cuda(), cin_pad=ci), None, co, 1, 0, out_f32=True, tap_mask=mask)
+        assert rel(dense.to_nchw_f32(om, co).cpu(), _ref(x, wm, None, 1, 0, rounded=(prec == "bf16"))) < bar
+    finally:
+        os.environ.pop("ADC_V2_NO_HSTACK", None)
+        os.environ.pop("ADC_V2_NO_PAIR", None)
+        dense.set_precision("bf16x3")
