@@ -28,6 +28,13 @@ struct WgradParams {
     int bseg;             // bytes reserved per 64-channel x block ((kp+2) rows of 128 bytes, rounded up to 1024)
     float* part;          // [groups][9][mrows][ncols]  (single: [groups][1][mrows][ncols])
     int single;           // 1: only the centre tap (dW[co][ci] = sum_p gy[p][co] * x[p][ci]: the weight gradient of a 1x1 convolution)
+    // rowpack (split mode, Cout <= 64): the A operand is [gy_hi ; gy_lo] -- its second 64-row block is the lo tile (LBO = distance between
+    // the tiles) instead of a replay of the first -- so [hi ; lo] x x_hi and [hi ; lo] x x_lo = 2 MMAs give all four products
+    // (rows r: gy_hi * x, rows 64 + r: gy_lo * x, added by the reduction) where hi*hi, lo*hi, hi*lo took 3 with half of M idle.
+    // stack (Cin <= 64): the three horizontal taps are ONE MMA of N = 3 x 64: the N blocks of an MN-major operand sit LBO bytes apart, and
+    // LBO = 128 bytes = one pixel makes block v the x segment shifted by v pixels (accumulator columns 64 v + ci).
+    int rowpack, stack;
+    int prow;             // rows per partial slot: mrows, or 64 + mrows with rowpack
 };
 
 // MN-major SWIZZLE_128B operand: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout 2 <<61
@@ -55,8 +62,9 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
     const int u = p.single ? 1 : blockIdx.x % 3, g = p.single ? blockIdx.x : blockIdx.x / 3;
     const int v0 = p.single ? 1 : 0, v1 = p.single ? 2 : 3, ntw = p.single ? 1 : 9;
     const int my_tiles = g < p.ktiles ? (p.ktiles - g + p.groups - 1) / p.groups : 0;
+    const int vcols = p.stack ? 64 : p.ncols;                     // accumulator columns per horizontal tap
     uint32_t ncols_alloc = 32;
-    while ((int)ncols_alloc < 3 * p.ncols) ncols_alloc <<= 1;
+    while ((int)ncols_alloc < 3 * vcols) ncols_alloc <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) {
@@ -94,9 +102,11 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
     } else if (warp == 1) {
         if (elect_one()) {
             // ===== MMA issuer =====
-            const uint32_t idesc = make_idesc_mn(128, p.ncols);
-            const uint32_t lbo_a = p.mb > 1 ? (uint32_t)(p.kp * 128) : 0u;    // one block only: rows 64..127 replay rows 0..63 (never read back)
-            const uint32_t lbo_b = (uint32_t)p.bseg;
+            const int rowpack = p.rowpack, stack = p.stack;
+            const uint32_t idesc = make_idesc_mn(128, stack ? 192 : p.ncols);
+            // one block only: rows 64..127 replay rows 0..63 (never read back) -- or, with rowpack, are the lo tile
+            const uint32_t lbo_a = rowpack ? (uint32_t)half : (p.mb > 1 ? (uint32_t)(p.kp * 128) : 0u);
+            const uint32_t lbo_b = stack ? 128u : (uint32_t)p.bseg;
             const int ksteps = p.kp / 16;
             // descriptors by 64-bit adds from two bases (low field = shared-memory address / 16) and loop invariants in registers: the
             // MMA asm's memory clobber otherwise makes the compiler rebuild both descriptors and re-read parameters for every MMA
@@ -108,13 +118,15 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
                 mbar_wait(&bars[s], use & 1);
                 tc_fence_after();
                 const uint32_t soff = (uint32_t)s * sstep;
-                for (int v = v0; v < v1; ++v) {
+                for (int v = v0; v < (stack ? v0 + 1 : v1); ++v) {
                     const uint32_t tacc = tmem_base + (uint32_t)(v * ncols);
                     const uint64_t dav = dA0 + soff, dbv = dB0 + (uint64_t)(soff + (uint32_t)(v * 8));     // + v * 128 bytes
                     for (int k = 0; k < ksteps; ++k) {       // 16 pixels = 2 swizzle atoms = 2048 bytes per K step
                         const uint64_t da = dav + (uint32_t)(k * 128), db = dbv + (uint32_t)(k * 128);
                         umma_bf16(tacc, da, db, idesc, (i | k) != 0);
-                        if (split) {
+                        if (rowpack) {
+                            umma_bf16(tacc, da, db + hoff, idesc, 1);
+                        } else if (split) {
                             umma_bf16(tacc, da + hoff, db, idesc, 1);
                             umma_bf16(tacc, da, db + hoff, idesc, 1);
                         }
@@ -131,17 +143,18 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
             mbar_wait(&bars[16], 0);
             tc_fence_after();
         }
+        const bool keep = row < p.mrows || (p.rowpack && row >= 64 && row < 64 + p.mrows);
         for (int v = v0; v < v1; ++v) {
-            float* dst = p.part + (((long long)g * ntw + (p.single ? 0 : u * 3 + v)) * p.mrows + row) * p.ncols;
+            float* dst = p.part + (((long long)g * ntw + (p.single ? 0 : u * 3 + v)) * p.prow + row) * p.ncols;
             for (int c0 = 0; c0 < p.ncols; c0 += 16) {
                 float r[16];
                 if (my_tiles > 0) {
-                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(v * p.ncols + c0), r);
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((p.stack ? (v - v0) * 64 : v * p.ncols) + c0), r);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) r[j] = 0.f;
                 }
-                if (row < p.mrows) {
+                if (keep) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
                 }
@@ -164,6 +177,7 @@ struct WgradBoxParams {
     int ncols, mrows, mb, nb, kp, ktiles, groups, nstages, split;
     float* part;
     int single;           // 1: the centre tap only (weight gradient of a 1x1 convolution of the same stride, no padding)
+    int rowpack, prow;    // as in WgradParams
 };
 
 __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_constant__ CUtensorMap map_g,
@@ -225,7 +239,8 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
     } else if (warp == 1) {
         if (elect_one()) {
             const uint32_t idesc = make_idesc_mn(128, p.ncols);
-            const uint32_t lbo_a = p.mb > 1 ? (uint32_t)blk : 0u, lbo_b = (uint32_t)blk;
+            const int rowpack = p.rowpack;
+            const uint32_t lbo_a = rowpack ? (uint32_t)half : (p.mb > 1 ? (uint32_t)blk : 0u), lbo_b = (uint32_t)blk;
             const int ksteps = p.kp / 16;
             const uint64_t dA0 = make_desc_mn(base, lbo_a), dB0 = make_desc_mn(base + a_bytes, lbo_b);      // (see the flat kernel)
             const uint32_t sstep = (uint32_t)stage_bytes >> 4, hoff = (uint32_t)half >> 4;
@@ -238,7 +253,9 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
                 for (int k = 0; k < ksteps; ++k) {
                     const uint64_t da = dA0 + (uint64_t)(soff + (uint32_t)(k * 128)), db = dB0 + (uint64_t)(soff + (uint32_t)(k * 128));
                     umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
-                    if (split) {
+                    if (rowpack) {
+                        umma_bf16(tmem_base, da, db + hoff, idesc, 1);
+                    } else if (split) {
                         umma_bf16(tmem_base, da + hoff, db, idesc, 1);
                         umma_bf16(tmem_base, da, db + hoff, idesc, 1);
                     }
@@ -253,7 +270,8 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
             mbar_wait(&bars[16], 0);
             tc_fence_after();
         }
-        float* dst = p.part + (p.single ? (long long)g * p.mrows + row : ((long long)g * 9 + tap) * p.mrows + row) * p.ncols;
+        const bool keep = row < p.mrows || (p.rowpack && row >= 64 && row < 64 + p.mrows);
+        float* dst = p.part + (p.single ? (long long)g * p.prow + row : ((long long)g * 9 + tap) * p.prow + row) * p.ncols;
         for (int c0 = 0; c0 < p.ncols; c0 += 16) {
             float r[16];
             if (my_tiles > 0) {
@@ -262,7 +280,7 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) r[j] = 0.f;
             }
-            if (row < p.mrows) {
+            if (keep) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
             }
@@ -274,8 +292,9 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_box_tc_kernel(const __grid_
 }
 
 // dW[co][ci][tap] = sum_g part[g][tap][co][ci]   (fixed order; reads coalesced along ci)
+// mrows = rows per partial slot; lo_rows = 64 when rows 64 + co hold a second term of the same element (rowpack), else 0
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int groups, int mrows,
-                                                              int ncols, int cout, int cin, int ntaps) {
+                                                              int ncols, int cout, int cin, int ntaps, int lo_rows) {
     const int total = ntaps * cout * cin;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ci = i % cin, co = (i / cin) % cout, tap = i / (cin * cout);
@@ -291,6 +310,18 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
             a3 += q[(long long)(g + 3) * gs];
         }
         for (; g < groups; ++g) a0 += q[(long long)g * gs];
+        if (lo_rows) {
+            const float* ql = q + (long long)lo_rows * ncols;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            for (g = 0; g + 3 < groups; g += 4) {
+                b0 += ql[(long long)g * gs];
+                b1 += ql[(long long)(g + 1) * gs];
+                b2 += ql[(long long)(g + 2) * gs];
+                b3 += ql[(long long)(g + 3) * gs];
+            }
+            for (; g < groups; ++g) b0 += ql[(long long)g * gs];
+            a0 += b0; a1 += b1; a2 += b2; a3 += b3;
+        }
         dw[((long long)co * cin + ci) * ntaps + tap] = (a0 + a1) + (a2 + a3);
     }
 }
@@ -317,7 +348,9 @@ extern "C" {
 size_t adc_conv3x3_wgrad_tc_workspace_bytes(int cin_pad, int cout) {
     if (cin_pad <= 0 || cout <= 0) return 0;
     const int mrows = (cout + 15) / 16 * 16;
-    return (size_t)wgrad_groups() * 9 * mrows * cin_pad * sizeof(float);
+    const int prow = cout <= 64 ? 64 + mrows : mrows;          // rowpack: a slot holds the gy_hi rows and, 64 rows on, the gy_lo rows
+    const int g = wgrad_groups() * 9 > sm_count() ? wgrad_groups() * 9 : sm_count();     // 3x3 forms: groups x 9 slots; 1x1 form: one slot per SM
+    return (size_t)g * prow * cin_pad * sizeof(float);
 }
 
 // gy: zero-bordered NHWC bf16 [N][H+2][W+2][gy_stride] (channels [gy_off, gy_off+cout) are read; border pixels must be 0);
@@ -358,6 +391,13 @@ static int wgrad_flat(const void* gy, const void* gy_lo, int gy_stride, int gy_o
     p.single = single;
     p.groups = single ? sm_count() : wgrad_groups();
     p.part = reinterpret_cast<float*>(workspace);
+    {
+        const char* e = getenv("ADC_WGRAD_PLAIN");           // (experiment: the three-MMA, one-tap-per-MMA form)
+        const bool plain = e && e[0] == '1';
+        p.rowpack = (p.split && p.mb == 1 && !plain) ? 1 : 0;
+        p.stack = (p.nb == 1 && !single && !plain) ? 1 : 0;
+        p.prow = p.rowpack ? 64 + p.mrows : p.mrows;
+    }
     const int budget = kSmemCap - 1024;
     for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
         p.bseg = ((p.kp + 2) * 128 + 1023) / 1024 * 1024;
@@ -407,7 +447,8 @@ static int wgrad_flat(const void* gy, const void* gy_lo, int gy_stride, int gy_o
     conv3x3_wgrad_tc_kernel<<<(single ? 1 : 3) * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
     if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_tc_kernel launch"))) return rc;
     const int total = (single ? 1 : 9) * cout * cin;
-    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin, single ? 1 : 9);
+    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.prow, p.ncols, cout, cin, single ? 1 : 9,
+                                                                p.rowpack ? 64 : 0);
     return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");
 }
 
@@ -461,6 +502,11 @@ static int wgrad_box(const void* gy, const void* gy_lo, int gy_stride, int gy_of
     p.single = single ? 1 : 0;
     p.groups = single ? sm_count() : wgrad_box_groups();
     p.part = reinterpret_cast<float*>(workspace);
+    {
+        const char* e = getenv("ADC_WGRAD_PLAIN");
+        p.rowpack = (p.split && p.mb == 1 && !(e && e[0] == '1')) ? 1 : 0;
+        p.prow = p.rowpack ? 64 + p.mrows : p.mrows;
+    }
     const int budget = kSmemCap - 1024;
     for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
         const int stage = (p.mb + p.nb) * p.kp * 128 * (p.split ? 2 : 1);
@@ -514,7 +560,8 @@ static int wgrad_box(const void* gy, const void* gy_lo, int gy_stride, int gy_of
     conv3x3_wgrad_box_tc_kernel<<<(single ? 1 : 9) * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
     if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_box_tc_kernel launch"))) return rc;
     const int total = (single ? 1 : 9) * cout * cin;
-    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.mrows, p.ncols, cout, cin, single ? 1 : 9);
+    wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.prow, p.ncols, cout, cin, single ? 1 : 9,
+                                                                p.rowpack ? 64 : 0);
     return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");
 }
 
