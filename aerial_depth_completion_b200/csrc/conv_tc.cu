@@ -1179,7 +1179,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.out_lo = out_f32 ? nullptr : out_lo; p.bias = bias;
     {   // thin layers: the three horizontal taps as one MMA (see the kernel); a tile is then 126 output pixels
         const char* e = getenv("ADC_V2_NO_HSTACK");
-        p.hstack = (!taps1 && 3 * (split ? 2 : 1) * npad <= 256 && !(e && e[0] == '1')) ? 1 : 0;
+        p.hstack = (!taps1 && npad <= 32 && !(e && e[0] == '1')) ? 1 : 0;      // (64 columns per tap: the epilogue's lane exchange costs more than the MMAs save)
     }
     { const char* e = getenv("ADC_V2_PF"); p.pf = e ? atoi(e) : 0; }      // measured: no gain (the loads are not DRAM-latency bound), kept as a switch
     const int tile_m = p.hstack ? 126 : 128;

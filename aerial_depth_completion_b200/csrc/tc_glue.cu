@@ -110,38 +110,111 @@ __global__ void __launch_bounds__(256) nhwc_grad_assemble_kernel(Slice A, int ha
     __shared__ float red[256][8];
     const int groups = 256 / C8;                               // C8 <= 32
     const int cl = threadIdx.x % C8, pg = threadIdx.x / C8, c = cl * 8;
-    const long long pixels = (long long)N * H * W;
+    const unsigned pixels = (unsigned)N * H * W;               // (host: < 2^31) -- 32-bit index arithmetic: the 64-bit divisions of the
+    const unsigned step = gridDim.x * groups;                  // first version cost more issue slots than the loads
     float s[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = 0.f;
-    if (pg < groups)
-        for (long long r = (long long)blockIdx.x * groups + pg; r < pixels; r += (long long)gridDim.x * groups) {
-            const int x = (int)(r % W), y = (int)((r / W) % H), n = (int)(r / ((long long)W * H));
+    // single-source forms of A (quad block or same-size tensor): two pixels per iteration, all ten 16-byte loads issued before the
+    // first use; the multi-child forms already have 8+ loads in flight per pixel
+    const bool fast = !hasA || a_quad || (Hd == H && Wd == W);
+    // general up-sampling ratios (odd sizes: Hd = 2H - 1): the children of row y / column x are a contiguous range, found ONCE per CTA
+    // (the first version searched 5 x 5 candidates with a floorf each for every pixel and 8-channel group: 100+ us on the small levels)
+    __shared__ short ytab[2][1024], xtab[2][1024];
+    const bool tables = !fast && !(Hd == 2 * H && Wd == 2 * W) && H <= 1024 && W <= 1024;
+    if (tables) {
+        for (int i = threadIdx.x; i < H + W; i += blockDim.x) {
+            const bool isy = i < H;
+            const int q = isy ? i : i - H, in = isy ? H : W, out = isy ? Hd : Wd;
+            const Near& m = isy ? mh : mw;
+            int d0 = (int)(((long long)q * out) / in) - 1, first = -1, cnt = 0;
+            for (int d = d0 < 0 ? 0 : d0; d < out && d <= d0 + 4; ++d)
+                if (m(d) == q) {
+                    if (first < 0) first = d;
+                    ++cnt;
+                }
+            (isy ? ytab : xtab)[0][q] = (short)(first < 0 ? 0 : first);
+            (isy ? ytab : xtab)[1][q] = (short)cnt;
+        }
+        __syncthreads();
+    }
+    if (pg < groups && fast) {
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (unsigned r0 = blockIdx.x * groups + pg; r0 < pixels; r0 += 2 * step) {
+            long long po[2];
+            uint4 ah[2], al[2], bh[2], bl[2], tt[2];
+            bool ok[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const unsigned r = r0 + q * step;
+                ok[q] = r < pixels;
+                const unsigned rr = ok[q] ? r : 0u;
+                const unsigned x = rr % (unsigned)W, t = rr / (unsigned)W, y = t % (unsigned)H, n = t / (unsigned)H;
+                po[q] = ((long long)n * (H + 2) + y + 1) * (W + 2) + x + 1;
+                ah[q] = al[q] = bh[q] = bl[q] = tt[q] = zero;
+                if (hasA) {
+                    const long long pa = a_quad ? ((long long)n * (Hd + 2) + (y >> 1) + 1) * (Wd + 2) + (x >> 1) + 1 : po[q];
+                    const int ca = a_quad ? (int)((y & 1) * 2 + (x & 1)) * C8 * 8 + c : c;
+                    ah[q] = *reinterpret_cast<const uint4*>(A.hi + pa * A.stride + A.off + ca);
+                    if (A.lo) al[q] = *reinterpret_cast<const uint4*>(A.lo + pa * A.stride + A.off + ca);
+                }
+                if (hasB) {
+                    bh[q] = *reinterpret_cast<const uint4*>(B.hi + po[q] * B.stride + B.off + c);
+                    if (B.lo) bl[q] = *reinterpret_cast<const uint4*>(B.lo + po[q] * B.stride + B.off + c);
+                }
+                if (hasAct) tt[q] = *reinterpret_cast<const uint4*>(act.hi + po[q] * act.stride + act.off + c);
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (!ok[q]) continue;
+                float v[8];
+                const __nv_bfloat162* p0 = reinterpret_cast<const __nv_bfloat162*>(&ah[q]);
+                const __nv_bfloat162* p1 = reinterpret_cast<const __nv_bfloat162*>(&al[q]);
+                const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&bh[q]);
+                const __nv_bfloat162* p3 = reinterpret_cast<const __nv_bfloat162*>(&bl[q]);
+                const __nv_bfloat162* pt = reinterpret_cast<const __nv_bfloat162*>(&tt[q]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    // same association as load8: (A_hi + A_lo) + (B_hi + B_lo)
+                    const float a0 = __low2float(p0[j]) + __low2float(p1[j]), a1 = __high2float(p0[j]) + __high2float(p1[j]);
+                    const float b0 = __low2float(p2[j]) + __low2float(p3[j]), b1 = __high2float(p2[j]) + __high2float(p3[j]);
+                    v[2 * j] = hasA ? (hasB ? a0 + b0 : a0) : b0;
+                    v[2 * j + 1] = hasA ? (hasB ? a1 + b1 : a1) : b1;
+                    if (hasAct) {
+                        v[2 * j] *= __low2float(pt[j]) > 0.f ? 1.f : slope;
+                        v[2 * j + 1] *= __high2float(pt[j]) > 0.f ? 1.f : slope;
+                    }
+                }
+                store8(out, po[q], c, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] += v[j];
+            }
+        }
+    } else if (pg < groups)
+        for (unsigned r = blockIdx.x * groups + pg; r < pixels; r += step) {
+            const int x = (int)(r % (unsigned)W), y = (int)((r / (unsigned)W) % (unsigned)H), n = (int)(r / ((unsigned)W * (unsigned)H));
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = 0.f;
-            if (hasA && a_quad) {
-                // A holds the data gradient of a stride-2 layer in quad form: pixel (y/2, x/2) of a (Hd, Wd) = ceil(H/2, W/2)
-                // tensor, channel block (2*(y&1) + (x&1)) * C
-                load8(A, ((long long)n * (Hd + 2) + (y >> 1) + 1) * (Wd + 2) + (x >> 1) + 1, ((y & 1) * 2 + (x & 1)) * C8 * 8 + c, v, true);
-            } else if (hasA) {
-                if (Hd == 2 * H && Wd == 2 * W) {              // exact 2x: the four children, row-major
+            if (Hd == 2 * H && Wd == 2 * W) {              // exact 2x: the four children, row-major
 #pragma unroll
-                    for (int dy = 0; dy < 2; ++dy)
+                for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                        for (int dx = 0; dx < 2; ++dx)
-                            load8(A, ((long long)n * (Hd + 2) + 2 * y + dy + 1) * (Wd + 2) + 2 * x + dx + 1, c, v, true);
-                } else if (Hd == H && Wd == W) {
-                    load8(A, ((long long)n * (Hd + 2) + y + 1) * (Wd + 2) + x + 1, c, v, true);
-                } else {
-                    // children of y: the yd with mh(yd) == y form a contiguous range around y*Hd/H
-                    int y0 = (int)(((long long)y * Hd) / H) - 1, x0 = (int)(((long long)x * Wd) / W) - 1;
-                    for (int yd = y0 < 0 ? 0 : y0; yd < Hd && yd <= y0 + 4; ++yd) {
-                        if (mh(yd) != y) continue;
-                        for (int xd = x0 < 0 ? 0 : x0; xd < Wd && xd <= x0 + 4; ++xd) {
-                            if (mw(xd) != x) continue;
-                            load8(A, ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1, c, v, true);
-                        }
+                    for (int dx = 0; dx < 2; ++dx)
+                        load8(A, ((long long)n * (Hd + 2) + 2 * y + dy + 1) * (Wd + 2) + 2 * x + dx + 1, c, v, true);
+            } else if (tables) {
+                const int yb = ytab[0][y], yn = ytab[1][y], xb = xtab[0][x], xn = xtab[1][x];
+                for (int yd = yb; yd < yb + yn; ++yd)
+                    for (int xd = xb; xd < xb + xn; ++xd)
+                        load8(A, ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1, c, v, true);
+            } else {
+                // children of y: the yd with mh(yd) == y form a contiguous range around y*Hd/H
+                int y0 = (int)(((long long)y * Hd) / H) - 1, x0 = (int)(((long long)x * Wd) / W) - 1;
+                for (int yd = y0 < 0 ? 0 : y0; yd < Hd && yd <= y0 + 4; ++yd) {
+                    if (mh(yd) != y) continue;
+                    for (int xd = x0 < 0 ? 0 : x0; xd < Wd && xd <= x0 + 4; ++xd) {
+                        if (mw(xd) != x) continue;
+                        load8(A, ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1, c, v, true);
                     }
                 }
             }
@@ -283,7 +356,8 @@ int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_
                            int out_stride, int out_off, int N, int C, int H, int W, float* colsum_part, int a_quad, adc_stream_t stream) {
     if (C > 256 || (!a && !b) || bad_slice(out, out_stride, out_off, C) || (a && bad_slice(a, a_stride, a_off, a_quad ? 4 * C : C)) ||
         (b && bad_slice(b, b_stride, b_off, C)) || (act && bad_slice(act, act_stride, act_off, C)) || N <= 0 || H <= 0 || W <= 0 ||
-        (a && !a_quad && (Hd < H || Wd < W)) || (a && a_quad && (Hd != (H + 1) / 2 || Wd != (W + 1) / 2))) {
+        (a && !a_quad && (Hd < H || Wd < W)) || (a && a_quad && (Hd != (H + 1) / 2 || Wd != (W + 1) / 2)) ||
+        (long long)N * H * W >= (1LL << 31)) {
         adc::set_error("adc_nhwc_grad_assemble: bad argument");
         return ADC_E_BADARG;
     }
