@@ -166,6 +166,114 @@ __global__ void __launch_bounds__(192) conv3x3_wgrad_tc_kernel(const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, ncols_alloc);
 }
 
+// CTA-pair form of the flat kernel (split mode, 64 < Cin <= 128): the two CTAs of a cluster execute ONE tcgen05.mma.cta_group::2 of
+// M = 256 per tap, K step and x plane.  CTA 0 holds the gy_hi tile and CTA 1 the gy_lo tile (its 128 rows of A); CTA r holds the 64-channel
+// block r of x, both planes (its N/2 = 64 columns of B).  D of CTA 0 = gy_hi * (x_hi + x_lo), D of CTA 1 = gy_lo * (x_hi + x_lo): all four
+// products in 2 instructions of 64 cycles (tools/micro/mma_pair_rate.cu) where the single-CTA form issues 3 of 102, and each CTA loads half
+// the bytes of a K tile.  Partial slot: rows [0, mrows) from CTA 0, [mrows, 2 mrows) from CTA 1, added by the reduction.
+__global__ void __launch_bounds__(192) conv3x3_wgrad_pair_tc_kernel(const __grid_constant__ CUtensorMap map_g,
+                                                                    const __grid_constant__ CUtensorMap map_x,
+                                                                    const __grid_constant__ CUtensorMap map_gl,
+                                                                    const __grid_constant__ CUtensorMap map_xl, WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int a_bytes = p.mb * p.kp * 128;
+    const int stage_bytes = a_bytes + 2 * p.bseg;                 // [gy plane of this CTA | x_hi block | x_lo block]
+    const int nst = p.nstages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);    // full[8], empty[8], done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pairid = blockIdx.x >> 1, u = pairid % 3, g = pairid / 3;
+    const int my_tiles = g < p.ktiles ? (p.ktiles - g + p.groups - 1) / p.groups : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 8; ++s) {
+            mbar_init(&bars[s], 1);
+            mbar_init(&bars[8 + s], 1);
+        }
+        mbar_init(&bars[16], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ===== TMA producer (both CTAs; the bytes are counted on the leader's barrier) =====
+            const CUtensorMap* mg = rank ? &map_gl : &map_g;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % nst, use = i / nst;
+                const long long p0 = (long long)(g + i * p.groups) * p.kp;
+                const long long x0 = p0 + (long long)(u - 1) * p.Wp - 1;
+                mbar_wait(&bars[8 + s], (use & 1) ^ 1);
+                uint8_t* sa = smem + s * stage_bytes;
+                const uint32_t fbar = mapa_u32(smem_u32(&bars[s]), 0);
+                if (rank == 0) mbar_expect_tx(&bars[s], (uint32_t)(2 * (p.mb * p.kp + 2 * (p.kp + 2)) * 128));
+                for (int b = 0; b < p.mb; ++b) tma_load_2d_pair(sa + b * p.kp * 128, mg, fbar, b * 64, (int)p0);
+                tma_load_2d_pair(sa + a_bytes, &map_x, fbar, 64 * (int)rank, (int)x0);
+                tma_load_2d_pair(sa + a_bytes + p.bseg, &map_xl, fbar, 64 * (int)rank, (int)x0);
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one()) {
+            // ===== MMA issuer (leader) =====
+            const uint32_t idesc = make_idesc_mn(256, 128);
+            const uint32_t lbo_a = p.mb > 1 ? (uint32_t)(p.kp * 128) : 0u;
+            const int ksteps = p.kp / 16;
+            const uint64_t dA0 = make_desc_mn(base, lbo_a), dB0 = make_desc_mn(base + a_bytes, 0u);
+            const uint32_t sstep = (uint32_t)stage_bytes >> 4, loff = (uint32_t)p.bseg >> 4;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int s = i % nst, use = i / nst;
+                mbar_wait(&bars[s], use & 1);
+                tc_fence_after();
+                const uint32_t soff = (uint32_t)s * sstep;
+                for (int v = 0; v < 3; ++v) {
+                    const uint32_t tacc = tmem_base + (uint32_t)(v * 128);
+                    const uint64_t dav = dA0 + soff, dbv = dB0 + (uint64_t)(soff + (uint32_t)(v * 8));     // + v pixels
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t da = dav + (uint32_t)(k * 128), db = dbv + (uint32_t)(k * 128);
+                        umma_bf16_pair(tacc, da, db, idesc, (i | k) != 0);
+                        umma_bf16_pair(tacc, da, db + loff, idesc, 1);
+                    }
+                }
+                umma_commit_pair(&bars[8 + s]);
+            }
+            umma_commit_pair(&bars[16]);
+        }
+    } else {
+        // ===== epilogue warps 2..5 of both CTAs: rows = channels of this CTA's gy plane =====
+        const int quarter = warp & 3, row = quarter * 32 + lane;
+        if (my_tiles > 0) {
+            mbar_wait(&bars[16], 0);
+            tc_fence_after();
+        }
+        for (int v = 0; v < 3; ++v) {
+            float* dst = p.part + (((long long)g * 9 + u * 3 + v) * p.prow + (long long)rank * p.mrows + row) * p.ncols;
+            for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+                float r[16];
+                if (my_tiles > 0) {
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(v * 128 + c0), r);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = 0.f;
+                }
+                if (row < p.mrows) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // Box variant for strided layers (GED conv1-5, stride 2): the flat-index trick needs equal geometry of gy and x, so here a K
 // tile is a BH x BW block of OUTPUT pixels of one image; gy comes as a 4-D TMA box and the x operand of tap (u,v) as a 4-D box
 // with element strides (stride, stride) starting at (ow0*stride + v - 1, oh0*stride + u - 1) -- out-of-bounds zero fill is
@@ -398,10 +506,24 @@ static int wgrad_flat(const void* gy, const void* gy_lo, int gy_stride, int gy_o
         p.stack = (p.nb == 1 && !single && !plain) ? 1 : 0;
         p.prow = p.rowpack ? 64 + p.mrows : p.mrows;
     }
+    bool pair = false;
+    {
+        // Measured (gudepthcompnet18 step, B = 16): the pair form is correct but SLOWER where it applies (832 vs 496 us for the 129-channel
+        // head, weight gradients 7.34 vs 7.00 ms per step): the single-CTA kernel already executes its three MMAs per product at
+        // ~1.4 PFLOP/s, the kernel is fed by TMA rather than bound by MMA issue, and 24 pairs per tap row split K more coarsely than
+        // 49 CTAs.  Kept behind a switch as the measured alternative.
+        const char* e = getenv("ADC_WGRAD_PAIR");
+        pair = p.split && p.nb == 2 && !single && sm_count() >= 6 && e && e[0] == '1';
+    }
+    if (pair) {
+        p.rowpack = 0;
+        p.prow = 2 * p.mrows;
+        p.groups = sm_count() / 6;          // pairs of CTAs: (group, u)
+    }
     const int budget = kSmemCap - 1024;
     for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
         p.bseg = ((p.kp + 2) * 128 + 1023) / 1024 * 1024;
-        const int stage = (p.mb * p.kp * 128 + p.nb * p.bseg) * (p.split ? 2 : 1);
+        const int stage = pair ? p.mb * p.kp * 128 + 2 * p.bseg : (p.mb * p.kp * 128 + p.nb * p.bseg) * (p.split ? 2 : 1);
         p.nstages = budget / stage;
         if (p.nstages > 8) p.nstages = 8;
         if (p.nstages >= 3 || (p.kp == 64 && p.nstages >= 2)) break;
@@ -411,7 +533,7 @@ static int wgrad_flat(const void* gy, const void* gy_lo, int gy_stride, int gy_o
         return ADC_E_UNSUPP;
     }
     p.ktiles = (int)((p.F + p.kp - 1) / p.kp);
-    const int smem = p.nstages * (p.mb * p.kp * 128 + p.nb * p.bseg) * (p.split ? 2 : 1) + 1024 + 256;
+    const int smem = p.nstages * (pair ? p.mb * p.kp * 128 + 2 * p.bseg : (p.mb * p.kp * 128 + p.nb * p.bseg) * (p.split ? 2 : 1)) + 1024 + 256;
 
     auto make = [&](CUtensorMap* m, const void* base_, int stride, int off, int rows) -> int {
         const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base_) + off;
@@ -439,16 +561,37 @@ static int wgrad_flat(const void* gy, const void* gy_lo, int gy_stride, int gy_o
         rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap),
                              "cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel)");
         if (rc) return rc;
+        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_wgrad_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap),
+                             "cudaFuncSetAttribute(conv3x3_wgrad_pair_tc_kernel)");
+        if (rc) return rc;
         attr_done = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     adc::Prof prof(st, adc::KIND_TC_WGRAD, 2.0 * N * H * W * (single ? 1.0 : 9.0) * cin_pad * cout);
     adc::count_launches(1);
-    conv3x3_wgrad_tc_kernel<<<(single ? 1 : 3) * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
-    if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_tc_kernel launch"))) return rc;
+    if (pair) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(6 * p.groups);
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if ((rc = adc::check_cuda(cudaLaunchKernelEx(&cfg, conv3x3_wgrad_pair_tc_kernel, mg, mx, mgl, mxl, p), "conv3x3_wgrad_pair_tc_kernel launch")))
+            return rc;
+    } else {
+        conv3x3_wgrad_tc_kernel<<<(single ? 1 : 3) * p.groups, 192, smem, st>>>(mg, mx, mgl, mxl, p);
+        if ((rc = adc::check_cuda(cudaGetLastError(), "conv3x3_wgrad_tc_kernel launch"))) return rc;
+    }
     const int total = (single ? 1 : 9) * cout * cin;
     wgrad_tc_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.part, dw, p.groups, p.prow, p.ncols, cout, cin, single ? 1 : 9,
-                                                                p.rowpack ? 64 : 0);
+                                                                pair ? p.mrows : (p.rowpack ? 64 : 0));
     return adc::check_cuda(cudaGetLastError(), "wgrad_tc_reduce_kernel launch");
 }
 
