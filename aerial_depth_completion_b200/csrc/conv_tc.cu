@@ -258,8 +258,12 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     const int kblocks = (p.cin + 63) / 64;
-    const int tpk = p.taps1 ? 1 : 9;                  // weight tiles per 64-channel block
-    const int tps = p.taps1 ? 1 : 3;                  // ... per pipeline step
+    // Weight tiles per 64-channel block: only the taps of the mask exist in shared memory (the parity blocks of a stride-2 data gradient
+    // have 1, 2 or 4 live taps of 9) -- except in the stacked form, whose MMA spans the three adjacent tiles of a tap row.
+    const bool compact = !p.taps1 && !p.hstack;
+    const uint32_t tmask = (uint32_t)p.tap_mask;
+    const int tpk = p.taps1 ? 1 : (compact ? __popc(tmask) : 9);
+    const int tps = p.taps1 ? 1 : 3;                  // ... per pipeline step (at most)
     // active tap rows (the quad forms of the stride-2 data gradients have whole rows / columns of zero taps)
     int rows[3], nrows = 0;
     for (int u = 0; u < 3; ++u)
@@ -343,8 +347,11 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 if (p.resident) {
                     if (rank == 0) mbar_expect_tx(&bars[20], (uint32_t)(2 * res_bytes));
                     for (int kb = 0; kb < kblocks; ++kb)
-                        for (int t = 0; t < tpk; ++t)
-                            tma_load_3d_pair(smem + (kb * tpk + t) * b_tile, mapw, wbar, kb * 64, 0, p.taps1 ? 4 : t);
+                        for (int t = 0, slot = 0; t < (p.taps1 ? 1 : 9); ++t) {
+                            if (compact && !((tmask >> t) & 1)) continue;
+                            tma_load_3d_pair(smem + (kb * tpk + slot) * b_tile, mapw, wbar, kb * 64, 0, p.taps1 ? 4 : t);
+                            ++slot;
+                        }
                 }
                 int q = 0;
                 for (int tile = blockIdx.x; tile - (int)rank < ntiles; tile += gridDim.x) {
@@ -355,7 +362,8 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                         mbar_wait(&bars[8 + s], (use & 1) ^ 1);
                         uint8_t* sa = stages + s * stage_bytes;
                         const uint32_t fbar = mapa_u32(smem_u32(&bars[s]), 0);
-                        if (rank == 0) mbar_expect_tx(&bars[s], (uint32_t)(2 * (2 * kSegRows * 128 + (p.resident ? 0 : tps * b_tile))));
+                        const uint32_t rmask = p.taps1 ? 1u : (compact ? (tmask >> (3 * u)) & 7u : 7u);     // weight tiles of this step
+                        if (rank == 0) mbar_expect_tx(&bars[s], (uint32_t)(2 * (2 * kSegRows * 128 + (p.resident ? 0 : __popc(rmask) * b_tile))));
                         const long long f0 = m0 + (long long)(u - 1) * p.Wp - 1;
                         tma_load_2d_pair(sa, &map_x, fbar, kb * 64, (int)f0);
                         tma_load_2d_pair(sa + kSegBytes, &map_xl, fbar, kb * 64, (int)f0);
@@ -365,18 +373,24 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                             tma_prefetch_2d(&map_xl, kb * 64, (int)fp);
                         }
                         if (!p.resident)
-                            for (int v = 0; v < tps; ++v) tma_load_3d_pair(sa + b_off + v * b_tile, mapw, fbar, kb * 64, 0, p.taps1 ? 4 : 3 * u + v);
+                            for (int v = 0, slot = 0; v < tps; ++v) {
+                                if (!((rmask >> v) & 1)) continue;
+                                tma_load_3d_pair(sa + b_off + slot * b_tile, mapw, fbar, kb * 64, 0, p.taps1 ? 4 : 3 * u + v);
+                                ++slot;
+                            }
                     }
                 }
             } else {
             if (p.resident) {      // all weight tiles once: they stay in shared memory for every tile of this CTA
                 mbar_expect_tx(&bars[20], (uint32_t)res_bytes);
                 for (int kb = 0; kb < kblocks; ++kb)
-                    for (int t = 0; t < tpk; ++t) {
-                        uint8_t* wt = smem + (kb * tpk + t) * (mult * b_tile);
+                    for (int t = 0, slot = 0; t < (p.taps1 ? 1 : 9); ++t) {
+                        if (compact && !((tmask >> t) & 1)) continue;
+                        uint8_t* wt = smem + (kb * tpk + slot) * (mult * b_tile);
                         const int tap = p.taps1 ? 4 : t;
                         tma_load_3d(wt, &map_w, &bars[20], kb * 64, 0, tap);
                         if (p.split) tma_load_3d(wt + b_tile, &map_wl, &bars[20], kb * 64, 0, tap);
+                        ++slot;
                     }
             }
             int q = 0;
@@ -387,7 +401,8 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     const int kb = st / nrows, u = rows[st % nrows];
                     mbar_wait(&bars[8 + s], (use & 1) ^ 1);
                     uint8_t* sa = stages + s * stage_bytes;
-                    mbar_expect_tx(&bars[s], (uint32_t)((kSegRows * 128 + (p.resident ? 0 : tps * b_tile)) * mult));
+                    const uint32_t rmask = p.taps1 ? 1u : (compact ? (tmask >> (3 * u)) & 7u : 7u);         // weight tiles of this step
+                    mbar_expect_tx(&bars[s], (uint32_t)((kSegRows * 128 + (p.resident ? 0 : __popc(rmask) * b_tile)) * mult));
                     const long long f0 = m0 + (long long)(u - 1) * p.Wp - 1;
                     tma_load_2d(sa, &map_x, &bars[s], kb * 64, (int)f0);
                     if (p.split) tma_load_2d(sa + kSegBytes, &map_xl, &bars[s], kb * 64, (int)f0);
@@ -397,11 +412,13 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                         if (p.split) tma_prefetch_2d(&map_xl, kb * 64, (int)fp);
                     }
                     if (!p.resident)
-                        for (int v = 0; v < tps; ++v) {
-                            uint8_t* wt = sa + b_off + v * (mult * b_tile);
+                        for (int v = 0, slot = 0; v < tps; ++v) {
+                            if (!((rmask >> v) & 1)) continue;
+                            uint8_t* wt = sa + b_off + slot * (mult * b_tile);
                             const int tap = p.taps1 ? 4 : 3 * u + v;
                             tma_load_3d(wt, &map_w, &bars[s], kb * 64, 0, tap);
                             if (p.split) tma_load_3d(wt + b_tile, &map_wl, &bars[s], kb * 64, 0, tap);
+                            ++slot;
                         }
                 }
             }
@@ -469,7 +486,11 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     for (int v = 0; v < 3; ++v) {
                         if (!((vmask >> v) & 1)) continue;
                         const uint64_t da = dA0 + (uint64_t)(soff + (uint32_t)(v * 8));            // + v * 128 bytes
-                        const uint32_t widx = resident ? (uint32_t)(kb * tpk + (taps1 ? 0 : 3 * u + v)) : (uint32_t)(taps1 ? 0 : v);
+                        // tile slot: resident = live taps below (u, v) of the whole mask; streamed = live taps below v of this row
+                        const uint32_t below = taps1 ? 0u : (compact ? (uint32_t)__popc(resident ? tmask & ((1u << (3 * u + v)) - 1u)
+                                                                                                       : (uint32_t)vmask & ((1u << v) - 1u))
+                                                                      : (uint32_t)(resident ? 3 * u + v : v));
+                        const uint32_t widx = resident ? (uint32_t)(kb * tpk) + below : below;
                         const uint64_t db = dB0 + (uint64_t)((resident ? 0u : soff) + widx * wstep);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -1286,7 +1307,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
         pair = split && p.ntiles >= 2 && !taps1 && !(p.hstack && npad <= 16) && !(e && e[0] == '1');
     }
     const int wmult = pair ? 1 : mult;
-    const int w_all = (taps1 ? 1 : 9) * kblocks * npad * 128;
+    const int w_all = (taps1 ? 1 : (p.hstack ? 9 : __builtin_popcount((unsigned)p.tap_mask))) * kblocks * npad * 128;   // live taps only
     // Shared-memory plan: weights resident if they fit next to >= 2 activation stages, otherwise streamed with every step.  A bf16
     // result wider than 64 channels stages all its column blocks at once if the pipeline keeps >= 3 stages, else one block in turn.
     const int oblk_bytes = 16384 * (p.out_lo ? 2 : 1), oblocks = (width + 63) / 64;
