@@ -52,6 +52,7 @@ struct ConvParams {
     // output pixel of tile-space pixel (oh, ow): (oh*omul + oay, ow*omul + oax) in an image of OutH x OutW
     int omul, oay, oax, OutH, OutW;
     int accum;              // fp32 output: out += result (a gradient buffer with several producers)
+    int ntiles;             // tiles_x * tiles_y * N: the CTAs are persistent over them
 };
 
 constexpr int kStages = 4;
@@ -71,24 +72,28 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
     const int al_off = (A_BYTES + b_bytes + 1023) & ~1023;         // A_lo (split mode)
     const int bl_off = al_off + A_BYTES;                           // B_lo
     const int stage_bytes = p.split ? 2 * al_off : al_off;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);   // full[kStages], empty[kStages], tmem_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+    // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
+    // Persistent CTAs (grid = SM count) with a continuous TMA pipeline and two TMEM accumulators: the first version launched one CTA per
+    // 128-pixel tile, so barrier set-up, TMEM allocation, pipeline fill / drain and the epilogue of every tile ran back to back with its
+    // 18-72 pipeline steps (39 waves of ~13 us for GED's conv2, ~4 us of each not overlapped with anything).
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
-    const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
-    const int ow0 = tx * p.BW, oh0 = ty * p.BH;
     const int kblocks = (p.cin + KBLK - 1) / KBLK;
     const int ksteps = p.ntaps * kblocks;
     uint32_t ncols = 32;
-    while ((int)ncols < p.npad) ncols <<= 1;
+    while ((int)ncols < 2 * p.npad) ncols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bars[s], 1);
             mbar_init(&bars[kStages + s], 1);
         }
-        mbar_init(&bars[2 * kStages], 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bars[2 * kStages + a], 1);
+            mbar_init(&bars[2 * kStages + 2 + a], 4);
+        }
         fence_barrier_init();
     }
     __shared__ __align__(16) float sbias[256];
@@ -98,22 +103,27 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
 
     if (warp == 0) {
         if (elect_one()) {
             // ===== TMA producer =====
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int s = ks % kStages, use = ks / kStages;
-                mbar_wait(&bars[kStages + s], (use & 1) ^ 1);
-                const int kb = ks / p.ntaps, t = ks % p.ntaps, tap = p.ttap[t];
-                const int ix = ow0 * p.stride + p.tdx[t] + p.x_pad, iy = oh0 * p.stride + p.tdy[t] + p.x_pad;
-                uint8_t* sa = smem + s * stage_bytes;
-                mbar_expect_tx(&bars[s], (uint32_t)((A_BYTES + b_bytes) * (p.split ? 2 : 1)));
-                tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ix, iy, n);
-                tma_load_3d(sa + b_off, &map_w, &bars[s], kb * KBLK, 0, tap);
-                if (p.split) {
-                    tma_load_4d(sa + al_off, &map_xl, &bars[s], kb * KBLK, ix, iy, n);
-                    tma_load_3d(sa + bl_off, &map_wl, &bars[s], kb * KBLK, 0, tap);
+            int q = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int ow0 = (tile % p.tiles_x) * p.BW, oh0 = ((tile / p.tiles_x) % p.tiles_y) * p.BH, n = tile / tiles_per_img;
+                for (int ks = 0; ks < ksteps; ++ks, ++q) {
+                    const int s = q % kStages, use = q / kStages;
+                    mbar_wait(&bars[kStages + s], (use & 1) ^ 1);
+                    const int kb = ks / p.ntaps, t = ks % p.ntaps, tap = p.ttap[t];
+                    const int ix = ow0 * p.stride + p.tdx[t] + p.x_pad, iy = oh0 * p.stride + p.tdy[t] + p.x_pad;
+                    uint8_t* sa = smem + s * stage_bytes;
+                    mbar_expect_tx(&bars[s], (uint32_t)((A_BYTES + b_bytes) * (p.split ? 2 : 1)));
+                    tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ix, iy, n);
+                    tma_load_3d(sa + b_off, &map_w, &bars[s], kb * KBLK, 0, tap);
+                    if (p.split) {
+                        tma_load_4d(sa + al_off, &map_xl, &bars[s], kb * KBLK, ix, iy, n);
+                        tma_load_3d(sa + bl_off, &map_wl, &bars[s], kb * KBLK, 0, tap);
+                    }
                 }
             }
         }
@@ -121,71 +131,87 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
         if (elect_one()) {
             // ===== MMA issuer =====
             const uint32_t idesc = make_idesc(128, p.npad);
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const int s = ks % kStages, use = ks / kStages;
-                mbar_wait(&bars[s], use & 1);
+            const int split = p.split, ntiles = p.ntiles, npad = p.npad;
+            const uint64_t dA0 = make_desc<ROWB>(base), dB0 = make_desc<ROWB>(base + b_off);
+            const uint32_t sstep = (uint32_t)stage_bytes >> 4, lo_a = (uint32_t)al_off >> 4, lo_b = (uint32_t)(bl_off - b_off) >> 4;
+            int q = 0, it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int a = it & 1;
+                mbar_wait(&bars[2 * kStages + 2 + a], ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = base + s * stage_bytes;
-                const uint64_t da = make_desc<ROWB>(sa), db = make_desc<ROWB>(sa + b_off);
+                const uint32_t tacc = tmem_base + (uint32_t)(a * npad);
+                for (int ks = 0; ks < ksteps; ++ks, ++q) {
+                    const int s = q % kStages, use = q / kStages;
+                    mbar_wait(&bars[s], use & 1);
+                    tc_fence_after();
+                    const uint64_t da = dA0 + (uint64_t)((uint32_t)s * sstep), db = dB0 + (uint64_t)((uint32_t)s * sstep);
 #pragma unroll
-                for (int k = 0; k < KBLK / 16; ++k)    // advance 16 bf16 = 32 bytes inside the swizzled row: +2 in the >>4 address field
-                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
-                if (p.split) {                         // + a_lo*b_hi + a_hi*b_lo  (a_lo*b_lo ~ 2^-18 is dropped)
-                    const uint64_t dal = make_desc<ROWB>(sa + al_off), dbl = make_desc<ROWB>(sa + bl_off);
+                    for (int k = 0; k < KBLK / 16; ++k)    // advance 16 bf16 = 32 bytes inside the swizzled row: +2 in the >>4 address field
+                        umma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+                    if (split) {                           // + a_lo*b_hi + a_hi*b_lo  (a_lo*b_lo ~ 2^-18 is dropped)
 #pragma unroll
-                    for (int k = 0; k < KBLK / 16; ++k) umma_bf16(tmem_base, dal + 2 * k, db + 2 * k, idesc, 1);
+                        for (int k = 0; k < KBLK / 16; ++k) umma_bf16(tacc, da + lo_a + 2 * k, db + 2 * k, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < KBLK / 16; ++k) umma_bf16(tmem_base, da + 2 * k, dbl + 2 * k, idesc, 1);
+                        for (int k = 0; k < KBLK / 16; ++k) umma_bf16(tacc, da + 2 * k, db + lo_b + 2 * k, idesc, 1);
+                    }
+                    umma_commit(&bars[kStages + s]);       // slot free once these MMAs have read it
                 }
-                umma_commit(&bars[kStages + s]);       // slot free once these MMAs have read it
+                umma_commit(&bars[2 * kStages + a]);       // accumulator complete
             }
-            umma_commit(&bars[2 * kStages]);           // accumulator complete
         }
     } else {
         // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;                      // GEMM row = pixel index in the block
-        const int oh = oh0 + m / p.BW, ow = ow0 + m % p.BW;
-        const bool valid = oh < p.Ho && ow < p.Wo;
-        mbar_wait(&bars[2 * kStages], 0);
-        tc_fence_after();
-        const int qh = oh * p.omul + p.oay, qw = ow * p.omul + p.oax;
-        const long long pix = p.out_pad ? ((long long)n * (p.OutH + 2) + qh + 1) * (p.OutW + 2) + qw + 1
-                                        : ((long long)n * p.OutH + qh) * p.OutW + qw;
-        for (int c0 = 0; c0 < p.npad; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            if (!valid) continue;
-            epi_bias_act16(v, sbias + c0, p.act);
-            if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < p.cout) o[j] = p.accum ? o[j] + v[j] : v[j];
-            } else {
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
-                __nv_bfloat16* ol = p.out_lo ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * p.out_pix_stride + p.out_ch_off + c0 : nullptr;
-                uint4 h[2], l[2];
-                epi_pack_hi(v, h);
-                if (ol) epi_pack_lo(v, h, l);
-                if (c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                    reinterpret_cast<uint4*>(o)[0] = h[0];
-                    reinterpret_cast<uint4*>(o)[1] = h[1];
-                    if (ol) {
-                        reinterpret_cast<uint4*>(ol)[0] = l[0];
-                        reinterpret_cast<uint4*>(ol)[1] = l[1];
-                    }
-                } else {
-                    const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(h);
-                    const __nv_bfloat16* ls = reinterpret_cast<const __nv_bfloat16*>(l);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            const int a = it & 1;
+            const int ow0 = (tile % p.tiles_x) * p.BW, oh0 = ((tile / p.tiles_x) % p.tiles_y) * p.BH, n = tile / tiles_per_img;
+            const int oh = oh0 + m / p.BW, ow = ow0 + m % p.BW;
+            const bool valid = oh < p.Ho && ow < p.Wo;
+            mbar_wait(&bars[2 * kStages + a], (it >> 1) & 1);
+            tc_fence_after();
+            const int qh = oh * p.omul + p.oay, qw = ow * p.omul + p.oax;
+            const long long pix = p.out_pad ? ((long long)n * (p.OutH + 2) + qh + 1) * (p.OutW + 2) + qw + 1
+                                            : ((long long)n * p.OutH + qh) * p.OutW + qw;
+            for (int c0 = 0; c0 < p.npad; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.npad + c0), v);
+                if (!valid) continue;
+                epi_bias_act16(v, sbias + c0, p.act);
+                if (p.out_f32) {
+                    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (c0 + j < p.cout) {
-                            o[j] = hs[j];
-                            if (ol) ol[j] = ls[j];
+                        if (c0 + j < p.cout) o[j] = p.accum ? o[j] + v[j] : v[j];
+                } else {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pix_stride + p.out_ch_off + c0;
+                    __nv_bfloat16* ol = p.out_lo ? reinterpret_cast<__nv_bfloat16*>(p.out_lo) + pix * p.out_pix_stride + p.out_ch_off + c0 : nullptr;
+                    uint4 h[2], l[2];
+                    epi_pack_hi(v, h);
+                    if (ol) epi_pack_lo(v, h, l);
+                    if (c0 + 16 <= p.cout && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                        reinterpret_cast<uint4*>(o)[0] = h[0];
+                        reinterpret_cast<uint4*>(o)[1] = h[1];
+                        if (ol) {
+                            reinterpret_cast<uint4*>(ol)[0] = l[0];
+                            reinterpret_cast<uint4*>(ol)[1] = l[1];
                         }
+                    } else {
+                        const __nv_bfloat16* hs = reinterpret_cast<const __nv_bfloat16*>(h);
+                        const __nv_bfloat16* ls = reinterpret_cast<const __nv_bfloat16*>(l);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < p.cout) {
+                                o[j] = hs[j];
+                                if (ol) ol[j] = ls[j];
+                            }
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[2 * kStages + 2 + a]);      // this warp has drained accumulator a
         }
     }
     tc_fence_before();
@@ -897,7 +923,14 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMa
     }
     adc::Prof prof(st, p.omul == 2 ? adc::KIND_TC_DGRAD_S2 : adc::KIND_TC_FPROP_V1,
                    2.0 * p.N * p.Ho * p.Wo * p.ntaps * (double)p.cin * p.cout);
-    conv3x3_fprop_tc_kernel<KBLK><<<p.tiles_x * p.tiles_y * p.N, 192, smem, st>>>(mx, mw, mxl, mwl, p);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    conv3x3_fprop_tc_kernel<KBLK><<<p.ntiles < sms ? p.ntiles : sms, 192, smem, st>>>(mx, mw, mxl, mwl, p);
     return adc::check_cuda(cudaGetLastError(), "conv3x3_fprop_tc_kernel launch");
 }
 
@@ -1034,6 +1067,7 @@ static int conv_v1(const V1Launch& d, const char* who, cudaStream_t st) {
     p.BW = p.Wo >= 24 ? 32 : (p.Wo >= 12 ? 16 : 8);
     p.BH = 128 / p.BW;
     p.tiles_x = (p.Wo + p.BW - 1) / p.BW; p.tiles_y = (p.Ho + p.BH - 1) / p.BH;
+    p.ntiles = p.tiles_x * p.tiles_y * d.N;
     p.act = d.act; p.out_f32 = d.out_f32; p.out_pix_stride = d.out_stride; p.out_ch_off = d.out_off; p.out = d.out; p.bias = d.bias;
     p.out_lo = d.out_f32 ? nullptr : d.out_lo;
     p.split = split;
