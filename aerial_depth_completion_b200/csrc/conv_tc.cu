@@ -53,6 +53,7 @@ struct ConvParams {
     int omul, oay, oax, OutH, OutW;
     int accum;              // fp32 output: out += result (a gradient buffer with several producers)
     int ntiles;             // tiles_x * tiles_y * N: the CTAs are persistent over them
+    int nstages;            // pipeline stages that fit (2..kStages)
 };
 
 constexpr int kStages = 4;
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
     const int bl_off = al_off + A_BYTES;                           // B_lo
     const int stage_bytes = p.split ? 2 * al_off : al_off;
     // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+    const int nst = p.nstages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     // Persistent CTAs (grid = SM count) with a continuous TMA pipeline and two TMEM accumulators: the first version launched one CTA per
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 const int ow0 = (tile % p.tiles_x) * p.BW, oh0 = ((tile / p.tiles_x) % p.tiles_y) * p.BH, n = tile / tiles_per_img;
                 for (int ks = 0; ks < ksteps; ++ks, ++q) {
-                    const int s = q % kStages, use = q / kStages;
+                    const int s = q % nst, use = q / nst;
                     mbar_wait(&bars[kStages + s], (use & 1) ^ 1);
                     const int kb = ks / p.ntaps, t = ks % p.ntaps, tap = p.ttap[t];
                     const int ix = ow0 * p.stride + p.tdx[t] + p.x_pad, iy = oh0 * p.stride + p.tdy[t] + p.x_pad;
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(a * npad);
                 for (int ks = 0; ks < ksteps; ++ks, ++q) {
-                    const int s = q % kStages, use = q / kStages;
+                    const int s = q % nst, use = q / nst;
                     mbar_wait(&bars[s], use & 1);
                     tc_fence_after();
                     const uint64_t da = dA0 + (uint64_t)((uint32_t)s * sstep), db = dB0 + (uint64_t)((uint32_t)s * sstep);
@@ -553,10 +555,10 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
             const int c_end = p.dbg == 2 ? 0 : (p.out_zero_to > p.npad ? p.out_zero_to : p.npad);
             // bf16 outputs are staged and stored one 64-channel column block at a time (an 80-channel slice = a 64- and a 16-channel box;
             // per-thread 16-byte stores at the pixel stride were measured at 3x the cost of the whole rest of a K = 48 layer)
-            const int nblk = (p.tma_store == 1 && c_end > 64) ? (c_end + 63) >> 6 : 1;
+            const int nblk = (p.tma_store && c_end > 64) ? (c_end + 63) >> 6 : 1;
             const bool multi = p.ostage_blocks > 1;          // every column block has its own staging tile: one store phase per tile
             for (int blk = 0; blk < nblk; ++blk) {
-            const int cb0 = p.tma_store == 1 ? blk * 64 : 0, cb1 = p.tma_store == 1 ? (c_end < cb0 + 64 ? c_end : cb0 + 64) : c_end;
+            const int cb0 = p.tma_store ? blk * 64 : 0, cb1 = p.tma_store ? (c_end < cb0 + 64 ? c_end : cb0 + 64) : c_end;
             uint8_t* ost = ostage + (multi ? blk * oblk_bytes : 0);
             if (p.tma_store && ((blk == 0 && it > 0) || (blk > 0 && !multi))) {
                 // the previous bulk store must have finished READING the staging tile before it is overwritten
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     // fp32 tile staged as 32-channel boxes of 128 rows x 128 bytes (16-byte chunks XOR-swizzled by row & 7): per-thread
                     // stores of a 256-byte pixel row are 32 sectors per instruction, the bulk store / reduce-add is one coalesced copy
                     const int row = quarter * 32 + lane;
-                    uint8_t* rowp = ostage + (c0 >> 5) * 16384 + row * 128;
+                    uint8_t* rowp = ostage + ((c0 - cb0) >> 5) * 16384 + row * 128;
                     const int ch0 = (c0 & 31) >> 2;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
@@ -692,9 +694,9 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                 if (warp == 2 && lane == 0) {
                     const long long m0 = (long long)tile * tile_m;
                     if (p.tma_store == 2) {
-                        for (int b = 0; b * 32 < c_end && b < 2; ++b) {
-                            if (p.accum) tma_reduce_add_2d(&map_o, ostage + b * 16384, b * 32, (int)m0);
-                            else tma_store_2d(&map_o, ostage + b * 16384, b * 32, (int)m0);
+                        for (int b = 0; cb0 + b * 32 < cb1 && b < 2; ++b) {      // (fp32 blocks are always staged in turn)
+                            if (p.accum) tma_reduce_add_2d(&map_o, ostage + b * 16384, cb0 + b * 32, (int)m0);
+                            else tma_store_2d(&map_o, ostage + b * 16384, cb0 + b * 32, (int)m0);
                         }
                     } else {
                         for (int b = multi ? 0 : blk; b <= blk; ++b) {
@@ -1115,7 +1117,13 @@ static int conv_v1(const V1Launch& d, const char* who, cudaStream_t st) {
     const int rowb = kblk * 2;
     const int al_off = (128 * rowb + npad * rowb + 1023) & ~1023;
     const int stage_bytes = split ? 2 * al_off : al_off;
-    const int smem = kStages * stage_bytes + 1024 + 256;
+    p.nstages = (kSmemCap - 1024 - 256) / stage_bytes;
+    if (p.nstages > kStages) p.nstages = kStages;
+    if (p.nstages < 2) {
+        adc::set_error("%s: a pipeline stage of %d bytes does not fit twice in shared memory (Cout too large)", who, stage_bytes);
+        return ADC_E_UNSUPP;
+    }
+    const int smem = p.nstages * stage_bytes + 1024 + 256;
     if (kblk == 64) return launch<64>(mx, mw, mxl, mwl, p, smem, st);
     if (kblk == 32) return launch<32>(mx, mw, mxl, mwl, p, smem, st);
     return launch<16>(mx, mw, mxl, mwl, p, smem, st);
@@ -1293,7 +1301,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     }
     {
         const char* e = getenv("ADC_V2_NO_F32_TMA");
-        if (out_f32 && width <= 64 && out_stride % 4 == 0 && out_off % 4 == 0 && !(e && e[0] == '1')) {
+        if (out_f32 && width <= 128 && out_stride % 4 == 0 && out_off % 4 == 0 && !(e && e[0] == '1')) {
             // fp32 result (the BN nets' raw convolution outputs and gradient buffers): one map of 32-channel x 128-row boxes over the
             // channels this launch owns (dims[0] clips the rest), stores or reduce-adds
             float* ob = reinterpret_cast<float*>(out) + out_off;
@@ -1338,7 +1346,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
         const char* e = getenv("ADC_V2_NO_PAIR");
         // measured (tools/time_rowseg.py): the pair wins wherever a tile carries enough MMAs to hide the cross-CTA handshakes; the 1x1 form
         // (one step per tile) and the thinnest stacked layers (16 accumulator columns per tap) are faster on single CTAs
-        pair = split && p.ntiles >= 2 && !taps1 && !(p.hstack && npad <= 16) && !(e && e[0] == '1');
+        pair = split && !taps1 && !(p.hstack && npad <= 16) && !(e && e[0] == '1');     // (a single tile: the peer's tile is all out of range)
     }
     const int wmult = pair ? 1 : mult;
     const int w_all = (taps1 ? 1 : (p.hstack ? 9 : __builtin_popcount((unsigned)p.tap_mask))) * kblocks * npad * 128;   // live taps only

@@ -4,6 +4,8 @@ convolution / weight-gradient / glue kernels).  The nets' modules are plain ``nn
 (identical ``state_dict`` keys); in the modes 'bf16x3' / 'bf16' their parameters are consumed by tc_train / tc_gms / tc_bn / tc_s2d, in
 'fp32' / 'tf32' the modules' own ATen forward runs (``BACKEND``: the measurement baseline).  Nothing here runs on the CPU.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -42,6 +44,15 @@ USE_V2 = True
 
 def _r16(c):
     return (c + 15) // 16 * 16
+
+
+# Output channels per row-segment launch.  In the split mode a CTA pair holds one weight plane per CTA, so 128-channel chunks fit the way
+# they do in the plain bf16 mode; ADC_CHUNK128=0 restores the 64-channel chunks of the single-CTA form.
+CHUNK128 = os.environ.get("ADC_CHUNK128", "1") != "0"
+
+
+def out_chunk():
+    return 128 if (PRECISION != "bf16x3" or CHUNK128) else 64
 
 
 def _stream():
@@ -166,7 +177,7 @@ def conv3x3_tc(act, cin, w_prep, bias, cout, stride=1, act_fn=0, x_off=0, out=No
     n, h, w = act.n, act.h, act.w
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     # v2 streams 3 taps x Cout16 weight rows per pipeline stage: in the split mode two stages fit only up to 80 output channels
-    v2 = USE_V2 and stride == 1 and act.pad and cin % 16 == 0 and cout <= (80 if _split() else 128) and (out is None or out.pad)
+    v2 = USE_V2 and stride == 1 and act.pad and cin % 16 == 0 and cout <= (80 if (_split() and not CHUNK128) else 128) and (out is None or out.pad)
     assert v2 or not tap_mask, "tap masks are a feature of the row-segment kernel"
     zero_to = out_zero_to if v2 else 0                      # slice width the layer owns (channels past cout written as 0)
     if out is None:

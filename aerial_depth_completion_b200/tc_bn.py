@@ -35,8 +35,8 @@ K_S1, K_1X1, K_BOX, K_1X1S2, K_CONVT2, K_1X1S2_DGRAD = 0, 1, 2, 3, 4, 5
 
 
 def _chunk():
-    """Output channels per launch: the split mode doubles every shared-memory tile."""
-    return 64 if dense._split() else 128
+    """Output channels per launch (dense.out_chunk: 128, or 64 for the single-CTA split form)."""
+    return dense.out_chunk()
 
 
 def _chunks(c, step):

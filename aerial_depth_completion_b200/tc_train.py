@@ -93,7 +93,7 @@ def _prep(weight, cin_pad, mode=0):
 def _dgrad_chunks(lo, hi):
     """Output-channel chunks of a stride-1 data gradient: the row-segment kernel's shared-memory budget takes 64 output channels
     in the split mode, 128 otherwise."""
-    step = 64 if dense._split() else 128
+    step = dense.out_chunk()
     return [(a, min(a + step, hi)) for a in range(lo, hi, step)]
 
 
