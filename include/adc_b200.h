@@ -343,7 +343,7 @@ int adc_conf_pr_histogram(const float* depth, const float* confidence, const flo
                           int num_bins, unsigned long long* hist, adc_stream_t stream);
 
 /* ---- descriptor form of the tensor-core convolutions (csrc/conv_tc.cu), used by the BN nets (model_zoo/s2d_u_resnet.py:64-190)
- * kind 0: 3x3 / stride 1 (row-segment kernel, zero-bordered tensors, cin % 16 == 0, cout <= 128; 64 in split mode);
+ * kind 0: 3x3 / stride 1 (row-segment kernel, zero-bordered tensors, cin % 16 == 0, cout <= 128 -- in the split mode up to 128 through the CTA-pair form, 80 with ADC_V2_NO_PAIR);
  * kind 1: 1x1 on the same kernel; kind 2: 3x3 of stride 1 or 2 (box kernel, tensors with or without border, cout <= 256);
  * kind 3: 1x1 / stride 2 (the ResNet shortcut, s2d_u_resnet.py:99-107); kind 4: ConvTranspose2d(3, stride 2, padding 1,
  * output_padding 1) forward = data gradient of a stride-2 convolution (H, W = the larger tensor, w prepared with mode 2);
