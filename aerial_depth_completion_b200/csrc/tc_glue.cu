@@ -368,7 +368,18 @@ int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_
     if (!a) { Hd = H; Wd = W; }
     const long long total = (long long)N * H * W * (C / 8);
     adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)total * 16.0 * (out_lo ? 2 : 1) * (1 + (a ? 1 : 0) + (b ? 1 : 0)));
-    nhwc_grad_assemble_kernel<<<kAssembleCtas, 256, 0, (cudaStream_t)stream>>>(A, a != nullptr, B, b != nullptr, T, act != nullptr, slope, O, N,
+    // Small levels: one wave of CTAs instead of 1184 (at 116 registers two CTAs share an SM, so the fixed grid ran 4 latency-bound waves
+    // of ~8 us each whatever the tensor size: 33-43 us for the 29x38 and smaller levels at B = 32).  The partial rows of the CTAs that are
+    // not launched are zeroed (the caller sums all adc_nhwc_grad_assemble_parts() rows).
+    const int groups_per_cta = 256 / (C / 8);
+    long long want = ((long long)N * H * W + 2LL * groups_per_cta - 1) / (2LL * groups_per_cta);
+    int grid = (int)(want < 148 ? 148 : (want > kAssembleCtas ? kAssembleCtas : want));
+    if (grid < kAssembleCtas && colsum_part) {
+        int rc0 = adc::check_cuda(cudaMemsetAsync(colsum_part + (size_t)grid * C, 0, (size_t)(kAssembleCtas - grid) * C * sizeof(float),
+                                                  (cudaStream_t)stream), "cudaMemsetAsync(colsum partial rows)");
+        if (rc0) return rc0;
+    }
+    nhwc_grad_assemble_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, a != nullptr, B, b != nullptr, T, act != nullptr, slope, O, N,
                                                                              C / 8, H, W, Hd, Wd, Near::make(H, Hd), Near::make(W, Wd), colsum_part, a_quad);
     return adc::check_cuda(cudaGetLastError(), "nhwc_grad_assemble_kernel launch");
 }

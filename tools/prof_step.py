@@ -67,3 +67,8 @@ for k, (us, cnt, work) in sorted(tot.items(), key=lambda kv: -kv[1][0]):
 print("top launches:")
 for us, k, work in sorted(rows, key=lambda r: -r[0])[:40]:
     print("  %8.1f us  %-20s work %.4g  -> %.1f per us (T)" % (us, k, work, work / max(us, 1e-9) / 1e6))
+if os.environ.get("ALL_KIND"):
+    print("all launches of kind %s, in issue order:" % os.environ["ALL_KIND"])
+    for us, k, work in rows:
+        if k == os.environ["ALL_KIND"]:
+            print("  %8.1f us  work %.4g  -> %.2f per us (T)" % (us, work, work / max(us, 1e-9) / 1e6))
