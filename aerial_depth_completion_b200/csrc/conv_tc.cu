@@ -1242,7 +1242,8 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     p.out_pix_stride = out_stride; p.out_ch_off = out_off; p.out = out; p.out_lo = out_f32 ? nullptr : out_lo; p.bias = bias;
     {   // thin layers: the three horizontal taps as one MMA (see the kernel); a tile is then 126 output pixels
         const char* e = getenv("ADC_V2_NO_HSTACK");
-        p.hstack = (!taps1 && npad <= 32 && !(e && e[0] == '1')) ? 1 : 0;      // (64 columns per tap: the epilogue's lane exchange costs more than the MMAs save)
+        const char* m = getenv("ADC_V2_HSTACK_MAX");       // (experiment: widest stacked layer, default 32 output channels)
+        p.hstack = (!taps1 && npad <= (m ? atoi(m) : 32) && !(e && e[0] == '1')) ? 1 : 0;      // (64 columns per tap: the epilogue's lane exchange costs more than the MMAs save)
     }
     { const char* e = getenv("ADC_V2_PF"); p.pf = e ? atoi(e) : 0; }      // measured: no gain (the loads are not DRAM-latency bound), kept as a switch
     const int tile_m = p.hstack ? 126 : 128;
@@ -1345,8 +1346,8 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     {
         const char* e = getenv("ADC_V2_NO_PAIR");
         // measured (tools/time_rowseg.py): the pair wins wherever a tile carries enough MMAs to hide the cross-CTA handshakes; the 1x1 form
-        // (one step per tile) and the thinnest stacked layers (16 accumulator columns per tap) are faster on single CTAs
-        pair = split && !taps1 && !(p.hstack && npad <= 16) && !(e && e[0] == '1');     // (a single tile: the peer's tile is all out of range)
+        // (one step per tile) and the stacked-tap layers (few, wide MMAs per tile: 64 -> 32 at 228x304 378 vs 443 us) are faster on single CTAs
+        pair = split && !taps1 && !p.hstack && !(e && e[0] == '1');     // (a single tile: the peer's tile is all out of range)
     }
     const int wmult = pair ? 1 : mult;
     const int w_all = (taps1 ? 1 : (p.hstack ? 9 : __builtin_popcount((unsigned)p.tap_mask))) * kblocks * npad * 128;   // live taps only

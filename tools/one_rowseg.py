@@ -1,4 +1,5 @@
-"""One GED-shaped layer on the row-segment kernel, three launches (for ncu: -k regex:conv3x3_s1 -s 1 -c 1).  LAYER = dgrad9 | fwd9 | quad4"""
+"""One GED / GMS shaped layer on the row-segment kernel, three launches (for ncu: -k regex:conv3x3_s1 -s 1 -c 1).
+LAYER = dgrad9 | dgrad9w | fwd9 | gms64 | quad4"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,6 +18,11 @@ def act(hw, c):
 
 if layer == "dgrad9":
     x, cin, cout, out, off, zt, mask, hw = act((114, 152), 64), 32, 64, act((114, 152), 128), 0, 64, 0, None
+elif layer == "dgrad9w":      # the whole 112-channel data gradient of conv9 in one launch (128-channel chunks)
+    x, cin, cout, out, off, zt, mask = act((114, 152), 64), 32, 112, act((114, 152), 128), 0, 0, 0
+elif layer == "gms64":        # a 64 -> 64 layer of GMSNet at B = 32
+    n = int(os.environ.get("B", 32))
+    x, cin, cout, out, off, zt, mask = act((228, 304), 64), 64, 64, act((228, 304), 64), 0, 64, 0
 elif layer == "fwd9":
     x, cin, cout, out, off, zt, mask = act((114, 152), 128), 112, 32, act((114, 152), 64), 0, 64, 0
 else:

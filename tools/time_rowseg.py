@@ -26,9 +26,9 @@ def run(name, x, cin, cout, out, out_off, zero_to, act_fn=0, one=False, mask=0, 
         (lambda: dense.conv3x3_tc(x, cin, wp, b, cout, 1, act_fn, x_off=x_off, out=out, out_off=out_off, out_zero_to=zero_to, tap_mask=mask))
     res = {}
     S = {"ADC_V2_NO_PAIR": "1"}
-    for tag, env in (("pair", {}), ("single", S), ("pair_epi4", {"ADC_V2_EPI4": "1"}), ("single_epi4", dict(S, ADC_V2_EPI4="1")),
-                     ("pair_noepi", {"ADC_V2_DBG": "2"}), ("single_noepi", dict(S, ADC_V2_DBG="2"))):
-        for k in ("ADC_V2_NO_PAIR", "ADC_V2_DBG", "ADC_V2_PF", "ADC_V2_MAXST", "ADC_V2_NO_WIDE_TMA", "ADC_V2_EPI4"):
+    for tag, env in (("pair", {}), ("single", S), ("pair_hs16", {"ADC_V2_HSTACK_MAX": "16"}), ("single_hs16", dict(S, ADC_V2_HSTACK_MAX="16")),
+                     ("pair_noepi", {"ADC_V2_DBG": "2"}), ("pair_hs16_noepi", {"ADC_V2_DBG": "2", "ADC_V2_HSTACK_MAX": "16"})):
+        for k in ("ADC_V2_NO_PAIR", "ADC_V2_DBG", "ADC_V2_PF", "ADC_V2_MAXST", "ADC_V2_NO_WIDE_TMA", "ADC_V2_EPI4", "ADC_V2_HSTACK_MAX"):
             os.environ.pop(k, None)
         os.environ.update(env)
         for _ in range(2):
@@ -41,7 +41,7 @@ def run(name, x, cin, cout, out, out_off, zero_to, act_fn=0, one=False, mask=0, 
         e1.record()
         torch.cuda.synchronize()
         res[tag] = round(e0.elapsed_time(e1) * 100, 1)
-    for k in ("ADC_V2_NO_PAIR", "ADC_V2_DBG", "ADC_V2_PF", "ADC_V2_MAXST", "ADC_V2_NO_WIDE_TMA", "ADC_V2_EPI4"):
+    for k in ("ADC_V2_NO_PAIR", "ADC_V2_DBG", "ADC_V2_PF", "ADC_V2_MAXST", "ADC_V2_NO_WIDE_TMA", "ADC_V2_EPI4", "ADC_V2_HSTACK_MAX"):
         os.environ.pop(k, None)
     print(name, json.dumps(res), flush=True)
 
@@ -53,7 +53,7 @@ if os.environ.get("SET", "ged") == "wide":
         a = act(hw, c)
         n = n0
         return a
-    for nn, hw, ci, co in ((32, (228, 304), 64, 64), (16, (120, 160), 64, 64), (16, (60, 80), 128, 64), (16, (30, 40), 256, 64),
+    for nn, hw, ci, co in ((32, (228, 304), 64, 32), (32, (228, 304), 64, 64), (16, (120, 160), 64, 64), (16, (60, 80), 128, 64), (16, (30, 40), 256, 64),
                            (16, (15, 20), 512, 64), (16, (240, 320), 144, 64)):
         n = nn
         x, o = act(hw, ci), act(hw, 64)
