@@ -251,6 +251,8 @@ struct ConvParamsV2 {
     int tap_mask;            // bit 3u+v set = tap (u,v) has non-zero weights; rows of taps that are all clear are never loaded
     int accum;               // fp32 output: out += result (a gradient buffer with several producers)
     int ktail;               // 16-channel K steps of the LAST 64-channel block that hold real channels (1..4): cin = 64*(kblocks-1) + 16*ktail
+    int tri;                 // CTA pair, npad >= 80: three MMAs of N = npad per product (hi*hi, hi*lo, lo*hi) into ONE accumulator; each CTA
+                             // holds both weight planes of HALF the output channels (see the kernel)
     int ostage_blocks;       // bf16 bulk stores: 64-channel column blocks the staging buffer holds (all of them, or 1 = staged in turn)
     int pf;                  // L2 prefetch distance in tiles of this CTA (0 = off): the segments of tile + pf * grid are requested early
     int hstack;              // 1: the three horizontal taps of a tap row are ONE MMA of N = 3 * (accumulator width) (see the kernel)
@@ -327,7 +329,12 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
     // warps of a quarter take alternate 16-column chunks (short-K layers were bound by the four warps' TMEM loads + conversions).
     const int nhalf = blockDim.x > 192 ? 2 : 1;
     const int epi_threads = 128 * nhalf;
-    const int acc_cols = mult * p.npad;               // accumulator columns of one tap (split: W_hi products | W_lo products)
+    // Pair form, wide layers (tri): the [W_hi | W_lo] operand makes A_lo x [W_hi | W_lo] compute lo*lo too -- free while an instruction's
+    // cost did not depend on N, a quarter of the tensor-pipe time now that the pair MMA costs N/2 cycles.  Here CTA r holds both planes of
+    // the output channels [r npad/2, (r+1) npad/2) and the three wanted products are three MMAs of N = npad accumulating into the SAME
+    // npad columns (3 x 64 cycles instead of 2 x 128 at npad = 128; half the TMEM columns; no hi/lo add in the epilogue).
+    const int tri = PAIR ? p.tri : 0;
+    const int acc_cols = tri ? p.npad : mult * p.npad;   // accumulator columns of one tap (split: W_hi products | W_lo products)
     // hstack (thin layers: 3 * acc_cols <= 256).  An MMA costs max(91, 38 + N/2) cycles whatever it computes, so with Cout <= 32 the
     // three horizontal taps (N = 64 each) run at a quarter of the tensor pipe's rate.  Their A operands are the SAME segment shifted
     // by v rows; instead of shifting A, one MMA of N = 3 * acc_cols multiplies rows 0..127 of the segment with [W(u,0) | W(u,1) |
@@ -377,7 +384,13 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     for (int kb = 0; kb < kblocks; ++kb)
                         for (int t = 0, slot = 0; t < (p.taps1 ? 1 : 9); ++t) {
                             if (compact && !((tmask >> t) & 1)) continue;
-                            tma_load_3d_pair(smem + (kb * tpk + slot) * b_tile, mapw, wbar, kb * 64, 0, p.taps1 ? 4 : t);
+                            uint8_t* wt = smem + (kb * tpk + slot) * b_tile;
+                            if (tri) {      // rows [rank * npad/2, +npad/2) of both planes: [hi half | lo half]
+                                tma_load_3d_pair(wt, &map_w, wbar, kb * 64, (int)rank * (p.npad / 2), t);
+                                tma_load_3d_pair(wt + (p.npad / 2) * 128, &map_wl, wbar, kb * 64, (int)rank * (p.npad / 2), t);
+                            } else {
+                                tma_load_3d_pair(wt, mapw, wbar, kb * 64, 0, p.taps1 ? 4 : t);
+                            }
                             ++slot;
                         }
                 }
@@ -403,7 +416,13 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                         if (!p.resident)
                             for (int v = 0, slot = 0; v < tps; ++v) {
                                 if (!((rmask >> v) & 1)) continue;
-                                tma_load_3d_pair(sa + b_off + slot * b_tile, mapw, fbar, kb * 64, 0, p.taps1 ? 4 : 3 * u + v);
+                                uint8_t* wt = sa + b_off + slot * b_tile;
+                                if (tri) {
+                                    tma_load_3d_pair(wt, &map_w, fbar, kb * 64, (int)rank * (p.npad / 2), 3 * u + v);
+                                    tma_load_3d_pair(wt + (p.npad / 2) * 128, &map_wl, fbar, kb * 64, (int)rank * (p.npad / 2), 3 * u + v);
+                                } else {
+                                    tma_load_3d_pair(wt, mapw, fbar, kb * 64, 0, p.taps1 ? 4 : 3 * u + v);
+                                }
                                 ++slot;
                             }
                     }
@@ -472,6 +491,7 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
             const int taps1 = p.taps1, tap_mask = p.tap_mask, split = p.split, resident = p.resident, ktail = p.ktail;
             const uint64_t dA0 = make_desc_sw128_off(sbase, 0);
             const uint64_t dB0 = make_desc<128>(resident ? base : sbase + b_off);
+            const uint32_t tri_lo = (uint32_t)((p.npad / 2) * 128) >> 4;
             const uint32_t wstep = (uint32_t)(wmult * b_tile) >> 4, lo_off = (uint32_t)kSegBytes >> 4, sstep = (uint32_t)stage_bytes >> 4;
             if (resident) {
                 mbar_wait(&bars[20], 0);
@@ -524,7 +544,15 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                         for (int k = 0; k < 4; ++k)
                             if (k < kn) mma(tacc, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
                         accumulate = 1;
-                        if (split) {
+                        if (tri) {          // hi*lo and lo*hi into the same columns (db = the W_hi half, + tri_lo = the W_lo half)
+                            const uint64_t dl = da + lo_off, dbl = db + tri_lo;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < kn) mma(tacc, da + 2 * k, dbl + 2 * k, idesc, 1);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < kn) mma(tacc, dl + 2 * k, db + 2 * k, idesc, 1);
+                        } else if (split) {
                             const uint64_t dl = da + lo_off;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
@@ -612,7 +640,7 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     for (int j = 0; j < 16; ++j) v[j] += s1[j] + s2[j];
                 } else if (c0 < p.npad) {
                     tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_cols + c0), v);
-                    if (p.split) {      // + the W_lo products of the second accumulator half
+                    if (p.split && !tri) {      // + the W_lo products of the second accumulator half
                         float v2[16];
                         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * acc_cols + p.npad + c0), v2);
 #pragma unroll
@@ -1254,6 +1282,22 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     p.ktail = cin % 64 ? (cin % 64) / 16 : 4;
     p.tap_mask = (tap_mask & 0x1FF) ? (tap_mask & 0x1FF) : 0x1FF;
     { const char* e = getenv("ADC_V2_DBG"); p.dbg = e ? atoi(e) : 0; }
+    // CTA pairs (cta_group::2) in the split mode: each CTA holds the hi OR the lo weight tiles
+    bool pair = false;
+    {
+        const char* e = getenv("ADC_V2_NO_PAIR");
+        // measured (tools/time_rowseg.py): the pair wins wherever a tile carries enough MMAs to hide the cross-CTA handshakes; the 1x1 form
+        // (one step per tile) and the stacked-tap layers (few, wide MMAs per tile: 64 -> 32 at 228x304 378 vs 443 us) are faster on single CTAs
+        // ... and so are layers with little MMA work per tile (live taps x K steps < 32: the K = 32 data gradients, the tap-masked parity
+        // blocks of the stride-2 data gradients: 161 vs 192 us), unless their 81..128 output channels only fit the pair's half-size weight tiles
+        const int work = __builtin_popcount((unsigned)p.tap_mask) * ((cin + 15) / 16);
+        pair = split && !taps1 && !p.hstack && (work >= 32 || npad > 80) && !(e && e[0] == '1');     // (a single tile: the peer's is out of range)
+    }
+    {
+        const char* e = getenv("ADC_V2_NO_TRI");
+        const char* m = getenv("ADC_V2_TRI_MIN");           // (experiment: narrowest layer in the three-product form)
+        p.tri = (pair && npad >= (m ? atoi(m) : 80) && !(e && e[0] == '1')) ? 1 : 0;
+    }
     CUtensorMap mx, mw, mxl, mwl;
     memset(&mxl, 0, sizeof(mxl));
     memset(&mwl, 0, sizeof(mwl));
@@ -1275,7 +1319,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     auto make_w = [&](CUtensorMap* m, const void* base_) -> int {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)npad, 9};
         cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2 * npad};
-        cuuint32_t box[3] = {64, (cuuint32_t)npad, 1};      // one tap per copy: hi and lo tiles interleave in shared memory
+        cuuint32_t box[3] = {64, (cuuint32_t)(p.tri ? npad / 2 : npad), 1};      // one tap (tri: one CTA's half of its rows) per copy
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base_), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1341,14 +1385,6 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     }
     // weights resident in shared memory if they fit next to >= 2 activation stages; otherwise streamed with every step
     const int kblocks = (cin + 63) / 64, mult = split ? 2 : 1;
-    // CTA pairs (cta_group::2) in the split mode: each CTA holds the hi OR the lo weight tiles
-    bool pair = false;
-    {
-        const char* e = getenv("ADC_V2_NO_PAIR");
-        // measured (tools/time_rowseg.py): the pair wins wherever a tile carries enough MMAs to hide the cross-CTA handshakes; the 1x1 form
-        // (one step per tile) and the stacked-tap layers (few, wide MMAs per tile: 64 -> 32 at 228x304 378 vs 443 us) are faster on single CTAs
-        pair = split && !taps1 && !p.hstack && !(e && e[0] == '1');     // (a single tile: the peer's tile is all out of range)
-    }
     const int wmult = pair ? 1 : mult;
     const int w_all = (taps1 ? 1 : (p.hstack ? 9 : __builtin_popcount((unsigned)p.tap_mask))) * kblocks * npad * 128;   // live taps only
     // Shared-memory plan: weights resident if they fit next to >= 2 activation stages, otherwise streamed with every step.  A bf16
