@@ -58,7 +58,10 @@ struct ConvParams {
 
 constexpr int kStages = 4;
 
-template <int KBLK>   // channels per K step: 64 / 32 / 16  (row bytes 128 / 64 / 32)
+// PAIR (split mode): clusters of two CTAs execute every MMA together (tcgen05.mma.cta_group::2, M = 256 = the two CTAs' pixel blocks).
+// CTA r holds both weight planes of the output channels [r npad/2, (r+1) npad/2): half the weight bytes per CTA and step, and the three
+// products of bf16x3 are three instructions of N = npad at N/2 cycles each (see conv3x3_s1_tc_v2_kernel for the barrier protocol).
+template <int KBLK, bool PAIR>   // channels per K step: 64 / 32 / 16  (row bytes 128 / 64 / 32)
 __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                const __grid_constant__ CUtensorMap map_w,
                                                                const __grid_constant__ CUtensorMap map_xl,
@@ -68,7 +71,9 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-    const int b_bytes = p.npad * ROWB;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int brows = PAIR ? p.npad / 2 : p.npad;          // weight rows (output channels) of a tap tile held by this CTA
+    const int b_bytes = brows * ROWB;
     const int b_off = A_BYTES;                                     // B_hi
     const int al_off = (A_BYTES + b_bytes + 1023) & ~1023;         // A_lo (split mode)
     const int bl_off = al_off + A_BYTES;                           // B_lo
@@ -94,15 +99,19 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bars[2 * kStages + a], 1);
-            mbar_init(&bars[2 * kStages + 2 + a], 4);
+            mbar_init(&bars[2 * kStages + 2 + a], PAIR ? 8 : 4);
         }
         fence_barrier_init();
     }
     __shared__ __align__(16) float sbias[256];
     for (int i = threadIdx.x; i < 256; i += 192) sbias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
-    if (warp == 1) tmem_alloc(tmem_slot, ncols);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_pair(tmem_slot, ncols);
+        else tmem_alloc(tmem_slot, ncols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
         if (elect_one()) {
             // ===== TMA producer =====
             int q = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile - (int)rank < p.ntiles; tile += gridDim.x) {     // (pair: the odd tile past the end loads zeros)
                 const int ow0 = (tile % p.tiles_x) * p.BW, oh0 = ((tile / p.tiles_x) % p.tiles_y) * p.BH, n = tile / tiles_per_img;
                 for (int ks = 0; ks < ksteps; ++ks, ++q) {
                     const int s = q % nst, use = q / nst;
@@ -119,6 +128,15 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                     const int kb = ks / p.ntaps, t = ks % p.ntaps, tap = p.ttap[t];
                     const int ix = ow0 * p.stride + p.tdx[t] + p.x_pad, iy = oh0 * p.stride + p.tdy[t] + p.x_pad;
                     uint8_t* sa = smem + s * stage_bytes;
+                    if (PAIR) {
+                        const uint32_t fbar = mapa_u32(smem_u32(&bars[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&bars[s], (uint32_t)(4 * (A_BYTES + b_bytes)));
+                        tma_load_4d_pair(sa, &map_x, fbar, kb * KBLK, ix, iy, n);
+                        tma_load_3d_pair(sa + b_off, &map_w, fbar, kb * KBLK, (int)rank * brows, tap);
+                        tma_load_4d_pair(sa + al_off, &map_xl, fbar, kb * KBLK, ix, iy, n);
+                        tma_load_3d_pair(sa + bl_off, &map_wl, fbar, kb * KBLK, (int)rank * brows, tap);
+                        continue;
+                    }
                     mbar_expect_tx(&bars[s], (uint32_t)((A_BYTES + b_bytes) * (p.split ? 2 : 1)));
                     tma_load_4d(sa, &map_x, &bars[s], kb * KBLK, ix, iy, n);
                     tma_load_3d(sa + b_off, &map_w, &bars[s], kb * KBLK, 0, tap);
@@ -130,16 +148,25 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = make_idesc(128, p.npad);
+        if (rank == 0 && elect_one()) {
+            // ===== MMA issuer (pair: the leader) =====
+            const uint32_t idesc = make_idesc(PAIR ? 256 : 128, p.npad);
+            auto mma = [](uint32_t d, uint64_t a_, uint64_t b_, uint32_t id, uint32_t acc) {
+                if (PAIR) umma_bf16_pair(d, a_, b_, id, acc);
+                else umma_bf16(d, a_, b_, id, acc);
+            };
+            auto commit = [](uint64_t* bar) {
+                if (PAIR) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
             const int split = p.split, ntiles = p.ntiles, npad = p.npad;
             const uint64_t dA0 = make_desc<ROWB>(base), dB0 = make_desc<ROWB>(base + b_off);
             const uint32_t sstep = (uint32_t)stage_bytes >> 4, lo_a = (uint32_t)al_off >> 4, lo_b = (uint32_t)(bl_off - b_off) >> 4;
             int q = 0, it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int a = it & 1;
-                mbar_wait(&bars[2 * kStages + 2 + a], ((it >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                if (PAIR) mbar_wait_cluster(&bars[2 * kStages + 2 + a], ((it >> 1) & 1) ^ 1);   // both CTAs' epilogues have drained it
+                else mbar_wait(&bars[2 * kStages + 2 + a], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(a * npad);
                 for (int ks = 0; ks < ksteps; ++ks, ++q) {
@@ -149,16 +176,16 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
                     const uint64_t da = dA0 + (uint64_t)((uint32_t)s * sstep), db = dB0 + (uint64_t)((uint32_t)s * sstep);
 #pragma unroll
                     for (int k = 0; k < KBLK / 16; ++k)    // advance 16 bf16 = 32 bytes inside the swizzled row: +2 in the >>4 address field
-                        umma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+                        mma(tacc, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
                     if (split) {                           // + a_lo*b_hi + a_hi*b_lo  (a_lo*b_lo ~ 2^-18 is dropped)
 #pragma unroll
-                        for (int k = 0; k < KBLK / 16; ++k) umma_bf16(tacc, da + lo_a + 2 * k, db + 2 * k, idesc, 1);
+                        for (int k = 0; k < KBLK / 16; ++k) mma(tacc, da + lo_a + 2 * k, db + 2 * k, idesc, 1);
 #pragma unroll
-                        for (int k = 0; k < KBLK / 16; ++k) umma_bf16(tacc, da + 2 * k, db + lo_b + 2 * k, idesc, 1);
+                        for (int k = 0; k < KBLK / 16; ++k) mma(tacc, da + 2 * k, db + lo_b + 2 * k, idesc, 1);
                     }
-                    umma_commit(&bars[kStages + s]);       // slot free once these MMAs have read it
+                    commit(&bars[kStages + s]);            // slot free once these MMAs have read it
                 }
-                umma_commit(&bars[2 * kStages + a]);       // accumulator complete
+                commit(&bars[2 * kStages + a]);            // accumulator complete
             }
         }
     } else {
@@ -166,11 +193,12 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
         const int quarter = warp & 3;
         const int m = quarter * 32 + lane;                      // GEMM row = pixel index in the block
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const uint32_t tmem_empty_remote = PAIR ? mapa_u32(smem_u32(&bars[2 * kStages + 2]), 0) : 0u;
+        for (int tile = blockIdx.x; tile - (int)rank < p.ntiles; tile += gridDim.x, ++it) {
             const int a = it & 1;
             const int ow0 = (tile % p.tiles_x) * p.BW, oh0 = ((tile / p.tiles_x) % p.tiles_y) * p.BH, n = tile / tiles_per_img;
             const int oh = oh0 + m / p.BW, ow = ow0 + m % p.BW;
-            const bool valid = oh < p.Ho && ow < p.Wo;
+            const bool valid = oh < p.Ho && ow < p.Wo && tile < p.ntiles;
             mbar_wait(&bars[2 * kStages + a], (it >> 1) & 1);
             tc_fence_after();
             const int qh = oh * p.omul + p.oay, qw = ow * p.omul + p.oax;
@@ -213,12 +241,19 @@ __global__ void __launch_bounds__(192) conv3x3_fprop_tc_kernel(const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[2 * kStages + 2 + a]);      // this warp has drained accumulator a
+            if (lane == 0) {                                             // this warp has drained accumulator a
+                if (PAIR) mbar_arrive_cluster(tmem_empty_remote + (uint32_t)(a * 8));
+                else mbar_arrive(&bars[2 * kStages + 2 + a]);
+            }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, ncols);
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 1) {
+        if (PAIR) tmem_dealloc_pair(tmem_base, ncols);
+        else tmem_dealloc(tmem_base, ncols);
+    }
 }
 
 // ---- v2: stride-1 kernel with tap reuse in shared memory, persistent CTAs and double-buffered TMEM accumulators ------
@@ -937,13 +972,16 @@ __global__ void __launch_bounds__(256) prep_conv_weights_batch_kernel(const __gr
 
 template <int KBLK>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mxl, const CUtensorMap& mwl, const ConvParams& p,
-                  int smem, cudaStream_t st) {
+                  int smem, bool pair, cudaStream_t st) {
     static bool done = false;
     if (!done) {   // opt in once to the largest configuration of this instantiation (npad = 256)
         int max_smem = 2 * kStages * ((128 * KBLK * 2 + 256 * KBLK * 2 + 1023) & ~1023) + 1024 + 256;
         if (max_smem > kSmemCap) max_smem = kSmemCap;
-        int rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_fprop_tc_kernel<KBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
+        int rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_fprop_tc_kernel<KBLK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
                                  "cudaFuncSetAttribute(conv3x3_fprop_tc_kernel)");
+        if (rc) return rc;
+        rc = adc::check_cuda(cudaFuncSetAttribute(conv3x3_fprop_tc_kernel<KBLK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
+                             "cudaFuncSetAttribute(conv3x3_fprop_tc_kernel<pair>)");
         if (rc) return rc;
         done = true;
     }
@@ -960,7 +998,25 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMa
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    conv3x3_fprop_tc_kernel<KBLK><<<p.ntiles < sms ? p.ntiles : sms, 192, smem, st>>>(mx, mw, mxl, mwl, p);
+    if (pair) {
+        const int pairs = (p.ntiles + 1) / 2, max_pairs = sms / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return adc::check_cuda(cudaLaunchKernelEx(&cfg, conv3x3_fprop_tc_kernel<KBLK, true>, mx, mw, mxl, mwl, p),
+                               "conv3x3_fprop_tc_kernel<pair> launch");
+    }
+    conv3x3_fprop_tc_kernel<KBLK, false><<<p.ntiles < sms ? p.ntiles : sms, 192, smem, st>>>(mx, mw, mxl, mwl, p);
     return adc::check_cuda(cudaGetLastError(), "conv3x3_fprop_tc_kernel launch");
 }
 
@@ -1126,10 +1182,17 @@ static int conv_v1(const V1Launch& d, const char* who, cudaStream_t st) {
         }
         return 0;
     };
+    // CTA pairs in the split mode (each CTA: both weight planes of half the output channels)
+    bool pair = false;
+    {
+        const char* e = getenv("ADC_BOX_NO_PAIR");
+        pair = split && !(e && e[0] == '1');
+    }
+    const int brows = pair ? npad / 2 : npad;
     auto make_w = [&](CUtensorMap* m, const void* base) -> int {
         cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)npad, 9};
         cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2 * npad};
-        cuuint32_t box[3] = {(cuuint32_t)kblk, (cuuint32_t)npad, 1};
+        cuuint32_t box[3] = {(cuuint32_t)kblk, (cuuint32_t)brows, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1143,7 +1206,7 @@ static int conv_v1(const V1Launch& d, const char* who, cudaStream_t st) {
     if ((rc = make_x(&mx, d.x)) || (rc = make_w(&mw, d.w))) return rc;
     if (split && ((rc = make_x(&mxl, d.x_lo)) || (rc = make_w(&mwl, d.w_lo)))) return rc;
     const int rowb = kblk * 2;
-    const int al_off = (128 * rowb + npad * rowb + 1023) & ~1023;
+    const int al_off = (128 * rowb + brows * rowb + 1023) & ~1023;
     const int stage_bytes = split ? 2 * al_off : al_off;
     p.nstages = (kSmemCap - 1024 - 256) / stage_bytes;
     if (p.nstages > kStages) p.nstages = kStages;
@@ -1152,9 +1215,9 @@ static int conv_v1(const V1Launch& d, const char* who, cudaStream_t st) {
         return ADC_E_UNSUPP;
     }
     const int smem = p.nstages * stage_bytes + 1024 + 256;
-    if (kblk == 64) return launch<64>(mx, mw, mxl, mwl, p, smem, st);
-    if (kblk == 32) return launch<32>(mx, mw, mxl, mwl, p, smem, st);
-    return launch<16>(mx, mw, mxl, mwl, p, smem, st);
+    if (kblk == 64) return launch<64>(mx, mw, mxl, mwl, p, smem, pair, st);
+    if (kblk == 32) return launch<32>(mx, mw, mxl, mwl, p, smem, pair, st);
+    return launch<16>(mx, mw, mxl, mwl, p, smem, pair, st);
 }
 
 // x: NHWC bf16 [N,H,W,x_stride] (channels [x_off, x_off+cin) are read, cin % 16 == 0); w: prepared bf16 [9][npad][cin];
