@@ -133,6 +133,8 @@ SIGNATURES = {
     "adc_quad_head_wgrad": (c_int, [_vp, _vp, c_int, _vp, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_quad_head_dgrad": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, c_int, _vp, _vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
     "adc_quad_unshuffle": (c_int, [_vp, c_int, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_quad_tap_mix": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, _vp]),
+    "adc_quad_tap_mix_adjoint": (c_int, [_vp, _vp, c_int, _vp]),
     "adc_conv3x3_wgrad_tc_workspace_bytes": (ctypes.c_size_t, [c_int, c_int]),
     "adc_conv3x3_wgrad_tc": (c_int, [_vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      _vp]),

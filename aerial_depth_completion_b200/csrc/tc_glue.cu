@@ -83,19 +83,37 @@ __device__ __forceinline__ void store8(const SliceW& s, long long pix, int c, co
 }
 
 // dst[n][yd][xd][c] = src[n][mh(yd)][mw(xd)][c]   (bit copy of hi and lo)
+// 32-bit index arithmetic (host: N*Hd*Wd*C8 < 2^31 -- the 64-bit divisions cost more issue slots than the copies) and two
+// 16-byte groups per thread with all loads issued before the first store.
 __global__ void __launch_bounds__(256) nhwc_upsample_kernel(Slice src, SliceW dst, int N, int C8, int Hs, int Ws, int Hd, int Wd, Near mh,
                                                             Near mw) {
-    const long long total = (long long)N * Hd * Wd * C8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C8) * 8;
-        long long r = i / C8;
-        const int xd = (int)(r % Wd);
-        r /= Wd;
-        const int yd = (int)(r % Hd), n = (int)(r / Hd);
-        const long long sp = ((long long)n * (Hs + 2) + mh(yd) + 1) * (Ws + 2) + mw(xd) + 1;
-        const long long dp = ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1;
-        *reinterpret_cast<uint4*>(dst.hi + dp * dst.stride + dst.off + c) = *reinterpret_cast<const uint4*>(src.hi + sp * src.stride + src.off + c);
-        if (dst.lo) *reinterpret_cast<uint4*>(dst.lo + dp * dst.stride + dst.off + c) = *reinterpret_cast<const uint4*>(src.lo + sp * src.stride + src.off + c);
+    const unsigned total = (unsigned)N * Hd * Wd * C8, step = gridDim.x * blockDim.x;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * step) {
+        long long sp[2], dp[2];
+        int c[2];
+        bool ok[2];
+        uint4 h[2], l[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned i = i0 + q * step;
+            ok[q] = i < total;
+            const unsigned ii = ok[q] ? i : 0u;
+            c[q] = (int)(ii % (unsigned)C8) * 8;
+            unsigned r = ii / (unsigned)C8;
+            const unsigned xd = r % (unsigned)Wd;
+            r /= (unsigned)Wd;
+            const unsigned yd = r % (unsigned)Hd, n = r / (unsigned)Hd;
+            sp[q] = ((long long)n * (Hs + 2) + mh((int)yd) + 1) * (Ws + 2) + mw((int)xd) + 1;
+            dp[q] = ((long long)n * (Hd + 2) + yd + 1) * (Wd + 2) + xd + 1;
+            h[q] = *reinterpret_cast<const uint4*>(src.hi + sp[q] * src.stride + src.off + c[q]);
+            if (dst.lo) l[q] = *reinterpret_cast<const uint4*>(src.lo + sp[q] * src.stride + src.off + c[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (!ok[q]) continue;
+            *reinterpret_cast<uint4*>(dst.hi + dp[q] * dst.stride + dst.off + c[q]) = h[q];
+            if (dst.lo) *reinterpret_cast<uint4*>(dst.lo + dp[q] * dst.stride + dst.off + c[q]) = l[q];
+        }
     }
 }
 
@@ -308,6 +326,47 @@ __global__ void __launch_bounds__(1024) sum_rows_kernel(const float* __restrict_
     }
 }
 
+// Quad (parity-block) forms of a 3x3 weight tensor, one thread per output element (the broadcast product + reduction these replace
+// materialised a [4][A][B][9][9] tensor per layer and step through three library launches):
+//  which 0 'up': conv3x3(up2(x)) at output parity (py,px): original tap (u,v) falls on low-resolution tap ((py+u-1)>>1)+1, ((px+v-1)>>1)+1
+//  which 1 's2': data gradient of a stride-2 conv at input parity (py,px): low-resolution tap (a,b) holds original tap (py+3-2a, px+3-2b)
+// forward: out[q][a][b][s] (or [q][b][a][s] when transposed) = sum over the original taps t that map to s of w[a][b][t]
+__device__ __forceinline__ int quad_up_slot(int py, int px, int t) {
+    const int u = t / 3, v = t - 3 * u;
+    return (((py + u - 1) >> 1) + 1) * 3 + ((px + v - 1) >> 1) + 1;
+}
+__global__ void __launch_bounds__(256) quad_tap_mix_kernel(const float* __restrict__ w, float* __restrict__ out, int A, int B, int which,
+                                                           int transposed) {
+    const int total = 4 * A * B * 9;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int s = i % 9, l = (i / 9) % (A * B), q = i / (9 * A * B);
+    const int py = q >> 1, px = q & 1;
+    const float* wl = w + (size_t)l * 9;
+    float r = 0.f;
+    if (which == 0) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+            if (quad_up_slot(py, px, t) == s) r += __ldg(wl + t);
+    } else {
+        const int a = s / 3, b = s - 3 * a, u = py + 3 - 2 * a, v = px + 3 - 2 * b;
+        if (u >= 0 && u < 3 && v >= 0 && v < 3) r = __ldg(wl + u * 3 + v);
+    }
+    const int ia = l / B, ib = l - ia * B;
+    const size_t o = transposed ? ((size_t)q * B + ib) * A + ia : (size_t)q * A * B + l;
+    out[o * 9 + s] = r;
+}
+// adjoint of the 'up' form: out[l][t] = sum_q in[q][l][slot(q, t)]
+__global__ void __launch_bounds__(256) quad_tap_mix_adjoint_kernel(const float* __restrict__ in, float* __restrict__ out, int L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * 9) return;
+    const int t = i % 9, l = i / 9;
+    float r = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r += __ldg(in + ((size_t)q * L + l) * 9 + quad_up_slot(q >> 1, q & 1, t));
+    out[i] = r;
+}
+
 static int grid_for(long long total) {
     long long b = (total + 255) / 256;
     const long long cap = 148LL * 16;
@@ -344,6 +403,10 @@ int adc_nhwc_upsample_nearest(const void* src, const void* src_lo, int src_strid
     Slice s{(const __nv_bfloat16*)src, (const __nv_bfloat16*)src_lo, src_stride, src_off};
     SliceW d{(__nv_bfloat16*)dst, (__nv_bfloat16*)dst_lo, dst_stride, dst_off};
     const long long total = (long long)N * Hd * Wd * (C / 8);
+    if (total >= (1LL << 31)) {
+        adc::set_error("adc_nhwc_upsample_nearest: more than 2^31 16-byte groups");
+        return ADC_E_BADARG;
+    }
     adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)total * 16.0 * (src_lo ? 4 : 2));
     nhwc_upsample_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(s, d, N, C / 8, Hs, Ws, Hd, Wd, Near::make(Hs, Hd), Near::make(Ws, Wd));
     return adc::check_cuda(cudaGetLastError(), "nhwc_upsample_kernel launch");
@@ -404,6 +467,27 @@ int adc_nhwc_colsum(const void* g, const void* g_lo, int g_stride, int g_off, in
     if (rc) return rc;
     nhwc_colsum2_kernel<<<(C + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float*>(workspace), nparts, Cp, C, out);
     return adc::check_cuda(cudaGetLastError(), "nhwc_colsum2_kernel launch");
+}
+
+int adc_quad_tap_mix(const float* w, float* out, int A, int B, int which, int transposed, adc_stream_t stream) {
+    if (!w || !out || A <= 0 || B <= 0 || which < 0 || which > 1 || (long long)A * B * 36 >= (1LL << 31)) {
+        adc::set_error("adc_quad_tap_mix: bad argument");
+        return ADC_E_BADARG;
+    }
+    const int total = 4 * A * B * 9;
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_PREP, (double)total * 8.0);
+    quad_tap_mix_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, out, A, B, which, transposed);
+    return adc::check_cuda(cudaGetLastError(), "quad_tap_mix_kernel launch");
+}
+
+int adc_quad_tap_mix_adjoint(const float* in, float* out, int L, adc_stream_t stream) {
+    if (!in || !out || L <= 0 || (long long)L * 36 >= (1LL << 31)) {
+        adc::set_error("adc_quad_tap_mix_adjoint: bad argument");
+        return ADC_E_BADARG;
+    }
+    adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_PREP, (double)L * 9 * 20.0);
+    quad_tap_mix_adjoint_kernel<<<(L * 9 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, out, L);
+    return adc::check_cuda(cudaGetLastError(), "quad_tap_mix_adjoint_kernel launch");
 }
 
 }  // extern "C"

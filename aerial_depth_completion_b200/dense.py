@@ -339,6 +339,29 @@ def quad_maps(device):
     return _QUAD_MAPS[key]
 
 
+def quad_tap_mix(w, which, transposed=False):
+    """Quad form of a 3x3 weight tensor ``w`` [A, B, 3, 3] (or [A, B, 9]) in one launch: [4, A, B, 9], or [4, B, A, 9] when
+    ``transposed``; ``which`` = 'up' | 's2' (the two identities of ``quad_maps``)."""
+    from ._lib import lib, check
+    _need_cuda(w)
+    a, b = w.shape[:2]
+    w = w.detach().reshape(a, b, 9).contiguous().float()
+    out = torch.empty((4, b, a, 9) if transposed else (4, a, b, 9), device=w.device, dtype=torch.float32)
+    check(lib.adc_quad_tap_mix(w.data_ptr(), out.data_ptr(), a, b, {"up": 0, "s2": 1}[which], int(bool(transposed)), _stream()),
+          "adc_quad_tap_mix")
+    return out
+
+
+def quad_tap_mix_adjoint(g):
+    """Transpose of ``quad_tap_mix(., 'up')``: ``g`` [4, L, 9] (gradient of the quad weights) -> [L, 9]."""
+    from ._lib import lib, check
+    _need_cuda(g)
+    g = g.contiguous().float()
+    out = torch.empty((g.shape[1], 9), device=g.device, dtype=torch.float32)
+    check(lib.adc_quad_tap_mix_adjoint(g.data_ptr(), out.data_ptr(), g.shape[1], _stream()), "adc_quad_tap_mix_adjoint")
+    return out
+
+
 def quad_s2_tap_masks():
     """tap_mask (bit 3a+b) of the low-resolution taps each parity block of a quad stride-2 data gradient uses, and their union."""
     masks = []

@@ -280,8 +280,14 @@ class ForwardConfidence(nn.Module):
 def _c0_of(x0):
     """c0 = (d > 0) for rgbd input, channel 4 for rgbdw (confidence_depth_framework.py:469-472)."""
     x0_d = x0[:, 3:4, :, :]
-    c0 = (x0_d > 0).float() if x0.shape[1] == 4 else x0[:, 4:5, :, :]
-    return x0_d, c0
+    if x0.shape[1] != 4:
+        return x0_d, x0[:, 4:5, :, :]
+    if x0.is_cuda and not (torch.is_grad_enabled() and x0.requires_grad):
+        # one copy + one compare written as fp32 (the pyramid and the dense net both want the depth plane contiguous: the slice
+        # used to be copied twice, and the mask went through a bool tensor)
+        x0_d = x0_d.contiguous()
+        return x0_d, torch.gt(x0_d, 0, out=torch.empty_like(x0_d))
+    return x0_d, (x0_d > 0).float()
 
 
 class GEDNet(nn.Module):

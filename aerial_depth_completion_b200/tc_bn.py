@@ -199,9 +199,7 @@ def quad_s2_weights(w_io):
     """[in, out, 3, 3] (contracted over ``in``) -> [4*out, in, 3, 3]: row (2py+px)*out + o holds, at low-resolution tap (di+1, dj+1), the
     original tap (py+1-2di, px+1-2dj) where it exists."""
     cin, cout = w_io.shape[:2]
-    _, s2 = dense.quad_maps(w_io.device)
-    w = w_io.detach().reshape(1, cin, cout, 1, 9)
-    return (w * s2.reshape(4, 1, 1, 9, 9)).sum(-1).permute(0, 2, 1, 3).reshape(4 * cout, cin, 3, 3)
+    return dense.quad_tap_mix(w_io, "s2", transposed=True).reshape(4 * cout, cin, 3, 3)
 
 
 def quad_s2(x, x_off, cin, wp, key, Y, y_off, cout, accumulate=False):

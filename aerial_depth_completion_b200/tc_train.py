@@ -113,20 +113,11 @@ def _dgrad_s1(G, weight, out, lo, hi, prepped=None, cy=None):
         dense.conv3x3_tc(G, cy, wp, None, b - a, 1, 0, out=out, out_off=a, out_zero_to=64 if a + 64 <= out.cs else 0)
 
 
-def _tap_mix(maps, w):
-    """out[q, ..., s] = sum_t maps[q, s, t] * w[..., t] for the constant 0/1 tap maps of dense.quad_maps ([4, 9, 9]) and a weight tensor
-    whose last dimension is the 9 original taps: a broadcast product and a reduction over <= 4 live terms (not a GEMM)."""
-    lead = w.dim() - 1
-    m = maps.reshape((4,) + (1,) * lead + (9, 9))
-    return (w.reshape((1,) + tuple(w.shape[:-1]) + (1, 9)) * m).sum(-1)
-
-
 def _quad_head_weights(w10):
     """[oc, 33, 3, 3] -> [4*oc, 32, 3, 3]: per parity (py, px) of the output pixel, the taps of conv10 that read the same pixel of
-    x9 through the 2x nearest up-sampling, summed (row (2py+px)*oc + o)."""
+    x9 through the 2x nearest up-sampling, summed (row (2py+px)*oc + o); one launch (dense.quad_tap_mix)."""
     oc = w10.shape[0]
-    up, _ = dense.quad_maps(w10.device)
-    return _tap_mix(up, w10[:, :32].reshape(oc, 32, 9)).reshape(4 * oc, 32, 3, 3)
+    return dense.quad_tap_mix(w10[:, :32], "up").reshape(4 * oc, 32, 3, 3)
 
 
 def _quad_head_backward(P, b, w10, g_x10, x10, x0_d, g_lli, need_x0d):
@@ -141,8 +132,7 @@ def _quad_head_backward(P, b, w10, g_x10, x10, x0_d, g_lli, need_x0d):
         extra = dense.to_nhwc_bf16(F.avg_pool2d(g_lli[:, :32], 2) * 4.0, cpad=32, pad=True)
     gb9 = dense.quad_head_dgrad(P.x9, gq, _quad_head_weights(w10), b["G9"], extra)
     dwq = dense.quad_head_wgrad(P.x9, gq, oc)                             # [4*oc, 32, 3, 3]
-    up, _ = dense.quad_maps(w10.device)
-    dw = (dwq.reshape(4, oc, 32, 9, 1) * up.reshape(4, 1, 1, 9, 9)).sum((0, 3)).reshape(oc, 32, 3, 3)      # adjoint of _tap_mix
+    dw = dense.quad_tap_mix_adjoint(dwq.reshape(4, oc * 32, 9)).reshape(oc, 32, 3, 3)                      # adjoint of quad_tap_mix 'up'
     dw = torch.cat((dw, s[:, :9].reshape(oc, 1, 3, 3)), 1)
     g_x0d = dense.ged_head_bwd_x0d(g_x10, x10, g_lli, w10) if need_x0d else None
     return g_x0d, dw, s[:, 9].contiguous(), gb9
@@ -247,14 +237,13 @@ class GEDDenseTC(torch.autograd.Function):
             add(i, _dgrad_reqs(W[i], dec_cy[i], 0, dec_cin[i]))
         # stride-2 layers conv5..conv2: quad form of the data gradient (dense.quad_maps 's2'): per parity block q a stride-1
         # convolution of the output gradient with the taps of W that reach that parity, [q][ci][co][3x3]
-        _, s2 = dense.quad_maps(dev)
         masks, mask_all = dense.quad_s2_tap_masks()
         for i in (4, 3, 2, 1):
-            wq = _tap_mix(s2, W[i].reshape(80, 80, 9)).permute(0, 2, 1, 3).contiguous().reshape(4, 80, 80, 3, 3)
+            wq = dense.quad_tap_mix(W[i], "s2", transposed=True).reshape(4, 80, 80, 3, 3)
             add(i, [(wq[q], 0, 80, 0, 80) for q in range(4)])
         # conv1's data gradient is needed for xout_d and cout_d only (channels 0 and 4 of its input): quad form = a stride-1
         # convolution of G1 at ITS resolution with 4 parity x 2 output channels (dense.quad_maps 's2')
-        Wd = _tap_mix(s2, torch.stack((W[0][:, 0], W[0][:, 4]), 1).reshape(80, 2, 9)).permute(0, 2, 1, 3).reshape(8, 80, 3, 3)
+        Wd = dense.quad_tap_mix(torch.stack((W[0][:, 0], W[0][:, 4]), 1), "s2", transposed=True).reshape(8, 80, 3, 3)
         add(0, [(Wd, 0, 80, 0, 80)])
         prepped = dense.prep_conv3x3_weights_batch(reqs)
         wp = {k: prepped[a:b_] for k, (a, b_) in where.items()}

@@ -297,6 +297,15 @@ int adc_quad_head_dgrad(const void* x9, int x9_stride, const float* gq, const fl
                         int extra_stride, void* g9, void* g9_lo, int g9_stride, float* part, int N, int oc, int H1, int W1,
                         adc_stream_t stream);
 int adc_quad_unshuffle(const float* q, int q_stride, float* out, int N, int K, int H, int W, adc_stream_t stream);
+/* Quad (parity-block) forms of a 3x3 weight tensor w [A][B][9] (fp32), replacing the per-step broadcast product + reduction over the
+ * constant 0/1 tap maps: out [4][A][B][9] (or [4][B][A][9] when `transposed`), parity q = 2*py + px.
+ *   which 0 ('up', conv10 behind the 2x nearest up-sampling, confidence_depth_framework.py:504-506): low-resolution tap
+ *           (((py+u-1)>>1)+1, ((px+v-1)>>1)+1) accumulates the original tap (u, v);
+ *   which 1 ('s2', data gradient of a 3x3 / stride-2 / pad-1 convolution, :442-452, and ConvTranspose2d(3, 2, 1, 1),
+ *           model_zoo/s2d_u_resnet.py:45-61): low-resolution tap (a, b) holds the original tap (py+3-2a, px+3-2b) where it exists.
+ * adc_quad_tap_mix_adjoint: the transpose of the 'up' form, out[l][t] = sum_q in[q][l][slot(q, t)] (weight gradient of conv10). */
+int adc_quad_tap_mix(const float* w, float* out, int A, int B, int which, int transposed, adc_stream_t stream);
+int adc_quad_tap_mix_adjoint(const float* in, float* out, int L, adc_stream_t stream);
 
 /* ---- cbr3-c1 confidence head behind its 3x3 convolution (confidence_depth_framework.py:299-329: conv1 -> bn1 -> LeakyReLU(0.2) ->
  * conv2 1x1 + bias -> sigmoid).  conv1, its data gradient and its weight gradient run on the tensor-core kernels above; these

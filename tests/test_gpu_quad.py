@@ -91,3 +91,28 @@ def test_pack_input_is_cat_plus_layout():
     finally:
         dense.set_precision("bf16x3")
     assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
+
+
+@pytest.mark.parametrize("a,b", [(80, 80), (80, 2), (2, 32), (1, 32), (64, 129)])
+def test_quad_tap_mix_vs_tap_maps(a, b):
+    """adc_quad_tap_mix / adc_quad_tap_mix_adjoint against the broadcast product with the constant 0/1 maps they replace
+    (dense.quad_maps): 's2' copies single taps (bit-exact), 'up' sums up to four (fp32 association may differ)."""
+    from aerial_depth_completion_b200 import dense
+    g = torch.Generator(device="cuda").manual_seed(7 + a + b)
+    w = torch.randn(a, b, 3, 3, device="cuda", generator=g)
+    up, s2 = dense.quad_maps(w.device)
+    for which, maps in (("up", up), ("s2", s2)):
+        ref = (w.reshape(1, a, b, 1, 9) * maps.reshape(4, 1, 1, 9, 9)).sum(-1)            # [4, a, b, 9]
+        got = dense.quad_tap_mix(w, which)
+        got_t = dense.quad_tap_mix(w, which, transposed=True)
+        if which == "s2":
+            assert torch.equal(got, ref) and torch.equal(got_t, ref.permute(0, 2, 1, 3).contiguous())
+        else:
+            assert relmax(got, ref) < 1e-6 and relmax(got_t, ref.permute(0, 2, 1, 3).contiguous()) < 1e-6
+    # a strided slice (conv10's first 32 input channels) goes through the same entry point
+    w33 = torch.randn(a, b + 1, 3, 3, device="cuda", generator=g)
+    ref = (w33[:, :b].reshape(1, a, b, 1, 9) * up.reshape(4, 1, 1, 9, 9)).sum(-1)
+    assert relmax(dense.quad_tap_mix(w33[:, :b], "up"), ref) < 1e-6
+    gq = torch.randn(4, a * b, 9, device="cuda", generator=g)
+    ref = (gq.reshape(4, a * b, 9, 1) * up.reshape(4, 1, 9, 9)).sum((0, 2))
+    assert relmax(dense.quad_tap_mix_adjoint(gq), ref) < 1e-6
