@@ -282,6 +282,11 @@ static int dispatch_bwd_weight(int Ci, int K, const SrcP& g, const SrcP& s0, con
 static int run_upsample_bwd(const float2* g_full, const SrcP& s, float2* G, float* bpart, int N, int H, int W, int ximg,
                             cudaStream_t st) {
     const long long planes = (long long)N * s.ch, total = planes * s.H * s.W;
+    if (H == 2 * s.H && W == 2 * s.W && total < (1LL << 31) && (reinterpret_cast<uintptr_t>(g_full) & 15) == 0) {
+        { ProfScope _p(st, KIND_UP_BWD, g_cur_call, 8.0 * s.ch * N * ((double)H * W + 2.0 * s.H * s.W));
+        pair_upsample2_bwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(g_full, s.p, G, bpart, s.ch, s.H, s.W, (unsigned)total, ximg); }
+        return check_cuda(cudaGetLastError(), "pair_upsample2_bwd_kernel launch");
+    }
     { ProfScope _p(st, KIND_UP_BWD, g_cur_call, 8.0 * s.ch * N * ((double)H * W + 2.0 * s.H * s.W));
     pair_upsample_bwd_kernel<<<(int)ceil_div_ll(total, 256), 256, 0, st>>>(g_full, s.p, G, bpart, s.ch, H, W, s.H, s.W, s.mh, s.mw,
                                                                           planes, ximg); }

@@ -182,20 +182,22 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
         win[u][0] = win[u][1] = make_float2(0.f, 0.f);
     }
 
-    // step j reads X row (grp*RH + j) [tile row grp*RH + j - P] and G row grp*RH + j (zero once j >= RH)
+    // step j reads X row (grp*RH + j) [tile row grp*RH + j - P] and G row grp*RH + j; tap row u of step j pairs that X row with
+    // G row j - u, which exists for 0 <= j - u < RH.  The first and the last block of K steps are peeled so the (step, tap row)
+    // pairs without a G row cost nothing (the uniform loop multiplied zero rows there: 20 % of the FFMA2 at K = 5, 11 % at K = 3).
     constexpr int XO = T::XOFF;
     constexpr int NP = (2 + K - 1 + XO + 1) & ~1;
-#pragma unroll 1
-    for (int jt = 0; jt < C::STEPS / K; ++jt) {
+    constexpr int NB = C::STEPS / K;
+    static_assert(C::RH >= 2 * K - 1 && NB >= 2, "peeled first / last blocks must not overlap");
+    auto block = [&](auto mode_c, int jt) {            // mode 0: first block (j < K), 1: middle, 2: last (j >= RH - 1)
+        constexpr int MODE = decltype(mode_c)::value;
 #pragma unroll
         for (int jj = 0; jj < K; ++jj) {
             const int j = jt * K + jj;
-            if (j < C::RH) {
+            if (MODE != 2 || jj == 0) {                // the last block starts at j = RH - 1, the last G row
                 const float4 a = *reinterpret_cast<const float4*>(gptr + j * C::TW);
                 win[jj][0] = make_float2(a.x, a.y);
                 win[jj][1] = make_float2(a.z, a.w);
-            } else {
-                win[jj][0] = win[jj][1] = make_float2(0.f, 0.f);
             }
             float2 xr[NP];
 #pragma unroll
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
             }
 #pragma unroll
             for (int u = 0; u < K; ++u) {
+                if ((MODE == 0 && u > jj) || (MODE == 2 && u < jj)) continue;
                 const int slot = ((jj - u) % K + K) % K;   // G row of step j-u
 #pragma unroll
                 for (int v = 0; v < K; ++v) {
@@ -214,7 +217,11 @@ __global__ void __launch_bounds__(WgCfg<CI, K>::NT) nconv_bwd_weight_kernel(cons
                 }
             }
         }
-    }
+    };
+    block(std::integral_constant<int, 0>{}, 0);
+#pragma unroll 1
+    for (int jt = 1; jt < NB - 1; ++jt) block(std::integral_constant<int, 1>{}, jt);
+    block(std::integral_constant<int, 2>{}, NB - 1);
 
 #pragma unroll
     for (int u = 0; u < K; ++u)
@@ -326,7 +333,7 @@ struct WgReduceArgs {
     int accumulate;
 };
 
-constexpr int kRedChunks = 16;   // first-stage blocks per call
+constexpr int kRedChunks = 64;   // first-stage blocks per call (16 left the four full-resolution calls of the pyramid on 64 CTAs)
 
 // Stage 1: grid (ncalls, kRedChunks) x 1024 threads = 8 row slices x 128 entries.  Each thread sums its rows with four
 // independent accumulators so the loads overlap (a single serial loop was DRAM-latency bound: 116 us for 1280 rows).
