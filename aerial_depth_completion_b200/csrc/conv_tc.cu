@@ -288,7 +288,7 @@ struct ConvParamsV2 {
     int ktail;               // 16-channel K steps of the LAST 64-channel block that hold real channels (1..4): cin = 64*(kblocks-1) + 16*ktail
     int tri;                 // CTA pair, npad >= 80: three MMAs of N = npad per product (hi*hi, hi*lo, lo*hi) into ONE accumulator; each CTA
                              // holds both weight planes of HALF the output channels (see the kernel)
-    int ostage_blocks;       // bf16 bulk stores: 64-channel column blocks the staging buffer holds (all of them, or 1 = staged in turn)
+    int ostage_blocks;       // bf16 bulk stores: staging slots of one 64-channel column block each (2 = used in turn with one store group per block, 1 = staged and drained in turn)
     int pf;                  // L2 prefetch distance in tiles of this CTA (0 = off): the segments of tile + pf * grid are requested early
     int hstack;              // 1: the three horizontal taps of a tap row are ONE MMA of N = 3 * (accumulator width) (see the kernel)
 };
@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Epilogue warps: 4 (192 threads) or 8 (320 threads).  A warp may only read the TMEM lane quarter (warp % 4); with 8 warps the two
     // warps of a quarter take alternate 16-column chunks (short-K layers were bound by the four warps' TMEM loads + conversions).
+    // (12 warps -- three per quarter -- were measured for layers of five or more chunks: no change, 371 vs 363 us for conv1's GEMM.)
     const int nhalf = blockDim.x > 192 ? 2 : 1;
     const int epi_threads = 128 * nhalf;
     // Pair form, wide layers (tri): the [W_hi | W_lo] operand makes A_lo x [W_hi | W_lo] compute lo*lo too -- free while an instruction's
@@ -604,6 +605,7 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         int it = 0;
         uint32_t cc = 0;                                   // hstack: exchange-buffer parity, one per accumulator chunk
+        uint32_t gblk = 0;                                 // column blocks staged so far by this CTA (staging slot = gblk & 1)
         const uint32_t tmem_empty_remote = PAIR ? mapa_u32(smem_u32(&bars[18]), 0) : 0u;
         // accumulator columns of horizontal tap v, W_hi / W_lo products: single CTA [v][hi | lo], pair [hi: v0 v1 v2 | lo: v0 v1 v2]
         const uint32_t vstr = (uint32_t)(PAIR ? p.npad : acc_cols), hstr = (uint32_t)(PAIR && hst ? 3 * p.npad : p.npad);
@@ -611,7 +613,9 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
             const int a = it & 1;
             const long long m = (long long)tile * tile_m + quarter * 32 + lane;
             const bool inrange = m < p.F && quarter * 32 + lane < tile_m;
-            const int wp = (int)(m % p.Wp), hp = (int)((m / p.Wp) % p.Hp);
+            // (host: F + 256 < 2^31 -- the 64-bit divisions of the first version were ~6 % of the epilogue's issue slots on thin-K layers)
+            const unsigned mu = (unsigned)m, wq = mu / (unsigned)p.Wp;
+            const int wp = (int)(mu - wq * (unsigned)p.Wp), hp = (int)(wq % (unsigned)p.Hp);
             const bool border = wp == 0 || wp == p.Wp - 1 || hp == 0 || hp == p.Hp - 1;
             mbar_wait(&bars[16 + a], (it >> 1) & 1);
             tc_fence_after();
@@ -619,11 +623,21 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
             // bf16 outputs are staged and stored one 64-channel column block at a time (an 80-channel slice = a 64- and a 16-channel box;
             // per-thread 16-byte stores at the pixel stride were measured at 3x the cost of the whole rest of a K = 48 layer)
             const int nblk = (p.tma_store && c_end > 64) ? (c_end + 63) >> 6 : 1;
-            const bool multi = p.ostage_blocks > 1;          // every column block has its own staging tile: one store phase per tile
+            // bf16 bulk stores with two staging slots (ostage_blocks == 2): column blocks go through the slots in turn, every block is
+            // its own bulk-store group, and a slot is only waited for when it comes round again -- the store of block g drains while
+            // block g + 1 is staged (the single-phase form stalled all epilogue warps behind `wait_group.read 0` once per tile: 20 % of
+            // the samples of conv1's K = 48 GEMM, whose epilogue is its critical path).  One slot: staged and drained in turn.
+            const bool ring = p.tma_store == 1 && p.ostage_blocks >= 2;
             for (int blk = 0; blk < nblk; ++blk) {
             const int cb0 = p.tma_store ? blk * 64 : 0, cb1 = p.tma_store ? (c_end < cb0 + 64 ? c_end : cb0 + 64) : c_end;
-            uint8_t* ost = ostage + (multi ? blk * oblk_bytes : 0);
-            if (p.tma_store && ((blk == 0 && it > 0) || (blk > 0 && !multi))) {
+            uint8_t* ost = ostage + (ring ? (gblk & 1u) * oblk_bytes : 0);
+            if (ring) {
+                if (gblk >= 2u) {
+                    // the store that used this slot two blocks ago must have finished READING it (the latest group may still be in flight)
+                    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
+                }
+            } else if (p.tma_store && (it > 0 || blk > 0)) {
                 // the previous bulk store must have finished READING the staging tile before it is overwritten
                 if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
@@ -750,8 +764,8 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                     else mbar_arrive(&bars[18 + a]);
                 }
             }
-            if (p.tma_store && (!multi || blk == nblk - 1)) {
-                // all four epilogue warps have staged their rows -> one thread issues the coalesced bulk store(s)
+            if (p.tma_store) {
+                // all epilogue warps have staged their rows of this block -> one thread issues the coalesced bulk store(s)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
                 if (warp == 2 && lane == 0) {
@@ -762,15 +776,13 @@ __global__ void __launch_bounds__(320) conv3x3_s1_tc_v2_kernel(const __grid_cons
                             else tma_store_2d(&map_o, ostage + b * 16384, cb0 + b * 32, (int)m0);
                         }
                     } else {
-                        for (int b = multi ? 0 : blk; b <= blk; ++b) {
-                            const uint8_t* src = ostage + (multi ? b * oblk_bytes : 0);
-                            tma_store_2d(&map_o, src, b * 64, (int)m0);
-                            if (p.out_lo) tma_store_2d(&map_ol, src + 16384, b * 64, (int)m0);
-                        }
+                        tma_store_2d(&map_o, ost, blk * 64, (int)m0);
+                        if (p.out_lo) tma_store_2d(&map_ol, ost + 16384, blk * 64, (int)m0);
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
+            ++gblk;
             }
         }
         if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1338,6 +1350,10 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     }
     { const char* e = getenv("ADC_V2_PF"); p.pf = e ? atoi(e) : 0; }      // measured: no gain (the loads are not DRAM-latency bound), kept as a switch
     const int tile_m = p.hstack ? 126 : 128;
+    if (p.F + 256 >= (1LL << 31)) {
+        adc::set_error("adc_conv3x3_s1_tc_v2: more than 2^31 flat pixels");
+        return ADC_E_UNSUPP;
+    }
     p.ntiles = (int)((p.F + tile_m - 1) / tile_m);
     p.out_zero_to = out_zero_to;
     p.taps1 = taps1;
@@ -1451,7 +1467,7 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
     const int wmult = pair ? 1 : mult;
     const int w_all = (taps1 ? 1 : (p.hstack ? 9 : __builtin_popcount((unsigned)p.tap_mask))) * kblocks * npad * 128;   // live taps only
     // Shared-memory plan: weights resident if they fit next to >= 2 activation stages, otherwise streamed with every step.  A bf16
-    // result wider than 64 channels stages all its column blocks at once if the pipeline keeps >= 3 stages, else one block in turn.
+    // result gets two staging slots of one 64-channel column block each if the pipeline keeps >= 3 stages, else one slot.
     const int oblk_bytes = 16384 * (p.out_lo ? 2 : 1), oblocks = (width + 63) / 64;
     const int kTail = 256 + 3072;          // mbarriers + TMEM slot, hstack exchange rows
     int smem = 0, ostage_bytes = 0;
@@ -1474,7 +1490,11 @@ static int conv_v2(const void* x, const void* x_lo, int x_stride, int x_off, con
             smem = p.nstages * st + ostage_bytes + 1024 + kTail;
         }
     };
-    plan(p.tma_store == 1 ? oblocks : 1);
+    {
+        const char* e = getenv("ADC_V2_NO_RING");              // (experiment / test: one staging slot, staged and drained in turn)
+        const bool ring = p.tma_store == 1 && oblocks <= 2 && !(e && e[0] == '1');
+        plan(ring ? 2 : 1);                                    // two staging slots (see the epilogue) if the pipeline keeps >= 3 stages
+    }
     if (p.ostage_blocks > 1 && p.nstages < 3) plan(1);
     {
         const char* e = getenv("ADC_V2_MAXST");

@@ -444,6 +444,17 @@ static int sm_count() {
     }
     return sms;
 }
+// ADC_WGRAD_SMEM_RESERVE=KB: shared memory the weight-gradient kernels leave free on every SM so that CTAs of the HBM-bound
+// gradient-assembly pass (16 KB static each) can be resident beside them (experiment; default 0).
+static int wgrad_smem_reserve() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ADC_WGRAD_SMEM_RESERVE");
+        const int kb = e ? atoi(e) : 0;
+        v = (kb < 0 ? 0 : (kb > 96 ? 96 : kb)) * 1024;
+    }
+    return v;
+}
 static int wgrad_groups() { return sm_count() / 3 > 0 ? sm_count() / 3 : 1; }        // flat kernel: CTA = (group, u)
 static int wgrad_box_groups() { return sm_count() / 9 > 0 ? sm_count() / 9 : 1; }    // box kernel: CTA = (group, tap)
 
@@ -520,7 +531,7 @@ static int wgrad_flat(const void* gy, const void* gy_lo, int gy_stride, int gy_o
         p.prow = 2 * p.mrows;
         p.groups = sm_count() / 6;          // pairs of CTAs: (group, u)
     }
-    const int budget = kSmemCap - 1024;
+    const int budget = kSmemCap - 1024 - wgrad_smem_reserve();
     for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
         p.bseg = ((p.kp + 2) * 128 + 1023) / 1024 * 1024;
         const int stage = pair ? p.mb * p.kp * 128 + 2 * p.bseg : (p.mb * p.kp * 128 + p.nb * p.bseg) * (p.split ? 2 : 1);
@@ -650,7 +661,7 @@ static int wgrad_box(const void* gy, const void* gy_lo, int gy_stride, int gy_of
         p.rowpack = (p.split && p.mb == 1 && !(e && e[0] == '1')) ? 1 : 0;
         p.prow = p.rowpack ? 64 + p.mrows : p.mrows;
     }
-    const int budget = kSmemCap - 1024;
+    const int budget = kSmemCap - 1024 - wgrad_smem_reserve();
     for (p.kp = 128; p.kp >= 64; p.kp /= 2) {
         const int stage = (p.mb + p.nb) * p.kp * 128 * (p.split ? 2 : 1);
         p.nstages = budget / stage;

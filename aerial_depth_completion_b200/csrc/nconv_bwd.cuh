@@ -33,9 +33,24 @@ __global__ void __launch_bounds__(128, (CI > 2 ? 3 : 4)) nconv_bwd_data_kernel(c
     const int n = blockIdx.z, h0 = blockIdx.y * C::TH, w0 = blockIdx.x * C::TW;
     const float* wc = &c_wimg[0][0][0][0] + (size_t)wimg * kWStride;
 
-    const bool pending = stage_sources<K, 128>(maps, g, g, false, n, h0, w0, H, W, planes, bar, tid);
-    __syncthreads();
-    if (pending) mbar_wait(bar, 0);
+    // TMA source: one box and one mbarrier per G plane, so the FFMA2 loop over plane 0 starts while plane 1 is in flight (as in the
+    // forward kernel); other sources: staged together.
+    const bool per_plane = g.tma != 0;
+    if (per_plane) {
+        if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+        __syncthreads();
+        if (tid == 0) {
+            const int x0 = 2 * (w0 - C::P - C::XOFF), y0 = h0 - C::P;
+            for (int c = 0; c < 2; ++c) {
+                mbar_expect_tx(bar + c, (uint32_t)(C::SH * C::SWP * 8));
+                tma_load_plane(planes + c * C::PLANE, &maps.m0, bar + c, x0, y0, c, n);
+            }
+        }
+    } else {
+        const bool pending = stage_sources<K, 128>(maps, g, g, false, n, h0, w0, H, W, planes, bar, tid);
+        __syncthreads();
+        if (pending) mbar_wait(bar, 0);
+    }
 
     const int tx = tid & 31, ty = tid >> 5;
     const int oh = h0 + ty * 8, ow = w0 + tx * 2;
@@ -45,10 +60,37 @@ __global__ void __launch_bounds__(128, (CI > 2 ? 3 : 4)) nconv_bwd_data_kernel(c
 
     if (active) {
         constexpr int NQ = (CI + 1) / 2, NO = CI == 1 ? 1 : 2;
+        // The epilogue multiplies the accumulators with the forward {x, c} of the same pixels, read straight from global memory
+        // AFTER the FFMA2 loop (no registers to hold them across it at the 128-register cap): request the lines into L2 now so
+        // those loads see L2 latency instead of HBM latency.
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) {
+            const bool first = ci < s0.ch;
+            const SrcP& s = first ? s0 : s1;
+            if (s.up || (W & 1)) continue;
+            const float2* xp = s.p + (long long)n * s.bs + (long long)(first ? ci : ci - s0.ch) * s.H * s.W + ow;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int h = oh + r < H ? oh + r : H - 1;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + (long long)h * W));
+            }
+        }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             float2 acc[NO][8][2];
-            conv_patch<2, NO, K>(planes, wc + q * (2 * 2 * K * K), tx, ty, acc);
+            if (per_plane) {
+#pragma unroll
+                for (int no = 0; no < NO; ++no)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) acc[no][r][0] = acc[no][r][1] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                for (int ni = 0; ni < 2; ++ni) {
+                    if (q == 0) mbar_wait(bar + ni, 0);
+                    conv_patch_plane<2, NO, K>(planes + ni * C::PLANE, wc + q * (2 * 2 * K * K), ni, tx, ty, acc);
+                }
+            } else {
+                conv_patch<2, NO, K>(planes, wc + q * (2 * 2 * K * K), tx, ty, acc);
+            }
 #pragma unroll
             for (int j = 0; j < NO; ++j) {
                 const int ci = 2 * q + j;

@@ -25,6 +25,9 @@ from . import dense
 
 _RELU, _LEAKY = 1, 2
 _SIDE_STREAM = os.environ.get("ADC_TC_SIDE_STREAM", "1") != "0"
+# weight gradient of a layer enqueued AFTER its data gradient (the side stream then starts it when the data gradient has finished, beside
+# the HBM-bound gradient-assembly pass of the next layer, instead of racing the data gradient for the same SMs)
+_WGRAD_AFTER = os.environ.get("ADC_WGRAD_AFTER", "1") != "0"
 
 
 def _half(v):
@@ -264,17 +267,23 @@ class GEDDenseTC(torch.autograd.Function):
                 G, gB[i] = asm(b[gname], co, a=b[src], act=xk, slope=0.2, colsum=True)
             else:
                 G, gB[i] = b[gname], gb9
-            gW[i] = wg(G, catk, cin, co, cin_pad=cin)
+            if not _WGRAD_AFTER:
+                gW[i] = wg(G, catk, cin, co, cin_pad=cin)
             _dgrad_s1(G, W[i], b[gcat], 0, cin, prepped=wp[i], cy=dec_cy[i])
+            if _WGRAD_AFTER:
+                gW[i] = wg(G, catk, cin, co, cin_pad=cin)
         # encoder layers 5..1 (stride 2, ReLU): G5 from the up-sampling children only, G4..G1 = relu' * (dgrad + skip gradient)
         G, gb = asm(b["G5"], 80, a=b["gcat6"], act=P.x5, slope=0.0, colsum=True)
         enc = ((4, P.cat6, 80, 4, "gx4", "G4", "gcat6", 80), (3, P.cat7, 64, 3, "gx3", "G3", "gcat7", 64),
                (2, P.cat8, 64, 2, "gx2", "G2", "gcat8", 64), (1, P.cat9, 32, 1, "gx1", "G1", "gcat9", 32))
         for i, xin, xoff, lvl, gxn, gn, gcat, goff in enc:
             gB[i] = gb
-            gW[i] = wgb(G, xin, 80, 80, 2, x_off=xoff, cin_pad=80)
+            if not _WGRAD_AFTER:
+                gW[i] = wgb(G, xin, 80, 80, 2, x_off=xoff, cin_pad=80)
             for q in range(4):
                 dense.conv3x3_tc(G, 80, wp[i][q], None, 80, 1, 0, out=b[gxn], out_off=80 * q, tap_mask=masks[q])
+            if _WGRAD_AFTER:
+                gW[i] = wgb(G, xin, 80, 80, 2, x_off=xoff, cin_pad=80)
             G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True, a_quad=True)
         gB[0] = gb
         gw1 = off_path(dense.conv1x1_wgrad_tc, G, P.x45, 45, 80, cin_pad=48)       # [80, 45], channel (3u+v)*5 + c

@@ -194,3 +194,36 @@ def test_row_segment_kernel_stacked_horizontal_taps(cfg):
         os.environ.pop("ADC_V2_NO_HSTACK", None)
         os.environ.pop("ADC_V2_NO_PAIR", None)
         dense.set_precision("bf16x3")
+
+
+@gpu
+@pytest.mark.parametrize("cfg", [(2, 48, 80, 57, 76, 32, 128), (1, 32, 112, 64, 80, 0, 128), (3, 64, 64, 29, 39, 0, 64), (2, 80, 32, 33, 47, 64, 128),
+                                 (1, 160, 128, 30, 40, 0, 128)])
+def test_row_segment_kernel_store_staging_forms(cfg):
+    """bf16 (hi, lo) outputs leave the row-segment kernel through shared-memory staging slots and TMA bulk stores: two slots used in
+    turn with one store group per 64-channel column block (default) against one slot staged and drained in turn (ADC_V2_NO_RING=1).
+    Bit-identical tensors, many tiles per CTA (the slot ring wraps), one and two column blocks, channel-slice outputs."""
+    import os
+    from aerial_depth_completion_b200 import dense
+    n, ci, co, h, w, off, cs = cfg
+    g = torch.Generator().manual_seed(ci + 3 * co + h)
+    x = torch.randn(n, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g) * (2.0 / (ci * 9)) ** 0.5
+    b = torch.randn(co, generator=g) * 0.1
+    try:
+        xa = dense.to_nhwc_bf16(x.cuda(), pad=True)
+        wp = dense.prep_conv3x3_weights(wt.cuda(), cin_pad=ci)
+        outs = []
+        for flag in ("0", "1"):
+            os.environ["ADC_V2_NO_RING"] = flag
+            out = dense.new_act(n, h, w, cs, "cuda", pad=True, zero=True)
+            dense.conv3x3_tc(xa, ci, wp, b.cuda(), co, 1, 1, out=out, out_off=off)
+            outs.append((out.hi.clone(), out.lo.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        got = (outs[0][0].float() + outs[0][1].float())[:, 1:-1, 1:-1, off:off + co].permute(0, 3, 1, 2).cpu()
+        ref = _ref(x, wt, b, 1, 1, rounded=False)
+        assert float((got - ref).abs().max() / ref.abs().max()) < 5e-5
+        if off > 0:
+            assert float(outs[0][0][..., :off].abs().max()) == 0.0          # the neighbouring slice is untouched
+    finally:
+        os.environ.pop("ADC_V2_NO_RING", None)

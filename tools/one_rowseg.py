@@ -1,5 +1,5 @@
 """One GED / GMS shaped layer on the row-segment kernel, three launches (for ncu: -k regex:conv3x3_s1 -s 1 -c 1).
-LAYER = dgrad9 | dgrad9w | fwd9 | gms64 | quad4"""
+LAYER = dgrad9 | dgrad9w | fwd9 | gms64 | quad4 | conv1"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -27,6 +27,17 @@ elif layer == "fwd9":
     x, cin, cout, out, off, zt, mask = act((114, 152), 128), 112, 32, act((114, 152), 64), 0, 64, 0
 else:
     x, cin, cout, out, off, zt, mask = act((57, 76), 128), 80, 80, act((57, 76), 320), 240, 0, 0b110110000
+if layer == "conv1":          # GED conv1 as a 1x1 GEMM over the im2col tensor: K = 48, 80 output channels + bias + ReLU into cat9[32:112]
+    x45, cat9 = act((114, 152), 64), act((114, 152), 128)
+    w1 = torch.zeros(80, 48, 3, 3, device="cuda")
+    w1[:, :45, 1, 1] = torch.randn(80, 45, device="cuda") * 0.05
+    wp1 = dense.prep_conv3x3_weights(w1, cin_pad=48)
+    bias = torch.randn(80, device="cuda")
+    for _ in range(3):
+        dense.conv1x1_tc(x45, 48, wp1, bias, 80, 1, out=cat9, out_off=32)
+    torch.cuda.synchronize()
+    print("ok")
+    sys.exit(0)
 wp = dense.prep_conv3x3_weights(torch.randn(cout, cin, 3, 3, device="cuda") * 0.05, cin_pad=cin)
 for _ in range(3):
     dense.conv3x3_tc(x, cin, wp, None, cout, 1, 0, out=out, out_off=off, out_zero_to=zt, tap_mask=mask)
