@@ -258,10 +258,13 @@ def sum_rows(part):
     return out
 
 
-def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None, act_off=0, slope=0.0, colsum=False, a_quad=False):
+def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None, act_off=0, slope=0.0, colsum=False, a_quad=False,
+                  reduce=None):
     """out[:, out_off:out_off+c] = d(act) * (sum over the up-sampling children of ``a`` + ``b``); see adc_nhwc_grad_assemble.
     a_quad: ``a`` is the quad form of a stride-2 data gradient (4 parity blocks of c channels at half resolution).
-    colsum=True also returns the per-channel sum of the result over all pixels (fp32 [c]: a bias gradient) from the same pass."""
+    colsum=True also returns the per-channel sum of the result over all pixels (fp32 [c]: a bias gradient) from the same pass;
+    ``reduce``: callable that sums the per-CTA partial rows (default ``sum_rows`` on the current stream; a caller may move this
+    second stage off its critical path)."""
     from ._lib import lib, check
     z = lambda t: (t.hi.data_ptr(), _ptr(t.lo), t.cs) if t is not None else (None, None, 0)
     ah, al, ast = z(a)
@@ -271,7 +274,7 @@ def grad_assemble(out, c, out_off=0, a=None, a_off=0, b=None, b_off=0, act=None,
                                      act.hi.data_ptr() if act is not None else None, act.cs if act is not None else 0, act_off,
                                      float(slope), out.hi.data_ptr(), _ptr(out.lo), out.cs, out_off, out.n, c, out.h, out.w, _ptr(part),
                                      int(a_quad), _stream()), "adc_nhwc_grad_assemble")
-    return (out, sum_rows(part)) if colsum else out
+    return (out, (reduce or sum_rows)(part)) if colsum else out
 
 
 def colsum(g, c, off=0):

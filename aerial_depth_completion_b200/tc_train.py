@@ -28,6 +28,7 @@ _SIDE_STREAM = os.environ.get("ADC_TC_SIDE_STREAM", "1") != "0"
 # weight gradient of a layer enqueued AFTER its data gradient (the side stream then starts it when the data gradient has finished, beside
 # the HBM-bound gradient-assembly pass of the next layer, instead of racing the data gradient for the same SMs)
 _WGRAD_AFTER = os.environ.get("ADC_WGRAD_AFTER", "1") != "0"
+_SUM_OFFPATH = os.environ.get("ADC_SUM_OFFPATH", "1") != "0"      # second stage of the bias-gradient reductions on the second stream
 
 
 def _half(v):
@@ -227,6 +228,16 @@ class GEDDenseTC(torch.autograd.Function):
                 out = fn(*a, **kw)
             out.record_stream(main)
             return out
+        def off_sum(part):
+            """Second stage of a bias-gradient reduction on the second stream (nothing on the data-gradient chain waits for it)."""
+            if side is main or not _SUM_OFFPATH:
+                return dense.sum_rows(part)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = dense.sum_rows(part)
+            part.record_stream(side)
+            out.record_stream(main)
+            return out
         wg = lambda *a, **kw: off_path(dense.conv3x3_wgrad_tc, *a, **kw)
         wgb = lambda *a, **kw: off_path(dense.conv3x3_wgrad_box_tc, *a, **kw)
         # all data-gradient weights of the step (transposed / flipped, per output-channel chunk) in ONE launch
@@ -264,7 +275,7 @@ class GEDDenseTC(torch.autograd.Function):
                (6, "G7", "gcat8", P.x7, 64, P.cat7, 144, "gcat7"), (5, "G6", "gcat7", P.x6, 64, P.cat6, 160, "gcat6"))
         for i, gname, src, xk, co, catk, cin, gcat in dec:
             if src is not None:
-                G, gB[i] = asm(b[gname], co, a=b[src], act=xk, slope=0.2, colsum=True)
+                G, gB[i] = asm(b[gname], co, a=b[src], act=xk, slope=0.2, colsum=True, reduce=off_sum)
             else:
                 G, gB[i] = b[gname], gb9
             if not _WGRAD_AFTER:
@@ -273,7 +284,7 @@ class GEDDenseTC(torch.autograd.Function):
             if _WGRAD_AFTER:
                 gW[i] = wg(G, catk, cin, co, cin_pad=cin)
         # encoder layers 5..1 (stride 2, ReLU): G5 from the up-sampling children only, G4..G1 = relu' * (dgrad + skip gradient)
-        G, gb = asm(b["G5"], 80, a=b["gcat6"], act=P.x5, slope=0.0, colsum=True)
+        G, gb = asm(b["G5"], 80, a=b["gcat6"], act=P.x5, slope=0.0, colsum=True, reduce=off_sum)
         enc = ((4, P.cat6, 80, 4, "gx4", "G4", "gcat6", 80), (3, P.cat7, 64, 3, "gx3", "G3", "gcat7", 64),
                (2, P.cat8, 64, 2, "gx2", "G2", "gcat8", 64), (1, P.cat9, 32, 1, "gx1", "G1", "gcat9", 32))
         for i, xin, xoff, lvl, gxn, gn, gcat, goff in enc:
@@ -284,7 +295,7 @@ class GEDDenseTC(torch.autograd.Function):
                 dense.conv3x3_tc(G, 80, wp[i][q], None, 80, 1, 0, out=b[gxn], out_off=80 * q, tap_mask=masks[q])
             if _WGRAD_AFTER:
                 gW[i] = wgb(G, xin, 80, 80, 2, x_off=xoff, cin_pad=80)
-            G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True, a_quad=True)
+            G, gb = asm(b[gn], 80, a=b[gxn], b=b[gcat], b_off=goff, act=xin, act_off=xoff, slope=0.0, colsum=True, a_quad=True, reduce=off_sum)
         gB[0] = gb
         gw1 = off_path(dense.conv1x1_wgrad_tc, G, P.x45, 45, 80, cin_pad=48)       # [80, 45], channel (3u+v)*5 + c
         dense.conv3x3_tc(G, 80, wp[0][0], None, 8, 1, 0, out=b["qin0"], tap_mask=mask_all)
