@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(256) nhwc_upsample_kernel(Slice src, SliceW ds
 // optional.  Fixed summation order (deterministic).  A thread keeps ONE 8-channel group for its whole life (thread = (pixel
 // slot, group)), so the per-channel sum of the output -- the bias gradient of the layer that produced `act` -- falls out of the
 // same pass: part[block][C] partial rows, summed by the caller in index order.
-__global__ void __launch_bounds__(256) nhwc_grad_assemble_kernel(Slice A, int hasA, Slice B, int hasB, Slice act, int hasAct, float slope,
+// Three resident CTAs per SM (80 registers, 16 bytes of spills): measured on one box against the 116-register / two-CTA build,
+// 551 vs 589 us for G1 at B = 128 (glue per step 1 390 -> 1 310 us); four CTAs (64 registers, 114 bytes of spills): 688 us.
+__global__ void __launch_bounds__(256, 3) nhwc_grad_assemble_kernel(Slice A, int hasA, Slice B, int hasB, Slice act, int hasAct, float slope,
                                                                  SliceW out, int N, int C8, int H, int W, int Hd, int Wd, Near mh, Near mw,
                                                                  float* __restrict__ part, int a_quad) {
     __shared__ float red[256][8];
@@ -373,7 +375,7 @@ static int grid_for(long long total) {
     return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
-constexpr int kAssembleCtas = 148 * 8;
+constexpr int kAssembleCtas = 148 * 9;      // three resident CTAs per SM (80 registers), three waves
 
 static bool bad_slice(const void* hi, int stride, int off, int C) { return !hi || stride % 8 != 0 || off % 8 != 0 || C % 8 != 0 || off + C > stride; }
 
@@ -431,7 +433,7 @@ int adc_nhwc_grad_assemble(const void* a, const void* a_lo, int a_stride, int a_
     if (!a) { Hd = H; Wd = W; }
     const long long total = (long long)N * H * W * (C / 8);
     adc::Prof prof((cudaStream_t)stream, adc::KIND_TC_GLUE, (double)total * 16.0 * (out_lo ? 2 : 1) * (1 + (a ? 1 : 0) + (b ? 1 : 0)));
-    // Small levels: one wave of CTAs instead of 1184 (at 116 registers two CTAs share an SM, so the fixed grid ran 4 latency-bound waves
+    // Small levels: one wave of CTAs instead of the full grid (at 116 registers two CTAs shared an SM, so the fixed grid of 1184 ran 4 latency-bound waves
     // of ~8 us each whatever the tensor size: 33-43 us for the 29x38 and smaller levels at B = 32).  The partial rows of the CTAs that are
     // not launched are zeroed (the caller sums all adc_nhwc_grad_assemble_parts() rows).
     const int groups_per_cta = 256 / (C / 8);
