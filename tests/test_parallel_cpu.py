@@ -108,3 +108,29 @@ def test_product_losses_and_metrics_refuse_host_tensors():
         mc.MaskedMSELoss()(None, t * 1.1, t)
     with pytest.raises(RuntimeError):
         Result().evaluate(t * 1.1, t)
+
+
+def test_single_process_gradient_adoption_equals_accumulation(monkeypatch):
+    """World 1: the trainer lets autograd ADOPT the incoming gradient tensors (.grad = None before backward) and moves them into the
+    flat bucket with one multi-tensor copy, instead of one accumulate launch per parameter into zeroed views (ADC_ADOPT_GRADS=0).
+    Same parameters after three steps, the flat views are back in place for the optimizer, and a parameter no gradient reaches
+    (conf_model) ends every step with a zero gradient like after zero_grad."""
+    from aerial_depth_completion_b200 import parallel
+    x, t = _data()
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ADC_ADOPT_GRADS", flag)
+        torch.manual_seed(0)
+        model = _tiny_model()
+        params = list(model.parameters())
+        opt = torch.optim.SGD(params, lr=0.1)
+        tr = parallel.DataParallelTrainer(model, _MaskedMSE(), opt, params, world_size=1)
+        assert tr._adopt == (flag == "1")
+        losses = [float(tr.step(x, t)) for _ in range(3)]
+        for p, v in zip(tr.params, tr._views):
+            assert p.grad is v and v.data_ptr() >= tr.flat.data_ptr()
+        assert float(model.conf_model.weight.grad.abs().max()) == 0.0
+        res[flag] = ([p.detach().clone() for p in params], losses, tr.flat.clone())
+    for a, b in zip(res["0"][0], res["1"][0]):
+        assert torch.equal(a, b)
+    assert res["0"][1] == res["1"][1] and torch.equal(res["0"][2], res["1"][2])
