@@ -60,7 +60,7 @@ def _load_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the NConv kernels from the committed `ncu --set full` capture
     (profiles/r2_nconv_traffic.json at the default batch, written by tools/ncu_traffic.py from the .ncu-rep): kernel name as in the roofline
     table.  Only reported when the capture's batch size is this run's (the source string names it)."""
-    for name in ("r2_nconv_traffic.json", "r1_nconv_traffic.json"):
+    for name in ("r2c_nconv_traffic.json", "r2_nconv_traffic.json", "r1_nconv_traffic.json"):
         try:
             return json.load(open(os.path.join(ROOT, "profiles", name)))
         except Exception:
