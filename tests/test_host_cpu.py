@@ -143,3 +143,68 @@ def test_checkpoint_wire_format_round_trip(tmp_path, args):
     for k, v in part.dc_model.state_dict().items():
         if v.shape == mr.dc_model.state_dict()[k].shape:
             assert torch.equal(v, mr.dc_model.state_dict()[k]), k
+
+
+def test_quad_tap_maps_are_the_identities_the_kernels_rely_on():
+    """dense.quad_maps (host constants behind adc_quad_tap_mix, the tap masks and five kernel uses) against the
+    convolutions they stand for, in fp64 on the CPU:
+      'up': conv3x3(nearest_up2(x), w)[2i+py, 2j+px] == conv3x3(x, sum of the taps of w that land on the same low-resolution pixel)[i, j]
+            (conv10 behind the 2x up-sampling, confidence_depth_framework.py:504-506);
+      's2': the input gradient of a 3x3 / stride-2 / pad-1 convolution at (2i+py, 2j+px) == a stride-1 3x3 convolution of the
+            output gradient with the taps that reach that parity (conv1..conv5, :442-452; ConvTranspose2d(3, 2, 1, 1) of
+            model_zoo/s2d_u_resnet.py:45-61 is the same map with the forward weights)."""
+    import torch.nn.functional as F
+    from aerial_depth_completion_b200 import dense
+    up, s2 = dense.quad_maps("cpu")
+    up, s2 = up.double(), s2.double()
+    g = torch.Generator().manual_seed(5)
+    ci, co, h, w = 3, 4, 6, 7
+    x = torch.randn(2, ci, h, w, generator=g, dtype=torch.float64)
+    wt = torch.randn(co, ci, 3, 3, generator=g, dtype=torch.float64)
+    # 'up'
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), wt, padding=1)                     # [2, co, 2h, 2w]
+    wq = (wt.reshape(1, co, ci, 1, 9) * up.reshape(4, 1, 1, 9, 9)).sum(-1).reshape(4, co, ci, 3, 3)
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        got = F.conv2d(x, wq[q], padding=1)
+        assert torch.allclose(got, ref[:, :, py::2, px::2], atol=1e-12)
+    # 's2' (even input size: every parity class has h x w pixels)
+    xin = torch.randn(2, ci, 2 * h, 2 * w, generator=g, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(xin, wt, stride=2, padding=1)                                                          # [2, co, h, w]
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (gx,) = torch.autograd.grad(y, xin, gy)
+    wd = (wt.reshape(1, co, ci, 1, 9) * s2.reshape(4, 1, 1, 9, 9)).sum(-1).permute(0, 2, 1, 3).reshape(4, ci, co, 3, 3)
+    masks, mask_all = dense.quad_s2_tap_masks()
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        got = F.conv2d(gy, wd[q], padding=1)
+        assert torch.allclose(got, gx[:, :, py::2, px::2], atol=1e-12)
+        live = sum(1 << t for t in range(9) if float(wd[q].reshape(ci, co, 9)[..., t].abs().max()) > 0)
+        assert live == masks[q]                       # the tap mask of a parity block names exactly its non-zero taps
+    assert [bin(m).count("1") for m in masks] == [1, 2, 2, 4] and mask_all == 0b111111111 & (masks[0] | masks[1] | masks[2] | masks[3])
+    # ConvTranspose2d(3, stride 2, padding 1, output_padding 1) with weight [in][out] = the same map
+    wio = torch.randn(co, ci, 3, 3, generator=g, dtype=torch.float64)                                   # [in = co][out = ci]
+    yt = F.conv_transpose2d(gy, wio, stride=2, padding=1, output_padding=1)
+    wtq = (wio.reshape(1, co, ci, 1, 9) * s2.reshape(4, 1, 1, 9, 9)).sum(-1).permute(0, 2, 1, 3).reshape(4, ci, co, 3, 3)
+    for q in range(4):
+        assert torch.allclose(F.conv2d(gy, wtq[q], padding=1), yt[:, :, (q >> 1)::2, (q & 1)::2], atol=1e-12)
+
+
+def test_quad_tap_mix_index_formulas_equal_the_tap_maps():
+    """The closed forms adc_quad_tap_mix computes on the device (csrc/tc_glue.cu: quad_up_slot and the 's2' tap (py+3-2a, px+3-2b)),
+    restated here, against the 0/1 tensors of dense.quad_maps (the GPU test compares the kernel's OUTPUT with the same tensors)."""
+    from aerial_depth_completion_b200 import dense
+    up, s2 = dense.quad_maps("cpu")
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        for t in range(9):
+            u, v = divmod(t, 3)
+            slot = (((py + u - 1) >> 1) + 1) * 3 + ((px + v - 1) >> 1) + 1
+            assert [int(up[q, s, t]) for s in range(9)] == [int(s == slot) for s in range(9)]
+        for s in range(9):
+            a, b = divmod(s, 3)
+            u, v = py + 3 - 2 * a, px + 3 - 2 * b
+            want = [0] * 9
+            if 0 <= u < 3 and 0 <= v < 3:
+                want[u * 3 + v] = 1
+            assert [int(s2[q, s, t]) for t in range(9)] == want
